@@ -1,0 +1,509 @@
+"""NumPy / torch-CPU / cv2 restatement of the post-model crown pipeline.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Each function cites
+the reference file:line it follows (paths relative to ``/root/reference``).
+Where the arithmetic lives in an absent third-party package the published
+algorithm is restated and the function says "parity unpinned".
+
+Pinned here against the reference's own code through ``oracle.refshim``:
+``nms_bbox``, ``crown_stats_combined``, ``crown_stats_height``,
+``crown_stats_ndvi``, ``containment``, ``ndvi_from_rgbi``, ``centroids``,
+``process_features`` / ``process_geojson`` (tests/test_oracle_vs_reference.py,
+tests/golden/*.npz).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import geom
+
+# ============================================================================
+# P2  paste + threshold  (detectron2, external; entered at prediction.py:183)
+# ============================================================================
+
+
+def scale_clip_boxes(boxes, in_hw, out_hw):
+    """detectron2 ``detector_postprocess``: scale boxes from the network input
+    size to the tile size, clip, and flag non-empty ones.
+
+    boxes (N,4) float32 xyxy in network-input pixels.  Returns (boxes32, keep).
+    parity unpinned (detectron2 absent); follows modeling/postprocessing.py and
+    structures/boxes.py (scale / clip / nonempty) of detectron2 v0.6.
+    """
+    b = np.array(boxes, dtype=np.float32).reshape(-1, 4).copy()
+    sx = np.float32(out_hw[1] / in_hw[1])   # python float scale applied to a float32 tensor
+    sy = np.float32(out_hw[0] / in_hw[0])
+    b[:, 0::2] *= sx
+    b[:, 1::2] *= sy
+    b[:, 0] = np.clip(b[:, 0], 0, np.float32(out_hw[1]))
+    b[:, 2] = np.clip(b[:, 2], 0, np.float32(out_hw[1]))
+    b[:, 1] = np.clip(b[:, 1], 0, np.float32(out_hw[0]))
+    b[:, 3] = np.clip(b[:, 3], 0, np.float32(out_hw[0]))
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return b, keep
+
+
+def paste_window(box, img_h, img_w):
+    """CPU-path window of ``_do_paste_mask`` (skip_empty=True, one instance per
+    chunk): [floor(x0)-1 clamp 0, ceil(x1)+1 clamp W) x [floor(y0)-1, ceil(y1)+1)."""
+    x0 = max(int(math.floor(float(box[0]))) - 1, 0)
+    y0 = max(int(math.floor(float(box[1]))) - 1, 0)
+    x1 = min(int(math.ceil(float(box[2]))) + 1, img_w)
+    y1 = min(int(math.ceil(float(box[3]))) + 1, img_h)
+    return x0, y0, x1, y1
+
+
+def paste_probs(box, prob, img_h, img_w):
+    """``_do_paste_mask`` for one instance on its CPU-path window, restated with
+    torch CPU ops in the same order (detectron2 layers/mask_ops.py).
+
+    box (4,) float32 xyxy in tile pixels, prob (M,M) float32 probabilities.
+    Returns (values float32 (h,w), (x0,y0,x1,y1)).
+    """
+    import torch
+    import torch.nn.functional as F
+
+    x0i, y0i, x1i, y1i = paste_window(box, img_h, img_w)
+    b = torch.as_tensor(np.asarray(box, dtype=np.float32)).reshape(1, 4)
+    m = torch.as_tensor(np.asarray(prob, dtype=np.float32))[None, None]
+    bx0, by0, bx1, by1 = torch.split(b, 1, dim=1)
+    img_y = torch.arange(y0i, y1i, dtype=torch.float32) + 0.5
+    img_x = torch.arange(x0i, x1i, dtype=torch.float32) + 0.5
+    img_y = (img_y - by0) / (by1 - by0) * 2 - 1
+    img_x = (img_x - bx0) / (bx1 - bx0) * 2 - 1
+    gx = img_x[:, None, :].expand(1, img_y.size(1), img_x.size(1))
+    gy = img_y[:, :, None].expand(1, img_y.size(1), img_x.size(1))
+    grid = torch.stack([gx, gy], dim=3)
+    out = F.grid_sample(m, grid, align_corners=False)
+    return out[0, 0].numpy(), (x0i, y0i, x1i, y1i)
+
+
+def paste_threshold(boxes, probs, img_h, img_w, threshold=0.5):
+    """``paste_masks_in_image`` (CPU path): bool masks (N, H, W).
+
+    Only for small cases (materialises N*H*W bools like the reference)."""
+    n = len(boxes)
+    out = np.zeros((n, img_h, img_w), dtype=bool)
+    for i in range(n):
+        v, (x0, y0, x1, y1) = paste_probs(boxes[i], probs[i], img_h, img_w)
+        out[i, y0:y1, x0:x1] = v >= np.float32(threshold)
+    return out
+
+
+def _fmaf(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in
+    float64, so one float64 add followed by a rounding reproduces fmaf."""
+    return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64)
+            + np.asarray(c, dtype=np.float64)).astype(np.float32)
+
+
+def paste_probs_closed_form(box, prob, img_h, img_w):
+    """Closed-form float32 restatement of ``_do_paste_mask`` + ATen's vectorised
+    CPU ``grid_sample`` (bilinear, zeros padding, align_corners=False).  This is
+    the operation order the CUDA kernel reproduces; it is bit-identical to
+    ``paste_probs`` (torch CPU) -- tests/test_oracle_paste.py:
+
+        g   = ((p + 0.5) - b0) / (b1 - b0) * 2 - 1      every op rounded to f32
+        u   = fma(g + 1, M/2, -0.5)                      ATen unnormalize, contracted
+        w   = u - floor(u);  e = 1 - w                   (x axis; n, s on the y axis)
+        out = fma(se, n*w, fma(sw, n*e, fma(ne, s*w, nw * (s*e))))
+              with zero padding outside [0, M)
+    """
+    f32 = np.float32
+    M = prob.shape[0]
+    x0i, y0i, x1i, y1i = paste_window(box, img_h, img_w)
+    bx0, by0, bx1, by1 = [f32(v) for v in box]
+    xs = (np.arange(x0i, x1i, dtype=np.float32) + f32(0.5))
+    ys = (np.arange(y0i, y1i, dtype=np.float32) + f32(0.5))
+    gx = (xs - bx0) / (bx1 - bx0) * f32(2) - f32(1)
+    gy = (ys - by0) / (by1 - by0) * f32(2) - f32(1)
+    ux = _fmaf(gx + f32(1), f32(M / 2), f32(-0.5))
+    uy = _fmaf(gy + f32(1), f32(M / 2), f32(-0.5))
+    xw = np.floor(ux); yn = np.floor(uy)
+    w = ux - xw; e = f32(1) - w
+    n = uy - yn; s = f32(1) - n
+    ixw = xw.astype(np.int64); iyn = yn.astype(np.int64)
+    pad = np.zeros((M + 2, M + 2), dtype=np.float32)
+    pad[1:-1, 1:-1] = prob
+
+    def at(iy, ix):
+        iy = np.clip(iy + 1, 0, M + 1); ix = np.clip(ix + 1, 0, M + 1)
+        return pad[iy[:, None], ix[None, :]]
+
+    nwv = at(iyn, ixw); nev = at(iyn, ixw + 1); swv = at(iyn + 1, ixw); sev = at(iyn + 1, ixw + 1)
+    cnw = s[:, None] * e[None, :]
+    cne = s[:, None] * w[None, :]
+    csw = n[:, None] * e[None, :]
+    cse = n[:, None] * w[None, :]
+    acc = nwv * cnw
+    acc = _fmaf(nev, cne, acc)
+    acc = _fmaf(swv, csw, acc)
+    acc = _fmaf(sev, cse, acc)
+    return acc.astype(np.float32), (x0i, y0i, x1i, y1i)
+
+
+# ============================================================================
+# P3  mask -> polygons   (prediction.py:197-265, utilities.py:182-207)
+# ============================================================================
+
+
+def find_contours(mask_u8):
+    """prediction.py:232-234 -- the same OpenCV call."""
+    import cv2
+    contours, _ = cv2.findContours(np.ascontiguousarray(mask_u8, dtype=np.uint8), cv2.RETR_TREE,
+                                   cv2.CHAIN_APPROX_SIMPLE)
+    return [c.reshape(-1, 2) for c in contours]
+
+
+def contour_to_ring_px(contour):
+    """prediction.py:235-239: keep contours with >= 4 points, flatten, close."""
+    if contour.size < 8:
+        return None
+    flat = contour.flatten().tolist()
+    if flat[:2] != flat[-2:]:
+        flat.extend(flat[:2])
+    return flat
+
+
+def xy_affine(transform, rows, cols):
+    """utilities.py:182-207 ``xy_gpu``: corner convention, float64."""
+    a, b, c, d, e, f = transform[:6]
+    xs = np.asarray(cols); ys = np.asarray(rows)
+    return a * xs + b * ys + c, d * xs + e * ys + f
+
+
+def mask_to_polygons(mask_bool, transform):
+    """prediction.py:216-251 for one instance: list of rings [(X,Y),...] in CRS
+    coordinates (one entry per kept contour, holes included as own polygons)."""
+    out = []
+    for cnt in find_contours(mask_bool.astype(np.uint8)):
+        flat = contour_to_ring_px(cnt)
+        if flat is None:
+            continue
+        X, Y = xy_affine(transform, flat[1::2], flat[::2])
+        out.append(list(zip(X.tolist(), Y.tolist())))
+    return out
+
+
+# ============================================================================
+# P4  stitch: simplify + tile box filter   (helpers.py:265-319, 419-476)
+# ============================================================================
+
+
+def tile_filter_box(minx, miny, width, buffer, shift=1):
+    """helpers.py:280-303 ``box_make``: note ``width`` is used for both axes."""
+    return (minx - buffer + shift, miny - buffer + shift, minx + width + buffer - shift, miny + width + buffer - shift)
+
+
+def stitch_tile(rings, scores, tile_box, simplify_tolerance=0.2):
+    """helpers.py:443-472: Polygon -> simplify(tol, preserve_topology) -> keep
+    iff within the shrunk tile box.  Returns (rings_out, scores_out)."""
+    ro, so = [], []
+    for ring, sc in zip(rings, scores):
+        p = geom.Polygon(ring)
+        if simplify_tolerance > 0:
+            p = p.simplify(simplify_tolerance, preserve_topology=True)
+        b = p.bounds
+        if b[0] >= tile_box[0] and b[1] >= tile_box[1] and b[2] <= tile_box[2] and b[3] <= tile_box[3]:
+            ro.append(p.exterior.coords)
+            so.append(sc)
+    return ro, so
+
+
+# ============================================================================
+# P5  NDVI  (helpers.py:862-896) and decimated reads (postprocessing.py:780-800)
+# ============================================================================
+
+
+def ndvi_from_rgbi(rgbi):
+    """helpers.py:880-896: bands 0 (red) and 3 (nir), /255, float64."""
+    red = rgbi[0].astype(np.float64) / 255.0
+    nir = rgbi[3].astype(np.float64) / 255.0
+    return (nir - red) / (nir + red + 1e-10)
+
+
+def _triangle_coeffs(in_size, out_size):
+    """Separable triangle-filter decimation weights (float64, normalised):
+    support = max(scale, 1), centre = (i + 0.5) * scale.  This is the
+    convolution form GDAL uses for RasterIO(bilinear) when down-sampling;
+    GDAL is absent here, so this restatement defines the result
+    (parity unpinned)."""
+    scale = in_size / out_size
+    fscale = max(scale, 1.0)
+    support = 1.0 * fscale
+    bounds = []
+    coeffs = []
+    for i in range(out_size):
+        center = (i + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size)
+        ws = []
+        for x in range(xmin, xmax):
+            t = abs((x - center + 0.5) / fscale)
+            ws.append(1.0 - t if t < 1.0 else 0.0)
+        tot = sum(ws)
+        ws = [w / tot for w in ws] if tot != 0.0 else ws
+        bounds.append((xmin, xmax - xmin))
+        coeffs.append(ws)
+    return bounds, coeffs
+
+
+def decimate_bilinear(band, out_h, out_w):
+    """postprocessing.py:782-786 / 793-796 (``Resampling.bilinear`` with an
+    ``out_shape``).  Two passes (horizontal then vertical), float32 weights and
+    accumulation in tap order; uint8 results are rounded half up and clamped,
+    float32 results are left as accumulated.  Identity when the shape is unchanged."""
+    h, w = band.shape
+    if (out_h, out_w) == (h, w):
+        return band.copy()
+    bx, cx = _triangle_coeffs(w, out_w)
+    by, cy = _triangle_coeffs(h, out_h)
+    src = band.astype(np.float32)
+    tmp = np.zeros((h, out_w), dtype=np.float32)
+    for j in range(out_w):
+        x0, n = bx[j]
+        acc = np.zeros(h, dtype=np.float32)
+        for k in range(n):
+            acc = acc + src[:, x0 + k] * np.float32(cx[j][k])
+        tmp[:, j] = acc
+    out = np.zeros((out_h, out_w), dtype=np.float32)
+    for i in range(out_h):
+        y0, n = by[i]
+        acc = np.zeros(out_w, dtype=np.float32)
+        for k in range(n):
+            acc = acc + tmp[y0 + k, :] * np.float32(cy[i][k])
+        out[i, :] = acc
+    if band.dtype == np.uint8:
+        return np.clip(np.floor(out + np.float32(0.5)), 0, 255).astype(np.uint8)
+    return out
+
+
+def scaled_transform(transform, width, height, out_w, out_h):
+    """postprocessing.py:787-788: ``src.transform * Affine.scale(W/w', H/h')``."""
+    a, b, c, d, e, f = transform[:6]
+    sx = width / out_w; sy = height / out_h
+    return (a * sx + b * 0.0, a * 0.0 + b * sy, a * 0.0 + b * 0.0 + c,
+            d * sx + e * 0.0, d * 0.0 + e * sy, d * 0.0 + e * 0.0 + f)
+
+
+# ============================================================================
+# P6  bbox NMS   (postprocessing.py:349-406, utilities.py:112-144)
+# ============================================================================
+
+
+def nms_bbox(bounds, conf, area, iou_threshold, area_threshold):
+    """Returns a bool array ``removed`` (True = suppressed), index order = input
+    order.  bounds (N,4) float64, conf (N,), area (N,).
+
+    dtypes: bbox float32, confidence float16, area float16
+    (postprocessing.py:367-369); python-scalar thresholds are weak, i.e. the
+    comparisons happen in float32 / float16."""
+    b = np.array([[np.float32(v) for v in row] for row in bounds], dtype=np.float32).reshape(-1, 4)
+    c16 = np.asarray(conf, dtype=np.float16)
+    a16 = np.asarray(area, dtype=np.float16)
+    n = len(b)
+    xA = np.maximum(b[:, 0][:, None], b[:, 0]); yA = np.maximum(b[:, 1][:, None], b[:, 1])
+    xB = np.minimum(b[:, 2][:, None], b[:, 2]); yB = np.minimum(b[:, 3][:, None], b[:, 3])
+    inter = np.maximum(0, xB - xA) * np.maximum(0, yB - yA)
+    ar = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    union = ar[:, None] + ar - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = inter / union
+        am = np.abs(a16[:, None] - a16) / np.maximum(a16[:, None], a16)
+    mask = (iou > iou_threshold) & (am < area_threshold)
+    removed = np.zeros(n, dtype=bool)
+    for i in range(n):
+        if removed[i]:
+            continue
+        connected = np.append(np.where(mask[i])[0], i)
+        best = connected[np.argmax(c16[connected])]
+        for j in connected:
+            if j != best:
+                removed[j] = True
+    return removed
+
+
+def nms_bbox_sparse(bounds, conf, area, iou_threshold, area_threshold):
+    """Same result as :func:`nms_bbox` without N^2 memory (pairs are found with
+    a sort-and-sweep on x); for parity checks at sizes the dense form cannot hold."""
+    b = np.asarray(bounds, dtype=np.float64).astype(np.float32).reshape(-1, 4)
+    c16 = np.asarray(conf, dtype=np.float16)
+    a16 = np.asarray(area, dtype=np.float16)
+    n = len(b)
+    order = np.argsort(b[:, 0], kind="stable")
+    nbrs = [[] for _ in range(n)]
+    thr_i = np.float32(iou_threshold); thr_a = np.float16(area_threshold)
+    ar = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    xs = b[order, 0]
+    for oi in range(n):
+        i = order[oi]
+        hi = np.searchsorted(xs, b[i, 2], side="right")
+        cand = order[oi:hi]
+        if len(cand) == 0:
+            continue
+        xA = np.maximum(b[i, 0], b[cand, 0]); yA = np.maximum(b[i, 1], b[cand, 1])
+        xB = np.minimum(b[i, 2], b[cand, 2]); yB = np.minimum(b[i, 3], b[cand, 3])
+        inter = np.maximum(np.float32(0), xB - xA) * np.maximum(np.float32(0), yB - yA)
+        union = (ar[i] + ar[cand]) - inter
+        with np.errstate(divide="ignore", invalid="ignore"):
+            iou = inter / union
+            am = np.abs(a16[i] - a16[cand]) / np.maximum(a16[i], a16[cand])
+        # NOTE union is computed as ar[i] + ar[j] - inter in both orders in the
+        # dense form; float32 addition is commutative so iou[i,j] == iou[j,i].
+        ok = (iou > thr_i) & (am < thr_a)
+        for j in cand[ok]:
+            if j == i:
+                nbrs[i].append(i)       # mask[i, i] True when iou(i,i)=1 > thr
+            else:
+                nbrs[i].append(j); nbrs[j].append(i)
+    removed = np.zeros(n, dtype=bool)
+    for i in range(n):
+        if removed[i]:
+            continue
+        connected = np.array(sorted(set(nbrs[i])) + [i], dtype=np.int64)
+        best = connected[np.argmax(c16[connected])]
+        for j in connected:
+            if j != best:
+                removed[j] = True
+    return removed
+
+
+# ============================================================================
+# P7  per-crown raster statistics   (postprocessing.py:25-347, utilities.py:38-98)
+# ============================================================================
+
+
+def pad_polygons(rings):
+    """postprocessing.py:509-540: NaN-padded (N,V) float32 vertex arrays."""
+    v = max(len(r) for r in rings)
+    px = np.full((len(rings), v), np.nan)
+    py = np.full((len(rings), v), np.nan)
+    for i, r in enumerate(rings):
+        px[i, :len(r)] = [p[0] for p in r]
+        py[i, :len(r)] = [p[1] for p in r]
+    return px.astype(np.float32), py.astype(np.float32)
+
+
+def centroids(px32, py32):
+    """utilities.py:163-180: nanmean over the padded float32 vertices."""
+    return np.stack((np.nanmean(px32, axis=1), np.nanmean(py32, axis=1)), axis=1)
+
+
+def crown_circle(px32_i, py32_i):
+    """postprocessing.py:285-301: bbox centre and max vertex distance, float32."""
+    valid = ~np.isnan(px32_i) & ~np.isnan(py32_i)
+    vx = px32_i[valid]; vy = py32_i[valid]
+    cx = (vx.min() + vx.max()) / 2
+    cy = (vy.min() + vy.max()) / 2
+    dx = vx - cx; dy = vy - cy
+    r = np.sqrt(dx ** 2 + dy ** 2).max()
+    return cx, cy, r
+
+
+def pixel_coords(transform, h, w, dtype):
+    """postprocessing.py:259-266 / 60-67: corner-convention pixel coordinates of
+    the whole raster, computed in float64 then cast (float32 in the combined
+    and NDVI paths, float64 in the height-only path)."""
+    a, b, c, d, e, f = transform[:6]
+    rows, cols = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    x = a * cols + b * rows + c
+    y = d * cols + e * rows + f
+    return x.astype(dtype), y.astype(dtype)
+
+
+def _stats_one(vals_h, xs, ys, inside_h, vals_n, inside_n):
+    out = {}
+    if inside_n is not None:
+        sel = vals_n[inside_n]
+        if sel.shape[0] == 0:
+            out.update(ndvi_min=-1.0, ndvi_max=-1.0, ndvi_mean=-1.0, ndvi_var=-1.0)
+        else:
+            out.update(ndvi_min=sel[np.argmin(sel)], ndvi_max=sel[np.argmax(sel)],
+                       ndvi_mean=np.mean(sel), ndvi_var=np.var(sel))
+    if inside_h is not None:
+        sel = vals_h[inside_h]
+        if sel.size == 0:
+            out.update(max_h=-1.0, hx=-1.0, hy=-1.0)
+        else:
+            k = np.argmax(sel)
+            out.update(max_h=sel[k], hx=xs[inside_h][k], hy=ys[inside_h][k])
+    return out
+
+
+def crown_stats_combined(px32, py32, ndvi32, height32, transform):
+    """postprocessing.py:221-347 ``get_metadata_within_polygon`` with the
+    raster's own bounds (subset == whole raster).
+    Height set: d^2 <= r^2; NDVI set: d^2 <= (0.5 r)^2; float32 coordinates.
+    Returns dict of float32 arrays."""
+    h, w = ndvi32.shape
+    xs, ys = pixel_coords(transform, h, w, np.float32)
+    xs = xs.ravel(); ys = ys.ravel()
+    hv = height32.ravel(); nv = ndvi32.ravel()
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in
+           ("max_h", "hx", "hy", "ndvi_min", "ndvi_max", "ndvi_mean", "ndvi_var")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        d2 = (xs - cx) ** 2 + (ys - cy) ** 2
+        inside_n = d2 <= (r * 0.5) ** 2
+        inside_h = d2 <= r ** 2
+        for k, v in _stats_one(hv, xs, ys, inside_h, nv, inside_n).items():
+            res[k][i] = v
+    return res
+
+
+def crown_stats_height(px32, py32, height32, transform):
+    """postprocessing.py:25-115 ``get_height_within_polygon``: float64 pixel
+    coordinates (:67), full radius."""
+    h, w = height32.shape
+    xs, ys = pixel_coords(transform, h, w, np.float64)
+    xs = xs.ravel(); ys = ys.ravel(); hv = height32.ravel()
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in ("max_h", "hx", "hy")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        inside = (xs - cx) ** 2 + (ys - cy) ** 2 <= r ** 2
+        for k, v in _stats_one(hv, xs, ys, inside, None, None).items():
+            res[k][i] = v
+    return res
+
+
+def crown_stats_ndvi(px32, py32, ndvi32, transform):
+    """postprocessing.py:117-219 ``get_ndvi_within_polygon``: float32 pixel
+    coordinates (:160), FULL radius (:195)."""
+    h, w = ndvi32.shape
+    xs, ys = pixel_coords(transform, h, w, np.float32)
+    xs = xs.ravel(); ys = ys.ravel(); nv = ndvi32.ravel()
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in ("ndvi_min", "ndvi_max", "ndvi_mean", "ndvi_var")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        inside = (xs - cx) ** 2 + (ys - cy) ** 2 <= r ** 2
+        for k, v in _stats_one(None, xs, ys, None, nv, inside).items():
+            res[k][i] = v
+    return res
+
+
+# ============================================================================
+# P8  containment   (postprocessing.py:408-476)
+# ============================================================================
+
+
+def containment(bounds, threshold):
+    """Returns (containment_ratio (N,) f32, is_contained (N,) bool,
+    num_contained (N,) int).  ratio[o,i] = area(o & i)/area(i) in float32."""
+    b = np.asarray(bounds, dtype=np.float32).reshape(-1, 4)
+    n = b.shape[0]
+    ix0 = np.maximum(b[:, 0][:, None], b[:, 0][None, :]); iy0 = np.maximum(b[:, 1][:, None], b[:, 1][None, :])
+    ix1 = np.minimum(b[:, 2][:, None], b[:, 2][None, :]); iy1 = np.minimum(b[:, 3][:, None], b[:, 3][None, :])
+    iw = np.maximum(0, ix1 - ix0); ih = np.maximum(0, iy1 - iy0)
+    inter = iw * ih
+    inner = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = inter / inner[None, :]
+    isc = ratio >= threshold
+    isc[np.arange(n), np.arange(n)] = False
+    num = isc.sum(axis=1)
+    return ratio.max(axis=0), isc.any(axis=0), num
