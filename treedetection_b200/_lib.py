@@ -1,0 +1,104 @@
+"""ctypes binding of ``libtreedet.so`` (the C-ABI declared in ``include/treedet.h``).
+
+There is no CPU fallback: if the shared object is missing or a call fails, the
+error is raised.  PyTorch tensors are only the interchange -- the library sees raw
+device pointers, sizes and the current CUDA stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtreedet.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+_d = C.c_double
+
+# name -> (restype, argtypes).  Mirrors include/treedet.h one to one
+# (tests/test_abi.py checks both directions).
+SIGNATURES = {
+    "td_version": (_i, []),
+    "td_last_error": (C.c_char_p, []),
+    "td_device_sms": (_i, []),
+    # P2
+    "td_paste_plan": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "td_paste_threshold_pack": (_i, [_p, _p, _p, _p, _i, _f, _p, _p]),
+    "td_paste_values": (_i, [_p, _p, _p, _p, _i, _p, _p]),
+    # P3
+    "td_trace_count": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p]),
+    "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
+                           _p]),
+    # P4 / P9 geometry
+    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p]),
+    "td_ring_bounds_area": (_i, [_p, _p, _i, _p, _p, _p]),
+    "td_box_filter": (_i, [_p, _p, _p, _i, _p, _p]),
+    # P5
+    "td_ndvi_decimate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "td_decimate_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    # P6 / P8
+    "td_bbox_nms_ordered": (_i, [_p, _p, _p, _i, _d, _d, _p, _p]),
+    "td_containment": (_i, [_p, _i, _d, _p, _p, _p, _p]),
+    # P7
+    "td_crown_stats": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "td_centroids": (_i, [_p, _p, _i, _p, _p]),
+    # P9
+    "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    # P1
+    "td_tile_cut_normalize": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    # P0a
+    "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+}
+
+_lib = None
+
+
+class TreedetError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the library (once).  Raises when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TreedetError(
+            f"{LIB_PATH} is missing: run `python -m treedetection_b200.build` (there is no CPU fallback)")
+    handle = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError:
+            continue  # reported by exported_symbols() / test_abi
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return handle
+
+
+def exported_symbols():
+    """Names from SIGNATURES the shared object really exports."""
+    h = lib()
+    out = []
+    for name in SIGNATURES:
+        try:
+            getattr(h, name)
+            out.append(name)
+        except AttributeError:
+            pass
+    return out
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().td_last_error()
+        raise TreedetError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args):
+    fn = getattr(lib(), name)
+    check(fn(*args), name)

@@ -1,0 +1,30 @@
+// libtreedet C-ABI plumbing: version, thread-local error string.
+// Every entry point is declared in include/treedet.h.
+#include <cstdarg>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void td_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int td_version() { return 100; }  // 0.1.0
+
+extern "C" const char* td_last_error() { return g_err; }
+
+// number of SMs of the current device (148 on B200); also proves the CUDA runtime
+// is usable from the calling process
+extern "C" int td_device_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { td_set_error("cudaGetDevice failed"); return TD_ERR_CUDA; }
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    td_set_error("cudaDeviceGetAttribute failed");
+    return TD_ERR_CUDA;
+  }
+  return n;
+}

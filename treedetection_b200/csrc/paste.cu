@@ -1,0 +1,212 @@
+// P2 -- mask paste + threshold + bit-pack.
+//
+// Replaces detectron2's detector_postprocess -> ROIMasks.to_bitmasks ->
+// paste_masks_in_image -> _do_paste_mask (external, entered from the reference at
+// TreeDetection/prediction.py:181-183) and the identity resize + uint8 cast at
+// prediction.py:222-229.  The reference materialises an (N,H,W) bool raster
+// (202 500 B per instance on a 450x450 tile); here every instance writes only
+// the 1-bit raster of its own paste window (the CPU-path window of
+// _do_paste_mask: [floor(x0)-1, ceil(x1)+1) x [floor(y0)-1, ceil(y1)+1), clipped
+// to the tile), 32 pixels per word, rows padded to a whole word.
+//
+// Arithmetic (float32, every operation rounded, contractions written out as
+// explicit fmaf so that the result is bit-identical to ATen's CPU grid_sample;
+// oracle: oracle/port.py paste_probs_closed_form):
+//     g   = ((p + 0.5) - b0) / (b1 - b0) * 2 - 1
+//     u   = fma(g + 1, M/2, -0.5)
+//     w   = u - floor(u);  e = 1 - w      (x axis; n, s on the y axis)
+//     out = fma(se, n*w, fma(sw, n*e, fma(ne, s*w, nw * (s*e))))   zero padded
+//     bit = out >= threshold
+#include "common.cuh"
+
+namespace {
+
+constexpr int kM = 28;              // mask side of Mask R-CNN's ROI head
+constexpr int kPad = kM + 2;        // zero border so that taps need no bounds test
+constexpr int kPasteThreads = 128;  // 4 warps per instance
+
+// ---------------------------------------------------------------------------
+// plan: scale + clip boxes, drop empty ones, compute the paste window
+// ---------------------------------------------------------------------------
+__global__ void paste_plan_kernel(const float* __restrict__ boxes_net, const int* __restrict__ inst_tile,
+                                  const int* __restrict__ tile_dims, int n, float* __restrict__ boxes_px,
+                                  int* __restrict__ win, long long* __restrict__ nwords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = inst_tile[i];
+  const int out_h = tile_dims[4 * t + 0], out_w = tile_dims[4 * t + 1];
+  const int net_h = tile_dims[4 * t + 2], net_w = tile_dims[4 * t + 3];
+  // detector_postprocess: python-float scale applied to a float32 tensor
+  const float sx = (float)((double)out_w / (double)net_w);
+  const float sy = (float)((double)out_h / (double)net_h);
+  float x0 = __fmul_rn(boxes_net[4 * i + 0], sx);
+  float y0 = __fmul_rn(boxes_net[4 * i + 1], sy);
+  float x1 = __fmul_rn(boxes_net[4 * i + 2], sx);
+  float y1 = __fmul_rn(boxes_net[4 * i + 3], sy);
+  const float fw = (float)out_w, fh = (float)out_h;
+  x0 = fminf(fmaxf(x0, 0.f), fw);
+  x1 = fminf(fmaxf(x1, 0.f), fw);
+  y0 = fminf(fmaxf(y0, 0.f), fh);
+  y1 = fminf(fmaxf(y1, 0.f), fh);
+  boxes_px[4 * i + 0] = x0;
+  boxes_px[4 * i + 1] = y0;
+  boxes_px[4 * i + 2] = x1;
+  boxes_px[4 * i + 3] = y1;
+  const bool keep = (__fsub_rn(x1, x0) > 0.f) && (__fsub_rn(y1, y0) > 0.f);
+  int wx0 = 0, wy0 = 0, ww = 0, wh = 0;
+  if (keep) {
+    wx0 = max((int)floorf(x0) - 1, 0);
+    wy0 = max((int)floorf(y0) - 1, 0);
+    const int wx1 = min((int)ceilf(x1) + 1, out_w);
+    const int wy1 = min((int)ceilf(y1) + 1, out_h);
+    ww = max(wx1 - wx0, 0);
+    wh = max(wy1 - wy0, 0);
+  }
+  win[4 * i + 0] = wx0;
+  win[4 * i + 1] = wy0;
+  win[4 * i + 2] = ww;
+  win[4 * i + 3] = wh;
+  nwords[i] = (long long)((ww + 31) >> 5) * (long long)wh;
+}
+
+// one axis of the sampling grid: pixel centre -> tap index and the two weights
+struct Tap {
+  int i0;    // floor(u) + 1 (index into the zero-padded 30x30 table), clamped
+  int i1;    // i0 + 1, clamped
+  float w1;  // weight of i1 (u - floor(u))
+  float w0;  // weight of i0 (1 - w1)
+};
+
+TD_D Tap make_tap(int p, float b0, float b1) {
+  const float c = __fadd_rn((float)p, 0.5f);
+  float g = __fdiv_rn(__fsub_rn(c, b0), __fsub_rn(b1, b0));
+  g = __fsub_rn(__fmul_rn(g, 2.f), 1.f);
+  const float u = __fmaf_rn(__fadd_rn(g, 1.f), (float)(kM / 2), -0.5f);
+  const float fl = floorf(u);
+  Tap t;
+  t.w1 = __fsub_rn(u, fl);
+  t.w0 = __fsub_rn(1.f, t.w1);
+  // clamp in float first: u can be far outside the table for pixels of the
+  // window that lie outside the box (and NaN/inf never occur: b1 > b0)
+  const float flc = fminf(fmaxf(fl, -2.f), (float)(kM + 1));
+  const int i = (int)flc;
+  t.i0 = min(max(i + 1, 0), kPad - 1);
+  t.i1 = min(max(i + 2, 0), kPad - 1);
+  return t;
+}
+
+TD_D float sample(const float (*tab)[kPad], const Tap& tx, const Tap& ty) {
+  const float nw = tab[ty.i0][tx.i0], ne = tab[ty.i0][tx.i1];
+  const float sw = tab[ty.i1][tx.i0], se = tab[ty.i1][tx.i1];
+  // weights: "n" = ty.w1 (distance from the north tap), "s" = ty.w0, "w" = tx.w1, "e" = tx.w0
+  const float cnw = __fmul_rn(ty.w0, tx.w0);
+  const float cne = __fmul_rn(ty.w0, tx.w1);
+  const float csw = __fmul_rn(ty.w1, tx.w0);
+  const float cse = __fmul_rn(ty.w1, tx.w1);
+  float acc = __fmul_rn(nw, cnw);
+  acc = __fmaf_rn(ne, cne, acc);
+  acc = __fmaf_rn(sw, csw, acc);
+  acc = __fmaf_rn(se, cse, acc);
+  return acc;
+}
+
+// ---------------------------------------------------------------------------
+// paste + threshold + pack: one CTA per instance, one warp per 32-pixel word
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPasteThreads)
+paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ win,
+                  const long long* __restrict__ word_off, const float* __restrict__ probs, int n, float thr,
+                  uint32_t* __restrict__ bits) {
+  __shared__ float tab[kPad][kPad];
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int ww = win[4 * i + 2], wh = win[4 * i + 3];
+  if (ww <= 0 || wh <= 0) return;
+  const int wx0 = win[4 * i + 0], wy0 = win[4 * i + 1];
+  for (int k = threadIdx.x; k < kPad * kPad; k += kPasteThreads) {
+    const int r = k / kPad, c = k % kPad;
+    float v = 0.f;
+    if (r >= 1 && r <= kM && c >= 1 && c <= kM) v = probs[(size_t)i * kM * kM + (r - 1) * kM + (c - 1)];
+    tab[r][c] = v;
+  }
+  __syncthreads();
+  const float bx0 = boxes_px[4 * i + 0], by0 = boxes_px[4 * i + 1];
+  const float bx1 = boxes_px[4 * i + 2], by1 = boxes_px[4 * i + 3];
+  const int wpr = (ww + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* out = bits + word_off[i];
+  const int ntask = wpr * wh;
+  for (int t = warp; t < ntask; t += kPasteThreads / 32) {
+    const int y = t / wpr, wi = t - y * wpr;
+    const int x = wi * 32 + lane;
+    bool on = false;
+    if (x < ww) {
+      const Tap tx = make_tap(wx0 + x, bx0, bx1);
+      const Tap ty = make_tap(wy0 + y, by0, by1);
+      on = sample(tab, tx, ty) >= thr;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) out[t] = word;
+  }
+}
+
+// debug / tolerance-test path: the pasted probabilities themselves (float32)
+__global__ void paste_values_kernel(const float* __restrict__ boxes_px, const int* __restrict__ win,
+                                    const long long* __restrict__ val_off, const float* __restrict__ probs, int n,
+                                    float* __restrict__ vals) {
+  __shared__ float tab[kPad][kPad];
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int ww = win[4 * i + 2], wh = win[4 * i + 3];
+  if (ww <= 0 || wh <= 0) return;
+  const int wx0 = win[4 * i + 0], wy0 = win[4 * i + 1];
+  for (int k = threadIdx.x; k < kPad * kPad; k += blockDim.x) {
+    const int r = k / kPad, c = k % kPad;
+    float v = 0.f;
+    if (r >= 1 && r <= kM && c >= 1 && c <= kM) v = probs[(size_t)i * kM * kM + (r - 1) * kM + (c - 1)];
+    tab[r][c] = v;
+  }
+  __syncthreads();
+  const float bx0 = boxes_px[4 * i + 0], by0 = boxes_px[4 * i + 1];
+  const float bx1 = boxes_px[4 * i + 2], by1 = boxes_px[4 * i + 3];
+  float* out = vals + val_off[i];
+  for (int k = threadIdx.x; k < ww * wh; k += blockDim.x) {
+    const int y = k / ww, x = k - y * ww;
+    out[k] = sample(tab, make_tap(wx0 + x, bx0, bx1), make_tap(wy0 + y, by0, by1));
+  }
+}
+
+}  // namespace
+
+extern "C" int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst,
+                             int n_tiles, float* boxes_px, int* win, long long* nwords, void* stream) {
+  TD_ARG(n_inst >= 0 && n_tiles >= 0);
+  if (n_inst == 0) return TD_OK;
+  TD_ARG(boxes_net && inst_tile && tile_dims && boxes_px && win && nwords);
+  paste_plan_kernel<<<td_div_up(n_inst, 256), 256, 0, (cudaStream_t)stream>>>(boxes_net, inst_tile, tile_dims, n_inst,
+                                                                              boxes_px, win, nwords);
+  TD_CHECK_LAUNCH("td_paste_plan");
+  return TD_OK;
+}
+
+extern "C" int td_paste_threshold_pack(const float* boxes_px, const int* win, const long long* word_off,
+                                       const float* probs, int n_inst, float threshold, uint32_t* bits,
+                                       void* stream) {
+  TD_ARG(n_inst >= 0);
+  if (n_inst == 0) return TD_OK;
+  TD_ARG(boxes_px && win && word_off && probs && bits);
+  paste_pack_kernel<<<n_inst, kPasteThreads, 0, (cudaStream_t)stream>>>(boxes_px, win, word_off, probs, n_inst,
+                                                                       threshold, bits);
+  TD_CHECK_LAUNCH("td_paste_threshold_pack");
+  return TD_OK;
+}
+
+extern "C" int td_paste_values(const float* boxes_px, const int* win, const long long* val_off, const float* probs,
+                               int n_inst, float* vals, void* stream) {
+  TD_ARG(n_inst >= 0);
+  if (n_inst == 0) return TD_OK;
+  TD_ARG(boxes_px && win && val_off && probs && vals);
+  paste_values_kernel<<<n_inst, 128, 0, (cudaStream_t)stream>>>(boxes_px, win, val_off, probs, n_inst, vals);
+  TD_CHECK_LAUNCH("td_paste_values");
+  return TD_OK;
+}

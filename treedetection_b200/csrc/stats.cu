@@ -1,0 +1,295 @@
+// P7 -- per-crown raster statistics, and the crown centroids (K11).
+//
+// Replaces get_metadata_within_polygon (TreeDetection/postprocessing.py:221-347), the
+// split pair get_height_within_polygon (:25-115) / get_ndvi_within_polygon (:117-219),
+// is_point_in_polygon_batch (utilities.py:78-98) and get_centroids (utilities.py:163-180).
+//
+// The reference tests EVERY raster pixel against every crown's circle (N x P work,
+// ~40 launches per crown).  Here one warp owns one crown and visits only a
+// conservative pixel window around the circle; inside that window the membership
+// test is evaluated in exactly the reference's arithmetic, so the selected pixel
+// set is identical:
+//     c = (min + max) / 2 of the float32 vertices, r = max sqrt(dx^2 + dy^2)   (float32)
+//     pixel coordinate = a*col + b*row + c0 (float64, corner convention) cast to
+//         float32 in the combined and NDVI paths (:266, :160), kept float64 in the
+//         height-only path (:67)
+//     inside <=> (px - cx)^2 + (py - cy)^2 <= radius^2
+//     radius = r for heights, 0.5 r for NDVI in the combined path (:304), r in the
+//         NDVI-only path (:195)
+// Outputs: max height + coordinates of the FIRST arg-max in row-major order,
+// NDVI min / max / mean / population variance; empty set -> -1.
+// mean / var are accumulated in float64 and rounded once (the reference sums in
+// float32; agreement is to ~1e-7, the contract is 1e-5 absolute).
+#include "common.cuh"
+
+namespace {
+
+struct Affine6 {
+  double a, b, c, d, e, f;
+};
+
+enum StatsMode { kCombined = 0, kHeightOnly = 1, kNdviOnly = 2 };
+
+// NaN-aware "numpy argmax" ordering on (value, flat index): NaN beats numbers,
+// ties go to the lower index
+TD_D bool better_max(float v, long long k, float bv, long long bk) {
+  if (bk < 0) return true;
+  const bool vn = isnan(v), bn = isnan(bv);
+  if (vn || bn) {
+    if (vn && bn) return k < bk;
+    return vn;
+  }
+  return v > bv || (v == bv && k < bk);
+}
+TD_D bool better_min(float v, long long k, float bv, long long bk) {
+  if (bk < 0) return true;
+  const bool vn = isnan(v), bn = isnan(bv);
+  if (vn || bn) {
+    if (vn && bn) return k < bk;
+    return vn;
+  }
+  return v < bv || (v == bv && k < bk);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
+                   const float* __restrict__ ndvi, const float* __restrict__ height, int rows, int cols, Affine6 T,
+                   float* __restrict__ max_h, float* __restrict__ hxy, float* __restrict__ ndvi_stats) {
+  const int lane = threadIdx.x & 31;
+  const int crown = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (crown >= n) return;
+  const unsigned full = 0xffffffffu;
+
+  // ---- circle from the float32 vertices ------------------------------------
+  const long long v0 = ring_off[crown], v1 = ring_off[crown + 1];
+  float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+  for (long long k = v0 + lane; k < v1; k += 32) {
+    const float x = __double2float_rn(verts[2 * k]), y = __double2float_rn(verts[2 * k + 1]);
+    if (isnan(x) || isnan(y)) continue;
+    mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
+    mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(full, mnx, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(full, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(full, mny, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(full, mxy, o));
+  }
+  const float cx = __fdiv_rn(__fadd_rn(mnx, mxx), 2.f);
+  const float cy = __fdiv_rn(__fadd_rn(mny, mxy), 2.f);
+  float r = -INFINITY;
+  for (long long k = v0 + lane; k < v1; k += 32) {
+    const float x = __double2float_rn(verts[2 * k]), y = __double2float_rn(verts[2 * k + 1]);
+    if (isnan(x) || isnan(y)) continue;
+    const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy);
+    r = fmaxf(r, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+  }
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(full, r, o));
+  const float r_h = r;
+  const float r_n = (MODE == kCombined) ? __fmul_rn(r, 0.5f) : r;
+  const float r2_h = __fmul_rn(r_h, r_h);
+  const float r2_n = __fmul_rn(r_n, r_n);
+
+  // ---- conservative pixel window -------------------------------------------
+  int c_lo = 0, c_hi = cols - 1, r_lo = 0, r_hi = rows - 1;
+  const bool axis_aligned = (T.b == 0.0 && T.d == 0.0 && T.a != 0.0 && T.e != 0.0);
+  if (axis_aligned && isfinite(r) && isfinite(cx) && isfinite(cy)) {
+    // margin: float32 rounding of the pixel coordinate (1 ulp of the magnitude)
+    // and of the squared-distance arithmetic, generously over-estimated
+    const double mag = fmax(fmax(fabs((double)cx), fabs((double)cy)), 1.0);
+    const double m = (double)r * 1e-3 + mag * 4.8e-7 + 1e-6;
+    const double xa = ((double)cx - (double)r - m - T.c) / T.a, xb = ((double)cx + (double)r + m - T.c) / T.a;
+    const double ya = ((double)cy - (double)r - m - T.f) / T.e, yb = ((double)cy + (double)r + m - T.f) / T.e;
+    const double cl = floor(fmin(xa, xb)) - 1.0, ch = ceil(fmax(xa, xb)) + 1.0;
+    const double rl = floor(fmin(ya, yb)) - 1.0, rh = ceil(fmax(ya, yb)) + 1.0;
+    c_lo = (int)fmax(cl, 0.0); c_hi = (int)fmin(ch, (double)(cols - 1));
+    r_lo = (int)fmax(rl, 0.0); r_hi = (int)fmin(rh, (double)(rows - 1));
+  }
+  const int ww = c_hi - c_lo + 1, wh = r_hi - r_lo + 1;
+
+  float bh = 0.f; long long bhk = -1;          // height arg-max
+  float nmin = 0.f; long long nmink = -1;      // NDVI arg-min / arg-max
+  float nmax = 0.f; long long nmaxk = -1;
+  double s1 = 0.0, s2 = 0.0; long long cnt = 0;
+  if (ww > 0 && wh > 0 && !isnan(r)) {
+    const long long total = (long long)ww * wh;
+    for (long long k = lane; k < total; k += 32) {
+      const int rr = r_lo + (int)(k / ww), cc = c_lo + (int)(k % ww);
+      const double xd = T.a * (double)cc + T.b * (double)rr + T.c;
+      const double yd = T.d * (double)cc + T.e * (double)rr + T.f;
+      const long long flat = (long long)rr * cols + cc;
+      if (MODE == kHeightOnly) {
+        const double dx = xd - (double)cx, dy = yd - (double)cy;
+        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (d2 <= (double)r2_h) {
+          const float v = height[flat];
+          if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
+        }
+      } else {
+        const float x = __double2float_rn(xd), y = __double2float_rn(yd);
+        const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy);
+        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (MODE == kCombined && d2 <= r2_h) {
+          const float v = height[flat];
+          if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
+        }
+        if (d2 <= r2_n) {
+          const float v = ndvi[flat];
+          if (better_min(v, flat, nmin, nmink)) { nmin = v; nmink = flat; }
+          if (better_max(v, flat, nmax, nmaxk)) { nmax = v; nmaxk = flat; }
+          s1 += (double)v; s2 += (double)v * (double)v; ++cnt;
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(full, bh, o); long long ok = __shfl_xor_sync(full, bhk, o);
+    if (ok >= 0 && better_max(ov, ok, bh, bhk)) { bh = ov; bhk = ok; }
+    ov = __shfl_xor_sync(full, nmin, o); ok = __shfl_xor_sync(full, nmink, o);
+    if (ok >= 0 && better_min(ov, ok, nmin, nmink)) { nmin = ov; nmink = ok; }
+    ov = __shfl_xor_sync(full, nmax, o); ok = __shfl_xor_sync(full, nmaxk, o);
+    if (ok >= 0 && better_max(ov, ok, nmax, nmaxk)) { nmax = ov; nmaxk = ok; }
+    s1 += __shfl_xor_sync(full, s1, o);
+    s2 += __shfl_xor_sync(full, s2, o);
+    cnt += __shfl_xor_sync(full, cnt, o);
+  }
+  if (lane != 0) return;
+  if (MODE != kNdviOnly) {
+    if (bhk < 0) {
+      max_h[crown] = -1.f; hxy[2 * crown] = -1.f; hxy[2 * crown + 1] = -1.f;
+    } else {
+      const int rr = (int)(bhk / cols), cc = (int)(bhk % cols);
+      max_h[crown] = bh;
+      hxy[2 * crown] = __double2float_rn(T.a * (double)cc + T.b * (double)rr + T.c);
+      hxy[2 * crown + 1] = __double2float_rn(T.d * (double)cc + T.e * (double)rr + T.f);
+    }
+  }
+  if (MODE != kHeightOnly) {
+    float* o = ndvi_stats + 4 * (size_t)crown;
+    if (cnt == 0) {
+      o[0] = o[1] = o[2] = o[3] = -1.f;
+    } else {
+      const double mean = s1 / (double)cnt;
+      double var = s2 / (double)cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      o[0] = nmin; o[1] = nmax; o[2] = (float)mean; o[3] = (float)var;
+    }
+  }
+}
+
+// ---- centroids: np.nanmean over the NaN-padded (N, V) float32 arrays ---------
+// numpy reduces every row with its pairwise summation over the PADDED length V
+// (NaN -> 0), so the blocking depends on V = the longest ring of the batch.
+struct RowGetter {
+  const double* verts;  // interleaved x,y
+  long long v0;
+  int len;    // ring length
+  int comp;   // 0 = x, 1 = y
+  TD_D float operator()(int i) const {
+    if (i >= len) return 0.f;
+    const float v = __double2float_rn(verts[2 * (v0 + i) + comp]);
+    return isnan(v) ? 0.f : v;
+  }
+};
+
+__device__ float np_pairwise_sum(const RowGetter& a, int lo, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, a(lo + i));
+    return res;
+  }
+  if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a(lo + j);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a(lo + i + j));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, a(lo + i));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(np_pairwise_sum(a, lo, n2), np_pairwise_sum(a, lo + n2, n - n2));
+}
+
+__global__ void max_ring_len_kernel(const long long* __restrict__ ring_off, int n, int* __restrict__ vmax) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = (i < n) ? (int)(ring_off[i + 1] - ring_off[i]) : 0;
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(vmax, len);
+}
+
+__global__ void centroid_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
+                                const int* __restrict__ vmax, float* __restrict__ centroid) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int V = *vmax;
+  RowGetter g;
+  g.verts = verts; g.v0 = ring_off[i]; g.len = (int)(ring_off[i + 1] - ring_off[i]);
+  long long cntx = 0, cnty = 0;
+  for (int k = 0; k < g.len; ++k) {
+    if (!isnan(__double2float_rn(verts[2 * (g.v0 + k)]))) ++cntx;
+    if (!isnan(__double2float_rn(verts[2 * (g.v0 + k) + 1]))) ++cnty;
+  }
+  g.comp = 0;
+  const float sx = np_pairwise_sum(g, 0, V);
+  g.comp = 1;
+  const float sy = np_pairwise_sum(g, 0, V);
+  // _divide_by_count: true_divide(float32 total, int64 count) evaluated in float64
+  centroid[2 * i] = (float)((double)sx / (double)cntx);
+  centroid[2 * i + 1] = (float)((double)sy / (double)cnty);
+}
+
+}  // namespace
+
+extern "C" int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi,
+                              const float* height, int rows, int cols, const double* transform6, int mode,
+                              float* max_h, float* hxy, float* ndvi_stats, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(verts && ring_off && transform6 && rows > 0 && cols > 0);
+  TD_ARG(mode >= 0 && mode <= 2);
+  if (mode != kNdviOnly) TD_ARG(height && max_h && hxy);
+  if (mode != kHeightOnly) TD_ARG(ndvi && ndvi_stats);
+  Affine6 T{transform6[0], transform6[1], transform6[2], transform6[3], transform6[4], transform6[5]};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 256;                       // 8 crowns per CTA
+  const int blocks = td_div_up((long long)n * 32, threads);
+  switch (mode) {
+    case kCombined:
+      crown_stats_kernel<kCombined><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
+                                                                 hxy, ndvi_stats);
+      break;
+    case kHeightOnly:
+      crown_stats_kernel<kHeightOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T,
+                                                                   max_h, hxy, ndvi_stats);
+      break;
+    default:
+      crown_stats_kernel<kNdviOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
+                                                                 hxy, ndvi_stats);
+  }
+  TD_CHECK_LAUNCH("td_crown_stats");
+  return TD_OK;
+}
+
+extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(verts && ring_off && centroid);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* vmax = nullptr;
+  TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
+  TD_CUDA(cudaMemsetAsync(vmax, 0, sizeof(int), st));
+  max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, n, vmax);
+  centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, n, vmax, centroid);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(vmax, st);
+  if (e != cudaSuccess) { td_set_error("td_centroids: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}

@@ -1,0 +1,212 @@
+"""Torch-tensor wrappers over the C-ABI (device pointers + current stream in,
+caller-allocated outputs).  One function per kernel family of SURVEY.md §8a.
+
+Every function requires CUDA tensors and raises otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+M = 28  # Mask R-CNN ROI mask side
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.TreedetError("libtreedet needs CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.TreedetError("libtreedet needs contiguous tensors")
+    return t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype:
+        raise _lib.TreedetError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+# ----------------------------------------------------------------------------
+# P2  paste + threshold + pack
+# ----------------------------------------------------------------------------
+def paste_plan(boxes_net, inst_tile, tile_dims):
+    """boxes_net (N,4) f32 in network-input pixels, inst_tile (N,) i32, tile_dims
+    (T,4) i32 = [tile_h, tile_w, net_h, net_w].  Returns boxes_px (N,4) f32, win
+    (N,4) i32 = [x0, y0, w, h] (w = h = 0 for dropped instances), nwords (N,) i64."""
+    n = boxes_net.shape[0]
+    dev = boxes_net.device
+    _chk(boxes_net, torch.float32, "boxes_net"); _chk(inst_tile, torch.int32, "inst_tile")
+    _chk(tile_dims, torch.int32, "tile_dims")
+    boxes_px = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    win = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    nwords = torch.empty((n,), dtype=torch.int64, device=dev)
+    _lib.call("td_paste_plan", _ptr(boxes_net), _ptr(inst_tile), _ptr(tile_dims), n, tile_dims.shape[0],
+              _ptr(boxes_px), _ptr(win), _ptr(nwords), _stream())
+    return boxes_px, win, nwords
+
+
+def exclusive_offsets(counts):
+    """(N,) i64 counts -> (N+1,) i64 offsets (torch plumbing)."""
+    off = torch.zeros(counts.shape[0] + 1, dtype=torch.int64, device=counts.device)
+    torch.cumsum(counts, 0, out=off[1:])
+    return off
+
+
+def paste_threshold_pack(boxes_px, win, word_off, probs, threshold=0.5, total_words=None):
+    """Returns the packed 1-bit rasters (uint32 words viewed as int32 tensor)."""
+    n = boxes_px.shape[0]
+    if total_words is None:
+        total_words = int(word_off[-1].item())
+    bits = torch.empty((max(total_words, 1),), dtype=torch.int32, device=boxes_px.device)
+    _chk(probs, torch.float32, "probs")
+    _lib.call("td_paste_threshold_pack", _ptr(boxes_px), _ptr(win), _ptr(word_off), _ptr(probs), n,
+              float(threshold), _ptr(bits), _stream())
+    return bits
+
+
+def paste_values(boxes_px, win, probs):
+    """Pasted probabilities of every instance window (float32), for tolerance tests."""
+    n = boxes_px.shape[0]
+    npx = (win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64))
+    off = exclusive_offsets(npx)
+    vals = torch.empty((max(int(off[-1].item()), 1),), dtype=torch.float32, device=boxes_px.device)
+    _lib.call("td_paste_values", _ptr(boxes_px), _ptr(win), _ptr(off), _ptr(probs), n, _ptr(vals), _stream())
+    return vals, off
+
+
+# ----------------------------------------------------------------------------
+# P3  contours -> rings
+# ----------------------------------------------------------------------------
+class Rings:
+    """Ragged polygon rings on the device: ``verts`` (V,2) f64 CRS coordinates,
+    ``ring_off`` (R+1,) i64, ``ring_inst`` (R,) i32 index of the producing instance."""
+
+    def __init__(self, verts, ring_off, ring_inst):
+        self.verts, self.ring_off, self.ring_inst = verts, ring_off, ring_inst
+
+    def __len__(self):
+        return self.ring_off.shape[0] - 1
+
+
+def trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words=None):
+    """P3: packed rasters -> closed CRS rings in cv2.findContours order.
+
+    tile_tf (T,6) f64: the tile window transforms of the tiles JSON."""
+    n = win.shape[0]
+    dev = win.device
+    if total_words is None:
+        total_words = int(word_off[-1].item())
+    _chk(tile_tf, torch.float64, "tile_tf")
+    planes = torch.empty((2 * max(total_words, 1),), dtype=torch.int32, device=dev)
+    counts = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    _lib.call("td_trace_count", _ptr(bits), _ptr(win), _ptr(word_off), n, total_words, _ptr(planes), _ptr(counts),
+              _stream())
+    if n and int(counts[:, 0].min().item()) < 0:
+        raise _lib.TreedetError("td_trace_count: more than 65534 borders in one instance window")
+    c64 = counts.to(torch.int64)
+    cont_off = exclusive_offsets(c64[:, 0]); pts_off = exclusive_offsets(c64[:, 1])
+    ring_base = exclusive_offsets(c64[:, 2]); vert_base = exclusive_offsets(c64[:, 3])
+    px_off = exclusive_offsets(win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64))
+    totals = torch.stack([cont_off[-1], pts_off[-1], ring_base[-1], vert_base[-1], px_off[-1]]).cpu().tolist()
+    tc, tp, tr, tv, tpx = [int(v) for v in totals]
+    labels = torch.empty((max(tpx, 1),), dtype=torch.int16, device=dev)
+    ct_int = torch.empty((6 * max(tc, 1),), dtype=torch.int32, device=dev)
+    ct_hole = torch.empty((max(tc, 1),), dtype=torch.uint8, device=dev)
+    pts = torch.empty((2 * max(tp, 1),), dtype=torch.int16, device=dev)
+    ring_off = torch.empty((tr + 1,), dtype=torch.int64, device=dev)
+    ring_inst = torch.empty((max(tr, 1),), dtype=torch.int32, device=dev)[:tr]
+    verts = torch.empty((max(tv, 1), 2), dtype=torch.float64, device=dev)[:tv]
+    ring_off[tr] = tv
+    _lib.call("td_trace_emit", _ptr(bits), _ptr(win), _ptr(word_off), n, total_words, _ptr(planes), _ptr(labels),
+              _ptr(px_off), _ptr(cont_off), _ptr(pts_off), _ptr(ring_base), _ptr(vert_base), _ptr(ct_int),
+              _ptr(ct_hole), _ptr(pts), tc, _ptr(inst_tile), _ptr(tile_tf), _ptr(ring_off), ring_inst.data_ptr(),
+              verts.data_ptr(), _stream())
+    return Rings(verts, ring_off, ring_inst)
+
+
+# ----------------------------------------------------------------------------
+# P5  NDVI + decimation
+# ----------------------------------------------------------------------------
+def ndvi_decimate(rgbi, out_h, out_w):
+    """rgbi (bands>=4, H, W) uint8 -> NDVI (out_h, out_w) float32."""
+    _chk(rgbi, torch.uint8, "rgbi")
+    b, h, w = rgbi.shape
+    out = torch.empty((out_h, out_w), dtype=torch.float32, device=rgbi.device)
+    _lib.call("td_ndvi_decimate", _ptr(rgbi), b, h, w, out_h, out_w, _ptr(out), _stream())
+    return out
+
+
+def decimate_f32(band, out_h, out_w):
+    _chk(band, torch.float32, "band")
+    h, w = band.shape
+    out = torch.empty((out_h, out_w), dtype=torch.float32, device=band.device)
+    _lib.call("td_decimate_f32", _ptr(band), h, w, out_h, out_w, _ptr(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------
+# P6 / P8
+# ----------------------------------------------------------------------------
+def bbox_nms_ordered(bounds, conf, area, iou_threshold, area_threshold):
+    """bounds (N,4) f64, conf (N,) f64, area (N,) f64 -> removed (N,) uint8."""
+    n = bounds.shape[0]
+    _chk(bounds, torch.float64, "bounds"); _chk(conf, torch.float64, "conf"); _chk(area, torch.float64, "area")
+    removed = torch.empty((n,), dtype=torch.uint8, device=bounds.device)
+    _lib.call("td_bbox_nms_ordered", _ptr(bounds), _ptr(conf), _ptr(area), n, float(iou_threshold),
+              float(area_threshold), _ptr(removed), _stream())
+    return removed
+
+
+def containment(bounds32, threshold):
+    """bounds32 (N,4) f32 -> (ratio_max f32, is_contained u8, num_contained i32)."""
+    n = bounds32.shape[0]
+    _chk(bounds32, torch.float32, "bounds32")
+    dev = bounds32.device
+    ratio = torch.empty((n,), dtype=torch.float32, device=dev)
+    isc = torch.empty((n,), dtype=torch.uint8, device=dev)
+    num = torch.empty((n,), dtype=torch.int32, device=dev)
+    _lib.call("td_containment", _ptr(bounds32), n, float(threshold), _ptr(ratio), _ptr(isc), _ptr(num), _stream())
+    return ratio, isc, num
+
+
+# ----------------------------------------------------------------------------
+# P7
+# ----------------------------------------------------------------------------
+STATS_COMBINED, STATS_HEIGHT_ONLY, STATS_NDVI_ONLY = 0, 1, 2
+
+
+def crown_stats(verts, ring_off, ndvi, height, transform6, mode=STATS_COMBINED):
+    """verts (V,2) f64, ring_off (N+1,) i64; rasters (H,W) f32; transform6 = 6 floats
+    (a,b,c,d,e,f).  Returns dict of float32 tensors."""
+    n = ring_off.shape[0] - 1
+    _chk(verts, torch.float64, "verts"); _chk(ring_off, torch.int64, "ring_off")
+    dev = verts.device
+    ref = ndvi if mode != STATS_HEIGHT_ONLY else height
+    rows, cols = ref.shape
+    tf = torch.tensor(list(transform6)[:6], dtype=torch.float64)  # host: passed by value through a pointer
+    max_h = hxy = stats = None
+    if mode != STATS_NDVI_ONLY:
+        _chk(height, torch.float32, "height")
+        max_h = torch.empty((n,), dtype=torch.float32, device=dev)
+        hxy = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    if mode != STATS_HEIGHT_ONLY:
+        _chk(ndvi, torch.float32, "ndvi")
+        stats = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    _lib.call("td_crown_stats", _ptr(verts), _ptr(ring_off), n,
+              _ptr(ndvi) if mode != STATS_HEIGHT_ONLY else None,
+              _ptr(height) if mode != STATS_NDVI_ONLY else None,
+              rows, cols, tf.data_ptr(), mode, _ptr(max_h), _ptr(hxy), _ptr(stats), _stream())
+    return {"max_h": max_h, "hxy": hxy, "ndvi": stats}
+
+
+def centroids(verts, ring_off):
+    n = ring_off.shape[0] - 1
+    out = torch.empty((n, 2), dtype=torch.float32, device=verts.device)
+    _lib.call("td_centroids", _ptr(verts), _ptr(ring_off), n, _ptr(out), _stream())
+    return out
