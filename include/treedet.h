@@ -1,0 +1,167 @@
+/* libtreedet -- C-ABI of the B200-native crown pipeline (sm_100a).
+ *
+ * Drop-in boundary for the post-model path of Jonetz/TreeDetection.  The reference has
+ * no FFI of its own: the path is Python calling CuPy / detectron2 / rasterio / shapely
+ * (SURVEY.md section 8b).  Each entry point below names the reference function(s)
+ * (file:line under /root/reference) whose work it replaces; INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add at that call site.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the comment says "host";
+ *  - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream);
+ *    calls are asynchronous on that stream unless stated otherwise;
+ *  - outputs are caller allocated; temporary scratch comes from the stream-ordered
+ *    CUDA memory pool (cudaMallocAsync) and is released before returning; no global
+ *    state, so calls on different streams / devices are independent;
+ *  - return value: 0 = ok, <0 = error (TD_ERR_*), text via td_last_error() (thread local);
+ *  - ragged polygon rings: `verts` (V,2) float64 interleaved x,y + `ring_off` (R+1) int64;
+ *    rings are closed (first vertex repeated at the end);
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef TREEDET_H_
+#define TREEDET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TD_OK 0
+#define TD_ERR_CUDA (-1)
+#define TD_ERR_ARG (-2)
+#define TD_ERR_OVERFLOW (-3)
+#define TD_ERR_UNSUPPORTED (-4)
+
+int td_version(void);               /* 100 = 0.1.0 */
+const char* td_last_error(void);    /* host string, thread local */
+int td_device_sms(void);            /* SM count of the current device (148 on B200) */
+
+/* ---- P1: tile cut + normalise ------------------------------------------------------
+ * Replaces Predictor._process_tile (TreeDetection/prediction.py:159-176): rasterio.mask
+ * crop of the tile window, band reorder (2,1,0), optional 255*x/65535 for 16-bit data,
+ * detectron2 ResizeShortestEdge(800, 1333) (PIL bilinear for uint8), float32 CHW.
+ *   image      (bands, H, W) planar uint8 (elem_size 1) or uint16 (elem_size 2)
+ *   tile_win   (T,4) int32 [col_off, row_off, w, h]        (tiling.tile_grid)
+ *   tile_net   (T,2) int32 [net_h, net_w]                  (tiling.resize_shortest_edge)
+ *   out_off    (T+1) int64 float offsets of each tile's (3, net_h, net_w) block in `out`
+ *   rescale16  (T) uint8 out: 1 where the 16-bit branch was taken (max(band 1) > 255) */
+int td_tile_cut_normalize(const void* image, int elem_size, int bands, int H, int W, const int* tile_win,
+                          const int* tile_net, int n_tiles, const long long* out_off, float* out,
+                          unsigned char* rescale16, void* stream);
+
+/* ---- P2: mask paste + threshold + bit-pack -------------------------------------------
+ * Replaces detectron2 detector_postprocess + paste_masks_in_image + _do_paste_mask
+ * (entered at TreeDetection/prediction.py:181-183) and the identity resize + uint8 cast
+ * of prediction.py:222-229.
+ *   boxes_net (N,4) f32 xyxy in network-input pixels; inst_tile (N) i32;
+ *   tile_dims (T,4) i32 [tile_h, tile_w, net_h, net_w]
+ *   -> boxes_px (N,4) f32 (scaled, clipped), win (N,4) i32 [x0,y0,w,h] (0,0,0,0 when the
+ *      box is empty and the instance is dropped), nwords (N) i64 = ceil(w/32)*h      */
+int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst, int n_tiles,
+                  float* boxes_px, int* win, long long* nwords, void* stream);
+/*   word_off (N+1) i64 = exclusive scan of nwords; probs (N,28,28) f32 probabilities;
+ *   bits: packed 1-bit rasters, row-major, 32 pixels per uint32 (LSB = leftmost)       */
+int td_paste_threshold_pack(const float* boxes_px, const int* win, const long long* word_off, const float* probs,
+                            int n_inst, float threshold, uint32_t* bits, void* stream);
+/*   the pasted float32 probabilities themselves (tolerance tests): val_off = scan of w*h */
+int td_paste_values(const float* boxes_px, const int* win, const long long* val_off, const float* probs,
+                    int n_inst, float* vals, void* stream);
+
+/* ---- P3: border following -> CRS rings ---------------------------------------------------
+ * Replaces Predictor._process_and_save_single (TreeDetection/prediction.py:197-265:
+ * cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE), contour.size >= 8, closing point) and
+ * xy_gpu (TreeDetection/utilities.py:182-207).  Two passes (sizes are data dependent).
+ *   planes  scratch, 2*total_words uint32 (zeroed by the call)
+ *   counts  (N,4) i32 out: [borders, points, kept rings, ring vertices]; borders < 0 when
+ *           one window holds more than 65534 borders                                      */
+int td_trace_count(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
+                   long long total_words, uint32_t* planes, int* counts, void* stream);
+/*   labels (sum w*h) u16 scratch; px_off / cont_off / pts_off / ring_base / vert_base:
+ *   (N+1) i64 exclusive scans of w*h and of the four count columns; ct_int: 6*total_contours
+ *   i32 scratch; ct_hole: total_contours u8 scratch; pts: 2*total_points i16 scratch;
+ *   tile_tf (T,6) f64 window transforms.  Outputs: ring_off[0..R) (caller sets
+ *   ring_off[R] = V), ring_inst (R) i32 producing instance, verts (V,2) f64.
+ *   Ring order = tile-major instance order, then cv2's contour order.                     */
+int td_trace_emit(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
+                  long long total_words, uint32_t* planes, unsigned short* labels, const long long* px_off,
+                  const long long* cont_off, const long long* pts_off, const long long* ring_base,
+                  const long long* vert_base, int* ct_int, unsigned char* ct_hole, short* pts,
+                  long long total_contours, const int* inst_tile, const double* tile_tf, long long* ring_off,
+                  int* ring_inst, double* verts, void* stream);
+
+/* ---- P4 (+ the area of P9's head): simplify, tile box filter ---------------------------------
+ * Replaces process_prediction_file_sync (TreeDetection/helpers.py:419-476: shapely
+ * simplify(tol, preserve_topology=True) + sjoin "within" the shrunk tile box of
+ * box_make, helpers.py:280-303) and shape(geom).simplify(2).area
+ * (TreeDetection/postprocessing.py:747-754).
+ *   scratch 5*V i32 (kept-vertex index lists live at scratch[5*ring_off[r] ..]);
+ *   alive   (V/32 + R + 2) u32 scratch;
+ *   boxes (B,4) f64 + ring_box (R) i32, or both null (no filter);
+ *   out_count (R) i32 kept vertices; out_bounds (R,4) f64 / out_area (R) f64 / out_keep (R)
+ *   u8 may be null.  tolerance <= 0: no simplification (bounds / area of the ring itself). */
+int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance, int* scratch,
+                      uint32_t* alive, const double* boxes, const int* ring_box, int* out_count,
+                      double* out_bounds, double* out_area, unsigned char* out_keep, void* stream);
+/*   output ring q = input ring sel[q]; dst_off (n_out+1) i64; scratch = the index lists
+ *   above (copy kept vertices only) or null (copy whole rings)                           */
+int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
+                  const int* scratch, const long long* dst_off, double* out_verts, void* stream);
+
+/* ---- P5: decimated raster reads + NDVI ----------------------------------------------------
+ * Replaces the rasterio reads with out_shape + Resampling.bilinear in process_geojson
+ * (TreeDetection/postprocessing.py:780-800) and ndvi_array_from_rgbi / ndvi_index
+ * (TreeDetection/helpers.py:862-896).  rgbi (bands>=4, H, W) planar uint8.            */
+int td_ndvi_decimate(const unsigned char* rgbi, int bands, int in_h, int in_w, int out_h, int out_w,
+                     float* ndvi_out, void* stream);
+int td_decimate_f32(const float* src, int in_h, int in_w, int out_h, int out_w, float* out, void* stream);
+
+/* ---- P6: ordered bbox NMS -------------------------------------------------------------------
+ * Replaces filter_polygons_by_iou_and_area (TreeDetection/postprocessing.py:349-406) and
+ * calculate_iou (TreeDetection/utilities.py:112-144).  bounds (N,4) f64, conf / area (N)
+ * f64 (cast to float32 / float16 / float16 as the reference does); removed (N) u8.
+ * Synchronises the stream once (one 8-byte read back sizes the adjacency).            */
+int td_bbox_nms_ordered(const double* bounds, const double* conf, const double* area, int n,
+                        double iou_threshold, double area_threshold, unsigned char* removed, void* stream);
+
+/* ---- P7: per-crown raster statistics, centroids ----------------------------------------------
+ * Replaces get_metadata_within_polygon (TreeDetection/postprocessing.py:221-347; mode 0),
+ * get_height_within_polygon (:25-115; mode 1), get_ndvi_within_polygon (:117-219; mode 2),
+ * is_point_in_polygon_batch (TreeDetection/utilities.py:78-98) and get_centroids
+ * (utilities.py:163-180).  transform6: HOST pointer to (a,b,c,d,e,f).
+ *   max_h (N) f32, hxy (N,2) f32, ndvi_stats (N,4) f32 [min,max,mean,var]; -1 when empty. */
+int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi, const float* height,
+                   int rows, int cols, const double* transform6, int mode, float* max_h, float* hxy,
+                   float* ndvi_stats, void* stream);
+int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, void* stream);
+
+/* ---- P8: bbox containment ---------------------------------------------------------------------
+ * Replaces process_containment_features (TreeDetection/postprocessing.py:408-476).
+ * bounds32 (N,4) f32 -> ratio_max (N) f32, is_contained (N) u8, num_contained (N) i32.  */
+int td_containment(const float* bounds32, int n, double threshold, float* ratio_max, unsigned char* is_contained,
+                   int* num_contained, void* stream);
+
+/* ---- P9: selection + coordinate rounding ----------------------------------------------------
+ * Replaces the pre-selection and containment case analysis of process_features
+ * (TreeDetection/postprocessing.py:571-667), element_is_near_border
+ * (TreeDetection/helpers.py:501-522) and round_coordinates (utilities.py:146-161).
+ *   params: HOST pointer to 14 doubles [use_overlap, is_seam_image, left, bottom, right, top,
+ *   band_left, band_right, band_top, band_bottom, height_thr, ndvi_mean_thr, ndvi_var_thr, 0]
+ *   pre (N) i32: pre-selected flag; out_idx (N) i32: crown emitted by crown i, or -1.    */
+int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats, const double* area,
+                     const int* num_contained, const unsigned char* is_contained, int n, const double* params,
+                     int* pre, int* out_idx, void* stream);
+int td_round_coords(const double* in, long long n, double* out, void* stream);
+
+/* ---- P0a: seam strips ---------------------------------------------------------------------------
+ * Replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,
+ * TreeDetection/helpers.py:1023-1085): mosaic of an image with its right (axis 0) or lower
+ * (axis 1) neighbour, centre-cropped to strip_w x strip_h pixels, without building the mosaic.
+ *   a, b: (bands, H, W) planar rasters of elem_size bytes; out (bands, strip_h, strip_w).  */
+int td_seam_crop(const void* a, const void* b, int elem_size, int bands, int ha, int wa, int hb, int wb, int axis,
+                 int strip_w, int strip_h, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREEDET_H_ */

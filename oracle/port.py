@@ -507,3 +507,151 @@ def containment(bounds, threshold):
     isc[np.arange(n), np.arange(n)] = False
     num = isc.sum(axis=1)
     return ratio.max(axis=0), isc.any(axis=0), num
+
+
+# ============================================================================
+# stage drivers (the order of operations of the reference's own drivers)
+# ============================================================================
+
+
+def predict_stage(det, tiles, simplify_tolerance=0.2, shift=1, mask_threshold=0.5, paste="closed_form"):
+    """prediction.py:178-265 + helpers.py:419-554 for one image.
+
+    det: object with boxes_net, scores, probs, inst_tile, tile_dims (treedetection_b200.synth.Detections
+    layout); tiles: the tiles JSON dict in tile order.  Returns (rings, conf): the crown
+    table of ``geojson_predictions/<image>.gpkg`` in canonical order (tile order of the
+    tiles JSON, instance order = model output order, contour order = cv2)."""
+    tile_ids = list(tiles.keys())
+    rings_out, conf_out = [], []
+    paste_fn = paste_probs_closed_form if paste == "closed_form" else paste_probs
+    n = len(det.scores)
+    i = 0
+    for t, tid in enumerate(tile_ids):
+        th, tw, nh, nw = [int(v) for v in det.tile_dims[t]]
+        j = i
+        while j < n and det.inst_tile[j] == t:
+            j += 1
+        rings_t, scores_t = [], []
+        if j > i:
+            boxes, keep = scale_clip_boxes(det.boxes_net[i:j], (nh, nw), (th, tw))
+            tf = tiles[tid]["transform"]
+            for k in range(i, j):
+                if not keep[k - i]:
+                    continue
+                v, (x0, y0, x1, y1) = paste_fn(boxes[k - i], det.probs[k], th, tw)
+                mask = np.zeros((th, tw), dtype=bool)
+                mask[y0:y1, x0:x1] = v >= np.float32(mask_threshold)
+                for ring in mask_to_polygons(mask, tf):
+                    rings_t.append(ring)
+                    scores_t.append(float(det.scores[k]))
+        parts = [int(p) for p in tid.split("_")[-5:]]
+        box = tile_filter_box(parts[0], parts[1], parts[2], parts[3], shift)
+        ro, so = stitch_tile(rings_t, scores_t, box, simplify_tolerance)
+        rings_out.extend(ro)
+        conf_out.extend(so)
+        i = j
+    return rings_out, conf_out
+
+
+def near_border(b, bounds, eps):
+    """helpers.py:501-522."""
+    left, bottom, right, top = bounds
+    return (b[0] < left + eps) or (b[2] > right - eps) or (b[1] < bottom + eps) or (b[3] > top - eps)
+
+
+def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, height_transform, height_bounds,
+                 pixel_x, pixel_y, cfg):
+    """postprocessing.py:722-809 (process_geojson) + :478-720 (process_features), restated
+    on arrays.  ``cfg``: dict with the config.yml keys.  Returns a list of feature dicts
+    {poly_id, Confidence_score, Area, TreeHeight, Centroid, is_contained, num_contained,
+    coords} in output order, plus a debug dict."""
+    f32 = np.float32
+    # 1. confidence filter, ids, simplify(2) area, area range
+    feats = [(r, c) for r, c in zip(rings, conf) if c is not None and float(c) >= cfg["confidence_threshold"]]
+    areas = [geom.Polygon(r).simplify(2).area for r, _ in feats]
+    ids = list(range(len(feats)))
+    debug = {"area_after_conf": list(areas)}
+    if not feats:
+        return [], debug
+    keep = [i for i in ids if areas[i] >= cfg["area_threshold"]]
+    keep = [i for i in keep if areas[i] <= 1000]
+    debug["ids_after_area"] = list(keep)
+    if not keep:
+        return [], debug
+    bounds = {i: geom.Polygon(feats[i][0]).bounds for i in keep}
+    # 3. NMS
+    removed = nms_bbox([bounds[i] for i in keep], [feats[i][1] for i in keep], [areas[i] for i in keep],
+                       cfg["iou_threshold"], cfg["area_threshold"])
+    F = [i for i, r in zip(keep, removed) if not r]
+    debug["ids_after_nms"] = list(F)
+    if not F:
+        return [], debug
+    # 4. process_features
+    Frings = [feats[i][0] for i in F]
+    px32, py32 = pad_polygons(Frings)
+    cent = centroids(px32, py32)
+    t_eq = all(abs(a - b) < 1e-5 for a, b in zip(height_transform[:6], ndvi_transform[:6]))
+    b_eq = all(abs(a - b) < 1e-3 for a, b in zip(height_bounds, ndvi_bounds))
+    if t_eq and b_eq:
+        st = crown_stats_combined(px32, py32, ndvi32, height32, ndvi_transform)
+    else:
+        st = dict(crown_stats_height(px32, py32, height32, height_transform))
+        st.update(crown_stats_ndvi(px32, py32, ndvi32, ndvi_transform))
+    heights, mean_ndvi, var_ndvi = st["max_h"], st["ndvi_mean"], st["ndvi_var"]
+    debug.update(stats=st, centroid=cent, combined=bool(t_eq and b_eq))
+    pre = []
+    rows, cols = ndvi32.shape
+    for k, i in enumerate(F):
+        b = bounds[i]
+        if cfg["use_overlap"]:
+            if near_border(b, ndvi_bounds, 1.0):
+                continue
+            vmh = ((cfg["tile_height"] + 2 * cfg["buffer"]) * cfg["overlapping_tiles_height"]) * pixel_y
+            hmw = ((cfg["tile_width"] + 2 * cfg["buffer"]) * cfg["overlapping_tiles_width"]) * pixel_x
+            if not (rows == vmh or cols == hmw):
+                right_border = ndvi_bounds[2] - hmw / 2.0
+                left_border = ndvi_bounds[0] + hmw / 2.0
+                top_border = ndvi_bounds[3] - vmh / 2.0
+                bottom_border = ndvi_bounds[1] + vmh / 2.0
+                if top_border < b[1] or bottom_border > b[3] or left_border > b[2] or right_border < b[0]:
+                    continue
+        if heights[k] < f32(cfg["height_threshold"]) and heights[k] > f32(-1.0):
+            continue
+        if (mean_ndvi[k] < f32(cfg["ndvi_mean_threshold"]) or var_ndvi[k] > f32(cfg["ndvi_var_threshold"])) \
+                and mean_ndvi[k] > f32(-1.0):
+            continue
+        pre.append(k)
+    b32 = np.array([bounds[i] for i in F], dtype=np.float32)
+    ratio, is_c, num_c = containment(b32, cfg["containment_threshold"])
+    debug.update(pre=list(pre), is_contained=is_c, num_contained=num_c)
+    contained_idx = [k for k in range(len(F)) if is_c[k]]
+    selected = []
+    for rank, k in enumerate(pre):
+        nc = int(num_c[k])
+        if nc >= 3:
+            continue
+        elif nc == 2:
+            continue          # postprocessing.py:642-649: no branch appends
+        elif nc == 1:
+            o = contained_idx[0]
+            if abs(mean_ndvi[k] - mean_ndvi[o]) > f32(0.05):
+                if var_ndvi[rank] < var_ndvi[o]:
+                    selected.append(k)
+                else:
+                    selected.append(o)
+            elif areas[F[k]] > 0:
+                selected.append(k)
+        else:
+            selected.append(k)
+    out = []
+    for k in selected:
+        i = F[k]
+        ring = feats[i][0]
+        out.append({
+            "poly_id": str(i), "Confidence_score": feats[i][1], "Area": areas[i],
+            "TreeHeight": float(heights[k]), "Centroid": (float(cent[k][0]), float(cent[k][1])),
+            "Diameter": 2 * (areas[i] / np.pi) ** 0.5,
+            "is_contained": bool(is_c[k]), "num_contained": int(num_c[k]),
+            "coords": [(round(x * 1000) / 1000, round(y * 1000) / 1000) for (x, y) in ring],
+        })
+    return out, debug

@@ -57,4 +57,29 @@ int hs_find_contours(const uint8_t* mask, int h, int w, int* npts_out, int max_c
   return nc;
 }
 
+#ifdef HS_HAVE_SIMPLIFY
+// ring: n points (x, y interleaved), closed.  Returns the number of kept vertices and
+// writes their indices; *area = |signed area| of the simplified ring.
+int hs_simplify_ring(const double* xy, int n, double tol, int* keep_idx, double* area) {
+  std::vector<int> scratch(5 * (size_t)n + 8);
+  std::vector<uint32_t> alive((n + 31) / 32 + 1);
+  const td::P2* pts = reinterpret_cast<const td::P2*>(xy);
+  const int m = td::simplify_ring(pts, n, tol, scratch.data(), alive.data());
+  for (int k = 0; k < m; ++k) keep_idx[k] = scratch[k];
+  if (area) *area = std::fabs(td::ring_signed_area(m, [&](int k) { return pts[scratch[k]]; }));
+  return m;
+}
+
+int hs_orientation(double ax, double ay, double bx, double by, double cx, double cy) {
+  return td::orientation(ax, ay, bx, by, cx, cy);
+}
+int hs_orientation_exact(double ax, double ay, double bx, double by, double cx, double cy) {
+  return td::orientation_exact(ax, ay, bx, by, cx, cy);
+}
+int hs_interior_intersection(const double* p) {
+  td::P2 a{p[0], p[1]}, b{p[2], p[3]}, c{p[4], p[5]}, d{p[6], p[7]};
+  return td::interior_intersection(a, b, c, d) ? 1 : 0;
+}
+#endif
+
 }  // extern "C"

@@ -139,6 +139,7 @@ def test_crown_stats_all_modes(dev, px):
     ndvi = rng.uniform(-1, 1, (size, size)).astype(np.float32)
     height = np.round(rng.uniform(0, 30, (size, size)), 1).astype(np.float32)  # ties for the arg-max rule
     rings = _rings(rng, 60, left - 5, top - size * px - 5, size * px + 10)     # some crowns leave the raster
+    rings += _rings(rng, 3, left - 500, top + 300, 20)                           # entirely outside: empty sets
     px32, py32 = port.pad_polygons(rings)
     verts, off = _ragged(rings, dev)
     nd = torch.from_numpy(ndvi).to(dev); hd = torch.from_numpy(height).to(dev)

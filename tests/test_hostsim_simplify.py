@@ -1,0 +1,96 @@
+"""simplify_core.cuh (host build) against the GEOS-semantics oracle (oracle/geom.py):
+identical kept-vertex lists, bit-identical areas, identical predicates."""
+import ctypes as C
+from fractions import Fraction
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import geom, port
+from tests import hostsim
+
+
+def _lib():
+    lib = hostsim.load()
+    lib.hs_orientation.argtypes = [C.c_double] * 6
+    lib.hs_orientation_exact.argtypes = [C.c_double] * 6
+    lib.hs_simplify_ring.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def ours(ring, tol):
+    lib = _lib()
+    xy = np.ascontiguousarray(np.asarray(ring, dtype=np.float64).reshape(-1, 2))
+    keep = np.zeros(len(xy) + 1, dtype=np.int32)
+    area = C.c_double(0.0)
+    m = lib.hs_simplify_ring(xy.ctypes.data_as(C.c_void_p), len(xy), float(tol), keep.ctypes.data_as(C.c_void_p),
+                             C.byref(area))
+    return [tuple(xy[k]) for k in keep[:m]], area.value
+
+
+def test_orientation_exact_on_near_degenerate_inputs():
+    lib = _lib()
+    rng = np.random.default_rng(0)
+    n_fallback = 0
+    for _ in range(4000):
+        ax, ay = 412000 + rng.uniform(0, 100), 5318000 + rng.uniform(0, 100)
+        dx, dy = rng.uniform(-5, 5), rng.uniform(-5, 5)
+        t1, t2 = rng.uniform(0, 3, 2)
+        bx, by = ax + t1 * dx, ay + t1 * dy
+        cx, cy = ax + t2 * dx, ay + t2 * dy          # collinear up to rounding
+        if rng.uniform() < 0.3:
+            cx = np.nextafter(cx, np.inf)
+        ax, ay, bx, by, cx, cy = [float(v) for v in (ax, ay, bx, by, cx, cy)]
+        fa = [Fraction(v) for v in (ax, ay, bx, by, cx, cy)]
+        d = (fa[0] - fa[4]) * (fa[3] - fa[5]) - (fa[1] - fa[5]) * (fa[2] - fa[4])
+        want = (d > 0) - (d < 0)
+        assert lib.hs_orientation(ax, ay, bx, by, cx, cy) == want
+        assert lib.hs_orientation_exact(ax, ay, bx, by, cx, cy) == want
+        assert geom.orientation(ax, ay, bx, by, cx, cy) == want
+        n_fallback += 1
+    assert n_fallback
+
+
+def _contour_rings(seed, tf):
+    rng = np.random.default_rng(seed)
+    h, w = int(rng.integers(40, 160)), int(rng.integers(40, 160))
+    low = rng.normal(size=(h // 8 + 2, w // 8 + 2)).astype(np.float32)
+    f = cv2.resize(low, (w, h), interpolation=cv2.INTER_CUBIC)
+    return port.mask_to_polygons(f > 0.1, tf)
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("tol", [0.2, 2.0])
+def test_simplify_matches_oracle_on_contour_rings(seed, tol):
+    tf = (0.2, 0.0, 412030.0, 0.0, -0.2, 5318090.0)
+    rings = _contour_rings(seed, tf)
+    assert rings
+    for ring in rings:
+        want = geom.simplify_ring([tuple(p) for p in ring], tol)
+        got, area = ours(ring, tol)
+        assert got == want
+        assert area == abs(geom.ring_signed_area(want))
+
+
+def test_simplify_random_star_polygons():
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        k = int(rng.integers(4, 120))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+        rad = rng.uniform(0.5, 8.0, k)
+        ring = [(float(412000 + 50 + rad[j] * np.cos(ang[j])), float(5318000 + 50 + rad[j] * np.sin(ang[j])))
+                for j in range(k)]
+        ring.append(ring[0])
+        for tol in (0.2, 1.0, 2.0, 5.0):
+            want = geom.simplify_ring(ring, tol)
+            got, area = ours(ring, tol)
+            assert got == want
+            assert area == abs(geom.ring_signed_area(want))
+
+
+def test_simplify_keeps_minimum_ring():
+    sq = [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (0.0, 0.0)]
+    got, area = ours(sq, 10.0)
+    assert got == geom.simplify_ring(sq, 10.0)
+    assert len(got) >= 4 and area > 0

@@ -33,9 +33,8 @@ SIGNATURES = {
     "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
                            _p]),
     # P4 / P9 geometry
-    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p]),
-    "td_ring_bounds_area": (_i, [_p, _p, _i, _p, _p, _p]),
-    "td_box_filter": (_i, [_p, _p, _p, _i, _p, _p]),
+    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "td_take_rings": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     # P5
     "td_ndvi_decimate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "td_decimate_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),
@@ -46,7 +45,8 @@ SIGNATURES = {
     "td_crown_stats": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p]),
     "td_centroids": (_i, [_p, _p, _i, _p, _p]),
     # P9
-    "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "td_round_coords": (_i, [_p, _ll, _p, _p]),
     # P1
     "td_tile_cut_normalize": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     # P0a

@@ -1,0 +1,111 @@
+// P4 -- stitch geometry: simplify(tol, preserve_topology=True) + the tile box filter;
+// and the simplify(2) area of P9's head.
+//
+// Replaces process_prediction_file_sync (TreeDetection/helpers.py:419-476: shapely
+// Polygon -> simplify(simplify_tolerance) -> geopandas sjoin "within" against the tile
+// box shrunk by shift) and the area computation of process_geojson
+// (TreeDetection/postprocessing.py:747-754: shape(geom).simplify(2).area).
+// `within` a rectangle is envelope containment for an areal geometry (GEOS
+// RectangleContains), so the filter is four comparisons on the simplified ring's bounds.
+//
+// One thread simplifies one ring (the algorithm is a sequential stack machine; there are
+// ~10^5 rings per image).  Results are index lists into the input ring, so a second tiny
+// kernel (td_take_rings) gathers the surviving vertices once the caller has scanned the counts.
+#include "common.cuh"
+#include "simplify_core.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(64)
+simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
+                int* __restrict__ scratch, uint32_t* __restrict__ alive, const double* __restrict__ boxes,
+                const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
+                double* __restrict__ out_area, unsigned char* __restrict__ out_keep) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const long long v0 = ring_off[r];
+  const int len = (int)(ring_off[r + 1] - v0);
+  const td::P2* pts = reinterpret_cast<const td::P2*>(verts) + v0;
+  int* sc = scratch + 5 * v0;
+  // alive words: ring r owns (len + 31) / 32 words starting at v0 / 32 + r  (disjoint)
+  uint32_t* al = alive + (v0 >> 5) + r;
+  int m;
+  if (tol > 0.0 && len > 0) {
+    m = td::simplify_ring(pts, len, tol, sc, al);
+  } else {  // helpers.py:463: simplification is skipped for a non-positive tolerance
+    for (int k = 0; k < len; ++k) sc[k] = k;
+    m = len;
+  }
+  out_count[r] = m;
+  double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+  for (int k = 0; k < m; ++k) {
+    const td::P2 p = pts[sc[k]];
+    minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
+    miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
+  }
+  if (out_bounds) {
+    out_bounds[4 * r + 0] = minx; out_bounds[4 * r + 1] = miny;
+    out_bounds[4 * r + 2] = maxx; out_bounds[4 * r + 3] = maxy;
+  }
+  if (out_area) out_area[r] = fabs(td::ring_signed_area(m, [&](int k) { return pts[sc[k]]; }));
+  if (out_keep) {
+    bool keep = true;
+    if (boxes) {
+      const double* b = boxes + 4 * (size_t)ring_box[r];
+      keep = (m > 0) && minx >= b[0] && miny >= b[1] && maxx <= b[2] && maxy <= b[3];
+    }
+    out_keep[r] = keep ? 1 : 0;
+  }
+}
+
+// one warp per OUTPUT ring q: source ring sel[q]; with idx lists (scratch != null) only
+// the kept vertices are copied, otherwise the whole ring
+__global__ void take_rings_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
+                                  const long long* __restrict__ sel, int n_out, const int* __restrict__ scratch,
+                                  const long long* __restrict__ dst_off, double* __restrict__ out_verts) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n_out) return;
+  const long long r = sel[q];
+  const long long v0 = ring_off[r];
+  const long long o = dst_off[q];
+  const int cnt = (int)(dst_off[q + 1] - o);
+  const int* sc = scratch ? scratch + 5 * v0 : nullptr;
+  for (int k = lane; k < cnt; k += 32) {
+    const long long s = v0 + (sc ? sc[k] : k);
+    out_verts[2 * (o + k)] = verts[2 * s];
+    out_verts[2 * (o + k) + 1] = verts[2 * s + 1];
+  }
+}
+
+}  // namespace
+
+// scratch: 5 ints per input vertex; alive: (V / 32 + n + 1) uint32.
+// boxes / ring_box / out_bounds / out_area / out_keep may be null.
+extern "C" int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance,
+                                 int* scratch, uint32_t* alive, const double* boxes, const int* ring_box,
+                                 int* out_count, double* out_bounds, double* out_area, unsigned char* out_keep,
+                                 void* stream) {
+  TD_ARG(n_rings >= 0);
+  if (n_rings == 0) return TD_OK;
+  TD_ARG(verts && ring_off && scratch && alive && out_count);
+  TD_ARG((boxes == nullptr) == (ring_box == nullptr));
+  simplify_kernel<<<td_div_up(n_rings, 64), 64, 0, (cudaStream_t)stream>>>(
+      verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep);
+  TD_CHECK_LAUNCH("td_simplify_rings");
+  return TD_OK;
+}
+
+// out ring q = ring sel[q] of the input; dst_off (n_out + 1) = offsets of the output rings
+// (lengths = kept counts when `scratch` holds the index lists of td_simplify_rings, else
+// the source ring lengths).
+extern "C" int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
+                             const int* scratch, const long long* dst_off, double* out_verts, void* stream) {
+  TD_ARG(n_out >= 0);
+  if (n_out == 0) return TD_OK;
+  TD_ARG(verts && ring_off && sel && dst_off && out_verts);
+  take_rings_kernel<<<td_div_up((long long)n_out * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      verts, ring_off, sel, n_out, scratch, dst_off, out_verts);
+  TD_CHECK_LAUNCH("td_take_rings");
+  return TD_OK;
+}

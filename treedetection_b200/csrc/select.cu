@@ -1,0 +1,140 @@
+// P9 -- pre-selection (border / overlap-band / height / NDVI rules), the containment
+// case analysis and coordinate rounding of process_features
+// (TreeDetection/postprocessing.py:571-720), element_is_near_border
+// (TreeDetection/helpers.py:501-522) and round_coordinates (utilities.py:146-161).
+//
+// The reference walks Python lists with O(N) `features.index(...)` lookups per crown;
+// the decisions themselves are O(1) per crown once three global facts are known: the
+// crown's rank among the pre-selected ones, and the index of the globally FIRST
+// contained crown.  Quirks that decide the crown set are reproduced verbatim
+// (SURVEY.md §8a-P9): "contains two" is always dropped; "contains one" compares
+// against the globally first contained crown, reads var_ndvi at the crown's rank in
+// the pre-selected list, may emit the OTHER crown (duplicates possible), and its area
+// fallback compares against 0.
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+struct SelectParams {
+  int use_overlap;
+  int is_seam_image;         // rows / cols match a merged strip: no overlap-band discard
+  double left, bottom, right, top;                          // raster bounds (ndvi_bounds)
+  double band_left, band_right, band_top, band_bottom;      // overlap-band borders
+  float height_threshold, ndvi_mean_threshold, ndvi_var_threshold;
+};
+
+__global__ void preselect_kernel(const double* __restrict__ bounds, const float* __restrict__ max_h,
+                                 const float* __restrict__ ndvi_stats, int n, SelectParams P,
+                                 int* __restrict__ pre, int* __restrict__ first_contained,
+                                 const unsigned char* __restrict__ is_contained) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool keep = true;
+  const double bx0 = bounds[4 * i], by0 = bounds[4 * i + 1], bx1 = bounds[4 * i + 2], by1 = bounds[4 * i + 3];
+  if (P.use_overlap) {
+    const double eps = 1.0;
+    if (bx0 < P.left + eps || bx1 > P.right - eps || by0 < P.bottom + eps || by1 > P.top - eps) keep = false;
+    if (keep && !P.is_seam_image) {
+      const bool in_top = P.band_top < by0;
+      const bool in_bottom = P.band_bottom > by1;
+      const bool in_left = P.band_left > bx1;
+      const bool in_right = P.band_right < bx0;
+      if (in_top || in_bottom || in_left || in_right) keep = false;
+    }
+  }
+  const float h = max_h[i];
+  if (keep && h < P.height_threshold && h > -1.0f) keep = false;
+  const float mean = ndvi_stats[4 * i + 2], var = ndvi_stats[4 * i + 3];
+  if (keep && (mean < P.ndvi_mean_threshold || var > P.ndvi_var_threshold) && mean > -1.0f) keep = false;
+  pre[i] = keep ? 1 : 0;
+  if (is_contained[i]) atomicMin(first_contained, i);
+}
+
+__global__ void decide_kernel(const int* __restrict__ pre, const int* __restrict__ rank,
+                              const int* __restrict__ num_contained, const float* __restrict__ ndvi_stats,
+                              const double* __restrict__ area, const int* __restrict__ first_contained, int n,
+                              int* __restrict__ out_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int out = -1;
+  if (pre[i]) {
+    const int nc = num_contained[i];
+    if (nc >= 3 || nc == 2) {
+      out = -1;  // ">= 3": discarded; "== 2": no branch of the reference ever appends
+    } else if (nc == 1) {
+      const int o = *first_contained;  // exists: somebody is contained by crown i
+      if (o >= 0 && o < n) {
+        const float mi = ndvi_stats[4 * i + 2], mo = ndvi_stats[4 * o + 2];
+        if (fabsf(__fsub_rn(mi, mo)) > 0.05f) {
+          const float v_rank = ndvi_stats[4 * rank[i] + 3];  // var_ndvi[i] with i = rank in the pre-selected list
+          out = (v_rank < ndvi_stats[4 * o + 3]) ? i : o;
+        } else if (area[i] > 0.0) {
+          out = i;
+        }
+      }
+    } else {
+      out = i;
+    }
+  }
+  out_idx[i] = out;
+}
+
+__global__ void round_coords_kernel(const double* __restrict__ in, long long n, double* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __ddiv_rn(rint(__dmul_rn(in[i], 1000.0)), 1000.0);
+}
+
+}  // namespace
+
+// params: 14 doubles = [use_overlap, is_seam_image, left, bottom, right, top, band_left,
+//   band_right, band_top, band_bottom, height_threshold, ndvi_mean_threshold,
+//   ndvi_var_threshold, reserved] (host pointer)
+// out_idx[i]: index of the crown emitted at position i of the pre-selected walk, or -1.
+extern "C" int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats,
+                                const double* area, const int* num_contained, const unsigned char* is_contained,
+                                int n, const double* params, int* pre, int* out_idx, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(bounds && max_h && ndvi_stats && area && num_contained && is_contained && params && pre && out_idx);
+  cudaStream_t st = (cudaStream_t)stream;
+  SelectParams P;
+  P.use_overlap = params[0] != 0.0; P.is_seam_image = params[1] != 0.0;
+  P.left = params[2]; P.bottom = params[3]; P.right = params[4]; P.top = params[5];
+  P.band_left = params[6]; P.band_right = params[7]; P.band_top = params[8]; P.band_bottom = params[9];
+  // python scalars compared with float32 array elements: the comparison is in float32
+  P.height_threshold = (float)params[10]; P.ndvi_mean_threshold = (float)params[11];
+  P.ndvi_var_threshold = (float)params[12];
+  int* first = nullptr;
+  int* rank = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  TD_CUDA(cudaMallocAsync((void**)&first, sizeof(int), st));
+  TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
+  const int big = 0x7fffffff;
+  TD_CUDA(cudaMemcpyAsync(first, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+  const int blocks = td_div_up(n, 256);
+  preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, pre, first, is_contained);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pre, rank, n, st);
+  TD_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
+  cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pre, rank, n, st);
+  decide_kernel<<<blocks, 256, 0, st>>>(pre, rank, num_contained, ndvi_stats, area, first, n, out_idx);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(tmp, st);
+  cudaFreeAsync(rank, st);
+  cudaFreeAsync(first, st);
+  if (e != cudaSuccess) { td_set_error("td_select_crowns: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}
+
+// round(coord * 1000) / 1000 with round-half-even, float64 (utilities.py:146-161)
+extern "C" int td_round_coords(const double* in, long long n, double* out, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(in && out);
+  round_coords_kernel<<<td_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(in, n, out);
+  TD_CHECK_LAUNCH("td_round_coords");
+  return TD_OK;
+}

@@ -1,0 +1,250 @@
+// P4 / P9 core -- GEOS-semantics ring simplification, area and bounds.
+//
+// Restates the shapely calls the hot path makes:
+//     Polygon(coords).simplify(tol, preserve_topology=True)   TreeDetection/helpers.py:464
+//     shape(geom).simplify(2) ... .area                       TreeDetection/postprocessing.py:749-750
+//     polygon.bounds                                          postprocessing.py:497-503
+// i.e. GEOS TopologyPreservingSimplifier on a single closed ring (Douglas-Peucker with
+// a minimum ring size of 4 and the interior-intersection guard against the input and
+// output segment sets), Distance::pointToSegment, Area::ofRingSigned and the robust
+// LineIntersector with an exact orientation predicate.  shapely / GEOS are un-pinned
+// third-party dependencies of the reference and absent here: oracle/geom.py defines
+// the results and this file reproduces them bit for bit (IEEE double, no contraction;
+// the orientation predicate falls back to exact expansion arithmetic).
+//
+// Plain C++ so that tests/hostsim compiles the same code with g++.
+#pragma once
+#include <cmath>
+
+#include "common.cuh"
+
+namespace td {
+
+struct P2 {
+  double x, y;
+};
+
+// ---- exact orientation ------------------------------------------------------
+TD_HD inline void two_sum(double a, double b, double& s, double& e) {
+  s = a + b;
+  const double bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+TD_HD inline void two_prod(double a, double b, double& p, double& e) {
+  p = a * b;
+  e = fma(a, b, -p);
+}
+
+// adds the double v to the non-overlapping expansion e[0..n) (increasing magnitude)
+TD_HD inline int grow_expansion(double* e, int n, double v) {
+  double q = v;
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    double s, err;
+    two_sum(q, e[i], s, err);
+    if (err != 0.0) e[m++] = err;
+    q = s;
+  }
+  if (q != 0.0 || m == 0) e[m++] = q;
+  return m;
+}
+
+// sign of (ax-cx)(by-cy) - (ay-cy)(bx-cx) evaluated exactly on the double inputs
+TD_HD inline int orientation_exact(double ax, double ay, double bx, double by, double cx, double cy) {
+  // = ax*by - ax*cy - cx*by - ay*bx + ay*cx + cy*bx   (cx*cy cancels)
+  const double pa[6] = {ax, -ax, -cx, -ay, ay, cy};
+  const double pb[6] = {by, cy, by, bx, cx, bx};
+  double e[16];
+  int n = 0;
+  for (int k = 0; k < 6; ++k) {
+    double p, err;
+    two_prod(pa[k], pb[k], p, err);
+    n = grow_expansion(e, n, err);
+    n = grow_expansion(e, n, p);
+  }
+  const double top = e[n - 1];
+  return (top > 0.0) - (top < 0.0);
+}
+
+TD_HD inline int orientation(double ax, double ay, double bx, double by, double cx, double cy) {
+  const double detleft = (ax - cx) * (by - cy);
+  const double detright = (ay - cy) * (bx - cx);
+  const double det = detleft - detright;
+  double detsum;
+  if (detleft > 0.0) {
+    if (detright <= 0.0) return (det > 0.0) - (det < 0.0);
+    detsum = detleft + detright;
+  } else if (detleft < 0.0) {
+    if (detright >= 0.0) return (det > 0.0) - (det < 0.0);
+    detsum = -detleft - detright;
+  } else {
+    return (det > 0.0) - (det < 0.0);
+  }
+  const double errbound = 3.3306690738754716e-16 * detsum;
+  if (det >= errbound || -det >= errbound) return (det > 0.0) - (det < 0.0);
+  return orientation_exact(ax, ay, bx, by, cx, cy);
+}
+
+// ---- robust segment intersection: "is there an interior intersection" --------
+TD_HD inline bool env_has_pt(const P2& p1, const P2& p2, const P2& q) {
+  return q.x >= fmin(p1.x, p2.x) && q.x <= fmax(p1.x, p2.x) && q.y >= fmin(p1.y, p2.y) && q.y <= fmax(p1.y, p2.y);
+}
+TD_HD inline bool env_overlap(const P2& p1, const P2& p2, const P2& q1, const P2& q2) {
+  double minq = fmin(q1.x, q2.x), maxq = fmax(q1.x, q2.x);
+  double minp = fmin(p1.x, p2.x), maxp = fmax(p1.x, p2.x);
+  if (minp > maxq || maxp < minq) return false;
+  minq = fmin(q1.y, q2.y); maxq = fmax(q1.y, q2.y);
+  minp = fmin(p1.y, p2.y); maxp = fmax(p1.y, p2.y);
+  if (minp > maxq || maxp < minq) return false;
+  return true;
+}
+TD_HD inline bool same(const P2& a, const P2& b) { return a.x == b.x && a.y == b.y; }
+
+// an intersection point ip is "interior" if it is not an endpoint of both segments
+TD_HD inline bool ip_interior(const P2& ip, const P2& p1, const P2& p2, const P2& q1, const P2& q2) {
+  if (!(same(ip, p1) || same(ip, p2))) return true;
+  if (!(same(ip, q1) || same(ip, q2))) return true;
+  return false;
+}
+
+TD_HD inline bool interior_intersection(const P2& p1, const P2& p2, const P2& q1, const P2& q2) {
+  if (!env_overlap(p1, p2, q1, q2)) return false;
+  const int Pq1 = orientation(p1.x, p1.y, p2.x, p2.y, q1.x, q1.y);
+  const int Pq2 = orientation(p1.x, p1.y, p2.x, p2.y, q2.x, q2.y);
+  if ((Pq1 > 0 && Pq2 > 0) || (Pq1 < 0 && Pq2 < 0)) return false;
+  const int Qp1 = orientation(q1.x, q1.y, q2.x, q2.y, p1.x, p1.y);
+  const int Qp2 = orientation(q1.x, q1.y, q2.x, q2.y, p2.x, p2.y);
+  if ((Qp1 > 0 && Qp2 > 0) || (Qp1 < 0 && Qp2 < 0)) return false;
+  if (Pq1 == 0 && Pq2 == 0 && Qp1 == 0 && Qp2 == 0) {
+    // collinear: up to two intersection points
+    const bool a = env_has_pt(p1, p2, q1), b = env_has_pt(p1, p2, q2);
+    const bool c = env_has_pt(q1, q2, p1), d = env_has_pt(q1, q2, p2);
+    P2 i0, i1;
+    int n = 0;
+    if (a && b) { i0 = q1; i1 = q2; n = 2; }
+    else if (c && d) { i0 = p1; i1 = p2; n = 2; }
+    else if (a && c) { i0 = q1; i1 = p1; n = (same(q1, p1) && !b && !d) ? 1 : 2; }
+    else if (a && d) { i0 = q1; i1 = p2; n = (same(q1, p2) && !b && !c) ? 1 : 2; }
+    else if (b && c) { i0 = q2; i1 = p1; n = (same(q2, p1) && !a && !d) ? 1 : 2; }
+    else if (b && d) { i0 = q2; i1 = p2; n = (same(q2, p2) && !a && !c) ? 1 : 2; }
+    if (n >= 1 && ip_interior(i0, p1, p2, q1, q2)) return true;
+    if (n >= 2 && ip_interior(i1, p1, p2, q1, q2)) return true;
+    return false;
+  }
+  if (Pq1 == 0 || Pq2 == 0 || Qp1 == 0 || Qp2 == 0) {
+    P2 ip;
+    if (same(p1, q1) || same(p1, q2)) ip = p1;
+    else if (same(p2, q1) || same(p2, q2)) ip = p2;
+    else if (Pq1 == 0) ip = q1;
+    else if (Pq2 == 0) ip = q2;
+    else if (Qp1 == 0) ip = p1;
+    else ip = p2;
+    return ip_interior(ip, p1, p2, q1, q2);
+  }
+  return true;  // proper crossing
+}
+
+TD_HD inline double point_segment_distance(const P2& p, const P2& A, const P2& B) {
+  if (A.x == B.x && A.y == B.y) {
+    const double dx = p.x - A.x, dy = p.y - A.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  const double len2 = (B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y);
+  const double r = ((p.x - A.x) * (B.x - A.x) + (p.y - A.y) * (B.y - A.y)) / len2;
+  if (r <= 0.0) {
+    const double dx = p.x - A.x, dy = p.y - A.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  if (r >= 1.0) {
+    const double dx = p.x - B.x, dy = p.y - B.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  const double s = ((A.y - p.y) * (B.x - A.x) - (A.x - p.x) * (B.y - A.y)) / len2;
+  return fabs(s) * sqrt(len2);
+}
+
+// ---- TopologyPreservingSimplifier on one closed ring ---------------------------
+// pts[0..n) with pts[0] == pts[n-1].  scratch: 5 * n ints.  Writes the indices of the
+// kept vertices (including the closing one) to res[0..m) and returns m.
+//   scratch layout: res[n] | flat[n] | stack[3n]   (flat[k] = 1 when result segment k
+//   is a flattened section, i.e. a member of the output segment index)
+//   alive: n bits in (n + 31) / 32 words (input segment k = pts[k], pts[k+1] still indexed)
+TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, uint32_t* alive) {
+  if (n <= 0) return 0;
+  int* res = scratch;
+  int* flat = scratch + n;
+  int* stack = scratch + 2 * n;
+  const int nseg = n - 1;
+  for (int k = 0; k < (n + 31) / 32; ++k) alive[k] = 0xffffffffu;
+  int m = 0;        // number of result segments; res[k], res[k+1] are its ends
+  int sp = 0;
+  stack[0] = 0; stack[1] = n - 1; stack[2] = 0;
+  sp = 1;
+  const int min_size = 4;
+  while (sp > 0) {
+    --sp;
+    const int i = stack[3 * sp], j = stack[3 * sp + 1];
+    const int depth = stack[3 * sp + 2] + 1;
+    if (i + 1 == j) {
+      res[m] = i; flat[m] = 0; ++m;
+      continue;
+    }
+    bool valid = true;
+    const int rsize = m == 0 ? 0 : m + 1;
+    if (rsize < min_size && depth + 1 < min_size) valid = false;
+    double maxd = -1.0;
+    int far = i;
+    const P2 A = pts[i], B = pts[j];
+    for (int k = i + 1; k < j; ++k) {
+      const double d = point_segment_distance(pts[k], A, B);
+      if (d > maxd) { maxd = d; far = k; }
+    }
+    if (maxd > tol) valid = false;
+    if (valid) {
+      bool bad = false;
+      for (int k = 0; k < m && !bad; ++k)
+        if (flat[k]) bad = interior_intersection(pts[res[k]], pts[flat[k] - 1], A, B);
+      for (int k = 0; k < nseg && !bad; ++k) {
+        if (!((alive[k >> 5] >> (k & 31)) & 1u)) continue;
+        if (k >= i && k < j) continue;
+        bad = interior_intersection(pts[k], pts[k + 1], A, B);
+      }
+      if (bad) valid = false;
+    }
+    if (valid) {
+      for (int k = i; k < j; ++k) alive[k >> 5] &= ~(1u << (k & 31));
+      res[m] = i; flat[m] = j + 1; ++m;   // flat stores end index + 1
+      continue;
+    }
+    // right section is processed second
+    stack[3 * sp] = far; stack[3 * sp + 1] = j; stack[3 * sp + 2] = depth; ++sp;
+    stack[3 * sp] = i; stack[3 * sp + 1] = far; stack[3 * sp + 2] = depth; ++sp;
+  }
+  res[m] = n - 1;
+  return m + 1;
+}
+
+// GEOS Area::ofRingSigned via an index accessor (so that it can run on the
+// simplified index list without materialising the ring)
+template <typename Get>
+TD_HD inline double ring_signed_area(int n, Get get) {
+  if (n < 3) return 0.0;
+  const P2 first = get(0);
+  const double x0 = first.x;
+  double p1y = first.y;
+  P2 q = get(1);
+  double p2x = q.x - x0, p2y = q.y;
+  double s = 0.0;
+  for (int i = 1; i < n - 1; ++i) {
+    const double p0y = p1y;
+    const double p1x = p2x;
+    p1y = p2y;
+    q = get(i + 1);
+    p2x = q.x - x0;
+    p2y = q.y;
+    s += p1x * (p0y - p2y);
+  }
+  return s / 2.0;
+}
+
+}  // namespace td

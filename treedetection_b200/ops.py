@@ -210,3 +210,71 @@ def centroids(verts, ring_off):
     out = torch.empty((n, 2), dtype=torch.float32, device=verts.device)
     _lib.call("td_centroids", _ptr(verts), _ptr(ring_off), n, _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------
+# P4 / P9 geometry
+# ----------------------------------------------------------------------------
+def simplify_rings(verts, ring_off, tolerance, boxes=None, ring_box=None, want_bounds=True, want_area=False):
+    """GEOS-semantics simplify(tol, preserve_topology=True) of every ring.
+
+    Returns dict(count i32 (R,), bounds f64 (R,4) of the simplified ring, area f64 (R,),
+    keep u8 (R,) = simplified ring within boxes[ring_box] (all ones without boxes),
+    scratch = kept-vertex index lists for :func:`take_rings`)."""
+    n = ring_off.shape[0] - 1
+    dev = verts.device
+    nv = verts.shape[0]
+    _chk(verts, torch.float64, "verts"); _chk(ring_off, torch.int64, "ring_off")
+    scratch = torch.empty((5 * max(nv, 1),), dtype=torch.int32, device=dev)
+    alive = torch.empty((nv // 32 + n + 2,), dtype=torch.int32, device=dev)
+    count = torch.empty((n,), dtype=torch.int32, device=dev)
+    bounds = torch.empty((n, 4), dtype=torch.float64, device=dev) if want_bounds else None
+    area = torch.empty((n,), dtype=torch.float64, device=dev) if want_area else None
+    keep = torch.empty((n,), dtype=torch.uint8, device=dev)
+    if boxes is not None:
+        _chk(boxes, torch.float64, "boxes"); _chk(ring_box, torch.int32, "ring_box")
+    _lib.call("td_simplify_rings", _ptr(verts), _ptr(ring_off), n, float(tolerance), _ptr(scratch), _ptr(alive),
+              _ptr(boxes), _ptr(ring_box), _ptr(count), _ptr(bounds), _ptr(area), _ptr(keep), _stream())
+    return {"count": count, "bounds": bounds, "area": area, "keep": keep, "scratch": scratch}
+
+
+def take_rings(verts, ring_off, sel, scratch=None, count=None):
+    """Rings ``sel`` (i64 indices) of a ragged ring set -> (verts, ring_off) of the subset.
+    With ``scratch``/``count`` from :func:`simplify_rings` only the kept vertices are copied."""
+    dev = verts.device
+    sel = sel.to(torch.int64).contiguous()
+    if count is not None:
+        lens = count.to(torch.int64)[sel]
+    else:
+        lens = (ring_off[1:] - ring_off[:-1])[sel]
+    dst_off = exclusive_offsets(lens)
+    total = int(dst_off[-1].item())
+    out = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)[:total]
+    _lib.call("td_take_rings", _ptr(verts), _ptr(ring_off), _ptr(sel), sel.shape[0], _ptr(scratch), _ptr(dst_off),
+              out.data_ptr(), _stream())
+    return out, dst_off
+
+
+# ----------------------------------------------------------------------------
+# P9 selection
+# ----------------------------------------------------------------------------
+def select_crowns(bounds, max_h, ndvi_stats, area, num_contained, is_contained, params):
+    """params: the 14 doubles documented at td_select_crowns.  Returns (pre i32 (N,),
+    out_idx i32 (N,)): out_idx[i] = crown emitted by pre-selected crown i, or -1."""
+    n = bounds.shape[0]
+    dev = bounds.device
+    _chk(bounds, torch.float64, "bounds"); _chk(max_h, torch.float32, "max_h")
+    _chk(ndvi_stats, torch.float32, "ndvi_stats"); _chk(area, torch.float64, "area")
+    _chk(num_contained, torch.int32, "num_contained"); _chk(is_contained, torch.uint8, "is_contained")
+    pre = torch.empty((n,), dtype=torch.int32, device=dev)
+    out_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    p = torch.tensor([float(v) for v in params] + [0.0] * (14 - len(params)), dtype=torch.float64)
+    _lib.call("td_select_crowns", _ptr(bounds), _ptr(max_h), _ptr(ndvi_stats), _ptr(area), _ptr(num_contained),
+              _ptr(is_contained), n, p.data_ptr(), _ptr(pre), _ptr(out_idx), _stream())
+    return pre, out_idx
+
+
+def round_coords(verts):
+    out = torch.empty_like(verts)
+    _lib.call("td_round_coords", _ptr(verts), verts.numel(), _ptr(out), _stream())
+    return out

@@ -1,0 +1,221 @@
+"""Device-resident crown pipeline for one image: P2 -> P3 -> P4 (predict side) and
+P5 -> P9 (post-processing side), composed from the C-ABI kernels in :mod:`ops`.
+
+Stage boundaries mirror the reference's on-disk artefacts:
+
+* ``predict_stage``   = ``Predictor._process_and_save_single`` + ``process_and_stitch_predictions``
+  (TreeDetection/prediction.py:197-265, helpers.py:419-600): raw ROI-head outputs ->
+  the crown table of ``geojson_predictions/<image>.gpkg`` (rings + Confidence_score).
+* ``postprocess_stage`` = ``process_geojson`` + ``process_features``
+  (TreeDetection/postprocessing.py:722-809, 478-720): crown table + rasters ->
+  the features of ``processed_<image>.gpkg``.
+
+Everything stays on the GPU between the two; only sizes needed for allocation are read
+back.  PyTorch is used for device memory, prefix sums and boolean compaction.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+from . import geo, ops
+
+
+@dataclass
+class PipelineParams:
+    """The subset of the reference's config.yml schema the path reads
+    (TreeDetection/config.py:182-233, example/config.yml)."""
+    tile_width: float = 50
+    tile_height: float = 50
+    buffer: float = 20
+    use_overlap: bool = True
+    overlapping_tiles_width: int = 3
+    overlapping_tiles_height: int = 3
+    confidence_threshold: float = 0.3
+    containment_threshold: float = 0.75
+    height_threshold: float = 3
+    ndvi_mean_threshold: float = 0.1
+    ndvi_var_threshold: float = 0.1
+    iou_threshold: float = 0.6
+    area_threshold: float = 1
+    ndvi_scaling_factor: float = 0.2
+    height_scaling_factor: float = 1.0
+    simplify_tolerance: float = 0.2
+    shift: int = 1                       # detection.py:240
+    mask_threshold: float = 0.5          # detectron2 ROI_HEADS mask threshold
+
+    @classmethod
+    def from_config(cls, config: dict):
+        names = cls.__dataclass_fields__.keys()
+        return cls(**{k: config[k] for k in names if k in config})
+
+
+@dataclass
+class CrownTable:
+    """``geojson_predictions/<image>.gpkg`` on the device: ragged rings + confidence."""
+    verts: torch.Tensor      # (V, 2) f64
+    ring_off: torch.Tensor   # (R + 1,) i64
+    conf: torch.Tensor       # (R,) f64  (float(score) of a float32 score)
+
+    def __len__(self):
+        return self.ring_off.shape[0] - 1
+
+
+@dataclass
+class Features:
+    """``processed_<image>.gpkg`` on the device (schema postprocessing.py:904-919)."""
+    verts: torch.Tensor          # (V, 2) f64, rounded to 3 decimals
+    ring_off: torch.Tensor       # (K + 1,) i64
+    poly_id: torch.Tensor        # (K,) i64
+    conf: torch.Tensor           # (K,) f64
+    area: torch.Tensor           # (K,) f64
+    tree_height: torch.Tensor    # (K,) f32
+    centroid: torch.Tensor       # (K, 2) f32
+    is_contained: torch.Tensor   # (K,) u8
+    num_contained: torch.Tensor  # (K,) i32
+    extras: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return self.ring_off.shape[0] - 1
+
+
+def tile_tables(tiles: dict, device):
+    """Device tables of the tiles JSON: window transforms (T,6) f64 and the stitch
+    filter boxes (T,4) f64 of helpers.py:265-303 (values parsed from the tile id as
+    integers; ``width`` is used for both axes)."""
+    tfs, boxes = [], []
+    for tid, meta in tiles.items():
+        tfs.append(list(meta["transform"][:6]))
+        parts = [int(p) for p in tid.split("_")[-5:]]
+        minx, miny, width, buf = parts[0], parts[1], parts[2], parts[3]
+        boxes.append((minx, miny, width, buf))
+    tile_tf = torch.tensor(tfs, dtype=torch.float64, device=device).reshape(-1, 6)
+    return tile_tf, boxes
+
+
+def filter_boxes(boxes_int, shift, device):
+    rows = [[minx - buf + shift, miny - buf + shift, minx + width + buf - shift, miny + width + buf - shift]
+            for (minx, miny, width, buf) in boxes_int]
+    return torch.tensor(rows, dtype=torch.float64, device=device).reshape(-1, 4)
+
+
+def predict_stage(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams):
+    """P2 + P3 + P4.  All arguments are device tensors (see :mod:`synth` for layouts)."""
+    boxes_px, win, nwords = ops.paste_plan(boxes_net, inst_tile, tile_dims)
+    word_off = ops.exclusive_offsets(nwords)
+    total_words = int(word_off[-1].item())
+    bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, total_words)
+    rings = ops.trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words)
+    n_rings = len(rings)
+    dev = boxes_net.device
+    if n_rings == 0:
+        return CrownTable(torch.zeros((0, 2), dtype=torch.float64, device=dev),
+                          torch.zeros((1,), dtype=torch.int64, device=dev),
+                          torch.zeros((0,), dtype=torch.float64, device=dev))
+    ring_tile = inst_tile[rings.ring_inst.long()].contiguous()
+    simp = ops.simplify_rings(rings.verts, rings.ring_off, p.simplify_tolerance, tile_boxes, ring_tile,
+                              want_bounds=False)
+    sel = torch.nonzero(simp["keep"]).flatten()
+    verts, ring_off = ops.take_rings(rings.verts, rings.ring_off, sel, simp["scratch"], simp["count"])
+    conf = scores[rings.ring_inst.long()[sel]].to(torch.float64)
+    return CrownTable(verts, ring_off, conf)
+
+
+def raster_stage(rgbi, rgbi_transform, ndsm, ndsm_transform, p: PipelineParams):
+    """P5: decimated reads + NDVI (postprocessing.py:780-800).  rgbi (4,H,W) u8,
+    ndsm (h,w) f32 on the device; transforms are 6-tuples."""
+    _, H, W = rgbi.shape
+    oh, ow = int(H * p.ndvi_scaling_factor), int(W * p.ndvi_scaling_factor)
+    ndvi = ops.ndvi_decimate(rgbi, oh, ow)
+    ndvi_tf = geo.compose(rgbi_transform, geo.scale(W / ow, H / oh))
+    ndvi_bounds = geo.raster_bounds(rgbi_transform, W, H)
+    h, w = ndsm.shape
+    hh, hw = int(h * p.height_scaling_factor), int(w * p.height_scaling_factor)
+    height = ops.decimate_f32(ndsm, hh, hw) if (hh, hw) != (h, w) else ndsm
+    height_tf = geo.compose(ndsm_transform, geo.scale(w / hw, h / hh))
+    height_bounds = geo.raster_bounds(ndsm_transform, w, h)
+    return {"ndvi": ndvi, "ndvi_transform": ndvi_tf, "ndvi_bounds": ndvi_bounds,
+            "height": height, "height_transform": height_tf, "height_bounds": height_bounds,
+            "pixel_x": abs(rgbi_transform[0]), "pixel_y": abs(rgbi_transform[4])}
+
+
+def _similar_bounds(a, b, tol=1e-3):
+    return all(abs(x - y) < tol for x, y in zip(a, b))
+
+
+def select_params(p: PipelineParams, ndvi_shape, ndvi_bounds, pixel_x, pixel_y):
+    """Overlap-band geometry of process_features (postprocessing.py:580-600)."""
+    rows, cols = ndvi_shape
+    vmh = ((p.tile_height + 2 * p.buffer) * p.overlapping_tiles_height) * pixel_y
+    hmw = ((p.tile_width + 2 * p.buffer) * p.overlapping_tiles_width) * pixel_x
+    is_seam = (rows == vmh) or (cols == hmw)
+    b = ndvi_bounds
+    return [1.0 if p.use_overlap else 0.0, 1.0 if is_seam else 0.0, b.left, b.bottom, b.right, b.top,
+            b.left + hmw / 2.0, b.right - hmw / 2.0, b.top - vmh / 2.0, b.bottom + vmh / 2.0,
+            float(p.height_threshold), float(p.ndvi_mean_threshold), float(p.ndvi_var_threshold)]
+
+
+def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_debug=False):
+    """P9 head, P6, P7, P8, P9 selection + attributes."""
+    dev = table.verts.device
+    extras = {}
+
+    def empty():
+        z = lambda dt, *s: torch.zeros(s, dtype=dt, device=dev)
+        return Features(z(torch.float64, 0, 2), z(torch.int64, 1), z(torch.int64, 0), z(torch.float64, 0),
+                        z(torch.float64, 0), z(torch.float32, 0), z(torch.float32, 0, 2), z(torch.uint8, 0),
+                        z(torch.int32, 0), extras)
+
+    # 1. confidence filter; poly_id = enumeration index after it (postprocessing.py:739-754)
+    sel0 = torch.nonzero(table.conf >= p.confidence_threshold).flatten()
+    if sel0.numel() == 0:
+        return empty()
+    verts0, off0 = ops.take_rings(table.verts, table.ring_off, sel0)
+    conf0 = table.conf[sel0]
+    # 2. area of simplify(2), bounds of the ORIGINAL ring
+    s2 = ops.simplify_rings(verts0, off0, 2.0, want_bounds=False, want_area=True)
+    area0 = s2["area"]
+    sel1 = torch.nonzero((area0 >= p.area_threshold) & (area0 <= 1000)).flatten()
+    if sel1.numel() == 0:
+        return empty()
+    verts1, off1 = ops.take_rings(verts0, off0, sel1)
+    conf1, area1, pid1 = conf0[sel1], area0[sel1].contiguous(), sel1
+    b1 = ops.simplify_rings(verts1, off1, 0.0, want_bounds=True)["bounds"]   # tolerance 0: plain bounds
+    # 3. ordered bbox NMS (P6)
+    removed = ops.bbox_nms_ordered(b1, conf1.contiguous(), area1, p.iou_threshold, p.area_threshold)
+    sel2 = torch.nonzero(removed == 0).flatten()
+    verts2, off2 = ops.take_rings(verts1, off1, sel2)
+    conf2, area2, pid2, b2 = conf1[sel2], area1[sel2].contiguous(), pid1[sel2], b1[sel2].contiguous()
+    n2 = sel2.numel()
+    if keep_debug:
+        extras.update(area0=area0, removed=removed, pid_after_area=pid1, pid_after_nms=pid2)
+    if n2 == 0:
+        return empty()
+    # 4. statistics (P7) + centroids
+    cent = ops.centroids(verts2, off2)
+    combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
+        _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
+    if combined:
+        st = ops.crown_stats(verts2, off2, rasters["ndvi"], rasters["height"], rasters["ndvi_transform"],
+                             ops.STATS_COMBINED)
+        max_h, hxy, nst = st["max_h"], st["hxy"], st["ndvi"]
+    else:
+        sh = ops.crown_stats(verts2, off2, None, rasters["height"], rasters["height_transform"], ops.STATS_HEIGHT_ONLY)
+        sn = ops.crown_stats(verts2, off2, rasters["ndvi"], None, rasters["ndvi_transform"], ops.STATS_NDVI_ONLY)
+        max_h, hxy, nst = sh["max_h"], sh["hxy"], sn["ndvi"]
+    # 5. containment (P8) on float32 bounds of ALL post-NMS crowns
+    ratio, isc, num = ops.containment(b2.to(torch.float32).contiguous(), p.containment_threshold)
+    # 6. selection (P9)
+    sp = select_params(p, tuple(rasters["ndvi"].shape), rasters["ndvi_bounds"], rasters["pixel_x"], rasters["pixel_y"])
+    pre, out_idx = ops.select_crowns(b2, max_h, nst, area2, num, isc, sp)
+    final = out_idx[out_idx >= 0].long()
+    if keep_debug:
+        extras.update(max_h=max_h, hxy=hxy, ndvi_stats=nst, centroid=cent, is_contained=isc, num_contained=num,
+                      containment_ratio=ratio, pre=pre, out_idx=out_idx, combined=combined)
+    if final.numel() == 0:
+        return empty()
+    vf, of = ops.take_rings(verts2, off2, final)
+    vf = ops.round_coords(vf)
+    return Features(vf, of, pid2[final], conf2[final], area2[final], max_h[final], cent[final], isc[final], num[final],
+                    extras)
