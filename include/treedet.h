@@ -41,11 +41,12 @@ int td_device_sms(void);            /* SM count of the current device (148 on B2
  * Replaces Predictor._process_tile (TreeDetection/prediction.py:159-176): rasterio.mask
  * crop of the tile window, band reorder (2,1,0), optional 255*x/65535 for 16-bit data,
  * detectron2 ResizeShortestEdge(800, 1333) (PIL bilinear for uint8), float32 CHW.
- *   image      (bands, H, W) planar uint8 (elem_size 1) or uint16 (elem_size 2)
- *   tile_win   (T,4) int32 [col_off, row_off, w, h]        (tiling.tile_grid)
- *   tile_net   (T,2) int32 [net_h, net_w]                  (tiling.resize_shortest_edge)
- *   out_off    (T+1) int64 float offsets of each tile's (3, net_h, net_w) block in `out`
- *   rescale16  (T) uint8 out: 1 where the 16-bit branch was taken (max(band 1) > 255) */
+ *   image      (bands, H, W) planar uint8 (elem_size 1) or uint16 (elem_size 2), device
+ *   tile_win   HOST (T,4) int32 [col_off, row_off, w, h]   (tiling.tile_grid)
+ *   tile_net   HOST (T,2) int32 [net_h, net_w]             (tiling.resize_shortest_edge)
+ *   out_off    HOST (T+1) int64 float offsets of each tile's (3, net_h, net_w) block in `out`
+ *   rescale16  (T) uint8 out, may be null: 0 = uint8 tile, 1 = 16-bit branch taken
+ *              (max(band 1) > 255), 2 = uint16 tile the reference fails on (left untouched) */
 int td_tile_cut_normalize(const void* image, int elem_size, int bands, int H, int W, const int* tile_win,
                           const int* tile_net, int n_tiles, const long long* out_off, float* out,
                           unsigned char* rescale16, void* stream);

@@ -655,3 +655,64 @@ def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, hei
             "coords": [(round(x * 1000) / 1000, round(y * 1000) / 1000) for (x, y) in ring],
         })
     return out, debug
+
+
+# ============================================================================
+# P1  tile cut + normalise   (prediction.py:159-176)
+# ============================================================================
+
+
+def resize_shortest_edge(h, w, short=800, max_size=1333):
+    """detectron2 ResizeShortestEdge.get_output_shape (test-time: 800 / 1333)."""
+    size = short * 1.0
+    scale = size / min(h, w)
+    if h < w:
+        newh, neww = size, scale * w
+    else:
+        newh, neww = scale * h, size
+    if max(newh, neww) > max_size:
+        scale = max_size * 1.0 / max(newh, neww)
+        newh = newh * scale
+        neww = neww * scale
+    return int(newh + 0.5), int(neww + 0.5)
+
+
+def tile_cut_normalize(image, window):
+    """prediction.py:164-171 for one tile.  image (bands,H,W) uint8 / uint16, window
+    (col_off,row_off,w,h) as rasterio.mask(crop=True) cuts it for a pixel-aligned box.
+    Returns float32 CHW, or None where the reference raises (uint16 data whose green band
+    does not exceed 255: torch cannot interpolate uint16) and skips the tile."""
+    import torch
+    import torch.nn.functional as F
+    from PIL import Image
+
+    c0, r0, w, h = window
+    out_img = image[:, r0:r0 + h, c0:c0 + w]
+    rgb = np.dstack((out_img[2], out_img[1], out_img[0]))
+    rgb_rescaled = 255 * rgb / 65535 if np.max(out_img[1]) > 255 else rgb
+    nh, nw = resize_shortest_edge(h, w)
+    if rgb_rescaled.dtype == np.uint8:
+        pil = Image.fromarray(np.ascontiguousarray(rgb_rescaled))
+        res = np.asarray(pil.resize((nw, nh), Image.BILINEAR))
+    elif rgb_rescaled.dtype == np.float64:
+        t = torch.from_numpy(np.ascontiguousarray(rgb_rescaled)).permute(2, 0, 1)[None]
+        res = F.interpolate(t, (nh, nw), mode="bilinear", align_corners=False)[0].permute(1, 2, 0).numpy()
+    else:
+        return None
+    return res.astype("float32").transpose(2, 0, 1)
+
+
+# ============================================================================
+# P0a  seam strips   (merging.py:34-110, helpers.py:1023-1085)
+# ============================================================================
+
+
+def seam_crop(a, b, axis, strip_w, strip_h):
+    """Mosaic of two edge-adjacent rasters on the same grid (rasterio.merge of
+    non-overlapping neighbours = concatenation), centre-cropped as crop_image does.
+    Returns (strip, (left, top)) -- the window offset gives the strip's transform."""
+    mosaic = np.concatenate([a, b], axis=2 if axis == 0 else 1)
+    _, mh, mw = mosaic.shape
+    left = max(mw // 2 - strip_w // 2, 0)
+    top = max(mh // 2 - strip_h // 2, 0)
+    return mosaic[:, top:top + strip_h, left:left + strip_w], (left, top)

@@ -48,9 +48,9 @@ SIGNATURES = {
     "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "td_round_coords": (_i, [_p, _ll, _p, _p]),
     # P1
-    "td_tile_cut_normalize": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
+    "td_tile_cut_normalize": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _p]),
     # P0a
-    "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
 
 _lib = None

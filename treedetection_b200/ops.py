@@ -278,3 +278,44 @@ def round_coords(verts):
     out = torch.empty_like(verts)
     _lib.call("td_round_coords", _ptr(verts), verts.numel(), _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------
+# P1  tile cut + normalise,  P0a  seam strips
+# ----------------------------------------------------------------------------
+def tile_cut_normalize(image, tile_win, tile_net, out=None):
+    """image (bands,H,W) uint8 / int16-viewed-uint16 device tensor; tile_win (T,4) and
+    tile_net (T,2) int32 HOST tensors.  Returns (out f32 flat, out_off i64 host, rescale16 u8)."""
+    if tile_win.is_cuda or tile_net.is_cuda:
+        raise _lib.TreedetError("tile tables are host tensors (they come from the tiles JSON)")
+    tile_win = tile_win.to(torch.int32).contiguous(); tile_net = tile_net.to(torch.int32).contiguous()
+    t = tile_win.shape[0]
+    sizes = 3 * tile_net[:, 0].to(torch.int64) * tile_net[:, 1].to(torch.int64)
+    out_off = torch.zeros(t + 1, dtype=torch.int64)
+    torch.cumsum(sizes, 0, out=out_off[1:])
+    total = int(out_off[-1])
+    if out is None:
+        out = torch.empty((max(total, 1),), dtype=torch.float32, device=image.device)
+    elif out.numel() < total:
+        raise _lib.TreedetError("tile_cut_normalize: output buffer too small")
+    elem = image.element_size()
+    if elem not in (1, 2):
+        raise _lib.TreedetError("tile_cut_normalize: uint8 or uint16 rasters only")
+    b, h, w = image.shape
+    flag = torch.zeros((t,), dtype=torch.uint8, device=image.device)
+    _lib.call("td_tile_cut_normalize", _ptr(image), elem, b, h, w, tile_win.data_ptr(), tile_net.data_ptr(), t,
+              out_off.data_ptr(), _ptr(out), _ptr(flag), _stream())
+    return out, out_off, flag
+
+
+def seam_crop(a, b, axis, strip_w, strip_h):
+    """a, b: (bands,H,W) device rasters of the same dtype; axis 0 = b is the right
+    neighbour, 1 = b is the lower neighbour.  Returns (bands, strip_h, strip_w)."""
+    if a.dtype != b.dtype:
+        raise _lib.TreedetError("seam_crop: dtype mismatch")
+    bands, ha, wa = a.shape
+    _, hb, wb = b.shape
+    out = torch.empty((bands, strip_h, strip_w), dtype=a.dtype, device=a.device)
+    _lib.call("td_seam_crop", _ptr(a), _ptr(b), a.element_size(), bands, ha, wa, hb, wb, axis, strip_w, strip_h,
+              _ptr(out), _stream())
+    return out
