@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- post-model crown pipeline throughput (km^2/s) on synthetic orthophoto + nDSM
+mosaics (BASELINE.json: configs[1], "synthetic 10k x 10k px RGB + nDSM orthophoto, single
+model, tile size/overlap from example/config.yml, 1 B200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size PX]
+
+A step = one pass of the hot path (P1 tile cut/normalise, P2 paste+pack, P3 contours, P4
+stitch, P5 NDVI/decimation, P6 NMS, P7 crown stats, P8 containment, P9 selection) over one
+image per GPU.  `value` has inputs resident in HBM; `e2e` goes through
+treedetection_b200.api.run_image with pinned HOST buffers (H2D + D2H inside the timed
+region).  Under torchrun every rank owns its own image (row-sharded mosaic, weak scaling).
+`--impl reference` times the CPU restatement of the reference (oracle/port.py) on the
+host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "post-model crown pipeline throughput"
+UNIT = "km^2/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=10000, help="image side in pixels (0.2 m)")
+    ap.add_argument("--ndsm-px", type=float, default=0.2, help="nDSM pixel size (0.2: split stats path, 1.0: combined)")
+    ap.add_argument("--cpu-sample", type=int, default=3000, help="side (px) of the CPU-baseline sample scene")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference, on a bounded sample of the workload
+# --------------------------------------------------------------------------------------
+def _cpu_sample_once(args):
+    """One pass of the reference's path (restated, oracle/port.py) over one sample scene."""
+    seed, size_px, ndsm_px = args
+    import numpy as np
+    from oracle import port
+    from treedetection_b200 import geo, pipeline, synth
+    sc = synth.make_scene(seed=seed, size_px=size_px, px=0.2, ndsm_px=ndsm_px, density_per_km2=2500.0)
+    p = pipeline.PipelineParams()
+    cfg = {k: getattr(p, k) for k in p.__dataclass_fields__}
+    t0 = time.perf_counter()
+    for meta in sc.tiles.values():                                   # P1
+        port.tile_cut_normalize(sc.rgbi, tuple(meta["window"]))
+    rings, conf = port.predict_stage(sc.det, sc.tiles, paste="torch")   # P2-P4
+    H, W = sc.rgbi.shape[1:]
+    oh, ow = int(H * p.ndvi_scaling_factor), int(W * p.ndvi_scaling_factor)
+    dec = np.stack([port.decimate_bilinear(sc.rgbi[b], oh, ow) for b in (0, 3)])        # P5
+    ndvi = port.ndvi_from_rgbi(np.stack([dec[0], dec[0], dec[0], dec[1]])).astype(np.float32)
+    ndvi_tf = geo.compose(sc.transform, geo.scale(W / ow, H / oh))
+    h, w = sc.ndsm.shape
+    out, _ = port.post_process(rings, conf, ndvi, ndvi_tf, tuple(geo.raster_bounds(sc.transform, W, H)), sc.ndsm,
+                               sc.ndsm_transform, tuple(geo.raster_bounds(sc.ndsm_transform, w, h)), 0.2, 0.2, cfg)
+    dt = time.perf_counter() - t0
+    return dt, sc.area_km2, len(rings), len(out)
+
+
+def cpu_rate(sample_px, ndsm_px, workers, repeats=1):
+    """km^2/s of the CPU restatement: `workers` processes, one sample scene each per repeat
+    (independent images are how the reference parallelises: ThreadPoolExecutor over files)."""
+    import multiprocessing as mp
+    jobs = [(1234 + i, sample_px, ndsm_px) for i in range(workers * repeats)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        res = [_cpu_sample_once(j) for j in jobs]
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            res = pool.map(_cpu_sample_once, jobs)
+    # scene synthesis happens inside the workers before their clocks start: the timed work
+    # is the path only; concurrent workers finish together, so the slowest one is the wall
+    area = sum(r[1] for r in res)
+    per_round = [max(r[0] for r in res[k * workers:(k + 1) * workers]) for k in range(repeats)]
+    wall = sum(per_round)
+    busy = sum(r[0] for r in res)
+    return {"wall_s": wall, "area_km2": area, "km2_per_s_wall": area / wall,
+            "km2_per_s_core": area / busy, "rings": res[0][2], "crowns": res[0][3],
+            "outer_wall_s": time.perf_counter() - t0}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    # bounded: one sample per worker per step; per-sample cost ~10-20 s on one core
+    times = []
+    area = 0.0
+    r = None
+    for step in range(a.warmup + a.steps):
+        r = cpu_rate(a.cpu_sample, a.ndsm_px, cores)
+        if step >= a.warmup:
+            times.append(r["wall_s"])
+            area += r["area_km2"]
+        if sum(times) > 240:
+            break
+    steps = max(len(times), 1)
+    value = area / max(sum(times), 1e-9)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "mixed: u8/f32/f64 (CPU)", "data": "synthetic",
+        "config": {"workload": f"synthetic {a.size}x{a.size} px RGBI + nDSM orthophoto, single model, tile 50 m / buffer 20 m",
+                   "sample": f"{cores} x ({a.cpu_sample}x{a.cpu_sample} px sub-scene) per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x one {a.cpu_sample}x{a.cpu_sample} px scene "
+                                   f"({r['rings']} candidate rings each) per step, P1-P9 restated in oracle/port.py"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    from treedetection_b200 import _lib, api, ops, pipeline, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    p = pipeline.PipelineParams()
+
+    # row-sharded mosaic: rank r owns the image of row r (its own seed / georeference)
+    sc = synth.make_scene(seed=1234 + rank, size_px=a.size, px=0.2, ndsm_px=a.ndsm_px, density_per_km2=2500.0,
+                          bottom=synth.ORIGIN_Y - rank * a.size * 0.2, stem=f"FDOP20_{rank:06d}_rgbi")
+    host = api.HostImage.from_scene(sc)
+    tables = api.TileTables(sc.tiles, dev, p.shift)
+    p1_out = torch.empty((tables.p1_floats,), dtype=torch.float32, device=dev)
+    # device-resident copies for the kernel-only figure
+    d = {k: getattr(host, k).to(dev) for k in ("rgbi", "ndsm", "boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
+    n_inst = int(host.scores.numel())
+    n_tiles = len(sc.tiles)
+    p1_bytes = int(sum(3 * int(w[2]) * int(w[3]) for w in tables.win.tolist())) + 4 * tables.p1_floats
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    p1_ev = []
+
+    def step_resident():
+        e0, e1 = ev(), ev()
+        e0.record()
+        ops.tile_cut_normalize(d["rgbi"], tables.win, tables.net, out=p1_out)
+        e1.record()
+        p1_ev.append((e0, e1))
+        table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
+                                       tables.tile_tf, tables.tile_boxes, p)
+        rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
+        feats = pipeline.postprocess_stage(table, rasters, p)
+        return len(table), len(feats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = ev(), ev()
+        s.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(a.warmup):
+        step_resident()
+    p1_ev.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms, (n_cand, n_final) = timed(step_resident, a.steps)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    p1_ms = statistics.mean(x.elapsed_time(y) for x, y in p1_ev)
+    area = sc.area_km2
+    value = world * area * a.steps / (ms / 1e3)
+
+    # end to end through the host-buffer API
+    def step_e2e():
+        out, _ = api.run_image(host, p, dev, tables, p1_out)
+        return out
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_e2e()
+    e2e_steps = max(1, min(a.steps, 5))
+    ms_e2e, out = timed(step_e2e, e2e_steps)
+    e2e_value = world * area * e2e_steps / (ms_e2e / 1e3)
+    d2h = int(sum(v.nbytes for v in out.values() if hasattr(v, "nbytes")))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = p1_bytes / (p1_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32 rasters, f32/f16 NMS, f64 geometry", "data": "synthetic",
+            "config": {"workload": f"synthetic {a.size}x{a.size} px RGBI + nDSM ({a.ndsm_px} m) orthophoto per GPU, "
+                                   f"single model, tile 50 m / buffer 20 m ({n_tiles} tiles, {n_inst} ROI-head "
+                                   f"instances replayed from fixtures -> {n_cand} candidate crowns -> {n_final} crowns)",
+                       "area_km2_per_gpu": area, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
+                       "cache": "inputs (rasters 0.8 GB, P1 output 12 GB) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"image-row sharding x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "tile_resize_u8_kernel (P1)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": p1_bytes, "ms_per_launch": p1_ms,
+                         "share_of_step": p1_ms / (ms / a.steps)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            r = cpu_rate(a.cpu_sample, a.ndsm_px, 1)
+            line["cpu_baseline"] = {"value": r["km2_per_s_wall"], "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": f"one {a.cpu_sample}x{a.cpu_sample} px sub-scene of the same workload "
+                                              f"({r['rings']} candidate rings), P1-P9 restated in oracle/port.py, "
+                                              f"{r['wall_s']:.1f} s on one core of {os.cpu_count()}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,16 @@ SIGNATURES = {
     "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
 
+# hand-written kernels launched per call (library kernels -- CUB sort / scan -- not counted);
+# bench.py reports the sum over the timed region as ``gpu_launches``
+OWN_KERNELS = {
+    "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 1,
+    "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
+    "td_bbox_nms_ordered": 7, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,
+    "td_round_coords": 1, "td_tile_cut_normalize": 1, "td_seam_crop": 1,
+}
+launch_count = 0
+
 _lib = None
 
 
@@ -100,5 +110,7 @@ def check(rc: int, what: str):
 
 
 def call(name: str, *args):
+    global launch_count
     fn = getattr(lib(), name)
     check(fn(*args), name)
+    launch_count += OWN_KERNELS.get(name, 0)

@@ -1,0 +1,90 @@
+"""Host-buffer entry of the crown pipeline for one image -- the call the reference-facing
+functions (``detection.predict_tiles`` / ``postprocess_files``) make once rasters and the
+predictor's raw outputs are in host memory.
+
+``run_image`` takes HOST arrays (pinned tensors are used as they are), copies them to the
+device on the current stream, runs P1..P9 through the C-ABI kernels and copies the final
+crown table back.  It is also what ``bench.py`` times for its end-to-end (``e2e``) figure.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, ops, pipeline, tiling
+
+
+@dataclass
+class HostImage:
+    """Everything the path consumes for one image, in host memory."""
+    rgbi: torch.Tensor            # (4, H, W) uint8  (pinned for async copies)
+    transform: tuple
+    ndsm: torch.Tensor            # (h, w) float32
+    ndsm_transform: tuple
+    tiles: dict                   # tiles JSON (tiling.tile_grid)
+    boxes_net: torch.Tensor       # (N, 4) f32   raw ROI-head outputs, tile-major
+    scores: torch.Tensor          # (N,) f32
+    probs: torch.Tensor           # (N, 28, 28) f32
+    inst_tile: torch.Tensor       # (N,) i32
+    tile_dims: torch.Tensor       # (T, 4) i32
+
+    @classmethod
+    def from_scene(cls, sc, pin=True):
+        def t(a):
+            x = torch.from_numpy(np.ascontiguousarray(a))
+            return x.pin_memory() if pin and torch.cuda.is_available() else x
+        d = sc.det
+        return cls(t(sc.rgbi), sc.transform, t(sc.ndsm), sc.ndsm_transform, sc.tiles, t(d.boxes_net), t(d.scores),
+                   t(d.probs), t(d.inst_tile), t(d.tile_dims))
+
+    def h2d_bytes(self):
+        return sum(x.numel() * x.element_size() for x in
+                   (self.rgbi, self.ndsm, self.boxes_net, self.scores, self.probs, self.inst_tile, self.tile_dims))
+
+
+class TileTables:
+    """Host + device tables derived once from the tiles JSON."""
+
+    def __init__(self, tiles: dict, device, shift=1):
+        self.win = torch.tensor([m["window"] for m in tiles.values()], dtype=torch.int32).reshape(-1, 4)
+        self.net = torch.tensor([tiling.resize_shortest_edge(int(w[3]), int(w[2])) for w in self.win.tolist()],
+                                dtype=torch.int32).reshape(-1, 2)
+        self.tile_tf, boxes_int = pipeline.tile_tables(tiles, device)
+        self.tile_boxes = pipeline.filter_boxes(boxes_int, shift, device)
+        self.p1_floats = int((3 * self.net[:, 0].long() * self.net[:, 1].long()).sum())
+
+
+def features_to_host(f: pipeline.Features):
+    """One device->host transfer of the final crown table."""
+    return {
+        "verts": f.verts.cpu().numpy(), "ring_off": f.ring_off.cpu().numpy(), "poly_id": f.poly_id.cpu().numpy(),
+        "conf": f.conf.cpu().numpy(), "area": f.area.cpu().numpy(), "tree_height": f.tree_height.cpu().numpy(),
+        "centroid": f.centroid.cpu().numpy(), "is_contained": f.is_contained.cpu().numpy(),
+        "num_contained": f.num_contained.cpu().numpy(),
+    }
+
+
+def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: TileTables = None, p1_out=None,
+              with_p1=True):
+    """Host buffers in, final crowns (host numpy) out.  ``p1_out``: optional reusable
+    device buffer for the normalised tiles (they feed the predictor, not this path)."""
+    if not torch.cuda.is_available():
+        raise _lib.TreedetError("run_image needs a CUDA device (there is no CPU fallback)")
+    tables = tables or TileTables(img.tiles, device, params.shift)
+    nb = True
+    rgbi = img.rgbi.to(device, non_blocking=nb)
+    ndsm = img.ndsm.to(device, non_blocking=nb)
+    boxes = img.boxes_net.to(device, non_blocking=nb); scores = img.scores.to(device, non_blocking=nb)
+    probs = img.probs.to(device, non_blocking=nb); inst_tile = img.inst_tile.to(device, non_blocking=nb)
+    tile_dims = img.tile_dims.to(device, non_blocking=nb)
+    tiles_out = None
+    if with_p1:
+        tiles_out, _, _ = ops.tile_cut_normalize(rgbi, tables.win, tables.net, out=p1_out)
+    table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf, tables.tile_boxes, params)
+    rasters = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
+    feats = pipeline.postprocess_stage(table, rasters, params)
+    host = features_to_host(feats)
+    host["n_candidates"] = len(table)
+    return host, tiles_out

@@ -10,9 +10,9 @@
 //        then vertical pass; float: F.interpolate(bilinear, align_corners=False) in float64
 //   astype(float32).transpose(2, 0, 1)         -> float32 CHW
 // The reference does this per tile on the CPU and ships 7.68 MB per tile to the GPU;
-// here the image is resident in HBM, every CTA produces a 128 x 8 block of output pixels
-// for the three channels: the horizontal pass of the few source rows it needs goes to
-// shared memory, the vertical pass streams coalesced float32 rows out.  The kernel is
+// here the image is resident in HBM, every CTA produces a 128 x 32 block of output pixels
+// for the three channels: the source window and the horizontal pass of the few source rows
+// it needs live in shared memory, the vertical pass streams 128-bit coalesced float32 rows out.  The kernel is
 // write bound: 0.81 MB in / 7.68 MB out per interior tile.
 //
 // P0a replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,
@@ -26,11 +26,11 @@
 
 namespace {
 
-constexpr int kBX = 128;            // output columns per CTA
-constexpr int kBY = 8;              // output rows per CTA
+constexpr int kBX = 128;           // output columns per CTA
+constexpr int kBY = 32;            // output rows per CTA
 constexpr int kThreads = 256;
 constexpr int kPrecisionBits = 32 - 8 - 2;   // PIL: 22-bit fixed-point coefficients
-constexpr int kMaxK = 8;            // taps per axis supported (down-scaling up to ~3.5x)
+constexpr int kMaxK = 8;           // taps per axis supported (down-scaling up to ~3.5x)
 
 struct TileDesc {
   int c_off, r_off, w, h;   // source window
@@ -38,6 +38,7 @@ struct TileDesc {
   long long out_off;        // float offset of the (3, nh, nw) block
   int xtab, ytab;           // offsets into the coefficient tables (entries)
   int kx, ky;               // taps per output index
+  int blk0, bx;             // first CTA of the tile in the flat grid, CTAs per row of CTAs
 };
 
 // host: PIL precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter
@@ -84,55 +85,145 @@ TD_D int clip8(int v) {
 }
 
 // ---- uint8 tiles: PIL fixed-point separable resize ---------------------------------------
+// One CTA = 128 x 32 output pixels x 3 channels of one tile.
+//   phase 0: the source window (<= max_rows rows x src_stride bytes x 3 bands) is staged in
+//            shared memory with coalesced 32-bit loads (one warp per source row);
+//   phase 1: horizontal pass, one thread per output column, rounded to uint8 (as PIL does);
+//   phase 2: vertical pass, one warp per output row, 4 adjacent pixels per lane from one
+//            packed 32-bit shared load per tap, 128-bit coalesced float stores.
+// K = compile-time tap bound (3: up-scaling, the usual case; 8: moderate down-scaling).
+template <int K>
 __global__ void __launch_bounds__(kThreads)
-tile_resize_u8_kernel(const unsigned char* __restrict__ image, int H, int W, const TileDesc* __restrict__ tiles,
-                      const int* __restrict__ tab_min, const int* __restrict__ tab_cnt,
-                      const int* __restrict__ tab_k, float* __restrict__ out, int max_rows) {
-  extern __shared__ unsigned char tmp[];  // [3][max_rows][kBX] horizontal pass, rounded to uint8
-  const TileDesc T = tiles[blockIdx.z];
-  const int ox0 = blockIdx.x * kBX, oy0 = blockIdx.y * kBY;
-  if (ox0 >= T.nw || oy0 >= T.nh) return;
-  const int oy1 = min(oy0 + kBY, T.nh) - 1;
-  const int row_lo = tab_min[T.ytab + oy0];
-  const int row_hi = tab_min[T.ytab + oy1] + tab_cnt[T.ytab + oy1];
-  const int nrows = row_hi - row_lo;
-  const size_t plane = (size_t)H * W;
-  // horizontal pass: items = (channel, source row, output column)
-  const int items = 3 * nrows * kBX;
-  for (int it = threadIdx.x; it < items; it += kThreads) {
-    const int x = it % kBX;
-    const int r = (it / kBX) % nrows;
-    const int c = it / (kBX * nrows);
-    const int ox = ox0 + x;
-    int v = 0;
-    if (ox < T.nw) {
-      const int xs = tab_min[T.xtab + ox], xn = tab_cnt[T.xtab + ox];
-      const int* k = tab_k + (size_t)(T.xtab + ox) * kMaxK;
-      // output channel c reads band 2 - c (BGR order)
-      const unsigned char* src = image + (size_t)(2 - c) * plane + (size_t)(T.r_off + row_lo + r) * W + T.c_off + xs;
-      int ss = 1 << (kPrecisionBits - 1);
-      for (int q = 0; q < xn; ++q) ss += (int)src[q] * k[q];
-      v = clip8(ss);
-    }
-    tmp[((size_t)c * max_rows + r) * kBX + x] = (unsigned char)v;
+tile_resize_u8_kernel(const unsigned char* __restrict__ image, long long image_bytes, int H, int W,
+                      const TileDesc* __restrict__ tiles, int n_tiles, const int* __restrict__ tab_min,
+                      const int* __restrict__ tab_cnt, const int* __restrict__ tab_k, float* __restrict__ out,
+                      int max_rows, int src_stride) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* s_src = smem;                                             // [3][max_rows][src_stride]
+  unsigned char* s_tmp = smem + (size_t)3 * max_rows * src_stride;         // [3][max_rows][kBX]
+  int* s_ytab = reinterpret_cast<int*>(s_tmp + (size_t)3 * max_rows * kBX);  // [kBY][2 + K]
+  // ---- which tile / block --------------------------------------------------------------
+  int lo = 0, hi = n_tiles - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tiles[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  __syncthreads();
-  // vertical pass: thread -> column x, rows y = ty, ty + 2, ...
-  const int x = threadIdx.x % kBX, ty = threadIdx.x / kBX;
-  const int ox = ox0 + x;
-  if (ox >= T.nw) return;
-  float* o = out + T.out_off;
-  const size_t oplane = (size_t)T.nh * T.nw;
-  for (int y = ty; y < kBY; y += kThreads / kBX) {
-    const int oy = oy0 + y;
-    if (oy >= T.nh) break;
-    const int ys = tab_min[T.ytab + oy] - row_lo, yn = tab_cnt[T.ytab + oy];
+  const TileDesc T = tiles[lo];
+  const int b = blockIdx.x - T.blk0;
+  const int ox0 = (b % T.bx) * kBX, oy0 = (b / T.bx) * kBY;
+  const int ox_last = min(ox0 + kBX, T.nw) - 1, oy_last = min(oy0 + kBY, T.nh) - 1;
+  const int row_lo = tab_min[T.ytab + oy0];
+  const int nrows = tab_min[T.ytab + oy_last] + tab_cnt[T.ytab + oy_last] - row_lo;
+  const int col_lo = tab_min[T.xtab + ox0];
+  const int ncols = tab_min[T.xtab + ox_last] + tab_cnt[T.xtab + ox_last] - col_lo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t plane = (size_t)H * W;
+  // ---- phase 0: stage the window -----------------------------------------------------------
+  for (int rr = warp; rr < 3 * nrows; rr += kThreads / 32) {
+    const int c = rr / nrows, r = rr - c * nrows;
+    // output channel c reads band 2 - c (BGR order)
+    const size_t a = (size_t)(2 - c) * plane + (size_t)(T.r_off + row_lo + r) * W + T.c_off + col_lo;
+    const size_t a0 = a & ~(size_t)3;
+    const int shift = (int)(a - a0);
+    const int nwords = (shift + ncols + 3) >> 2;
+    unsigned char* dst = s_src + ((size_t)c * max_rows + r) * src_stride;
+    for (int q = lane; q < nwords; q += 32) {
+      const size_t wa = a0 + 4 * (size_t)q;
+      uint32_t v;
+      if (wa + 4 <= (size_t)image_bytes) {
+        v = *reinterpret_cast<const uint32_t*>(image + wa);
+      } else {
+        v = 0;
+        for (int z = 0; z < 4; ++z)
+          if (wa + z < (size_t)image_bytes) v |= (uint32_t)image[wa + z] << (8 * z);
+      }
+      *reinterpret_cast<uint32_t*>(dst + 4 * q) = v;
+    }
+  }
+  // y taps of the CTA's rows
+  if (threadIdx.x < kBY) {
+    const int oy = min(oy0 + (int)threadIdx.x, T.nh - 1);
+    int* e = s_ytab + threadIdx.x * (2 + K);
+    e[0] = tab_min[T.ytab + oy] - row_lo;
+    e[1] = tab_cnt[T.ytab + oy];
     const int* k = tab_k + (size_t)(T.ytab + oy) * kMaxK;
 #pragma unroll
+    for (int q = 0; q < K; ++q) e[2 + q] = k[q];
+  }
+  __syncthreads();
+  // ---- phase 1: horizontal pass ------------------------------------------------------------
+  {
+    const int x = threadIdx.x & (kBX - 1), g = threadIdx.x >> 7;
+    const int ox = ox0 + x;
+    int xs = 0, kx[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) kx[q] = 0;
+    if (ox < T.nw) {
+      xs = tab_min[T.xtab + ox] - col_lo;
+      const int* k = tab_k + (size_t)(T.xtab + ox) * kMaxK;
+#pragma unroll
+      for (int q = 0; q < K; ++q) kx[q] = k[q];      // taps beyond the count are 0
+    }
+    const size_t a_row0 = (size_t)T.c_off + col_lo;   // only the low 2 bits matter below
     for (int c = 0; c < 3; ++c) {
-      int ss = 1 << (kPrecisionBits - 1);
-      for (int q = 0; q < yn; ++q) ss += (int)tmp[((size_t)c * max_rows + ys + q) * kBX + x] * k[q];
-      o[c * oplane + (size_t)oy * T.nw + ox] = (float)clip8(ss);
+      for (int r = g; r < nrows; r += kThreads / kBX) {
+        const size_t a = (size_t)(2 - c) * plane + (size_t)(T.r_off + row_lo + r) * W + a_row0;
+        const int shift = (int)(a & 3);
+        const unsigned char* p = s_src + ((size_t)c * max_rows + r) * src_stride + shift + xs;
+        int ss = 1 << (kPrecisionBits - 1);
+#pragma unroll
+        for (int q = 0; q < K; ++q) ss += (int)p[q] * kx[q];
+        s_tmp[((size_t)c * max_rows + r) * kBX + x] = (unsigned char)(ox < T.nw ? clip8(ss) : 0);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: vertical pass ----------------------------------------------------------------
+  float* o = out + T.out_off;
+  const size_t oplane = (size_t)T.nh * T.nw;
+  const bool vec = ((T.nw & 3) == 0) && ((T.out_off & 3) == 0);
+  for (int y = warp; y < kBY; y += kThreads / 32) {
+    const int oy = oy0 + y;
+    if (oy >= T.nh) break;
+    const int* e = s_ytab + y * (2 + K);
+    const int ys = e[0];
+    int ky[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) ky[q] = e[2 + q];
+    if (vec) {
+      const int x4 = 4 * lane;
+      if (ox0 + x4 >= T.nw) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0, s3 = s0;
+        const unsigned char* col = s_tmp + ((size_t)c * max_rows + ys) * kBX + x4;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          // rows beyond the tap count have coefficient 0; stay inside the staged rows
+          const uint32_t u = (K <= 3 || q < e[1]) ? *reinterpret_cast<const uint32_t*>(col + (size_t)q * kBX) : 0u;
+          s0 += (int)(u & 255u) * ky[q];
+          s1 += (int)((u >> 8) & 255u) * ky[q];
+          s2 += (int)((u >> 16) & 255u) * ky[q];
+          s3 += (int)(u >> 24) * ky[q];
+        }
+        float4 v = make_float4((float)clip8(s0), (float)clip8(s1), (float)clip8(s2), (float)clip8(s3));
+        *reinterpret_cast<float4*>(o + c * oplane + (size_t)oy * T.nw + ox0 + x4) = v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = lane + 32 * j;
+        if (ox0 + x >= T.nw) break;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int ss = 1 << (kPrecisionBits - 1);
+          const unsigned char* col = s_tmp + ((size_t)c * max_rows + ys) * kBX + x;
+#pragma unroll
+          for (int q = 0; q < K; ++q)
+            if (K <= 3 || q < e[1]) ss += (int)col[(size_t)q * kBX] * ky[q];
+          o[c * oplane + (size_t)oy * T.nw + ox0 + x] = (float)clip8(ss);
+        }
+      }
     }
   }
 }
@@ -216,37 +307,36 @@ extern "C" int td_tile_cut_normalize(const void* image, int elem_size, int bands
   if (n_tiles == 0) return TD_OK;
   TD_ARG(image && tile_win && tile_net && out_off && out);
   TD_ARG(bands >= 3 && H > 0 && W > 0 && (elem_size == 1 || elem_size == 2));
+  TD_ARG(((uintptr_t)out & 15) == 0 && ((uintptr_t)image & 3) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<TileDesc> td(n_tiles);
   std::map<std::pair<int, int>, std::pair<int, int>> tabs;  // (in,out) -> (offset, ksize)
   std::vector<int> tmin, tcnt, tk;
-  int max_nw = 0, max_nh = 0, max_rows = 1;
-  auto table = [&](int in_size, int out_size, int group) {
+  int max_nw = 0, max_nh = 0, max_rows = 1, max_cols = 1, max_k = 1;
+  long long n_blocks = 0;
+  // group > 0: also track the widest source span of `group` consecutive outputs
+  auto table = [&](int in_size, int out_size, int group, int& max_span) {
     auto key = std::make_pair(in_size, out_size);
     auto it = tabs.find(key);
     std::pair<int, int> res;
-    std::vector<int> xm, cn, kk;
-    std::vector<double> kd;
-    int ks = 0;
     if (it == tabs.end()) {
+      std::vector<int> xm, cn, kk;
+      std::vector<double> kd;
+      int ks = 0;
       pil_coeffs(in_size, out_size, xm, cn, kk, kd, ks);
       res = std::make_pair((int)tmin.size(), ks);
-      if (ks <= kMaxK) {
-        for (int i = 0; i < out_size; ++i) {
-          tmin.push_back(xm[i]); tcnt.push_back(cn[i]);
-          for (int q = 0; q < kMaxK; ++q) tk.push_back(q < ks ? kk[(size_t)i * ks + q] : 0);
-        }
+      for (int i = 0; i < out_size; ++i) {
+        tmin.push_back(xm[i]); tcnt.push_back(cn[i]);
+        for (int q = 0; q < kMaxK; ++q) tk.push_back((q < ks && q < kMaxK) ? kk[(size_t)i * ks + q] : 0);
       }
       tabs[key] = res;
     } else {
       res = it->second;
     }
-    if (group > 0 && res.second <= kMaxK) {  // rows of shared memory the vertical pass needs
-      for (int i = 0; i < out_size; i += group) {
-        const int last = (i + group < out_size ? i + group : out_size) - 1;
-        const int span = tmin[res.first + last] + tcnt[res.first + last] - tmin[res.first + i];
-        if (span > max_rows) max_rows = span;
-      }
+    for (int i = 0; i < out_size; i += group) {
+      const int last = (i + group < out_size ? i + group : out_size) - 1;
+      const int span = tmin[res.first + last] + tcnt[res.first + last] - tmin[res.first + i];
+      if (span > max_span) max_span = span;
     }
     return res;
   };
@@ -257,17 +347,23 @@ extern "C" int td_tile_cut_normalize(const void* image, int elem_size, int bands
     d.out_off = out_off[t];
     TD_ARG(d.w > 0 && d.h > 0 && d.nh > 0 && d.nw > 0 && d.c_off >= 0 && d.r_off >= 0 && d.c_off + d.w <= W &&
            d.r_off + d.h <= H);
+    d.xtab = d.ytab = d.kx = d.ky = 0;
     if (elem_size == 1) {
-      auto tx = table(d.w, d.nw, 0);
-      auto ty = table(d.h, d.nh, kBY);
+      auto tx = table(d.w, d.nw, kBX, max_cols);
+      auto ty = table(d.h, d.nh, kBY, max_rows);
       if (tx.second > kMaxK || ty.second > kMaxK) {
-        td_set_error("td_tile_cut_normalize: down-scaling factor needs %d taps (max %d)", tx.second, kMaxK);
+        td_set_error("td_tile_cut_normalize: down-scaling factor needs %d taps (max %d)",
+                     tx.second > ty.second ? tx.second : ty.second, kMaxK);
         return TD_ERR_UNSUPPORTED;
       }
       d.xtab = tx.first; d.kx = tx.second; d.ytab = ty.first; d.ky = ty.second;
-    } else {
-      d.xtab = d.ytab = d.kx = d.ky = 0;
+      if (d.kx > max_k) max_k = d.kx;
+      if (d.ky > max_k) max_k = d.ky;
     }
+    d.bx = td_div_up(d.nw, kBX);
+    d.blk0 = (int)n_blocks;
+    n_blocks += (long long)d.bx * td_div_up(d.nh, kBY);
+    TD_ARG(n_blocks < 0x7fffffffLL);
     if (d.nw > max_nw) max_nw = d.nw;
     if (d.nh > max_nh) max_nh = d.nh;
   }
@@ -284,12 +380,21 @@ extern "C" int td_tile_cut_normalize(const void* image, int elem_size, int bands
     TD_CUDA(cudaMemcpyAsync(d_cnt, tcnt.data(), sizeof(int) * tcnt.size(), cudaMemcpyHostToDevice, st));
     TD_CUDA(cudaMemcpyAsync(d_k, tk.data(), sizeof(int) * tk.size(), cudaMemcpyHostToDevice, st));
     if (rescale16) TD_CUDA(cudaMemsetAsync(rescale16, 0, n_tiles, st));
-    const size_t smem = (size_t)3 * max_rows * kBX;
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(tile_resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(td_div_up(max_nw, kBX), td_div_up(max_nh, kBY), n_tiles);
-    tile_resize_u8_kernel<<<grid, kThreads, smem, st>>>((const unsigned char*)image, H, W, d_td, d_min, d_cnt, d_k, out,
-                                                        max_rows);
+    const int K = max_k <= 3 ? 3 : kMaxK;
+    const int src_stride = (3 + max_cols + K + 3) & ~3;
+    const size_t smem = (size_t)3 * max_rows * src_stride + (size_t)3 * max_rows * kBX + sizeof(int) * kBY * (2 + K);
+    const long long image_bytes = (long long)bands * H * W;
+    if (K == 3) {
+      auto kern = tile_resize_u8_kernel<3>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(unsigned)n_blocks, kThreads, smem, st>>>((const unsigned char*)image, image_bytes, H, W, d_td, n_tiles,
+                                                       d_min, d_cnt, d_k, out, max_rows, src_stride);
+    } else {
+      auto kern = tile_resize_u8_kernel<kMaxK>;
+      if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<(unsigned)n_blocks, kThreads, smem, st>>>((const unsigned char*)image, image_bytes, H, W, d_td, n_tiles,
+                                                       d_min, d_cnt, d_k, out, max_rows, src_stride);
+    }
   } else {
     TD_CUDA(cudaMallocAsync((void**)&d_max, sizeof(int) * n_tiles, st));
     TD_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int) * n_tiles, st));

@@ -1,0 +1,241 @@
+"""Minimal GeoTIFF reader / writer for the rasters on the path (NumPy only).
+
+The reference reads and writes its rasters through rasterio/GDAL
+(``TreeDetection/prediction.py:61``, ``postprocessing.py:781-800``, ``merging.py:56-75``);
+neither is available here.  Supported: classic (non-Big) TIFF, little or big endian,
+strips or tiles, chunky or planar configuration, uint8 / uint16 / int16 / float32 samples,
+no compression or deflate (zlib, predictor 1), the GeoTIFF tags ModelPixelScale (33550),
+ModelTiepoint (33922), ModelTransformation (34264), GeoKeyDirectory (34735, EPSG code of the
+projected / geographic CRS) and GDAL_NODATA (42113).  That covers the bundled
+``data/nDSM/324125317.tif`` and everything this package writes.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+from dataclasses import dataclass
+
+import numpy as np
+
+_TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 7: ("B", 1), 8: ("h", 2),
+          9: ("i", 4), 10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 16: ("Q", 8)}
+
+
+@dataclass
+class GeoInfo:
+    width: int
+    height: int
+    count: int
+    dtype: np.dtype
+    transform: tuple            # (a, b, c, d, e, f)
+    epsg: int | None
+    nodata: float | None
+
+    @property
+    def bounds(self):
+        a, b, c, d, e, f = self.transform
+        return (c, f + e * self.height, c + a * self.width, f)
+
+
+def _read_ifd(buf, bo):
+    off = struct.unpack(bo + "I", buf[4:8])[0]
+    n = struct.unpack(bo + "H", buf[off:off + 2])[0]
+    tags = {}
+    for i in range(n):
+        e = buf[off + 2 + 12 * i: off + 14 + 12 * i]
+        tag, typ, cnt = struct.unpack(bo + "HHI", e[:8])
+        fmt, size = _TYPES.get(typ, ("B", 1))
+        total = size * cnt
+        if total <= 4:
+            raw = e[8:8 + total]
+        else:
+            p = struct.unpack(bo + "I", e[8:12])[0]
+            raw = buf[p:p + total]
+        if typ == 2:
+            val = raw.split(b"\x00")[0].decode("latin1")
+        elif typ in (5, 10):
+            v = struct.unpack(bo + fmt[0] * (2 * cnt), raw)
+            val = tuple(v[2 * k] / v[2 * k + 1] if v[2 * k + 1] else 0.0 for k in range(cnt))
+        else:
+            val = struct.unpack(bo + fmt * cnt, raw)
+        tags[tag] = val
+    return tags
+
+
+def _info_from_tags(t):
+    width, height = int(t[256][0]), int(t[257][0])
+    spp = int(t.get(277, (1,))[0])
+    bits = int(t.get(258, (8,))[0])
+    fmt = int(t.get(339, (1,))[0])
+    dtype = {(8, 1): np.uint8, (16, 1): np.uint16, (16, 2): np.int16, (32, 3): np.float32, (32, 1): np.uint32,
+             (32, 2): np.int32, (64, 3): np.float64}.get((bits, fmt))
+    if dtype is None:
+        raise ValueError(f"unsupported sample format: {bits} bits, format {fmt}")
+    if 34264 in t:
+        m = t[34264]
+        transform = (m[0], m[1], m[3], m[4], m[5], m[7])
+    elif 33550 in t and 33922 in t:
+        sx, sy = t[33550][0], t[33550][1]
+        i, j, _, x, y, _ = t[33922][:6]
+        transform = (sx, 0.0, x - i * sx, 0.0, -sy, y + j * sy)
+    else:
+        transform = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+    epsg = None
+    if 34735 in t:
+        g = t[34735]
+        for k in range(1, g[3] + 1):
+            key, loc, cnt, val = g[4 * k: 4 * k + 4]
+            if key in (3072, 2048) and loc == 0 and (epsg is None or key == 3072):
+                epsg = int(val)
+    nodata = None
+    if 42113 in t:
+        try:
+            nodata = float(str(t[42113]).strip())
+        except ValueError:
+            nodata = None
+    return GeoInfo(width, height, spp, np.dtype(dtype), tuple(float(v) for v in transform), epsg, nodata)
+
+
+def read_info(path) -> GeoInfo:
+    with open(path, "rb") as f:
+        head = f.read(8)
+        bo = "<" if head[:2] == b"II" else ">"
+        if struct.unpack(bo + "H", head[2:4])[0] != 42:
+            raise ValueError("not a classic TIFF")
+        buf = head + f.read()          # IFD may be anywhere; files on this path are modest
+    return _info_from_tags(_read_ifd(buf, bo))
+
+
+def read(path, window=None):
+    """Returns (array (bands, H, W), GeoInfo).  window = (col_off, row_off, w, h)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    bo = "<" if buf[:2] == b"II" else ">"
+    if struct.unpack(bo + "H", buf[2:4])[0] != 42:
+        raise ValueError("not a classic TIFF")
+    t = _read_ifd(buf, bo)
+    info = _info_from_tags(t)
+    comp = int(t.get(259, (1,))[0])
+    if comp not in (1, 8, 32946):
+        raise ValueError(f"unsupported TIFF compression {comp}")
+    if int(t.get(317, (1,))[0]) != 1:
+        raise ValueError("unsupported TIFF predictor")
+    planar = int(t.get(284, (1,))[0])
+    W, H, C = info.width, info.height, info.count
+    dt = info.dtype.newbyteorder(bo)
+    out = np.empty((C, H, W), dtype=info.dtype)
+
+    def chunk(off, cnt):
+        raw = buf[off:off + cnt]
+        return zlib.decompress(raw) if comp != 1 else raw
+
+    if 322 in t:   # tiles
+        tw, th = int(t[322][0]), int(t[323][0])
+        offs, cnts = t[324], t[325]
+        tx, ty = (W + tw - 1) // tw, (H + th - 1) // th
+        per_plane = tx * ty
+        for p in range(C if planar == 2 else 1):
+            for j in range(ty):
+                for i in range(tx):
+                    k = p * per_plane + j * tx + i
+                    a = np.frombuffer(chunk(offs[k], cnts[k]), dtype=dt)
+                    hh, ww = min(th, H - j * th), min(tw, W - i * tw)
+                    if planar == 2:
+                        out[p, j * th:j * th + hh, i * tw:i * tw + ww] = a.reshape(th, tw)[:hh, :ww]
+                    else:
+                        out[:, j * th:j * th + hh, i * tw:i * tw + ww] = a.reshape(th, tw, C)[:hh, :ww].transpose(2, 0, 1)
+    else:
+        rps = int(t.get(278, (H,))[0])
+        offs, cnts = t[273], t[279]
+        ns = (H + rps - 1) // rps
+        for p in range(C if planar == 2 else 1):
+            for s_ in range(ns):
+                k = p * ns + s_
+                r0 = s_ * rps
+                hh = min(rps, H - r0)
+                a = np.frombuffer(chunk(offs[k], cnts[k]), dtype=dt)
+                if planar == 2:
+                    out[p, r0:r0 + hh] = a[:hh * W].reshape(hh, W)
+                else:
+                    out[:, r0:r0 + hh] = a[:hh * W * C].reshape(hh, W, C).transpose(2, 0, 1)
+    if window is not None:
+        c0, r0, w, h = window
+        out = np.ascontiguousarray(out[:, r0:r0 + h, c0:c0 + w])
+        a, b, c, d, e, f = info.transform
+        info = GeoInfo(w, h, C, info.dtype, (a, b, a * c0 + b * r0 + c, d, e, d * c0 + e * r0 + f), info.epsg, info.nodata)
+    return out, info
+
+
+def write(path, array, transform, epsg=None, nodata=None):
+    """Uncompressed, little-endian, planar (band-sequential) strips -- one strip per band row
+    block, so that a device tensor's (bands, H, W) layout is written without a transpose."""
+    arr = np.ascontiguousarray(array)
+    if arr.ndim == 2:
+        arr = arr[None]
+    C, H, W = arr.shape
+    dt = arr.dtype
+    fmt = {"u": 1, "i": 2, "f": 3}[dt.kind]
+    bits = dt.itemsize * 8
+    rps = max(1, min(H, (1 << 22) // max(1, W * dt.itemsize)))
+    ns = (H + rps - 1) // rps
+    a, b, c, d, e, f = transform
+    entries = []
+    extra = bytearray()
+
+    def add(tag, typ, values):
+        fmtc, size = _TYPES[typ]
+        if typ == 2:
+            raw = values.encode("latin1") + b"\x00"
+            cnt = len(raw)
+        else:
+            cnt = len(values)
+            raw = struct.pack("<" + fmtc * cnt, *values)
+        entries.append((tag, typ, cnt, raw))
+
+    add(256, 4, [W]); add(257, 4, [H]); add(258, 3, [bits] * C); add(259, 3, [1])
+    add(262, 3, [1]); add(277, 3, [C]); add(278, 4, [rps]); add(284, 3, [2]); add(339, 3, [fmt] * C)
+    if C > 1:
+        add(338, 3, [0] * (C - 1))
+    add(33550, 12, [abs(a), abs(e), 0.0])
+    add(33922, 12, [0.0, 0.0, 0.0, c, f, 0.0])
+    if epsg is not None:
+        add(34735, 3, [1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 1, 3072, 0, 1, int(epsg)])
+    if nodata is not None:
+        add(42113, 2, repr(float(nodata)))
+    strip_bytes = [min(rps, H - s * rps) * W * dt.itemsize for s in range(ns)] * C
+    add(273, 4, [0] * (ns * C)); add(279, 4, strip_bytes)
+    entries.sort(key=lambda x: x[0])
+    ifd_off = 8
+    ifd_size = 2 + 12 * len(entries) + 4
+    extra_off = ifd_off + ifd_size
+    # layout: header | IFD | out-of-line values | pixel data
+    pos = extra_off
+    placed = []
+    for tag, typ, cnt, raw in entries:
+        if len(raw) <= 4:
+            placed.append((tag, typ, cnt, raw.ljust(4, b"\x00"), None))
+        else:
+            placed.append((tag, typ, cnt, struct.pack("<I", pos), raw))
+            pos += len(raw) + (len(raw) & 1)
+    data_off = (pos + 15) & ~15
+    offsets, o = [], data_off
+    for sb in strip_bytes:
+        offsets.append(o); o += sb
+    if o >= (1 << 32):
+        raise ValueError("raster too large for classic TIFF")
+    with open(path, "wb") as fh:
+        fh.write(b"II" + struct.pack("<HI", 42, ifd_off))
+        fh.write(struct.pack("<H", len(placed)))
+        blob = bytearray()
+        for tag, typ, cnt, val, raw in placed:
+            if tag == 273:
+                raw = struct.pack("<" + "I" * len(offsets), *offsets)
+                if len(raw) <= 4:
+                    val, raw = raw.ljust(4, b"\x00"), None
+            fh.write(struct.pack("<HHI", tag, typ, cnt) + val)
+            if raw is not None:
+                blob += raw + (b"\x00" if len(raw) & 1 else b"")
+        fh.write(struct.pack("<I", 0))
+        fh.write(bytes(blob))
+        fh.write(b"\x00" * (data_off - extra_off - len(blob)))
+        fh.write(arr.astype(dt.newbyteorder("<"), copy=False).tobytes())

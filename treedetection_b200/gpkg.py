@@ -1,0 +1,154 @@
+"""GeoPackage (SQLite + GeoPackageBinary/WKB) codec for the vector artefacts of the path.
+
+The reference writes ``geojson_predictions/<image>.gpkg`` through geopandas
+(``TreeDetection/helpers.py:545-548``: columns ``Confidence_score`` + geometry) and
+``processed_<image>.gpkg`` through fiona (``TreeDetection/postprocessing.py:904-939``:
+``Confidence_score, poly_id, Area, TreeHeight, Centroid, Diameter, is_contained,
+num_contained``).  fiona / geopandas / GDAL are absent here; this module writes the same
+layers with the standard library so that QGIS / geopandas users see a drop-in
+(GeoPackage 1.2: application_id 'GPKG', user_version 10200, gpkg_spatial_ref_sys,
+gpkg_contents, gpkg_geometry_columns, one feature table, single-ring Polygon geometries).
+"""
+from __future__ import annotations
+
+import os
+import sqlite3
+import struct
+from datetime import datetime, timezone
+
+import numpy as np
+
+_WKT = {
+    4326: 'GEOGCS["WGS 84",DATUM["WGS_1984",SPHEROID["WGS 84",6378137,298.257223563]],PRIMEM["Greenwich",0],'
+          'UNIT["degree",0.0174532925199433],AUTHORITY["EPSG","4326"]]',
+    25832: 'PROJCS["ETRS89 / UTM zone 32N",GEOGCS["ETRS89",DATUM["European_Terrestrial_Reference_System_1989",'
+           'SPHEROID["GRS 1980",6378137,298.257222101]],PRIMEM["Greenwich",0],UNIT["degree",0.0174532925199433]],'
+           'PROJECTION["Transverse_Mercator"],PARAMETER["latitude_of_origin",0],PARAMETER["central_meridian",9],'
+           'PARAMETER["scale_factor",0.9996],PARAMETER["false_easting",500000],PARAMETER["false_northing",0],'
+           'UNIT["metre",1],AXIS["Easting",EAST],AXIS["Northing",NORTH],AUTHORITY["EPSG","25832"]]',
+}
+
+_SQL_TYPES = {"float": "REAL", "int": "MEDIUMINT", "str": "TEXT"}
+
+
+def _gpb_polygon(ring: np.ndarray, srs_id: int) -> bytes:
+    """GeoPackageBinary header (little endian, xy envelope) + WKB Polygon with one ring."""
+    n = ring.shape[0]
+    if n == 0:
+        return b"GP\x00" + bytes([0x11]) + struct.pack("<i", srs_id) + struct.pack("<BII", 1, 3, 0)
+    minx, miny = ring.min(axis=0)
+    maxx, maxy = ring.max(axis=0)
+    head = b"GP\x00" + bytes([0x03]) + struct.pack("<i", srs_id) + struct.pack("<4d", minx, maxx, miny, maxy)
+    return head + struct.pack("<BIII", 1, 3, 1, n) + np.ascontiguousarray(ring, dtype="<f8").tobytes()
+
+
+def _parse_gpb(blob: bytes) -> np.ndarray:
+    flags = blob[3]
+    env = {0: 0, 1: 32, 2: 48, 3: 48, 4: 64}[(flags >> 1) & 7]
+    wkb = blob[8 + env:]
+    bo = "<" if wkb[0] == 1 else ">"
+    gtype, nrings = struct.unpack(bo + "II", wkb[1:9])
+    if gtype % 1000 == 6:      # MultiPolygon: first polygon (postprocessing.py:493-494)
+        wkb = wkb[9:]
+        bo = "<" if wkb[0] == 1 else ">"
+        gtype, nrings = struct.unpack(bo + "II", wkb[1:9])
+    if gtype % 1000 != 3 or nrings == 0:
+        return np.zeros((0, 2))
+    npts = struct.unpack(bo + "I", wkb[9:13])[0]
+    dims = 2 + (1 if gtype >= 1000 else 0)
+    pts = np.frombuffer(wkb, dtype=bo + "f8", count=npts * dims, offset=13).reshape(npts, dims)
+    return np.array(pts[:, :2], dtype=np.float64)
+
+
+def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=25832):
+    """verts (V,2) f64 + ring_off (R+1): one Polygon per ring.  columns: name -> sequence of
+    R values; schema: name -> 'float' | 'int' | 'str' (fiona's names), in column order."""
+    verts = np.asarray(verts, dtype=np.float64).reshape(-1, 2)
+    ring_off = np.asarray(ring_off, dtype=np.int64)
+    n = len(ring_off) - 1
+    if os.path.exists(path):
+        os.remove(path)
+    con = sqlite3.connect(path)
+    try:
+        cur = con.cursor()
+        cur.execute("PRAGMA application_id = 1196444487")      # 'GPKG'
+        cur.execute("PRAGMA user_version = 10200")
+        cur.execute("CREATE TABLE gpkg_spatial_ref_sys (srs_name TEXT NOT NULL, srs_id INTEGER NOT NULL PRIMARY KEY, "
+                    "organization TEXT NOT NULL, organization_coordsys_id INTEGER NOT NULL, definition TEXT NOT NULL, "
+                    "description TEXT)")
+        rows = [("Undefined cartesian SRS", -1, "NONE", -1, "undefined", "undefined cartesian coordinate reference system"),
+                ("Undefined geographic SRS", 0, "NONE", 0, "undefined", "undefined geographic coordinate reference system"),
+                ("WGS 84 geodetic", 4326, "EPSG", 4326, _WKT[4326], "longitude/latitude coordinates in decimal degrees")]
+        if epsg not in (-1, 0, 4326):
+            rows.append((f"EPSG:{epsg}", epsg, "EPSG", epsg, _WKT.get(epsg, "undefined"), None))
+        cur.executemany("INSERT INTO gpkg_spatial_ref_sys VALUES (?,?,?,?,?,?)", rows)
+        cur.execute("CREATE TABLE gpkg_contents (table_name TEXT NOT NULL PRIMARY KEY, data_type TEXT NOT NULL, "
+                    "identifier TEXT UNIQUE, description TEXT DEFAULT '', last_change DATETIME NOT NULL, min_x DOUBLE, "
+                    "min_y DOUBLE, max_x DOUBLE, max_y DOUBLE, srs_id INTEGER)")
+        cur.execute("CREATE TABLE gpkg_geometry_columns (table_name TEXT NOT NULL, column_name TEXT NOT NULL, "
+                    "geometry_type_name TEXT NOT NULL, srs_id INTEGER NOT NULL, z TINYINT NOT NULL, m TINYINT NOT NULL, "
+                    "CONSTRAINT pk_geom_cols PRIMARY KEY (table_name, column_name))")
+        cols_sql = ", ".join(f'"{k}" {_SQL_TYPES[v]}' for k, v in schema.items())
+        cur.execute(f'CREATE TABLE "{layer}" (fid INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, geom POLYGON'
+                    + (", " + cols_sql if cols_sql else "") + ")")
+        if len(verts):
+            mn, mx = verts.min(axis=0), verts.max(axis=0)
+            ext = (float(mn[0]), float(mn[1]), float(mx[0]), float(mx[1]))
+        else:
+            ext = (None, None, None, None)
+        now = datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%S.000Z")
+        cur.execute("INSERT INTO gpkg_contents VALUES (?,?,?,?,?,?,?,?,?,?)",
+                    (layer, "features", layer, "", now, *ext, epsg))
+        cur.execute("INSERT INTO gpkg_geometry_columns VALUES (?,?,?,?,?,?)", (layer, "geom", "POLYGON", epsg, 0, 0))
+        names = list(schema.keys())
+        conv = {"float": float, "int": int, "str": str}
+        data = []
+        for i in range(n):
+            ring = verts[ring_off[i]:ring_off[i + 1]]
+            rec = [_gpb_polygon(ring, epsg)]
+            for k in names:
+                v = columns[k][i]
+                rec.append(None if v is None else conv[schema[k]](v))
+            data.append(rec)
+        ph = ",".join("?" * (1 + len(names)))
+        colnames = ", ".join(["geom"] + [f'"{k}"' for k in names])
+        cur.executemany(f'INSERT INTO "{layer}" ({colnames}) VALUES ({ph})', data)
+        con.commit()
+    finally:
+        con.close()
+
+
+def read_layer(path, layer=None):
+    """Returns (verts (V,2) f64, ring_off (R+1) i64, columns dict name -> list, epsg)."""
+    con = sqlite3.connect(path)
+    try:
+        cur = con.cursor()
+        if layer is None:
+            row = cur.execute("SELECT table_name FROM gpkg_contents WHERE data_type='features'").fetchone()
+            if row is None:
+                return np.zeros((0, 2)), np.zeros(1, dtype=np.int64), {}, None
+            layer = row[0]
+        gcol, epsg = cur.execute("SELECT column_name, srs_id FROM gpkg_geometry_columns WHERE table_name=?",
+                                 (layer,)).fetchone()
+        info = cur.execute(f'PRAGMA table_info("{layer}")').fetchall()
+        pk = [r[1] for r in info if r[5]]
+        names = [r[1] for r in info if r[1] != gcol and r[1] not in pk]
+        sel = ", ".join([f'"{gcol}"'] + [f'"{k}"' for k in names])
+        order = f' ORDER BY "{pk[0]}"' if pk else ""
+        rings, cols = [], {k: [] for k in names}
+        for rec in cur.execute(f'SELECT {sel} FROM "{layer}"{order}'):
+            rings.append(_parse_gpb(rec[0]) if rec[0] is not None else np.zeros((0, 2)))
+            for k, v in zip(names, rec[1:]):
+                cols[k].append(v)
+    finally:
+        con.close()
+    off = np.zeros(len(rings) + 1, dtype=np.int64)
+    if rings:
+        off[1:] = np.cumsum([len(r) for r in rings])
+    verts = np.concatenate(rings) if rings and off[-1] > 0 else np.zeros((0, 2))
+    return verts, off, cols, epsg
+
+
+PROCESSED_SCHEMA = {"Confidence_score": "float", "poly_id": "str", "Area": "float", "TreeHeight": "float",
+                    "Centroid": "str", "Diameter": "float", "is_contained": "str", "num_contained": "int"}
+STITCHED_SCHEMA = {"Confidence_score": "float"}
