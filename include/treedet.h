@@ -41,15 +41,20 @@ int td_device_sms(void);            /* SM count of the current device (148 on B2
  * Replaces Predictor._process_tile (TreeDetection/prediction.py:159-176): rasterio.mask
  * crop of the tile window, band reorder (2,1,0), optional 255*x/65535 for 16-bit data,
  * detectron2 ResizeShortestEdge(800, 1333) (PIL bilinear for uint8), float32 CHW.
- *   image      (bands, H, W) planar uint8 (elem_size 1) or uint16 (elem_size 2), device
+ * Plan / execute: the tile tables (windows, PIL coefficient tables) are built and uploaded
+ * once per tiling, every image with that tiling re-uses the plan.
  *   tile_win   HOST (T,4) int32 [col_off, row_off, w, h]   (tiling.tile_grid)
  *   tile_net   HOST (T,2) int32 [net_h, net_w]             (tiling.resize_shortest_edge)
  *   out_off    HOST (T+1) int64 float offsets of each tile's (3, net_h, net_w) block in `out`
+ *   elem_size  1 = uint8 raster, 2 = uint16 raster; H, W = raster size                    */
+int td_tile_plan_create(const int* tile_win, const int* tile_net, const long long* out_off, int n_tiles,
+                        int elem_size, int H, int W, void** plan_out);
+int td_tile_plan_destroy(void* plan);
+/*   image      (bands, H, W) planar raster on the device (16-byte aligned `out`)
  *   rescale16  (T) uint8 out, may be null: 0 = uint8 tile, 1 = 16-bit branch taken
  *              (max(band 1) > 255), 2 = uint16 tile the reference fails on (left untouched) */
-int td_tile_cut_normalize(const void* image, int elem_size, int bands, int H, int W, const int* tile_win,
-                          const int* tile_net, int n_tiles, const long long* out_off, float* out,
-                          unsigned char* rescale16, void* stream);
+int td_tile_cut_normalize(const void* plan, const void* image, int bands, float* out, unsigned char* rescale16,
+                          void* stream);
 
 /* ---- P2: mask paste + threshold + bit-pack -------------------------------------------
  * Replaces detectron2 detector_postprocess + paste_masks_in_image + _do_paste_mask

@@ -1,0 +1,129 @@
+"""Drop-in API on the B200: get_config -> preprocess_files -> predict_tiles ->
+postprocess_files on a two-image synthetic mosaic (seam strip included), artefacts in the
+reference's directory layout, final crowns compared with the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from oracle import port
+from treedetection_b200 import detection, geo, geotiff, gpkg, predictor, synth
+
+pytestmark = pytest.mark.gpu
+
+PX = 0.2
+
+
+def _project(tmp_path):
+    left, bottom = synth.ORIGIN_X, synth.ORIGIN_Y
+    field = synth.tree_field(77, 400.0, 200.0, 5000.0, left, bottom)
+    rgbi = synth.make_rgbi(field, PX, 77)            # (4, 1000, 2000)
+    ndsm = synth.make_ndsm(field, 1.0, 77)           # (200, 400)
+    img_dir, h_dir = tmp_path / "rgb", tmp_path / "ndsm"
+    img_dir.mkdir(); h_dir.mkdir()
+    top = bottom + 200.0
+    for k, name in enumerate(("000001", "000002")):
+        x0 = left + 200.0 * k
+        geotiff.write(str(img_dir / f"FDOP20_{name}_rgbi.tif"), rgbi[:, :, 1000 * k:1000 * (k + 1)],
+                      (PX, 0.0, x0, 0.0, -PX, top), epsg=25832)
+        geotiff.write(str(h_dir / f"nDSM_{name}_1km.tif"), ndsm[:, 200 * k:200 * (k + 1)],
+                      (1.0, 0.0, x0, 0.0, -1.0, top), epsg=25832, nodata=-3.4028234663852886e38)
+    model = tmp_path / "model_fixtures"
+    model.mkdir()
+    cfg = {
+        "image_directory": str(img_dir), "height_data_path": str(h_dir),
+        "image_regex": "FDOP20_(\\d+)_rgbi\\.tif", "height_data_regex": "nDSM_(\\d+)_1km\\.tif",
+        "combined_model": str(model), "output_directory": str(tmp_path / "output"), "tiles_path": str(tmp_path / "tiles"),
+        "use_overlap": True, "merged_path": "merged", "overlapping_tiles_width": 3, "overlapping_tiles_height": 3,
+        "image_merged_regex": "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_rgbi\\.tif",
+        "height_data_merged_regex": "nDSM_(\\d+)(\\d+)_1km\\.tif",
+        "tile_width": 50, "tile_height": 50, "buffer": 20, "batch_size": 10,
+        "ndvi_scaling_factor": 0.2, "height_scaling_factor": 1.0, "confidence_threshold": 0.3,
+        "containment_threshold": 0.75, "height_threshold": 3, "ndvi_mean_threshold": 0.1, "ndvi_var_threshold": 0.1,
+        "iou_threshold": 0.6, "confidence_threshold_stitching": 0.3, "area_threshold": 1, "parallel": True,
+        "num_workers": 5, "keep_intermediate": True, "device": "0",
+    }
+    path = tmp_path / "config.yml"
+    path.write_text(yaml.safe_dump(cfg))
+    return str(path), field, model
+
+
+def test_process_files_end_to_end(tmp_path):
+    cfg_path, field, model = _project(tmp_path)
+    config, cfg_obj = detection.get_config(cfg_path)
+    assert cfg_obj.tile_width == 50 and config["simplify_tolerance"] == 0.2 and config["device"] == "0"
+    images = detection.preprocess_files(config)
+    # two images + the right-seam strip (270 px wide, full height)
+    assert len(images) == 3
+    strip = [p for p in images if "merged" in p]
+    assert len(strip) == 1 and os.path.basename(strip[0]) == "FDOP20_412000_5318200_412200_5318200_rgbi.tif"
+    sinfo = geotiff.read_info(strip[0])
+    assert (sinfo.width, sinfo.height) == (270, 1000)
+    assert os.path.exists(os.path.join(config["height_data_path"], "merged", "nDSM_41200053182004122005318200_1km.tif"))
+    assert os.path.exists(os.path.join(config["tiles_path"], "recovery.yaml"))
+    # stage the "model": ROI-head fixtures for every image, from the same tree field
+    dets = {}
+    for p in images:
+        stem = os.path.splitext(os.path.basename(p))[0]
+        tiles = json.load(open(os.path.join(config["tiles_path"], stem + ".json")))
+        dets[stem] = synth.make_detections(field, tiles, PX, seed=5)
+        predictor.dump_fixtures(str(model), stem, dets[stem])
+    detection.predict_tiles(config)
+    detection.postprocess_files(config)
+    out = config["output_directory"]
+    for p in images:
+        stem = os.path.splitext(os.path.basename(p))[0]
+        assert os.path.exists(os.path.join(out, "geojson_predictions", stem + ".gpkg"))
+        assert os.path.exists(os.path.join(out, "geojson_predictions", f"processed_{stem}.gpkg"))
+        assert os.path.exists(os.path.join(out, stem + ".gpkg"))
+        assert os.path.isdir(os.path.join(out, "predictions", stem))
+    # ---- parity of one plain image and of the seam strip with the oracle ----
+    for p in (images[0], strip[0]):
+        stem = os.path.splitext(os.path.basename(p))[0]
+        tiles = json.load(open(os.path.join(config["tiles_path"], stem + ".json")))
+        rings, conf = port.predict_stage(dets[stem], tiles)
+        v, o, cols, epsg = gpkg.read_layer(os.path.join(out, "geojson_predictions", stem + ".gpkg"))
+        assert epsg == 25832 and len(o) - 1 == len(rings)
+        np.testing.assert_array_equal(v, np.array([q for r in rings for q in r]).reshape(-1, 2))
+        np.testing.assert_array_equal(np.array(cols["Confidence_score"]), np.array(conf))
+        rgbi, rinfo = geotiff.read(p)
+        if "merged" in p:
+            hp = os.path.join(config["height_data_path"], "merged", "nDSM_41200053182004122005318200_1km.tif")
+        else:
+            hp = os.path.join(config["height_data_path"], "nDSM_000001_1km.tif")
+        ndsm, hinfo = geotiff.read(hp)
+        H, W = rgbi.shape[1:]
+        oh, ow = int(H * 0.2), int(W * 0.2)
+        dec = np.stack([port.decimate_bilinear(rgbi[b], oh, ow) for b in (0, 0, 0, 3)])
+        ndvi = port.ndvi_from_rgbi(dec).astype(np.float32)
+        ndvi_tf = geo.compose(rinfo.transform, geo.scale(W / ow, H / oh))
+        want, dbg = port.post_process(rings, conf, ndvi, ndvi_tf, tuple(geo.raster_bounds(rinfo.transform, W, H)),
+                                      ndsm[0], hinfo.transform,
+                                      tuple(geo.raster_bounds(hinfo.transform, hinfo.width, hinfo.height)), PX, PX,
+                                      config)
+        v, o, cols, _ = gpkg.read_layer(os.path.join(out, stem + ".gpkg"))
+        assert list(cols.keys()) == list(gpkg.PROCESSED_SCHEMA.keys())
+        assert cols["poly_id"] == [w["poly_id"] for w in want]
+        np.testing.assert_array_equal(np.array(cols["Area"]), np.array([w["Area"] for w in want]))
+        np.testing.assert_array_equal(np.array(cols["TreeHeight"], dtype=np.float32),
+                                      np.array([w["TreeHeight"] for w in want], dtype=np.float32))
+        assert cols["is_contained"] == [str(w["is_contained"]) for w in want]
+        assert cols["Centroid"] == [json.dumps({"x": w["Centroid"][0], "y": w["Centroid"][1]}) for w in want]
+        np.testing.assert_array_equal(v, np.array([q for w in want for q in w["coords"]]).reshape(-1, 2))
+        if "merged" not in p:
+            assert len(want) > 10
+    # cleanup removes intermediates unless asked to keep them
+    config["keep_intermediate"] = False
+    detection.cleanup_files(config)
+    assert not os.path.exists(config["tiles_path"])
+    assert sorted(os.listdir(out)) == sorted(["logs"] + [os.path.splitext(os.path.basename(p))[0] + ".gpkg"
+                                                        for p in images])
+
+
+def test_config_errors(tmp_path):
+    p = tmp_path / "c.yml"
+    p.write_text(yaml.safe_dump({"image_directory": str(tmp_path / "missing"), "height_data_path": str(tmp_path)}))
+    with pytest.raises(AssertionError):
+        detection.get_config(str(p))

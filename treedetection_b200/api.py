@@ -54,6 +54,14 @@ class TileTables:
         self.tile_tf, boxes_int = pipeline.tile_tables(tiles, device)
         self.tile_boxes = pipeline.filter_boxes(boxes_int, shift, device)
         self.p1_floats = int((3 * self.net[:, 0].long() * self.net[:, 1].long()).sum())
+        self._plans = {}
+
+    def plan(self, image):
+        """P1 plan (device tile tables) for rasters shaped like ``image``; built once."""
+        key = (image.element_size(), image.shape[1], image.shape[2])
+        if key not in self._plans:
+            self._plans[key] = ops.TilePlan(self.win, self.net, *key)
+        return self._plans[key]
 
 
 def features_to_host(f: pipeline.Features):
@@ -81,7 +89,7 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     tile_dims = img.tile_dims.to(device, non_blocking=nb)
     tiles_out = None
     if with_p1:
-        tiles_out, _, _ = ops.tile_cut_normalize(rgbi, tables.win, tables.net, out=p1_out)
+        tiles_out, _, _ = tables.plan(rgbi).run(rgbi, p1_out)
     table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf, tables.tile_boxes, params)
     rasters = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
     feats = pipeline.postprocess_stage(table, rasters, params)

@@ -13,6 +13,21 @@ void td_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Temporary scratch comes from the device's default stream-ordered pool.  Its default release
+// threshold is 0, i.e. every stream synchronisation hands the freed blocks back to the OS and
+// the next call pays for mapping them again (milliseconds); keep them cached instead.
+void td_ensure_pool() {
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done[dev] = true;
+}
+
 extern "C" int td_version() { return 100; }  // 0.1.0
 
 extern "C" const char* td_last_error() { return g_err; }

@@ -26,6 +26,7 @@
 
 #if defined(__CUDACC__)
 void td_set_error(const char* fmt, ...);
+void td_ensure_pool();   // keeps the stream-ordered scratch pool cached across synchronisations
 
 #define TD_CHECK_LAUNCH(name)                                                        \
   do {                                                                               \

@@ -5,8 +5,8 @@
 // identity resize, cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE), contour.size >= 8,
 // closing point) and xy_gpu (TreeDetection/utilities.py:182-207: corner convention,
 // float64).  The reference moves H*W*4 bytes to the device and back and launches ~8
-// kernels per contour; here one thread walks one instance window (the algorithm is
-// inherently sequential per instance, there are ~10^5 independent instances per image).
+// kernels per contour; here one warp owns one instance window staged in shared memory (the walk
+// is inherently sequential per instance, there are ~10^5 independent instances per image).
 //
 // Two passes because output sizes are data dependent: td_trace_count returns, per
 // instance, the number of borders / points / kept rings / ring vertices; after a scan
@@ -16,27 +16,70 @@
 
 namespace {
 
-__global__ void __launch_bounds__(64)
-trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ win, const long long* __restrict__ word_off,
-                   int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+constexpr int kTraceWarps = 4;                 // instances per CTA (one warp each)
+constexpr int kTraceSmemPerWarp = 12 * 1024;   // bit planes (+ labels) of a window live here when they fit
+
+// Border following is sequential per instance, and every step depends on the previous
+// pixel test: run from global memory a step costs an L2 round trip.  So one WARP owns one
+// instance: the lanes copy the window's foreground plane into shared memory (and clear the
+// two scratch planes), lane 0 walks the borders at shared-memory latency, and in the emit
+// pass all lanes write the ring vertices.  Windows that do not fit the per-warp budget
+// (12 KB: e.g. 180 x 180 px for counting, ~70 x 70 px with labels) fall back to the global
+// scratch planes.
+struct WarpRaster {
   td::Raster R;
+  bool in_smem;
+};
+
+__device__ WarpRaster stage_window(const uint32_t* bits, const int* win, const long long* word_off, int i,
+                                   uint32_t* planes, long long total_words, unsigned short* labels_global,
+                                   unsigned char* smem_warp, bool want_labels) {
+  WarpRaster W;
+  td::Raster& R = W.R;
   R.w = win[4 * i + 2];
   R.h = win[4 * i + 3];
   R.wpr = (R.w + 31) >> 5;
-  td::ContourCounts cc = {0, 0, 0, 0};
-  if (R.w > 0 && R.h > 0) {
-    R.fg = bits + word_off[i];
+  const int lane = threadIdx.x & 31;
+  const int nwords = R.wpr * R.h;
+  const uint32_t* fg = bits + word_off[i];
+  const size_t need = (size_t)12 * nwords + (want_labels ? (size_t)2 * R.w * R.h : 0);
+  W.in_smem = nwords > 0 && need <= (size_t)kTraceSmemPerWarp;
+  if (W.in_smem) {
+    uint32_t* s_fg = reinterpret_cast<uint32_t*>(smem_warp);
+    uint32_t* s_vis = s_fg + nwords;
+    uint32_t* s_rgt = s_vis + nwords;
+    for (int k = lane; k < nwords; k += 32) { s_fg[k] = fg[k]; s_vis[k] = 0u; s_rgt[k] = 0u; }
+    R.fg = s_fg; R.visited = s_vis; R.right = s_rgt;
+    R.label = want_labels ? reinterpret_cast<unsigned short*>(s_rgt + nwords) : nullptr;
+  } else {
+    R.fg = fg;
     R.visited = planes + word_off[i];
     R.right = planes + total_words + word_off[i];
-    R.label = nullptr;
-    cc = td::scan_instance(R, nullptr);
+    R.label = want_labels ? labels_global : nullptr;
   }
-  counts[4 * i + 0] = cc.n_contours;
-  counts[4 * i + 1] = cc.n_points;
-  counts[4 * i + 2] = cc.n_rings;
-  counts[4 * i + 3] = cc.n_ring_verts;
+  __syncwarp();
+  return W;
+}
+
+__global__ void __launch_bounds__(32 * kTraceWarps)
+trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ win, const long long* __restrict__ word_off,
+                   int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kTraceWarps + warp;
+  if (i >= n) return;
+  td::ContourCounts cc = {0, 0, 0, 0};
+  if (win[4 * i + 2] > 0 && win[4 * i + 3] > 0) {
+    WarpRaster W = stage_window(bits, win, word_off, i, planes, total_words, nullptr,
+                                smem + (size_t)warp * kTraceSmemPerWarp, false);
+    if (lane == 0) cc = td::scan_instance(W.R, nullptr);
+  }
+  if (lane == 0) {
+    counts[4 * i + 0] = cc.n_contours;
+    counts[4 * i + 1] = cc.n_points;
+    counts[4 * i + 2] = cc.n_rings;
+    counts[4 * i + 3] = cc.n_ring_verts;
+  }
 }
 
 struct EmitArgs {
@@ -65,33 +108,32 @@ struct EmitArgs {
   double* verts;               // (V, 2)
 };
 
-__global__ void __launch_bounds__(64) trace_emit_kernel(EmitArgs A) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * kTraceWarps) trace_emit_kernel(EmitArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kTraceWarps + warp;
   if (i >= A.n) return;
-  td::Raster R;
   const int wx0 = A.win[4 * i + 0], wy0 = A.win[4 * i + 1];
-  R.w = A.win[4 * i + 2];
-  R.h = A.win[4 * i + 3];
-  R.wpr = (R.w + 31) >> 5;
-  if (R.w <= 0 || R.h <= 0) return;
+  if (A.win[4 * i + 2] <= 0 || A.win[4 * i + 3] <= 0) return;
   const long long c0 = A.cont_off[i];
   const int nc = (int)(A.cont_off[i + 1] - c0);
   if (nc == 0) return;
-  R.fg = A.bits + A.word_off[i];
-  R.visited = A.planes + A.word_off[i];
-  R.right = A.planes + A.total_words + A.word_off[i];
-  R.label = A.labels + A.px_off[i];
+  WarpRaster W = stage_window(A.bits, A.win, A.word_off, i, A.planes, A.total_words, A.labels + A.px_off[i],
+                              smem + (size_t)warp * kTraceSmemPerWarp, true);
   td::ContourOut out;
   out.parent = A.ct_parent + c0;
   out.npts = A.ct_npts + c0;
   out.pt_off = A.ct_ptoff + c0;
   out.is_hole = A.ct_hole + c0;
   out.pts = A.pts + 2 * A.pts_off[i];
-  td::scan_instance(R, &out);
   int* last_child = A.ct_scratch + 3 * c0;
   int* prev_sib = last_child + nc;
   int* order = prev_sib + nc;
-  td::contour_order(nc, out.parent, last_child, prev_sib, order);
+  if (lane == 0) {
+    td::scan_instance(W.R, &out);
+    td::contour_order(nc, out.parent, last_child, prev_sib, order);
+  }
+  __syncwarp();   // lane 0's tables and points become visible to the warp
   const double* tf = A.tile_tf + 6 * (size_t)A.inst_tile[i];
   const double ta = tf[0], tb = tf[1], tc = tf[2], td_ = tf[3], te = tf[4], tff = tf[5];
   long long ring = A.ring_base[i];
@@ -101,19 +143,21 @@ __global__ void __launch_bounds__(64) trace_emit_kernel(EmitArgs A) {
     const int np = out.npts[c];
     if (np < 4) continue;
     const short* p = out.pts + 2 * (size_t)out.pt_off[c];
-    A.ring_off[ring] = v;
-    A.ring_inst[ring] = i;
-    ++ring;
     const bool close = (p[0] != p[2 * (np - 1)]) || (p[1] != p[2 * (np - 1) + 1]);
     const int nv = np + (close ? 1 : 0);
-    for (int q = 0; q < nv; ++q) {
+    if (lane == 0) {
+      A.ring_off[ring] = v;
+      A.ring_inst[ring] = i;
+    }
+    for (int q = lane; q < nv; q += 32) {
       const int qq = q < np ? q : 0;
       const double col = (double)(p[2 * qq] + wx0), row = (double)(p[2 * qq + 1] + wy0);
       // xy_gpu: a * x + b * y + c, every operation rounded (float64)
-      A.verts[2 * v] = __dadd_rn(__dadd_rn(__dmul_rn(ta, col), __dmul_rn(tb, row)), tc);
-      A.verts[2 * v + 1] = __dadd_rn(__dadd_rn(__dmul_rn(td_, col), __dmul_rn(te, row)), tff);
-      ++v;
+      A.verts[2 * (v + q)] = __dadd_rn(__dadd_rn(__dmul_rn(ta, col), __dmul_rn(tb, row)), tc);
+      A.verts[2 * (v + q) + 1] = __dadd_rn(__dadd_rn(__dmul_rn(td_, col), __dmul_rn(te, row)), tff);
     }
+    ++ring;
+    v += nv;
   }
 }
 
@@ -127,7 +171,8 @@ extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long l
   TD_ARG(bits && win && word_off && planes && counts);
   cudaStream_t st = (cudaStream_t)stream;
   TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
-  trace_count_kernel<<<td_div_up(n_inst, 64), 64, 0, st>>>(bits, win, word_off, n_inst, planes, total_words, counts);
+  trace_count_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kTraceSmemPerWarp, st>>>(
+      bits, win, word_off, n_inst, planes, total_words, counts);
   TD_CHECK_LAUNCH("td_trace_count");
   return TD_OK;
 }
@@ -156,7 +201,7 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   A.ct_scratch = ct_int5 + 3 * total_contours;
   A.ct_hole = ct_hole; A.pts = pts; A.inst_tile = inst_tile; A.tile_tf = tile_tf;
   A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
-  trace_emit_kernel<<<td_div_up(n_inst, 64), 64, 0, st>>>(A);
+  trace_emit_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kTraceSmemPerWarp, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
   return TD_OK;
 }

@@ -8,20 +8,23 @@
 // `within` a rectangle is envelope containment for an areal geometry (GEOS
 // RectangleContains), so the filter is four comparisons on the simplified ring's bounds.
 //
-// One thread simplifies one ring (the algorithm is a sequential stack machine; there are
-// ~10^5 rings per image).  Results are index lists into the input ring, so a second tiny
+// One warp simplifies one ring: the algorithm is a sequential stack machine (run redundantly by
+// all lanes) whose inner scans are split over the lanes; there are ~10^5 rings per image.  Results are index lists into the input ring, so a second tiny
 // kernel (td_take_rings) gathers the surviving vertices once the caller has scanned the counts.
 #include "common.cuh"
 #include "simplify_core.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(64)
+// one warp per ring: the stack machine runs redundantly on all lanes, the farthest-point
+// and intersection scans are strided over the lanes (td::WarpCoop)
+__global__ void __launch_bounds__(128)
 simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
                 int* __restrict__ scratch, uint32_t* __restrict__ alive, const double* __restrict__ boxes,
                 const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
                 double* __restrict__ out_area, unsigned char* __restrict__ out_keep) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const long long v0 = ring_off[r];
   const int len = (int)(ring_off[r + 1] - v0);
@@ -31,22 +34,31 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   uint32_t* al = alive + (v0 >> 5) + r;
   int m;
   if (tol > 0.0 && len > 0) {
-    m = td::simplify_ring(pts, len, tol, sc, al);
+    m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
   } else {  // helpers.py:463: simplification is skipped for a non-positive tolerance
-    for (int k = 0; k < len; ++k) sc[k] = k;
+    for (int k = lane; k < len; k += 32) sc[k] = k;
     m = len;
   }
-  out_count[r] = m;
+  __syncwarp();
   double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-  for (int k = 0; k < m; ++k) {
+  for (int k = lane; k < m; k += 32) {
     const td::P2 p = pts[sc[k]];
     minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
     miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+    maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+    miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+    maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+  }
+  if (lane != 0) return;
+  out_count[r] = m;
   if (out_bounds) {
     out_bounds[4 * r + 0] = minx; out_bounds[4 * r + 1] = miny;
     out_bounds[4 * r + 2] = maxx; out_bounds[4 * r + 3] = maxy;
   }
+  // the shoelace sum is order dependent: one lane, in ring order
   if (out_area) out_area[r] = fabs(td::ring_signed_area(m, [&](int k) { return pts[sc[k]]; }));
   if (out_keep) {
     bool keep = true;
@@ -90,7 +102,7 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
   if (n_rings == 0) return TD_OK;
   TD_ARG(verts && ring_off && scratch && alive && out_count);
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
-  simplify_kernel<<<td_div_up(n_rings, 64), 64, 0, (cudaStream_t)stream>>>(
+  simplify_kernel<<<td_div_up((long long)n_rings * 32, 128), 128, 0, (cudaStream_t)stream>>>(
       verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep);
   TD_CHECK_LAUNCH("td_simplify_rings");
   return TD_OK;

@@ -170,6 +170,7 @@ void free_axis(DevAxis& d, cudaStream_t st) {
 
 template <typename T, int EPI>
 int run_decimate(const T* s0, const T* s1, int in_h, int in_w, int out_h, int out_w, float* out, cudaStream_t st) {
+  td_ensure_pool();
   DevAxis dx, dy;
   int rc = upload_axis(in_w, out_w, kTileW, dx, st);
   if (rc == TD_OK) rc = upload_axis(in_h, out_h, kTileH, dy, st);

@@ -386,6 +386,7 @@ extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, con
   if (n == 0) return TD_OK;
   TD_ARG(bounds && conf && area && removed);
   cudaStream_t st = (cudaStream_t)stream;
+  td_ensure_pool();
   Scratch sc(st);
   float4* box32 = (float4*)sc.get(sizeof(float4) * n);
   GridParams* gp = (GridParams*)sc.get(sizeof(GridParams));
@@ -454,6 +455,7 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   if (n == 0) return TD_OK;
   TD_ARG(bounds32 && ratio_max && is_contained && num_contained);
   cudaStream_t st = (cudaStream_t)stream;
+  td_ensure_pool();
   Scratch sc(st);
   float4* box32 = (float4*)sc.get(sizeof(float4) * n);
   GridParams* gp = (GridParams*)sc.get(sizeof(GridParams));

@@ -228,6 +228,162 @@ tile_resize_u8_kernel(const unsigned char* __restrict__ image, long long image_b
   }
 }
 
+// ---- fast path: up-scaling (at most 2 taps per axis), the configuration of every tile
+// of the reference's example config (450 -> 800 px).  Same phases as above, tuned for
+// instruction count (the first version of this kernel was issue bound, not HBM bound):
+//   phase 0 looks its tile up in a per-CTA table, stages the window byte-aligned (funnel
+//           shift) so that later phases need no per-row shift;
+//   phase 1 makes 4 adjacent columns per thread and stores them as one packed word;
+//   phase 2 gives each warp 4 CONSECUTIVE output rows, so the two intermediate rows a
+//           row needs are usually already unpacked in registers (0.56 new rows per output
+//           row at 450 -> 800); no clipping is needed (2 non-negative taps summing to
+//           2^22 +- 1 cannot leave [0, 255]) and int -> float is one LOP + one FADD.
+__global__ void __launch_bounds__(kThreads)
+tile_resize_u8_up_kernel(const unsigned char* __restrict__ image, long long image_bytes, int H, int W,
+                         const TileDesc* __restrict__ tiles, const int2* __restrict__ blk,
+                         const int* __restrict__ tab_min, const int* __restrict__ tab_cnt,
+                         const int* __restrict__ tab_k, float* __restrict__ out, int max_rows, int src_stride) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char* s_src = smem;                                             // [3][max_rows][src_stride]
+  unsigned char* s_tmp = smem + (size_t)3 * max_rows * src_stride;         // [3][max_rows][kBX]
+  int4* s_ytab = reinterpret_cast<int4*>(s_tmp + (size_t)3 * max_rows * kBX + kBX);  // [kBY]: ys, k0, k1, -
+  const int2 me = blk[blockIdx.x];
+  const TileDesc T = tiles[me.x];
+  const int ox0 = (me.y & 0xffff) * kBX, oy0 = (me.y >> 16) * kBY;
+  const int ox_last = min(ox0 + kBX, T.nw) - 1, oy_last = min(oy0 + kBY, T.nh) - 1;
+  const int row_lo = tab_min[T.ytab + oy0];
+  const int nrows = tab_min[T.ytab + oy_last] + tab_cnt[T.ytab + oy_last] - row_lo;
+  const int col_lo = tab_min[T.xtab + ox0];
+  const int ncols = tab_min[T.xtab + ox_last] + tab_cnt[T.xtab + ox_last] - col_lo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kHalf = 1 << (kPrecisionBits - 1);
+  const size_t plane = (size_t)H * W;
+  const unsigned char* img_end = image + image_bytes;
+  // ---- phase 0: stage the window, one warp per source row, 32-bit loads ---------------------
+  {
+    const int nwords = (ncols + 3) >> 2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // output channel c reads band 2 - c (BGR order)
+      const unsigned char* base = image + (size_t)(2 - c) * plane + (size_t)(T.r_off + row_lo) * W + T.c_off + col_lo;
+      unsigned char* dst_c = s_src + (size_t)c * max_rows * src_stride;
+      for (int r = warp; r < nrows; r += kWarps) {
+        const unsigned char* a = base + (size_t)r * W;
+        const unsigned char* a0 = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(a) & ~(uintptr_t)3);
+        const int sh = 8 * (int)(a - a0);
+        for (int q = lane; q < nwords; q += 32) {
+          const unsigned char* wa = a0 + 4 * q;
+          uint32_t w0 = 0, w1 = 0;
+          if (wa + 8 <= img_end) {
+            w0 = *reinterpret_cast<const uint32_t*>(wa);
+            w1 = *reinterpret_cast<const uint32_t*>(wa + 4);
+          } else {
+            for (int z = 0; z < 4; ++z) {
+              if (wa + z < img_end) w0 |= (uint32_t)wa[z] << (8 * z);
+              if (wa + 4 + z < img_end) w1 |= (uint32_t)wa[4 + z] << (8 * z);
+            }
+          }
+          *reinterpret_cast<uint32_t*>(dst_c + (size_t)r * src_stride + 4 * q) = __funnelshift_r(w0, w1, sh);
+        }
+      }
+    }
+  }
+  if (threadIdx.x < kBY) {
+    const int oy = min(oy0 + (int)threadIdx.x, T.nh - 1);
+    const int* k = tab_k + (size_t)(T.ytab + oy) * kMaxK;
+    s_ytab[threadIdx.x] = make_int4(tab_min[T.ytab + oy] - row_lo, k[0], k[1], 0);
+  }
+  __syncthreads();
+  // ---- phase 1: horizontal pass, 4 columns per thread -----------------------------------------
+  const int x4 = 4 * lane;
+  {
+    int xs[4], k0[4], k1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ox = ox0 + x4 + j;
+      xs[j] = 0; k0[j] = 0; k1[j] = 0;
+      if (ox < T.nw) {
+        xs[j] = tab_min[T.xtab + ox] - col_lo;
+        const int2 kk = *reinterpret_cast<const int2*>(tab_k + (size_t)(T.xtab + ox) * kMaxK);
+        k0[j] = kk.x; k1[j] = kk.y;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned char* src_c = s_src + (size_t)c * max_rows * src_stride;
+      unsigned char* tmp_c = s_tmp + (size_t)c * max_rows * kBX + x4;
+      for (int r = warp; r < nrows; r += kWarps) {
+        const unsigned char* p = src_c + r * src_stride;
+        const int v0 = ((int)p[xs[0]] * k0[0] + (int)p[xs[0] + 1] * k1[0] + kHalf) >> kPrecisionBits;
+        const int v1 = ((int)p[xs[1]] * k0[1] + (int)p[xs[1] + 1] * k1[1] + kHalf) >> kPrecisionBits;
+        const int v2 = ((int)p[xs[2]] * k0[2] + (int)p[xs[2] + 1] * k1[2] + kHalf) >> kPrecisionBits;
+        const int v3 = ((int)p[xs[3]] * k0[3] + (int)p[xs[3] + 1] * k1[3] + kHalf) >> kPrecisionBits;
+        *reinterpret_cast<uint32_t*>(tmp_c + r * kBX) =
+            (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: vertical pass, 4 consecutive rows per warp, 4 pixels per lane -----------------
+  if (ox0 + x4 >= T.nw) return;
+  const size_t oplane = (size_t)T.nh * T.nw;
+  const bool vec = ((T.nw & 3) == 0) && ((T.out_off & 3) == 0);
+  constexpr int kRows = kBY / kWarps;
+  const int y_begin = warp * kRows;
+  float* orow = out + T.out_off + (size_t)(oy0 + y_begin) * T.nw + ox0 + x4;
+  const unsigned char* colbase = s_tmp + x4;
+  const int cstride = max_rows * kBX;
+  int cur = -2;
+  int a[3][4], bb[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[c][j] = 0; bb[c][j] = 0; }
+#pragma unroll
+  for (int yy = 0; yy < kRows; ++yy) {
+    if (oy0 + y_begin + yy >= T.nh) break;
+    const int4 e = s_ytab[y_begin + yy];
+    if (e.x != cur) {
+      const bool adv = (e.x == cur + 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (adv) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[c][j] = bb[c][j];
+        } else {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(colbase + c * cstride + e.x * kBX);
+          a[c][0] = u & 255u; a[c][1] = (u >> 8) & 255u; a[c][2] = (u >> 16) & 255u; a[c][3] = u >> 24;
+        }
+        // row e.x + 1 may be one past the staged rows when the tap count is 1: its weight is 0
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(colbase + c * cstride + (e.x + 1) * kBX);
+        bb[c][0] = u & 255u; bb[c][1] = (u >> 8) & 255u; bb[c][2] = (u >> 16) & 255u; bb[c][3] = u >> 24;
+      }
+      cur = e.x;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 f;
+      // exact int -> float for 0..255: (2^23 + v) as float bits, minus 2^23
+      f.x = __int_as_float(0x4B000000 | ((a[c][0] * e.y + bb[c][0] * e.z + kHalf) >> kPrecisionBits)) - 8388608.0f;
+      f.y = __int_as_float(0x4B000000 | ((a[c][1] * e.y + bb[c][1] * e.z + kHalf) >> kPrecisionBits)) - 8388608.0f;
+      f.z = __int_as_float(0x4B000000 | ((a[c][2] * e.y + bb[c][2] * e.z + kHalf) >> kPrecisionBits)) - 8388608.0f;
+      f.w = __int_as_float(0x4B000000 | ((a[c][3] * e.y + bb[c][3] * e.z + kHalf) >> kPrecisionBits)) - 8388608.0f;
+      float* dst = orow + c * oplane;
+      if (vec) {
+        __stcs(reinterpret_cast<float4*>(dst), f);
+      } else {
+        const int rem = T.nw - (ox0 + x4);
+        dst[0] = f.x;
+        if (rem > 1) dst[1] = f.y;
+        if (rem > 2) dst[2] = f.z;
+        if (rem > 3) dst[3] = f.w;
+      }
+    }
+    orow += T.nw;
+  }
+}
+
 // ---- uint16 images: per-tile max of band 1 decides the branch (prediction.py:167) ----------
 __global__ void tile_band1_max_kernel(const unsigned short* __restrict__ image, int H, int W,
                                       const TileDesc* __restrict__ tiles, int* __restrict__ tile_max) {
@@ -299,21 +455,26 @@ __global__ void seam_crop_kernel(const T* __restrict__ a, const T* __restrict__ 
 
 }  // namespace
 
+// ---- plan / execute: the tile tables are uploaded once per tiling --------------------------
+struct TilePlan {
+  int n_tiles = 0, elem_size = 1, H = 0, W = 0;
+  int max_nw = 0, max_nh = 0, max_rows = 1, max_cols = 1, max_k = 1, max_cnt = 0;
+  long long n_blocks = 0;
+  TileDesc* d_td = nullptr;
+  int *d_min = nullptr, *d_cnt = nullptr, *d_k = nullptr, *d_max = nullptr;
+  int2* d_blk = nullptr;   // per CTA: tile index, (block row << 16) | block column
+};
+
 // tile_win (T,4) [col_off,row_off,w,h], tile_net (T,2) [net_h,net_w], out_off (T+1): HOST pointers
-extern "C" int td_tile_cut_normalize(const void* image, int elem_size, int bands, int H, int W, const int* tile_win,
-                                     const int* tile_net, int n_tiles, const long long* out_off, float* out,
-                                     unsigned char* rescale16, void* stream) {
-  TD_ARG(n_tiles >= 0);
-  if (n_tiles == 0) return TD_OK;
-  TD_ARG(image && tile_win && tile_net && out_off && out);
-  TD_ARG(bands >= 3 && H > 0 && W > 0 && (elem_size == 1 || elem_size == 2));
-  TD_ARG(((uintptr_t)out & 15) == 0 && ((uintptr_t)image & 3) == 0);
-  cudaStream_t st = (cudaStream_t)stream;
+extern "C" int td_tile_plan_create(const int* tile_win, const int* tile_net, const long long* out_off, int n_tiles,
+                                   int elem_size, int H, int W, void** plan_out) {
+  TD_ARG(n_tiles > 0 && tile_win && tile_net && out_off && plan_out);
+  TD_ARG(H > 0 && W > 0 && (elem_size == 1 || elem_size == 2));
+  TilePlan* P = new TilePlan();
+  P->n_tiles = n_tiles; P->elem_size = elem_size; P->H = H; P->W = W;
   std::vector<TileDesc> td(n_tiles);
   std::map<std::pair<int, int>, std::pair<int, int>> tabs;  // (in,out) -> (offset, ksize)
   std::vector<int> tmin, tcnt, tk;
-  int max_nw = 0, max_nh = 0, max_rows = 1, max_cols = 1, max_k = 1;
-  long long n_blocks = 0;
   // group > 0: also track the widest source span of `group` consecutive outputs
   auto table = [&](int in_size, int out_size, int group, int& max_span) {
     auto key = std::make_pair(in_size, out_size);
@@ -340,77 +501,124 @@ extern "C" int td_tile_cut_normalize(const void* image, int elem_size, int bands
     }
     return res;
   };
-  for (int t = 0; t < n_tiles; ++t) {
+  int rc = TD_OK;
+  for (int t = 0; t < n_tiles && rc == TD_OK; ++t) {
     TileDesc& d = td[t];
     d.c_off = tile_win[4 * t]; d.r_off = tile_win[4 * t + 1]; d.w = tile_win[4 * t + 2]; d.h = tile_win[4 * t + 3];
     d.nh = tile_net[2 * t]; d.nw = tile_net[2 * t + 1];
     d.out_off = out_off[t];
-    TD_ARG(d.w > 0 && d.h > 0 && d.nh > 0 && d.nw > 0 && d.c_off >= 0 && d.r_off >= 0 && d.c_off + d.w <= W &&
-           d.r_off + d.h <= H);
+    if (!(d.w > 0 && d.h > 0 && d.nh > 0 && d.nw > 0 && d.c_off >= 0 && d.r_off >= 0 && d.c_off + d.w <= W &&
+          d.r_off + d.h <= H)) {
+      td_set_error("td_tile_plan_create: tile %d window outside the raster", t);
+      rc = TD_ERR_ARG;
+      break;
+    }
     d.xtab = d.ytab = d.kx = d.ky = 0;
     if (elem_size == 1) {
-      auto tx = table(d.w, d.nw, kBX, max_cols);
-      auto ty = table(d.h, d.nh, kBY, max_rows);
+      auto tx = table(d.w, d.nw, kBX, P->max_cols);
+      auto ty = table(d.h, d.nh, kBY, P->max_rows);
       if (tx.second > kMaxK || ty.second > kMaxK) {
-        td_set_error("td_tile_cut_normalize: down-scaling factor needs %d taps (max %d)",
+        td_set_error("td_tile_plan_create: down-scaling factor needs %d taps (max %d)",
                      tx.second > ty.second ? tx.second : ty.second, kMaxK);
-        return TD_ERR_UNSUPPORTED;
+        rc = TD_ERR_UNSUPPORTED;
+        break;
       }
       d.xtab = tx.first; d.kx = tx.second; d.ytab = ty.first; d.ky = ty.second;
-      if (d.kx > max_k) max_k = d.kx;
-      if (d.ky > max_k) max_k = d.ky;
+      if (d.kx > P->max_k) P->max_k = d.kx;
+      if (d.ky > P->max_k) P->max_k = d.ky;
     }
     d.bx = td_div_up(d.nw, kBX);
-    d.blk0 = (int)n_blocks;
-    n_blocks += (long long)d.bx * td_div_up(d.nh, kBY);
-    TD_ARG(n_blocks < 0x7fffffffLL);
-    if (d.nw > max_nw) max_nw = d.nw;
-    if (d.nh > max_nh) max_nh = d.nh;
+    d.blk0 = (int)P->n_blocks;
+    P->n_blocks += (long long)d.bx * td_div_up(d.nh, kBY);
+    if (P->n_blocks >= 0x7fffffffLL) { td_set_error("td_tile_plan_create: too many CTAs"); rc = TD_ERR_OVERFLOW; }
+    if (d.nw > P->max_nw) P->max_nw = d.nw;
+    if (d.nh > P->max_nh) P->max_nh = d.nh;
   }
-  TileDesc* d_td = nullptr;
-  int *d_min = nullptr, *d_cnt = nullptr, *d_k = nullptr, *d_max = nullptr;
-  TD_CUDA(cudaMallocAsync((void**)&d_td, sizeof(TileDesc) * n_tiles, st));
-  TD_CUDA(cudaMemcpyAsync(d_td, td.data(), sizeof(TileDesc) * n_tiles, cudaMemcpyHostToDevice, st));
-  int rc = TD_OK;
-  if (elem_size == 1) {
-    TD_CUDA(cudaMallocAsync((void**)&d_min, sizeof(int) * (tmin.size() + 1), st));
-    TD_CUDA(cudaMallocAsync((void**)&d_cnt, sizeof(int) * (tcnt.size() + 1), st));
-    TD_CUDA(cudaMallocAsync((void**)&d_k, sizeof(int) * (tk.size() + 1), st));
-    TD_CUDA(cudaMemcpyAsync(d_min, tmin.data(), sizeof(int) * tmin.size(), cudaMemcpyHostToDevice, st));
-    TD_CUDA(cudaMemcpyAsync(d_cnt, tcnt.data(), sizeof(int) * tcnt.size(), cudaMemcpyHostToDevice, st));
-    TD_CUDA(cudaMemcpyAsync(d_k, tk.data(), sizeof(int) * tk.size(), cudaMemcpyHostToDevice, st));
+  for (int v : tcnt) if (v > P->max_cnt) P->max_cnt = v;
+  std::vector<int2> blk;
+  if (rc == TD_OK && elem_size == 1) {
+    blk.reserve((size_t)P->n_blocks);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int by = td_div_up(td[t].nh, kBY);
+      for (int j = 0; j < by; ++j)
+        for (int i = 0; i < td[t].bx; ++i) blk.push_back(make_int2(t, (j << 16) | i));
+    }
+  }
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (cudaMalloc(dst, bytes ? bytes : 4) != cudaSuccess) return false;
+    return bytes == 0 || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (rc == TD_OK) {
+    bool ok = up((void**)&P->d_td, td.data(), sizeof(TileDesc) * n_tiles);
+    if (elem_size == 1) {
+      ok = ok && up((void**)&P->d_min, tmin.data(), sizeof(int) * tmin.size());
+      ok = ok && up((void**)&P->d_cnt, tcnt.data(), sizeof(int) * tcnt.size());
+      ok = ok && up((void**)&P->d_k, tk.data(), sizeof(int) * tk.size());
+      ok = ok && up((void**)&P->d_blk, blk.data(), sizeof(int2) * blk.size());
+    } else {
+      ok = ok && (cudaMalloc((void**)&P->d_max, sizeof(int) * n_tiles) == cudaSuccess);
+    }
+    if (!ok) { td_set_error("td_tile_plan_create: %s", cudaGetErrorString(cudaGetLastError())); rc = TD_ERR_CUDA; }
+  }
+  if (rc != TD_OK) {
+    cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk);
+    delete P;
+    return rc;
+  }
+  *plan_out = P;
+  return TD_OK;
+}
+
+extern "C" int td_tile_plan_destroy(void* plan) {
+  if (!plan) return TD_OK;
+  TilePlan* P = (TilePlan*)plan;
+  cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk);
+  delete P;
+  return TD_OK;
+}
+
+extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int bands, float* out,
+                                     unsigned char* rescale16, void* stream) {
+  TD_ARG(plan && image && out && bands >= 3);
+  TD_ARG(((uintptr_t)out & 15) == 0 && ((uintptr_t)image & 3) == 0);
+  const TilePlan* P = (const TilePlan*)plan;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = P->H, W = P->W, n_tiles = P->n_tiles;
+  if (P->elem_size == 1) {
     if (rescale16) TD_CUDA(cudaMemsetAsync(rescale16, 0, n_tiles, st));
-    const int K = max_k <= 3 ? 3 : kMaxK;
-    const int src_stride = (3 + max_cols + K + 3) & ~3;
+    const int K = P->max_k <= 3 ? 3 : kMaxK;
+    const int src_stride = (P->max_cols + K + 8 + 15) & ~15;   // 16-byte multiple keeps every region aligned
+    const int max_rows = P->max_rows;
     const size_t smem = (size_t)3 * max_rows * src_stride + (size_t)3 * max_rows * kBX + sizeof(int) * kBY * (2 + K);
     const long long image_bytes = (long long)bands * H * W;
-    if (K == 3) {
+    const unsigned grid = (unsigned)P->n_blocks;
+    const unsigned char* img = (const unsigned char*)image;
+    if (P->max_cnt <= 2 && P->max_k <= 3) {
+      // up-scaling fast path; one extra intermediate row is readable (weight 0 taps)
+      const size_t smem_up = (size_t)3 * max_rows * src_stride + (size_t)3 * max_rows * kBX + kBX + sizeof(int4) * kBY;
+      auto kern = tile_resize_u8_up_kernel;
+      if (smem_up > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_up);
+      kern<<<grid, kThreads, smem_up, st>>>(img, image_bytes, H, W, P->d_td, P->d_blk, P->d_min, P->d_cnt, P->d_k, out,
+                                            max_rows, src_stride);
+    } else if (K == 3) {
       auto kern = tile_resize_u8_kernel<3>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<(unsigned)n_blocks, kThreads, smem, st>>>((const unsigned char*)image, image_bytes, H, W, d_td, n_tiles,
-                                                       d_min, d_cnt, d_k, out, max_rows, src_stride);
+      kern<<<grid, kThreads, smem, st>>>(img, image_bytes, H, W, P->d_td, n_tiles, P->d_min, P->d_cnt, P->d_k, out,
+                                         max_rows, src_stride);
     } else {
       auto kern = tile_resize_u8_kernel<kMaxK>;
       if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      kern<<<(unsigned)n_blocks, kThreads, smem, st>>>((const unsigned char*)image, image_bytes, H, W, d_td, n_tiles,
-                                                       d_min, d_cnt, d_k, out, max_rows, src_stride);
+      kern<<<grid, kThreads, smem, st>>>(img, image_bytes, H, W, P->d_td, n_tiles, P->d_min, P->d_cnt, P->d_k, out,
+                                         max_rows, src_stride);
     }
   } else {
-    TD_CUDA(cudaMallocAsync((void**)&d_max, sizeof(int) * n_tiles, st));
-    TD_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int) * n_tiles, st));
-    tile_band1_max_kernel<<<n_tiles, 256, 0, st>>>((const unsigned short*)image, H, W, d_td, d_max);
-    dim3 grid(td_div_up(max_nw, 128), max_nh, n_tiles);
-    tile_resize_u16_kernel<<<grid, 128, 0, st>>>((const unsigned short*)image, H, W, d_td, d_max, out, rescale16);
+    TD_CUDA(cudaMemsetAsync(P->d_max, 0, sizeof(int) * n_tiles, st));
+    tile_band1_max_kernel<<<n_tiles, 256, 0, st>>>((const unsigned short*)image, H, W, P->d_td, P->d_max);
+    dim3 grid(td_div_up(P->max_nw, 128), P->max_nh, n_tiles);
+    tile_resize_u16_kernel<<<grid, 128, 0, st>>>((const unsigned short*)image, H, W, P->d_td, P->d_max, out, rescale16);
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { td_set_error("td_tile_cut_normalize: %s", cudaGetErrorString(e)); rc = TD_ERR_CUDA; }
-  // host vectors were staged by the copies above; device tables die in stream order
-  cudaFreeAsync(d_td, st);
-  if (d_min) cudaFreeAsync(d_min, st);
-  if (d_cnt) cudaFreeAsync(d_cnt, st);
-  if (d_k) cudaFreeAsync(d_k, st);
-  if (d_max) cudaFreeAsync(d_max, st);
-  return rc;
+  TD_CHECK_LAUNCH("td_tile_cut_normalize");
+  return TD_OK;
 }
 
 extern "C" int td_seam_crop(const void* a, const void* b, int elem_size, int bands, int ha, int wa, int hb, int wb,

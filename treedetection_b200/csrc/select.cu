@@ -107,6 +107,7 @@ extern "C" int td_select_crowns(const double* bounds, const float* max_h, const 
   // python scalars compared with float32 array elements: the comparison is in float32
   P.height_threshold = (float)params[10]; P.ndvi_mean_threshold = (float)params[11];
   P.ndvi_var_threshold = (float)params[12];
+  td_ensure_pool();
   int* first = nullptr;
   int* rank = nullptr;
   void* tmp = nullptr;

@@ -163,20 +163,55 @@ TD_HD inline double point_segment_distance(const P2& p, const P2& A, const P2& B
   return fabs(s) * sqrt(len2);
 }
 
+// ---- cooperation policy ---------------------------------------------------------------------
+// The simplifier is a sequential stack machine, but its two inner loops (farthest point of a
+// section, interior-intersection scan over the segment sets) are data parallel.  `Coop` says
+// how many lanes run the function together; every lane executes the control flow redundantly
+// on identical values (identical writes to the shared scratch are benign), only the loops are
+// strided over the lanes and combined with the two collectives below.
+struct SerialCoop {
+  TD_HD int lane() const { return 0; }
+  TD_HD int size() const { return 1; }
+  // all lanes receive the maximum d and, among equal maxima, the lowest k
+  TD_HD void argmax_first(double&, int&) const {}
+  TD_HD bool any(bool b) const { return b; }
+  TD_HD void sync() const {}
+};
+
+#if defined(__CUDACC__)
+struct WarpCoop {
+  __device__ int lane() const { return threadIdx.x & 31; }
+  __device__ int size() const { return 32; }
+  __device__ void argmax_first(double& d, int& k) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, d, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+      if (od > d || (od == d && ok < k)) { d = od; k = ok; }
+    }
+  }
+  __device__ bool any(bool b) const { return __any_sync(0xffffffffu, b); }
+  __device__ void sync() const { __syncwarp(); }   // orders the lanes' scratch writes
+};
+#endif
+
 // ---- TopologyPreservingSimplifier on one closed ring ---------------------------
 // pts[0..n) with pts[0] == pts[n-1].  scratch: 5 * n ints.  Writes the indices of the
 // kept vertices (including the closing one) to res[0..m) and returns m.
-//   scratch layout: res[n] | flat[n] | stack[3n]   (flat[k] = 1 when result segment k
-//   is a flattened section, i.e. a member of the output segment index)
+//   scratch layout: res[n] | flat[n] | stack[3n]   (flat[k] = end index + 1 when result
+//   segment k is a flattened section, i.e. a member of the output segment index, else 0)
 //   alive: n bits in (n + 31) / 32 words (input segment k = pts[k], pts[k+1] still indexed)
-TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, uint32_t* alive) {
+template <typename Coop>
+TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, uint32_t* alive, const Coop& co) {
   if (n <= 0) return 0;
   int* res = scratch;
   int* flat = scratch + n;
   int* stack = scratch + 2 * n;
   const int nseg = n - 1;
-  for (int k = 0; k < (n + 31) / 32; ++k) alive[k] = 0xffffffffu;
-  int m = 0;        // number of result segments; res[k], res[k+1] are its ends
+  const int lane = co.lane(), nl = co.size();
+  for (int k = lane; k < (n + 31) / 32; k += nl) alive[k] = 0xffffffffu;
+  co.sync();
+  int m = 0;        // number of result segments; res[k] and the next start (or flat end) are its ends
   int sp = 0;
   stack[0] = 0; stack[1] = n - 1; stack[2] = 0;
   sp = 1;
@@ -195,25 +230,39 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
     double maxd = -1.0;
     int far = i;
     const P2 A = pts[i], B = pts[j];
-    for (int k = i + 1; k < j; ++k) {
+    for (int k = i + 1 + lane; k < j; k += nl) {
       const double d = point_segment_distance(pts[k], A, B);
       if (d > maxd) { maxd = d; far = k; }
     }
+    if (maxd < 0.0) far = 0x7fffffff;      // lane without work: loses every tie
+    co.argmax_first(maxd, far);
     if (maxd > tol) valid = false;
     if (valid) {
       bool bad = false;
-      for (int k = 0; k < m && !bad; ++k)
-        if (flat[k]) bad = interior_intersection(pts[res[k]], pts[flat[k] - 1], A, B);
-      for (int k = 0; k < nseg && !bad; ++k) {
-        if (!((alive[k >> 5] >> (k & 31)) & 1u)) continue;
-        if (k >= i && k < j) continue;
-        bad = interior_intersection(pts[k], pts[k + 1], A, B);
+      for (int k = lane; k < m; k += nl)
+        if (flat[k] && !bad) bad = interior_intersection(pts[res[k]], pts[flat[k] - 1], A, B);
+      bad = co.any(bad);
+      if (!bad) {
+        for (int k = lane; k < nseg; k += nl) {
+          if (bad) break;
+          if (!((alive[k >> 5] >> (k & 31)) & 1u)) continue;
+          if (k >= i && k < j) continue;
+          bad = interior_intersection(pts[k], pts[k + 1], A, B);
+        }
+        bad = co.any(bad);
       }
       if (bad) valid = false;
     }
     if (valid) {
-      for (int k = i; k < j; ++k) alive[k >> 5] &= ~(1u << (k & 31));
-      res[m] = i; flat[m] = j + 1; ++m;   // flat stores end index + 1
+      // clear bits [i, j): whole words strided over the lanes (identical result for 1 lane)
+      for (int w = (i >> 5) + lane; w <= ((j - 1) >> 5); w += nl) {
+        const int lo = w == (i >> 5) ? (i & 31) : 0;
+        const int hi = w == ((j - 1) >> 5) ? ((j - 1) & 31) : 31;
+        const uint32_t mask = (hi == 31 ? 0xffffffffu : ((2u << hi) - 1u)) & ~((1u << lo) - 1u);
+        alive[w] &= ~mask;
+      }
+      co.sync();
+      res[m] = i; flat[m] = j + 1; ++m;
       continue;
     }
     // right section is processed second
@@ -222,6 +271,10 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
   }
   res[m] = n - 1;
   return m + 1;
+}
+
+TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, uint32_t* alive) {
+  return simplify_ring(pts, n, tol, scratch, alive, SerialCoop());
 }
 
 // GEOS Area::ofRingSigned via an index accessor (so that it can run on the

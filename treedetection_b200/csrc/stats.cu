@@ -283,6 +283,7 @@ extern "C" int td_centroids(const double* verts, const long long* ring_off, int 
   if (n == 0) return TD_OK;
   TD_ARG(verts && ring_off && centroid);
   cudaStream_t st = (cudaStream_t)stream;
+  td_ensure_pool();
   int* vmax = nullptr;
   TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
   TD_CUDA(cudaMemsetAsync(vmax, 0, sizeof(int), st));

@@ -283,29 +283,55 @@ def round_coords(verts):
 # ----------------------------------------------------------------------------
 # P1  tile cut + normalise,  P0a  seam strips
 # ----------------------------------------------------------------------------
+class TilePlan:
+    """Device tables of one tiling (td_tile_plan_create): re-used by every image / step."""
+
+    def __init__(self, tile_win, tile_net, elem_size, H, W):
+        import ctypes as C
+        if tile_win.is_cuda or tile_net.is_cuda:
+            raise _lib.TreedetError("tile tables are host tensors (they come from the tiles JSON)")
+        self.win = tile_win.to(torch.int32).contiguous()
+        self.net = tile_net.to(torch.int32).contiguous()
+        t = self.win.shape[0]
+        sizes = 3 * self.net[:, 0].to(torch.int64) * self.net[:, 1].to(torch.int64)
+        self.out_off = torch.zeros(t + 1, dtype=torch.int64)
+        torch.cumsum(sizes, 0, out=self.out_off[1:])
+        self.total = int(self.out_off[-1])
+        self.n_tiles, self.elem_size, self.H, self.W = t, elem_size, H, W
+        self._h = C.c_void_p()
+        _lib.call("td_tile_plan_create", self.win.data_ptr(), self.net.data_ptr(), self.out_off.data_ptr(), t,
+                  elem_size, H, W, C.byref(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().td_tile_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def run(self, image, out=None):
+        b, h, w = image.shape
+        if (h, w) != (self.H, self.W) or image.element_size() != self.elem_size:
+            raise _lib.TreedetError("tile plan was made for another raster shape / dtype")
+        if out is None:
+            out = torch.empty((max(self.total, 1),), dtype=torch.float32, device=image.device)
+        elif out.numel() < self.total:
+            raise _lib.TreedetError("tile_cut_normalize: output buffer too small")
+        flag = torch.empty((self.n_tiles,), dtype=torch.uint8, device=image.device)
+        _lib.call("td_tile_cut_normalize", self._h, _ptr(image), b, _ptr(out), _ptr(flag), _stream())
+        return out, self.out_off, flag
+
+
 def tile_cut_normalize(image, tile_win, tile_net, out=None):
     """image (bands,H,W) uint8 / int16-viewed-uint16 device tensor; tile_win (T,4) and
-    tile_net (T,2) int32 HOST tensors.  Returns (out f32 flat, out_off i64 host, rescale16 u8)."""
-    if tile_win.is_cuda or tile_net.is_cuda:
-        raise _lib.TreedetError("tile tables are host tensors (they come from the tiles JSON)")
-    tile_win = tile_win.to(torch.int32).contiguous(); tile_net = tile_net.to(torch.int32).contiguous()
-    t = tile_win.shape[0]
-    sizes = 3 * tile_net[:, 0].to(torch.int64) * tile_net[:, 1].to(torch.int64)
-    out_off = torch.zeros(t + 1, dtype=torch.int64)
-    torch.cumsum(sizes, 0, out=out_off[1:])
-    total = int(out_off[-1])
-    if out is None:
-        out = torch.empty((max(total, 1),), dtype=torch.float32, device=image.device)
-    elif out.numel() < total:
-        raise _lib.TreedetError("tile_cut_normalize: output buffer too small")
+    tile_net (T,2) int32 HOST tensors.  Returns (out f32 flat, out_off i64 host, rescale16 u8).
+    One-shot convenience; hold a :class:`TilePlan` when the tiling is re-used."""
     elem = image.element_size()
     if elem not in (1, 2):
         raise _lib.TreedetError("tile_cut_normalize: uint8 or uint16 rasters only")
-    b, h, w = image.shape
-    flag = torch.zeros((t,), dtype=torch.uint8, device=image.device)
-    _lib.call("td_tile_cut_normalize", _ptr(image), elem, b, h, w, tile_win.data_ptr(), tile_net.data_ptr(), t,
-              out_off.data_ptr(), _ptr(out), _ptr(flag), _stream())
-    return out, out_off, flag
+    _, h, w = image.shape
+    return TilePlan(tile_win, tile_net, elem, h, w).run(image, out)
 
 
 def seam_crop(a, b, axis, strip_w, strip_h):
