@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import json
+
 import os
 import statistics
 import subprocess
@@ -184,6 +185,7 @@ class ClockSampler:
 # B200 arm
 # --------------------------------------------------------------------------------------
 def run_b200(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -213,6 +215,48 @@ def run_b200(a):
     n_tiles = len(sc.tiles)
     p1_bytes = int(sum(3 * int(w[2]) * int(w[3]) for w in tables.win.tolist())) + 4 * tables.p1_floats
 
+    # ---- N > 1: the down-seam strip between image row r and r + 1 (the one exchange step) ----
+    strip = None
+    if world > 1:
+        from treedetection_b200 import sharding, tiling
+        rows = sharding.halo_rows(p.tile_height, p.buffer, p.overlapping_tiles_height)
+        tops = [d["rgbi"][:, :rows].contiguous(), d["ndsm"][None, :rows].contiguous()]
+        if rank + 1 < world:
+            px = 0.2
+            nb = synth.tree_field(1234 + rank + 1, a.size * px, a.size * px, 2500.0, synth.ORIGIN_X,
+                                  synth.ORIGIN_Y - (rank + 1) * a.size * px)
+            own = sc.field
+            both = synth.TreeField(*[np.concatenate([getattr(own, k), getattr(nb, k)]) for k in
+                                     ("x", "y", "r", "h", "score", "ecc")], own.left, nb.bottom, own.width_m,
+                                   2 * own.height_m)
+            top = own.bottom + rows * px                       # strip = bottom rows of own + top rows of neighbour
+            s_tf = synth.image_transform(own.left, top, px)
+            s_tiles = tiling.tile_grid(f"FDOP20_seam{rank}_rgbi", s_tf, a.size, 2 * rows, synth.EPSG, p.tile_width,
+                                       p.tile_height, p.buffer)
+            s_det = synth.make_detections(both, s_tiles, px, 1234 + rank)
+            s_tables = api.TileTables(s_tiles, dev, p.shift)
+            n_rows = rows if a.ndsm_px == 0.2 else rows
+            strip = {
+                "tf": s_tf, "ndsm_tf": synth.image_transform(own.left, own.bottom + n_rows * a.ndsm_px, a.ndsm_px),
+                "tables": s_tables, "p1": torch.empty((s_tables.p1_floats,), dtype=torch.float32, device=dev),
+                "det": {k: torch.from_numpy(getattr(s_det, k)).to(dev) for k in
+                        ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")},
+            }
+
+    def step_strip():
+        """halo exchange (NCCL send/recv) + the seam strip through the same path"""
+        recv = sharding.exchange_down_halos(tops, rank, world)
+        if recv is None or strip is None:
+            return
+        s_rgbi = sharding.assemble_down_strip(d["rgbi"], recv[0])
+        s_ndsm = sharding.assemble_down_strip(d["ndsm"][None], recv[1])[0]
+        strip["tables"].plan(s_rgbi).run(s_rgbi, strip["p1"])
+        sd = strip["det"]
+        table = pipeline.predict_stage(sd["boxes_net"], sd["scores"], sd["probs"], sd["inst_tile"], sd["tile_dims"],
+                                       strip["tables"].tile_tf, strip["tables"].tile_boxes, p)
+        rasters = pipeline.raster_stage(s_rgbi, strip["tf"], s_ndsm, strip["ndsm_tf"], p)
+        pipeline.postprocess_stage(table, rasters, p)
+
     ev = lambda: torch.cuda.Event(enable_timing=True)
     p1_ev = []
 
@@ -232,6 +276,8 @@ def run_b200(a):
         feats = pipeline.postprocess_stage(table, rasters, p)
         e[4].record()
         stage_ev.append(e)
+        if world > 1:
+            step_strip()
         return len(table), len(feats)
 
     def barrier():
@@ -274,6 +320,8 @@ def run_b200(a):
     # end to end through the host-buffer API
     def step_e2e():
         out, _ = api.run_image(host, p, dev, tables, p1_out)
+        if world > 1:
+            step_strip()
         return out
     for _ in range(max(1, min(a.warmup, 2))):
         step_e2e()
@@ -301,7 +349,10 @@ def run_b200(a):
                        "area_km2_per_gpu": area, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
                        "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                        "cache": "inputs (rasters 0.8 GB, P1 output 12 GB) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"image-row sharding x{world}, no data-path collective"},
+                       "parallelism": (f"image-row sharding x{world}; per step every rank r < N-1 also receives the "
+                                       f"135-row RGBI + nDSM halo of rank r+1 (NCCL send/recv) and runs the down-seam "
+                                       f"strip through the same path" if world > 1 else
+                                       "1 GPU; image-row sharding for N > 1")},
             "roofline": {"bound": "hbm", "kernel": "tile_resize_u8_kernel (P1)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",

@@ -74,23 +74,48 @@ def features_to_host(f: pipeline.Features):
     }
 
 
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device).index
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
 def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: TileTables = None, p1_out=None,
               with_p1=True):
     """Host buffers in, final crowns (host numpy) out.  ``p1_out``: optional reusable
-    device buffer for the normalised tiles (they feed the predictor, not this path)."""
+    device buffer for the normalised tiles (they feed the predictor, not this path).
+
+    The three host->device transfers ride a copy stream in the order the stages need them
+    (ROI-head outputs, RGBI, nDSM) and the compute stream waits on one event per group, so
+    P2-P4 overlap the RGBI copy and P1 / P5 overlap the nDSM copy."""
     if not torch.cuda.is_available():
         raise _lib.TreedetError("run_image needs a CUDA device (there is no CPU fallback)")
     tables = tables or TileTables(img.tiles, device, params.shift)
-    nb = True
-    rgbi = img.rgbi.to(device, non_blocking=nb)
-    ndsm = img.ndsm.to(device, non_blocking=nb)
-    boxes = img.boxes_net.to(device, non_blocking=nb); scores = img.scores.to(device, non_blocking=nb)
-    probs = img.probs.to(device, non_blocking=nb); inst_tile = img.inst_tile.to(device, non_blocking=nb)
-    tile_dims = img.tile_dims.to(device, non_blocking=nb)
+    main = torch.cuda.current_stream(device)
+    cs = _copy_stream(device)
+    cs.wait_stream(main)
+    with torch.cuda.stream(cs):
+        boxes = img.boxes_net.to(device, non_blocking=True); scores = img.scores.to(device, non_blocking=True)
+        probs = img.probs.to(device, non_blocking=True); inst_tile = img.inst_tile.to(device, non_blocking=True)
+        tile_dims = img.tile_dims.to(device, non_blocking=True)
+        ev_det = cs.record_event()
+        rgbi = img.rgbi.to(device, non_blocking=True)
+        ev_rgbi = cs.record_event()
+        ndsm = img.ndsm.to(device, non_blocking=True)
+        ev_ndsm = cs.record_event()
+    for t in (boxes, scores, probs, inst_tile, tile_dims, rgbi, ndsm):
+        t.record_stream(main)
+    main.wait_event(ev_det)
+    table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf, tables.tile_boxes, params)
+    main.wait_event(ev_rgbi)
     tiles_out = None
     if with_p1:
         tiles_out, _, _ = tables.plan(rgbi).run(rgbi, p1_out)
-    table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf, tables.tile_boxes, params)
+    main.wait_event(ev_ndsm)
     rasters = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
     feats = pipeline.postprocess_stage(table, rasters, params)
     host = features_to_host(feats)

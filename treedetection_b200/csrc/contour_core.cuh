@@ -40,11 +40,14 @@ struct ContourCounts {
   int n_ring_verts;   // their points + the closing point where first != last (:238-239)
 };
 
-struct Raster {
+// LabelT: unsigned short in general; unsigned char when the window has < 255 borders (known
+// from the count pass), which halves the shared-memory footprint of the emit pass.
+template <typename LabelT>
+struct RasterT {
   const uint32_t* fg;
   uint32_t* visited;
   uint32_t* right;
-  unsigned short* label;
+  LabelT* label;
   int w, h, wpr;
 
   TD_HD bool is_fg(int x, int y) const {
@@ -55,16 +58,16 @@ struct Raster {
     if (wi < 0 || wi >= wpr) return 0u;
     return plane[(size_t)y * wpr + wi];
   }
-  TD_HD void mark(int x, int y, bool right_flag, unsigned short lab) {
+  TD_HD void mark(int x, int y, bool right_flag, int lab) {
     const size_t wi = (size_t)y * wpr + (x >> 5);
     const uint32_t bit = 1u << (x & 31);
     if (right_flag) {
       right[wi] |= bit;
       visited[wi] |= bit;
-      if (label) label[(size_t)y * w + x] = lab;
+      if (label) label[(size_t)y * w + x] = (LabelT)lab;
     } else if (!(visited[wi] & bit)) {
       visited[wi] |= bit;
-      if (label) label[(size_t)y * w + x] = lab;
+      if (label) label[(size_t)y * w + x] = (LabelT)lab;
     }
   }
   // label of the nearest visited pixel strictly left of x in row y; -1 if none
@@ -86,6 +89,8 @@ struct Raster {
   }
 };
 
+using Raster = RasterT<unsigned short>;
+
 TD_HD inline int ctz32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return __ffs((int)v) - 1;
@@ -96,7 +101,8 @@ TD_HD inline int ctz32(uint32_t v) {
 
 // Follows one border from (x0, y0).  Returns the number of CHAIN_APPROX_SIMPLE
 // points; writes them when pts != nullptr; reports first / last point.
-TD_HD inline int follow_border(Raster& R, int x0, int y0, bool hole, unsigned short lab, short* pts, int* first_xy,
+template <typename RasterType>
+TD_HD inline int follow_border(RasterType& R, int x0, int y0, bool hole, int lab, short* pts, int* first_xy,
                                int* last_xy) {
   const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
   const int dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
@@ -153,7 +159,8 @@ TD_HD inline int follow_border(Raster& R, int x0, int y0, bool hole, unsigned sh
 // Scans one instance raster.  `out` == nullptr: count only (labels are not needed:
 // R.label may be null).  Returns counts; counts.n_contours < 0 when the 16-bit label
 // space would overflow.
-TD_HD inline ContourCounts scan_instance(Raster& R, ContourOut* out) {
+template <typename RasterType>
+TD_HD inline ContourCounts scan_instance(RasterType& R, ContourOut* out) {
   ContourCounts cc = {0, 0, 0, 0};
   const int kMaxLabel = 65534;
   for (int y = 0; y < R.h; ++y) {
@@ -189,7 +196,7 @@ TD_HD inline ContourCounts scan_instance(Raster& R, ContourOut* out) {
         const int idx = cc.n_contours;
         int first_xy[2] = {0, 0}, last_xy[2] = {0, 0};
         short* pts = out ? out->pts + 2 * (size_t)cc.n_points : nullptr;
-        const int np = follow_border(R, x, y, hole, (unsigned short)idx, pts, first_xy, last_xy);
+        const int np = follow_border(R, x, y, hole, idx, pts, first_xy, last_xy);
         if (out) {
           out->parent[idx] = parent;
           out->npts[idx] = np;

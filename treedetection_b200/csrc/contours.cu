@@ -16,41 +16,36 @@
 
 namespace {
 
-constexpr int kTraceWarps = 4;                 // instances per CTA (one warp each)
-constexpr int kTraceSmemPerWarp = 12 * 1024;   // bit planes (+ labels) of a window live here when they fit
+constexpr int kTraceWarps = 8;                 // instances per CTA (one warp each)
+constexpr int kCountSmemPerWarp = 3 * 1024;    // count pass: 3 bit planes (windows up to ~90 x 90 px)
+constexpr int kEmitSmemPerWarp = 6 * 1024;     // emit pass: + labels (1 B / px below 255 borders)
 
 // Border following is sequential per instance, and every step depends on the previous
 // pixel test: run from global memory a step costs an L2 round trip.  So one WARP owns one
 // instance: the lanes copy the window's foreground plane into shared memory (and clear the
 // two scratch planes), lane 0 walks the borders at shared-memory latency, and in the emit
-// pass all lanes write the ring vertices.  Windows that do not fit the per-warp budget
-// (12 KB: e.g. 180 x 180 px for counting, ~70 x 70 px with labels) fall back to the global
-// scratch planes.
-struct WarpRaster {
-  td::Raster R;
-  bool in_smem;
-};
-
-__device__ WarpRaster stage_window(const uint32_t* bits, const int* win, const long long* word_off, int i,
-                                   uint32_t* planes, long long total_words, unsigned short* labels_global,
-                                   unsigned char* smem_warp, bool want_labels) {
-  WarpRaster W;
-  td::Raster& R = W.R;
+// pass all lanes write the ring vertices.  The per-warp budgets are small on purpose: the
+// walk is latency bound, so what matters is how many warps an SM can keep resident (64 with
+// these budgets).  Windows that do not fit fall back to the global scratch planes.
+template <typename LabelT>
+__device__ bool stage_window(td::RasterT<LabelT>& R, const uint32_t* bits, const int* win, const long long* word_off,
+                             int i, uint32_t* planes, long long total_words, LabelT* labels_global,
+                             unsigned char* smem_warp, int budget, bool want_labels) {
   R.w = win[4 * i + 2];
   R.h = win[4 * i + 3];
   R.wpr = (R.w + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwords = R.wpr * R.h;
   const uint32_t* fg = bits + word_off[i];
-  const size_t need = (size_t)12 * nwords + (want_labels ? (size_t)2 * R.w * R.h : 0);
-  W.in_smem = nwords > 0 && need <= (size_t)kTraceSmemPerWarp;
-  if (W.in_smem) {
+  const size_t need = (size_t)12 * nwords + (want_labels ? sizeof(LabelT) * (size_t)R.w * R.h : 0);
+  const bool in_smem = nwords > 0 && need <= (size_t)budget;
+  if (in_smem) {
     uint32_t* s_fg = reinterpret_cast<uint32_t*>(smem_warp);
     uint32_t* s_vis = s_fg + nwords;
     uint32_t* s_rgt = s_vis + nwords;
     for (int k = lane; k < nwords; k += 32) { s_fg[k] = fg[k]; s_vis[k] = 0u; s_rgt[k] = 0u; }
     R.fg = s_fg; R.visited = s_vis; R.right = s_rgt;
-    R.label = want_labels ? reinterpret_cast<unsigned short*>(s_rgt + nwords) : nullptr;
+    R.label = want_labels ? reinterpret_cast<LabelT*>(s_rgt + nwords) : nullptr;
   } else {
     R.fg = fg;
     R.visited = planes + word_off[i];
@@ -58,7 +53,7 @@ __device__ WarpRaster stage_window(const uint32_t* bits, const int* win, const l
     R.label = want_labels ? labels_global : nullptr;
   }
   __syncwarp();
-  return W;
+  return in_smem;
 }
 
 __global__ void __launch_bounds__(32 * kTraceWarps)
@@ -70,9 +65,10 @@ trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ wi
   if (i >= n) return;
   td::ContourCounts cc = {0, 0, 0, 0};
   if (win[4 * i + 2] > 0 && win[4 * i + 3] > 0) {
-    WarpRaster W = stage_window(bits, win, word_off, i, planes, total_words, nullptr,
-                                smem + (size_t)warp * kTraceSmemPerWarp, false);
-    if (lane == 0) cc = td::scan_instance(W.R, nullptr);
+    td::Raster R;
+    stage_window<unsigned short>(R, bits, win, word_off, i, planes, total_words, nullptr,
+                                 smem + (size_t)warp * kCountSmemPerWarp, kCountSmemPerWarp, false);
+    if (lane == 0) cc = td::scan_instance(R, nullptr);
   }
   if (lane == 0) {
     counts[4 * i + 0] = cc.n_contours;
@@ -118,8 +114,7 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_emit_kernel(EmitArgs A
   const long long c0 = A.cont_off[i];
   const int nc = (int)(A.cont_off[i + 1] - c0);
   if (nc == 0) return;
-  WarpRaster W = stage_window(A.bits, A.win, A.word_off, i, A.planes, A.total_words, A.labels + A.px_off[i],
-                              smem + (size_t)warp * kTraceSmemPerWarp, true);
+  unsigned char* my_smem = smem + (size_t)warp * kEmitSmemPerWarp;
   td::ContourOut out;
   out.parent = A.ct_parent + c0;
   out.npts = A.ct_npts + c0;
@@ -129,10 +124,26 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_emit_kernel(EmitArgs A
   int* last_child = A.ct_scratch + 3 * c0;
   int* prev_sib = last_child + nc;
   int* order = prev_sib + nc;
-  if (lane == 0) {
-    td::scan_instance(W.R, &out);
-    td::contour_order(nc, out.parent, last_child, prev_sib, order);
+  // labels are border indices: one byte is enough below 255 borders (global fallback keeps u16)
+  bool staged8 = false;
+  if (nc < 255) {
+    td::RasterT<unsigned char> R8;
+    R8.w = A.win[4 * i + 2]; R8.h = A.win[4 * i + 3]; R8.wpr = (R8.w + 31) >> 5;
+    const size_t need = (size_t)12 * R8.wpr * R8.h + (size_t)R8.w * R8.h;
+    if (need <= (size_t)kEmitSmemPerWarp) {
+      stage_window<unsigned char>(R8, A.bits, A.win, A.word_off, i, A.planes, A.total_words, nullptr, my_smem,
+                                  kEmitSmemPerWarp, true);
+      if (lane == 0) td::scan_instance(R8, &out);
+      staged8 = true;
+    }
   }
+  if (!staged8) {
+    td::Raster R;
+    stage_window<unsigned short>(R, A.bits, A.win, A.word_off, i, A.planes, A.total_words, A.labels + A.px_off[i],
+                                 my_smem, kEmitSmemPerWarp, true);
+    if (lane == 0) td::scan_instance(R, &out);
+  }
+  if (lane == 0) td::contour_order(nc, out.parent, last_child, prev_sib, order);
   __syncwarp();   // lane 0's tables and points become visible to the warp
   const double* tf = A.tile_tf + 6 * (size_t)A.inst_tile[i];
   const double ta = tf[0], tb = tf[1], tc = tf[2], td_ = tf[3], te = tf[4], tff = tf[5];
@@ -171,7 +182,7 @@ extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long l
   TD_ARG(bits && win && word_off && planes && counts);
   cudaStream_t st = (cudaStream_t)stream;
   TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
-  trace_count_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kTraceSmemPerWarp, st>>>(
+  trace_count_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kCountSmemPerWarp, st>>>(
       bits, win, word_off, n_inst, planes, total_words, counts);
   TD_CHECK_LAUNCH("td_trace_count");
   return TD_OK;
@@ -201,7 +212,7 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   A.ct_scratch = ct_int5 + 3 * total_contours;
   A.ct_hole = ct_hole; A.pts = pts; A.inst_tile = inst_tile; A.tile_tf = tile_tf;
   A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
-  trace_emit_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kTraceSmemPerWarp, st>>>(A);
+  trace_emit_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kEmitSmemPerWarp, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
   return TD_OK;
 }

@@ -1,0 +1,48 @@
+"""Row sharding of a mosaic over the GPUs of one box.
+
+Every image file -- seam strips included -- is an independent unit through P0b..P9 (the
+reference never compares crowns of different files, TreeDetection/postprocessing.py:1030-1075),
+so rank r simply owns image row r.  The one exchange step of the path is the seam strip between
+row r and row r + 1 (TreeDetection/merging.py:81-107): it needs the top ``halo`` pixel rows of
+the lower neighbour's rasters.  Rank r + 1 sends them to rank r (NCCL send/recv over NVLink;
+``gloo`` in the CPU tests), rank r assembles the strip on its device with ``td_seam_crop``.
+No other collective is on the data path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def halo_rows(tile_height, buffer, overlapping_tiles_height):
+    """Half of the down-seam strip height in pixels: the strip is
+    ``(tile_height + 2 * buffer) * overlapping_tiles_height`` PIXELS high (merging.py:98-100),
+    centred on the seam."""
+    return int((tile_height + 2 * buffer) * overlapping_tiles_height) // 2
+
+
+def exchange_down_halos(tops, rank, world, group=None):
+    """``tops``: list of contiguous tensors holding the TOP halo rows of this rank's rasters.
+    Sends them to rank - 1 and returns the list received from rank + 1 (``None`` on the last
+    rank).  One batched isend/irecv per call; tensors keep their device."""
+    if world == 1:
+        return None
+    ops_, recv = [], None
+    if rank + 1 < world:
+        recv = [torch.empty_like(t) for t in tops]
+        ops_ += [dist.P2POp(dist.irecv, t, rank + 1, group) for t in recv]
+    if rank > 0:
+        ops_ += [dist.P2POp(dist.isend, t, rank - 1, group) for t in tops]
+    for w in dist.batch_isend_irecv(ops_):
+        w.wait()
+    return recv
+
+
+def assemble_down_strip(own, halo):
+    """own (bands, H, W) device raster of this rank, halo (bands, rows, W) = top rows of the
+    lower neighbour.  Returns the (bands, 2 * rows, W) seam strip: the centre crop of the
+    two-image mosaic, gathered without building the mosaic."""
+    from . import ops
+    rows = halo.shape[1]
+    bottom = own[:, own.shape[1] - rows:, :].contiguous()
+    return ops.seam_crop(bottom, halo, 1, own.shape[2], 2 * rows)
