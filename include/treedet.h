@@ -159,6 +159,19 @@ int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi
                      int* pre, int* out_idx, void* stream);
 int td_round_coords(const double* in, long long n, double* out, void* stream);
 
+/* ---- P10: forest-outline predicates (two-model fusion, tile flags) -----------------------------
+ * Replaces the GEOS predicates of fuse_predictions (TreeDetection/helpers.py:795-811) and of
+ * tile_single_file (TreeDetection/preprocessing.py:67-96).  a_*: query rings (crowns or tile
+ * boxes); f_*: forest polygons, one closed ring each (no holes); f_bounds (n_f,4) f64;
+ * a_filter (n_a,4) f64 or null: pick candidate polygons by strict bbox overlap with this box
+ * (the un-buffered tile box) instead of the ring's own bounds.
+ * out_intersects / out_within (n_a) u8: 1 = ring intersects / lies within the union of the
+ * forest polygons, 0 = not, 2 = capacity exceeded (> 128 overlapping polygons or > 62
+ * crossings on one edge).                                                                  */
+int td_forest_predicates(const double* a_verts, const long long* a_off, int n_a, const double* f_verts,
+                         const long long* f_off, const double* f_bounds, int n_f, const double* a_filter,
+                         unsigned char* out_intersects, unsigned char* out_within, void* stream);
+
 /* ---- P0a: seam strips ---------------------------------------------------------------------------
  * Replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,
  * TreeDetection/helpers.py:1023-1085): mosaic of an image with its right (axis 0) or lower

@@ -716,3 +716,140 @@ def seam_crop(a, b, axis, strip_w, strip_h):
     left = max(mw // 2 - strip_w // 2, 0)
     top = max(mh // 2 - strip_h // 2, 0)
     return mosaic[:, top:top + strip_h, left:left + strip_w], (left, top)
+
+
+# ============================================================================
+# P10  forest-outline predicates   (helpers.py:795-811, preprocessing.py:67-96)
+# ============================================================================
+# shapely/GEOS are absent: the predicates are restated for single-ring polygons against the
+# union of single-ring forest polygons (see treedetection_b200/csrc/forest_core.cuh for the
+# definition and its two documented simplifications).  parity with GEOS: unpinned.
+
+
+def locate_in_ring(p, ring):
+    """1 inside, 0 boundary, -1 outside (GEOS RayCrossingCounter)."""
+    crossings = 0
+    for k in range(len(ring) - 1):
+        p1, p2 = ring[k], ring[k + 1]
+        if p1[0] < p[0] and p2[0] < p[0]:
+            continue
+        if p[0] == p2[0] and p[1] == p2[1]:
+            return 0
+        if p1[1] == p[1] and p2[1] == p[1]:
+            if min(p1[0], p2[0]) <= p[0] <= max(p1[0], p2[0]):
+                return 0
+            continue
+        if (p1[1] > p[1] and p2[1] <= p[1]) or (p2[1] > p[1] and p1[1] <= p[1]):
+            sign = geom.orientation(p1[0], p1[1], p2[0], p2[1], p[0], p[1])
+            if sign == 0:
+                return 0
+            if p2[1] < p1[1]:
+                sign = -sign
+            if sign > 0:
+                crossings += 1
+    return 1 if crossings & 1 else -1
+
+
+def segments_touch(p1, p2, q1, q2):
+    if not geom._env_intersects_seg(p1, p2, q1, q2):
+        return False
+    o1 = geom.orientation(p1[0], p1[1], p2[0], p2[1], q1[0], q1[1])
+    o2 = geom.orientation(p1[0], p1[1], p2[0], p2[1], q2[0], q2[1])
+    if (o1 > 0 and o2 > 0) or (o1 < 0 and o2 < 0):
+        return False
+    o3 = geom.orientation(q1[0], q1[1], q2[0], q2[1], p1[0], p1[1])
+    o4 = geom.orientation(q1[0], q1[1], q2[0], q2[1], p2[0], p2[1])
+    if (o3 > 0 and o4 > 0) or (o3 < 0 and o4 < 0):
+        return False
+    return True
+
+
+def ring_intersects_ring(A, F):
+    for i in range(len(A) - 1):
+        for j in range(len(F) - 1):
+            if segments_touch(A[i], A[i + 1], F[j], F[j + 1]):
+                return True
+    if A and locate_in_ring(A[0], F) >= 0:
+        return True
+    if F and locate_in_ring(F[0], A) >= 0:
+        return True
+    return False
+
+
+def _split_params(a0, a1, q1, q2):
+    if not segments_touch(a0, a1, q1, q2):
+        return []
+    dx = a1[0] - a0[0]; dy = a1[1] - a0[1]
+    ex = q2[0] - q1[0]; ey = q2[1] - q1[1]
+    den = dx * ey - dy * ex
+    if den != 0.0:
+        return [((q1[0] - a0[0]) * ey - (q1[1] - a0[1]) * ex) / den]
+    len2 = dx * dx + dy * dy
+    if len2 == 0.0:
+        return []
+    return [((q1[0] - a0[0]) * dx + (q1[1] - a0[1]) * dy) / len2,
+            ((q2[0] - a0[0]) * dx + (q2[1] - a0[1]) * dy) / len2]
+
+
+def ring_within_union(A, forest):
+    if len(A) < 2 or not forest:
+        return False
+    for i in range(len(A) - 1):
+        a0, a1 = A[i], A[i + 1]
+        ts = [0.0, 1.0]
+        for F in forest:
+            for j in range(len(F) - 1):
+                for t in _split_params(a0, a1, F[j], F[j + 1]):
+                    if 0.0 < t < 1.0:
+                        ts.append(t)
+        ts.sort()
+        for k in range(len(ts) - 1):
+            if not ts[k + 1] > ts[k]:
+                continue
+            tm = (ts[k] + ts[k + 1]) / 2.0
+            m = (a0[0] + (a1[0] - a0[0]) * tm, a0[1] + (a1[1] - a0[1]) * tm)
+            if not any(locate_in_ring(m, F) >= 0 for F in forest):
+                return False
+    return True
+
+
+def _bounds(ring):
+    xs = [p[0] for p in ring]; ys = [p[1] for p in ring]
+    return min(xs), min(ys), max(xs), max(ys)
+
+
+def forest_predicates(rings, forest):
+    """(intersects, within) of every ring against the union of the forest rings; forest
+    polygons are pre-filtered by bounding-box overlap exactly as the kernel does."""
+    fb = [_bounds(F) for F in forest]
+    inter, within = [], []
+    for A in rings:
+        ab = _bounds(A)
+        cand = [F for F, b in zip(forest, fb) if not (ab[0] > b[2] or ab[2] < b[0] or ab[1] > b[3] or ab[3] < b[1])]
+        hit = any(ring_intersects_ring(A, F) for F in cand)
+        inter.append(hit)
+        within.append(bool(hit and ring_within_union(A, cand)))
+    return np.array(inter), np.array(within)
+
+
+def tile_flags(tile_bounds, buffered_box_ring, forest):
+    """preprocessing.py:67-96 for one tile: (only_forest, only_urban).  ``tile_bounds`` =
+    un-buffered tile box (bbox prefilter, strict inequalities), ``buffered_box_ring`` = the
+    buffered tile box as a ring (the geometry tests)."""
+    minx, miny, maxx, maxy = tile_bounds
+    cand = [F for F in forest
+            if (_bounds(F)[2] > minx and _bounds(F)[0] < maxx and _bounds(F)[3] > miny and _bounds(F)[1] < maxy)]
+    if not cand:
+        return False, True
+    hit = [F for F in cand if ring_intersects_ring(buffered_box_ring, F)]
+    if not hit:
+        return False, True
+    return bool(ring_within_union(buffered_box_ring, hit)), False
+
+
+def fuse(urban, forest_crowns, forest):
+    """helpers.py:795-811: indices of the forest-model crowns that intersect the forest union
+    and of the urban-model crowns that are NOT within it (forest first in the output)."""
+    fi, _ = forest_predicates(forest_crowns, forest)
+    _, uw = forest_predicates(urban, forest)
+    return np.nonzero(fi)[0], np.nonzero(~uw)[0]

@@ -13,6 +13,10 @@
 #include "simplify_core.cuh"
 #define HS_HAVE_SIMPLIFY 1
 #endif
+#if __has_include("forest_core.cuh")
+#include "forest_core.cuh"
+#define HS_HAVE_FOREST 1
+#endif
 
 extern "C" {
 
@@ -79,6 +83,42 @@ int hs_orientation_exact(double ax, double ay, double bx, double by, double cx, 
 int hs_interior_intersection(const double* p) {
   td::P2 a{p[0], p[1]}, b{p[2], p[3]}, c{p[4], p[5]}, d{p[6], p[7]};
   return td::interior_intersection(a, b, c, d) ? 1 : 0;
+}
+#endif
+
+#ifdef HS_HAVE_FOREST
+// query rings vs forest rings (ragged, closed); all candidates = every forest ring whose
+// bounding box overlaps (as the kernel does).  out: intersects / within per query ring.
+void hs_forest_predicates(const double* a_xy, const long long* a_off, int n_a, const double* f_xy,
+                          const long long* f_off, int n_f, unsigned char* inter, unsigned char* within) {
+  const td::P2* AV = reinterpret_cast<const td::P2*>(a_xy);
+  const td::P2* FV = reinterpret_cast<const td::P2*>(f_xy);
+  std::vector<td::Box2> fb(n_f);
+  for (int k = 0; k < n_f; ++k) {
+    td::Box2 b = {1e300, 1e300, -1e300, -1e300};
+    for (long long v = f_off[k]; v < f_off[k + 1]; ++v) {
+      b.minx = std::fmin(b.minx, FV[v].x); b.maxx = std::fmax(b.maxx, FV[v].x);
+      b.miny = std::fmin(b.miny, FV[v].y); b.maxy = std::fmax(b.maxy, FV[v].y);
+    }
+    fb[k] = b;
+  }
+  for (int r = 0; r < n_a; ++r) {
+    const td::P2* A = AV + a_off[r];
+    const int na = (int)(a_off[r + 1] - a_off[r]);
+    td::Box2 ab = {1e300, 1e300, -1e300, -1e300};
+    for (int k = 0; k < na; ++k) {
+      ab.minx = std::fmin(ab.minx, A[k].x); ab.maxx = std::fmax(ab.maxx, A[k].x);
+      ab.miny = std::fmin(ab.miny, A[k].y); ab.maxy = std::fmax(ab.maxy, A[k].y);
+    }
+    std::vector<int> cand;
+    for (int k = 0; k < n_f; ++k)
+      if (td::boxes_overlap(ab, fb[k])) cand.push_back(k);
+    bool hit = false;
+    for (size_t c = 0; c < cand.size() && !hit; ++c)
+      hit = td::ring_intersects_ring(A, na, FV + f_off[cand[c]], (int)(f_off[cand[c] + 1] - f_off[cand[c]]));
+    inter[r] = hit ? 1 : 0;
+    within[r] = (hit ? (unsigned char)td::ring_within_union(A, na, FV, f_off, cand.data(), (int)cand.size()) : 0);
+  }
 }
 #endif
 

@@ -51,6 +51,8 @@ SIGNATURES = {
     "td_tile_plan_create": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "td_tile_plan_destroy": (_i, [_p]),
     "td_tile_cut_normalize": (_i, [_p, _p, _i, _p, _p, _p]),
+    # P10
+    "td_forest_predicates": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p]),
     # P0a
     "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
@@ -61,7 +63,7 @@ OWN_KERNELS = {
     "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 1,
     "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
     "td_bbox_nms_ordered": 7, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,
-    "td_round_coords": 1, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0,
+    "td_round_coords": 1, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1,
 }
 launch_count = 0
 

@@ -18,6 +18,8 @@
 // P0a replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,
 // TreeDetection/helpers.py:1023-1085): the strip is gathered straight from the two source
 // rasters; the 2-image mosaic (800 MB at 10k x 10k) is never built.
+#include <cuda.h>
+
 #include <map>
 #include <utility>
 #include <vector>
@@ -384,6 +386,187 @@ tile_resize_u8_up_kernel(const unsigned char* __restrict__ image, long long imag
   }
 }
 
+// ---- TMA variant of the fast path -----------------------------------------------------------
+// Phase 0 of the kernel above costs ~1/3 of its instructions (address arithmetic, two loads
+// and a funnel shift per staged word).  Here one elected thread issues three
+// cp.async.bulk.tensor.3d loads (one per band: box = box_w bytes x max_rows rows x 1 band of the
+// (W, H, bands) uint8 tensor, zero fill outside the raster) that land directly in shared
+// memory, completion is signalled on an mbarrier, and the other threads fetch their filter taps
+// meanwhile.  Needs W % 16 == 0 (global strides of a tensor map are multiples of 16 bytes).
+TD_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kThreads)
+tile_resize_u8_up_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TileDesc* __restrict__ tiles,
+                             const int2* __restrict__ blk, const int* __restrict__ tab_min,
+                             const int* __restrict__ tab_cnt, const int* __restrict__ tab_k, float* __restrict__ out,
+                             int max_rows, int box_w, int region) {
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  unsigned char* s_src = smem_tma;                               // [3][region]  (region = box_w * max_rows, 128-aligned)
+  unsigned char* s_tmp = smem_tma + (size_t)3 * region;          // [3][max_rows][kBX]
+  int4* s_ytab = reinterpret_cast<int4*>(s_tmp + (size_t)3 * max_rows * kBX + kBX);   // [kBY]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_ytab + kBY);
+  const int2 me = blk[blockIdx.x];
+  const TileDesc T = tiles[me.x];
+  const int ox0 = (me.y & 0xffff) * kBX, oy0 = (me.y >> 16) * kBY;
+  const int oy_last = min(oy0 + kBY, T.nh) - 1;
+  const int row_lo = tab_min[T.ytab + oy0];
+  const int nrows = tab_min[T.ytab + oy_last] + tab_cnt[T.ytab + oy_last] - row_lo;
+  const int col_lo = tab_min[T.xtab + ox0];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kHalf = 1 << (kPrecisionBits - 1);
+  // ---- phase 0: three TMA box loads ------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"((uint32_t)(3 * box_w * max_rows))
+                 : "memory");
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // output channel c reads band 2 - c (BGR order)
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(smem_u32(s_src + (size_t)c * region)), "l"(&tmap), "r"(T.c_off + col_lo), "r"(T.r_off + row_lo),
+          "r"(2 - c), "r"(smem_u32(bar))
+          : "memory");
+    }
+  }
+  // overlapped with the copies: y taps of the CTA's rows and this thread's x taps
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kBY) {
+    const int y = threadIdx.x - 32;
+    const int oy = min(oy0 + y, T.nh - 1);
+    const int* k = tab_k + (size_t)(T.ytab + oy) * kMaxK;
+    s_ytab[y] = make_int4(tab_min[T.ytab + oy] - row_lo, k[0], k[1], 0);
+  }
+  const int x4 = 4 * lane;
+  int xs[4], k0[4], k1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ox = ox0 + x4 + j;
+    xs[j] = 0; k0[j] = 0; k1[j] = 0;
+    if (ox < T.nw) {
+      xs[j] = tab_min[T.xtab + ox] - col_lo;
+      const int2 kk = *reinterpret_cast<const int2*>(tab_k + (size_t)(T.xtab + ox) * kMaxK);
+      k0[j] = kk.x; k1[j] = kk.y;
+    }
+  }
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(0u)
+          : "memory");
+    }
+  }
+  // ---- phase 1: horizontal pass, 4 columns per thread -----------------------------------------
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const unsigned char* src_c = s_src + (size_t)c * region;
+    unsigned char* tmp_c = s_tmp + (size_t)c * max_rows * kBX + x4;
+    for (int r = warp; r < nrows; r += kWarps) {
+      const unsigned char* p = src_c + r * box_w;
+      const uint32_t v0 = (uint32_t)((int)p[xs[0]] * k0[0] + (int)p[xs[0] + 1] * k1[0] + kHalf) >> kPrecisionBits;
+      const uint32_t v1 = (uint32_t)((int)p[xs[1]] * k0[1] + (int)p[xs[1] + 1] * k1[1] + kHalf) >> kPrecisionBits;
+      const uint32_t v2 = (uint32_t)((int)p[xs[2]] * k0[2] + (int)p[xs[2] + 1] * k1[2] + kHalf) >> kPrecisionBits;
+      const uint32_t v3 = (uint32_t)((int)p[xs[3]] * k0[3] + (int)p[xs[3] + 1] * k1[3] + kHalf) >> kPrecisionBits;
+      *reinterpret_cast<uint32_t*>(tmp_c + r * kBX) = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: vertical pass, 4 consecutive rows per warp, 4 pixels per lane -----------------
+  if (ox0 + x4 >= T.nw) return;
+  const size_t oplane = (size_t)T.nh * T.nw;
+  const bool vec = ((T.nw & 3) == 0) && ((T.out_off & 3) == 0);
+  constexpr int kRows = kBY / kWarps;
+  const int y_begin = warp * kRows;
+  float* orow = out + T.out_off + (size_t)(oy0 + y_begin) * T.nw + ox0 + x4;
+  const unsigned char* colbase = s_tmp + x4;
+  const int cstride = max_rows * kBX;
+  int cur = -2;
+  int a[3][4], bb[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[c][j] = 0; bb[c][j] = 0; }
+#pragma unroll
+  for (int yy = 0; yy < kRows; ++yy) {
+    if (oy0 + y_begin + yy >= T.nh) break;
+    const int4 e = s_ytab[y_begin + yy];
+    if (e.x != cur) {
+      const bool adv = (e.x == cur + 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (adv) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[c][j] = bb[c][j];
+        } else {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(colbase + c * cstride + e.x * kBX);
+          a[c][0] = __byte_perm(u, 0, 0x4440); a[c][1] = __byte_perm(u, 0, 0x4441);
+          a[c][2] = __byte_perm(u, 0, 0x4442); a[c][3] = __byte_perm(u, 0, 0x4443);
+        }
+        // row e.x + 1 may be one past the staged rows when the tap count is 1: its weight is 0
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(colbase + c * cstride + (e.x + 1) * kBX);
+        bb[c][0] = __byte_perm(u, 0, 0x4440); bb[c][1] = __byte_perm(u, 0, 0x4441);
+        bb[c][2] = __byte_perm(u, 0, 0x4442); bb[c][3] = __byte_perm(u, 0, 0x4443);
+      }
+      cur = e.x;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 f;
+      // (acc >> 22) | 0x4B000000 in ONE funnel shift (hi word 0x4B000000 >> 10), then minus 2^23:
+      // exact int -> float for 0..255
+      f.x = __uint_as_float(__funnelshift_r((uint32_t)(a[c][0] * e.y + bb[c][0] * e.z + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.y = __uint_as_float(__funnelshift_r((uint32_t)(a[c][1] * e.y + bb[c][1] * e.z + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.z = __uint_as_float(__funnelshift_r((uint32_t)(a[c][2] * e.y + bb[c][2] * e.z + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.w = __uint_as_float(__funnelshift_r((uint32_t)(a[c][3] * e.y + bb[c][3] * e.z + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      float* dst = orow + c * oplane;
+      if (vec) {
+        __stcs(reinterpret_cast<float4*>(dst), f);
+      } else {
+        const int rem = T.nw - (ox0 + x4);
+        dst[0] = f.x;
+        if (rem > 1) dst[1] = f.y;
+        if (rem > 2) dst[2] = f.z;
+        if (rem > 3) dst[3] = f.w;
+      }
+    }
+    orow += T.nw;
+  }
+}
+
+// host: tensor map of the (W, H, bands) uint8 raster with a (box_w, box_h, 1) box
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool make_image_tensor_map(CUtensorMap* map, const void* image, int bands, int H, int W, int box_w, int box_h) {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)bands};
+  const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * (cuuint64_t)H};   // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(image), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- uint16 images: per-tile max of band 1 decides the branch (prediction.py:167) ----------
 __global__ void tile_band1_max_kernel(const unsigned short* __restrict__ image, int H, int W,
                                       const TileDesc* __restrict__ tiles, int* __restrict__ tile_max) {
@@ -593,7 +776,24 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
     const long long image_bytes = (long long)bands * H * W;
     const unsigned grid = (unsigned)P->n_blocks;
     const unsigned char* img = (const unsigned char*)image;
-    if (P->max_cnt <= 2 && P->max_k <= 3) {
+    bool launched = false;
+    if (P->max_cnt <= 2 && P->max_k <= 3 && (W % 16) == 0 && ((size_t)H * W) % 16 == 0 &&
+        ((uintptr_t)image & 15) == 0 && max_rows <= 256 && !getenv("TREEDET_NO_TMA")) {
+      // TMA-staged fast path
+      const int box_w = (P->max_cols + 2 + 15) & ~15;
+      const int region = (box_w * max_rows + 127) & ~127;
+      CUtensorMap tmap;
+      if (box_w <= 256 && make_image_tensor_map(&tmap, image, bands, H, W, box_w, max_rows)) {
+        const size_t smem_tma = (size_t)3 * region + (size_t)3 * max_rows * kBX + kBX + sizeof(int4) * kBY + 16;
+        auto kern = tile_resize_u8_up_tma_kernel;
+        if (smem_tma > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+        kern<<<grid, kThreads, smem_tma, st>>>(tmap, P->d_td, P->d_blk, P->d_min, P->d_cnt, P->d_k, out, max_rows, box_w,
+                                               region);
+        launched = true;
+      }
+    }
+    if (launched) {
+    } else if (P->max_cnt <= 2 && P->max_k <= 3) {
       // up-scaling fast path; one extra intermediate row is readable (weight 0 taps)
       const size_t smem_up = (size_t)3 * max_rows * src_stride + (size_t)3 * max_rows * kBX + kBX + sizeof(int4) * kBY;
       auto kern = tile_resize_u8_up_kernel;

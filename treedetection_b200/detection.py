@@ -64,7 +64,7 @@ def tile_data(file_list, out_dir, buffer=30, tile_width=200, tile_height=200, pa
     forest = None
     if forest_shapefile:
         from .fusion import ForestIndex
-        forest = ForestIndex.from_file(forest_shapefile)
+        forest = ForestIndex.from_file(forest_shapefile, logger=logger)
     total = len(todo)
     for i, data_path in enumerate(todo):
         try:

@@ -345,3 +345,25 @@ def seam_crop(a, b, axis, strip_w, strip_h):
     _lib.call("td_seam_crop", _ptr(a), _ptr(b), a.element_size(), bands, ha, wa, hb, wb, axis, strip_w, strip_h,
               _ptr(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------
+# P10  forest-outline predicates
+# ----------------------------------------------------------------------------
+def forest_predicates(a_verts, a_off, f_verts, f_off, f_bounds=None, a_filter=None):
+    """Query rings (crowns / tile boxes) against the union of the forest polygons.
+    Returns (intersects u8 (Na,), within u8 (Na,)); raises when the kernel's capacity
+    limits were exceeded for some query."""
+    na = a_off.shape[0] - 1
+    nf = f_off.shape[0] - 1
+    dev = a_verts.device
+    if f_bounds is None and nf > 0:
+        f_bounds = simplify_rings(f_verts, f_off, 0.0, want_bounds=True)["bounds"]
+    inter = torch.zeros((na,), dtype=torch.uint8, device=dev)
+    within = torch.zeros((na,), dtype=torch.uint8, device=dev)
+    _lib.call("td_forest_predicates", _ptr(a_verts), _ptr(a_off), na, _ptr(f_verts) if nf else None,
+              _ptr(f_off) if nf else None, _ptr(f_bounds) if nf else None, nf, _ptr(a_filter), _ptr(inter), _ptr(within),
+              _stream())
+    if na and int(torch.maximum(inter.max(), within.max()).item()) > 1:
+        raise _lib.TreedetError("td_forest_predicates: forest outline too dense for the kernel's per-query limits")
+    return inter, within

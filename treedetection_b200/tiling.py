@@ -28,8 +28,6 @@ def tile_grid(stem, transform, width, height, epsg, tile_width=50, tile_height=5
             tile_id = f"{stem}_{int(minx_f)}_{int(miny_f)}_{int(tile_width)}_{int(buffer)}_{epsg}"
             bounds = [minx_f - buffer, miny_f - buffer, minx_f + tile_width + buffer, miny_f + tile_height + buffer]
             only_forest, only_urban = False, False
-            if forest is not None:
-                only_forest, only_urban = forest.flags(minx_f, miny_f, minx_f + tile_width, miny_f + tile_height, bounds)
             win = geo.geometry_window(transform, width, height, *bounds)
             tf = geo.window_transform(transform, win.col_off, win.row_off)
             out[tile_id] = {
@@ -39,7 +37,16 @@ def tile_grid(stem, transform, width, height, epsg, tile_width=50, tile_height=5
                 "only_forest": bool(only_forest),
                 "only_urban": bool(only_urban),
                 "window": [win.col_off, win.row_off, win.width, win.height],
+                "_tile_box": [minx_f, miny_f, minx_f + tile_width, miny_f + tile_height],
             }
+    if forest is not None and out:
+        only_forest, only_urban = forest.tile_flags([m["_tile_box"] for m in out.values()],
+                                                    [m["bounds"] for m in out.values()])
+        for k, m in enumerate(out.values()):
+            m["only_forest"] = bool(only_forest[k])
+            m["only_urban"] = bool(only_urban[k])
+    for m in out.values():
+        del m["_tile_box"]
     return out
 
 
