@@ -36,7 +36,7 @@ UNIT = "km^2/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=10000, help="image side in pixels (0.2 m)")
@@ -325,7 +325,7 @@ def run_b200(a):
         return out
     for _ in range(max(1, min(a.warmup, 2))):
         step_e2e()
-    e2e_steps = max(1, min(a.steps, 10))
+    e2e_steps = max(1, min(a.steps, 20))
     ms_e2e, out = timed(step_e2e, e2e_steps)
     e2e_value = world * area * e2e_steps / (ms_e2e / 1e3)
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions

@@ -33,6 +33,24 @@ def test_tile_cut_normalize_uint8_bit_exact(dev):
     assert len(shapes) >= 3          # corner, edge and interior tiles
 
 
+def test_tile_cut_normalize_tma_path(dev):
+    """Raster width a multiple of 16: the TMA-staged kernel (UTMALDG) runs; windows start at
+    arbitrary, mostly 16-byte-unaligned columns."""
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, size=(4, 1200, 1600), dtype=np.uint8)
+    tf = synth.image_transform(synth.ORIGIN_X, synth.ORIGIN_Y + 1200 * 0.25, 0.25)
+    tiles = tiling.tile_grid("x", tf, 1600, 1200, 25832, 50, 50, 20)
+    win, net = _tables(tiles)
+    win = np.concatenate([win, np.array([[3, 5, 357, 211], [1243, 7, 357, 300], [0, 0, 1600, 1200][:4]], dtype=np.int32)])
+    win[-1] = [1201, 901, 399, 299]
+    net = np.array([tiling.resize_shortest_edge(int(w[3]), int(w[2])) for w in win], dtype=np.int32)
+    out, off, _ = ops.tile_cut_normalize(torch.from_numpy(img).to(dev), torch.from_numpy(win), torch.from_numpy(net))
+    out = out.cpu().numpy(); off = off.numpy()
+    for t in range(len(win)):
+        ref = port.tile_cut_normalize(img, tuple(int(v) for v in win[t]))
+        np.testing.assert_array_equal(out[off[t]:off[t + 1]].reshape(ref.shape), ref)
+
+
 def test_tile_cut_normalize_downscale(dev):
     rng = np.random.default_rng(1)
     img = rng.integers(0, 256, size=(4, 1300, 1700), dtype=np.uint8)
