@@ -104,15 +104,17 @@ TD_HD inline int ctz32(uint32_t v) {
 template <typename RasterType>
 TD_HD inline int follow_border(RasterType& R, int x0, int y0, bool hole, int lab, short* pts, int* first_xy,
                                int* last_xy) {
-  const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-  const int dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+  // 8-neighbourhood in OpenCV's order (E, NE, N, NW, W, SW, S, SE), two bits per entry (d + 1),
+  // so that a direction lookup is two ALU ops instead of a local-memory load
+  auto dx = [](int k) { return (int)((0x901Au >> (2 * (k & 7))) & 3u) - 1; };
+  auto dy = [](int k) { return (int)((0xA901u >> (2 * (k & 7))) & 3u) - 1; };
   int s_end = hole ? 0 : 4, s = s_end;
   int x1 = x0, y1 = y0;
   bool found = false;
   do {
     s = (s - 1) & 7;
-    x1 = x0 + dx[s];
-    y1 = y0 + dy[s];
+    x1 = x0 + dx(s);
+    y1 = y0 + dy(s);
     found = R.is_fg(x1, y1);
   } while (!found && s != s_end);
   int n = 0;
@@ -135,8 +137,8 @@ TD_HD inline int follow_border(RasterType& R, int x0, int y0, bool hole, int lab
     int k = s;
     while (k < 15) {
       ++k;
-      x4 = x3 + dx[k & 7];
-      y4 = y3 + dy[k & 7];
+      x4 = x3 + dx(k);
+      y4 = y3 + dy(k);
       if (R.is_fg(x4, y4)) break;
     }
     s = k & 7;
@@ -146,8 +148,8 @@ TD_HD inline int follow_border(RasterType& R, int x0, int y0, bool hole, int lab
       emit(px, py);
       prev_s = s;
     }
-    px += dx[s];
-    py += dy[s];
+    px += dx(s);
+    py += dy(s);
     if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
     x3 = x4;
     y3 = y4;
