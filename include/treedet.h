@@ -105,10 +105,13 @@ int td_trace_emit(const uint32_t* bits, const int* win, const long long* word_of
  *   alive   (V/32 + R + 2) u32 scratch;
  *   boxes (B,4) f64 + ring_box (R) i32, or both null (no filter);
  *   out_count (R) i32 kept vertices; out_bounds (R,4) f64 / out_area (R) f64 / out_keep (R)
- *   u8 may be null.  tolerance <= 0: no simplification (bounds / area of the ring itself). */
+ *   u8 may be null.  tolerance <= 0: no simplification (bounds / area of the ring itself).
+ *   bounds_of_input != 0: out_bounds holds the bounds of the INPUT ring (polygon.bounds of the
+ *   un-simplified crown, postprocessing.py:497-503) while out_area is that of simplify(tol).  */
 int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance, int* scratch,
                       uint32_t* alive, const double* boxes, const int* ring_box, int* out_count,
-                      double* out_bounds, double* out_area, unsigned char* out_keep, void* stream);
+                      double* out_bounds, double* out_area, unsigned char* out_keep, int bounds_of_input,
+                      void* stream);
 /*   output ring q = input ring sel[q]; dst_off (n_out+1) i64; scratch = the index lists
  *   above (copy kept vertices only) or null (copy whole rings)                           */
 int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,

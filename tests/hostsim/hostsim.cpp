@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "contour_core.cuh"
+#include "contour_lockstep.cuh"
 #if __has_include("simplify_core.cuh")
 #include "simplify_core.cuh"
 #define HS_HAVE_SIMPLIFY 1
@@ -50,6 +51,49 @@ int hs_find_contours(const uint8_t* mask, int h, int w, int* npts_out, int max_c
   out.pts = pts.data();
   td::ContourCounts c2 = td::scan_instance(R, &out);
   if (c2.n_contours != cc.n_contours || c2.n_points != cc.n_points) return -2;
+  td::contour_order(nc, parent.data(), lc.data(), ps.data(), order.data());
+  size_t k = 0;
+  for (int q = 0; q < nc; ++q) {
+    const int c = order[q];
+    npts_out[q] = npts[c];
+    std::memcpy(pts_out + 2 * k, pts.data() + 2 * (size_t)ptoff[c], sizeof(short) * 2 * npts[c]);
+    k += npts[c];
+  }
+  return nc;
+}
+
+// same contract as hs_find_contours, through the lock-step state machine (one lane)
+int hs_find_contours_lockstep(const uint8_t* mask, int h, int w, int* npts_out, int max_contours, short* pts_out,
+                              int max_points, int* counts4, long long* steps_out) {
+  const int wpr = (w + 31) / 32;
+  std::vector<uint32_t> fg((size_t)wpr * h, 0u), vis((size_t)wpr * h, 0u), rgt((size_t)wpr * h, 0u);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      if (mask[(size_t)y * w + x]) fg[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+  td::LaneState<unsigned short> S;
+  S.R.fg = fg.data(); S.R.visited = vis.data(); S.R.right = rgt.data(); S.R.label = nullptr;
+  S.R.w = w; S.R.h = h; S.R.wpr = wpr;
+  td::lane_init(S, nullptr);
+  long long steps = 0;
+  while (S.mode != td::kDone) { td::lane_step(S); ++steps; }
+  td::ContourCounts cc = S.cc;
+  if (counts4) { counts4[0] = cc.n_contours; counts4[1] = cc.n_points; counts4[2] = cc.n_rings; counts4[3] = cc.n_ring_verts; }
+  if (steps_out) *steps_out = steps;
+  if (cc.n_contours < 0 || cc.n_contours > max_contours || cc.n_points > max_points) return -1;
+  std::fill(vis.begin(), vis.end(), 0u);
+  std::fill(rgt.begin(), rgt.end(), 0u);
+  std::vector<unsigned short> lab((size_t)w * h + 1, 0);
+  S.R.label = lab.data();
+  const int nc = cc.n_contours;
+  std::vector<int> parent(nc + 1), npts(nc + 1), ptoff(nc + 1), lc(nc + 1), ps(nc + 1), order(nc + 1);
+  std::vector<unsigned char> hole(nc + 1);
+  std::vector<short> pts(2 * (size_t)cc.n_points + 2);
+  td::ContourOut out;
+  out.parent = parent.data(); out.npts = npts.data(); out.pt_off = ptoff.data(); out.is_hole = hole.data();
+  out.pts = pts.data();
+  td::lane_init(S, &out);
+  while (S.mode != td::kDone) td::lane_step(S);
+  if (S.cc.n_contours != cc.n_contours || S.cc.n_points != cc.n_points) return -2;
   td::contour_order(nc, parent.data(), lc.data(), ps.data(), order.data());
   size_t k = 0;
   for (int q = 0; q < nc; ++q) {

@@ -11,7 +11,7 @@ import pytest
 from tests import hostsim
 
 
-def ours(mask):
+def ours(mask, lockstep=False):
     lib = hostsim.load()
     h, w = mask.shape
     maxc, maxp = 70000, 4 * h * w + 16
@@ -19,8 +19,12 @@ def ours(mask):
     pts = np.zeros(2 * maxp, dtype=np.int16)
     counts = np.zeros(4, dtype=np.int32)
     m = np.ascontiguousarray(mask, dtype=np.uint8)
-    n = lib.hs_find_contours(m.ctypes.data_as(C.c_void_p), h, w, npts.ctypes.data_as(C.c_void_p), maxc,
-                             pts.ctypes.data_as(C.c_void_p), maxp, counts.ctypes.data_as(C.c_void_p))
+    if lockstep:
+        n = lib.hs_find_contours_lockstep(m.ctypes.data_as(C.c_void_p), h, w, npts.ctypes.data_as(C.c_void_p), maxc,
+                                          pts.ctypes.data_as(C.c_void_p), maxp, counts.ctypes.data_as(C.c_void_p), None)
+    else:
+        n = lib.hs_find_contours(m.ctypes.data_as(C.c_void_p), h, w, npts.ctypes.data_as(C.c_void_p), maxc,
+                                 pts.ctypes.data_as(C.c_void_p), maxp, counts.ctypes.data_as(C.c_void_p))
     assert n >= 0, n
     out, k = [], 0
     for i in range(n):
@@ -35,14 +39,15 @@ def theirs(mask):
 
 
 def check(mask):
-    a, counts = ours(mask)
     b = theirs(mask)
-    assert len(a) == len(b), (len(a), len(b))
-    for p, q in zip(a, b):
-        np.testing.assert_array_equal(p, q)
     rings = [c for c in b if c.size >= 8]
-    assert counts[2] == len(rings)
-    assert counts[3] == sum(len(c) + (0 if (c[0] == c[-1]).all() else 1) for c in rings)
+    for lockstep in (False, True):      # sequential core and the lock-step state machine
+        a, counts = ours(mask, lockstep)
+        assert len(a) == len(b), (lockstep, len(a), len(b))
+        for p, q in zip(a, b):
+            np.testing.assert_array_equal(p, q)
+        assert counts[2] == len(rings)
+        assert counts[3] == sum(len(c) + (0 if (c[0] == c[-1]).all() else 1) for c in rings)
 
 
 def test_nested_holes_and_islands():

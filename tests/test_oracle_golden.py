@@ -61,3 +61,30 @@ def test_post_process_port_matches_reference(name):
     got_verts = np.array([p for f in out for p in f["coords"]]).reshape(-1, 2)
     np.testing.assert_array_equal(got_verts, g["out_verts"])
     assert len(out) > 50
+
+
+def test_config1_port_matches_reference():
+    """BASELINE config 1 (bundled nDSM tile + synthetic RGBI): the oracle port against the
+    outputs of the reference's own process_features (tests/golden/make_golden_config1.py)."""
+    from tests.golden.make_golden_config1 import config1_scene
+    from treedetection_b200 import geo
+    g = np.load(os.path.join(G, "config1.npz"))
+    sc = config1_scene()
+    assert len(sc.det.scores) == int(g["n_instances"][0])
+    rings, conf = port.predict_stage(sc.det, sc.tiles)
+    np.testing.assert_array_equal(np.array(conf), g["stitched_conf"])
+    H, W = sc.rgbi.shape[1:]
+    oh, ow = int(H * 0.2), int(W * 0.2)
+    dec = np.stack([port.decimate_bilinear(sc.rgbi[b], oh, ow) for b in (0, 0, 0, 3)])
+    ndvi = port.ndvi_from_rgbi(dec).astype(np.float32)
+    ndvi_tf = geo.compose(sc.transform, geo.scale(W / ow, H / oh))
+    h, w = sc.ndsm.shape
+    cfg = dict(CFG)
+    out, dbg = port.post_process(rings, conf, ndvi, ndvi_tf, tuple(geo.raster_bounds(sc.transform, W, H)), sc.ndsm,
+                                 sc.ndsm_transform, tuple(geo.raster_bounds(sc.ndsm_transform, w, h)), 0.2, 0.2, cfg)
+    assert dbg["combined"]
+    np.testing.assert_array_equal(np.array(dbg["ids_after_nms"]), g["ids_after_nms"])
+    np.testing.assert_array_equal(np.array([int(f["poly_id"]) for f in out]), g["out_poly_id"])
+    np.testing.assert_array_equal(np.array([f["Area"] for f in out]), g["out_area"])
+    np.testing.assert_array_equal(np.array([f["TreeHeight"] for f in out], dtype=np.float32), g["out_height"])
+    np.testing.assert_array_equal(np.array([p for f in out for p in f["coords"]]).reshape(-1, 2), g["out_verts"])

@@ -33,7 +33,7 @@ SIGNATURES = {
     "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
                            _p]),
     # P4 / P9 geometry
-    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "td_take_rings": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     # P5
     "td_ndvi_decimate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),

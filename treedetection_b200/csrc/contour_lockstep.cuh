@@ -1,0 +1,200 @@
+// P3 core, lock-step form -- the same border following as contour_core.cuh (Suzuki-Abe with
+// OpenCV's conventions and output order; oracle: cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE),
+// TreeDetection/prediction.py:232-234), restructured as a per-lane STATE MACHINE so that the 32
+// lanes of a warp can each walk their own instance window in lock step:
+//
+//     while (any lane still working)  lane_step(state)
+//
+// One call performs one bounded micro-step: either "advance the raster scan to the next border
+// start (and begin that border)" or "one step along the current border".  The step along a
+// border is branch-light: the 8 neighbours are gathered into a bit mask from three 3-bit row
+// reads and the next direction is a find-first-set on the rotated mask.  contour_core.cuh keeps
+// the straightforward sequential form; both are checked against cv2 (tests/test_hostsim_contours.py).
+//
+// Plain C++ (tests/hostsim runs it with a single lane).
+#pragma once
+#include "contour_core.cuh"
+
+namespace td {
+
+enum LaneMode { kScan = 0, kFollow = 1, kDone = 2 };
+
+template <typename LabelT>
+struct LaneState {
+  RasterT<LabelT> R;
+  ContourOut* out;      // null: count only
+  ContourCounts cc;
+  int mode;
+  // raster scan
+  int y, wi, min_o, min_h;
+  // current border
+  int x0, y0, x1, y1, x3, y3, s, prev_s, px, py, npts, hole;
+  int first_x, first_y, last_x, last_y, parent;
+};
+
+TD_HD inline int dir_dx(int k) { return (int)((0x901Au >> (2 * (k & 7))) & 3u) - 1; }
+TD_HD inline int dir_dy(int k) { return (int)((0xA901u >> (2 * (k & 7))) & 3u) - 1; }
+
+TD_HD inline int ffs32(uint32_t v) {   // index of the lowest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+// bits (x-1, x, x+1) of row y as a 3-bit value, zero outside the window
+template <typename LabelT>
+TD_HD inline uint32_t row3(const RasterT<LabelT>& R, int x, int y) {
+  if ((unsigned)y >= (unsigned)R.h) return 0u;
+  const int wi = x >> 5, b = x & 31;
+  const uint32_t* row = R.fg + (size_t)y * R.wpr;
+  const uint32_t lo = row[wi];
+  if (b == 0) return (wi > 0 ? (row[wi - 1] >> 31) : 0u) | ((lo & 3u) << 1);
+  if (b == 31) return ((lo >> 30) & 3u) | ((wi + 1 < R.wpr ? (row[wi + 1] & 1u) : 0u) << 2);
+  return (lo >> (b - 1)) & 7u;
+}
+
+// 8-neighbour foreground mask of (x, y), bit k = direction k (E, NE, N, NW, W, SW, S, SE)
+template <typename LabelT>
+TD_HD inline uint32_t neighbours(const RasterT<LabelT>& R, int x, int y) {
+  const uint32_t t = row3(R, x, y - 1), m = row3(R, x, y), b = row3(R, x, y + 1);
+  return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
+         ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
+}
+
+template <typename LabelT>
+TD_HD inline void lane_emit(LaneState<LabelT>& S, int x, int y) {
+  if (S.out) {
+    short* p = S.out->pts + 2 * ((size_t)S.cc.n_points + S.npts);
+    p[0] = (short)x;
+    p[1] = (short)y;
+  }
+  if (S.npts == 0) { S.first_x = x; S.first_y = y; }
+  S.last_x = x;
+  S.last_y = y;
+  ++S.npts;
+}
+
+template <typename LabelT>
+TD_HD inline void lane_finish_border(LaneState<LabelT>& S) {
+  const int idx = S.cc.n_contours;
+  if (S.out) {
+    S.out->parent[idx] = S.parent;
+    S.out->npts[idx] = S.npts;
+    S.out->pt_off[idx] = S.cc.n_points;
+    S.out->is_hole[idx] = S.hole ? 1 : 0;
+  }
+  S.cc.n_contours += 1;
+  S.cc.n_points += S.npts;
+  if (S.npts >= 4) {
+    S.cc.n_rings += 1;
+    S.cc.n_ring_verts += S.npts + ((S.first_x != S.last_x || S.first_y != S.last_y) ? 1 : 0);
+  }
+  if (S.hole) { S.min_o = S.x0 + 1; S.min_h = S.x0 + 1; }
+  else { S.min_o = S.x0 + 1; S.min_h = S.x0; }
+  S.mode = kScan;
+}
+
+template <typename LabelT>
+TD_HD inline void lane_init(LaneState<LabelT>& S, ContourOut* out) {
+  S.out = out;
+  S.cc.n_contours = S.cc.n_points = S.cc.n_rings = S.cc.n_ring_verts = 0;
+  S.y = 0; S.wi = 0; S.min_o = 0; S.min_h = 0;
+  S.mode = (S.R.w > 0 && S.R.h > 0) ? kScan : kDone;
+  S.npts = 0; S.hole = 0; S.parent = -1;
+  S.x0 = S.y0 = S.x1 = S.y1 = S.x3 = S.y3 = S.s = S.prev_s = S.px = S.py = 0;
+  S.first_x = S.first_y = S.last_x = S.last_y = 0;
+}
+
+// one micro-step of one lane
+template <typename LabelT>
+TD_HD inline void lane_step(LaneState<LabelT>& S) {
+  RasterT<LabelT>& R = S.R;
+  if (S.mode == kFollow) {
+    // ---- one step along the border ------------------------------------------------------------
+    const int s_end = S.s;
+    const uint32_t m = neighbours(R, S.x3, S.y3);
+    // first foreground neighbour counter-clockwise after s_end: directions s_end+1 .. s_end+8
+    const uint32_t rot = ((m | (m << 8)) >> (s_end + 1)) & 0xffu;
+    const int k = s_end + 1 + ffs32(rot | 0x100u);     // rot != 0: we arrived from a neighbour
+    const int s = k & 7;
+    const int x4 = S.x3 + dir_dx(s), y4 = S.y3 + dir_dy(s);
+    R.mark(S.x3, S.y3, (unsigned)(s - 1) < (unsigned)s_end, S.cc.n_contours);
+    if (s != S.prev_s) {
+      lane_emit(S, S.px, S.py);
+      S.prev_s = s;
+    }
+    S.px += dir_dx(s);
+    S.py += dir_dy(s);
+    if (x4 == S.x0 && y4 == S.y0 && S.x3 == S.x1 && S.y3 == S.y1) {
+      lane_finish_border(S);
+      return;
+    }
+    S.x3 = x4;
+    S.y3 = y4;
+    S.s = (s + 4) & 7;
+    return;
+  }
+  if (S.mode != kScan) return;
+  // ---- advance the raster scan to the next border start ----------------------------------------
+  const int y = S.y;
+  for (; S.wi < R.wpr; ++S.wi) {
+    const int wi = S.wi;
+    const uint32_t F = R.word(R.fg, y, wi);
+    if (!F) continue;
+    const uint32_t Fl = R.word(R.fg, y, wi - 1), Fr = R.word(R.fg, y, wi + 1);
+    const uint32_t V = R.word(R.visited, y, wi), N = R.word(R.right, y, wi);
+    const uint32_t prevfg = (F << 1) | (Fl >> 31);
+    const uint32_t nextfg = (F >> 1) | (Fr << 31);
+    uint32_t O = F & ~V & ~prevfg;   // unvisited pixel after a 0
+    uint32_t H = F & ~N & ~nextfg;   // pixel without the right flag before a 0
+    const int base = wi * 32;
+    if (S.min_o > base) O &= (S.min_o - base >= 32) ? 0u : ~((1u << (S.min_o - base)) - 1u);
+    if (S.min_h > base) H &= (S.min_h - base >= 32) ? 0u : ~((1u << (S.min_h - base)) - 1u);
+    if (!(O | H)) continue;
+    const int a = O ? ffs32(O) : 64, b = H ? ffs32(H) : 64;
+    const bool hole = !(a <= b);
+    const int x = base + (hole ? b : a);
+    if (S.cc.n_contours >= 65534) { S.cc.n_contours = -1; S.mode = kDone; return; }
+    // parent from the label of the last visited pixel on this row (see contour_core.cuh)
+    int parent = -1;
+    if (S.out) {
+      const int ln = R.lnbd(hole ? x + 1 : x, y);
+      if (ln >= 0) {
+        parent = ln;
+        if ((S.out->is_hole[ln] != 0) == hole) parent = S.out->parent[ln];
+      }
+    }
+    S.parent = parent;
+    S.hole = hole ? 1 : 0;
+    S.x0 = x; S.y0 = y; S.npts = 0;
+    // first neighbour clockwise from west (outer) / east (hole)
+    const int s_end = hole ? 0 : 4;
+    const uint32_t m = neighbours(R, x, y);
+    int s = s_end;
+    bool found = false;
+    for (int j = 0; j < 8 && !found; ++j) {
+      s = (s - 1) & 7;
+      found = (m >> s) & 1u;
+      if (s == s_end) break;
+    }
+    if (!found || s == s_end) {   // isolated pixel
+      R.mark(x, y, true, S.cc.n_contours);
+      lane_emit(S, x, y);
+      lane_finish_border(S);
+      return;                     // stay on this word: more starts may follow
+    }
+    S.x1 = x + dir_dx(s); S.y1 = y + dir_dy(s);
+    S.x3 = x; S.y3 = y;
+    S.s = s; S.prev_s = s ^ 4;
+    S.px = x; S.py = y;
+    S.mode = kFollow;
+    return;
+  }
+  // row exhausted
+  S.wi = 0; S.min_o = 0; S.min_h = 0;
+  if (++S.y >= R.h) S.mode = kDone;
+}
+
+}  // namespace td

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128)
 simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
                 int* __restrict__ scratch, uint32_t* __restrict__ alive, const double* __restrict__ boxes,
                 const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
-                double* __restrict__ out_area, unsigned char* __restrict__ out_keep) {
+                double* __restrict__ out_area, unsigned char* __restrict__ out_keep, int bounds_of_input) {
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
@@ -41,8 +41,9 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   }
   __syncwarp();
   double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-  for (int k = lane; k < m; k += 32) {
-    const td::P2 p = pts[sc[k]];
+  const int nb = bounds_of_input ? len : m;
+  for (int k = lane; k < nb; k += 32) {
+    const td::P2 p = bounds_of_input ? pts[k] : pts[sc[k]];
     minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
     miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
   }
@@ -97,13 +98,14 @@ __global__ void take_rings_kernel(const double* __restrict__ verts, const long l
 extern "C" int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance,
                                  int* scratch, uint32_t* alive, const double* boxes, const int* ring_box,
                                  int* out_count, double* out_bounds, double* out_area, unsigned char* out_keep,
-                                 void* stream) {
+                                 int bounds_of_input, void* stream) {
   TD_ARG(n_rings >= 0);
   if (n_rings == 0) return TD_OK;
   TD_ARG(verts && ring_off && scratch && alive && out_count);
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
   simplify_kernel<<<td_div_up((long long)n_rings * 32, 128), 128, 0, (cudaStream_t)stream>>>(
-      verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep);
+      verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep,
+      bounds_of_input);
   TD_CHECK_LAUNCH("td_simplify_rings");
   return TD_OK;
 }

@@ -167,21 +167,20 @@ def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_
                         z(torch.float64, 0), z(torch.float32, 0), z(torch.float32, 0, 2), z(torch.uint8, 0),
                         z(torch.int32, 0), extras)
 
-    # 1. confidence filter; poly_id = enumeration index after it (postprocessing.py:739-754)
-    sel0 = torch.nonzero(table.conf >= p.confidence_threshold).flatten()
-    if sel0.numel() == 0:
-        return empty()
-    verts0, off0 = ops.take_rings(table.verts, table.ring_off, sel0)
-    conf0 = table.conf[sel0]
-    # 2. area of simplify(2), bounds of the ORIGINAL ring
-    s2 = ops.simplify_rings(verts0, off0, 2.0, want_bounds=False, want_area=True)
-    area0 = s2["area"]
-    sel1 = torch.nonzero((area0 >= p.area_threshold) & (area0 <= 1000)).flatten()
+    # 1. + 2. confidence filter, poly_id = enumeration index after it, area of simplify(2) in
+    #    [area_threshold, 1000] (postprocessing.py:739-768) -- one kernel pass over all stitched rings
+    #    (area of simplify(2) + bounds of the ORIGINAL ring), one compaction
+    conf_ok = table.conf >= p.confidence_threshold
+    s2 = ops.simplify_rings(table.verts, table.ring_off, 2.0, want_bounds=True, want_area=True, bounds_of_input=True)
+    area_all = s2["area"]
+    pid_all = torch.cumsum(conf_ok.to(torch.int64), 0) - 1
+    sel1 = torch.nonzero(conf_ok & (area_all >= p.area_threshold) & (area_all <= 1000)).flatten()
     if sel1.numel() == 0:
         return empty()
-    verts1, off1 = ops.take_rings(verts0, off0, sel1)
-    conf1, area1, pid1 = conf0[sel1], area0[sel1].contiguous(), sel1
-    b1 = ops.simplify_rings(verts1, off1, 0.0, want_bounds=True)["bounds"]   # tolerance 0: plain bounds
+    verts1, off1 = ops.take_rings(table.verts, table.ring_off, sel1)
+    conf1, area1, pid1 = table.conf[sel1], area_all[sel1].contiguous(), pid_all[sel1]
+    b1 = s2["bounds"][sel1].contiguous()
+    area0 = area_all
     # 3. ordered bbox NMS (P6)
     removed = ops.bbox_nms_ordered(b1, conf1.contiguous(), area1, p.iou_threshold, p.area_threshold)
     sel2 = torch.nonzero(removed == 0).flatten()
