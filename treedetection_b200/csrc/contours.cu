@@ -5,76 +5,90 @@
 // identity resize, cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE), contour.size >= 8,
 // closing point) and xy_gpu (TreeDetection/utilities.py:182-207: corner convention,
 // float64).  The reference moves H*W*4 bytes to the device and back and launches ~8
-// kernels per contour; here one warp owns one instance window staged in shared memory (the walk
-// is inherently sequential per instance, there are ~10^5 independent instances per image).
+// kernels per contour; here every lane of a warp walks its own instance window in lock step, the
+// windows' bit planes staged in shared memory (the walk is inherently sequential per instance,
+// there are ~10^5 independent instances per image).
 //
 // Two passes because output sizes are data dependent: td_trace_count returns, per
 // instance, the number of borders / points / kept rings / ring vertices; after a scan
 // (caller side) td_trace_emit re-walks and writes rings in OpenCV's order.
 #include "common.cuh"
 #include "contour_core.cuh"
+#include "contour_lockstep.cuh"
 
 namespace {
 
-constexpr int kTraceWarps = 8;                 // instances per CTA (one warp each)
-constexpr int kCountSmemPerWarp = 3 * 1024;    // count pass: 3 bit planes (windows up to ~90 x 90 px)
-constexpr int kEmitSmemPerWarp = 6 * 1024;     // emit pass: + labels (1 B / px below 255 borders)
+constexpr int kSmemPerWarp = 32 * 1024;   // bit planes of the 32 windows a warp walks
 
-// Border following is sequential per instance, and every step depends on the previous
-// pixel test: run from global memory a step costs an L2 round trip.  So one WARP owns one
-// instance: the lanes copy the window's foreground plane into shared memory (and clear the
-// two scratch planes), lane 0 walks the borders at shared-memory latency, and in the emit
-// pass all lanes write the ring vertices.  The per-warp budgets are small on purpose: the
-// walk is latency bound, so what matters is how many warps an SM can keep resident (64 with
-// these budgets).  Windows that do not fit fall back to the global scratch planes.
+// Border following is sequential per instance and issue bound, so the 32 lanes of a warp each
+// walk their OWN instance window in lock step (contour_lockstep.cuh: a per-lane state machine,
+// one bounded micro-step per iteration).  The three bit planes of a window (foreground + the
+// two scratch planes) are packed into the warp's shared memory by a warp prefix sum over the
+// windows' sizes; windows that do not fit (rare, large boxes) use the global scratch planes.
+// Labels (needed only for the parent lookup at a border start) stay in global memory.
 template <typename LabelT>
-__device__ bool stage_window(td::RasterT<LabelT>& R, const uint32_t* bits, const int* win, const long long* word_off,
-                             int i, uint32_t* planes, long long total_words, LabelT* labels_global,
-                             unsigned char* smem_warp, int budget, bool want_labels) {
-  R.w = win[4 * i + 2];
-  R.h = win[4 * i + 3];
-  R.wpr = (R.w + 31) >> 5;
+__device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_t* __restrict__ bits,
+                              const int* __restrict__ win, const long long* __restrict__ word_off, int i,
+                              uint32_t* __restrict__ planes, long long total_words, unsigned char* smem) {
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  R.w = active ? win[4 * i + 2] : 0;
+  R.h = active ? win[4 * i + 3] : 0;
+  R.wpr = (R.w + 31) >> 5;
   const int nwords = R.wpr * R.h;
-  const uint32_t* fg = bits + word_off[i];
-  const size_t need = (size_t)12 * nwords + (want_labels ? sizeof(LabelT) * (size_t)R.w * R.h : 0);
-  const bool in_smem = nwords > 0 && need <= (size_t)budget;
-  if (in_smem) {
-    uint32_t* s_fg = reinterpret_cast<uint32_t*>(smem_warp);
-    uint32_t* s_vis = s_fg + nwords;
-    uint32_t* s_rgt = s_vis + nwords;
-    for (int k = lane; k < nwords; k += 32) { s_fg[k] = fg[k]; s_vis[k] = 0u; s_rgt[k] = 0u; }
-    R.fg = s_fg; R.visited = s_vis; R.right = s_rgt;
-    R.label = want_labels ? reinterpret_cast<LabelT*>(s_rgt + nwords) : nullptr;
-  } else {
-    R.fg = fg;
-    R.visited = planes + word_off[i];
-    R.right = planes + total_words + word_off[i];
-    R.label = want_labels ? labels_global : nullptr;
+  const long long woff = active ? word_off[i] : 0;
+  // warp exclusive scan of the bytes each window needs in shared memory
+  const int need = 12 * nwords;
+  int incl = need;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int off = incl - need;
+  const bool in_smem = nwords > 0 && incl <= kSmemPerWarp;
+  uint32_t* s_fg = reinterpret_cast<uint32_t*>(smem + off);
+  // cooperative copy: all lanes copy window j's words (coalesced), then clear its scratch planes
+  for (int j = 0; j < 32; ++j) {
+    const int nw_j = __shfl_sync(full, nwords, j);
+    const int in_j = __shfl_sync(full, (int)in_smem, j);
+    const int off_j = __shfl_sync(full, off, j);
+    const long long woff_j = __shfl_sync(full, woff, j);
+    if (!in_j) continue;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + off_j);
+    const uint32_t* src = bits + woff_j;
+    for (int k = lane; k < nw_j; k += 32) {
+      dst[k] = src[k];
+      dst[nw_j + k] = 0u;
+      dst[2 * nw_j + k] = 0u;
+    }
   }
   __syncwarp();
-  return in_smem;
+  if (in_smem) {
+    R.fg = s_fg; R.visited = s_fg + nwords; R.right = s_fg + 2 * nwords;
+  } else {
+    R.fg = bits + woff;
+    R.visited = planes + woff;
+    R.right = planes + total_words + woff;
+  }
+  R.label = nullptr;
 }
 
-__global__ void __launch_bounds__(32 * kTraceWarps)
+__global__ void __launch_bounds__(32)
 trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ win, const long long* __restrict__ word_off,
                    int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * kTraceWarps + warp;
-  if (i >= n) return;
-  td::ContourCounts cc = {0, 0, 0, 0};
-  if (win[4 * i + 2] > 0 && win[4 * i + 3] > 0) {
-    td::Raster R;
-    stage_window<unsigned short>(R, bits, win, word_off, i, planes, total_words, nullptr,
-                                 smem + (size_t)warp * kCountSmemPerWarp, kCountSmemPerWarp, false);
-    if (lane == 0) cc = td::scan_instance(R, nullptr);
-  }
-  if (lane == 0) {
-    counts[4 * i + 0] = cc.n_contours;
-    counts[4 * i + 1] = cc.n_points;
-    counts[4 * i + 2] = cc.n_rings;
-    counts[4 * i + 3] = cc.n_ring_verts;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool active = i < n;
+  td::LaneState<unsigned short> S;
+  stage_windows(S.R, active, bits, win, word_off, i, planes, total_words, smem);
+  td::lane_init(S, nullptr);
+  while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
+  if (active) {
+    counts[4 * i + 0] = S.cc.n_contours;
+    counts[4 * i + 1] = S.cc.n_points;
+    counts[4 * i + 2] = S.cc.n_rings;
+    counts[4 * i + 3] = S.cc.n_ring_verts;
   }
 }
 
@@ -104,47 +118,30 @@ struct EmitArgs {
   double* verts;               // (V, 2)
 };
 
-__global__ void __launch_bounds__(32 * kTraceWarps) trace_emit_kernel(EmitArgs A) {
+__global__ void __launch_bounds__(32) trace_emit_kernel(EmitArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * kTraceWarps + warp;
-  if (i >= A.n) return;
-  const int wx0 = A.win[4 * i + 0], wy0 = A.win[4 * i + 1];
-  if (A.win[4 * i + 2] <= 0 || A.win[4 * i + 3] <= 0) return;
-  const long long c0 = A.cont_off[i];
-  const int nc = (int)(A.cont_off[i + 1] - c0);
-  if (nc == 0) return;
-  unsigned char* my_smem = smem + (size_t)warp * kEmitSmemPerWarp;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool active = i < A.n;
+  td::LaneState<unsigned short> S;
+  stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem);
+  const long long c0 = active ? A.cont_off[i] : 0;
+  const int nc = active ? (int)(A.cont_off[i + 1] - c0) : 0;
   td::ContourOut out;
   out.parent = A.ct_parent + c0;
   out.npts = A.ct_npts + c0;
   out.pt_off = A.ct_ptoff + c0;
   out.is_hole = A.ct_hole + c0;
-  out.pts = A.pts + 2 * A.pts_off[i];
+  out.pts = A.pts + 2 * (active ? A.pts_off[i] : 0);
+  if (active) S.R.label = A.labels + A.px_off[i];
+  td::lane_init(S, &out);
+  if (nc == 0) S.mode = td::kDone;          // nothing to emit: skip the walk
+  while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
+  if (!active || nc == 0) return;
   int* last_child = A.ct_scratch + 3 * c0;
   int* prev_sib = last_child + nc;
   int* order = prev_sib + nc;
-  // labels are border indices: one byte is enough below 255 borders (global fallback keeps u16)
-  bool staged8 = false;
-  if (nc < 255) {
-    td::RasterT<unsigned char> R8;
-    R8.w = A.win[4 * i + 2]; R8.h = A.win[4 * i + 3]; R8.wpr = (R8.w + 31) >> 5;
-    const size_t need = (size_t)12 * R8.wpr * R8.h + (size_t)R8.w * R8.h;
-    if (need <= (size_t)kEmitSmemPerWarp) {
-      stage_window<unsigned char>(R8, A.bits, A.win, A.word_off, i, A.planes, A.total_words, nullptr, my_smem,
-                                  kEmitSmemPerWarp, true);
-      if (lane == 0) td::scan_instance(R8, &out);
-      staged8 = true;
-    }
-  }
-  if (!staged8) {
-    td::Raster R;
-    stage_window<unsigned short>(R, A.bits, A.win, A.word_off, i, A.planes, A.total_words, A.labels + A.px_off[i],
-                                 my_smem, kEmitSmemPerWarp, true);
-    if (lane == 0) td::scan_instance(R, &out);
-  }
-  if (lane == 0) td::contour_order(nc, out.parent, last_child, prev_sib, order);
-  __syncwarp();   // lane 0's tables and points become visible to the warp
+  td::contour_order(nc, out.parent, last_child, prev_sib, order);
+  const int wx0 = A.win[4 * i + 0], wy0 = A.win[4 * i + 1];
   const double* tf = A.tile_tf + 6 * (size_t)A.inst_tile[i];
   const double ta = tf[0], tb = tf[1], tc = tf[2], td_ = tf[3], te = tf[4], tff = tf[5];
   long long ring = A.ring_base[i];
@@ -156,11 +153,9 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_emit_kernel(EmitArgs A
     const short* p = out.pts + 2 * (size_t)out.pt_off[c];
     const bool close = (p[0] != p[2 * (np - 1)]) || (p[1] != p[2 * (np - 1) + 1]);
     const int nv = np + (close ? 1 : 0);
-    if (lane == 0) {
-      A.ring_off[ring] = v;
-      A.ring_inst[ring] = i;
-    }
-    for (int q = lane; q < nv; q += 32) {
+    A.ring_off[ring] = v;
+    A.ring_inst[ring] = i;
+    for (int q = 0; q < nv; ++q) {
       const int qq = q < np ? q : 0;
       const double col = (double)(p[2 * qq] + wx0), row = (double)(p[2 * qq + 1] + wy0);
       // xy_gpu: a * x + b * y + c, every operation rounded (float64)
@@ -182,8 +177,7 @@ extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long l
   TD_ARG(bits && win && word_off && planes && counts);
   cudaStream_t st = (cudaStream_t)stream;
   TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
-  trace_count_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kCountSmemPerWarp, st>>>(
-      bits, win, word_off, n_inst, planes, total_words, counts);
+  trace_count_kernel<<<td_div_up(n_inst, 32), 32, kSmemPerWarp, st>>>(bits, win, word_off, n_inst, planes, total_words, counts);
   TD_CHECK_LAUNCH("td_trace_count");
   return TD_OK;
 }
@@ -212,7 +206,7 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   A.ct_scratch = ct_int5 + 3 * total_contours;
   A.ct_hole = ct_hole; A.pts = pts; A.inst_tile = inst_tile; A.tile_tf = tile_tf;
   A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
-  trace_emit_kernel<<<td_div_up(n_inst, kTraceWarps), 32 * kTraceWarps, kTraceWarps * kEmitSmemPerWarp, st>>>(A);
+  trace_emit_kernel<<<td_div_up(n_inst, 32), 32, kSmemPerWarp, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
   return TD_OK;
 }
