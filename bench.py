@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=3000, help="side (px) of the CPU-baseline sample scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--serial", action="store_true",
+                    help="one stream: P1 and the P2-P9 chain back to back (default: P1 on its own stream, "
+                         "overlapping the latency-bound chain)")
     return ap.parse_args()
 
 
@@ -262,7 +265,40 @@ def run_b200(a):
 
     stage_ev = []
 
+    # P1 (HBM bound, feeds the predictor) and the P2-P9 chain (latency bound, consumes the
+    # predictor's outputs) are independent: P1 rides its own stream, the chain a high-priority one
+    p1_stream = torch.cuda.Stream(device=dev)
+    chain_stream = torch.cuda.Stream(device=dev, priority=-1)
+
     def step_resident():
+        if a.serial:
+            return step_serial()
+        main = torch.cuda.current_stream()
+        e = [ev() for _ in range(5)]
+        p1_stream.wait_stream(main)
+        chain_stream.wait_stream(main)
+        with torch.cuda.stream(p1_stream):
+            e[0].record()
+            tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+            e[1].record()
+        p1_ev.append((e[0], e[1]))
+        with torch.cuda.stream(chain_stream):
+            s0 = ev(); s0.record()
+            table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
+                                           tables.tile_tf, tables.tile_boxes, p)
+            e[2].record()
+            rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
+            e[3].record()
+            feats = pipeline.postprocess_stage(table, rasters, p)
+            e[4].record()
+        stage_ev.append([e[0], e[1], s0, e[2], e[3], e[4]])
+        main.wait_stream(p1_stream)
+        main.wait_stream(chain_stream)
+        if world > 1:
+            step_strip()
+        return len(table), len(feats)
+
+    def step_serial():
         e = [ev() for _ in range(5)]
         e[0].record()
         tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
@@ -275,7 +311,7 @@ def run_b200(a):
         e[3].record()
         feats = pipeline.postprocess_stage(table, rasters, p)
         e[4].record()
-        stage_ev.append(e)
+        stage_ev.append([e[0], e[1], e[1], e[2], e[3], e[4]])
         if world > 1:
             step_strip()
         return len(table), len(feats)
@@ -313,7 +349,8 @@ def run_b200(a):
     launches = _lib.launch_count - l0
     p1_ms = statistics.mean(x.elapsed_time(y) for x, y in p1_ev)
     names = ["P1 tile cut/normalise", "P2-P4 paste/contours/stitch", "P5 NDVI/decimation", "P6-P9 NMS/stats/select"]
-    stage_ms = {n: statistics.mean(e[i].elapsed_time(e[i + 1]) for e in stage_ev) for i, n in enumerate(names)}
+    pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
+    stage_ms = {n: statistics.mean(e[i].elapsed_time(e[j]) for e in stage_ev) for (i, j), n in zip(pairs, names)}
     area = sc.area_km2
     value = world * area * a.steps / (ms / 1e3)
 
@@ -371,6 +408,17 @@ def run_b200(a):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = p1_bytes / (p1_ms / 1e3) / 1e9
+        # whole path: SURVEY.md section 8d per-unit algorithmic bytes x the units of this run
+        hh, ww = host.rgbi.shape[1:]
+        ndvi_px = int(hh * p.ndvi_scaling_factor) * int(ww * p.ndvi_scaling_factor)
+        path_bytes = {
+            "P1": p1_bytes,
+            "P2-P4": n_inst * (3136 + 20 + 320) + n_inst * (320 + 512) + n_cand * 1024,
+            "P5": 2 * hh * ww + 4 * int(host.ndsm.numel()) + 4 * ndvi_px,
+            "P6-P9": 37 * n_cand + n_final * ((10752 if a.ndsm_px == 0.2 else 717) + 205),
+        }
+        path_total = sum(path_bytes.values())
+        path_gbs = path_total / (ms / a.steps / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -379,17 +427,23 @@ def run_b200(a):
                                    f"single model, tile 50 m / buffer 20 m ({n_tiles} tiles, {n_inst} ROI-head "
                                    f"instances replayed from fixtures -> {n_cand} candidate crowns -> {n_final} crowns)",
                        "area_km2_per_gpu": area, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
+                       "streams": ("one stream, stages back to back" if a.serial else
+                                   "P1 on its own stream concurrent with the P2-P9 chain (high-priority stream); "
+                                   "stage_ms are per-stream CUDA-event times and overlap"),
                        "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                        "cache": "inputs (rasters 0.8 GB, P1 output 12 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": (f"image-row sharding x{world}; per step every rank r < N-1 also receives the "
                                        f"135-row RGBI + nDSM halo of rank r+1 (NCCL send/recv) and runs the down-seam "
                                        f"strip through the same path" if world > 1 else
                                        "1 GPU; image-row sharding for N > 1")},
-            "roofline": {"bound": "hbm", "kernel": "tile_resize_u8_kernel (P1)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "tile_resize_u8_up_tma_kernel (P1)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": p1_bytes, "ms_per_launch": p1_ms,
                          "share_of_step": p1_ms / (ms / a.steps)},
+            "path_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": path_total, "by_stage": path_bytes,
+                              "achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
+                              "note": "all stages of one step against the same HBM peak (SURVEY 8d per-unit bytes)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,

@@ -490,12 +490,188 @@ tile_resize_u8_up_tma_kernel(const __grid_constant__ CUtensorMap tmap, const Til
   up_phase2(T, s_tmp, s_ytab, max_rows, ox0, oy0, warp, x4, out);
 }
 
-// host: tensor map of the (W, H, bands) uint8 raster with a (box_w, box_h, 1) box
+// ---- warp-autonomous variant of the fast path ("v6") -------------------------------------------
+// The CTA kernels above spend more than half of their issue slots outside the arithmetic: the
+// intermediate (horizontally filtered) rows make a round trip through shared memory (pack, store,
+// barrier, load, unpack) and every short-lived CTA pays a serial prologue (table look-ups, TMA
+// round trip) that its few sibling CTAs must hide.  Here ONE WARP owns a 128-column strip of
+// `nrows` consecutive output rows of one tile and needs nobody else:
+//   * source rows stream through a private two-stage ring in shared memory, filled by TMA
+//     (one cp.async.bulk.tensor.3d per chunk: box = box_w bytes x kChunk rows x 3 bands; chunk
+//     k + 1 is requested when the first row of chunk k is touched, so the copy hides behind the
+//     ~14 output rows the chunk feeds);
+//   * the horizontal pass of a source row goes straight into registers (4 pixels x 3 channels
+//     per lane) exactly once per strip -- the two source rows an output row blends live in two
+//     register sets indexed by the parity of the source row, so advancing a row overwrites the
+//     stale set and only the two vertical coefficients swap;
+//   * the vertical pass streams 128-bit coalesced float rows out (st.global.cs).
+// No __syncthreads, no shared-memory intermediates: ~8 instructions per output float instead of ~20.
+constexpr int kChunk = 8;          // source rows per TMA chunk
+constexpr int kWarpsV6 = 4;        // warps per CTA (independent of each other)
+#ifndef TD_P1_MINBLOCKS
+#define TD_P1_MINBLOCKS 6
+#endif
+constexpr int kMinBlocksV6 = TD_P1_MINBLOCKS;   // 6 CTAs x 4 warps per SM: 80 registers, no spills
+
+// One warp's work, fully resolved at plan time (64 bytes, four independent 128-bit loads): the
+// kernel's prologue is one round trip for this record and one for the taps it points to.
+struct StripItem {
+  int x_box, y_box;        // TMA start coordinates of chunk 0 (x_box 16-byte aligned)
+  int n_chunks, nrows;     // source chunks / output rows of this item
+  int xtab, ytab;          // first entries of the strip's x taps / the item's y taps in the tables
+  int xbias, row_lo;       // added to tab_min[x] -> byte offset in a staged row; first source row (table units)
+  long long out_off;       // float offset of (channel 0, first row, first column of the strip)
+  long long oplane;        // floats per output channel plane
+  int nw, ncols;           // output row pitch; live columns of the strip (<= 128)
+  int pad0, pad1;
+};
+static_assert(sizeof(StripItem) == 64, "StripItem is loaded as four int4");
+
+TD_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+// kVec: every tile row is 16-byte aligned in the output (nw % 4 == 0, out_off % 4 == 0);
+// kBoxW: bytes per staged source row (compile-time so that every shared-memory offset is an immediate);
+// tab_y: per output row {first source row, k0, k1, tap count} (the y tables of tab_min / tab_k, interleaved)
+template <bool kVec, int kBoxW>
+__global__ void __launch_bounds__(32 * kWarpsV6, kMinBlocksV6)
+tile_resize_u8_up_warp_kernel(const __grid_constant__ CUtensorMap tmap, const StripItem* __restrict__ items,
+                              int n_items, const int* __restrict__ tab_min, const int* __restrict__ tab_k,
+                              const int4* __restrict__ tab_y, float* __restrict__ out) {
+  constexpr int box_w = kBoxW;
+  extern __shared__ __align__(128) unsigned char smem_v6[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * kWarpsV6 + warp;
+  if (item >= n_items) return;
+  constexpr int band_bytes = kChunk * box_w;      // one band of one chunk
+  constexpr int stage_bytes = 3 * band_bytes;     // multiple of 128 (box_w is a multiple of 16)
+  unsigned char* ring = smem_v6 + (size_t)warp * 2 * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v6 + (size_t)kWarpsV6 * 2 * stage_bytes) + 2 * warp;
+  float* stage = reinterpret_cast<float*>(smem_v6 + (size_t)kWarpsV6 * (2 * stage_bytes + 16)) + kBX * warp;   // !kVec only
+  const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(bars);
+  const int4* ip = reinterpret_cast<const int4*>(items + item);
+  const int4 i0 = ip[0], i1 = ip[1], i2 = ip[2], i3 = ip[3];
+  const int x_box = i0.x, y_box = i0.y, n_chunks = i0.z, nrows = i0.w;
+  const int xbias = i1.z, row_lo = i1.w;
+  const long long out_off = ((long long)(uint32_t)i2.x) | ((long long)i2.y << 32);
+  const size_t oplane = (size_t)(((long long)(uint32_t)i2.z) | ((long long)i2.w << 32));
+  const int nw = i3.x, ncols = i3.y;
+  const int x4 = 4 * lane;
+  const int4* __restrict__ yrec = tab_y + i1.y;
+  auto request = [&](int chunk) {   // lane 0 only
+    const uint32_t bar = bar_s + 8 * (chunk & 1);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)stage_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(ring_s + (chunk & 1) * stage_bytes), "l"(&tmap), "r"(x_box), "r"(y_box + chunk * kChunk), "r"(0),
+        "r"(bar)
+        : "memory");
+  };
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    request(0);
+  }
+  __syncwarp();
+  // x taps of this lane's 4 columns (byte offsets inside a staged row)
+  XTaps taps;
+  const bool live = x4 < ncols;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    taps.xs[j] = 0; taps.k0[j] = 0; taps.k1[j] = 0;
+    if (x4 + j < ncols) {
+      taps.xs[j] = tab_min[i1.x + x4 + j] + xbias;
+      const int2 kk = *reinterpret_cast<const int2*>(tab_k + (size_t)(i1.x + x4 + j) * kMaxK);
+      taps.k0[j] = kk.x; taps.k1[j] = kk.y;
+    }
+  }
+  float* orow = out + out_off + x4;
+  constexpr int kHalf = 1 << (kPrecisionBits - 1);
+  int E[3][4], O[3][4];      // horizontally filtered source rows of even / odd parity
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { E[c][j] = 0; O[c][j] = 0; }
+  int have = -1;             // last source row (relative to row_lo) already filtered
+  int cur_chunk = -1;
+  // horizontal pass of source row r into one register set
+  auto hpass = [&](int r, int (&dst)[3][4]) {
+    const int chunk = r / kChunk;
+    if (chunk != cur_chunk) {
+      cur_chunk = chunk;
+      __syncwarp();                                   // every lane is done with chunk - 1
+      if (lane == 0 && chunk + 1 < n_chunks) request(chunk + 1);
+      mbar_wait(bar_s + 8 * (chunk & 1), (uint32_t)((chunk >> 1) & 1));
+    }
+    const unsigned char* p = ring + (chunk & 1) * stage_bytes + (r & (kChunk - 1)) * box_w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned char* q = p + (2 - c) * band_bytes;     // output channel c reads band 2 - c (BGR order)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[c][j] = (int)((uint32_t)((int)q[taps.xs[j]] * taps.k0[j] + (int)q[taps.xs[j] + 1] * taps.k1[j] + kHalf) >>
+                          kPrecisionBits);
+    }
+  };
+  int4 rec_n = yrec[0];
+  for (int y = 0; y < nrows; ++y) {
+    const int4 rec = rec_n;
+    if (y + 1 < nrows) rec_n = yrec[y + 1];   // next row's taps are in flight while this row is computed
+    const int ys = rec.x - row_lo;
+    // rec.w = tap count (1 on the last source row of a window: row ys + 1 is then not needed).  Using
+    // all four fields also keeps the register of the in-flight prefetch from being recycled early.
+    const int need = ys + rec.w - 1;
+    while (have < need) {
+      ++have;
+      if (have & 1) hpass(have, O); else hpass(have, E);
+    }
+    const int ke = (ys & 1) ? rec.z : rec.y, ko = (ys & 1) ? rec.y : rec.z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 f;
+      // (acc >> 22) | 0x4B000000 in one funnel shift, minus 2^23: exact int -> float for 0..255; no
+      // clipping needed (2 non-negative taps summing to 2^22 +- 1)
+      f.x = __uint_as_float(__funnelshift_r((uint32_t)(E[c][0] * ke + O[c][0] * ko + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.y = __uint_as_float(__funnelshift_r((uint32_t)(E[c][1] * ke + O[c][1] * ko + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.z = __uint_as_float(__funnelshift_r((uint32_t)(E[c][2] * ke + O[c][2] * ko + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      f.w = __uint_as_float(__funnelshift_r((uint32_t)(E[c][3] * ke + O[c][3] * ko + kHalf), 0x0012C000u, kPrecisionBits)) - 8388608.0f;
+      float* dst = orow + c * oplane;
+      if (kVec) {
+        if (live) __stcs(reinterpret_cast<float4*>(dst), f);
+      } else {
+        // rows of this tile are not 16-byte aligned: transpose the warp's 128 floats through shared
+        // memory so that each of the four scalar stores writes 32 consecutive floats
+        __syncwarp();
+        *reinterpret_cast<float4*>(stage + x4) = f;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int col = lane + 32 * m;
+          if (col < ncols) __stcs(dst - x4 + col, stage[col]);
+        }
+      }
+    }
+    orow += nw;
+  }
+}
+
+// host: tensor map of the (W, H, bands) uint8 raster with a (box_w, box_h, box_bands) box
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-bool make_image_tensor_map(CUtensorMap* map, const void* image, int bands, int H, int W, int box_w, int box_h) {
+bool make_image_tensor_map(CUtensorMap* map, const void* image, int bands, int H, int W, int box_w, int box_h,
+                           int box_bands) {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -509,7 +685,7 @@ bool make_image_tensor_map(CUtensorMap* map, const void* image, int bands, int H
   if (!fn) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)bands};
   const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * (cuuint64_t)H};   // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_bands};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(image), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -595,6 +771,12 @@ struct TilePlan {
   TileDesc* d_td = nullptr;
   int *d_min = nullptr, *d_cnt = nullptr, *d_k = nullptr, *d_max = nullptr;
   int2* d_blk = nullptr;   // per CTA: tile index, (block row << 16) | block column
+  int4* d_y = nullptr;            // per table entry {min, k0, k1, count} (v6 kernel's y taps)
+  StripItem* d_items = nullptr;   // per warp of the v6 kernel: tile, column strip, first row, rows
+  int n_items = 0, n_items_vec = 0;   // the first n_items_vec items belong to tiles with 16-byte aligned rows
+  // the (few) unaligned tiles run on a side stream next to the aligned ones
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // tile_win (T,4) [col_off,row_off,w,h], tile_net (T,2) [net_h,net_w], out_off (T+1): HOST pointers
@@ -676,6 +858,41 @@ extern "C" int td_tile_plan_create(const int* tile_win, const int* tile_net, con
         for (int i = 0; i < td[t].bx; ++i) blk.push_back(make_int2(t, (j << 16) | i));
     }
   }
+  std::vector<StripItem> items;
+  if (rc == TD_OK && elem_size == 1) {
+    int rows_per_item = 20;
+    if (const char* e = getenv("TREEDET_P1_ROWS")) rows_per_item = atoi(e) > 0 ? atoi(e) : rows_per_item;
+    // tiles whose output rows are 16-byte aligned first (128-bit stores), the others after them
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < n_tiles; ++t) {
+        const bool vec = ((td[t].nw & 3) == 0) && ((td[t].out_off & 3) == 0);
+        if (vec != (pass == 0)) continue;
+        const TileDesc& d = td[t];
+        for (int r0 = 0; r0 < d.nh; r0 += rows_per_item)
+          for (int i = 0; i < d.bx; ++i) {
+            StripItem it{};
+            const int ox0 = i * kBX;
+            it.nrows = d.nh - r0 < rows_per_item ? d.nh - r0 : rows_per_item;
+            const int col_lo = tmin[d.xtab + ox0];
+            it.x_box = (d.c_off + col_lo) & ~15;
+            it.xbias = (d.c_off + col_lo) - it.x_box - col_lo;
+            it.row_lo = tmin[d.ytab + r0];
+            it.y_box = d.r_off + it.row_lo;
+            const int n_src = tmin[d.ytab + r0 + it.nrows - 1] + 2 - it.row_lo;   // rows ys and ys + 1 of every row
+            it.n_chunks = (n_src + kChunk - 1) / kChunk;
+            it.xtab = d.xtab + ox0;
+            it.ytab = d.ytab + r0;
+            it.out_off = d.out_off + (long long)r0 * d.nw + ox0;
+            it.oplane = (long long)d.nh * d.nw;
+            it.nw = d.nw;
+            it.ncols = d.nw - ox0 < kBX ? d.nw - ox0 : kBX;
+            items.push_back(it);
+          }
+      }
+      if (pass == 0) P->n_items_vec = (int)items.size();
+    }
+    P->n_items = (int)items.size();
+  }
   auto up = [&](void** dst, const void* src, size_t bytes) {
     if (cudaMalloc(dst, bytes ? bytes : 4) != cudaSuccess) return false;
     return bytes == 0 || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -687,15 +904,27 @@ extern "C" int td_tile_plan_create(const int* tile_win, const int* tile_net, con
       ok = ok && up((void**)&P->d_cnt, tcnt.data(), sizeof(int) * tcnt.size());
       ok = ok && up((void**)&P->d_k, tk.data(), sizeof(int) * tk.size());
       ok = ok && up((void**)&P->d_blk, blk.data(), sizeof(int2) * blk.size());
+      ok = ok && up((void**)&P->d_items, items.data(), sizeof(StripItem) * items.size());
+      std::vector<int4> ty(tmin.size());
+      for (size_t i = 0; i < tmin.size(); ++i) ty[i] = make_int4(tmin[i], tk[i * kMaxK], tk[i * kMaxK + 1], tcnt[i]);
+      ok = ok && up((void**)&P->d_y, ty.data(), sizeof(int4) * ty.size());
     } else {
       ok = ok && (cudaMalloc((void**)&P->d_max, sizeof(int) * n_tiles) == cudaSuccess);
     }
     if (!ok) { td_set_error("td_tile_plan_create: %s", cudaGetErrorString(cudaGetLastError())); rc = TD_ERR_CUDA; }
   }
   if (rc != TD_OK) {
-    cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk);
+    cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk); cudaFree(P->d_items); cudaFree(P->d_y);
     delete P;
     return rc;
+  }
+  if (P->n_items > P->n_items_vec && P->n_items_vec > 0) {
+    if (cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&P->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      P->side = nullptr;   // fall back to two launches on the caller's stream
+    }
   }
   *plan_out = P;
   return TD_OK;
@@ -704,7 +933,10 @@ extern "C" int td_tile_plan_create(const int* tile_win, const int* tile_net, con
 extern "C" int td_tile_plan_destroy(void* plan) {
   if (!plan) return TD_OK;
   TilePlan* P = (TilePlan*)plan;
-  cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk);
+  if (P->ev_fork) cudaEventDestroy(P->ev_fork);
+  if (P->ev_join) cudaEventDestroy(P->ev_join);
+  if (P->side) cudaStreamDestroy(P->side);
+  cudaFree(P->d_td); cudaFree(P->d_min); cudaFree(P->d_cnt); cudaFree(P->d_k); cudaFree(P->d_max); cudaFree(P->d_blk); cudaFree(P->d_items); cudaFree(P->d_y);
   delete P;
   return TD_OK;
 }
@@ -732,7 +964,30 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
       const int box_w = (P->max_cols + 2 + 15 + 15) & ~15;   // + up to 15 bytes of start alignment
       const int region = (box_w * max_rows + 127) & ~127;
       CUtensorMap tmap;
-      if (box_w <= 256 && make_image_tensor_map(&tmap, image, bands, H, W, box_w, max_rows)) {
+      // v6 (warp-autonomous strips): staged row pitch 96 bytes (every 450 -> 800 tile) or 160 (any up-scaling)
+      const int box_v6 = box_w <= 96 ? 96 : 160;
+      if (box_w <= 160 && !getenv("TREEDET_P1_CTA") && make_image_tensor_map(&tmap, image, bands, H, W, box_v6, kChunk, 3)) {
+        const size_t smem_v6 = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
+        const bool fork = P->side && P->n_items_vec > 0 && P->n_items > P->n_items_vec;
+        if (fork) {
+          TD_CUDA(cudaEventRecord(P->ev_fork, st));
+          TD_CUDA(cudaStreamWaitEvent(P->side, P->ev_fork, 0));
+        }
+        for (int pass = 1; pass >= 0; --pass) {
+          const int first = pass == 0 ? 0 : P->n_items_vec;
+          const int count = pass == 0 ? P->n_items_vec : P->n_items - P->n_items_vec;
+          if (count == 0) continue;
+          cudaStream_t st_pass = (fork && pass == 1) ? P->side : st;
+          auto kern = box_v6 == 96 ? (pass == 0 ? tile_resize_u8_up_warp_kernel<true, 96> : tile_resize_u8_up_warp_kernel<false, 96>)
+                                   : (pass == 0 ? tile_resize_u8_up_warp_kernel<true, 160> : tile_resize_u8_up_warp_kernel<false, 160>);
+          if (smem_v6 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v6);
+          kern<<<td_div_up(count, kWarpsV6), 32 * kWarpsV6, smem_v6, st_pass>>>(tmap, P->d_items + first, count, P->d_min,
+                                                                                 P->d_k, P->d_y, out);
+          if (fork && pass == 1) TD_CUDA(cudaEventRecord(P->ev_join, P->side));
+        }
+        if (fork) TD_CUDA(cudaStreamWaitEvent(st, P->ev_join, 0));
+        launched = true;
+      } else if (box_w <= 256 && make_image_tensor_map(&tmap, image, bands, H, W, box_w, max_rows, 1)) {
         const size_t smem_tma = (size_t)3 * region + (size_t)3 * max_rows * kBX + kBX + sizeof(int4) * kBY + 16;
         auto kern = tile_resize_u8_up_tma_kernel;
         if (smem_tma > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
