@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=3000, help="side (px) of the CPU-baseline sample scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--exact", action="store_true",
+                    help="exact-size chain (a host synchronisation before every allocation) instead of the "
+                         "sync-free capacity-buffer chain")
     ap.add_argument("--serial", action="store_true",
                     help="one stream: P1 and the P2-P9 chain back to back (default: P1 on its own stream, "
                          "overlapping the latency-bound chain)")
@@ -246,75 +249,99 @@ def run_b200(a):
                         ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")},
             }
 
+    det_keys = ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")
+    runner = pipeline.ChainRunner(p)           # P2-P9 without host synchronisation (capacity buffers)
+    strip_runner = pipeline.ChainRunner(p)
+    pending = []                               # tickets of enqueued images, collected one step later
+
     def step_strip():
         """halo exchange (NCCL send/recv) + the seam strip through the same path"""
         recv = sharding.exchange_down_halos(tops, rank, world)
         if recv is None or strip is None:
-            return
+            return None
         s_rgbi = sharding.assemble_down_strip(d["rgbi"], recv[0])
         s_ndsm = sharding.assemble_down_strip(d["ndsm"][None], recv[1])[0]
         strip["tables"].plan(s_rgbi).run(s_rgbi, strip["p1"])
         sd = strip["det"]
-        table = pipeline.predict_stage(sd["boxes_net"], sd["scores"], sd["probs"], sd["inst_tile"], sd["tile_dims"],
-                                       strip["tables"].tile_tf, strip["tables"].tile_boxes, p)
-        rasters = pipeline.raster_stage(s_rgbi, strip["tf"], s_ndsm, strip["ndsm_tf"], p)
-        pipeline.postprocess_stage(table, rasters, p)
+        if a.exact:
+            table = pipeline.predict_stage(sd["boxes_net"], sd["scores"], sd["probs"], sd["inst_tile"],
+                                           sd["tile_dims"], strip["tables"].tile_tf, strip["tables"].tile_boxes, p)
+            rasters = pipeline.raster_stage(s_rgbi, strip["tf"], s_ndsm, strip["ndsm_tf"], p)
+            pipeline.postprocess_stage(table, rasters, p)
+            return None
+        return strip_runner.submit({k: sd[k] for k in det_keys}, strip["tables"].tile_tf, strip["tables"].tile_boxes,
+                                   lambda: pipeline.raster_stage(s_rgbi, strip["tf"], s_ndsm, strip["ndsm_tf"], p))
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     p1_ev = []
 
     stage_ev = []
+    results = []
 
     # P1 (HBM bound, feeds the predictor) and the P2-P9 chain (latency bound, consumes the
     # predictor's outputs) are independent: P1 rides its own stream, the chain a high-priority one
     p1_stream = torch.cuda.Stream(device=dev)
     chain_stream = torch.cuda.Stream(device=dev, priority=-1)
 
+    def chain(e):
+        """P2-P9 of the resident image on the current stream; e[2..5] bracket the stages"""
+        e[2].record()
+        if a.exact:
+            table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
+                                           tables.tile_tf, tables.tile_boxes, p)
+            e[3].record()
+            rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
+            e[4].record()
+            feats = pipeline.postprocess_stage(table, rasters, p)
+            e[5].record()
+            results.append((len(table), len(feats)))
+            return None
+        marks = {"p4": e[3], "p5": e[4], "p9": e[5]}
+        return runner.submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
+                             lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p),
+                             mark=lambda name: marks[name].record())
+
     def step_resident():
-        if a.serial:
-            return step_serial()
+        # results of the image enqueued one step ago (the only host wait; the GPU is already busy with
+        # nothing pending only at the very first step)
+        while len(pending) > 1:
+            r, t = pending.pop(0)
+            n_c, f = r.collect(t)
+            if r is runner:
+                results.append((n_c, len(f)))
         main = torch.cuda.current_stream()
-        e = [ev() for _ in range(5)]
-        p1_stream.wait_stream(main)
-        chain_stream.wait_stream(main)
-        with torch.cuda.stream(p1_stream):
+        e = [ev() for _ in range(6)]
+        if a.serial:
             e[0].record()
             tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
             e[1].record()
+            t = chain(e)
+        else:
+            p1_stream.wait_stream(main)
+            chain_stream.wait_stream(main)
+            with torch.cuda.stream(p1_stream):
+                e[0].record()
+                tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+                e[1].record()
+            with torch.cuda.stream(chain_stream):
+                t = chain(e)
+            main.wait_stream(p1_stream)
+            main.wait_stream(chain_stream)
         p1_ev.append((e[0], e[1]))
-        with torch.cuda.stream(chain_stream):
-            s0 = ev(); s0.record()
-            table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
-                                           tables.tile_tf, tables.tile_boxes, p)
-            e[2].record()
-            rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
-            e[3].record()
-            feats = pipeline.postprocess_stage(table, rasters, p)
-            e[4].record()
-        stage_ev.append([e[0], e[1], s0, e[2], e[3], e[4]])
-        main.wait_stream(p1_stream)
-        main.wait_stream(chain_stream)
+        stage_ev.append(e)
+        if t is not None:
+            pending.append((runner, t))
         if world > 1:
-            step_strip()
-        return len(table), len(feats)
+            ts = step_strip()
+            if ts is not None:
+                pending.append((strip_runner, ts))
 
-    def step_serial():
-        e = [ev() for _ in range(5)]
-        e[0].record()
-        tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
-        e[1].record()
-        p1_ev.append((e[0], e[1]))
-        table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
-                                       tables.tile_tf, tables.tile_boxes, p)
-        e[2].record()
-        rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
-        e[3].record()
-        feats = pipeline.postprocess_stage(table, rasters, p)
-        e[4].record()
-        stage_ev.append([e[0], e[1], e[1], e[2], e[3], e[4]])
-        if world > 1:
-            step_strip()
-        return len(table), len(feats)
+    def drain():
+        while pending:
+            r, t = pending.pop(0)
+            n_c, f = r.collect(t)
+            if r is runner:
+                results.append((n_c, len(f)))
 
     def barrier():
         if world > 1:
@@ -339,17 +366,24 @@ def run_b200(a):
 
     for _ in range(a.warmup):
         step_resident()
+    drain()
     p1_ev.clear()
     stage_ev.clear()
+    results.clear()
     sampler = ClockSampler(local)
     if rank == 0 and not a.no_clocks:
         sampler.start()
     l0 = _lib.launch_count
-    ms, (n_cand, n_final) = timed(step_resident, a.steps)
+    ms, _ = timed(step_resident, a.steps)
+    drain()
     launches = _lib.launch_count - l0
+    assert len(results) == a.steps and len(set(results)) == 1, "steps disagree on the crown counts"
+    n_cand, n_final = results[-1]
     p1_ms = statistics.mean(x.elapsed_time(y) for x, y in p1_ev)
     names = ["P1 tile cut/normalise", "P2-P4 paste/contours/stitch", "P5 NDVI/decimation", "P6-P9 NMS/stats/select"]
     pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
+    chain_mode = "exact sizes (host sync before every allocation)" if a.exact else \
+        f"sync-free (capacity buffers, device-side counts; {runner.fallbacks} exact-size fallbacks in the timed region)"
     stage_ms = {n: statistics.mean(e[i].elapsed_time(e[j]) for e in stage_ev) for (i, j), n in zip(pairs, names)}
     area = sc.area_km2
     value = world * area * a.steps / (ms / 1e3)
@@ -427,6 +461,7 @@ def run_b200(a):
                                    f"single model, tile 50 m / buffer 20 m ({n_tiles} tiles, {n_inst} ROI-head "
                                    f"instances replayed from fixtures -> {n_cand} candidate crowns -> {n_final} crowns)",
                        "area_km2_per_gpu": area, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
+                       "chain": chain_mode,
                        "streams": ("one stream, stages back to back" if a.serial else
                                    "P1 on its own stream concurrent with the P2-P9 chain (high-priority stream); "
                                    "stage_ms are per-stream CUDA-event times and overlap"),

@@ -16,6 +16,10 @@
  *  - return value: 0 = ok, <0 = error (TD_ERR_*), text via td_last_error() (thread local);
  *  - ragged polygon rings: `verts` (V,2) float64 interleaved x,y + `ring_off` (R+1) int64;
  *    rings are closed (first vertex repeated at the end);
+ *  - `n_dev` (where present, may be null): DEVICE pointer to the live item count; the by-value
+ *    count is then the capacity the grid is sized for and items >= *n_dev are left untouched.
+ *    This is what lets a whole image run without a host synchronisation (see "Device-side
+ *    bookkeeping" below);
  *  - there is no CPU fallback anywhere in this library.
  */
 #ifndef TREEDET_H_
@@ -111,11 +115,12 @@ int td_trace_emit(const uint32_t* bits, const int* win, const long long* word_of
 int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance, int* scratch,
                       uint32_t* alive, const double* boxes, const int* ring_box, int* out_count,
                       double* out_bounds, double* out_area, unsigned char* out_keep, int bounds_of_input,
-                      void* stream);
+                      const long long* n_dev, void* stream);
 /*   output ring q = input ring sel[q]; dst_off (n_out+1) i64; scratch = the index lists
  *   above (copy kept vertices only) or null (copy whole rings)                           */
 int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
-                  const int* scratch, const long long* dst_off, double* out_verts, void* stream);
+                  const int* scratch, const long long* dst_off, double* out_verts, const long long* n_dev,
+                  void* stream);
 
 /* ---- P5: decimated raster reads + NDVI ----------------------------------------------------
  * Replaces the rasterio reads with out_shape + Resampling.bilinear in process_geojson
@@ -132,6 +137,12 @@ int td_decimate_f32(const float* src, int in_h, int in_w, int out_h, int out_w, 
  * Synchronises the stream once (one 8-byte read back sizes the adjacency).            */
 int td_bbox_nms_ordered(const double* bounds, const double* conf, const double* area, int n,
                         double iou_threshold, double area_threshold, unsigned char* removed, void* stream);
+/*   capacity form (no synchronisation): n = capacity, *n_dev = live count, neighbour lists limited
+ *   to nbr_cap entries; bit 1 of *flag is raised when nbr_cap is too small (removed undefined) and
+ *   nothing is resolved when *flag is already non-zero on entry                                  */
+int td_bbox_nms_ordered_dyn(const double* bounds, const double* conf, const double* area, int n,
+                            const long long* n_dev, double iou_threshold, double area_threshold, long long nbr_cap,
+                            long long* flag, unsigned char* removed, void* stream);
 
 /* ---- P7: per-crown raster statistics, centroids ----------------------------------------------
  * Replaces get_metadata_within_polygon (TreeDetection/postprocessing.py:221-347; mode 0),
@@ -141,14 +152,15 @@ int td_bbox_nms_ordered(const double* bounds, const double* conf, const double* 
  *   max_h (N) f32, hxy (N,2) f32, ndvi_stats (N,4) f32 [min,max,mean,var]; -1 when empty. */
 int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi, const float* height,
                    int rows, int cols, const double* transform6, int mode, float* max_h, float* hxy,
-                   float* ndvi_stats, void* stream);
-int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, void* stream);
+                   float* ndvi_stats, const long long* n_dev, void* stream);
+int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, const long long* n_dev,
+                 void* stream);
 
 /* ---- P8: bbox containment ---------------------------------------------------------------------
  * Replaces process_containment_features (TreeDetection/postprocessing.py:408-476).
  * bounds32 (N,4) f32 -> ratio_max (N) f32, is_contained (N) u8, num_contained (N) i32.  */
 int td_containment(const float* bounds32, int n, double threshold, float* ratio_max, unsigned char* is_contained,
-                   int* num_contained, void* stream);
+                   int* num_contained, const long long* n_dev, void* stream);
 
 /* ---- P9: selection + coordinate rounding ----------------------------------------------------
  * Replaces the pre-selection and containment case analysis of process_features
@@ -159,7 +171,7 @@ int td_containment(const float* bounds32, int n, double threshold, float* ratio_
  *   pre (N) i32: pre-selected flag; out_idx (N) i32: crown emitted by crown i, or -1.    */
 int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats, const double* area,
                      const int* num_contained, const unsigned char* is_contained, int n, const double* params,
-                     int* pre, int* out_idx, void* stream);
+                     int* pre, int* out_idx, const long long* n_dev, void* stream);
 int td_round_coords(const double* in, long long n, double* out, void* stream);
 
 /* ---- P10: forest-outline predicates (two-model fusion, tile flags) -----------------------------
@@ -174,6 +186,25 @@ int td_round_coords(const double* in, long long n, double* out, void* stream);
 int td_forest_predicates(const double* a_verts, const long long* a_off, int n_a, const double* f_verts,
                          const long long* f_off, const double* f_bounds, int n_f, const double* a_filter,
                          unsigned char* out_intersects, unsigned char* out_within, void* stream);
+
+/* ---- Device-side bookkeeping of the sync-free chain ----------------------------------------------
+ * The reference sizes every intermediate through the host (len(), .get(), Python lists, e.g.
+ * TreeDetection/postprocessing.py:389-405, 739-768).  These helpers keep counts on the device.
+ *   td_scan_clamp: sizes (k,n) i64 -> offs (k,n+1) i64 exclusive scans, truncated at the first item
+ *     whose end exceeds caps[r] (HOST array of k capacities) in any row or whose size is negative:
+ *     that item and all later ones become empty, bit 0 of *flag is raised, win_zero (nullable, (n,4)
+ *     i32) gets w = h = 0 for them; totals (k) i64 = offs[r][n].
+ *   td_compact_flags: sel[0..count) = ascending i with flags[i] != 0 (i < n, i < *n_dev), tail 0.
+ *   td_compact_nonneg: out[0..count) = the non-negative values[i] in order, tail 0.
+ *   td_ring_tail: ring_off[i] = *n_verts for *n_rings <= i <= cap_rings, ring_inst tail = 0.        */
+int td_scan_clamp(const long long* sizes, int k, int n, const long long* caps, long long* offs, long long* totals,
+                  long long* flag, int* win_zero, void* stream);
+int td_compact_flags(const unsigned char* flags, int n, const long long* n_dev, long long* sel, long long* count,
+                     void* stream);
+int td_compact_nonneg(const int* values, int n, const long long* n_dev, long long* out, long long* count,
+                      void* stream);
+int td_ring_tail(long long* ring_off, int* ring_inst, int cap_rings, const long long* n_rings,
+                 const long long* n_verts, void* stream);
 
 /* ---- P0a: seam strips ---------------------------------------------------------------------------
  * Replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,

@@ -23,12 +23,18 @@ d = {k: getattr(host, k).to(dev) for k in ("rgbi", "ndsm", "boxes_net", "scores"
 p1_out = torch.empty((tables.p1_floats,), dtype=torch.float32, device=dev)
 
 
+runner = pipeline.ChainRunner(p)
+det = {k: d[k] for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
+last = []
+
+
 def step():
     tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
-    table = pipeline.predict_stage(d["boxes_net"], d["scores"], d["probs"], d["inst_tile"], d["tile_dims"],
-                                   tables.tile_tf, tables.tile_boxes, p)
-    rasters = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
-    return pipeline.postprocess_stage(table, rasters, p)
+    t = runner.submit(det, tables.tile_tf, tables.tile_boxes,
+                      lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p))
+    if last:
+        runner.collect(last.pop())
+    last.append(t)
 
 
 for _ in range(5):

@@ -33,19 +33,20 @@ SIGNATURES = {
     "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
                            _p]),
     # P4 / P9 geometry
-    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
-    "td_take_rings": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
+    "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
+    "td_take_rings": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p]),
     # P5
     "td_ndvi_decimate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "td_decimate_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     # P6 / P8
     "td_bbox_nms_ordered": (_i, [_p, _p, _p, _i, _d, _d, _p, _p]),
-    "td_containment": (_i, [_p, _i, _d, _p, _p, _p, _p]),
+    "td_bbox_nms_ordered_dyn": (_i, [_p, _p, _p, _i, _p, _d, _d, _ll, _p, _p, _p]),
+    "td_containment": (_i, [_p, _i, _d, _p, _p, _p, _p, _p]),
     # P7
-    "td_crown_stats": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p]),
-    "td_centroids": (_i, [_p, _p, _i, _p, _p]),
+    "td_crown_stats": (_i, [_p, _p, _i, _p, _p, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "td_centroids": (_i, [_p, _p, _i, _p, _p, _p]),
     # P9
-    "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "td_round_coords": (_i, [_p, _ll, _p, _p]),
     # P1
     "td_tile_plan_create": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
@@ -53,6 +54,11 @@ SIGNATURES = {
     "td_tile_cut_normalize": (_i, [_p, _p, _i, _p, _p, _p]),
     # P10
     "td_forest_predicates": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p]),
+    # device-side bookkeeping
+    "td_scan_clamp": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "td_compact_flags": (_i, [_p, _i, _p, _p, _p, _p]),
+    "td_compact_nonneg": (_i, [_p, _i, _p, _p, _p, _p]),
+    "td_ring_tail": (_i, [_p, _p, _i, _p, _p, _p]),
     # P0a
     "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
@@ -62,7 +68,8 @@ SIGNATURES = {
 OWN_KERNELS = {
     "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 1,
     "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
-    "td_bbox_nms_ordered": 7, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,
+    "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 2, "td_compact_flags": 1, "td_compact_nonneg": 1,
+    "td_ring_tail": 1, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,
     "td_round_coords": 1, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1,
 }
 launch_count = 0

@@ -22,10 +22,11 @@ __global__ void __launch_bounds__(128)
 simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
                 int* __restrict__ scratch, uint32_t* __restrict__ alive, const double* __restrict__ boxes,
                 const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
-                double* __restrict__ out_area, unsigned char* __restrict__ out_keep, int bounds_of_input) {
+                double* __restrict__ out_area, unsigned char* __restrict__ out_keep, int bounds_of_input,
+                const long long* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= n) return;
+  if (r >= n || (n_dev && r >= *n_dev)) return;
   const long long v0 = ring_off[r];
   const int len = (int)(ring_off[r + 1] - v0);
   const td::P2* pts = reinterpret_cast<const td::P2*>(verts) + v0;
@@ -75,10 +76,11 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
 // the kept vertices are copied, otherwise the whole ring
 __global__ void take_rings_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
                                   const long long* __restrict__ sel, int n_out, const int* __restrict__ scratch,
-                                  const long long* __restrict__ dst_off, double* __restrict__ out_verts) {
+                                  const long long* __restrict__ dst_off, double* __restrict__ out_verts,
+                                  const long long* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= n_out) return;
+  if (q >= n_out || (n_dev && q >= *n_dev)) return;
   const long long r = sel[q];
   const long long v0 = ring_off[r];
   const long long o = dst_off[q];
@@ -94,18 +96,19 @@ __global__ void take_rings_kernel(const double* __restrict__ verts, const long l
 }  // namespace
 
 // scratch: 5 ints per input vertex; alive: (V / 32 + n + 1) uint32.
+// n_dev (nullable, device): live ring count; rings r >= *n_dev are not touched (n_rings is then the capacity).
 // boxes / ring_box / out_bounds / out_area / out_keep may be null.
 extern "C" int td_simplify_rings(const double* verts, const long long* ring_off, int n_rings, double tolerance,
                                  int* scratch, uint32_t* alive, const double* boxes, const int* ring_box,
                                  int* out_count, double* out_bounds, double* out_area, unsigned char* out_keep,
-                                 int bounds_of_input, void* stream) {
+                                 int bounds_of_input, const long long* n_dev, void* stream) {
   TD_ARG(n_rings >= 0);
   if (n_rings == 0) return TD_OK;
   TD_ARG(verts && ring_off && scratch && alive && out_count);
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
   simplify_kernel<<<td_div_up((long long)n_rings * 32, 128), 128, 0, (cudaStream_t)stream>>>(
       verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep,
-      bounds_of_input);
+      bounds_of_input, n_dev);
   TD_CHECK_LAUNCH("td_simplify_rings");
   return TD_OK;
 }
@@ -114,12 +117,13 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
 // (lengths = kept counts when `scratch` holds the index lists of td_simplify_rings, else
 // the source ring lengths).
 extern "C" int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
-                             const int* scratch, const long long* dst_off, double* out_verts, void* stream) {
+                             const int* scratch, const long long* dst_off, double* out_verts,
+                             const long long* n_dev, void* stream) {
   TD_ARG(n_out >= 0);
   if (n_out == 0) return TD_OK;
   TD_ARG(verts && ring_off && sel && dst_off && out_verts);
   take_rings_kernel<<<td_div_up((long long)n_out * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      verts, ring_off, sel, n_out, scratch, dst_off, out_verts);
+      verts, ring_off, sel, n_out, scratch, dst_off, out_verts, n_dev);
   TD_CHECK_LAUNCH("td_take_rings");
   return TD_OK;
 }

@@ -52,8 +52,9 @@ __global__ void grid_init_kernel(GridParams* gp) {
 // bounds f64 (N,4) -> f32 boxes (the reference casts every coordinate with
 // np.float32, postprocessing.py:366) + extent reduction
 __global__ void prep_boxes_kernel(const double* __restrict__ bounds, int n, float4* __restrict__ box32,
-                                  GridParams* gp) {
+                                  GridParams* gp, const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = (int)*n_dev < n ? (int)*n_dev : n;
   float x0 = 0, y0 = 0, w = 0, h = 0;
   bool ok = false;
   if (i < n) {
@@ -107,9 +108,11 @@ TD_D unsigned long long cell_key(int cx, int cy) {
 }
 
 __global__ void cell_keys_kernel(const float4* __restrict__ box32, int n, const GridParams* __restrict__ gp,
-                                 unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+                                 unsigned long long* __restrict__ keys, int* __restrict__ idx,
+                                 const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_dev && i >= *n_dev) { keys[i] = ~0ull; idx[i] = i; return; }   // capacity tail sorts to the end
   const float c = cell_size(gp);
   const Cell ce = cell_of(box32[i].x, box32[i].y, gp, c);
   keys[i] = cell_key(ce.cx, ce.cy);
@@ -132,7 +135,12 @@ struct PairGrid {
   const GridParams* gp;
   int n;
   int all_pairs;  // threshold <= 0: zero-overlap pairs matter, enumerate everything
+  const long long* n_dev;   // nullable: live count on the device (n is then the capacity)
 };
+
+TD_D void live_count(PairGrid& g) {
+  if (g.n_dev) g.n = (int)*g.n_dev < g.n ? (int)*g.n_dev : g.n;
+}
 
 // calls f(j) for every candidate partner j of crown i (j == i included)
 template <typename F>
@@ -179,9 +187,10 @@ TD_D bool nms_connected(const float4& bi, const float4& bj, __half ai, __half aj
 }
 
 __global__ void to_half_kernel(const double* __restrict__ conf, const double* __restrict__ area, int n,
-                               __half* __restrict__ c16, __half* __restrict__ a16) {
+                               __half* __restrict__ c16, __half* __restrict__ a16,
+                               const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || (n_dev && i >= *n_dev)) return;
   c16[i] = __double2half(conf[i]);
   a16[i] = __double2half(area[i]);
 }
@@ -190,9 +199,18 @@ __global__ void to_half_kernel(const double* __restrict__ conf, const double* __
 template <bool kFill>
 __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16, const __half* __restrict__ a16,
                                      float iou_thr, __half area_thr, long long* __restrict__ deg_or_off,
-                                     int* __restrict__ nbr, int* __restrict__ best) {
+                                     int* __restrict__ nbr, int* __restrict__ best, long long nbr_cap,
+                                     long long* __restrict__ flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  live_count(g);
   if (i >= g.n) return;
+  // capacity mode: a neighbour list that does not fit is not written (bit 1 of *flag is raised,
+  // the resolve kernel then does nothing and the caller discards the result)
+  bool fits = true;
+  if (kFill && nbr_cap >= 0 && deg_or_off[i + 1] > nbr_cap) {
+    fits = false;
+    atomicOr((unsigned long long*)flag, 2ull);
+  }
   const float4 bi = g.box32[i];
   const __half ai = a16[i];
   long long cnt = 0;
@@ -208,7 +226,7 @@ __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16,
     if (!nms_connected(bi, g.box32[j], ai, a16[j], iou_thr, area_thr)) return;
     if (j == i) { self_in = true; }
     else {
-      if (kFill) nbr[off + cnt] = j;
+      if (kFill && fits) nbr[off + cnt] = j;
       ++cnt;
     }
     if (kFill) {
@@ -239,8 +257,11 @@ __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16,
 // state: 0 undecided, 1 fires, 2 skipped (was already removed when visited)
 __global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, const int* __restrict__ nbr,
                                    const int* __restrict__ best, volatile int* state, int* pending,
-                                   unsigned char* __restrict__ removed) {
+                                   unsigned char* __restrict__ removed, const long long* __restrict__ n_dev,
+                                   const long long* __restrict__ flag) {
   cg::grid_group grid = cg::this_grid();
+  if (flag && *((const volatile long long*)flag) != 0) return;   // uniform: an earlier stage overflowed
+  if (n_dev) n = (int)*n_dev < n ? (int)*n_dev : n;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
   for (int i = tid; i < n; i += nth) state[i] = 0;
@@ -282,10 +303,12 @@ __global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, con
 }
 
 // ---- P8 ---------------------------------------------------------------------
-__global__ void box32_from_f32_kernel(const float* __restrict__ b, int n, float4* __restrict__ box32, GridParams* gp) {
+__global__ void box32_from_f32_kernel(const float* __restrict__ b, int n, float4* __restrict__ box32, GridParams* gp,
+                                      const long long* __restrict__ n_dev) {
   // containment takes bounds that the reference already holds as float32
   // (cp.array(polygon_bounds, dtype=float32), postprocessing.py:621)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = (int)*n_dev < n ? (int)*n_dev : n;
   float x0 = 0, y0 = 0, w = 0, h = 0;
   bool ok = false;
   if (i < n) {
@@ -313,6 +336,7 @@ __global__ void box32_from_f32_kernel(const float* __restrict__ b, int n, float4
 __global__ void containment_kernel(PairGrid g, float thr, float* __restrict__ ratio_max,
                                    unsigned char* __restrict__ is_contained, int* __restrict__ num_contained) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
+  live_count(g);
   if (t >= g.n) return;
   const float4 bt = g.box32[t];
   const float at = box_area(bt);
@@ -358,14 +382,15 @@ struct Scratch {
   }
 };
 
-int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, unsigned long long** keys_out, int** idx_out) {
+int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, unsigned long long** keys_out, int** idx_out,
+               const long long* n_dev) {
   cudaStream_t st = sc.s;
   auto* keys_a = (unsigned long long*)sc.get(sizeof(unsigned long long) * n);
   auto* keys_b = (unsigned long long*)sc.get(sizeof(unsigned long long) * n);
   int* idx_a = (int*)sc.get(sizeof(int) * n);
   int* idx_b = (int*)sc.get(sizeof(int) * n);
   if (!keys_a || !keys_b || !idx_a || !idx_b) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
-  cell_keys_kernel<<<td_div_up(n, 256), 256, 0, st>>>(box32, n, gp, keys_a, idx_a);
+  cell_keys_kernel<<<td_div_up(n, 256), 256, 0, st>>>(box32, n, gp, keys_a, idx_a, n_dev);
   TD_CHECK_LAUNCH("cell_keys");
   size_t tmp_bytes = 0;
   TD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, st));
@@ -379,9 +404,10 @@ int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, unsigned long 
 
 }  // namespace
 
-extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, const double* area, int n,
-                                   double iou_threshold, double area_threshold, unsigned char* removed,
-                                   void* stream) {
+// nbr_cap < 0: exact mode (one read back sizes the neighbour lists); >= 0: capacity mode, no read back
+static int nms_impl(const double* bounds, const double* conf, const double* area, int n, const long long* n_dev,
+                    double iou_threshold, double area_threshold, long long nbr_cap, long long* flag,
+                    unsigned char* removed, void* stream) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(bounds && conf && area && removed);
@@ -403,22 +429,23 @@ extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, con
   }
   const int blocks = td_div_up(n, 256);
   grid_init_kernel<<<1, 1, 0, st>>>(gp);
-  prep_boxes_kernel<<<blocks, 256, 0, st>>>(bounds, n, box32, gp);
-  to_half_kernel<<<blocks, 256, 0, st>>>(conf, area, n, c16, a16);
+  prep_boxes_kernel<<<blocks, 256, 0, st>>>(bounds, n, box32, gp, n_dev);
+  to_half_kernel<<<blocks, 256, 0, st>>>(conf, area, n, c16, a16, n_dev);
   TD_CHECK_LAUNCH("nms prep");
   PairGrid g;
-  g.box32 = box32; g.gp = gp; g.n = n;
+  g.box32 = box32; g.gp = gp; g.n = n; g.n_dev = n_dev;
   // thresholds are python scalars: compared in the array dtype (float32 / float16)
   const float iou_thr = (float)iou_threshold;
   const __half area_thr = __double2half(area_threshold);
   g.all_pairs = !(iou_thr >= 0.f);
   unsigned long long* keys = nullptr;
   int* idx = nullptr;
-  int rc = build_grid(sc, box32, gp, n, &keys, &idx);
+  int rc = build_grid(sc, box32, gp, n, &keys, &idx, n_dev);
   if (rc != TD_OK) return rc;
   g.keys = keys; g.idx = idx;
   TD_CUDA(cudaMemsetAsync(deg, 0, sizeof(long long) * (n + 1), st));
-  nms_adjacency_kernel<false><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, deg, nullptr, nullptr);
+  nms_adjacency_kernel<false><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, deg, nullptr, nullptr, -1,
+                                                      nullptr);
   TD_CHECK_LAUNCH("nms count");
   size_t tmp_bytes = 0;
   TD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, off, n + 1, st));
@@ -426,12 +453,14 @@ extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, con
   if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
   TD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, off, n + 1, st));
   // the neighbour count is data dependent: one 8-byte read back sizes the CSR array
-  long long total = 0;
-  TD_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  TD_CUDA(cudaStreamSynchronize(st));
+  long long total = nbr_cap;
+  if (nbr_cap < 0) {
+    TD_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+  }
   int* nbr = (int*)sc.get(sizeof(int) * (size_t)(total > 0 ? total : 1));
   if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
-  nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best);
+  nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, nbr_cap, flag);
   TD_CHECK_LAUNCH("nms fill");
   // cooperative fixed-point resolution: one resident wave
   int per_sm = 0;
@@ -444,13 +473,30 @@ extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, con
   const long long* off_c = off;
   const int* nbr_c = nbr;
   const int* best_c = best;
-  void* args[] = {&n_, &off_c, &nbr_c, &best_c, &state, &pending, &removed};
+  const long long* flag_c = flag;
+  void* args[] = {&n_, &off_c, &nbr_c, &best_c, &state, &pending, &removed, &n_dev, &flag_c};
   TD_CUDA(cudaLaunchCooperativeKernel((void*)nms_resolve_kernel, dim3(grid), dim3(256), args, 0, st));
   return TD_OK;
 }
 
+extern "C" int td_bbox_nms_ordered(const double* bounds, const double* conf, const double* area, int n,
+                                   double iou_threshold, double area_threshold, unsigned char* removed,
+                                   void* stream) {
+  return nms_impl(bounds, conf, area, n, nullptr, iou_threshold, area_threshold, -1, nullptr, removed, stream);
+}
+
+// Capacity form of the same operation: n = capacity, *n_dev = live count, neighbour lists limited to
+// nbr_cap entries in total.  No host synchronisation; bit 1 of *flag is raised when nbr_cap was too
+// small (removed[] is then undefined) and nothing is resolved when *flag is already non-zero.
+extern "C" int td_bbox_nms_ordered_dyn(const double* bounds, const double* conf, const double* area, int n,
+                                       const long long* n_dev, double iou_threshold, double area_threshold,
+                                       long long nbr_cap, long long* flag, unsigned char* removed, void* stream) {
+  TD_ARG(n_dev && flag && nbr_cap >= 0);
+  return nms_impl(bounds, conf, area, n, n_dev, iou_threshold, area_threshold, nbr_cap, flag, removed, stream);
+}
+
 extern "C" int td_containment(const float* bounds32, int n, double threshold, float* ratio_max,
-                              unsigned char* is_contained, int* num_contained, void* stream) {
+                              unsigned char* is_contained, int* num_contained, const long long* n_dev, void* stream) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(bounds32 && ratio_max && is_contained && num_contained);
@@ -462,16 +508,16 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   if (!box32 || !gp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
   const int blocks = td_div_up(n, 256);
   grid_init_kernel<<<1, 1, 0, st>>>(gp);
-  box32_from_f32_kernel<<<blocks, 256, 0, st>>>(bounds32, n, box32, gp);
+  box32_from_f32_kernel<<<blocks, 256, 0, st>>>(bounds32, n, box32, gp, n_dev);
   TD_CHECK_LAUNCH("containment prep");
   PairGrid g;
-  g.box32 = box32; g.gp = gp; g.n = n;
+  g.box32 = box32; g.gp = gp; g.n = n; g.n_dev = n_dev;
   // ratio is float32 and the python threshold is compared in float32
   const float thr = (float)threshold;
   g.all_pairs = !(thr > 0.f);
   unsigned long long* keys = nullptr;
   int* idx = nullptr;
-  int rc = build_grid(sc, box32, gp, n, &keys, &idx);
+  int rc = build_grid(sc, box32, gp, n, &keys, &idx, n_dev);
   if (rc != TD_OK) return rc;
   g.keys = keys; g.idx = idx;
   containment_kernel<<<blocks, 256, 0, st>>>(g, thr, ratio_max, is_contained, num_contained);

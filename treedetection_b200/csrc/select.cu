@@ -28,9 +28,11 @@ struct SelectParams {
 __global__ void preselect_kernel(const double* __restrict__ bounds, const float* __restrict__ max_h,
                                  const float* __restrict__ ndvi_stats, int n, SelectParams P,
                                  int* __restrict__ pre, int* __restrict__ first_contained,
-                                 const unsigned char* __restrict__ is_contained) {
+                                 const unsigned char* __restrict__ is_contained,
+                                 const long long* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_dev && i >= *n_dev) { pre[i] = 0; return; }   // capacity tail: keeps the rank scan exact
   bool keep = true;
   const double bx0 = bounds[4 * i], by0 = bounds[4 * i + 1], bx1 = bounds[4 * i + 2], by1 = bounds[4 * i + 3];
   if (P.use_overlap) {
@@ -55,8 +57,9 @@ __global__ void preselect_kernel(const double* __restrict__ bounds, const float*
 __global__ void decide_kernel(const int* __restrict__ pre, const int* __restrict__ rank,
                               const int* __restrict__ num_contained, const float* __restrict__ ndvi_stats,
                               const double* __restrict__ area, const int* __restrict__ first_contained, int n,
-                              int* __restrict__ out_idx) {
+                              int* __restrict__ out_idx, const long long* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = (int)*n_dev < n ? (int)*n_dev : n;
   if (i >= n) return;
   int out = -1;
   if (pre[i]) {
@@ -95,7 +98,8 @@ __global__ void round_coords_kernel(const double* __restrict__ in, long long n, 
 // out_idx[i]: index of the crown emitted at position i of the pre-selected walk, or -1.
 extern "C" int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats,
                                 const double* area, const int* num_contained, const unsigned char* is_contained,
-                                int n, const double* params, int* pre, int* out_idx, void* stream) {
+                                int n, const double* params, int* pre, int* out_idx, const long long* n_dev,
+                                void* stream) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(bounds && max_h && ndvi_stats && area && num_contained && is_contained && params && pre && out_idx);
@@ -114,14 +118,13 @@ extern "C" int td_select_crowns(const double* bounds, const float* max_h, const 
   size_t tmp_bytes = 0;
   TD_CUDA(cudaMallocAsync((void**)&first, sizeof(int), st));
   TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
-  const int big = 0x7fffffff;
-  TD_CUDA(cudaMemcpyAsync(first, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+  TD_CUDA(cudaMemsetAsync(first, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: larger than any index
   const int blocks = td_div_up(n, 256);
-  preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, pre, first, is_contained);
+  preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, pre, first, is_contained, n_dev);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pre, rank, n, st);
   TD_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pre, rank, n, st);
-  decide_kernel<<<blocks, 256, 0, st>>>(pre, rank, num_contained, ndvi_stats, area, first, n, out_idx);
+  decide_kernel<<<blocks, 256, 0, st>>>(pre, rank, num_contained, ndvi_stats, area, first, n, out_idx, n_dev);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(tmp, st);
   cudaFreeAsync(rank, st);

@@ -55,10 +55,11 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
                    const float* __restrict__ ndvi, const float* __restrict__ height, int rows, int cols, Affine6 T,
-                   float* __restrict__ max_h, float* __restrict__ hxy, float* __restrict__ ndvi_stats) {
+                   float* __restrict__ max_h, float* __restrict__ hxy, float* __restrict__ ndvi_stats,
+                   const long long* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int crown = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (crown >= n) return;
+  if (crown >= n || (n_dev && crown >= *n_dev)) return;
   const unsigned full = 0xffffffffu;
 
   // ---- circle from the float32 vertices ------------------------------------
@@ -218,17 +219,19 @@ __device__ float np_pairwise_sum(const RowGetter& a, int lo, int n) {
   return __fadd_rn(np_pairwise_sum(a, lo, n2), np_pairwise_sum(a, lo + n2, n - n2));
 }
 
-__global__ void max_ring_len_kernel(const long long* __restrict__ ring_off, int n, int* __restrict__ vmax) {
+__global__ void max_ring_len_kernel(const long long* __restrict__ ring_off, int n, int* __restrict__ vmax,
+                                    const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int len = (i < n) ? (int)(ring_off[i + 1] - ring_off[i]) : 0;
+  int len = (i < n && !(n_dev && i >= *n_dev)) ? (int)(ring_off[i + 1] - ring_off[i]) : 0;
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
   if ((threadIdx.x & 31) == 0) atomicMax(vmax, len);
 }
 
 __global__ void centroid_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
-                                const int* __restrict__ vmax, float* __restrict__ centroid) {
+                                const int* __restrict__ vmax, float* __restrict__ centroid,
+                                const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || (n_dev && i >= *n_dev)) return;
   const int V = *vmax;
   RowGetter g;
   g.verts = verts; g.v0 = ring_off[i]; g.len = (int)(ring_off[i + 1] - ring_off[i]);
@@ -250,7 +253,7 @@ __global__ void centroid_kernel(const double* __restrict__ verts, const long lon
 
 extern "C" int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi,
                               const float* height, int rows, int cols, const double* transform6, int mode,
-                              float* max_h, float* hxy, float* ndvi_stats, void* stream) {
+                              float* max_h, float* hxy, float* ndvi_stats, const long long* n_dev, void* stream) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(verts && ring_off && transform6 && rows > 0 && cols > 0);
@@ -264,21 +267,22 @@ extern "C" int td_crown_stats(const double* verts, const long long* ring_off, in
   switch (mode) {
     case kCombined:
       crown_stats_kernel<kCombined><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
-                                                                 hxy, ndvi_stats);
+                                                                 hxy, ndvi_stats, n_dev);
       break;
     case kHeightOnly:
       crown_stats_kernel<kHeightOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T,
-                                                                   max_h, hxy, ndvi_stats);
+                                                                   max_h, hxy, ndvi_stats, n_dev);
       break;
     default:
       crown_stats_kernel<kNdviOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
-                                                                 hxy, ndvi_stats);
+                                                                 hxy, ndvi_stats, n_dev);
   }
   TD_CHECK_LAUNCH("td_crown_stats");
   return TD_OK;
 }
 
-extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, void* stream) {
+extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid,
+                            const long long* n_dev, void* stream) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(verts && ring_off && centroid);
@@ -287,8 +291,8 @@ extern "C" int td_centroids(const double* verts, const long long* ring_off, int 
   int* vmax = nullptr;
   TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
   TD_CUDA(cudaMemsetAsync(vmax, 0, sizeof(int), st));
-  max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, n, vmax);
-  centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, n, vmax, centroid);
+  max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, n, vmax, n_dev);
+  centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, n, vmax, centroid, n_dev);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(vmax, st);
   if (e != cudaSuccess) { td_set_error("td_centroids: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }

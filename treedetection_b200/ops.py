@@ -89,8 +89,9 @@ class Rings:
     """Ragged polygon rings on the device: ``verts`` (V,2) f64 CRS coordinates,
     ``ring_off`` (R+1,) i64, ``ring_inst`` (R,) i32 index of the producing instance."""
 
-    def __init__(self, verts, ring_off, ring_inst):
+    def __init__(self, verts, ring_off, ring_inst, n_contours=0, n_points=0):
         self.verts, self.ring_off, self.ring_inst = verts, ring_off, ring_inst
+        self.n_contours, self.n_points = n_contours, n_points   # totals of the border walk (capacity planning)
 
     def __len__(self):
         return self.ring_off.shape[0] - 1
@@ -132,6 +133,35 @@ def trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words=None):
               _ptr(px_off), _ptr(cont_off), _ptr(pts_off), _ptr(ring_base), _ptr(vert_base), _ptr(ct_int),
               _ptr(ct_hole), _ptr(pts), tc, _ptr(inst_tile), _ptr(tile_tf), _ptr(ring_off), ring_inst.data_ptr(),
               verts.data_ptr(), _stream())
+    return Rings(verts, ring_off, ring_inst, tc, tp)
+
+
+def trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag, totals):
+    """Capacity form of :func:`trace_rings` (no synchronisation).  ``caps``: dict with the capacities
+    ``words, px, contours, points, rings, verts``; ``totals`` (4,) i64 device slot receiving the live
+    [contours, points, rings, vertices].  Returns Rings whose arrays have capacity length: ``ring_off``
+    (rings + 2,), ``ring_inst`` (rings + 1,), ``verts`` (verts, 2); rings past the live count are empty."""
+    n = win.shape[0]
+    dev = win.device
+    _chk(tile_tf, torch.float64, "tile_tf")
+    cw, cpx, cc, cp, cr, cv = (int(caps[k]) for k in ("words", "px", "contours", "points", "rings", "verts"))
+    planes = torch.empty((2 * max(cw, 1),), dtype=torch.int32, device=dev)
+    counts = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    _lib.call("td_trace_count", _ptr(bits), _ptr(win), _ptr(word_off), n, cw, _ptr(planes), _ptr(counts), _stream())
+    sizes = counts.t().to(torch.int64).contiguous()
+    offs, _ = scan_clamp(sizes, [cc, cp, cr, cv], flag, totals=totals)
+    labels = torch.empty((max(cpx, 1),), dtype=torch.int16, device=dev)
+    ct_int = torch.empty((6 * max(cc, 1),), dtype=torch.int32, device=dev)
+    ct_hole = torch.empty((max(cc, 1),), dtype=torch.uint8, device=dev)
+    pts = torch.empty((2 * max(cp, 1),), dtype=torch.int16, device=dev)
+    ring_off = torch.empty((cr + 2,), dtype=torch.int64, device=dev)
+    ring_inst = torch.empty((cr + 1,), dtype=torch.int32, device=dev)
+    verts = torch.empty((max(cv, 1), 2), dtype=torch.float64, device=dev)
+    _lib.call("td_trace_emit", _ptr(bits), _ptr(win), _ptr(word_off), n, cw, _ptr(planes), _ptr(labels),
+              _ptr(px_off), _ptr(offs[0]), _ptr(offs[1]), _ptr(offs[2]), _ptr(offs[3]), _ptr(ct_int),
+              _ptr(ct_hole), _ptr(pts), cc, _ptr(inst_tile), _ptr(tile_tf), _ptr(ring_off), _ptr(ring_inst),
+              _ptr(verts), _stream())
+    _lib.call("td_ring_tail", _ptr(ring_off), _ptr(ring_inst), cr + 1, _ptr(totals[2:3]), _ptr(totals[3:4]), _stream())
     return Rings(verts, ring_off, ring_inst)
 
 
@@ -168,7 +198,59 @@ def bbox_nms_ordered(bounds, conf, area, iou_threshold, area_threshold):
     return removed
 
 
-def containment(bounds32, threshold):
+def bbox_nms_ordered_dyn(bounds, conf, area, n_dev, iou_threshold, area_threshold, nbr_cap, flag):
+    """Capacity form of :func:`bbox_nms_ordered` (no synchronisation): rows >= *n_dev are ignored,
+    bit 1 of ``flag`` is raised when ``nbr_cap`` neighbour entries were not enough."""
+    n = bounds.shape[0]
+    _chk(bounds, torch.float64, "bounds"); _chk(conf, torch.float64, "conf"); _chk(area, torch.float64, "area")
+    removed = torch.empty((n,), dtype=torch.uint8, device=bounds.device)
+    _lib.call("td_bbox_nms_ordered_dyn", _ptr(bounds), _ptr(conf), _ptr(area), n, _ptr(n_dev), float(iou_threshold),
+              float(area_threshold), int(nbr_cap), _ptr(flag), _ptr(removed), _stream())
+    return removed
+
+
+# ----------------------------------------------------------------------------
+# device-side bookkeeping (counts stay on the device)
+# ----------------------------------------------------------------------------
+def scan_clamp(sizes, caps, flag, win_zero=None, totals=None):
+    """sizes (k,n) i64 -> (offs (k,n+1) i64, totals (k,) i64 on the device); see td_scan_clamp.
+    ``totals``: optional (k,) i64 device slot to write into."""
+    _chk(sizes, torch.int64, "sizes"); _chk(flag, torch.int64, "flag")
+    k, n = sizes.shape
+    offs = torch.empty((k, n + 1), dtype=torch.int64, device=sizes.device)
+    if totals is None:
+        totals = torch.empty((k,), dtype=torch.int64, device=sizes.device)
+    caps_h = torch.tensor([int(c) for c in caps], dtype=torch.int64)
+    _lib.call("td_scan_clamp", _ptr(sizes), k, n, caps_h.data_ptr(), _ptr(offs), _ptr(totals), _ptr(flag),
+              _ptr(win_zero), _stream())
+    return offs, totals
+
+
+def compact_flags(flags, n_dev=None, count=None):
+    """flags (n,) u8 / bool -> (sel (n,) i64 with a zero tail, count (1,) i64 on the device)."""
+    if flags.dtype == torch.bool:
+        flags = flags.view(torch.uint8)
+    _chk(flags, torch.uint8, "flags")
+    n = flags.shape[0]
+    sel = torch.empty((n,), dtype=torch.int64, device=flags.device)
+    if count is None:
+        count = torch.empty((1,), dtype=torch.int64, device=flags.device)
+    _lib.call("td_compact_flags", _ptr(flags), n, _ptr(n_dev), _ptr(sel), _ptr(count), _stream())
+    return sel, count
+
+
+def compact_nonneg(values, n_dev=None, count=None):
+    """values (n,) i32 -> (the non-negative ones in order (n,) i64 with a zero tail, count (1,) i64)."""
+    _chk(values, torch.int32, "values")
+    n = values.shape[0]
+    out = torch.empty((n,), dtype=torch.int64, device=values.device)
+    if count is None:
+        count = torch.empty((1,), dtype=torch.int64, device=values.device)
+    _lib.call("td_compact_nonneg", _ptr(values), n, _ptr(n_dev), _ptr(out), _ptr(count), _stream())
+    return out, count
+
+
+def containment(bounds32, threshold, n_dev=None):
     """bounds32 (N,4) f32 -> (ratio_max f32, is_contained u8, num_contained i32)."""
     n = bounds32.shape[0]
     _chk(bounds32, torch.float32, "bounds32")
@@ -176,7 +258,8 @@ def containment(bounds32, threshold):
     ratio = torch.empty((n,), dtype=torch.float32, device=dev)
     isc = torch.empty((n,), dtype=torch.uint8, device=dev)
     num = torch.empty((n,), dtype=torch.int32, device=dev)
-    _lib.call("td_containment", _ptr(bounds32), n, float(threshold), _ptr(ratio), _ptr(isc), _ptr(num), _stream())
+    _lib.call("td_containment", _ptr(bounds32), n, float(threshold), _ptr(ratio), _ptr(isc), _ptr(num), _ptr(n_dev),
+              _stream())
     return ratio, isc, num
 
 
@@ -186,7 +269,7 @@ def containment(bounds32, threshold):
 STATS_COMBINED, STATS_HEIGHT_ONLY, STATS_NDVI_ONLY = 0, 1, 2
 
 
-def crown_stats(verts, ring_off, ndvi, height, transform6, mode=STATS_COMBINED):
+def crown_stats(verts, ring_off, ndvi, height, transform6, mode=STATS_COMBINED, n_dev=None):
     """verts (V,2) f64, ring_off (N+1,) i64; rasters (H,W) f32; transform6 = 6 floats
     (a,b,c,d,e,f).  Returns dict of float32 tensors."""
     n = ring_off.shape[0] - 1
@@ -206,14 +289,14 @@ def crown_stats(verts, ring_off, ndvi, height, transform6, mode=STATS_COMBINED):
     _lib.call("td_crown_stats", _ptr(verts), _ptr(ring_off), n,
               _ptr(ndvi) if mode != STATS_HEIGHT_ONLY else None,
               _ptr(height) if mode != STATS_NDVI_ONLY else None,
-              rows, cols, tf.data_ptr(), mode, _ptr(max_h), _ptr(hxy), _ptr(stats), _stream())
+              rows, cols, tf.data_ptr(), mode, _ptr(max_h), _ptr(hxy), _ptr(stats), _ptr(n_dev), _stream())
     return {"max_h": max_h, "hxy": hxy, "ndvi": stats}
 
 
-def centroids(verts, ring_off):
+def centroids(verts, ring_off, n_dev=None):
     n = ring_off.shape[0] - 1
     out = torch.empty((n, 2), dtype=torch.float32, device=verts.device)
-    _lib.call("td_centroids", _ptr(verts), _ptr(ring_off), n, _ptr(out), _stream())
+    _lib.call("td_centroids", _ptr(verts), _ptr(ring_off), n, _ptr(out), _ptr(n_dev), _stream())
     return out
 
 
@@ -221,7 +304,7 @@ def centroids(verts, ring_off):
 # P4 / P9 geometry
 # ----------------------------------------------------------------------------
 def simplify_rings(verts, ring_off, tolerance, boxes=None, ring_box=None, want_bounds=True, want_area=False,
-                   bounds_of_input=False):
+                   bounds_of_input=False, n_dev=None):
     """GEOS-semantics simplify(tol, preserve_topology=True) of every ring.
 
     Returns dict(count i32 (R,), bounds f64 (R,4) of the simplified ring (of the INPUT ring with
@@ -242,7 +325,7 @@ def simplify_rings(verts, ring_off, tolerance, boxes=None, ring_box=None, want_b
         _chk(boxes, torch.float64, "boxes"); _chk(ring_box, torch.int32, "ring_box")
     _lib.call("td_simplify_rings", _ptr(verts), _ptr(ring_off), n, float(tolerance), _ptr(scratch), _ptr(alive),
               _ptr(boxes), _ptr(ring_box), _ptr(count), _ptr(bounds), _ptr(area), _ptr(keep),
-              1 if bounds_of_input else 0, _stream())
+              1 if bounds_of_input else 0, _ptr(n_dev), _stream())
     return {"count": count, "bounds": bounds, "area": area, "keep": keep, "scratch": scratch}
 
 
@@ -259,14 +342,31 @@ def take_rings(verts, ring_off, sel, scratch=None, count=None):
     total = int(dst_off[-1].item())
     out = torch.empty((max(total, 1), 2), dtype=torch.float64, device=dev)[:total]
     _lib.call("td_take_rings", _ptr(verts), _ptr(ring_off), _ptr(sel), sel.shape[0], _ptr(scratch), _ptr(dst_off),
-              out.data_ptr(), _stream())
+              out.data_ptr(), None, _stream())
+    return out, dst_off
+
+
+def take_rings_dyn(verts, ring_off, sel, n_dev, out_cap, scratch=None, count=None):
+    """Capacity form of :func:`take_rings`: ``sel`` has capacity length (tail = 0), ``n_dev`` is the
+    live count on the device, ``out_cap`` bounds the output vertices (the caller knows a bound: the
+    input vertex count).  Returns (verts (out_cap,2), dst_off (cap+1,)); rows / offsets past the live
+    count are undefined.  No synchronisation."""
+    dev = verts.device
+    if count is not None:
+        lens = count.to(torch.int64)[sel]
+    else:
+        lens = (ring_off[1:] - ring_off[:-1])[sel]
+    dst_off = exclusive_offsets(lens)
+    out = torch.empty((max(out_cap, 1), 2), dtype=torch.float64, device=dev)
+    _lib.call("td_take_rings", _ptr(verts), _ptr(ring_off), _ptr(sel), sel.shape[0], _ptr(scratch), _ptr(dst_off),
+              out.data_ptr(), _ptr(n_dev), _stream())
     return out, dst_off
 
 
 # ----------------------------------------------------------------------------
 # P9 selection
 # ----------------------------------------------------------------------------
-def select_crowns(bounds, max_h, ndvi_stats, area, num_contained, is_contained, params):
+def select_crowns(bounds, max_h, ndvi_stats, area, num_contained, is_contained, params, n_dev=None):
     """params: the 14 doubles documented at td_select_crowns.  Returns (pre i32 (N,),
     out_idx i32 (N,)): out_idx[i] = crown emitted by pre-selected crown i, or -1."""
     n = bounds.shape[0]
@@ -278,7 +378,7 @@ def select_crowns(bounds, max_h, ndvi_stats, area, num_contained, is_contained, 
     out_idx = torch.empty((n,), dtype=torch.int32, device=dev)
     p = torch.tensor([float(v) for v in params] + [0.0] * (14 - len(params)), dtype=torch.float64)
     _lib.call("td_select_crowns", _ptr(bounds), _ptr(max_h), _ptr(ndvi_stats), _ptr(area), _ptr(num_contained),
-              _ptr(is_contained), n, p.data_ptr(), _ptr(pre), _ptr(out_idx), _stream())
+              _ptr(is_contained), n, p.data_ptr(), _ptr(pre), _ptr(out_idx), _ptr(n_dev), _stream())
     return pre, out_idx
 
 

@@ -107,8 +107,13 @@ def predict_stage(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_
     total_words = int(word_off[-1].item())
     bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, total_words)
     rings = ops.trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words)
+    return _stitch(rings, scores, inst_tile, tile_boxes, p)
+
+
+def _stitch(rings, scores, inst_tile, tile_boxes, p: PipelineParams):
+    """P4: simplify + tile box filter of the traced rings -> the stitched crown table."""
     n_rings = len(rings)
-    dev = boxes_net.device
+    dev = scores.device
     if n_rings == 0:
         return CrownTable(torch.zeros((0, 2), dtype=torch.float64, device=dev),
                           torch.zeros((1,), dtype=torch.int64, device=dev),
@@ -218,3 +223,200 @@ def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_
     vf = ops.round_coords(vf)
     return Features(vf, of, pid2[final], conf2[final], area2[final], max_h[final], cent[final], isc[final], num[final],
                     extras)
+
+
+# ======================================================================================
+# Sync-free form of the two stages.
+#
+# The exact-size functions above read a size back from the device before every allocation
+# (about ten host synchronisations per image).  The functions below allocate by CAPACITY
+# (remembered from earlier images with the same tiling, see ChainRunner), keep every live
+# count on the device (``n_dev`` arguments of the C-ABI) and record them in one small
+# counter tensor, so an image is enqueued without waiting for the GPU; the counters are
+# read once, when the results are consumed.  Results are bit-identical to the exact-size
+# path; an overflow of any capacity raises bit 0 / 1 of the flag and the image is redone
+# with exact sizes.
+# ======================================================================================
+CTR_FLAG, CTR_WORDS, CTR_PX, CTR_CONT, CTR_PTS, CTR_RINGS, CTR_VERTS = 0, 1, 2, 3, 4, 5, 6
+CTR_NTABLE, CTR_VTABLE, CTR_N1, CTR_N2, CTR_NFINAL, CTR_VFINAL, CTR_SIZE = 7, 8, 9, 10, 11, 12, 16
+
+
+@dataclass
+class DynTable:
+    """Capacity-sized CrownTable: rows / vertices past the live counts are undefined."""
+    verts: torch.Tensor      # (cap_v, 2) f64
+    ring_off: torch.Tensor   # (cap_r + 1,) i64
+    conf: torch.Tensor       # (cap_r,) f64
+    n_dev: torch.Tensor      # (1,) i64 live ring count (a view into the counter tensor)
+
+
+def new_counters(device):
+    return torch.zeros((CTR_SIZE,), dtype=torch.int64, device=device)
+
+
+def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams,
+                      caps: dict, ctr: torch.Tensor) -> DynTable:
+    """P2 + P3 + P4 without host synchronisation (see the section comment)."""
+    flag = ctr[CTR_FLAG:CTR_FLAG + 1]
+    boxes_px, win, nwords = ops.paste_plan(boxes_net, inst_tile, tile_dims)
+    npx = win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64)
+    offs1, _ = ops.scan_clamp(torch.stack([nwords, npx]), [caps["words"], caps["px"]], flag, win_zero=win,
+                              totals=ctr[CTR_WORDS:CTR_PX + 1])
+    word_off, px_off = offs1[0], offs1[1]
+    bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, int(caps["words"]))
+    rings = ops.trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
+                                ctr[CTR_CONT:CTR_VERTS + 1])
+    n_rings = ctr[CTR_RINGS:CTR_RINGS + 1]
+    cap_r = int(caps["rings"])
+    ring_inst = rings.ring_inst[:cap_r].long()
+    ring_tile = inst_tile[ring_inst].contiguous()
+    ring_off = rings.ring_off[:cap_r + 1]
+    simp = ops.simplify_rings(rings.verts, ring_off, p.simplify_tolerance, tile_boxes, ring_tile, want_bounds=False,
+                              n_dev=n_rings)
+    n_table = ctr[CTR_NTABLE:CTR_NTABLE + 1]
+    sel, _ = ops.compact_flags(simp["keep"], n_dev=n_rings, count=n_table)
+    verts, dst_off = ops.take_rings_dyn(rings.verts, ring_off, sel, n_table, int(caps["verts"]), simp["scratch"],
+                                        simp["count"])
+    ctr[CTR_VTABLE:CTR_VTABLE + 1] = dst_off.gather(0, n_table)
+    conf = scores[ring_inst[sel]].to(torch.float64)
+    return DynTable(verts, dst_off, conf, n_table)
+
+
+def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, caps: dict, ctr: torch.Tensor):
+    """P9 head, P6, P7, P8, P9 without host synchronisation.  Returns a capacity-sized Features whose
+    live sizes are ctr[CTR_NFINAL] rings / ctr[CTR_VFINAL] vertices."""
+    dev = table.verts.device
+    cap = table.conf.shape[0]
+    cap_v = table.verts.shape[0]
+    flag = ctr[CTR_FLAG:CTR_FLAG + 1]
+    n0 = table.n_dev
+    valid = torch.arange(cap, device=dev) < n0
+    conf_ok = (table.conf >= p.confidence_threshold) & valid
+    s2 = ops.simplify_rings(table.verts, table.ring_off, 2.0, want_bounds=True, want_area=True, bounds_of_input=True,
+                            n_dev=n0)
+    area_all = s2["area"]
+    pid_all = torch.cumsum(conf_ok.to(torch.int64), 0) - 1
+    n1 = ctr[CTR_N1:CTR_N1 + 1]
+    sel1, _ = ops.compact_flags(conf_ok & (area_all >= p.area_threshold) & (area_all <= 1000), count=n1)
+    verts1, off1 = ops.take_rings_dyn(table.verts, table.ring_off, sel1, n1, cap_v)
+    conf1, area1, pid1 = table.conf[sel1], area_all[sel1].contiguous(), pid_all[sel1]
+    b1 = s2["bounds"][sel1].contiguous()
+    removed = ops.bbox_nms_ordered_dyn(b1, conf1.contiguous(), area1, n1, p.iou_threshold, p.area_threshold,
+                                       int(caps["nbr"]), flag)
+    n2 = ctr[CTR_N2:CTR_N2 + 1]
+    sel2, _ = ops.compact_flags(removed == 0, n_dev=n1, count=n2)
+    verts2, off2 = ops.take_rings_dyn(verts1, off1, sel2, n2, cap_v)
+    conf2, area2, pid2, b2 = conf1[sel2], area1[sel2].contiguous(), pid1[sel2], b1[sel2].contiguous()
+    cent = ops.centroids(verts2, off2, n_dev=n2)
+    combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
+        _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
+    if combined:
+        st = ops.crown_stats(verts2, off2, rasters["ndvi"], rasters["height"], rasters["ndvi_transform"],
+                             ops.STATS_COMBINED, n_dev=n2)
+        max_h, nst = st["max_h"], st["ndvi"]
+    else:
+        sh = ops.crown_stats(verts2, off2, None, rasters["height"], rasters["height_transform"], ops.STATS_HEIGHT_ONLY,
+                             n_dev=n2)
+        sn = ops.crown_stats(verts2, off2, rasters["ndvi"], None, rasters["ndvi_transform"], ops.STATS_NDVI_ONLY,
+                             n_dev=n2)
+        max_h, nst = sh["max_h"], sn["ndvi"]
+    ratio, isc, num = ops.containment(b2.to(torch.float32).contiguous(), p.containment_threshold, n_dev=n2)
+    sp = select_params(p, tuple(rasters["ndvi"].shape), rasters["ndvi_bounds"], rasters["pixel_x"], rasters["pixel_y"])
+    pre, out_idx = ops.select_crowns(b2, max_h, nst, area2, num, isc, sp, n_dev=n2)
+    nf = ctr[CTR_NFINAL:CTR_NFINAL + 1]
+    final, _ = ops.compact_nonneg(out_idx, n_dev=n2, count=nf)
+    vf, of = ops.take_rings_dyn(verts2, off2, final, nf, cap_v)
+    ctr[CTR_VFINAL:CTR_VFINAL + 1] = of.gather(0, nf)
+    vf = ops.round_coords(vf)
+    return Features(vf, of, pid2[final], conf2[final], area2[final], max_h[final], cent[final], isc[final], num[final],
+                    {})
+
+
+def trim_features(f: Features, n: int, v: int) -> Features:
+    """Views of a capacity-sized Features cut to the live sizes (read from the counters)."""
+    return Features(f.verts[:v], f.ring_off[:n + 1], f.poly_id[:n], f.conf[:n], f.area[:n], f.tree_height[:n],
+                    f.centroid[:n], f.is_contained[:n], f.num_contained[:n], f.extras)
+
+
+class ChainRunner:
+    """P2-P9 for a stream of images with the same tiling.  The first image (and any image whose
+    sizes outgrow the remembered capacities) runs through the exact-size path; the others are
+    enqueued without synchronisation.  ``submit`` returns a ticket, ``collect`` turns it into
+    (n_candidates, Features) -- the only point where the host waits for the GPU."""
+
+    GROW = 1.25
+
+    def __init__(self, params: PipelineParams):
+        self.p = params
+        self.caps = None
+        self.nbr_per_crown = 8
+        self.fallbacks = 0
+        self._pinned = []          # recycled pinned read-back buffers (allocating one costs ~0.1 ms)
+
+    def _learn(self, sizes: dict):
+        def cap(v):
+            return int(v * self.GROW) + 1024
+        new = {k: cap(v) for k, v in sizes.items()}
+        if self.caps is None:
+            self.caps = new
+        else:
+            self.caps = {k: max(self.caps[k], new[k]) for k in new}
+        self.caps["nbr"] = self.nbr_per_crown * self.caps["rings"]
+
+    def _exact(self, det, tile_tf, tile_boxes, rasters_fn):
+        """Exact-size path; also measures the sizes the capacities are learnt from."""
+        p = self.p
+        boxes_px, win, nwords = ops.paste_plan(det["boxes_net"], det["inst_tile"], det["tile_dims"])
+        word_off = ops.exclusive_offsets(nwords)
+        total_words = int(word_off[-1].item())
+        px = int((win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64)).sum().item())
+        bits = ops.paste_threshold_pack(boxes_px, win, word_off, det["probs"], p.mask_threshold, total_words)
+        rings = ops.trace_rings(bits, win, word_off, det["inst_tile"], tile_tf, total_words)
+        sizes = {"words": total_words, "px": px, "contours": rings.n_contours, "points": rings.n_points,
+                 "rings": len(rings), "verts": int(rings.verts.shape[0])}
+        self._learn(sizes)
+        table = _stitch(rings, det["scores"], det["inst_tile"], tile_boxes, p)
+        feats = postprocess_stage(table, rasters_fn(), p)
+        return len(table), feats
+
+    def submit(self, det: dict, tile_tf, tile_boxes, rasters_fn, mark=None):
+        """det: dict of device tensors boxes_net, scores, probs, inst_tile, tile_dims;
+        rasters_fn(): the P5 rasters dict (called after P2-P4 are enqueued);
+        mark(name): optional callback at the stage boundaries ("p4", "p5", "p9"), e.g. to record events."""
+        mark = mark or (lambda name: None)
+        if self.caps is None:
+            out = ("done",) + self._exact(det, tile_tf, tile_boxes, rasters_fn)
+            for name in ("p4", "p5", "p9"):
+                mark(name)
+            return out
+        dev = det["boxes_net"].device
+        ctr = new_counters(dev)
+        table = predict_stage_dyn(det["boxes_net"], det["scores"], det["probs"], det["inst_tile"], det["tile_dims"],
+                                  tile_tf, tile_boxes, self.p, self.caps, ctr)
+        mark("p4")
+        rasters = rasters_fn()
+        mark("p5")
+        feats = postprocess_stage_dyn(table, rasters, self.p, self.caps, ctr)
+        mark("p9")
+        host = self._pinned.pop() if self._pinned else torch.empty((CTR_SIZE,), dtype=torch.int64).pin_memory()
+        host.copy_(ctr, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ("dyn", ev, host, feats, (det, tile_tf, tile_boxes, rasters_fn))
+
+    def collect(self, ticket):
+        if ticket[0] == "done":
+            return ticket[1], ticket[2]
+        _, ev, host, feats, again = ticket
+        ev.synchronize()
+        c = host.tolist()
+        self._pinned.append(host)
+        if c[CTR_FLAG] != 0:
+            # some capacity was too small: redo this image with exact sizes (which also re-learns them)
+            self.fallbacks += 1
+            if c[CTR_FLAG] & 2:
+                self.nbr_per_crown *= 2
+            return self._exact(*again)
+        self._learn({"words": c[CTR_WORDS], "px": c[CTR_PX], "contours": c[CTR_CONT], "points": c[CTR_PTS],
+                     "rings": c[CTR_RINGS], "verts": c[CTR_VERTS]})
+        return c[CTR_NTABLE], trim_features(feats, c[CTR_NFINAL], c[CTR_VFINAL])
