@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=10000, help="image side in pixels (0.2 m)")
     ap.add_argument("--ndsm-px", type=float, default=0.2, help="nDSM pixel size (0.2: split stats path, 1.0: combined)")
-    ap.add_argument("--cpu-sample", type=int, default=3000, help="side (px) of the CPU-baseline sample scene")
+    ap.add_argument("--cpu-sample", type=int, default=2500, help="side (px) of the CPU-baseline sample scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--exact", action="store_true",
@@ -56,13 +56,25 @@ def parse():
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference, on a bounded sample of the workload
 # --------------------------------------------------------------------------------------
+_SCENES = {}
+
+
+def _cpu_scene(seed, size_px, ndsm_px):
+    key = (seed, size_px, ndsm_px)
+    if key not in _SCENES:
+        from treedetection_b200 import synth
+        _SCENES[key] = synth.make_scene(seed=seed, size_px=size_px, px=0.2, ndsm_px=ndsm_px, density_per_km2=2500.0)
+    return _SCENES[key]
+
+
 def _cpu_sample_once(args):
-    """One pass of the reference's path (restated, oracle/port.py) over one sample scene."""
+    """One pass of the reference's path (restated, oracle/port.py) over one sample scene.  The scene
+    is synthesised once per process and re-used; only the path is timed."""
     seed, size_px, ndsm_px = args
     import numpy as np
     from oracle import port
-    from treedetection_b200 import geo, pipeline, synth
-    sc = synth.make_scene(seed=seed, size_px=size_px, px=0.2, ndsm_px=ndsm_px, density_per_km2=2500.0)
+    from treedetection_b200 import geo, pipeline
+    sc = _cpu_scene(seed, size_px, ndsm_px)
     p = pipeline.PipelineParams()
     cfg = {k: getattr(p, k) for k in p.__dataclass_fields__}
     t0 = time.perf_counter()
@@ -81,55 +93,64 @@ def _cpu_sample_once(args):
     return dt, sc.area_km2, len(rings), len(out)
 
 
-def cpu_rate(sample_px, ndsm_px, workers, repeats=1):
-    """km^2/s of the CPU restatement: `workers` processes, one sample scene each per repeat
-    (independent images are how the reference parallelises: ThreadPoolExecutor over files)."""
-    import multiprocessing as mp
-    jobs = [(1234 + i, sample_px, ndsm_px) for i in range(workers * repeats)]
-    t0 = time.perf_counter()
-    if workers == 1:
-        res = [_cpu_sample_once(j) for j in jobs]
-    else:
-        with mp.get_context("spawn").Pool(workers) as pool:
-            res = pool.map(_cpu_sample_once, jobs)
-    # scene synthesis happens inside the workers before their clocks start: the timed work
-    # is the path only; concurrent workers finish together, so the slowest one is the wall
+def _summarise(res, workers):
     area = sum(r[1] for r in res)
-    per_round = [max(r[0] for r in res[k * workers:(k + 1) * workers]) for k in range(repeats)]
-    wall = sum(per_round)
-    busy = sum(r[0] for r in res)
-    return {"wall_s": wall, "area_km2": area, "km2_per_s_wall": area / wall,
-            "km2_per_s_core": area / busy, "rings": res[0][2], "crowns": res[0][3],
-            "outer_wall_s": time.perf_counter() - t0}
+    wall = max(r[0] for r in res)        # concurrent workers finish together: the slowest one is the wall
+    return {"wall_s": wall, "area_km2": area, "km2_per_s_wall": area / wall, "rings": res[0][2], "crowns": res[0][3]}
+
+
+def cpu_rate(sample_px, ndsm_px, workers, repeats=1):
+    """km^2/s of the CPU restatement on one sample scene, one process (the cpu_baseline of the b200 arm)."""
+    r = _summarise([_cpu_sample_once((1234, sample_px, ndsm_px))], 1)
+    return r
 
 
 def run_reference(a):
+    """The reference's CPU path (its restatement oracle/port.py: the reference itself needs CuPy,
+    detectron2, rasterio and shapely, none of which exist offline) on all host cores.  A step = every
+    worker process runs the path once over its own copy of a bounded sample scene of the workload
+    (independent images are how the reference parallelises: ThreadPoolExecutor over files).  The sample
+    side is chosen from a first calibration pass so that warmup + steps end within ~2.5 minutes; the
+    reference's statistics are O(crowns x pixels), so its km^2/s falls with the sample size -- the line
+    states the sample it was measured on."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import multiprocessing as mp
     cores = max(1, min(os.cpu_count() or 1, 32))
-    # bounded: one sample per worker per step; per-sample cost ~10-20 s on one core
-    times = []
-    area = 0.0
-    r = None
-    for step in range(a.warmup + a.steps):
-        r = cpu_rate(a.cpu_sample, a.ndsm_px, cores)
-        if step >= a.warmup:
-            times.append(r["wall_s"])
-            area += r["area_km2"]
-        if sum(times) > 240:
-            break
-    steps = max(len(times), 1)
+    total = a.warmup + a.steps
+    budget_s = 150.0
+    with mp.get_context("spawn").Pool(cores) as pool:
+        def one_step(side):
+            return _summarise(pool.map(_cpu_sample_once, [(1234, side, a.ndsm_px)] * cores, chunksize=1), cores)
+        # calibration on a small sample (also pays the imports and page faults of every worker)
+        cal_side = 600
+        one_step(cal_side)
+        t_cal = one_step(cal_side)["wall_s"]
+        side = cal_side
+        for cand in (800, 1000, 1250, 1500, 2000, 2500, 3000):
+            est = t_cal * (cand / cal_side) ** 3.5      # measured growth between 600 and 3000 px
+            if cand <= a.size and est * total <= budget_s:
+                side = cand
+        times, area, r = [], 0.0, None
+        for step in range(total):
+            r = one_step(side)
+            if step >= a.warmup:
+                times.append(r["wall_s"])
+                area += r["area_km2"]
+    steps = len(times)
     value = area / max(sum(times), 1e-9)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "mixed: u8/f32/f64 (CPU)", "data": "synthetic",
         "config": {"workload": f"synthetic {a.size}x{a.size} px RGBI + nDSM orthophoto, single model, tile 50 m / buffer 20 m",
-                   "sample": f"{cores} x ({a.cpu_sample}x{a.cpu_sample} px sub-scene) per step"},
+                   "sample": f"{cores} x ({side}x{side} px sub-scene) per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} processes x one {a.cpu_sample}x{a.cpu_sample} px scene "
-                                   f"({r['rings']} candidate rings each) per step, P1-P9 restated in oracle/port.py"},
+                         "sample": f"{cores} processes x one {side}x{side} px scene ({r['rings']} candidate rings each) "
+                                   f"per step, P1-P9 restated in oracle/port.py; sample side chosen so that "
+                                   f"{total} steps fit {budget_s:.0f} s (the reference's statistics are "
+                                   f"O(crowns x pixels): km^2/s depends on the sample size)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -389,8 +410,9 @@ def run_b200(a):
     value = world * area * a.steps / (ms / 1e3)
 
     # end to end through the host-buffer API
+    e2e_runner = pipeline.ChainRunner(p)
     def step_e2e():
-        out, _ = api.run_image(host, p, dev, tables, p1_out)
+        out, _ = api.run_image(host, p, dev, tables, p1_out, runner=None if a.exact else e2e_runner)
         if world > 1:
             step_strip()
         return out
@@ -442,6 +464,13 @@ def run_b200(a):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = p1_bytes / (p1_ms / 1e3) / 1e9
+        traffic = traffic_src = None
+        try:      # dram bytes per launch from the committed ncu capture of this kernel (profiles/ncu_traffic.py)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "p1_traffic.json")))
+            if a.size == 10000:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         # whole path: SURVEY.md section 8d per-unit algorithmic bytes x the units of this run
         hh, ww = host.rgbi.shape[1:]
         ndvi_px = int(hh * p.ndvi_scaling_factor) * int(ww * p.ndvi_scaling_factor)
@@ -472,7 +501,9 @@ def run_b200(a):
                                        f"strip through the same path" if world > 1 else
                                        "1 GPU; image-row sharding for N > 1")},
             "roofline": {"bound": "hbm", "kernel": "tile_resize_u8_up_tma_kernel (P1)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "write_only_peak": "a pure fill of 12 GiB runs at 7.45 TB/s on this part (scripts/hbm_probe.py); "
+                                            "the kernel writes 12.6 GB and reads 0.4 GB, so frac can approach 1.1",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": p1_bytes, "ms_per_launch": p1_ms,
                          "share_of_step": p1_ms / (ms / a.steps)},

@@ -64,14 +64,30 @@ class TileTables:
         return self._plans[key]
 
 
+_FIELDS = ("verts", "ring_off", "poly_id", "conf", "area", "tree_height", "centroid", "is_contained", "num_contained")
+_pinned = {}
+
+
+def _pinned_like(name, t):
+    """A pinned host buffer of at least t.numel() elements (kept and re-used: allocating pinned
+    memory costs more than the copy it serves)."""
+    buf = _pinned.get(name)
+    if buf is None or buf.dtype != t.dtype or buf.numel() < t.numel():
+        buf = torch.empty((max(int(t.numel() * 1.25), 1024),), dtype=t.dtype).pin_memory()
+        _pinned[name] = buf
+    return buf[:t.numel()].view(t.shape)
+
+
 def features_to_host(f: pipeline.Features):
-    """One device->host transfer of the final crown table."""
-    return {
-        "verts": f.verts.cpu().numpy(), "ring_off": f.ring_off.cpu().numpy(), "poly_id": f.poly_id.cpu().numpy(),
-        "conf": f.conf.cpu().numpy(), "area": f.area.cpu().numpy(), "tree_height": f.tree_height.cpu().numpy(),
-        "centroid": f.centroid.cpu().numpy(), "is_contained": f.is_contained.cpu().numpy(),
-        "num_contained": f.num_contained.cpu().numpy(),
-    }
+    """The final crown table in host memory: asynchronous copies into pinned buffers, one wait."""
+    host = {}
+    for name in _FIELDS:
+        t = getattr(f, name)
+        h = _pinned_like(name, t)
+        h.copy_(t, non_blocking=True)
+        host[name] = h
+    torch.cuda.current_stream().synchronize()
+    return {k: v.numpy().copy() for k, v in host.items()}
 
 
 _copy_streams = {}
@@ -85,13 +101,17 @@ def _copy_stream(device):
 
 
 def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: TileTables = None, p1_out=None,
-              with_p1=True):
+              with_p1=True, runner: pipeline.ChainRunner = None):
     """Host buffers in, final crowns (host numpy) out.  ``p1_out``: optional reusable
     device buffer for the normalised tiles (they feed the predictor, not this path).
+    ``runner``: a :class:`pipeline.ChainRunner` kept across images of the same tiling -- P2-P9 are
+    then enqueued without host synchronisation (capacity buffers); without it every image takes the
+    exact-size path.
 
     The three host->device transfers ride a copy stream in the order the stages need them
-    (ROI-head outputs, RGBI, nDSM) and the compute stream waits on one event per group, so
-    P2-P4 overlap the RGBI copy and P1 / P5 overlap the nDSM copy."""
+    (ROI-head outputs, RGBI, nDSM) and the compute streams wait on one event per group: P2-P4
+    overlap the RGBI copy, P1 (own stream), P5 and the statistics-free part of P6-P9 overlap the
+    nDSM copy; only the per-crown statistics wait for the nDSM."""
     if not torch.cuda.is_available():
         raise _lib.TreedetError("run_image needs a CUDA device (there is no CPU fallback)")
     tables = tables or TileTables(img.tiles, device, params.shift)
@@ -99,25 +119,54 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     cs = _copy_stream(device)
     cs.wait_stream(main)
     with torch.cuda.stream(cs):
-        boxes = img.boxes_net.to(device, non_blocking=True); scores = img.scores.to(device, non_blocking=True)
-        probs = img.probs.to(device, non_blocking=True); inst_tile = img.inst_tile.to(device, non_blocking=True)
-        tile_dims = img.tile_dims.to(device, non_blocking=True)
+        det = {k: getattr(img, k).to(device, non_blocking=True) for k in
+               ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
         ev_det = cs.record_event()
         rgbi = img.rgbi.to(device, non_blocking=True)
         ev_rgbi = cs.record_event()
         ndsm = img.ndsm.to(device, non_blocking=True)
         ev_ndsm = cs.record_event()
-    for t in (boxes, scores, probs, inst_tile, tile_dims, rgbi, ndsm):
+    for t in (*det.values(), rgbi, ndsm):
         t.record_stream(main)
     main.wait_event(ev_det)
-    table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf, tables.tile_boxes, params)
-    main.wait_event(ev_rgbi)
     tiles_out = None
-    if with_p1:
-        tiles_out, _, _ = tables.plan(rgbi).run(rgbi, p1_out)
-    main.wait_event(ev_ndsm)
-    rasters = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
-    feats = pipeline.postprocess_stage(table, rasters, params)
+
+    def rasters_fn():
+        nonlocal tiles_out
+        main.wait_event(ev_rgbi)
+        if with_p1:       # P1 feeds the predictor, nothing downstream here: its own stream
+            ps = _p1_stream(device)
+            ps.wait_event(ev_rgbi)
+            rgbi.record_stream(ps)
+            with torch.cuda.stream(ps):
+                tiles_out, _, _ = tables.plan(rgbi).run(rgbi, p1_out)
+        h, w = ndsm.shape
+        decimated = (int(h * params.height_scaling_factor), int(w * params.height_scaling_factor)) != (h, w)
+        if decimated:
+            main.wait_event(ev_ndsm)
+        r = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
+        r["height_ready"] = None if decimated else ev_ndsm
+        return r
+
+    if runner is None:
+        table = pipeline.predict_stage(det["boxes_net"], det["scores"], det["probs"], det["inst_tile"],
+                                       det["tile_dims"], tables.tile_tf, tables.tile_boxes, params)
+        feats = pipeline.postprocess_stage(table, rasters_fn(), params)
+        n_cand = len(table)
+    else:
+        n_cand, feats = runner.collect(runner.submit(det, tables.tile_tf, tables.tile_boxes, rasters_fn))
     host = features_to_host(feats)
-    host["n_candidates"] = len(table)
+    host["n_candidates"] = n_cand
+    if with_p1:
+        main.wait_stream(_p1_stream(device))
     return host, tiles_out
+
+
+_p1_streams = {}
+
+
+def _p1_stream(device):
+    key = torch.device(device).index
+    if key not in _p1_streams:
+        _p1_streams[key] = torch.cuda.Stream(device=device)
+    return _p1_streams[key]
