@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2500, help="side (px) of the CPU-baseline sample scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
+    ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
     ap.add_argument("--exact", action="store_true",
                     help="exact-size chain (a host synchronisation before every allocation) instead of the "
                          "sync-free capacity-buffer chain")
@@ -303,6 +304,7 @@ def run_b200(a):
     # predictor's outputs) are independent: P1 rides its own stream, the chain a high-priority one
     p1_stream = torch.cuda.Stream(device=dev)
     chain_stream = torch.cuda.Stream(device=dev, priority=-1)
+    strip_stream = torch.cuda.Stream(device=dev, priority=-1)   # N > 1: the seam strip, next to the image
 
     def chain(e):
         """P2-P9 of the resident image on the current stream; e[2..5] bracket the stages"""
@@ -332,30 +334,34 @@ def run_b200(a):
                 results.append((n_c, len(f)))
         main = torch.cuda.current_stream()
         e = [ev() for _ in range(6)]
+        ts = None
         if a.serial:
             e[0].record()
             tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
             e[1].record()
             t = chain(e)
+            if world > 1:
+                ts = step_strip()
         else:
-            p1_stream.wait_stream(main)
-            chain_stream.wait_stream(main)
+            for st in (p1_stream, chain_stream, strip_stream):
+                st.wait_stream(main)
             with torch.cuda.stream(p1_stream):
                 e[0].record()
                 tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
                 e[1].record()
             with torch.cuda.stream(chain_stream):
                 t = chain(e)
-            main.wait_stream(p1_stream)
-            main.wait_stream(chain_stream)
+            if world > 1:
+                with torch.cuda.stream(strip_stream):
+                    ts = step_strip()
+            for st in (p1_stream, chain_stream, strip_stream):
+                main.wait_stream(st)
         p1_ev.append((e[0], e[1]))
         stage_ev.append(e)
         if t is not None:
             pending.append((runner, t))
-        if world > 1:
-            ts = step_strip()
-            if ts is not None:
-                pending.append((strip_runner, ts))
+        if ts is not None:
+            pending.append((strip_runner, ts))
 
     def drain():
         while pending:
@@ -426,7 +432,7 @@ def run_b200(a):
 
     # ---- secondary metric of BASELINE.json: crowns merged/s (config 4, dense-forest stress) ----
     merged = None
-    if rank == 0:
+    if rank == 0 and not a.no_merged:
         rng = np.random.default_rng(4)
         n_c = 800_000                                   # ~2,000 crowns per 50 m tile over 400 tiles (1 km^2)
         cx = synth.ORIGIN_X + rng.uniform(0, 1000.0, n_c); cy = synth.ORIGIN_Y + rng.uniform(0, 1000.0, n_c)

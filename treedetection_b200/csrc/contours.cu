@@ -12,13 +12,36 @@
 // Two passes because output sizes are data dependent: td_trace_count returns, per
 // instance, the number of borders / points / kept rings / ring vertices; after a scan
 // (caller side) td_trace_emit re-walks and writes rings in OpenCV's order.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "contour_core.cuh"
 #include "contour_lockstep.cuh"
 
 namespace {
 
-constexpr int kSmemPerWarp = 32 * 1024;   // bit planes of the 32 windows a warp walks
+constexpr int kSmemPerWarpDefault = 32 * 1024;   // bit planes of the 32 windows a warp walks
+
+// Shared memory per warp (= per CTA).  The walk is latency bound, so what counts is that ALL warps of
+// the launch are resident at once (one wave): the budget shrinks from 32 KB as far as needed for
+// ceil(warps / SMs) CTAs to fit the 227 KB of an SM, but not below 16 KB (windows that do not fit
+// use the global scratch planes, which costs more than a second wave).
+int smem_per_warp(int n_inst) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("TREEDET_TRACE_SMEM");
+    forced = e && atoi(e) > 0 ? atoi(e) : 0;
+  }
+  if (forced) return forced;
+  const int warps = td_div_up(n_inst, 32);
+  const int per_sm = td_div_up(warps, td_num_sms());
+  int v = kSmemPerWarpDefault;
+  if (per_sm > 0) {
+    const int fit = ((227 * 1024) / per_sm - 1024) & ~1023;      // 1 KB per CTA is reserved by the system
+    if (fit < v) v = fit < 16 * 1024 ? kSmemPerWarpDefault : fit;
+  }
+  return v;
+}
 
 // Border following is sequential per instance and issue bound, so the 32 lanes of a warp each
 // walk their OWN instance window in lock step (contour_lockstep.cuh: a per-lane state machine,
@@ -29,7 +52,8 @@ constexpr int kSmemPerWarp = 32 * 1024;   // bit planes of the 32 windows a warp
 template <typename LabelT>
 __device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_t* __restrict__ bits,
                               const int* __restrict__ win, const long long* __restrict__ word_off, int i,
-                              uint32_t* __restrict__ planes, long long total_words, unsigned char* smem) {
+                              uint32_t* __restrict__ planes, long long total_words, unsigned char* smem,
+                              int smem_bytes) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   R.w = active ? win[4 * i + 2] : 0;
@@ -46,7 +70,7 @@ __device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_
     if (lane >= o) incl += v;
   }
   const int off = incl - need;
-  const bool in_smem = nwords > 0 && incl <= kSmemPerWarp;
+  const bool in_smem = nwords > 0 && incl <= smem_bytes;
   uint32_t* s_fg = reinterpret_cast<uint32_t*>(smem + off);
   // cooperative copy: all lanes copy window j's words (coalesced), then clear its scratch planes
   for (int j = 0; j < 32; ++j) {
@@ -76,12 +100,13 @@ __device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_
 
 __global__ void __launch_bounds__(32)
 trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ win, const long long* __restrict__ word_off,
-                   int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts) {
+                   int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts,
+                   int smem_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const bool active = i < n;
   td::LaneState<unsigned short> S;
-  stage_windows(S.R, active, bits, win, word_off, i, planes, total_words, smem);
+  stage_windows(S.R, active, bits, win, word_off, i, planes, total_words, smem, smem_bytes);
   td::lane_init(S, nullptr);
   while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
   if (active) {
@@ -116,6 +141,7 @@ struct EmitArgs {
   long long* ring_off;         // (R + 1)  [R written by the caller]
   int* ring_inst;              // (R)
   double* verts;               // (V, 2)
+  int smem_bytes;
 };
 
 __global__ void __launch_bounds__(32) trace_emit_kernel(EmitArgs A) {
@@ -123,7 +149,7 @@ __global__ void __launch_bounds__(32) trace_emit_kernel(EmitArgs A) {
   const int i = blockIdx.x * 32 + threadIdx.x;
   const bool active = i < A.n;
   td::LaneState<unsigned short> S;
-  stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem);
+  stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem, A.smem_bytes);
   const long long c0 = active ? A.cont_off[i] : 0;
   const int nc = active ? (int)(A.cont_off[i + 1] - c0) : 0;
   td::ContourOut out;
@@ -177,7 +203,9 @@ extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long l
   TD_ARG(bits && win && word_off && planes && counts);
   cudaStream_t st = (cudaStream_t)stream;
   TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
-  trace_count_kernel<<<td_div_up(n_inst, 32), 32, kSmemPerWarp, st>>>(bits, win, word_off, n_inst, planes, total_words, counts);
+  const int smem_bytes = smem_per_warp(n_inst);
+  trace_count_kernel<<<td_div_up(n_inst, 32), 32, smem_bytes, st>>>(bits, win, word_off, n_inst, planes, total_words, counts,
+                                                                  smem_bytes);
   TD_CHECK_LAUNCH("td_trace_count");
   return TD_OK;
 }
@@ -206,7 +234,8 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   A.ct_scratch = ct_int5 + 3 * total_contours;
   A.ct_hole = ct_hole; A.pts = pts; A.inst_tile = inst_tile; A.tile_tf = tile_tf;
   A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
-  trace_emit_kernel<<<td_div_up(n_inst, 32), 32, kSmemPerWarp, st>>>(A);
+  A.smem_bytes = smem_per_warp(n_inst);
+  trace_emit_kernel<<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
   return TD_OK;
 }

@@ -967,7 +967,8 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
       // v6 (warp-autonomous strips): staged row pitch 96 bytes (every 450 -> 800 tile) or 160 (any up-scaling)
       const int box_v6 = box_w <= 96 ? 96 : 160;
       if (box_w <= 160 && !getenv("TREEDET_P1_CTA") && make_image_tensor_map(&tmap, image, bands, H, W, box_v6, kChunk, 3)) {
-        const size_t smem_v6 = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
+        size_t smem_v6 = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
+        if (const char* e = getenv("TREEDET_P1_SMEM_PAD")) smem_v6 += (size_t)atoi(e);   // experiment: fewer CTAs per SM
         const bool fork = P->side && P->n_items_vec > 0 && P->n_items > P->n_items_vec;
         if (fork) {
           TD_CUDA(cudaEventRecord(P->ev_fork, st));
