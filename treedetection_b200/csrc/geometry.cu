@@ -11,6 +11,8 @@
 // One warp simplifies one ring: the algorithm is a sequential stack machine (run redundantly by
 // all lanes) whose inner scans are split over the lanes; there are ~10^5 rings per image.  Results are index lists into the input ring, so a second tiny
 // kernel (td_take_rings) gathers the surviving vertices once the caller has scanned the counts.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "simplify_core.cuh"
 
@@ -106,7 +108,9 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
   if (n_rings == 0) return TD_OK;
   TD_ARG(verts && ring_off && scratch && alive && out_count);
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
-  simplify_kernel<<<td_div_up((long long)n_rings * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+  static int bs = 0;
+  if (bs == 0) { const char* e = getenv("TREEDET_SIMPLIFY_BLOCK"); bs = e && atoi(e) > 0 ? atoi(e) : 64; }
+  simplify_kernel<<<td_div_up((long long)n_rings * 32, bs), bs, 0, (cudaStream_t)stream>>>(
       verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep,
       bounds_of_input, n_dev);
   TD_CHECK_LAUNCH("td_simplify_rings");
