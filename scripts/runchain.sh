@@ -1,4 +1,5 @@
-for bs in 128 64 32; do
-echo "block $bs"; TREEDET_SIMPLIFY_BLOCK=$bs timeout 300 python bench.py --no-cpu-baseline --no-clocks --no-merged --steps 30 --serial 2>&1 | tail -1 > gpurun_out/b.json; python -c "
-import json; d=json.load(open('gpurun_out/b.json')); print(d['value'], d['ms_per_step'], d['config']['stage_ms'])"
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python bench.py --no-cpu-baseline --no-clocks --steps 30 --serial 2>&1 | tail -1 > gpurun_out/b.json; python -c "
+import json; d=json.load(open('gpurun_out/b.json')); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['crowns_merged']['value'])"
+timeout 300 python bench.py --no-cpu-baseline --no-clocks --no-merged --steps 30 2>&1 | tail -1 > gpurun_out/b.json; python -c "
+import json; d=json.load(open('gpurun_out/b.json')); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['roofline']['frac'], d['roofline']['ms_per_launch'])"

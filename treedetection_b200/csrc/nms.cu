@@ -31,6 +31,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+typedef unsigned int KeyT;   // sort key of a grid cell
+
 struct GridParams {
   int minx_enc, miny_enc;  // order-preserving int encodings (atomicMin/Max)
   int maxw_enc, maxh_enc;
@@ -103,23 +105,25 @@ TD_D Cell cell_of(float x0, float y0, const GridParams* gp, float c) {
   return r;
 }
 
-TD_D unsigned long long cell_key(int cx, int cy) {
-  return ((unsigned long long)(unsigned)cy << 32) | (unsigned long long)(unsigned)cx;
+// 16 bits per axis: cells beyond 65535 alias into the last one, which only adds candidates (every
+// pair is tested exactly); a 32-bit key halves the radix-sort passes
+TD_D unsigned int cell_key(int cx, int cy) {
+  return ((unsigned)min(cy, 65535) << 16) | (unsigned)min(cx, 65535);
 }
 
 __global__ void cell_keys_kernel(const float4* __restrict__ box32, int n, const GridParams* __restrict__ gp,
-                                 unsigned long long* __restrict__ keys, int* __restrict__ idx,
+                                 KeyT* __restrict__ keys, int* __restrict__ idx,
                                  const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (n_dev && i >= *n_dev) { keys[i] = ~0ull; idx[i] = i; return; }   // capacity tail sorts to the end
+  if (n_dev && i >= *n_dev) { keys[i] = ~(KeyT)0; idx[i] = i; return; }   // capacity tail sorts to the end
   const float c = cell_size(gp);
   const Cell ce = cell_of(box32[i].x, box32[i].y, gp, c);
   keys[i] = cell_key(ce.cx, ce.cy);
   idx[i] = i;
 }
 
-TD_D int lower_bound_key(const unsigned long long* __restrict__ keys, int n, unsigned long long k) {
+TD_D int lower_bound_key(const KeyT* __restrict__ keys, int n, KeyT k) {
   int lo = 0, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -130,7 +134,7 @@ TD_D int lower_bound_key(const unsigned long long* __restrict__ keys, int n, uns
 
 struct PairGrid {
   const float4* box32;
-  const unsigned long long* keys;  // sorted
+  const KeyT* keys;  // sorted
   const int* idx;                  // sorted order -> crown index
   const GridParams* gp;
   int n;
@@ -157,7 +161,7 @@ TD_D void for_each_candidate(const PairGrid& g, int i, F f) {
     const int cx_lo = max(ce.cx - 1, 0);
     const long long cx_hi = (long long)ce.cx + 1;
     const int s = lower_bound_key(g.keys, g.n, cell_key(cx_lo, (int)cy));
-    const unsigned long long kend = cell_key((int)cx_hi, (int)cy);
+    const KeyT kend = cell_key((int)cx_hi, (int)cy);
     for (int p = s; p < g.n && g.keys[p] <= kend; ++p) f(g.idx[p]);
   }
 }
@@ -382,21 +386,21 @@ struct Scratch {
   }
 };
 
-int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, unsigned long long** keys_out, int** idx_out,
+int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, KeyT** keys_out, int** idx_out,
                const long long* n_dev) {
   cudaStream_t st = sc.s;
-  auto* keys_a = (unsigned long long*)sc.get(sizeof(unsigned long long) * n);
-  auto* keys_b = (unsigned long long*)sc.get(sizeof(unsigned long long) * n);
+  auto* keys_a = (KeyT*)sc.get(sizeof(KeyT) * n);
+  auto* keys_b = (KeyT*)sc.get(sizeof(KeyT) * n);
   int* idx_a = (int*)sc.get(sizeof(int) * n);
   int* idx_b = (int*)sc.get(sizeof(int) * n);
   if (!keys_a || !keys_b || !idx_a || !idx_b) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
   cell_keys_kernel<<<td_div_up(n, 256), 256, 0, st>>>(box32, n, gp, keys_a, idx_a, n_dev);
   TD_CHECK_LAUNCH("cell_keys");
   size_t tmp_bytes = 0;
-  TD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, st));
+  TD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 32, st));
   void* tmp = sc.get(tmp_bytes);
   if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
-  TD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, st));
+  TD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 32, st));
   *keys_out = keys_b;
   *idx_out = idx_b;
   return TD_OK;
@@ -438,7 +442,7 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
   const float iou_thr = (float)iou_threshold;
   const __half area_thr = __double2half(area_threshold);
   g.all_pairs = !(iou_thr >= 0.f);
-  unsigned long long* keys = nullptr;
+  KeyT* keys = nullptr;
   int* idx = nullptr;
   int rc = build_grid(sc, box32, gp, n, &keys, &idx, n_dev);
   if (rc != TD_OK) return rc;
@@ -515,7 +519,7 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   // ratio is float32 and the python threshold is compared in float32
   const float thr = (float)threshold;
   g.all_pairs = !(thr > 0.f);
-  unsigned long long* keys = nullptr;
+  KeyT* keys = nullptr;
   int* idx = nullptr;
   int rc = build_grid(sc, box32, gp, n, &keys, &idx, n_dev);
   if (rc != TD_OK) return rc;

@@ -113,25 +113,47 @@ TD_D float sample(const float (*tab)[kPad], const Tap& tx, const Tap& ty) {
 // ---------------------------------------------------------------------------
 // paste + threshold + pack: one CTA per instance, one warp per 32-pixel word
 // ---------------------------------------------------------------------------
+// The sampling grid is separable: the tap of a pixel column depends on x only, that of a row on y
+// only.  Both tap tables are built once per instance in shared memory (w + h divisions instead of
+// 2 * w * h); windows wider / higher than kTapCap (rare: crowns are tens of pixels across) compute
+// the missing taps on the fly.  Same operations on the same values -> same bits.
+constexpr int kTapCap = 160;
+
+struct PackedTap {
+  int idx;    // i0 | i1 << 8
+  float w1;
+};
+
+TD_D PackedTap pack_tap(const Tap& t) { return PackedTap{t.i0 | (t.i1 << 8), t.w1}; }
+TD_D Tap unpack_tap(const PackedTap& p) {
+  Tap t;
+  t.i0 = p.idx & 0xff; t.i1 = p.idx >> 8;
+  t.w1 = p.w1; t.w0 = __fsub_rn(1.f, p.w1);
+  return t;
+}
+
 __global__ void __launch_bounds__(kPasteThreads)
 paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ win,
                   const long long* __restrict__ word_off, const float* __restrict__ probs, int n, float thr,
                   uint32_t* __restrict__ bits) {
   __shared__ float tab[kPad][kPad];
+  __shared__ PackedTap s_tx[kTapCap], s_ty[kTapCap];
   const int i = blockIdx.x;
   if (i >= n) return;
   const int ww = win[4 * i + 2], wh = win[4 * i + 3];
   if (ww <= 0 || wh <= 0) return;
   const int wx0 = win[4 * i + 0], wy0 = win[4 * i + 1];
+  const float bx0 = boxes_px[4 * i + 0], by0 = boxes_px[4 * i + 1];
+  const float bx1 = boxes_px[4 * i + 2], by1 = boxes_px[4 * i + 3];
   for (int k = threadIdx.x; k < kPad * kPad; k += kPasteThreads) {
     const int r = k / kPad, c = k % kPad;
     float v = 0.f;
     if (r >= 1 && r <= kM && c >= 1 && c <= kM) v = probs[(size_t)i * kM * kM + (r - 1) * kM + (c - 1)];
     tab[r][c] = v;
   }
+  for (int k = threadIdx.x; k < min(ww, kTapCap); k += kPasteThreads) s_tx[k] = pack_tap(make_tap(wx0 + k, bx0, bx1));
+  for (int k = threadIdx.x; k < min(wh, kTapCap); k += kPasteThreads) s_ty[k] = pack_tap(make_tap(wy0 + k, by0, by1));
   __syncthreads();
-  const float bx0 = boxes_px[4 * i + 0], by0 = boxes_px[4 * i + 1];
-  const float bx1 = boxes_px[4 * i + 2], by1 = boxes_px[4 * i + 3];
   const int wpr = (ww + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* out = bits + word_off[i];
@@ -141,8 +163,8 @@ paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ wi
     const int x = wi * 32 + lane;
     bool on = false;
     if (x < ww) {
-      const Tap tx = make_tap(wx0 + x, bx0, bx1);
-      const Tap ty = make_tap(wy0 + y, by0, by1);
+      const Tap tx = x < kTapCap ? unpack_tap(s_tx[x]) : make_tap(wx0 + x, bx0, bx1);
+      const Tap ty = y < kTapCap ? unpack_tap(s_ty[y]) : make_tap(wy0 + y, by0, by1);
       on = sample(tab, tx, ty) >= thr;
     }
     const uint32_t word = __ballot_sync(0xffffffffu, on);
