@@ -214,6 +214,12 @@ int td_ring_tail(long long* ring_off, int* ring_inst, int cap_rings, const long 
 int td_seam_crop(const void* a, const void* b, int elem_size, int bands, int ha, int wa, int hb, int wb, int axis,
                  int strip_w, int strip_h, void* out, void* stream);
 
+/* ---- N1: GeoTIFF LZW codec (HOST function, host pointers) ------------------------------------------
+ * Replaces the GDAL LZW decoder behind rasterio.open(...).read (TreeDetection/prediction.py:61,
+ * postprocessing.py:781-800, merging.py:56-75).  One call decodes one strip / tile (TIFF 6.0
+ * section 13); returns the bytes written to dst (<= cap) or a negative TD_ERR_* code.            */
+long long td_tiff_lzw_decode(const unsigned char* src, long long n_src, unsigned char* dst, long long cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ def header_decls():
     text = open(os.path.join(ROOT, "include", "treedet.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(int|const char\*)\s+(td_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(int|long long|const char\*)\s+(td_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(3).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         decls[m.group(2)] = n

@@ -1,0 +1,79 @@
+"""N1: the GeoTIFF reader against PIL / libtiff on compressed files -- LZW and deflate,
+predictors 1 / 2 / 3, strips and tiles, uint8 / uint16 / float32 (the rasters the reference reads with
+rasterio: prediction.py:61, postprocessing.py:781-800).  No GPU needed: td_tiff_lzw_decode is a host
+function of libtreedet."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from treedetection_b200 import _lib, geotiff
+
+
+def _save(path, arr, compression, predictor=None, tile=None):
+    if arr.ndim == 3:
+        img = Image.fromarray(np.ascontiguousarray(arr.transpose(1, 2, 0)))
+    else:
+        img = Image.fromarray(arr)
+    info = {}
+    if predictor:
+        info[317] = predictor
+    kw = {"compression": compression, "tiffinfo": info}
+    if tile:
+        kw["tiffinfo"] = {**info, 322: tile, 323: tile}
+    img.save(path, format="TIFF", **kw)
+
+
+def _cases():
+    rng = np.random.default_rng(0)
+    smooth = (np.add.outer(np.arange(300), np.arange(517)) % 251).astype(np.uint8)
+    rgba = np.stack([smooth, smooth[::-1], (smooth // 3), rng.integers(0, 255, smooth.shape).astype(np.uint8)])
+    f32 = (np.sin(np.arange(300)[:, None] / 17.0) * 20 + rng.normal(0, 0.1, (300, 517))).astype(np.float32)
+    u16 = (np.add.outer(np.arange(300), np.arange(517)) * 37 % 60000).astype(np.uint16)
+    return {"rgba": rgba, "f32": f32, "u16": u16, "noise": rng.integers(0, 256, (64, 4000)).astype(np.uint8)}
+
+
+@pytest.mark.parametrize("name", ["rgba", "f32", "u16", "noise"])
+@pytest.mark.parametrize("compression,predictor", [("tiff_lzw", None), ("tiff_lzw", 2), ("tiff_adobe_deflate", None),
+                                                   ("tiff_adobe_deflate", 2), ("tiff_lzw", 3)])
+def test_reader_matches_pil(tmp_path, name, compression, predictor):
+    arr = _cases()[name]
+    if predictor == 3 and arr.dtype != np.float32:
+        pytest.skip("floating-point predictor is for float samples")
+    if predictor == 2 and arr.dtype == np.float32:
+        pytest.skip("libtiff refuses horizontal differencing for float samples")
+    path = str(tmp_path / "x.tif")
+    try:
+        _save(path, arr, compression, predictor)
+    except Exception as e:       # a libtiff build without this combination
+        pytest.skip(f"PIL cannot write {compression}/{predictor}: {e}")
+    with Image.open(path) as im:
+        ref = np.array(im)
+    got, info = geotiff.read(path)
+    got = got[0] if arr.ndim == 2 else got.transpose(1, 2, 0)
+    assert got.dtype == ref.dtype
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(got, arr if arr.ndim == 2 else arr.transpose(1, 2, 0))
+
+
+def test_lzw_decoder_errors_and_kwkwk():
+    lib = _lib.lib()
+    # the classic KwKwK case: 'aaaaaaa...' forces code == next
+    data = np.full((1, 5000), 97, np.uint8)
+    import io
+    buf = io.BytesIO()
+    Image.fromarray(data).save(buf, format="TIFF", compression="tiff_lzw")
+    raw = buf.getvalue()
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".tif", delete=False) as f:
+        f.write(raw)
+    got, _ = geotiff.read(f.name)
+    os.unlink(f.name)
+    np.testing.assert_array_equal(got[0], data)
+    dst = C.create_string_buffer(16)
+    assert lib.td_tiff_lzw_decode(b"\x80\x00", 2, dst, 0) == 0            # ClearCode then end of input
+    bad = bytes([0xFF, 0xFF, 0xFF, 0xFF])
+    assert lib.td_tiff_lzw_decode(bad, len(bad), dst, 16) < 0             # code beyond the table
+    assert b"corrupt" in lib.td_last_error()

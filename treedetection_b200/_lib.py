@@ -59,6 +59,8 @@ SIGNATURES = {
     "td_compact_flags": (_i, [_p, _i, _p, _p, _p, _p]),
     "td_compact_nonneg": (_i, [_p, _i, _p, _p, _p, _p]),
     "td_ring_tail": (_i, [_p, _p, _i, _p, _p, _p]),
+    # N1 (host function)
+    "td_tiff_lzw_decode": (_ll, [_p, _ll, _p, _ll]),
     # P0a
     "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }

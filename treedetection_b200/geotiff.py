@@ -4,7 +4,9 @@ The reference reads and writes its rasters through rasterio/GDAL
 (``TreeDetection/prediction.py:61``, ``postprocessing.py:781-800``, ``merging.py:56-75``);
 neither is available here.  Supported: classic (non-Big) TIFF, little or big endian,
 strips or tiles, chunky or planar configuration, uint8 / uint16 / int16 / float32 samples,
-no compression or deflate (zlib, predictor 1), the GeoTIFF tags ModelPixelScale (33550),
+no compression, deflate (zlib) or LZW (libtreedet's td_tiff_lzw_decode, strips / tiles decoded on a
+thread pool), predictors 1, 2 (horizontal differencing) and 3 (floating point), the GeoTIFF tags
+ModelPixelScale (33550),
 ModelTiepoint (33922), ModelTransformation (34264), GeoKeyDirectory (34735, EPSG code of the
 projected / geographic CRS) and GDAL_NODATA (42113).  That covers the bundled
 ``data/nDSM/324125317.tif`` and everything this package writes.
@@ -96,6 +98,17 @@ def _info_from_tags(t):
     return GeoInfo(width, height, spp, np.dtype(dtype), tuple(float(v) for v in transform), epsg, nodata)
 
 
+def _lzw(raw: bytes, cap: int) -> bytes:
+    """One LZW strip / tile through libtreedet (host function td_tiff_lzw_decode)."""
+    import ctypes as C
+    from . import _lib
+    dst = C.create_string_buffer(max(cap, 1))
+    n = _lib.lib().td_tiff_lzw_decode(raw, len(raw), dst, cap)
+    if n < 0:
+        _lib.check(int(n), "td_tiff_lzw_decode")
+    return dst.raw[:n]
+
+
 def read_info(path) -> GeoInfo:
     with open(path, "rb") as f:
         head = f.read(8)
@@ -116,18 +129,56 @@ def read(path, window=None):
     t = _read_ifd(buf, bo)
     info = _info_from_tags(t)
     comp = int(t.get(259, (1,))[0])
-    if comp not in (1, 8, 32946):
+    if comp not in (1, 5, 8, 32946):
         raise ValueError(f"unsupported TIFF compression {comp}")
-    if int(t.get(317, (1,))[0]) != 1:
-        raise ValueError("unsupported TIFF predictor")
+    pred = int(t.get(317, (1,))[0])
+    if pred not in (1, 2, 3) or (pred == 3 and info.dtype != np.float32):
+        raise ValueError(f"unsupported TIFF predictor {pred}")
     planar = int(t.get(284, (1,))[0])
     W, H, C = info.width, info.height, info.count
     dt = info.dtype.newbyteorder(bo)
     out = np.empty((C, H, W), dtype=info.dtype)
+    spp = 1 if planar == 2 else C              # samples per pixel inside one chunk
+    if 322 in t:
+        chunk_rows, chunk_cols = int(t[323][0]), int(t[322][0])
+    else:
+        chunk_rows, chunk_cols = int(t.get(278, (H,))[0]), W
+    chunk_bytes = chunk_rows * chunk_cols * spp * info.dtype.itemsize
 
-    def chunk(off, cnt):
+    def unpredict(raw, rows):
+        """undo the TIFF predictor of one decoded chunk (rows x chunk_cols x spp samples)"""
+        if pred == 1:
+            return raw
+        if pred == 2:      # horizontal differencing per sample, modulo the sample width
+            a = np.frombuffer(raw, dtype=dt)[:rows * chunk_cols * spp].reshape(rows, chunk_cols, spp)
+            return np.cumsum(a, axis=1, dtype=info.dtype).astype(dt).tobytes()
+        # predictor 3: bytes of every row are plane-separated (most significant first) and differenced
+        n = chunk_cols * spp
+        b = np.frombuffer(raw, dtype=np.uint8)[:rows * n * 4].reshape(rows, 4 * n)
+        b = np.cumsum(b.reshape(rows, 4, n).reshape(rows, 4 * n).astype(np.uint8), axis=1, dtype=np.uint8)
+        b = b.reshape(rows, 4, n)[:, ::-1, :] if bo == "<" else b.reshape(rows, 4, n)
+        return np.ascontiguousarray(b.transpose(0, 2, 1)).tobytes()
+
+    def decode(k):
+        off, cnt = all_offs[k], all_cnts[k]
         raw = buf[off:off + cnt]
-        return zlib.decompress(raw) if comp != 1 else raw
+        if comp == 5:
+            raw = _lzw(raw, chunk_bytes)
+        elif comp != 1:
+            raw = zlib.decompress(raw)
+        return raw
+
+    all_offs, all_cnts = (t[324], t[325]) if 322 in t else (t[273], t[279])
+    if comp != 1 and len(all_offs) > 4:      # zlib and the LZW decoder release the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            decoded = list(ex.map(decode, range(len(all_offs))))
+    else:
+        decoded = [decode(k) for k in range(len(all_offs))]
+
+    def chunk(k, rows):
+        return unpredict(decoded[k], rows)
 
     if 322 in t:   # tiles
         tw, th = int(t[322][0]), int(t[323][0])
@@ -138,7 +189,7 @@ def read(path, window=None):
             for j in range(ty):
                 for i in range(tx):
                     k = p * per_plane + j * tx + i
-                    a = np.frombuffer(chunk(offs[k], cnts[k]), dtype=dt)
+                    a = np.frombuffer(chunk(k, th), dtype=dt)
                     hh, ww = min(th, H - j * th), min(tw, W - i * tw)
                     if planar == 2:
                         out[p, j * th:j * th + hh, i * tw:i * tw + ww] = a.reshape(th, tw)[:hh, :ww]
@@ -153,7 +204,7 @@ def read(path, window=None):
                 k = p * ns + s_
                 r0 = s_ * rps
                 hh = min(rps, H - r0)
-                a = np.frombuffer(chunk(offs[k], cnts[k]), dtype=dt)
+                a = np.frombuffer(chunk(k, hh), dtype=dt)
                 if planar == 2:
                     out[p, r0:r0 + hh] = a[:hh * W].reshape(hh, W)
                 else:
