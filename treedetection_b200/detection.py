@@ -231,15 +231,17 @@ def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10,
             if getattr(predictor, "wants_tiles", False):
                 tiles_dev, tiles_off, flags = tables.plan(d_img).run(d_img)
                 det = predictor.forward(stem, tiles, tiles_dev, tiles_off, flags)
-            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             boxes, scores, probs, inst_tile, tile_dims = (t(det.boxes_net), t(det.scores), t(det.probs),
                                                           t(det.inst_tile), t(det.tile_dims))
+            host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else a
             if config.get("keep_intermediate", False) and len(det.scores):
                 bpx, win, nwords = ops.paste_plan(boxes, inst_tile, tile_dims)
                 woff = ops.exclusive_offsets(nwords)
                 bits = ops.paste_threshold_pack(bpx, win, woff, probs, params.mask_threshold)
                 rings = ops.trace_rings(bits, win, woff, inst_tile, tables.tile_tf)
-                _write_tile_predictions(os.path.join(output_path, stem), fp, tiles, rings, det.inst_tile, det.scores)
+                _write_tile_predictions(os.path.join(output_path, stem), fp, tiles, rings, host(det.inst_tile),
+                                        host(det.scores))
             table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf,
                                            tables.tile_boxes, params)
             gpkg.write_layer(os.path.join(stitched_path, stem + ".gpkg"), stem, table.verts.cpu().numpy(),

@@ -11,8 +11,8 @@ A "model path" in config.yml (``combined_model`` / ``urban_model`` / ``forrest_m
 therefore be a directory of fixtures: ``<model_path>/<image stem>.npz`` with arrays
 ``boxes_net (N,4) f32, scores (N,) f32, probs (N,28,28) f32, inst_tile (N,) i32`` (tile
 index in the order of the tiles JSON) and ``tile_ids`` (the ids, for validation).  Any object
-with the same ``raw_outputs`` method can be passed as ``config["predictor"]`` instead (the
-adapter for a live detectron2 / torchvision model is the "next" row N3).
+with the same ``raw_outputs`` method can be passed as ``config["predictor"]`` instead;
+:class:`TorchvisionPredictor` is such an object for a live torchvision Mask R-CNN (row N3).
 """
 from __future__ import annotations
 
@@ -71,3 +71,104 @@ def dump_fixtures(model_path, image_stem, det: Detections):
     os.makedirs(model_path, exist_ok=True)
     np.savez(os.path.join(model_path, image_stem + ".npz"), boxes_net=det.boxes_net, scores=det.scores,
              probs=det.probs, inst_tile=det.inst_tile, tile_ids=np.array(det.tile_ids))
+
+
+class TorchvisionPredictor:
+    """N3: a live Mask R-CNN behind the predictor plug.
+
+    The reference runs detectron2's ``DefaultPredictor`` per batch of tiles and lets it paste the
+    masks (TreeDetection/prediction.py:178-195).  This adapter consumes the P1 output where it lies
+    -- normalised float32 CHW tiles in HBM -- runs backbone, RPN and ROI heads of a torchvision
+    ``MaskRCNN`` on the same stream and hands the RAW ROI-head outputs (boxes in network-input pixels,
+    scores, 28x28 mask probabilities, i.e. before any paste) to P2 as device tensors: no host round
+    trip between P1, the model and P2.  detectron2 is absent offline; torchvision's Mask R-CNN has the
+    same ROI-head contract.  With ``model=None`` a random-init ResNet-FPN model is built
+    (BASELINE.json: checkpoints are not available offline) -- useful for end-to-end timing and for
+    exercising the path on real network outputs, not for detection quality.
+    """
+    wants_tiles = True
+
+    def __init__(self, model=None, device="cuda", batch_tiles=4, backbone="resnet50", score_thresh=0.3,
+                 nms_thresh=0.5, detections_per_img=100, seed=0, exclude_vars=None):
+        import torch
+        self.device = torch.device(device)
+        self.batch_tiles = int(batch_tiles)
+        self.exclude_vars = exclude_vars or []
+        if model is None:
+            from torchvision.models.detection import MaskRCNN
+            from torchvision.models.detection.backbone_utils import resnet_fpn_backbone
+            torch.manual_seed(seed)
+            model = MaskRCNN(resnet_fpn_backbone(backbone_name=backbone, weights=None), num_classes=2,
+                             box_score_thresh=score_thresh, box_nms_thresh=nms_thresh,
+                             box_detections_per_img=detections_per_img)
+        self.model = model.to(self.device).eval()
+        # P1 delivers BGR 0..255 (detectron2's input convention, prediction.py:166); torchvision's
+        # statistics are RGB 0..1
+        mean = torch.tensor(self.model.transform.image_mean, dtype=torch.float32, device=self.device) * 255.0
+        std = torch.tensor(self.model.transform.image_std, dtype=torch.float32, device=self.device) * 255.0
+        self._mean = mean.flip(0).view(3, 1, 1)
+        self._std = std.flip(0).view(3, 1, 1)
+
+    def raw_outputs(self, image_stem, tiles):
+        """The tiling only (no instances): the live outputs come from :meth:`forward`."""
+        tile_ids = list(tiles.keys())
+        tile_dims = np.zeros((len(tile_ids), 4), dtype=np.int32)
+        for t, tid in enumerate(tile_ids):
+            _, _, w, h = tiles[tid]["window"]
+            nh, nw = resize_shortest_edge(h, w)
+            tile_dims[t] = (h, w, nh, nw)
+        z = np.zeros
+        return Detections(z((0, 4), np.float32), z(0, np.float32), z((0, 28, 28), np.float32), z(0, np.int32),
+                          tile_dims, tile_ids, tiles)
+
+    def forward(self, image_stem, tiles, tiles_dev, tiles_off, flags=None):
+        """tiles_dev: flat float32 device buffer of P1 (tile t = (3, net_h, net_w) at tiles_off[t]).
+        Returns Detections whose boxes_net / scores / probs / inst_tile are DEVICE tensors."""
+        import torch
+        from torchvision.models.detection.image_list import ImageList
+        base = self.raw_outputs(image_stem, tiles)
+        dims = base.tile_dims
+        skip = np.zeros(len(base.tile_ids), dtype=bool)
+        if self.exclude_vars:     # tiles excluded for this model (prediction.py:79-93)
+            skip = np.array([any(bool(tiles[tid].get(v, False)) for v in self.exclude_vars) for tid in base.tile_ids])
+        boxes, scores, probs, inst = [], [], [], []
+        order = [t for t in range(len(base.tile_ids)) if not skip[t]]
+        # batches of tiles with the same network size (ResizeShortestEdge: 800 x 800 except at the image edge)
+        groups = {}
+        for t in order:
+            groups.setdefault((int(dims[t, 2]), int(dims[t, 3])), []).append(t)
+        per_tile = {}
+        with torch.no_grad():
+            for (nh, nw), ts in groups.items():
+                for b0 in range(0, len(ts), self.batch_tiles):
+                    tb = ts[b0:b0 + self.batch_tiles]
+                    x = torch.stack([tiles_dev[int(tiles_off[t]):int(tiles_off[t]) + 3 * nh * nw].view(3, nh, nw)
+                                     for t in tb])
+                    x = ((x - self._mean) / self._std).flip(1)          # BGR -> RGB, normalised
+                    pad_h, pad_w = (-nh) % 32, (-nw) % 32
+                    if pad_h or pad_w:
+                        x = torch.nn.functional.pad(x, (0, pad_w, 0, pad_h))
+                    images = ImageList(x, [(nh, nw)] * len(tb))
+                    feats = self.model.backbone(x)
+                    if isinstance(feats, torch.Tensor):
+                        feats = {"0": feats}
+                    proposals, _ = self.model.rpn(images, feats)
+                    dets, _ = self.model.roi_heads(feats, proposals, images.image_sizes)
+                    for t, det in zip(tb, dets):
+                        per_tile[t] = det
+        for t in order:           # tile-major, instance order = model output order (score descending)
+            det = per_tile[t]
+            n = det["scores"].shape[0]
+            if n == 0:
+                continue
+            boxes.append(det["boxes"].to(torch.float32))
+            scores.append(det["scores"].to(torch.float32))
+            probs.append(det["masks"].to(torch.float32).reshape(n, 28, 28))
+            inst.append(torch.full((n,), t, dtype=torch.int32, device=self.device))
+        if boxes:
+            out = (torch.cat(boxes).contiguous(), torch.cat(scores).contiguous(), torch.cat(probs).contiguous(),
+                   torch.cat(inst).contiguous())
+        else:
+            z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=self.device)
+            out = (z(0, 4), z(0), z(0, 28, 28), z(0, dt=torch.int32))
+        return Detections(out[0], out[1], out[2], out[3], dims, base.tile_ids, tiles)
