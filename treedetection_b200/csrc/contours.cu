@@ -162,11 +162,28 @@ __global__ void __launch_bounds__(32) trace_emit_kernel(EmitArgs A) {
   td::lane_init(S, &out);
   if (nc == 0) S.mode = td::kDone;          // nothing to emit: skip the walk
   while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
-  if (!active || nc == 0) return;
+}
+
+// Second half of the emit pass: contours in OpenCV's order -> closed CRS rings.  One WARP per
+// instance (the walk above leaves per-lane contour tables and window-relative int16 points):
+// lane 0 orders the (few) contours, all lanes convert and store the vertices, so the float64
+// writes are coalesced instead of being a serial tail of the border walk.
+__global__ void __launch_bounds__(256) trace_rings_kernel(EmitArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= A.n) return;
+  const long long c0 = A.cont_off[i];
+  const int nc = (int)(A.cont_off[i + 1] - c0);
+  if (nc == 0) return;
+  const int* parent = A.ct_parent + c0;
+  const int* npts = A.ct_npts + c0;
+  const int* pt_off = A.ct_ptoff + c0;
+  const short* pts = A.pts + 2 * A.pts_off[i];
   int* last_child = A.ct_scratch + 3 * c0;
   int* prev_sib = last_child + nc;
   int* order = prev_sib + nc;
-  td::contour_order(nc, out.parent, last_child, prev_sib, order);
+  if (lane == 0) td::contour_order(nc, parent, last_child, prev_sib, order);
+  __syncwarp();
   const int wx0 = A.win[4 * i + 0], wy0 = A.win[4 * i + 1];
   const double* tf = A.tile_tf + 6 * (size_t)A.inst_tile[i];
   const double ta = tf[0], tb = tf[1], tc = tf[2], td_ = tf[3], te = tf[4], tff = tf[5];
@@ -174,14 +191,16 @@ __global__ void __launch_bounds__(32) trace_emit_kernel(EmitArgs A) {
   long long v = A.vert_base[i];
   for (int k = 0; k < nc; ++k) {
     const int c = order[k];
-    const int np = out.npts[c];
+    const int np = npts[c];
     if (np < 4) continue;
-    const short* p = out.pts + 2 * (size_t)out.pt_off[c];
+    const short* p = pts + 2 * (size_t)pt_off[c];
     const bool close = (p[0] != p[2 * (np - 1)]) || (p[1] != p[2 * (np - 1) + 1]);
     const int nv = np + (close ? 1 : 0);
-    A.ring_off[ring] = v;
-    A.ring_inst[ring] = i;
-    for (int q = 0; q < nv; ++q) {
+    if (lane == 0) {
+      A.ring_off[ring] = v;
+      A.ring_inst[ring] = i;
+    }
+    for (int q = lane; q < nv; q += 32) {
       const int qq = q < np ? q : 0;
       const double col = (double)(p[2 * qq] + wx0), row = (double)(p[2 * qq + 1] + wy0);
       // xy_gpu: a * x + b * y + c, every operation rounded (float64)
@@ -236,6 +255,7 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
   A.smem_bytes = smem_per_warp(n_inst);
   trace_emit_kernel<<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
+  trace_rings_kernel<<<td_div_up((long long)n_inst * 32, 256), 256, 0, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
   return TD_OK;
 }
