@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
+    ap.add_argument("--no-alone", action="store_true",
+                    help="do not time the roofline kernel alone after the timed region (profiling runs: keeps the "
+                         "launch list to whole steps); the roofline entry then uses the in-step time")
     ap.add_argument("--exact", action="store_true",
                     help="exact-size chain (a host synchronisation before every allocation) instead of the "
                          "sync-free capacity-buffer chain")
@@ -410,17 +413,17 @@ def run_b200(a):
     # the roofline kernel timed alone (CUDA events on its stream, after the timed region): inside the
     # step it shares the GPU with the P2-P9 chain, which says nothing about the kernel itself
     p1_alone = []
-    for _ in range(3):
+    for _ in range(0 if a.no_alone else 3):
         tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
     torch.cuda.synchronize()
-    for _ in range(20):
+    for _ in range(0 if a.no_alone else 20):
         s0, s1 = ev(), ev()
         s0.record()
         tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
         s1.record()
         p1_alone.append((s0, s1))
     torch.cuda.synchronize()
-    p1_ms = statistics.mean(x.elapsed_time(y) for x, y in p1_alone)
+    p1_ms = statistics.mean(x.elapsed_time(y) for x, y in p1_alone) if p1_alone else p1_ms_in_step
     names = ["P1 tile cut/normalise", "P2-P4 paste/contours/stitch", "P5 NDVI/decimation", "P6-P9 NMS/stats/select"]
     pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
     chain_mode = "exact sizes (host sync before every allocation)" if a.exact else \
@@ -527,8 +530,9 @@ def run_b200(a):
                                             "the kernel writes 12.6 GB and reads 0.4 GB, so frac can approach 1.1",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": p1_bytes, "ms_per_launch": p1_ms,
-                         "timed": "alone: 20 launches after the timed region, CUDA events on the launching stream "
-                                  "(burst peak applies)",
+                         "timed": ("in the step" if a.no_alone else
+                                   "alone: 20 launches after the timed region, CUDA events on the launching stream "
+                                   "(burst peak applies)"),
                          "ms_per_launch_in_step": p1_ms_in_step,
                          "in_step_note": ("serial step: the kernel runs alone inside the step" if a.serial else
                                           "inside the step the kernel shares the GPU with the concurrent P2-P9 chain"),

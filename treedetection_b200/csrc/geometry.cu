@@ -35,6 +35,33 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   int* sc = scratch + 5 * v0;
   // alive words: ring r owns (len + 31) / 32 words starting at v0 / 32 + r  (disjoint)
   uint32_t* al = alive + (v0 >> 5) + r;
+  // bounds of the input ring (needed for the pre-filter below and for bounds_of_input)
+  double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+  if (boxes || bounds_of_input) {
+    for (int k = lane; k < len; k += 32) {
+      const td::P2 p = pts[k];
+      minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
+      miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+      maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+      miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+      maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+  }
+  // Pre-filter of the tile box test: every vertex the simplifier drops lies within `tol` of the chord
+  // that replaces it, and a chord point outside the (convex) box means a kept end point outside it.
+  // So a ring that sticks out of the box by more than tol cannot be `within` it after simplification
+  // either: it is rejected without being simplified (a quarter of the rings of a tiled image).
+  if (boxes && !out_bounds && !out_area && out_keep && len > 0) {
+    const double* b = boxes + 4 * (size_t)ring_box[r];
+    const double slack = (tol > 0.0 ? tol : 0.0) * (1.0 + 1e-9) + 1e-9;
+    if (minx < b[0] - slack || miny < b[1] - slack || maxx > b[2] + slack || maxy > b[3] + slack) {
+      if (lane == 0) { out_count[r] = 0; out_keep[r] = 0; }
+      return;
+    }
+  }
   int m;
   if (tol > 0.0 && len > 0) {
     m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
@@ -43,18 +70,19 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
     m = len;
   }
   __syncwarp();
-  double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-  const int nb = bounds_of_input ? len : m;
-  for (int k = lane; k < nb; k += 32) {
-    const td::P2 p = bounds_of_input ? pts[k] : pts[sc[k]];
-    minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
-    miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
-    maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-    miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
-    maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+  if (!bounds_of_input) {
+    minx = INFINITY; miny = INFINITY; maxx = -INFINITY; maxy = -INFINITY;
+    for (int k = lane; k < m; k += 32) {
+      const td::P2 p = pts[sc[k]];
+      minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
+      miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+      maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+      miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+      maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
   }
   if (lane != 0) return;
   out_count[r] = m;

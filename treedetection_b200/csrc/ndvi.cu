@@ -17,6 +17,9 @@
 // stored as float32 -- the reference's float64 array is only ever consumed through
 // cp.array(ndvi_data, dtype=float32) (postprocessing.py:543); the float32 value is
 // identical for all 65 536 uint8 input pairs (tests/test_oracle_vs_reference.py).
+#include <cstdlib>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -139,61 +142,71 @@ struct DevAxis {
   int* count = nullptr;
   float* w = nullptr;
   int ktaps = 0;
-  int max_rows = 0;  // max source span of kTileH consecutive outputs
+  int max_rows = 0;  // max source span of `group` consecutive outputs
+  int max_count = 0;
 };
 
-int upload_axis(int in_size, int out_size, int group, DevAxis& d, cudaStream_t st) {
+// Axis tables depend on (in, out, group) only: built and uploaded once, kept for the life of the
+// process (a few hundred KB), so a call launches its kernel and nothing else.
+struct AxisKey {
+  int dev, in_size, out_size, group;
+  bool operator<(const AxisKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (in_size != o.in_size) return in_size < o.in_size;
+    if (out_size != o.out_size) return out_size < o.out_size;
+    return group < o.group;
+  }
+};
+
+int get_axis(int in_size, int out_size, int group, DevAxis& d) {
+  static std::mutex mu;
+  static std::map<AxisKey, DevAxis> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  const AxisKey key{dev, in_size, out_size, group};
+  auto it = cache.find(key);
+  if (it != cache.end()) { d = it->second; return TD_OK; }
   std::vector<int> s, c;
   std::vector<float> w;
   build_axis(in_size, out_size, s, c, w, d.ktaps);
   d.max_rows = 0;
+  d.max_count = 0;
   for (int i = 0; i < out_size; i += group) {
     const int last = (i + group < out_size ? i + group : out_size) - 1;
     const int span = s[last] + c[last] - s[i];
     if (span > d.max_rows) d.max_rows = span;
   }
-  TD_CUDA(cudaMallocAsync((void**)&d.start, sizeof(int) * out_size, st));
-  TD_CUDA(cudaMallocAsync((void**)&d.count, sizeof(int) * out_size, st));
-  TD_CUDA(cudaMallocAsync((void**)&d.w, sizeof(float) * w.size(), st));
-  TD_CUDA(cudaMemcpyAsync(d.start, s.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice, st));
-  TD_CUDA(cudaMemcpyAsync(d.count, c.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice, st));
-  TD_CUDA(cudaMemcpyAsync(d.w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice, st));
-  // pageable sources: the copies above are staged before returning, the vectors may die
+  TD_CUDA(cudaMalloc((void**)&d.start, sizeof(int) * out_size));
+  TD_CUDA(cudaMalloc((void**)&d.count, sizeof(int) * out_size));
+  TD_CUDA(cudaMalloc((void**)&d.w, sizeof(float) * w.size()));
+  TD_CUDA(cudaMemcpy(d.start, s.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+  TD_CUDA(cudaMemcpy(d.count, c.data(), sizeof(int) * out_size, cudaMemcpyHostToDevice));
+  TD_CUDA(cudaMemcpy(d.w, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+  cache[key] = d;
   return TD_OK;
-}
-
-void free_axis(DevAxis& d, cudaStream_t st) {
-  if (d.start) cudaFreeAsync(d.start, st);
-  if (d.count) cudaFreeAsync(d.count, st);
-  if (d.w) cudaFreeAsync(d.w, st);
 }
 
 template <typename T, int EPI>
 int run_decimate(const T* s0, const T* s1, int in_h, int in_w, int out_h, int out_w, float* out, cudaStream_t st) {
-  td_ensure_pool();
   DevAxis dx, dy;
-  int rc = upload_axis(in_w, out_w, kTileW, dx, st);
-  if (rc == TD_OK) rc = upload_axis(in_h, out_h, kTileH, dy, st);
-  if (rc == TD_OK) {
-    if (dx.ktaps > kMaxTaps || dy.ktaps > kMaxTaps) {
-      td_set_error("decimation factor too large for the fused kernel (taps %d x %d)", dx.ktaps, dy.ktaps);
-      rc = TD_ERR_UNSUPPORTED;
-    }
+  int rc = get_axis(in_w, out_w, kTileW, dx);
+  if (rc != TD_OK) return rc;
+  rc = get_axis(in_h, out_h, kTileH, dy);
+  if (rc != TD_OK) return rc;
+  if (dx.ktaps > kMaxTaps || dy.ktaps > kMaxTaps) {
+    td_set_error("decimation factor too large for the fused kernel (taps %d x %d)", dx.ktaps, dy.ktaps);
+    return TD_ERR_UNSUPPORTED;
   }
-  if (rc == TD_OK) {
-    constexpr int NB = EPI == 1 ? 2 : 1;
-    const size_t smem = sizeof(float) * NB * (size_t)dy.max_rows * kTileW;
-    auto kern = decimate_kernel<T, EPI>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    AxisTable ax{dx.start, dx.count, dx.w, dx.ktaps}, ay{dy.start, dy.count, dy.w, dy.ktaps};
-    dim3 grid(td_div_up(out_w, kTileW), td_div_up(out_h, kTileH));
-    kern<<<grid, kTileW * kTileH, smem, st>>>(s0, s1, in_h, in_w, out_h, out_w, ax, ay, out, dy.max_rows);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { td_set_error("decimate: %s", cudaGetErrorString(e)); rc = TD_ERR_CUDA; }
-  }
-  free_axis(dx, st);
-  free_axis(dy, st);
-  return rc;
+  constexpr int NB = EPI == 1 ? 2 : 1;
+  const size_t smem = sizeof(float) * NB * (size_t)dy.max_rows * kTileW;
+  auto kern = decimate_kernel<T, EPI>;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  AxisTable ax{dx.start, dx.count, dx.w, dx.ktaps}, ay{dy.start, dy.count, dy.w, dy.ktaps};
+  dim3 grid(td_div_up(out_w, kTileW), td_div_up(out_h, kTileH));
+  kern<<<grid, kTileW * kTileH, smem, st>>>(s0, s1, in_h, in_w, out_h, out_w, ax, ay, out, dy.max_rows);
+  TD_CHECK_LAUNCH("decimate");
+  return TD_OK;
 }
 
 }  // namespace
