@@ -205,6 +205,14 @@ int td_compact_nonneg(const int* values, int n, const long long* n_dev, long lon
                       void* stream);
 int td_ring_tail(long long* ring_off, int* ring_inst, int cap_rings, const long long* n_rings,
                  const long long* n_verts, void* stream);
+/*   td_ring_offsets: dst_off (n+1) i64 = exclusive offsets of the rings sel[0..n) -- lengths from
+ *     `count` (kept vertices, td_simplify_rings) when given, else from ring_off.
+ *   td_gather_rows: k <= 8 row gathers in one launch, out[a][i] = in[a][sel[i]] for i < n (< *n_dev);
+ *     in / out / row_bytes are HOST arrays of k device pointers / row sizes in bytes.               */
+int td_ring_offsets(const long long* ring_off, const int* count, const long long* sel, int n, long long* dst_off,
+                    void* stream);
+int td_gather_rows(const void* const* in, void* const* out, const int* row_bytes, int k, const long long* sel, int n,
+                   const long long* n_dev, void* stream);
 
 /* ---- P0a: seam strips ---------------------------------------------------------------------------
  * Replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,

@@ -84,6 +84,43 @@ __global__ void ring_tail_kernel(long long* __restrict__ ring_off, int* __restri
   }
 }
 
+// lens[i] = length of ring sel[i]: from the kept-vertex counts of td_simplify_rings, or from ring_off
+struct SelLen {
+  const long long* sel;
+  const int* count;
+  const long long* ring_off;
+  __host__ __device__ long long operator()(int i) const {
+    const long long r = sel[i];
+    return count ? (long long)count[r] : ring_off[r + 1] - ring_off[r];
+  }
+};
+
+constexpr int kMaxGather = 8;
+struct GatherArgs {
+  const unsigned char* in[kMaxGather];
+  unsigned char* out[kMaxGather];
+  int row_bytes[kMaxGather];
+  int k;
+};
+
+// out_a[i] = in_a[sel[i]] for every array a: one thread per (row, array)
+__global__ void gather_rows_kernel(GatherArgs A, const long long* __restrict__ sel, int n,
+                                   const long long* __restrict__ n_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (n_dev && i >= *n_dev)) return;
+  const int a = blockIdx.y;
+  const int rb = A.row_bytes[a];
+  const unsigned char* src = A.in[a] + (size_t)sel[i] * rb;
+  unsigned char* dst = A.out[a] + (size_t)i * rb;
+  if ((rb & 7) == 0) {
+    for (int b = 0; b < rb; b += 8) *reinterpret_cast<uint64_t*>(dst + b) = *reinterpret_cast<const uint64_t*>(src + b);
+  } else if ((rb & 3) == 0) {
+    for (int b = 0; b < rb; b += 4) *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(src + b);
+  } else {
+    for (int b = 0; b < rb; ++b) dst[b] = src[b];
+  }
+}
+
 template <typename InIt, typename FlagIt>
 int select_flagged(InIt in, FlagIt flags, long long* out, long long* count, int n, cudaStream_t st) {
   size_t bytes = 0;
@@ -177,5 +214,45 @@ extern "C" int td_ring_tail(long long* ring_off, int* ring_inst, int cap_rings, 
   ring_tail_kernel<<<td_div_up(cap_rings + 1, 256), 256, 0, (cudaStream_t)stream>>>(ring_off, ring_inst, cap_rings,
                                                                                      n_rings, n_verts);
   TD_CHECK_LAUNCH("td_ring_tail");
+  return TD_OK;
+}
+
+// dst_off (n + 1) = exclusive offsets of the rings sel[0..n): lengths from `count` (kept vertices of
+// td_simplify_rings) when given, else from ring_off.  Rows past *n_dev are harmless garbage.
+extern "C" int td_ring_offsets(const long long* ring_off, const int* count, const long long* sel, int n,
+                               long long* dst_off, void* stream) {
+  TD_ARG(n >= 0 && dst_off && (ring_off || count));
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_CUDA(cudaMemsetAsync(dst_off, 0, sizeof(long long), st));
+  if (n == 0) return TD_OK;
+  TD_ARG(sel);
+  td_ensure_pool();
+  cub::CountingInputIterator<int> iota(0);
+  cub::TransformInputIterator<long long, SelLen, cub::CountingInputIterator<int>> lens(iota, SelLen{sel, count, ring_off});
+  size_t bytes = 0;
+  TD_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, lens, dst_off + 1, n, st));
+  void* tmp = nullptr;
+  TD_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, st));
+  cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, bytes, lens, dst_off + 1, n, st);
+  cudaFreeAsync(tmp, st);
+  if (e != cudaSuccess) { td_set_error("td_ring_offsets: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}
+
+// k <= 8 row gathers in one launch: out[a][i] = in[a][sel[i]] (rows of row_bytes[a] bytes) for i < n
+// (and < *n_dev).  in / out / row_bytes: HOST arrays of k device pointers / sizes.
+extern "C" int td_gather_rows(const void* const* in, void* const* out, const int* row_bytes, int k,
+                              const long long* sel, int n, const long long* n_dev, void* stream) {
+  TD_ARG(k > 0 && k <= kMaxGather && n >= 0 && in && out && row_bytes);
+  if (n == 0) return TD_OK;
+  TD_ARG(sel);
+  GatherArgs A;
+  A.k = k;
+  for (int a = 0; a < k; ++a) {
+    TD_ARG(in[a] && out[a] && row_bytes[a] > 0);
+    A.in[a] = (const unsigned char*)in[a]; A.out[a] = (unsigned char*)out[a]; A.row_bytes[a] = row_bytes[a];
+  }
+  gather_rows_kernel<<<dim3(td_div_up(n, 256), k), 256, 0, (cudaStream_t)stream>>>(A, sel, n, n_dev);
+  TD_CHECK_LAUNCH("td_gather_rows");
   return TD_OK;
 }

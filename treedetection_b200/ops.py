@@ -352,15 +352,27 @@ def take_rings_dyn(verts, ring_off, sel, n_dev, out_cap, scratch=None, count=Non
     input vertex count).  Returns (verts (out_cap,2), dst_off (cap+1,)); rows / offsets past the live
     count are undefined.  No synchronisation."""
     dev = verts.device
-    if count is not None:
-        lens = count.to(torch.int64)[sel]
-    else:
-        lens = (ring_off[1:] - ring_off[:-1])[sel]
-    dst_off = exclusive_offsets(lens)
+    dst_off = torch.empty((sel.shape[0] + 1,), dtype=torch.int64, device=dev)
+    _lib.call("td_ring_offsets", _ptr(ring_off), _ptr(count), _ptr(sel), sel.shape[0], _ptr(dst_off), _stream())
     out = torch.empty((max(out_cap, 1), 2), dtype=torch.float64, device=dev)
     _lib.call("td_take_rings", _ptr(verts), _ptr(ring_off), _ptr(sel), sel.shape[0], _ptr(scratch), _ptr(dst_off),
               out.data_ptr(), _ptr(n_dev), _stream())
     return out, dst_off
+
+
+def gather_rows(arrays, sel, n_dev=None):
+    """[a[sel] for a in arrays] in ONE launch (td_gather_rows); arrays: contiguous device tensors whose
+    first dimension is the row; ``sel`` (n,) i64 with valid indices everywhere (zero tail)."""
+    import ctypes as C
+    k = len(arrays)
+    n = sel.shape[0]
+    outs = [torch.empty((n,) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device) for a in arrays]
+    rb = [a.element_size() * (a[0].numel() if a.dim() > 1 else 1) for a in arrays]
+    ins_p = (C.c_void_p * k)(*[_ptr(a) for a in arrays])
+    outs_p = (C.c_void_p * k)(*[o.data_ptr() for o in outs])
+    rb_p = (C.c_int * k)(*rb)
+    _lib.call("td_gather_rows", ins_p, outs_p, rb_p, k, _ptr(sel), n, _ptr(n_dev), _stream())
+    return outs
 
 
 # ----------------------------------------------------------------------------

@@ -301,14 +301,13 @@ def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, cap
     n1 = ctr[CTR_N1:CTR_N1 + 1]
     sel1, _ = ops.compact_flags(conf_ok & (area_all >= p.area_threshold) & (area_all <= 1000), count=n1)
     verts1, off1 = ops.take_rings_dyn(table.verts, table.ring_off, sel1, n1, cap_v)
-    conf1, area1, pid1 = table.conf[sel1], area_all[sel1].contiguous(), pid_all[sel1]
-    b1 = s2["bounds"][sel1].contiguous()
-    removed = ops.bbox_nms_ordered_dyn(b1, conf1.contiguous(), area1, n1, p.iou_threshold, p.area_threshold,
+    conf1, area1, pid1, b1 = ops.gather_rows([table.conf, area_all, pid_all, s2["bounds"]], sel1, n1)
+    removed = ops.bbox_nms_ordered_dyn(b1, conf1, area1, n1, p.iou_threshold, p.area_threshold,
                                        int(caps["nbr"]), flag)
     n2 = ctr[CTR_N2:CTR_N2 + 1]
     sel2, _ = ops.compact_flags(removed == 0, n_dev=n1, count=n2)
     verts2, off2 = ops.take_rings_dyn(verts1, off1, sel2, n2, cap_v)
-    conf2, area2, pid2, b2 = conf1[sel2], area1[sel2].contiguous(), pid1[sel2], b1[sel2].contiguous()
+    conf2, area2, pid2, b2 = ops.gather_rows([conf1, area1, pid1, b1], sel2, n2)
     cent = ops.centroids(verts2, off2, n_dev=n2)
     if rasters.get("height_ready") is not None:      # the nDSM may still be on its way (api.run_image)
         torch.cuda.current_stream().wait_event(rasters["height_ready"])
@@ -332,8 +331,8 @@ def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, cap
     vf, of = ops.take_rings_dyn(verts2, off2, final, nf, cap_v)
     ctr[CTR_VFINAL:CTR_VFINAL + 1] = of.gather(0, nf)
     vf = ops.round_coords(vf)
-    return Features(vf, of, pid2[final], conf2[final], area2[final], max_h[final], cent[final], isc[final], num[final],
-                    {})
+    pidf, conff, areaf, hf, centf, iscf, numf = ops.gather_rows([pid2, conf2, area2, max_h, cent, isc, num], final, nf)
+    return Features(vf, of, pidf, conff, areaf, hf, centf, iscf, numf, {})
 
 
 def trim_features(f: Features, n: int, v: int) -> Features:
