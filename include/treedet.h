@@ -69,7 +69,8 @@ int td_tile_cut_normalize(const void* plan, const void* image, int bands, float*
  *   -> boxes_px (N,4) f32 (scaled, clipped), win (N,4) i32 [x0,y0,w,h] (0,0,0,0 when the
  *      box is empty and the instance is dropped), nwords (N) i64 = ceil(w/32)*h      */
 int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst, int n_tiles,
-                  float* boxes_px, int* win, long long* nwords, void* stream);
+                  float* boxes_px, int* win, long long* nwords, long long* npx, void* stream);
+/*   npx (N) i64, may be null: w*h of every window (sizes the label plane of td_trace_emit)       */
 /*   word_off (N+1) i64 = exclusive scan of nwords; probs (N,28,28) f32 probabilities;
  *   bits: packed 1-bit rasters, row-major, 32 pixels per uint32 (LSB = leftmost)       */
 int td_paste_threshold_pack(const float* boxes_px, const int* win, const long long* word_off, const float* probs,
@@ -86,7 +87,8 @@ int td_paste_values(const float* boxes_px, const int* win, const long long* val_
  *   counts  (N,4) i32 out: [borders, points, kept rings, ring vertices]; borders < 0 when
  *           one window holds more than 65534 borders                                      */
 int td_trace_count(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
-                   long long total_words, uint32_t* planes, int* counts, void* stream);
+                   long long total_words, uint32_t* planes, int* counts, long long* sizes_kn, void* stream);
+/*   sizes_kn (4,N) i64, may be null: the same counts as rows (the layout td_scan_clamp consumes)  */
 /*   labels (sum w*h) u16 scratch; px_off / cont_off / pts_off / ring_base / vert_base:
  *   (N+1) i64 exclusive scans of w*h and of the four count columns; ct_int: 6*total_contours
  *   i32 scratch; ct_hole: total_contours u8 scratch; pts: 2*total_points i16 scratch;
@@ -173,6 +175,11 @@ int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi
                      const int* num_contained, const unsigned char* is_contained, int n, const double* params,
                      int* pre, int* out_idx, const long long* n_dev, void* stream);
 int td_round_coords(const double* in, long long n, double* out, void* stream);
+/*   head of process_geojson (postprocessing.py:739-768): flags (N) u8 = conf >= conf_thr and
+ *   area_min <= area <= area_max (area of simplify(2)); poly_id (N) i64 = enumeration index after the
+ *   confidence filter                                                                              */
+int td_select_head(const double* conf, const double* area, int n, const long long* n_dev, double conf_thr,
+                   double area_min, double area_max, unsigned char* flags, long long* poly_id, void* stream);
 
 /* ---- P10: forest-outline predicates (two-model fusion, tile flags) -----------------------------
  * Replaces the GEOS predicates of fuse_predictions (TreeDetection/helpers.py:795-811) and of

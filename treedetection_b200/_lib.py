@@ -25,11 +25,11 @@ SIGNATURES = {
     "td_last_error": (C.c_char_p, []),
     "td_device_sms": (_i, []),
     # P2
-    "td_paste_plan": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "td_paste_plan": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "td_paste_threshold_pack": (_i, [_p, _p, _p, _p, _i, _f, _p, _p]),
     "td_paste_values": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     # P3
-    "td_trace_count": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p]),
+    "td_trace_count": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
     "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
                            _p]),
     # P4 / P9 geometry
@@ -48,6 +48,7 @@ SIGNATURES = {
     # P9
     "td_select_crowns": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "td_round_coords": (_i, [_p, _ll, _p, _p]),
+    "td_select_head": (_i, [_p, _p, _i, _p, _d, _d, _d, _p, _p, _p]),
     # P1
     "td_tile_plan_create": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "td_tile_plan_destroy": (_i, [_p]),
@@ -74,7 +75,7 @@ OWN_KERNELS = {
     "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
     "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 2, "td_compact_flags": 1, "td_compact_nonneg": 1,
     "td_ring_tail": 1, "td_ring_offsets": 0, "td_gather_rows": 1, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,
-    "td_round_coords": 1, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1,
+    "td_round_coords": 1, "td_select_head": 2, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1,
 }
 launch_count = 0
 

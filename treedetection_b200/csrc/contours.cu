@@ -101,7 +101,7 @@ __device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_
 __global__ void __launch_bounds__(32)
 trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ win, const long long* __restrict__ word_off,
                    int n, uint32_t* __restrict__ planes, long long total_words, int* __restrict__ counts,
-                   int smem_bytes) {
+                   long long* __restrict__ sizes_kn, int smem_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const bool active = i < n;
@@ -114,6 +114,12 @@ trace_count_kernel(const uint32_t* __restrict__ bits, const int* __restrict__ wi
     counts[4 * i + 1] = S.cc.n_points;
     counts[4 * i + 2] = S.cc.n_rings;
     counts[4 * i + 3] = S.cc.n_ring_verts;
+    if (sizes_kn) {      // the same four counts as (4, n) int64 rows: what td_scan_clamp consumes
+      sizes_kn[i] = S.cc.n_contours;
+      sizes_kn[(size_t)n + i] = S.cc.n_points;
+      sizes_kn[2 * (size_t)n + i] = S.cc.n_rings;
+      sizes_kn[3 * (size_t)n + i] = S.cc.n_ring_verts;
+    }
   }
 }
 
@@ -216,7 +222,8 @@ __global__ void __launch_bounds__(256) trace_rings_kernel(EmitArgs A) {
 
 // planes: scratch of 2 * total_words uint32, zeroed by this call.
 extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
-                              long long total_words, uint32_t* planes, int* counts, void* stream) {
+                              long long total_words, uint32_t* planes, int* counts, long long* sizes_kn,
+                              void* stream) {
   TD_ARG(n_inst >= 0 && total_words >= 0);
   if (n_inst == 0) return TD_OK;
   TD_ARG(bits && win && word_off && planes && counts);
@@ -224,7 +231,7 @@ extern "C" int td_trace_count(const uint32_t* bits, const int* win, const long l
   TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
   const int smem_bytes = smem_per_warp(n_inst);
   trace_count_kernel<<<td_div_up(n_inst, 32), 32, smem_bytes, st>>>(bits, win, word_off, n_inst, planes, total_words, counts,
-                                                                  smem_bytes);
+                                                                  sizes_kn, smem_bytes);
   TD_CHECK_LAUNCH("td_trace_count");
   return TD_OK;
 }

@@ -30,7 +30,8 @@ constexpr int kPasteThreads = 128;  // 4 warps per instance
 // ---------------------------------------------------------------------------
 __global__ void paste_plan_kernel(const float* __restrict__ boxes_net, const int* __restrict__ inst_tile,
                                   const int* __restrict__ tile_dims, int n, float* __restrict__ boxes_px,
-                                  int* __restrict__ win, long long* __restrict__ nwords) {
+                                  int* __restrict__ win, long long* __restrict__ nwords,
+                                  long long* __restrict__ npx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int t = inst_tile[i];
@@ -67,6 +68,7 @@ __global__ void paste_plan_kernel(const float* __restrict__ boxes_net, const int
   win[4 * i + 2] = ww;
   win[4 * i + 3] = wh;
   nwords[i] = (long long)((ww + 31) >> 5) * (long long)wh;
+  if (npx) npx[i] = (long long)ww * (long long)wh;
 }
 
 // one axis of the sampling grid: pixel centre -> tap index and the two weights
@@ -201,12 +203,13 @@ __global__ void paste_values_kernel(const float* __restrict__ boxes_px, const in
 }  // namespace
 
 extern "C" int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst,
-                             int n_tiles, float* boxes_px, int* win, long long* nwords, void* stream) {
+                             int n_tiles, float* boxes_px, int* win, long long* nwords, long long* npx,
+                             void* stream) {
   TD_ARG(n_inst >= 0 && n_tiles >= 0);
   if (n_inst == 0) return TD_OK;
   TD_ARG(boxes_net && inst_tile && tile_dims && boxes_px && win && nwords);
   paste_plan_kernel<<<td_div_up(n_inst, 256), 256, 0, (cudaStream_t)stream>>>(boxes_net, inst_tile, tile_dims, n_inst,
-                                                                              boxes_px, win, nwords);
+                                                                              boxes_px, win, nwords, npx);
   TD_CHECK_LAUNCH("td_paste_plan");
   return TD_OK;
 }

@@ -84,6 +84,24 @@ __global__ void decide_kernel(const int* __restrict__ pre, const int* __restrict
   out_idx[i] = out;
 }
 
+// P9 head (process_geojson, postprocessing.py:739-768): confidence filter, then the area filter on
+// simplify(2).area; poly_id = enumeration index after the confidence filter.
+__global__ void head_flags_kernel(const double* __restrict__ conf, const double* __restrict__ area, int n,
+                                  const long long* __restrict__ n_dev, double conf_thr, double area_min,
+                                  double area_max, int* __restrict__ conf_ok, unsigned char* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool live = !(n_dev && i >= *n_dev);
+  const bool ok = live && conf[i] >= conf_thr;
+  conf_ok[i] = ok ? 1 : 0;
+  flags[i] = (ok && area[i] >= area_min && area[i] <= area_max) ? 1 : 0;
+}
+
+__global__ void widen_kernel(const int* __restrict__ in, int n, long long* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
 __global__ void round_coords_kernel(const double* __restrict__ in, long long n, double* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -130,6 +148,38 @@ extern "C" int td_select_crowns(const double* bounds, const float* max_h, const 
   cudaFreeAsync(rank, st);
   cudaFreeAsync(first, st);
   if (e != cudaSuccess) { td_set_error("td_select_crowns: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}
+
+// flags (n) u8 = conf >= conf_thr && area_min <= area <= area_max; poly_id (n) i64 = number of crowns
+// before i that pass the confidence filter (the id process_geojson gives crown i if it passes).
+extern "C" int td_select_head(const double* conf, const double* area, int n, const long long* n_dev,
+                              double conf_thr, double area_min, double area_max, unsigned char* flags,
+                              long long* poly_id, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(conf && area && flags && poly_id);
+  cudaStream_t st = (cudaStream_t)stream;
+  td_ensure_pool();
+  int* ok = nullptr;
+  int* rank = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  TD_CUDA(cudaMallocAsync((void**)&ok, sizeof(int) * n, st));
+  TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
+  const int blocks = td_div_up(n, 256);
+  head_flags_kernel<<<blocks, 256, 0, st>>>(conf, area, n, n_dev, conf_thr, area_min, area_max, ok, flags);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ok, rank, n, st);
+  cudaError_t e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st);
+  if (e == cudaSuccess) {
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ok, rank, n, st);
+    widen_kernel<<<blocks, 256, 0, st>>>(rank, n, poly_id);
+    e = cudaGetLastError();
+    cudaFreeAsync(tmp, st);
+  }
+  cudaFreeAsync(rank, st);
+  cudaFreeAsync(ok, st);
+  if (e != cudaSuccess) { td_set_error("td_select_head: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
 

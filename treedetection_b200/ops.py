@@ -37,19 +37,20 @@ def _chk(t, dtype, name):
 # ----------------------------------------------------------------------------
 # P2  paste + threshold + pack
 # ----------------------------------------------------------------------------
-def paste_plan(boxes_net, inst_tile, tile_dims):
+def paste_plan(boxes_net, inst_tile, tile_dims, sizes=None):
     """boxes_net (N,4) f32 in network-input pixels, inst_tile (N,) i32, tile_dims
     (T,4) i32 = [tile_h, tile_w, net_h, net_w].  Returns boxes_px (N,4) f32, win
-    (N,4) i32 = [x0, y0, w, h] (w = h = 0 for dropped instances), nwords (N,) i64."""
+    (N,4) i32 = [x0, y0, w, h] (w = h = 0 for dropped instances), nwords (N,) i64.
+    ``sizes``: optional (2,N) i64 buffer receiving [nwords, w*h] (``nwords`` is then its first row)."""
     n = boxes_net.shape[0]
     dev = boxes_net.device
     _chk(boxes_net, torch.float32, "boxes_net"); _chk(inst_tile, torch.int32, "inst_tile")
     _chk(tile_dims, torch.int32, "tile_dims")
     boxes_px = torch.empty((n, 4), dtype=torch.float32, device=dev)
     win = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    nwords = torch.empty((n,), dtype=torch.int64, device=dev)
+    nwords = torch.empty((n,), dtype=torch.int64, device=dev) if sizes is None else sizes[0]
     _lib.call("td_paste_plan", _ptr(boxes_net), _ptr(inst_tile), _ptr(tile_dims), n, tile_dims.shape[0],
-              _ptr(boxes_px), _ptr(win), _ptr(nwords), _stream())
+              _ptr(boxes_px), _ptr(win), _ptr(nwords), None if sizes is None else _ptr(sizes[1]), _stream())
     return boxes_px, win, nwords
 
 
@@ -109,7 +110,7 @@ def trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words=None):
     planes = torch.empty((2 * max(total_words, 1),), dtype=torch.int32, device=dev)
     counts = torch.empty((n, 4), dtype=torch.int32, device=dev)
     _lib.call("td_trace_count", _ptr(bits), _ptr(win), _ptr(word_off), n, total_words, _ptr(planes), _ptr(counts),
-              _stream())
+              None, _stream())
     c64 = counts.to(torch.int64)
     # one exclusive scan over the five per-instance sizes (rows of a (5, n) tensor, scanned along
     # the contiguous dimension), one read back for the totals
@@ -147,8 +148,9 @@ def trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
     cw, cpx, cc, cp, cr, cv = (int(caps[k]) for k in ("words", "px", "contours", "points", "rings", "verts"))
     planes = torch.empty((2 * max(cw, 1),), dtype=torch.int32, device=dev)
     counts = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    _lib.call("td_trace_count", _ptr(bits), _ptr(win), _ptr(word_off), n, cw, _ptr(planes), _ptr(counts), _stream())
-    sizes = counts.t().to(torch.int64).contiguous()
+    sizes = torch.empty((4, n), dtype=torch.int64, device=dev)
+    _lib.call("td_trace_count", _ptr(bits), _ptr(win), _ptr(word_off), n, cw, _ptr(planes), _ptr(counts), _ptr(sizes),
+              _stream())
     offs, _ = scan_clamp(sizes, [cc, cp, cr, cv], flag, totals=totals)
     labels = torch.empty((max(cpx, 1),), dtype=torch.int16, device=dev)
     ct_int = torch.empty((6 * max(cc, 1),), dtype=torch.int32, device=dev)
@@ -392,6 +394,17 @@ def select_crowns(bounds, max_h, ndvi_stats, area, num_contained, is_contained, 
     _lib.call("td_select_crowns", _ptr(bounds), _ptr(max_h), _ptr(ndvi_stats), _ptr(area), _ptr(num_contained),
               _ptr(is_contained), n, p.data_ptr(), _ptr(pre), _ptr(out_idx), _ptr(n_dev), _stream())
     return pre, out_idx
+
+
+def select_head(conf, area, conf_thr, area_min, area_max, n_dev=None):
+    """P9 head: (flags u8 (N,), poly_id i64 (N,)); see td_select_head."""
+    n = conf.shape[0]
+    _chk(conf, torch.float64, "conf"); _chk(area, torch.float64, "area")
+    flags = torch.empty((n,), dtype=torch.uint8, device=conf.device)
+    pid = torch.empty((n,), dtype=torch.int64, device=conf.device)
+    _lib.call("td_select_head", _ptr(conf), _ptr(area), n, _ptr(n_dev), float(conf_thr), float(area_min),
+              float(area_max), _ptr(flags), _ptr(pid), _stream())
+    return flags, pid
 
 
 def round_coords(verts):

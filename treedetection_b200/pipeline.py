@@ -260,9 +260,9 @@ def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, t
                       caps: dict, ctr: torch.Tensor) -> DynTable:
     """P2 + P3 + P4 without host synchronisation (see the section comment)."""
     flag = ctr[CTR_FLAG:CTR_FLAG + 1]
-    boxes_px, win, nwords = ops.paste_plan(boxes_net, inst_tile, tile_dims)
-    npx = win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64)
-    offs1, _ = ops.scan_clamp(torch.stack([nwords, npx]), [caps["words"], caps["px"]], flag, win_zero=win,
+    sizes1 = torch.empty((2, boxes_net.shape[0]), dtype=torch.int64, device=boxes_net.device)
+    boxes_px, win, _ = ops.paste_plan(boxes_net, inst_tile, tile_dims, sizes=sizes1)
+    offs1, _ = ops.scan_clamp(sizes1, [caps["words"], caps["px"]], flag, win_zero=win,
                               totals=ctr[CTR_WORDS:CTR_PX + 1])
     word_off, px_off = offs1[0], offs1[1]
     bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, int(caps["words"]))
@@ -292,14 +292,12 @@ def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, cap
     cap_v = table.verts.shape[0]
     flag = ctr[CTR_FLAG:CTR_FLAG + 1]
     n0 = table.n_dev
-    valid = torch.arange(cap, device=dev) < n0
-    conf_ok = (table.conf >= p.confidence_threshold) & valid
     s2 = ops.simplify_rings(table.verts, table.ring_off, 2.0, want_bounds=True, want_area=True, bounds_of_input=True,
                             n_dev=n0)
     area_all = s2["area"]
-    pid_all = torch.cumsum(conf_ok.to(torch.int64), 0) - 1
+    flags1, pid_all = ops.select_head(table.conf, area_all, p.confidence_threshold, p.area_threshold, 1000.0, n_dev=n0)
     n1 = ctr[CTR_N1:CTR_N1 + 1]
-    sel1, _ = ops.compact_flags(conf_ok & (area_all >= p.area_threshold) & (area_all <= 1000), count=n1)
+    sel1, _ = ops.compact_flags(flags1, count=n1)
     verts1, off1 = ops.take_rings_dyn(table.verts, table.ring_off, sel1, n1, cap_v)
     conf1, area1, pid1, b1 = ops.gather_rows([table.conf, area_all, pid_all, s2["bounds"]], sel1, n1)
     removed = ops.bbox_nms_ordered_dyn(b1, conf1, area1, n1, p.iou_threshold, p.area_threshold,
