@@ -238,15 +238,28 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
     co.argmax_first(maxd, far);
     if (maxd > tol) valid = false;
     if (valid) {
+      // The segments next to the section share an end point with its chord (A or B).  Two segments
+      // that share an end point and are not collinear meet in that point only, which is interior to
+      // neither: interior_intersection is false (its "touching" branch picks the shared point).
+      // One exact orientation decides that; only collinear neighbours take the full predicate.
+      auto touches_only = [&](const P2& other) {
+        return orientation(A.x, A.y, B.x, B.y, other.x, other.y) != 0;
+      };
       bool bad = false;
-      for (int k = lane; k < m; k += nl)
-        if (flat[k] && !bad) bad = interior_intersection(pts[res[k]], pts[flat[k] - 1], A, B);
+      for (int k = lane; k < m; k += nl) {
+        if (!flat[k] || bad) continue;
+        const int u = res[k], v = flat[k] - 1;
+        if (v == i && touches_only(pts[u])) continue;          // output segment ending in A
+        bad = interior_intersection(pts[u], pts[v], A, B);
+      }
       bad = co.any(bad);
       if (!bad) {
         for (int k = lane; k < nseg; k += nl) {
           if (bad) break;
           if (!((alive[k >> 5] >> (k & 31)) & 1u)) continue;
           if (k >= i && k < j) continue;
+          if (k == j && touches_only(pts[k + 1])) continue;    // input segment starting in B
+          if (k + 1 == i && touches_only(pts[k])) continue;    // input segment ending in A
           bad = interior_intersection(pts[k], pts[k + 1], A, B);
         }
         bad = co.any(bad);
