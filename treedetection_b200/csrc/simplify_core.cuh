@@ -50,6 +50,10 @@ TD_HD inline int grow_expansion(double* e, int n, double v) {
 }
 
 // sign of (ax-cx)(by-cy) - (ay-cy)(bx-cx) evaluated exactly on the double inputs
+// (rare fallback: kept out of line on the device so that the callers stay small)
+#if defined(__CUDACC__)
+__noinline__
+#endif
 TD_HD inline int orientation_exact(double ax, double ay, double bx, double by, double cx, double cy) {
   // = ax*by - ax*cy - cx*by - ay*bx + ay*cx + cy*bx   (cx*cy cancels)
   const double pa[6] = {ax, -ax, -cx, -ay, ay, cy};
