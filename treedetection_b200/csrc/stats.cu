@@ -114,32 +114,36 @@ crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict
   float nmax = 0.f; long long nmaxk = -1;
   double s1 = 0.0, s2 = 0.0; long long cnt = 0;
   if (ww > 0 && wh > 0 && !isnan(r)) {
-    const long long total = (long long)ww * wh;
-    for (long long k = lane; k < total; k += 32) {
-      const int rr = r_lo + (int)(k / ww), cc = c_lo + (int)(k % ww);
-      const double xd = T.a * (double)cc + T.b * (double)rr + T.c;
-      const double yd = T.d * (double)cc + T.e * (double)rr + T.f;
-      const long long flat = (long long)rr * cols + cc;
-      if (MODE == kHeightOnly) {
-        const double dx = xd - (double)cx, dy = yd - (double)cy;
-        const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        if (d2 <= (double)r2_h) {
-          const float v = height[flat];
-          if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
-        }
-      } else {
-        const float x = __double2float_rn(xd), y = __double2float_rn(yd);
-        const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy);
-        const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-        if (MODE == kCombined && d2 <= r2_h) {
-          const float v = height[flat];
-          if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
-        }
-        if (d2 <= r2_n) {
-          const float v = ndvi[flat];
-          if (better_min(v, flat, nmin, nmink)) { nmin = v; nmink = flat; }
-          if (better_max(v, flat, nmax, nmaxk)) { nmax = v; nmaxk = flat; }
-          s1 += (double)v; s2 += (double)v * (double)v; ++cnt;
+    // rows outer, lanes over the columns of a row (no per-pixel division); the arithmetic of the
+    // pixel coordinates is the reference's, with the row terms hoisted (same operations, same rounding)
+    for (int rr = r_lo; rr <= r_hi; ++rr) {
+      const double brr = T.b * (double)rr, err = T.e * (double)rr;
+      const long long row_flat = (long long)rr * cols;
+      for (int cc = c_lo + lane; cc <= c_hi; cc += 32) {
+        const double xd = T.a * (double)cc + brr + T.c;
+        const double yd = T.d * (double)cc + err + T.f;
+        const long long flat = row_flat + cc;
+        if (MODE == kHeightOnly) {
+          const double dx = xd - (double)cx, dy = yd - (double)cy;
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (d2 <= (double)r2_h) {
+            const float v = height[flat];
+            if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
+          }
+        } else {
+          const float x = __double2float_rn(xd), y = __double2float_rn(yd);
+          const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy);
+          const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+          if (MODE == kCombined && d2 <= r2_h) {
+            const float v = height[flat];
+            if (better_max(v, flat, bh, bhk)) { bh = v; bhk = flat; }
+          }
+          if (d2 <= r2_n) {
+            const float v = ndvi[flat];
+            if (better_min(v, flat, nmin, nmink)) { nmin = v; nmink = flat; }
+            if (better_max(v, flat, nmax, nmaxk)) { nmax = v; nmaxk = flat; }
+            s1 += (double)v; s2 += (double)v * (double)v; ++cnt;
+          }
         }
       }
     }
