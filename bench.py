@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
+    ap.add_argument("--strip-last", action="store_true", help="N > 1: enqueue the seam strip after the image's chain")
     ap.add_argument("--no-alone", action="store_true",
                     help="do not time the roofline kernel alone after the timed region (profiling runs: keeps the "
                          "launch list to whole steps); the roofline entry then uses the in-step time")
@@ -352,9 +353,14 @@ def run_b200(a):
                 e[0].record()
                 tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
                 e[1].record()
+            # the strip's ~130 small dependent launches go in first: they run under P1 while the host is
+            # still enqueuing, instead of queueing behind the image's big kernels
+            if world > 1 and not a.strip_last:
+                with torch.cuda.stream(strip_stream):
+                    ts = step_strip()
             with torch.cuda.stream(chain_stream):
                 t = chain(e)
-            if world > 1:
+            if world > 1 and a.strip_last:
                 with torch.cuda.stream(strip_stream):
                     ts = step_strip()
             for st in (p1_stream, chain_stream, strip_stream):
