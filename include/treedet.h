@@ -70,7 +70,8 @@ int td_tile_cut_normalize(const void* plan, const void* image, int bands, float*
  *      box is empty and the instance is dropped), nwords (N) i64 = ceil(w/32)*h      */
 int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst, int n_tiles,
                   float* boxes_px, int* win, long long* nwords, long long* npx, void* stream);
-/*   npx (N) i64, may be null: w*h of every window (sizes the label plane of td_trace_emit)       */
+/*   npx (2,N) i64, may be null: row 0 = w*h of every window (label plane of td_trace_emit / _walk),
+ *   row 1 = the instance's point slot for td_trace_walk, 4*(w+h)+64 (0 for dropped instances)     */
 /*   word_off (N+1) i64 = exclusive scan of nwords; probs (N,28,28) f32 probabilities;
  *   bits: packed 1-bit rasters, row-major, 32 pixels per uint32 (LSB = leftmost)       */
 int td_paste_threshold_pack(const float* boxes_px, const int* win, const long long* word_off, const float* probs,
@@ -101,6 +102,21 @@ int td_trace_emit(const uint32_t* bits, const int* win, const long long* word_of
                   const long long* vert_base, int* ct_int, unsigned char* ct_hole, short* pts,
                   long long total_contours, const int* inst_tile, const double* tile_tf, long long* ring_off,
                   int* ring_inst, double* verts, void* stream);
+
+/*   Single-pass form for the sync-free chain: the walk writes into per-instance slots (cap_contours
+ *   table rows at i*cap_contours, points at pts_off[i]..pts_off[i+1]) and counts at the same time;
+ *   an instance that outgrows its slot raises bit 2 of *flag.  ct_int6: 6*N*cap_contours i32,
+ *   ct_hole: N*cap_contours u8, pts: 2*pts_off[N] i16, counts (N,4) i32, sizes_kn (2,N) i64 = [kept
+ *   rings, ring vertices].  td_trace_rings turns the slots into the outputs of td_trace_emit given
+ *   ring_base / vert_base = exclusive scans of sizes_kn.                                          */
+int td_trace_walk(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
+                  long long total_words, uint32_t* planes, unsigned short* labels, const long long* px_off,
+                  const long long* pts_off, int cap_contours, int* ct_int6, unsigned char* ct_hole, short* pts,
+                  int* counts, long long* sizes_kn, long long* flag, void* stream);
+int td_trace_rings(const int* win, int n_inst, const int* counts, const long long* pts_off, int cap_contours,
+                   int* ct_int6, const unsigned char* ct_hole, const short* pts, const long long* ring_base,
+                   const long long* vert_base, const int* inst_tile, const double* tile_tf, long long* ring_off,
+                   int* ring_inst, double* verts, void* stream);
 
 /* ---- P4 (+ the area of P9's head): simplify, tile box filter ---------------------------------
  * Replaces process_prediction_file_sync (TreeDetection/helpers.py:419-476: shapely

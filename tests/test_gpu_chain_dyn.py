@@ -64,7 +64,7 @@ def test_dyn_chain_other_image_same_capacities(dev):
     _same(f, ref)
 
 
-@pytest.mark.parametrize("small", ["words", "px", "contours", "points", "rings", "verts", "nbr"])
+@pytest.mark.parametrize("small", ["words", "px", "ptslots", "rings", "verts", "nbr"])
 def test_capacity_overflow_falls_back(dev, small):
     sc, det, tile_tf, tile_boxes, rasters, p = _setup(dev, 31, size_px=1000)
     table = pipeline.predict_stage(**det, tile_tf=tile_tf, tile_boxes=tile_boxes, p=p)

@@ -78,6 +78,32 @@ def test_trace_rings_noise_masks_match_cv2(dev):
     np.testing.assert_array_equal(inst, np.array(want_inst))
     for a, b in zip(got, want):
         assert a == [tuple(q) for q in b]
+    # the single-pass form (one walk into per-instance slots): identical rings when the slots are big
+    # enough, bit 2 of the flag when an instance outgrows its slot (noise masks have hundreds of borders)
+    d_win = torch.tensor(win, dtype=torch.int32, device=dev)
+    d_off = torch.from_numpy(off).to(dev)
+    hw = np.array([[m.shape[1], m.shape[0]] for m in masks], dtype=np.int64)
+    px_off = np.zeros(len(masks) + 1, dtype=np.int64); px_off[1:] = np.cumsum(hw[:, 0] * hw[:, 1])
+    for slot_pts, slot_contours, expect_flag in [(20000, 4096, 0), (4 * 220 + 64, 16, 4)]:
+        slot_off = torch.arange(len(masks) + 1, dtype=torch.int64, device=dev) * slot_pts
+        caps = {"words": int(off[-1]), "px": int(px_off[-1]), "ptslots": slot_pts * len(masks),
+                "rings": len(want) + 5, "verts": int(rings.verts.shape[0]) + 7}
+        flag = torch.zeros(1, dtype=torch.int64, device=dev)
+        totals = torch.zeros(2, dtype=torch.int64, device=dev)
+        old = ops.TRACE_SLOT_CONTOURS
+        ops.TRACE_SLOT_CONTOURS = slot_contours
+        try:
+            r2 = ops.trace_rings_slots(bits, d_win, d_off, torch.from_numpy(px_off).to(dev), slot_off,
+                                       torch.zeros(len(masks), dtype=torch.int32, device=dev),
+                                       torch.tensor([tf], dtype=torch.float64, device=dev), caps, flag, totals)
+        finally:
+            ops.TRACE_SLOT_CONTOURS = old
+        assert int(flag) == expect_flag
+        if expect_flag == 0:
+            nr, nv = [int(v) for v in totals.tolist()]
+            assert nr == len(want) and nv == rings.verts.shape[0]
+            assert torch.equal(r2.verts[:nv], rings.verts) and torch.equal(r2.ring_off[:nr + 1], rings.ring_off)
+            assert torch.equal(r2.ring_inst[:nr], rings.ring_inst)
 
 
 @pytest.mark.parametrize("name", ["combined", "split"])

@@ -32,6 +32,8 @@ SIGNATURES = {
     "td_trace_count": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p]),
     "td_trace_emit": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p,
                            _p]),
+    "td_trace_walk": (_i, [_p, _p, _p, _i, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "td_trace_rings": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     # P4 / P9 geometry
     "td_simplify_rings": (_i, [_p, _p, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "td_take_rings": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p]),
@@ -71,7 +73,7 @@ SIGNATURES = {
 # hand-written kernels launched per call (library kernels -- CUB sort / scan -- not counted);
 # bench.py reports the sum over the timed region as ``gpu_launches``
 OWN_KERNELS = {
-    "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 2,
+    "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 2, "td_trace_walk": 1, "td_trace_rings": 1,
     "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
     "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 2, "td_compact_flags": 1, "td_compact_nonneg": 1,
     "td_ring_tail": 1, "td_ring_offsets": 0, "td_gather_rows": 1, "td_containment": 4, "td_crown_stats": 1, "td_centroids": 2, "td_select_crowns": 2,

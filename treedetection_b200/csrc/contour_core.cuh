@@ -31,6 +31,10 @@ struct ContourOut {
   int* pt_off;        // per contour: offset of its first point (relative to the instance)
   unsigned char* is_hole;
   short* pts;         // (x, y) pairs, window-relative
+  // capacities of the tables above (single-pass walk into per-instance slots): contours / points
+  // beyond them are counted but not stored
+  int cap_contours = 0x7fffffff;
+  int cap_points = 0x7fffffff;
 };
 
 struct ContourCounts {

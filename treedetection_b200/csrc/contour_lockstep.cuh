@@ -65,7 +65,7 @@ TD_HD inline uint32_t neighbours(const RasterT<LabelT>& R, int x, int y) {
 
 template <typename LabelT>
 TD_HD inline void lane_emit(LaneState<LabelT>& S, int x, int y) {
-  if (S.out) {
+  if (S.out && S.cc.n_points + S.npts < S.out->cap_points) {
     short* p = S.out->pts + 2 * ((size_t)S.cc.n_points + S.npts);
     p[0] = (short)x;
     p[1] = (short)y;
@@ -79,7 +79,7 @@ TD_HD inline void lane_emit(LaneState<LabelT>& S, int x, int y) {
 template <typename LabelT>
 TD_HD inline void lane_finish_border(LaneState<LabelT>& S) {
   const int idx = S.cc.n_contours;
-  if (S.out) {
+  if (S.out && idx < S.out->cap_contours) {
     S.out->parent[idx] = S.parent;
     S.out->npts[idx] = S.npts;
     S.out->pt_off[idx] = S.cc.n_points;
@@ -161,7 +161,7 @@ TD_HD inline void lane_step(LaneState<LabelT>& S) {
     int parent = -1;
     if (S.out) {
       const int ln = R.lnbd(hole ? x + 1 : x, y);
-      if (ln >= 0) {
+      if (ln >= 0 && ln < S.out->cap_contours) {
         parent = ln;
         if ((S.out->is_hole[ln] != 0) == hole) parent = S.out->parent[ln];
       }

@@ -218,6 +218,119 @@ __global__ void __launch_bounds__(256) trace_rings_kernel(EmitArgs A) {
   }
 }
 
+// ---- single pass into per-instance capacity slots (the sync-free chain) ------------------------------
+// The two-pass form walks every border twice because the exact sizes must be known before the
+// outputs are allocated.  With capacity buffers the walk can write into a SLOT per instance --
+// cap_contours table rows at i * cap_contours, points at pts_off[i] .. pts_off[i + 1] -- and count
+// at the same time; an instance that outgrows its slot is counted to the end but not stored and
+// raises bit 2 of *flag (the caller then redoes the image through the exact two-pass form).
+struct WalkArgs {
+  const uint32_t* bits;
+  const int* win;
+  const long long* word_off;
+  int n;
+  uint32_t* planes;
+  long long total_words;
+  unsigned short* labels;
+  const long long* px_off;
+  const long long* pts_off;    // (n+1) point slots
+  int cap_contours;
+  int* ct_parent;              // n * cap_contours each
+  int* ct_npts;
+  int* ct_ptoff;
+  unsigned char* ct_hole;
+  int* ct_scratch;             // 3 * n * cap_contours
+  short* pts;
+  int* counts;                 // (n, 4)
+  long long* sizes_kn;         // (2, n): kept rings, ring vertices
+  long long* flag;
+  const long long* ring_base;  // (n+1), second kernel
+  const long long* vert_base;
+  const int* inst_tile;
+  const double* tile_tf;
+  long long* ring_off;
+  int* ring_inst;
+  double* verts;
+  int smem_bytes;
+};
+
+__global__ void __launch_bounds__(32) trace_walk_kernel(WalkArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool active = i < A.n;
+  td::LaneState<unsigned short> S;
+  stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem, A.smem_bytes);
+  const size_t c0 = (size_t)(active ? i : 0) * A.cap_contours;
+  td::ContourOut out;
+  out.parent = A.ct_parent + c0;
+  out.npts = A.ct_npts + c0;
+  out.pt_off = A.ct_ptoff + c0;
+  out.is_hole = A.ct_hole + c0;
+  const long long p0 = active ? A.pts_off[i] : 0;
+  out.pts = A.pts + 2 * p0;
+  out.cap_contours = A.cap_contours;
+  out.cap_points = active ? (int)(A.pts_off[i + 1] - p0) : 0;
+  if (active) S.R.label = A.labels + A.px_off[i];
+  td::lane_init(S, &out);
+  while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
+  if (!active) return;
+  const bool over = S.cc.n_contours < 0 || S.cc.n_contours > out.cap_contours || S.cc.n_points > out.cap_points;
+  if (over) atomicOr((unsigned long long*)A.flag, 4ull);
+  A.counts[4 * i + 0] = over ? 0 : S.cc.n_contours;
+  A.counts[4 * i + 1] = over ? 0 : S.cc.n_points;
+  A.counts[4 * i + 2] = over ? 0 : S.cc.n_rings;
+  A.counts[4 * i + 3] = over ? 0 : S.cc.n_ring_verts;
+  A.sizes_kn[i] = over ? 0 : S.cc.n_rings;
+  A.sizes_kn[(size_t)A.n + i] = over ? 0 : S.cc.n_ring_verts;
+}
+
+// slot form of trace_rings_kernel: one warp per instance
+__global__ void __launch_bounds__(256) trace_rings_slots_kernel(WalkArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= A.n) return;
+  const int nc = A.counts[4 * i];
+  if (nc <= 0) return;
+  // instances truncated by the capacity clamp of the ring / vertex scans emit nothing
+  if (A.ring_base[i + 1] - A.ring_base[i] != A.counts[4 * i + 2] ||
+      A.vert_base[i + 1] - A.vert_base[i] != A.counts[4 * i + 3]) return;
+  const size_t c0 = (size_t)i * A.cap_contours;
+  const int* parent = A.ct_parent + c0;
+  const int* npts = A.ct_npts + c0;
+  const int* pt_off = A.ct_ptoff + c0;
+  const short* pts = A.pts + 2 * A.pts_off[i];
+  int* last_child = A.ct_scratch + 3 * c0;
+  int* prev_sib = last_child + nc;
+  int* order = prev_sib + nc;
+  if (lane == 0) td::contour_order(nc, parent, last_child, prev_sib, order);
+  __syncwarp();
+  const int wx0 = A.win[4 * i + 0], wy0 = A.win[4 * i + 1];
+  const double* tf = A.tile_tf + 6 * (size_t)A.inst_tile[i];
+  const double ta = tf[0], tb = tf[1], tc = tf[2], td_ = tf[3], te = tf[4], tff = tf[5];
+  long long ring = A.ring_base[i];
+  long long v = A.vert_base[i];
+  for (int k = 0; k < nc; ++k) {
+    const int c = order[k];
+    const int np = npts[c];
+    if (np < 4) continue;
+    const short* p = pts + 2 * (size_t)pt_off[c];
+    const bool close = (p[0] != p[2 * (np - 1)]) || (p[1] != p[2 * (np - 1) + 1]);
+    const int nv = np + (close ? 1 : 0);
+    if (lane == 0) {
+      A.ring_off[ring] = v;
+      A.ring_inst[ring] = i;
+    }
+    for (int q = lane; q < nv; q += 32) {
+      const int qq = q < np ? q : 0;
+      const double col = (double)(p[2 * qq] + wx0), row = (double)(p[2 * qq + 1] + wy0);
+      A.verts[2 * (v + q)] = __dadd_rn(__dadd_rn(__dmul_rn(ta, col), __dmul_rn(tb, row)), tc);
+      A.verts[2 * (v + q) + 1] = __dadd_rn(__dadd_rn(__dmul_rn(td_, col), __dmul_rn(te, row)), tff);
+    }
+    ++ring;
+    v += nv;
+  }
+}
+
 }  // namespace
 
 // planes: scratch of 2 * total_words uint32, zeroed by this call.
@@ -264,5 +377,55 @@ extern "C" int td_trace_emit(const uint32_t* bits, const int* win, const long lo
   trace_emit_kernel<<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
   trace_rings_kernel<<<td_div_up((long long)n_inst * 32, 256), 256, 0, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_emit");
+  return TD_OK;
+}
+
+// Single-pass walk into capacity slots (see trace_walk_kernel).  ct_int6: 6 * n_inst * cap_contours i32
+// (parent, npts, ptoff, 3 x scratch), ct_hole: n_inst * cap_contours u8, pts: 2 * pts_off[n_inst] i16,
+// counts (N,4) i32 out, sizes_kn (2,N) i64 out = [kept rings, ring vertices], flag: bit 2 raised when an
+// instance outgrew its slot.  planes (2 * total_words) is zeroed by the call.
+extern "C" int td_trace_walk(const uint32_t* bits, const int* win, const long long* word_off, int n_inst,
+                             long long total_words, uint32_t* planes, unsigned short* labels,
+                             const long long* px_off, const long long* pts_off, int cap_contours, int* ct_int6,
+                             unsigned char* ct_hole, short* pts, int* counts, long long* sizes_kn, long long* flag,
+                             void* stream) {
+  TD_ARG(n_inst >= 0 && total_words >= 0 && cap_contours > 0);
+  if (n_inst == 0) return TD_OK;
+  TD_ARG(bits && win && word_off && planes && labels && px_off && pts_off && ct_int6 && ct_hole && pts && counts &&
+         sizes_kn && flag);
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_CUDA(cudaMemsetAsync(planes, 0, sizeof(uint32_t) * 2 * (size_t)total_words, st));
+  WalkArgs A = {};
+  const size_t nc = (size_t)n_inst * cap_contours;
+  A.bits = bits; A.win = win; A.word_off = word_off; A.n = n_inst; A.planes = planes; A.total_words = total_words;
+  A.labels = labels; A.px_off = px_off; A.pts_off = pts_off; A.cap_contours = cap_contours;
+  A.ct_parent = ct_int6; A.ct_npts = ct_int6 + nc; A.ct_ptoff = ct_int6 + 2 * nc; A.ct_scratch = ct_int6 + 3 * nc;
+  A.ct_hole = ct_hole; A.pts = pts; A.counts = counts; A.sizes_kn = sizes_kn; A.flag = flag;
+  A.smem_bytes = smem_per_warp(n_inst);
+  trace_walk_kernel<<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
+  TD_CHECK_LAUNCH("td_trace_walk");
+  return TD_OK;
+}
+
+// Second half of the single-pass form: slots -> closed CRS rings (ring_base / vert_base = scans of
+// sizes_kn; instances the scans truncated emit nothing).  Same outputs as td_trace_emit.
+extern "C" int td_trace_rings(const int* win, int n_inst, const int* counts, const long long* pts_off,
+                              int cap_contours, int* ct_int6, const unsigned char* ct_hole, const short* pts,
+                              const long long* ring_base, const long long* vert_base, const int* inst_tile,
+                              const double* tile_tf, long long* ring_off, int* ring_inst, double* verts,
+                              void* stream) {
+  TD_ARG(n_inst >= 0 && cap_contours > 0);
+  if (n_inst == 0) return TD_OK;
+  TD_ARG(win && counts && pts_off && ct_int6 && ct_hole && pts && ring_base && vert_base && inst_tile && tile_tf &&
+         ring_off && ring_inst && verts);
+  WalkArgs A = {};
+  const size_t nc = (size_t)n_inst * cap_contours;
+  A.win = win; A.n = n_inst; A.counts = const_cast<int*>(counts); A.pts_off = pts_off; A.cap_contours = cap_contours;
+  A.ct_parent = ct_int6; A.ct_npts = ct_int6 + nc; A.ct_ptoff = ct_int6 + 2 * nc; A.ct_scratch = ct_int6 + 3 * nc;
+  A.ct_hole = const_cast<unsigned char*>(ct_hole); A.pts = const_cast<short*>(pts);
+  A.ring_base = ring_base; A.vert_base = vert_base; A.inst_tile = inst_tile; A.tile_tf = tile_tf;
+  A.ring_off = ring_off; A.ring_inst = ring_inst; A.verts = verts;
+  trace_rings_slots_kernel<<<td_div_up((long long)n_inst * 32, 256), 256, 0, (cudaStream_t)stream>>>(A);
+  TD_CHECK_LAUNCH("td_trace_rings");
   return TD_OK;
 }

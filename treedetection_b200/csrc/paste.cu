@@ -68,7 +68,10 @@ __global__ void paste_plan_kernel(const float* __restrict__ boxes_net, const int
   win[4 * i + 2] = ww;
   win[4 * i + 3] = wh;
   nwords[i] = (long long)((ww + 31) >> 5) * (long long)wh;
-  if (npx) npx[i] = (long long)ww * (long long)wh;
+  if (npx) {   // (2, n): label-plane pixels; point slot of the single-pass border walk (td_trace_walk)
+    npx[i] = (long long)ww * (long long)wh;
+    npx[(size_t)n + i] = ww > 0 && wh > 0 ? 4ll * (ww + wh) + 64 : 0;
+  }
 }
 
 // one axis of the sampling grid: pixel centre -> tap index and the two weights

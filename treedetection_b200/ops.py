@@ -41,7 +41,8 @@ def paste_plan(boxes_net, inst_tile, tile_dims, sizes=None):
     """boxes_net (N,4) f32 in network-input pixels, inst_tile (N,) i32, tile_dims
     (T,4) i32 = [tile_h, tile_w, net_h, net_w].  Returns boxes_px (N,4) f32, win
     (N,4) i32 = [x0, y0, w, h] (w = h = 0 for dropped instances), nwords (N,) i64.
-    ``sizes``: optional (2,N) i64 buffer receiving [nwords, w*h] (``nwords`` is then its first row)."""
+    ``sizes``: optional (3,N) i64 buffer receiving [nwords, w*h, point slot] (``nwords`` is then its
+    first row; the point slot sizes the single-pass border walk, :func:`trace_rings_slots`)."""
     n = boxes_net.shape[0]
     dev = boxes_net.device
     _chk(boxes_net, torch.float32, "boxes_net"); _chk(inst_tile, torch.int32, "inst_tile")
@@ -164,6 +165,40 @@ def trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
               _ptr(ct_hole), _ptr(pts), cc, _ptr(inst_tile), _ptr(tile_tf), _ptr(ring_off), _ptr(ring_inst),
               _ptr(verts), _stream())
     _lib.call("td_ring_tail", _ptr(ring_off), _ptr(ring_inst), cr + 1, _ptr(totals[2:3]), _ptr(totals[3:4]), _stream())
+    return Rings(verts, ring_off, ring_inst)
+
+
+TRACE_SLOT_CONTOURS = 16     # contour table rows per instance of the single-pass walk
+
+
+def trace_rings_slots(bits, win, word_off, px_off, slot_off, inst_tile, tile_tf, caps, flag, totals):
+    """Single-pass capacity form of :func:`trace_rings`: ONE border walk into per-instance slots
+    (td_trace_walk), a scan of the ring / vertex counts, then td_trace_rings.  ``slot_off`` (N+1,):
+    point slots; ``caps``: words, px, ptslots, rings, verts; ``totals`` (2,) i64 device slot receiving
+    the live [rings, vertices].  An instance that outgrows its slot raises bit 2 of ``flag``."""
+    n = win.shape[0]
+    dev = win.device
+    _chk(tile_tf, torch.float64, "tile_tf")
+    cw, cpx, cps, cr, cv = (int(caps[k]) for k in ("words", "px", "ptslots", "rings", "verts"))
+    cc = TRACE_SLOT_CONTOURS
+    planes = torch.empty((2 * max(cw, 1),), dtype=torch.int32, device=dev)
+    labels = torch.empty((max(cpx, 1),), dtype=torch.int16, device=dev)
+    ct_int = torch.empty((6 * max(n * cc, 1),), dtype=torch.int32, device=dev)
+    ct_hole = torch.empty((max(n * cc, 1),), dtype=torch.uint8, device=dev)
+    pts = torch.empty((2 * max(cps, 1),), dtype=torch.int16, device=dev)
+    counts = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    sizes = torch.empty((2, n), dtype=torch.int64, device=dev)
+    _lib.call("td_trace_walk", _ptr(bits), _ptr(win), _ptr(word_off), n, cw, _ptr(planes), _ptr(labels), _ptr(px_off),
+              _ptr(slot_off), cc, _ptr(ct_int), _ptr(ct_hole), _ptr(pts), _ptr(counts), _ptr(sizes), _ptr(flag),
+              _stream())
+    offs, _ = scan_clamp(sizes, [cr, cv], flag, totals=totals)
+    ring_off = torch.empty((cr + 2,), dtype=torch.int64, device=dev)
+    ring_inst = torch.empty((cr + 1,), dtype=torch.int32, device=dev)
+    verts = torch.empty((max(cv, 1), 2), dtype=torch.float64, device=dev)
+    _lib.call("td_trace_rings", _ptr(win), n, _ptr(counts), _ptr(slot_off), cc, _ptr(ct_int), _ptr(ct_hole), _ptr(pts),
+              _ptr(offs[0]), _ptr(offs[1]), _ptr(inst_tile), _ptr(tile_tf), _ptr(ring_off), _ptr(ring_inst),
+              _ptr(verts), _stream())
+    _lib.call("td_ring_tail", _ptr(ring_off), _ptr(ring_inst), cr + 1, _ptr(totals[0:1]), _ptr(totals[1:2]), _stream())
     return Rings(verts, ring_off, ring_inst)
 
 

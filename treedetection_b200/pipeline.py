@@ -239,8 +239,10 @@ def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_
 # path; an overflow of any capacity raises bit 0 / 1 of the flag and the image is redone
 # with exact sizes.
 # ======================================================================================
-CTR_FLAG, CTR_WORDS, CTR_PX, CTR_CONT, CTR_PTS, CTR_RINGS, CTR_VERTS = 0, 1, 2, 3, 4, 5, 6
-CTR_NTABLE, CTR_VTABLE, CTR_N1, CTR_N2, CTR_NFINAL, CTR_VFINAL, CTR_SIZE = 7, 8, 9, 10, 11, 12, 16
+CTR_FLAG, CTR_WORDS, CTR_PX, CTR_SLOTS, CTR_CONT, CTR_PTS, CTR_RINGS, CTR_VERTS = 0, 1, 2, 3, 4, 5, 6, 7
+CTR_NTABLE, CTR_VTABLE, CTR_N1, CTR_N2, CTR_NFINAL, CTR_VFINAL, CTR_SIZE = 8, 9, 10, 11, 12, 13, 16
+# the border walk of the capacity form: one pass into per-instance slots (default) or count + emit
+TRACE_TWO_PASS = bool(__import__("os").environ.get("TREEDET_TRACE_TWO_PASS"))
 
 
 @dataclass
@@ -260,14 +262,18 @@ def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, t
                       caps: dict, ctr: torch.Tensor) -> DynTable:
     """P2 + P3 + P4 without host synchronisation (see the section comment)."""
     flag = ctr[CTR_FLAG:CTR_FLAG + 1]
-    sizes1 = torch.empty((2, boxes_net.shape[0]), dtype=torch.int64, device=boxes_net.device)
+    sizes1 = torch.empty((3, boxes_net.shape[0]), dtype=torch.int64, device=boxes_net.device)
     boxes_px, win, _ = ops.paste_plan(boxes_net, inst_tile, tile_dims, sizes=sizes1)
-    offs1, _ = ops.scan_clamp(sizes1, [caps["words"], caps["px"]], flag, win_zero=win,
-                              totals=ctr[CTR_WORDS:CTR_PX + 1])
-    word_off, px_off = offs1[0], offs1[1]
+    offs1, _ = ops.scan_clamp(sizes1, [caps["words"], caps["px"], caps["ptslots"]], flag, win_zero=win,
+                              totals=ctr[CTR_WORDS:CTR_SLOTS + 1])
+    word_off, px_off, slot_off = offs1[0], offs1[1], offs1[2]
     bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, int(caps["words"]))
-    rings = ops.trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
-                                ctr[CTR_CONT:CTR_VERTS + 1])
+    if TRACE_TWO_PASS:
+        rings = ops.trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
+                                    ctr[CTR_CONT:CTR_VERTS + 1])
+    else:      # one border walk into per-instance slots
+        rings = ops.trace_rings_slots(bits, win, word_off, px_off, slot_off, inst_tile, tile_tf, caps, flag,
+                                      ctr[CTR_RINGS:CTR_VERTS + 1])
     n_rings = ctr[CTR_RINGS:CTR_RINGS + 1]
     cap_r = int(caps["rings"])
     ring_inst = rings.ring_inst[:cap_r].long()
@@ -361,7 +367,7 @@ class ChainRunner:
         if self.caps is None:
             self.caps = new
         else:
-            self.caps = {k: max(self.caps[k], new[k]) for k in new}
+            self.caps.update({k: max(self.caps.get(k, 0), new[k]) for k in new})
         self.caps["nbr"] = self.nbr_per_crown * self.caps["rings"]
 
     def _exact(self, det, tile_tf, tile_boxes, rasters_fn):
@@ -370,10 +376,13 @@ class ChainRunner:
         boxes_px, win, nwords = ops.paste_plan(det["boxes_net"], det["inst_tile"], det["tile_dims"])
         word_off = ops.exclusive_offsets(nwords)
         total_words = int(word_off[-1].item())
-        px = int((win[:, 2].to(torch.int64) * win[:, 3].to(torch.int64)).sum().item())
+        w64, h64 = win[:, 2].to(torch.int64), win[:, 3].to(torch.int64)
+        px, slots = [int(v) for v in torch.stack([(w64 * h64).sum(),
+                                                  torch.where(w64 * h64 > 0, 4 * (w64 + h64) + 64, 0).sum()]).tolist()]
         bits = ops.paste_threshold_pack(boxes_px, win, word_off, det["probs"], p.mask_threshold, total_words)
         rings = ops.trace_rings(bits, win, word_off, det["inst_tile"], tile_tf, total_words)
-        sizes = {"words": total_words, "px": px, "contours": rings.n_contours, "points": rings.n_points,
+        sizes = {"words": total_words, "px": px, "ptslots": slots, "contours": rings.n_contours,
+                 "points": rings.n_points,
                  "rings": len(rings), "verts": int(rings.verts.shape[0])}
         self._learn(sizes)
         table = _stitch(rings, det["scores"], det["inst_tile"], tile_boxes, p)
@@ -418,6 +427,9 @@ class ChainRunner:
             if c[CTR_FLAG] & 2:
                 self.nbr_per_crown *= 2
             return self._exact(*again)
-        self._learn({"words": c[CTR_WORDS], "px": c[CTR_PX], "contours": c[CTR_CONT], "points": c[CTR_PTS],
-                     "rings": c[CTR_RINGS], "verts": c[CTR_VERTS]})
+        learnt = {"words": c[CTR_WORDS], "px": c[CTR_PX], "ptslots": c[CTR_SLOTS], "rings": c[CTR_RINGS],
+                  "verts": c[CTR_VERTS]}
+        if TRACE_TWO_PASS:
+            learnt.update(contours=c[CTR_CONT], points=c[CTR_PTS])
+        self._learn(learnt)
         return c[CTR_NTABLE], trim_features(feats, c[CTR_NFINAL], c[CTR_VFINAL])
