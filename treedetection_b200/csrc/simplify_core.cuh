@@ -186,12 +186,20 @@ struct SerialCoop {
 struct WarpCoop {
   __device__ int lane() const { return threadIdx.x & 31; }
   __device__ int size() const { return 32; }
+  // max d (d >= 0, or -1 for a lane without work), lowest k among equal maxima: non-negative doubles
+  // order like their bit patterns, so three warp-wide integer reductions (REDUX) do it
   __device__ void argmax_first(double& d, int& k) const {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, d, o);
-      const int ok = __shfl_xor_sync(0xffffffffu, k, o);
-      if (od > d || (od == d && ok < k)) { d = od; k = ok; }
+    const unsigned full = 0xffffffffu;
+    const unsigned long long bits = d < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(d);
+    const unsigned hi = (unsigned)(bits >> 32);
+    const unsigned mhi = __reduce_max_sync(full, hi);
+    const unsigned lo = hi == mhi ? (unsigned)bits : 0u;
+    const unsigned mlo = __reduce_max_sync(full, lo);
+    const bool top = d >= 0.0 && hi == mhi && (unsigned)bits == mlo;
+    const unsigned kk = __reduce_min_sync(full, top ? (unsigned)k : 0x7fffffffu);
+    if (kk != 0x7fffffffu) {       // some lane had work
+      d = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+      k = (int)kk;
     }
   }
   __device__ bool any(bool b) const { return __any_sync(0xffffffffu, b); }
