@@ -167,6 +167,42 @@ TD_HD inline double point_segment_distance(const P2& p, const P2& A, const P2& B
   return fabs(s) * sqrt(len2);
 }
 
+// The same distance with everything that depends on the segment alone computed once (the farthest-
+// point scan of a section evaluates many points against one chord): identical operations on
+// identical values, so identical results.
+struct SegPrep {
+  P2 A, B;
+  double ux, uy;       // B - A
+  double len2, root;   // |B - A|^2 and its square root
+  bool degenerate;
+};
+TD_HD inline SegPrep prepare_segment(const P2& A, const P2& B) {
+  SegPrep s;
+  s.A = A; s.B = B;
+  s.ux = B.x - A.x; s.uy = B.y - A.y;
+  s.degenerate = (A.x == B.x && A.y == B.y);
+  s.len2 = s.ux * s.ux + s.uy * s.uy;
+  s.root = sqrt(s.len2);
+  return s;
+}
+TD_HD inline double point_segment_distance(const P2& p, const SegPrep& g) {
+  if (g.degenerate) {
+    const double dx = p.x - g.A.x, dy = p.y - g.A.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  const double r = ((p.x - g.A.x) * g.ux + (p.y - g.A.y) * g.uy) / g.len2;
+  if (r <= 0.0) {
+    const double dx = p.x - g.A.x, dy = p.y - g.A.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  if (r >= 1.0) {
+    const double dx = p.x - g.B.x, dy = p.y - g.B.y;
+    return sqrt(dx * dx + dy * dy);
+  }
+  const double s = ((g.A.y - p.y) * g.ux - (g.A.x - p.x) * g.uy) / g.len2;
+  return fabs(s) * g.root;
+}
+
 // ---- cooperation policy ---------------------------------------------------------------------
 // The simplifier is a sequential stack machine, but its two inner loops (farthest point of a
 // section, interior-intersection scan over the segment sets) are data parallel.  `Coop` says
@@ -242,8 +278,9 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
     double maxd = -1.0;
     int far = i;
     const P2 A = pts[i], B = pts[j];
+    const SegPrep chord = prepare_segment(A, B);
     for (int k = i + 1 + lane; k < j; k += nl) {
-      const double d = point_segment_distance(pts[k], A, B);
+      const double d = point_segment_distance(pts[k], chord);
       if (d > maxd) { maxd = d; far = k; }
     }
     if (maxd < 0.0) far = 0x7fffffff;      // lane without work: loses every tie
