@@ -105,3 +105,37 @@ def test_bookkeeping_ops(dev):
     out, cnt = ops.compact_nonneg(v, n_dev=nd)
     want = v[:3000][v[:3000] >= 0].long()
     assert int(cnt) == want.numel() and torch.equal(out[:int(cnt)], want)
+
+
+def test_fused_bookkeeping_ops(dev):
+    """td_ring_offsets, td_gather_rows, td_select_head against their torch compositions"""
+    rng = np.random.default_rng(1)
+    n_rings = 700
+    lens = torch.from_numpy(rng.integers(4, 60, n_rings)).to(dev)
+    ring_off = ops.exclusive_offsets(lens)
+    count = torch.from_numpy(rng.integers(4, 30, n_rings).astype(np.int32)).to(dev)
+    sel = torch.from_numpy(np.sort(rng.choice(n_rings, 300, replace=False))).to(dev)
+    for cnt in (None, count):
+        dst = torch.empty(sel.shape[0] + 1, dtype=torch.int64, device=dev)
+        _ = ops._lib.call("td_ring_offsets", ops._ptr(ring_off), ops._ptr(cnt), ops._ptr(sel), sel.shape[0],
+                          ops._ptr(dst), ops._stream())
+        want = ops.exclusive_offsets((lens if cnt is None else cnt.long())[sel])
+        assert torch.equal(dst, want)
+    arrays = [torch.from_numpy(rng.normal(size=n_rings)).to(dev), torch.from_numpy(rng.normal(size=(n_rings, 4))).to(dev),
+              torch.from_numpy(rng.integers(0, 255, n_rings).astype(np.uint8)).to(dev),
+              torch.from_numpy(rng.normal(size=(n_rings, 2)).astype(np.float32)).to(dev),
+              torch.from_numpy(rng.integers(0, 9, n_rings).astype(np.int32)).to(dev)]
+    nd = torch.tensor([250], dtype=torch.int64, device=dev)
+    outs = ops.gather_rows(arrays, sel, nd)
+    for a, o in zip(arrays, outs):
+        assert o.dtype == a.dtype and torch.equal(o[:250], a[sel][:250])
+    conf = torch.from_numpy(np.round(rng.uniform(0.1, 1.0, n_rings), 3)).to(dev)
+    area = torch.from_numpy(rng.uniform(0.0, 1500.0, n_rings)).to(dev)
+    nd = torch.tensor([600], dtype=torch.int64, device=dev)
+    flags, pid = ops.select_head(conf, area, 0.3, 1.0, 1000.0, n_dev=nd)
+    valid = torch.arange(n_rings, device=dev) < 600
+    ok = (conf >= 0.3) & valid
+    want_flags = ok & (area >= 1.0) & (area <= 1000.0)
+    assert torch.equal(flags.bool(), want_flags)
+    want_pid = torch.cumsum(ok.long(), 0) - 1
+    assert torch.equal(pid[ok], want_pid[ok])

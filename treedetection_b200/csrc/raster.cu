@@ -967,8 +967,17 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
       // v6 (warp-autonomous strips): staged row pitch 96 bytes (every 450 -> 800 tile) or 160 (any up-scaling)
       const int box_v6 = box_w <= 96 ? 96 : 160;
       if (box_w <= 160 && !getenv("TREEDET_P1_CTA") && make_image_tensor_map(&tmap, image, bands, H, W, box_v6, kChunk, 3)) {
-        size_t smem_v6 = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
-        if (const char* e = getenv("TREEDET_P1_SMEM_PAD")) smem_v6 += (size_t)atoi(e);   // experiment: fewer CTAs per SM
+        const size_t smem_need = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
+        // Residency: 4 CTAs (16 warps) per SM already saturate HBM (2.11 ms alone against 2.14 with 6), and
+        // what they leave free -- a third of the registers, ~40 KB of shared memory -- lets the latency-
+        // bound P2-P9 kernels of the other stream run NEXT to this kernel instead of waiting for it
+        // (step 4.76 -> 4.5 ms).  There is no launch attribute for "at most n CTAs per SM"; asking for
+        // 46 KB of dynamic shared memory per CTA does it (4 x 46 <= 227 < 5 x 46).  A persistent grid
+        // of 4 CTAs per SM was tried instead and ran 30 % slower.
+        size_t smem_v6 = smem_need;
+        static int pad_kb = -1;
+        if (pad_kb < 0) { const char* e = getenv("TREEDET_P1_SMEM_KB"); pad_kb = e ? atoi(e) : 46; }
+        if ((size_t)pad_kb * 1024 > smem_v6) smem_v6 = (size_t)pad_kb * 1024;
         const bool fork = P->side && P->n_items_vec > 0 && P->n_items > P->n_items_vec;
         if (fork) {
           TD_CUDA(cudaEventRecord(P->ev_fork, st));
@@ -981,8 +990,9 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
           cudaStream_t st_pass = (fork && pass == 1) ? P->side : st;
           auto kern = box_v6 == 96 ? (pass == 0 ? tile_resize_u8_up_warp_kernel<true, 96> : tile_resize_u8_up_warp_kernel<false, 96>)
                                    : (pass == 0 ? tile_resize_u8_up_warp_kernel<true, 160> : tile_resize_u8_up_warp_kernel<false, 160>);
-          if (smem_v6 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v6);
-          kern<<<td_div_up(count, kWarpsV6), 32 * kWarpsV6, smem_v6, st_pass>>>(tmap, P->d_items + first, count, P->d_min,
+          const size_t smem_pass = pass == 0 ? smem_v6 : smem_need;      // the few unaligned tiles: no limit
+          if (smem_pass > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pass);
+          kern<<<td_div_up(count, kWarpsV6), 32 * kWarpsV6, smem_pass, st_pass>>>(tmap, P->d_items + first, count, P->d_min,
                                                                                  P->d_k, P->d_y, out);
           if (fork && pass == 1) TD_CUDA(cudaEventRecord(P->ev_join, P->side));
         }
