@@ -198,8 +198,9 @@ def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_
         return empty()
     # 4. statistics (P7) + centroids
     cent = ops.centroids(verts2, off2)
-    if rasters.get("height_ready") is not None:      # the nDSM may still be on its way (api.run_image)
-        torch.cuda.current_stream().wait_event(rasters["height_ready"])
+    for key in ("height_ready", "ndvi_ready"):       # rasters produced / copied on another stream
+        if rasters.get(key) is not None:
+            torch.cuda.current_stream().wait_event(rasters[key])
     combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
         _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
     if combined:
@@ -313,8 +314,9 @@ def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, cap
     verts2, off2 = ops.take_rings_dyn(verts1, off1, sel2, n2, cap_v)
     conf2, area2, pid2, b2 = ops.gather_rows([conf1, area1, pid1, b1], sel2, n2)
     cent = ops.centroids(verts2, off2, n_dev=n2)
-    if rasters.get("height_ready") is not None:      # the nDSM may still be on its way (api.run_image)
-        torch.cuda.current_stream().wait_event(rasters["height_ready"])
+    for key in ("height_ready", "ndvi_ready"):       # rasters produced / copied on another stream
+        if rasters.get(key) is not None:
+            torch.cuda.current_stream().wait_event(rasters[key])
     combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
         _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
     if combined:
