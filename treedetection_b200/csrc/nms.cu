@@ -203,22 +203,18 @@ __global__ void to_half_kernel(const double* __restrict__ conf, const double* __
 template <bool kFill>
 __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16, const __half* __restrict__ a16,
                                      float iou_thr, __half area_thr, long long* __restrict__ deg_or_off,
-                                     int* __restrict__ nbr, int* __restrict__ best, long long nbr_cap,
-                                     long long* __restrict__ flag) {
+                                     int* __restrict__ nbr, int* __restrict__ best, int slots,
+                                     long long* __restrict__ end, long long* __restrict__ flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   live_count(g);
   if (i >= g.n) return;
-  // capacity mode: a neighbour list that does not fit is not written (bit 1 of *flag is raised,
-  // the resolve kernel then does nothing and the caller discards the result)
-  bool fits = true;
-  if (kFill && nbr_cap >= 0 && deg_or_off[i + 1] > nbr_cap) {
-    fits = false;
-    atomicOr((unsigned long long*)flag, 2ull);
-  }
+  // slots > 0 (capacity form): no count pass, crown i owns nbr[i * slots .. (i + 1) * slots); a list
+  // that does not fit raises bit 1 of *flag (the resolve kernel then does nothing and the caller
+  // discards the result)
   const float4 bi = g.box32[i];
   const __half ai = a16[i];
   long long cnt = 0;
-  long long off = kFill ? deg_or_off[i] : 0;
+  const long long off = !kFill ? 0 : (slots > 0 ? (long long)i * slots : deg_or_off[i]);
   // argmax(conf16[group]) with group = sorted(where(mask[i])) ++ [i]: first maximum wins,
   // i.e. the smallest index among the maxima; the appended i only wins ties when it is
   // also a regular member (mask[i][i]), otherwise it is last.  NaN counts as the maximum.
@@ -230,7 +226,7 @@ __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16,
     if (!nms_connected(bi, g.box32[j], ai, a16[j], iou_thr, area_thr)) return;
     if (j == i) { self_in = true; }
     else {
-      if (kFill && fits) nbr[off + cnt] = j;
+      if (kFill && (slots <= 0 || cnt < slots)) nbr[off + cnt] = j;
       ++cnt;
     }
     if (kFill) {
@@ -245,6 +241,11 @@ __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16,
     }
   });
   if (!kFill) { deg_or_off[i] = cnt; return; }
+  if (slots > 0) {
+    if (cnt > slots) atomicOr((unsigned long long*)flag, 2ull);
+    deg_or_off[i] = off;
+    end[i] = off + (cnt < slots ? cnt : slots);
+  }
   if (!self_in) {  // i appended last: wins only with a strictly larger confidence
     const float ci = __half2float(c16[i]);
     const bool in_ = isnan(ci);
@@ -259,7 +260,8 @@ __global__ void nms_adjacency_kernel(PairGrid g, const __half* __restrict__ c16,
 }
 
 // state: 0 undecided, 1 fires, 2 skipped (was already removed when visited)
-__global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, const int* __restrict__ nbr,
+__global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, const long long* __restrict__ end,
+                                   const int* __restrict__ nbr,
                                    const int* __restrict__ best, volatile int* state, int* pending,
                                    unsigned char* __restrict__ removed, const long long* __restrict__ n_dev,
                                    const long long* __restrict__ flag) {
@@ -278,7 +280,7 @@ __global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, con
     for (int i = tid; i < n; i += nth) {
       if (state[i] != 0) continue;
       bool killed = false, wait = false;
-      for (long long p = off[i]; p < off[i + 1]; ++p) {
+      for (long long p = off[i]; p < end[i]; ++p) {
         const int j = nbr[p];
         if (j >= i || best[j] == i) continue;
         const int s = state[j];
@@ -298,7 +300,7 @@ __global__ void nms_resolve_kernel(int n, const long long* __restrict__ off, con
   }
   for (int k = tid; k < n; k += nth) {
     bool rem = (state[k] == 1 && best[k] != k);
-    for (long long p = off[k]; p < off[k + 1] && !rem; ++p) {
+    for (long long p = off[k]; p < end[k] && !rem; ++p) {
       const int j = nbr[p];
       rem = (state[j] == 1 && best[j] != k);
     }
@@ -447,25 +449,35 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
   int rc = build_grid(sc, box32, gp, n, &keys, &idx, n_dev);
   if (rc != TD_OK) return rc;
   g.keys = keys; g.idx = idx;
-  TD_CUDA(cudaMemsetAsync(deg, 0, sizeof(long long) * (n + 1), st));
-  nms_adjacency_kernel<false><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, deg, nullptr, nullptr, -1,
-                                                      nullptr);
-  TD_CHECK_LAUNCH("nms count");
-  size_t tmp_bytes = 0;
-  TD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, off, n + 1, st));
-  void* tmp = sc.get(tmp_bytes);
-  if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
-  TD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, off, n + 1, st));
-  // the neighbour count is data dependent: one 8-byte read back sizes the CSR array
-  long long total = nbr_cap;
-  if (nbr_cap < 0) {
+  int* nbr = nullptr;
+  const long long* end_c = off + 1;
+  if (nbr_cap >= 0) {
+    // capacity form: fixed slots per crown, one pass (deg doubles as the end-offset array)
+    const int slots = (int)(nbr_cap / n > 0 ? nbr_cap / n : 1);
+    nbr = (int*)sc.get(sizeof(int) * (size_t)n * slots);
+    if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, slots, deg, flag);
+    TD_CHECK_LAUNCH("nms fill (slots)");
+    end_c = deg;
+  } else {
+    TD_CUDA(cudaMemsetAsync(deg, 0, sizeof(long long) * (n + 1), st));
+    nms_adjacency_kernel<false><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, deg, nullptr, nullptr, 0, nullptr,
+                                                        nullptr);
+    TD_CHECK_LAUNCH("nms count");
+    size_t tmp_bytes = 0;
+    TD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, off, n + 1, st));
+    void* tmp = sc.get(tmp_bytes);
+    if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    TD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, off, n + 1, st));
+    // the neighbour count is data dependent: one 8-byte read back sizes the CSR array
+    long long total = 0;
     TD_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
+    nbr = (int*)sc.get(sizeof(int) * (size_t)(total > 0 ? total : 1));
+    if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, 0, nullptr, nullptr);
+    TD_CHECK_LAUNCH("nms fill");
   }
-  int* nbr = (int*)sc.get(sizeof(int) * (size_t)(total > 0 ? total : 1));
-  if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
-  nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, nbr_cap, flag);
-  TD_CHECK_LAUNCH("nms fill");
   // cooperative fixed-point resolution: one resident wave
   int per_sm = 0;
   TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_resolve_kernel, 256, 0));
@@ -478,7 +490,7 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
   const int* nbr_c = nbr;
   const int* best_c = best;
   const long long* flag_c = flag;
-  void* args[] = {&n_, &off_c, &nbr_c, &best_c, &state, &pending, &removed, &n_dev, &flag_c};
+  void* args[] = {&n_, &off_c, &end_c, &nbr_c, &best_c, &state, &pending, &removed, &n_dev, &flag_c};
   TD_CUDA(cudaLaunchCooperativeKernel((void*)nms_resolve_kernel, dim3(grid), dim3(256), args, 0, st));
   return TD_OK;
 }
