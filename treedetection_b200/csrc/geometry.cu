@@ -18,6 +18,9 @@
 
 namespace {
 
+constexpr int kSmemRing = 128;                              // vertices of a ring whose scratch fits shared memory
+constexpr int kSmemInts = 5 * kSmemRing + kSmemRing / 32 + 4;   // per warp: res | flat | stack | alive bits
+
 // one warp per ring: the stack machine runs redundantly on all lanes, the farthest-point
 // and intersection scans are strided over the lanes (td::WarpCoop)
 __global__ void __launch_bounds__(128)
@@ -64,7 +67,20 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   }
   int m;
   if (tol > 0.0 && len > 0) {
-    m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+    // The stack machine pushes and pops its scratch (result list, flags, stack, live-segment bits)
+    // at every node; in global memory each pop is an L2 round trip (stores do not allocate in L1),
+    // and those round trips get long when a bandwidth-bound kernel runs next to this one.  Rings of
+    // up to kSmemRing vertices (nearly all) keep the scratch in shared memory; the kept-vertex list
+    // is copied out at the end for td_take_rings.
+    extern __shared__ int s_work[];
+    int* my = s_work + (threadIdx.x >> 5) * kSmemInts;
+    if (len <= kSmemRing) {
+      m = td::simplify_ring(pts, len, tol, my, reinterpret_cast<uint32_t*>(my + 5 * kSmemRing), td::WarpCoop());
+      __syncwarp();
+      for (int k = lane; k < m; k += 32) sc[k] = my[k];
+    } else {
+      m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+    }
   } else {  // helpers.py:463: simplification is skipped for a non-positive tolerance
     for (int k = lane; k < len; k += 32) sc[k] = k;
     m = len;
@@ -138,7 +154,7 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
   static int bs = 0;
   if (bs == 0) { const char* e = getenv("TREEDET_SIMPLIFY_BLOCK"); bs = e && atoi(e) > 0 ? atoi(e) : 64; }
-  simplify_kernel<<<td_div_up((long long)n_rings * 32, bs), bs, 0, (cudaStream_t)stream>>>(
+  simplify_kernel<<<td_div_up((long long)n_rings * 32, bs), bs, sizeof(int) * (bs / 32) * kSmemInts, (cudaStream_t)stream>>>(
       verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep,
       bounds_of_input, n_dev);
   TD_CHECK_LAUNCH("td_simplify_rings");
