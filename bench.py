@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
+    ap.add_argument("--p1-after-walk", action="store_true",
+                    help="start P1 only when the border walk of the image is done (they compete for shared memory)")
     ap.add_argument("--strip-last", action="store_true", help="N > 1: enqueue the seam strip after the image's chain")
     ap.add_argument("--no-alone", action="store_true",
                     help="do not time the roofline kernel alone after the timed region (profiling runs: keeps the "
@@ -313,7 +315,7 @@ def run_b200(a):
     pre_rasters = []
     p5_ev = []
 
-    def chain(e):
+    def chain(e, on_p3=None):
         """P2-P9 of the resident image on the current stream; e[2..5] bracket the stages"""
         e[2].record()
         if a.exact:
@@ -327,11 +329,18 @@ def run_b200(a):
             results.append((len(table), len(feats)))
             return None
         marks = {"p4": e[3], "p5": e[4], "p9": e[5]}
+
+        def mark(name):
+            if name == "p3":
+                if on_p3 is not None:
+                    on_p3()
+            else:
+                marks[name].record()
         pre = pre_rasters.pop() if pre_rasters else None
         return runner.submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
                              (lambda: pre) if pre is not None else
                              (lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)),
-                             mark=lambda name: marks[name].record())
+                             mark=mark)
 
     def step_resident():
         # results of the image enqueued one step ago (the only host wait; the GPU is already busy with
@@ -354,10 +363,16 @@ def run_b200(a):
         else:
             for st in (p1_stream, chain_stream, strip_stream):
                 st.wait_stream(main)
-            with torch.cuda.stream(p1_stream):
-                e[0].record()
-                tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
-                e[1].record()
+            def launch_p1(after=None):
+                with torch.cuda.stream(p1_stream):
+                    if after is not None:
+                        p1_stream.wait_event(after)
+                    e[0].record()
+                    tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+                    e[1].record()
+            p1_late = a.p1_after_walk and not a.exact
+            if not p1_late:
+                launch_p1()
             if not a.exact:
                 # P5 (issue bound, needed only by the statistics) on its own stream, next to P2-P4
                 p5_stream.wait_stream(main)
@@ -376,7 +391,8 @@ def run_b200(a):
                 with torch.cuda.stream(strip_stream):
                     ts = step_strip()
             with torch.cuda.stream(chain_stream):
-                t = chain(e)
+                # --p1-after-walk: P1 starts when the border walk (which wants the SM's shared memory) is done
+                t = chain(e, on_p3=(lambda: launch_p1(chain_stream.record_event())) if p1_late else None)
             if world > 1 and a.strip_last:
                 with torch.cuda.stream(strip_stream):
                     ts = step_strip()

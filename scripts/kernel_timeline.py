@@ -28,7 +28,25 @@ det = {k: d[k] for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims
 last = []
 
 
+overlap = len(sys.argv) > 3 and sys.argv[3] == "overlap"
+p1_stream = torch.cuda.Stream(device=dev)
+chain_stream = torch.cuda.Stream(device=dev, priority=-1)
+
+
 def step():
+    if overlap:      # as bench.py's default step: P1 next to the chain
+        main = torch.cuda.current_stream()
+        p1_stream.wait_stream(main); chain_stream.wait_stream(main)
+        with torch.cuda.stream(p1_stream):
+            tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+        with torch.cuda.stream(chain_stream):
+            t = runner.submit(det, tables.tile_tf, tables.tile_boxes,
+                              lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p))
+        main.wait_stream(p1_stream); main.wait_stream(chain_stream)
+        if last:
+            runner.collect(last.pop())
+        last.append(t)
+        return
     tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
     t = runner.submit(det, tables.tile_tf, tables.tile_boxes,
                       lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p))

@@ -260,8 +260,10 @@ def new_counters(device):
 
 
 def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams,
-                      caps: dict, ctr: torch.Tensor) -> DynTable:
-    """P2 + P3 + P4 without host synchronisation (see the section comment)."""
+                      caps: dict, ctr: torch.Tensor, mark=None) -> DynTable:
+    """P2 + P3 + P4 without host synchronisation (see the section comment).  ``mark("p3")`` is called
+    once the border walk is enqueued (schedulers use it to start work that should not share the SMs
+    with the shared-memory hungry walk)."""
     flag = ctr[CTR_FLAG:CTR_FLAG + 1]
     sizes1 = torch.empty((3, boxes_net.shape[0]), dtype=torch.int64, device=boxes_net.device)
     boxes_px, win, _ = ops.paste_plan(boxes_net, inst_tile, tile_dims, sizes=sizes1)
@@ -275,6 +277,8 @@ def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, t
     else:      # one border walk into per-instance slots
         rings = ops.trace_rings_slots(bits, win, word_off, px_off, slot_off, inst_tile, tile_tf, caps, flag,
                                       ctr[CTR_RINGS:CTR_VERTS + 1])
+    if mark is not None:
+        mark("p3")
     n_rings = ctr[CTR_RINGS:CTR_RINGS + 1]
     cap_r = int(caps["rings"])
     ring_inst = rings.ring_inst[:cap_r].long()
@@ -398,13 +402,13 @@ class ChainRunner:
         mark = mark or (lambda name: None)
         if self.caps is None:
             out = ("done",) + self._exact(det, tile_tf, tile_boxes, rasters_fn)
-            for name in ("p4", "p5", "p9"):
+            for name in ("p3", "p4", "p5", "p9"):
                 mark(name)
             return out
         dev = det["boxes_net"].device
         ctr = new_counters(dev)
         table = predict_stage_dyn(det["boxes_net"], det["scores"], det["probs"], det["inst_tile"], det["tile_dims"],
-                                  tile_tf, tile_boxes, self.p, self.caps, ctr)
+                                  tile_tf, tile_boxes, self.p, self.caps, ctr, mark=mark)
         mark("p4")
         rasters = rasters_fn()
         mark("p5")
