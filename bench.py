@@ -466,7 +466,9 @@ def run_b200(a):
     names = ["P1 tile cut/normalise", "P2-P4 paste/contours/stitch", "P5 NDVI/decimation", "P6-P9 NMS/stats/select"]
     pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
     chain_mode = "exact sizes (host sync before every allocation)" if a.exact else \
-        f"sync-free (capacity buffers, device-side counts; {runner.fallbacks} exact-size fallbacks in the timed region)"
+        f"sync-free (capacity buffers, device-side counts; exact-size fallbacks incl. warm-up: image {runner.fallbacks}, " \
+        f"seam strip {strip_runner.fallbacks}; border walk: {'two-pass' if runner.two_pass else 'single-pass'} / " \
+        f"strip {'two-pass' if strip_runner.two_pass else 'single-pass'})"
     stage_ms = {n: statistics.mean(e[i].elapsed_time(e[j]) for e in stage_ev) for (i, j), n in zip(pairs, names)}
     p1_ms_in_step = stage_ms[names[0]]
     if p5_ev:      # P5 ran on its own stream

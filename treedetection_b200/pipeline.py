@@ -260,7 +260,7 @@ def new_counters(device):
 
 
 def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams,
-                      caps: dict, ctr: torch.Tensor, mark=None) -> DynTable:
+                      caps: dict, ctr: torch.Tensor, mark=None, two_pass=False) -> DynTable:
     """P2 + P3 + P4 without host synchronisation (see the section comment).  ``mark("p3")`` is called
     once the border walk is enqueued (schedulers use it to start work that should not share the SMs
     with the shared-memory hungry walk)."""
@@ -271,7 +271,7 @@ def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, t
                               totals=ctr[CTR_WORDS:CTR_SLOTS + 1])
     word_off, px_off, slot_off = offs1[0], offs1[1], offs1[2]
     bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, int(caps["words"]))
-    if TRACE_TWO_PASS:
+    if TRACE_TWO_PASS or two_pass:
         rings = ops.trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
                                     ctr[CTR_CONT:CTR_VERTS + 1])
     else:      # one border walk into per-instance slots
@@ -364,6 +364,7 @@ class ChainRunner:
         self.caps = None
         self.nbr_per_crown = 8
         self.fallbacks = 0
+        self.two_pass = TRACE_TWO_PASS     # border walk: one pass into slots, or count + emit
         self._pinned = []          # recycled pinned read-back buffers (allocating one costs ~0.1 ms)
 
     def _learn(self, sizes: dict):
@@ -408,7 +409,7 @@ class ChainRunner:
         dev = det["boxes_net"].device
         ctr = new_counters(dev)
         table = predict_stage_dyn(det["boxes_net"], det["scores"], det["probs"], det["inst_tile"], det["tile_dims"],
-                                  tile_tf, tile_boxes, self.p, self.caps, ctr, mark=mark)
+                                  tile_tf, tile_boxes, self.p, self.caps, ctr, mark=mark, two_pass=self.two_pass)
         mark("p4")
         rasters = rasters_fn()
         mark("p5")
@@ -432,10 +433,14 @@ class ChainRunner:
             self.fallbacks += 1
             if c[CTR_FLAG] & 2:
                 self.nbr_per_crown *= 2
+            if c[CTR_FLAG] & 4:
+                # an instance outgrew its slot of the single-pass walk (ragged mask: many borders or a
+                # long outline); the same image would do so again, so this runner walks twice from now on
+                self.two_pass = True
             return self._exact(*again)
         learnt = {"words": c[CTR_WORDS], "px": c[CTR_PX], "ptslots": c[CTR_SLOTS], "rings": c[CTR_RINGS],
                   "verts": c[CTR_VERTS]}
-        if TRACE_TWO_PASS:
+        if self.two_pass:
             learnt.update(contours=c[CTR_CONT], points=c[CTR_PTS])
         self._learn(learnt)
         return c[CTR_NTABLE], trim_features(feats, c[CTR_NFINAL], c[CTR_VFINAL])
