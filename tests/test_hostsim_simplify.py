@@ -94,3 +94,47 @@ def test_simplify_keeps_minimum_ring():
     got, area = ours(sq, 10.0)
     assert got == geom.simplify_ring(sq, 10.0)
     assert len(got) >= 4 and area > 0
+
+
+def _degenerate_rings(rng):
+    """Rings that drive the intersection guard through its collinear / touching branches: runs of
+    collinear vertices, spikes (A -> B -> A), repeated points, axis-parallel combs whose teeth are
+    thinner than the tolerance.  The neighbour shortcut of simplify_ring (one orientation instead of
+    the full predicate when a neighbour segment is not collinear with the chord) must not change any
+    of them with respect to the full GEOS-semantics restatement in oracle/geom.py."""
+    out = []
+    for k in range(60):
+        pts = []
+        x, y = 412000.0 + k, 5318000.0
+        n = int(rng.integers(6, 40))
+        kind = k % 4
+        for i in range(n):
+            if kind == 0:      # staircase with long collinear runs
+                x += float(rng.choice([0.0, 0.2, 0.4])); y += float(rng.choice([0.0, 0.2])) if i % 3 == 0 else 0.0
+            elif kind == 1:    # comb: teeth of 0.1 m on a base line
+                x += 0.2; y = 5318000.0 + (0.1 if i % 2 else 0.0)
+            elif kind == 2:    # spikes and repeated points
+                step = rng.choice([-0.2, 0.0, 0.2], size=2)
+                x += float(step[0]); y += float(step[1])
+            else:              # diagonal runs (collinear at 45 degrees) with kinks
+                d = 0.2 * float(rng.integers(1, 4))
+                x += d; y += d if i % 5 else -d
+            pts.append((x, y))
+        # come back below the start so that the ring has area, then close
+        pts.append((pts[-1][0], 5317999.0 - (k % 3)))
+        pts.append((pts[0][0], 5317999.0 - (k % 3)))
+        pts.append(pts[0])
+        out.append(pts)
+    return out
+
+
+@pytest.mark.parametrize("tol", [0.05, 0.2, 2.0])
+def test_simplify_collinear_and_touching_neighbours(tol):
+    rng = np.random.default_rng(99)
+    checked = 0
+    for ring in _degenerate_rings(rng):
+        want = geom.simplify_ring([tuple(p) for p in ring], tol)
+        got, _ = ours(ring, tol)
+        assert got == [tuple(map(float, q)) for q in want], (tol, ring)
+        checked += 1
+    assert checked == 60
