@@ -138,3 +138,31 @@ def test_simplify_collinear_and_touching_neighbours(tol):
         assert got == [tuple(map(float, q)) for q in want], (tol, ring)
         checked += 1
     assert checked == 60
+
+
+@pytest.mark.parametrize("tol", [0.2, 2.0])
+def test_tile_box_prefilter_is_conservative(tol):
+    """simplify_kernel rejects a ring WITHOUT simplifying it when its bounds stick out of the tile box by
+    more than the tolerance (geometry.cu).  That is only allowed if such a ring can never be `within` the
+    box after simplification: checked here on contour rings against boxes cutting through them."""
+    tf = (0.2, 0.0, 412000.0, 0.0, -0.2, 5318100.0)
+    rng = np.random.default_rng(7)
+    n_pre = n_rings = 0
+    for seed in range(12):
+        for ring in _contour_rings(seed, tf):
+            xy = np.asarray(ring, dtype=np.float64)
+            simp = np.asarray(geom.simplify_ring([tuple(p) for p in ring], tol), dtype=np.float64)
+            x0, y0, x1, y1 = xy[:, 0].min(), xy[:, 1].min(), xy[:, 0].max(), xy[:, 1].max()
+            for _ in range(6):
+                # a box edge somewhere near the ring's own extent
+                j = tol + 1.0
+                bx0 = x0 + rng.uniform(-j, j); by0 = y0 + rng.uniform(-j, j)
+                bx1 = x1 + rng.uniform(-j, j); by1 = y1 + rng.uniform(-j, j)
+                slack = tol * (1.0 + 1e-9) + 1e-9
+                pre_reject = x0 < bx0 - slack or y0 < by0 - slack or x1 > bx1 + slack or y1 > by1 + slack
+                within = bool(len(simp)) and simp[:, 0].min() >= bx0 and simp[:, 1].min() >= by0 and \
+                    simp[:, 0].max() <= bx1 and simp[:, 1].max() <= by1
+                assert not (pre_reject and within)
+                n_pre += pre_reject
+                n_rings += 1
+    assert n_pre > 50 and n_rings - n_pre > 50
