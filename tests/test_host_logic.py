@@ -1,0 +1,152 @@
+"""Host logic on the CPU against golden values produced by the REFERENCE'S OWN functions
+(tests/golden/make_golden_host.py through oracle.refshim): get_config keys / defaults / assertion
+messages, the tile-id parser behind the stitch filter boxes, coordinate rounding; plus the tile grid
+(preprocessing.py:57-120 restated in tiling.tile_grid) against its closed form, ResizeShortestEdge, the
+GPKG and GeoTIFF codecs' round trips and the capacity planning of the sync-free chain."""
+import json
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from treedetection_b200 import config as tconfig, geo, geotiff, gpkg, pipeline, synth, tiling
+
+G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_logic.json")))
+SKIP = {"logger", "image_directory", "height_data_path", "combined_model", "urban_model", "forrest_model",
+        "forrest_outline", "output_directory", "tiles_path", "continue"}
+
+
+def _get_config(tmp_path, extra, drop=()):
+    img, h, model = (tmp_path / n for n in ("rgb", "ndsm", "model"))
+    for d in (img, h, model):
+        d.mkdir(exist_ok=True)
+    cfg = {"image_directory": str(img), "height_data_path": str(h), "combined_model": str(model),
+           "output_directory": str(tmp_path / "out"), "tiles_path": str(tmp_path / "tiles")}
+    cfg.update(extra)
+    for k in drop:
+        cfg.pop(k, None)
+    path = tmp_path / "c.yml"
+    path.write_text(yaml.safe_dump(cfg))
+    return tconfig.get_config(str(path))
+
+
+@pytest.mark.parametrize("name,extra", [("config_minimal", {}),
+                                        ("config_overrides", {"tile_width": 64, "buffer": 8, "iou_threshold": 0.6,
+                                                              "exclude_files": ["a.gpkg"], "device": "cuda:1",
+                                                              "ndvi_scaling_factor": 0.2, "debug": True})])
+def test_get_config_matches_reference(tmp_path, name, extra):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("the golden was produced without CUDA (device falls back to 'cpu')")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cfg, obj = _get_config(tmp_path, extra)
+    got = {k: v for k, v in cfg.items() if k not in SKIP}
+    assert got == G[name]
+    assert obj.tile_width == cfg["tile_width"] and tconfig.Config().buffer == cfg["buffer"]     # singleton
+    assert cfg["continue"] == os.path.join(cfg["output_directory"], "continue.yml")
+    assert os.path.isdir(os.path.join(cfg["output_directory"], "logs"))
+
+
+@pytest.mark.parametrize("name,drop", [("config_no_images", "image_directory"), ("config_no_height", "height_data_path"),
+                                       ("config_no_model", "combined_model")])
+def test_get_config_assertions_match_reference(tmp_path, name, drop):
+    with pytest.raises(AssertionError) as e:
+        _get_config(tmp_path, {}, drop=(drop,))
+    assert str(e.value) == G[name]["assertion"]
+
+
+def test_tile_id_parser_matches_filename_geoinfo():
+    """pipeline.tile_tables parses the last five '_' fields of a tile id, as helpers.filename_geoinfo does"""
+    for tid, want in G["filename_geoinfo"].items():
+        parts = [int(p) for p in tid.split("_")[-5:]]
+        assert parts == want
+
+
+def test_round_coordinates_rule():
+    """round(coord * 1000) / 1000 with Python's round-half-even (utilities.py:146-161): the rule
+    td_round_coords implements with rint; checked here on the host against the reference's outputs"""
+    vals = np.array(G["round_coordinates"]["in"])
+    want = np.array(G["round_coordinates"]["out"])
+    got = np.stack([np.rint(vals * 1000.0) / 1000.0, np.rint(-vals * 1000.0) / 1000.0], 1)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_tile_grid_closed_form():
+    px, W, H = 0.2, 1500, 1000
+    tf = synth.image_transform(412000.0, 5318200.0, px)          # top-left origin
+    tiles = tiling.tile_grid("img", tf, W, H, 25832, 50, 50, 20)
+    ids = list(tiles)
+    # x outer, y inner, from the BOTTOM-left corner (preprocessing.py:57-58)
+    assert ids[0] == "img_412000_5318000_50_20_25832" and ids[1] == "img_412000_5318050_50_20_25832"
+    assert len(ids) == 6 * 4
+    for tid, m in tiles.items():
+        minx, miny = [int(v) for v in tid.split("_")[1:3]]
+        assert m["bounds"] == [minx - 20, miny - 20, minx + 70, miny + 70]
+        c0, r0, w, h = m["window"]
+        # geometry_window: floor / ceil of the pixel bounds, clipped to the raster
+        assert c0 == max(int(np.floor((minx - 20 - 412000.0) / px)), 0)
+        assert c0 + w == min(int(np.ceil((minx + 70 - 412000.0) / px)), W)
+        assert r0 == max(int(np.floor((5318200.0 - (miny + 70)) / px)), 0)
+        assert r0 + h == min(int(np.ceil((5318200.0 - (miny - 20)) / px)), H)
+        a, b, c, d, e, f = m["transform"][:6]
+        assert (a, b, d, e) == (px, 0.0, 0.0, -px) and c == 412000.0 + c0 * px and f == 5318200.0 - r0 * px
+        assert m["transform"][6:] == [0.0, 0.0, 1.0] and m["crs"] == 25832
+
+
+@pytest.mark.parametrize("hw,want", [((450, 450), (800, 800)), ((450, 350), (1029, 800)), ((350, 450), (800, 1029)),
+                                     ((100, 400), (333, 1333)), ((1000, 1000), (800, 800))])
+def test_resize_shortest_edge(hw, want):
+    """detectron2 ResizeShortestEdge(800, max 1333): scale the short side to 800, cap the long side,
+    round half up (int(x + 0.5))"""
+    assert tiling.resize_shortest_edge(*hw) == want
+
+
+def test_gpkg_round_trip(tmp_path):
+    rng = np.random.default_rng(0)
+    rings = [np.concatenate([r, r[:1]]) for r in (412000 + rng.uniform(0, 100, (k, 2)) for k in (4, 9, 33))]
+    verts = np.concatenate(rings)
+    off = np.zeros(4, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in rings])
+    cols = {"Confidence_score": np.array([0.3, 0.75, 0.999])}
+    path = str(tmp_path / "x.gpkg")
+    gpkg.write_layer(path, "x", verts, off, cols, gpkg.STITCHED_SCHEMA, epsg=25832)
+    v2, o2, c2 = gpkg.read_layer(path)[:3]
+    np.testing.assert_array_equal(v2, verts)
+    np.testing.assert_array_equal(o2, off)
+    np.testing.assert_array_equal(np.asarray(c2["Confidence_score"], dtype=np.float64), cols["Confidence_score"])
+
+
+def test_geotiff_round_trip_with_geo_tags(tmp_path):
+    rng = np.random.default_rng(1)
+    arr = rng.integers(0, 255, (4, 37, 53), dtype=np.uint8)
+    tf = (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0)
+    path = str(tmp_path / "a.tif")
+    geotiff.write(path, arr, tf, epsg=25832)
+    got, info = geotiff.read(path)
+    np.testing.assert_array_equal(got, arr)
+    assert info.transform == tf and info.epsg == 25832 and (info.width, info.height, info.count) == (53, 37, 4)
+    win, winfo = geotiff.read(path, window=(5, 7, 20, 11))
+    np.testing.assert_array_equal(win, arr[:, 7:18, 5:25])
+    assert winfo.transform == geo.window_transform(tf, 5, 7)
+    f32 = rng.normal(size=(29, 31)).astype(np.float32)
+    geotiff.write(str(tmp_path / "h.tif"), f32, (1.0, 0.0, 412000.0, 0.0, -1.0, 5318000.0), epsg=25832,
+                  nodata=-3.4028234663852886e38)
+    got, info = geotiff.read(str(tmp_path / "h.tif"))
+    np.testing.assert_array_equal(got[0], f32)
+    assert info.nodata == pytest.approx(-3.4028234663852886e38)
+
+
+def test_chain_runner_capacity_planning():
+    """capacities grow, never shrink, and the NMS neighbour capacity follows the ring capacity"""
+    run = pipeline.ChainRunner(pipeline.PipelineParams())
+    run._learn({"words": 1000, "px": 50000, "ptslots": 9000, "contours": 40, "points": 700, "rings": 35, "verts": 600})
+    first = dict(run.caps)
+    assert first["words"] == int(1000 * 1.25) + 1024 and first["nbr"] == 8 * first["rings"]
+    run._learn({"words": 10, "px": 10, "ptslots": 10, "rings": 3, "verts": 5})
+    assert run.caps == first
+    run.nbr_per_crown = 16
+    run._learn({"words": 5000, "px": 10, "ptslots": 10, "rings": 300, "verts": 5})
+    assert run.caps["words"] == int(5000 * 1.25) + 1024 and run.caps["px"] == first["px"]
+    assert run.caps["nbr"] == 16 * run.caps["rings"] and run.caps["contours"] == first["contours"]

@@ -48,98 +48,85 @@ def setup_logging(log_path: str, debug: bool):
     return logger
 
 
+def _gpu_index(raw_device):
+    """Device spec of the YAML (int, "2", "cuda", "cuda:2", anything else -> 0) as a GPU index string."""
+    if isinstance(raw_device, int):
+        return raw_device
+    if isinstance(raw_device, str):
+        spec = raw_device[5:] if raw_device.startswith("cuda:") else raw_device
+        if spec.isdigit():
+            return spec
+    return "0"
+
+
 def set_device_configuration(config, raw_device):
-    """config["device"]: GPU index string, or "cpu" when CUDA is absent (config.py:112-142).
-    NOTE: with "cpu" this implementation refuses to run the kernels -- there is no CPU path."""
+    """config["device"]: GPU index string, or "cpu" when CUDA is absent (reference config.py:112-142:
+    same accepted spellings, same messages).  With "cpu" this implementation refuses to run the
+    kernels -- there is no CPU path."""
     import torch
-    if torch.cuda.is_available():
-        if raw_device is not None:
-            device_str = "0"
-            if isinstance(raw_device, int):
-                device_str = raw_device
-            elif isinstance(raw_device, str) and raw_device.startswith("cuda"):
-                if raw_device.replace("cuda:", "").isdigit():
-                    device_str = raw_device.replace("cuda:", "")
-                elif raw_device == "cuda":
-                    device_str = "0"
-            elif isinstance(raw_device, str) and raw_device.isdigit():
-                device_str = raw_device
-            try:
-                gpu_index = int(device_str)
-                assert torch.cuda.device_count() > gpu_index, f"GPU index {gpu_index} is out of range."
-            except (IndexError, ValueError):
-                raise ValueError(f"Invalid CUDA device specification: {raw_device}")
-            config["device"] = str(device_str)
-        else:
-            config["device"] = "0"
-    else:
+    if not torch.cuda.is_available():
         if isinstance(raw_device, str) and raw_device.startswith("cuda"):
             warnings.warn(f"CUDA device '{raw_device}' requested but CUDA is not available. Falling back to CPU.")
         config["device"] = "cpu"
+        return
+    index = "0" if raw_device is None else _gpu_index(raw_device)
+    if raw_device is not None:
+        try:
+            assert torch.cuda.device_count() > int(index), f"GPU index {int(index)} is out of range."
+        except (IndexError, ValueError):
+            raise ValueError(f"Invalid CUDA device specification: {raw_device}")
+    config["device"] = str(index)
+
+
+# (key, message) -- paths that must be present and exist (reference config.py:173-180)
+_REQUIRED = [
+    ("image_directory", "Input path is missing from the configuration or path is incorrect."),
+    ("height_data_path", "nDOM path is missing from the configuration or path is incorrect."),
+]
+_REQUIRED_WITHOUT_COMBINED_MODEL = [
+    ("urban_model", "Urban model path is missing from the configuration or path is incorrect."),
+    ("forrest_model", "Forrest model path is missing from the configuration."),
+    ("forrest_outline", "Forrest outline path is missing from the configuration."),
+]
+
+# the reference's defaults (config.py:182-233), in the order it fills them in
+_DEFAULTS = [
+    ("output_directory", "./output"), ("tiles_path", "./tiles"),
+    ("tile_width", 50), ("tile_height", 50), ("buffer", 20), ("batch_size", 10),
+    ("use_overlap", True), ("overlapping_tiles_width", 3), ("overlapping_tiles_height", 3), ("merged_path", "merged"),
+    ("image_merged_regex", "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_(\\d+)\\.tif"),
+    ("height_data_merged_regex", "FDOP20_(\\d+)_(\\d+)\\.tif"),
+    ("iou_threshold", 0.5), ("confidence_threshold_stitching", 0.3), ("area_threshold", 1),
+    ("exclude_files", []), ("confidence_threshold", 0.3), ("containment_threshold", 0.9), ("height_threshold", 3),
+    ("parallel", True), ("num_workers", None), ("verbose", False), ("debug", False),
+    ("keep_intermediate", False), ("timestamped_output_directory", False), ("simplify_tolerance", 0.2),
+    ("building_shapes", None),
+]
+
+
+def _present(config, key):
+    return bool(config.get(key)) and os.path.exists(config.get(key))
 
 
 def get_config(config_path: str):
     """YAML -> (dict with defaults filled in, Config singleton).  Same keys, defaults and
-    assertion messages as the reference; ``ndvi_scaling_factor``, ``height_scaling_factor``,
-    ``ndvi_mean_threshold`` and ``ndvi_var_threshold`` have no defaults there either."""
+    assertion messages as the reference (TreeDetection/config.py:144-238); ``ndvi_scaling_factor``,
+    ``height_scaling_factor``, ``ndvi_mean_threshold`` and ``ndvi_var_threshold`` have no defaults
+    there either."""
     config = load_config(config_path)
-
-    assert config.get("image_directory") and os.path.exists(config.get("image_directory")), \
-        "Input path is missing from the configuration or path is incorrect."
-    assert config.get("height_data_path") and os.path.exists(config.get("height_data_path")), \
-        "nDOM path is missing from the configuration or path is incorrect."
-
-    if not config.get("combined_model") or not os.path.exists(config.get("combined_model")):
-        assert config.get("urban_model") and os.path.exists(config.get("urban_model")), \
-            "Urban model path is missing from the configuration or path is incorrect."
-        assert config.get("forrest_model") and os.path.exists(config.get("forrest_model")), \
-            "Forrest model path is missing from the configuration."
-        assert config.get("forrest_outline") and os.path.exists(config.get("forrest_outline")), \
-            "Forrest outline path is missing from the configuration."
-
-    config["output_directory"] = config.get("output_directory", "./output")
-    if not config["output_directory"]:
-        os.makedirs(config["output_directory"], exist_ok=True)
-    config["tiles_path"] = config.get("tiles_path", "./tiles")
-    if not config["tiles_path"]:
-        os.makedirs(config["tiles_path"], exist_ok=True)
-    config["continue"] = config.get("continue", os.path.join(config["output_directory"], "continue.yml"))
-
-    config["tile_width"] = config.get("tile_width", 50)
-    config["tile_height"] = config.get("tile_height", 50)
-    config["buffer"] = config.get("buffer", 20)
-    config["batch_size"] = config.get("batch_size", 10)
-
-    config["use_overlap"] = config.get("use_overlap", True)
-    config["overlapping_tiles_width"] = config.get("overlapping_tiles_width", 3)
-    config["overlapping_tiles_height"] = config.get("overlapping_tiles_height", 3)
-    config["merged_path"] = config.get("merged_path", "merged")
-    config["image_merged_regex"] = config.get("image_merged_regex", "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_(\\d+)\\.tif")
-    config["height_data_merged_regex"] = config.get("height_data_merged_regex", "FDOP20_(\\d+)_(\\d+)\\.tif")
-
-    config["iou_threshold"] = config.get("iou_threshold", 0.5)
-    config["confidence_threshold_stitching"] = config.get("confidence_threshold_stitching", 0.3)
-    config["area_threshold"] = config.get("area_threshold", 1)
-
-    config["exclude_files"] = config.get("exclude_files", [])
-    config["confidence_threshold"] = config.get("confidence_threshold", 0.3)
-    config["containment_threshold"] = config.get("containment_threshold", 0.9)
-    config["height_threshold"] = config.get("height_threshold", 3)
-
-    raw_device = config.get("device", None)
-    set_device_configuration(config, raw_device)
-
-    config["parallel"] = config.get("parallel", True)
-    config["num_workers"] = config.get("num_workers", None)
-    config["verbose"] = config.get("verbose", False)
-    config["debug"] = config.get("debug", False)
+    for key, message in _REQUIRED:
+        assert _present(config, key), message
+    if not _present(config, "combined_model"):
+        for key, message in _REQUIRED_WITHOUT_COMBINED_MODEL:
+            assert _present(config, key), message
+    for key, default in _DEFAULTS:
+        config.setdefault(key, list(default) if isinstance(default, list) else default)
+    for key in ("output_directory", "tiles_path"):
+        if not config[key]:                      # as the reference: an empty path fails here
+            os.makedirs(config[key], exist_ok=True)
+    config.setdefault("continue", os.path.join(config["output_directory"], "continue.yml"))
+    set_device_configuration(config, config.get("device", None))
     config["logger"] = setup_logging(os.path.join(config["output_directory"], "logs"), config["debug"])
-    config["keep_intermediate"] = config.get("keep_intermediate", False)
-    config["timestamped_output_directory"] = config.get("timestamped_output_directory", False)
-    config["simplify_tolerance"] = config.get("simplify_tolerance", 0.2)
-
-    config["building_shapes"] = config.get("building_shapes", None)
-
-    config_obj = Config()
-    config_obj._load_into_config(config)
-    return config, config_obj
+    cfg = Config()
+    cfg._load_into_config(config)
+    return config, cfg
