@@ -105,6 +105,50 @@ int hs_find_contours_lockstep(const uint8_t* mask, int h, int w, int* npts_out, 
   return nc;
 }
 
+// Single-pass walk into a SLOT (contours.cu trace_walk_kernel): tables of cap_contours rows and
+// cap_points points, guarded by canaries.  Returns 0 when everything fitted, 1 when the instance
+// outgrew its slot (the counts are still complete), -1 when a canary was overwritten.
+int hs_walk_slot(const uint8_t* mask, int h, int w, int cap_contours, int cap_points, int* counts4, int* npts_out,
+                 short* pts_out) {
+  const int wpr = (w + 31) / 32;
+  std::vector<uint32_t> fg((size_t)wpr * h, 0u), vis((size_t)wpr * h, 0u), rgt((size_t)wpr * h, 0u);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      if (mask[(size_t)y * w + x]) fg[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+  const int kCanary = 0x5a5a5a5a;
+  std::vector<int> parent(cap_contours + 4, kCanary), npts(cap_contours + 4, kCanary), ptoff(cap_contours + 4, kCanary);
+  std::vector<unsigned char> hole(cap_contours + 4, 0x5a);
+  std::vector<short> pts(2 * (size_t)cap_points + 8, (short)0x5a5a);
+  std::vector<unsigned short> lab((size_t)w * h + 1, 0);
+  td::LaneState<unsigned short> S;
+  S.R.fg = fg.data(); S.R.visited = vis.data(); S.R.right = rgt.data(); S.R.label = lab.data();
+  S.R.w = w; S.R.h = h; S.R.wpr = wpr;
+  td::ContourOut out;
+  out.parent = parent.data(); out.npts = npts.data(); out.pt_off = ptoff.data(); out.is_hole = hole.data();
+  out.pts = pts.data();
+  out.cap_contours = cap_contours; out.cap_points = cap_points;
+  td::lane_init(S, &out);
+  while (S.mode != td::kDone) td::lane_step(S);
+  counts4[0] = S.cc.n_contours; counts4[1] = S.cc.n_points; counts4[2] = S.cc.n_rings; counts4[3] = S.cc.n_ring_verts;
+  for (int k = cap_contours; k < cap_contours + 4; ++k)
+    if (parent[k] != kCanary || npts[k] != kCanary || ptoff[k] != kCanary || hole[k] != 0x5a) return -1;
+  for (size_t k = 2 * (size_t)cap_points; k < pts.size(); ++k)
+    if (pts[k] != (short)0x5a5a) return -1;
+  const bool over = S.cc.n_contours < 0 || S.cc.n_contours > cap_contours || S.cc.n_points > cap_points;
+  if (over) return 1;
+  const int nc = S.cc.n_contours;
+  std::vector<int> lc(nc + 1), ps(nc + 1), order(nc + 1);
+  td::contour_order(nc, parent.data(), lc.data(), ps.data(), order.data());
+  size_t k = 0;
+  for (int q = 0; q < nc; ++q) {
+    const int c = order[q];
+    npts_out[q] = npts[c];
+    std::memcpy(pts_out + 2 * k, pts.data() + 2 * (size_t)ptoff[c], sizeof(short) * 2 * npts[c]);
+    k += npts[c];
+  }
+  return 0;
+}
+
 #ifdef HS_HAVE_SIMPLIFY
 // ring: n points (x, y interleaved), closed.  Returns the number of kept vertices and
 // writes their indices; *area = |signed area| of the simplified ring.

@@ -93,3 +93,43 @@ def test_diagonal_and_checkerboard():
     yy, xx = np.mgrid[0:30, 0:45]
     check(((yy + xx) % 2 == 0).astype(np.uint8))
     check(((yy % 2 == 0) & (xx % 2 == 0)).astype(np.uint8))
+
+
+def _walk_slot(mask, cap_contours, cap_points):
+    lib = hostsim.load()
+    h, w = mask.shape
+    npts = np.zeros(max(cap_contours, 1), dtype=np.int32)
+    pts = np.zeros(2 * max(cap_points, 1), dtype=np.int16)
+    counts = np.zeros(4, dtype=np.int32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    rc = lib.hs_walk_slot(m.ctypes.data_as(C.c_void_p), h, w, cap_contours, cap_points,
+                          counts.ctypes.data_as(C.c_void_p), npts.ctypes.data_as(C.c_void_p),
+                          pts.ctypes.data_as(C.c_void_p))
+    out, k = [], 0
+    if rc == 0:
+        for i in range(counts[0]):
+            out.append(pts[2 * k:2 * (k + npts[i])].reshape(-1, 2).astype(np.int32))
+            k += npts[i]
+    return rc, counts, out
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_single_pass_walk_into_slots(seed):
+    """trace_walk_kernel's walk (contours.cu): one pass with labels into capacity slots.  A slot that is
+    big enough gives cv2's contours; one that is too small still counts everything, writes nothing outside
+    the slot (canaries) and reports the overflow."""
+    rng = np.random.default_rng(100 + seed)
+    h, w = int(rng.integers(5, 70)), int(rng.integers(5, 100))
+    mask = (rng.uniform(size=(h, w)) < [0.35, 0.6, 0.85][seed % 3]).astype(np.uint8)
+    want = theirs(mask)
+    n_pts = sum(len(c) for c in want)
+    rc, counts, got = _walk_slot(mask, len(want), n_pts)            # exact fit
+    assert rc == 0 and counts[0] == len(want) and counts[1] == n_pts
+    for p, q in zip(got, want):
+        np.testing.assert_array_equal(p, q)
+    for cc, cp in [(max(len(want) // 2, 0), n_pts), (len(want), max(n_pts // 3, 0)), (0, 0), (1, 1)]:
+        if cc >= len(want) and cp >= n_pts:
+            continue
+        rc2, counts2, _ = _walk_slot(mask, cc, cp)
+        assert rc2 == 1, "overflow must be reported and no canary touched"
+        np.testing.assert_array_equal(counts2, counts)
