@@ -314,6 +314,8 @@ def run_b200(a):
     p5_stream = torch.cuda.Stream(device=dev)
     pre_rasters = []
     p5_ev = []
+    p5_bufs = [{}, {}, {}]     # NDVI output rasters, rotated (two steps are in flight at most)
+    p5_seq = [0]
 
     def chain(e, on_p3=None):
         """P2-P9 of the resident image on the current stream; e[2..5] bracket the stages"""
@@ -379,11 +381,12 @@ def run_b200(a):
                 with torch.cuda.stream(p5_stream):
                     q0, q1 = ev(), ev()
                     q0.record()
-                    r = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)
+                    p5_seq[0] += 1
+                    r = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p,
+                                              buffers=p5_bufs[p5_seq[0] % len(p5_bufs)])
                     q1.record()
                     p5_ev.append((q0, q1))
                     r["ndvi_ready"] = p5_stream.record_event()
-                    r["ndvi"].record_stream(chain_stream)
                 pre_rasters.append(r)
             # the strip's ~130 small dependent launches go in first: they run under P1 while the host is
             # still enqueuing, instead of queueing behind the image's big kernels
@@ -466,9 +469,8 @@ def run_b200(a):
     names = ["P1 tile cut/normalise", "P2-P4 paste/contours/stitch", "P5 NDVI/decimation", "P6-P9 NMS/stats/select"]
     pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
     chain_mode = "exact sizes (host sync before every allocation)" if a.exact else \
-        f"sync-free (capacity buffers, device-side counts; exact-size fallbacks incl. warm-up: image {runner.fallbacks}, " \
-        f"seam strip {strip_runner.fallbacks}; border walk: {'two-pass' if runner.two_pass else 'single-pass'} / " \
-        f"strip {'two-pass' if strip_runner.two_pass else 'single-pass'})"
+        f"td_chain (capacity workspace, device-side counts, {'CUDA-graph replay' if runner.use_graph else 'direct launches'}; " \
+        f"exact-size fallbacks incl. warm-up: image {runner.fallbacks}, seam strip {strip_runner.fallbacks})"
     stage_ms = {n: statistics.mean(e[i].elapsed_time(e[j]) for e in stage_ev) for (i, j), n in zip(pairs, names)}
     p1_ms_in_step = stage_ms[names[0]]
     if p5_ev:      # P5 ran on its own stream

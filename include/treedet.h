@@ -237,6 +237,46 @@ int td_ring_offsets(const long long* ring_off, const int* count, const long long
 int td_gather_rows(const void* const* in, void* const* out, const int* row_bytes, int k, const long long* sel, int n,
                    const long long* n_dev, void* stream);
 
+/* ---- The whole chain of one image as one host call per stage (CUDA-graph replay) -------------------
+ * Replaces, for a stream of images with the same tiling, the per-image host loops of
+ *   Predictor._process_and_save_single + process_and_stitch_predictions
+ *       (TreeDetection/prediction.py:197-265, TreeDetection/helpers.py:419-600)   -> td_chain_predict
+ *   process_geojson + process_features (TreeDetection/postprocessing.py:722-809, 478-720) -> td_chain_post
+ * Every variable-length intermediate lives, by capacity, in ONE caller-allocated device workspace; live
+ * counts stay on the device (16 int64 counters per output slot: [overflow flag, words, label pixels,
+ * point slots, -, -, traced rings, traced vertices, table rings, table vertices, after head, after NMS,
+ * final crowns, final vertices, -, -]); the static launch sequence is captured into a CUDA graph per
+ * (slot, input pointers) and replayed with one cudaGraphLaunch.  An overflow of a capacity raises a bit
+ * of counter 0 (1 = a buffer, 2 = NMS neighbour slots, 4 = contour slot of the single-pass walk) and
+ * the image has to be redone through the exact-size entry points above.
+ *   cfg   HOST 16 doubles: [mask_threshold, simplify_tolerance, area simplify tolerance (2.0),
+ *         confidence_threshold, area_min, area_max, iou_threshold, area_threshold,
+ *         containment_threshold, 0 ...]
+ *   caps  HOST 8 int64: [instances, packed words, label pixels, point slots, rings, vertices, NMS
+ *         neighbour slots per crown, contour rows per instance]
+ *   workspace: device memory, 256-byte aligned, td_chain_workspace_bytes(caps, n_slots) bytes
+ *   n_slots (1..8): output slots (results of slot s stay valid until slot s is used again)        */
+long long td_chain_workspace_bytes(const long long* caps, int n_slots);
+int td_chain_create(const double* cfg, const long long* caps, int n_slots, void* workspace,
+                    long long workspace_bytes, void** chain_out);
+int td_chain_destroy(void* chain);
+/*   byte offsets (HOST, 16 int64 out) of slot `slot`'s outputs inside the workspace: counters (16 i64),
+ *   table verts (V,2) f64, table ring_off (R+1) i64, table conf (R) f64, verts (V,2) f64 rounded,
+ *   ring_off (R+1) i64, poly_id (R) i64, conf (R) f64, area (R) f64, tree_height (R) f32, centroid (R,2)
+ *   f32, is_contained (R) u8, num_contained (R) i32, height arg-max xy (R,2) f32, ndvi stats (R,4) f32  */
+int td_chain_layout(const void* chain, int slot, long long* offsets16);
+/*   P2 + P3 + P4: boxes_net (N,4) f32, scores (N) f32, probs (N,28,28) f32, inst_tile (N) i32,
+ *   tile_dims (T,4) i32, tile_tf (T,6) f64, tile_boxes (T,4) f64 (helpers.py:280-303), all device      */
+int td_chain_predict(void* chain, int slot, const float* boxes_net, const float* scores, const float* probs,
+                     const int* inst_tile, int n_inst, const int* tile_dims, const double* tile_tf,
+                     const double* tile_boxes, int n_tiles, int use_graph, void* stream);
+/*   P9 head + P6 + P7 + P8 + P9 on the table of `slot`: ndvi / height device rasters (f32) with HOST
+ *   6-double transforms; combined != 0: get_metadata_within_polygon (shared grid), else the split pair;
+ *   select_params: the 14 HOST doubles of td_select_crowns                                         */
+int td_chain_post(void* chain, int slot, const float* ndvi, int ndvi_rows, int ndvi_cols, const double* ndvi_tf,
+                  const float* height, int height_rows, int height_cols, const double* height_tf, int combined,
+                  const double* select_params, int use_graph, void* stream);
+
 /* ---- P0a: seam strips ---------------------------------------------------------------------------
  * Replaces crop_single_image / merge_images / crop_image (TreeDetection/merging.py:34-110,
  * TreeDetection/helpers.py:1023-1085): mosaic of an image with its right (axis 0) or lower

@@ -486,9 +486,114 @@ def crown_stats_ndvi(px32, py32, ndvi32, transform):
     return res
 
 
+# ---- windowed forms (test infrastructure for FULL-SIZE scenes) ---------------------------------
+# The three functions above follow the reference literally: every crown is tested against EVERY raster
+# pixel (O(N * P): 10^4 crowns x 10^8 pixels at BASELINE config 2).  The forms below evaluate the same
+# arithmetic on a conservative pixel window around the crown's circle only.  The selected pixels, their
+# row-major order (which fixes numpy's pairwise float32 mean / variance and the first arg-max) and every
+# value are identical as long as the window covers the circle, which a margin of `_WINDOW_MARGIN` metres
+# (far above the float32 rounding of UTM coordinates, <= 0.5 m) guarantees for axis-aligned transforms;
+# tests/test_oracle_windowed.py checks them against the literal forms.
+_WINDOW_MARGIN = 3.0
+
+
+def _crown_window(cx, cy, r, transform, h, w):
+    a, b, c, d, e, f = transform[:6]
+    if b != 0.0 or d != 0.0 or a == 0.0 or e == 0.0 or not np.isfinite([cx, cy, r]).all():
+        return 0, h, 0, w
+    m = float(r) + _WINDOW_MARGIN
+    xa, xb = (float(cx) - m - c) / a, (float(cx) + m - c) / a
+    ya, yb = (float(cy) - m - f) / e, (float(cy) + m - f) / e
+    c0 = int(max(np.floor(min(xa, xb)) - 2, 0)); c1 = int(min(np.ceil(max(xa, xb)) + 3, w))
+    r0 = int(max(np.floor(min(ya, yb)) - 2, 0)); r1 = int(min(np.ceil(max(ya, yb)) + 3, h))
+    return r0, max(r1, r0), c0, max(c1, c0)
+
+
+def _window_coords(transform, r0, r1, c0, c1, dtype):
+    a, b, c, d, e, f = transform[:6]
+    rows, cols = np.meshgrid(np.arange(r0, r1), np.arange(c0, c1), indexing="ij")
+    x = a * cols + b * rows + c
+    y = d * cols + e * rows + f
+    return x.astype(dtype).ravel(), y.astype(dtype).ravel()
+
+
+def crown_stats_combined_windowed(px32, py32, ndvi32, height32, transform):
+    h, w = ndvi32.shape
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in
+           ("max_h", "hx", "hy", "ndvi_min", "ndvi_max", "ndvi_mean", "ndvi_var")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        r0, r1, c0, c1 = _crown_window(cx, cy, r, transform, h, w)
+        xs, ys = _window_coords(transform, r0, r1, c0, c1, np.float32)
+        d2 = (xs - cx) ** 2 + (ys - cy) ** 2
+        inside_n = d2 <= (r * 0.5) ** 2
+        inside_h = d2 <= r ** 2
+        for k, v in _stats_one(height32[r0:r1, c0:c1].ravel(), xs, ys, inside_h, ndvi32[r0:r1, c0:c1].ravel(),
+                               inside_n).items():
+            res[k][i] = v
+    return res
+
+
+def crown_stats_height_windowed(px32, py32, height32, transform):
+    h, w = height32.shape
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in ("max_h", "hx", "hy")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        r0, r1, c0, c1 = _crown_window(cx, cy, r, transform, h, w)
+        xs, ys = _window_coords(transform, r0, r1, c0, c1, np.float64)
+        inside = (xs - cx) ** 2 + (ys - cy) ** 2 <= r ** 2
+        for k, v in _stats_one(height32[r0:r1, c0:c1].ravel(), xs, ys, inside, None, None).items():
+            res[k][i] = v
+    return res
+
+
+def crown_stats_ndvi_windowed(px32, py32, ndvi32, transform):
+    h, w = ndvi32.shape
+    n = px32.shape[0]
+    res = {k: np.zeros(n, dtype=np.float32) for k in ("ndvi_min", "ndvi_max", "ndvi_mean", "ndvi_var")}
+    for i in range(n):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        r0, r1, c0, c1 = _crown_window(cx, cy, r, transform, h, w)
+        xs, ys = _window_coords(transform, r0, r1, c0, c1, np.float32)
+        inside = (xs - cx) ** 2 + (ys - cy) ** 2 <= r ** 2
+        for k, v in _stats_one(None, xs, ys, None, ndvi32[r0:r1, c0:c1].ravel(), inside).items():
+            res[k][i] = v
+    return res
+
+
 # ============================================================================
 # P8  containment   (postprocessing.py:408-476)
 # ============================================================================
+
+
+def containment_chunked(bounds, threshold, chunk=512):
+    """:func:`containment` evaluated over row blocks of the N x N matrices (same float32 arithmetic per
+    element; for crown tables whose N x N temporaries do not fit comfortably)."""
+    b = np.asarray(bounds, dtype=np.float32).reshape(-1, 4)
+    n = b.shape[0]
+    inner = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    rmax = np.full(n, -np.inf, dtype=np.float32)
+    any_c = np.zeros(n, dtype=bool)
+    num = np.zeros(n, dtype=np.int64)
+    has_nan = np.zeros(n, dtype=bool)
+    for o0 in range(0, n, chunk):
+        o = b[o0:o0 + chunk]
+        ix0 = np.maximum(o[:, 0][:, None], b[:, 0][None, :]); iy0 = np.maximum(o[:, 1][:, None], b[:, 1][None, :])
+        ix1 = np.minimum(o[:, 2][:, None], b[:, 2][None, :]); iy1 = np.minimum(o[:, 3][:, None], b[:, 3][None, :])
+        inter = np.maximum(0, ix1 - ix0) * np.maximum(0, iy1 - iy0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = inter / inner[None, :]
+        isc = ratio >= threshold
+        k = np.arange(o.shape[0])
+        isc[k, o0 + k] = False
+        has_nan |= np.isnan(ratio).any(axis=0)
+        rmax = np.fmax(rmax, np.nanmax(np.where(np.isnan(ratio), -np.inf, ratio), axis=0))
+        any_c |= isc.any(axis=0)
+        num[o0:o0 + chunk] = isc.sum(axis=1)
+    rmax = np.where(has_nan, np.float32(np.nan), rmax)
+    return rmax, any_c, num
 
 
 def containment(bounds, threshold):
@@ -560,11 +665,13 @@ def near_border(b, bounds, eps):
 
 
 def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, height_transform, height_bounds,
-                 pixel_x, pixel_y, cfg):
+                 pixel_x, pixel_y, cfg, large=False):
     """postprocessing.py:722-809 (process_geojson) + :478-720 (process_features), restated
     on arrays.  ``cfg``: dict with the config.yml keys.  Returns a list of feature dicts
     {poly_id, Confidence_score, Area, TreeHeight, Centroid, is_contained, num_contained,
-    coords} in output order, plus a debug dict."""
+    coords} in output order, plus a debug dict.  ``large``: full-size scenes -- the sparse NMS, the
+    windowed statistics and the chunked containment (each proven equal to the literal form in the tests)
+    instead of the N x N / N x P literal forms."""
     f32 = np.float32
     # 1. confidence filter, ids, simplify(2) area, area range
     feats = [(r, c) for r, c in zip(rings, conf) if c is not None and float(c) >= cfg["confidence_threshold"]]
@@ -580,8 +687,9 @@ def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, hei
         return [], debug
     bounds = {i: geom.Polygon(feats[i][0]).bounds for i in keep}
     # 3. NMS
-    removed = nms_bbox([bounds[i] for i in keep], [feats[i][1] for i in keep], [areas[i] for i in keep],
-                       cfg["iou_threshold"], cfg["area_threshold"])
+    removed = (nms_bbox_sparse if large else nms_bbox)([bounds[i] for i in keep], [feats[i][1] for i in keep],
+                                                       [areas[i] for i in keep], cfg["iou_threshold"],
+                                                       cfg["area_threshold"])
     F = [i for i, r in zip(keep, removed) if not r]
     debug["ids_after_nms"] = list(F)
     if not F:
@@ -592,11 +700,13 @@ def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, hei
     cent = centroids(px32, py32)
     t_eq = all(abs(a - b) < 1e-5 for a, b in zip(height_transform[:6], ndvi_transform[:6]))
     b_eq = all(abs(a - b) < 1e-3 for a, b in zip(height_bounds, ndvi_bounds))
+    s_comb, s_h, s_n = (crown_stats_combined_windowed, crown_stats_height_windowed, crown_stats_ndvi_windowed) \
+        if large else (crown_stats_combined, crown_stats_height, crown_stats_ndvi)
     if t_eq and b_eq:
-        st = crown_stats_combined(px32, py32, ndvi32, height32, ndvi_transform)
+        st = s_comb(px32, py32, ndvi32, height32, ndvi_transform)
     else:
-        st = dict(crown_stats_height(px32, py32, height32, height_transform))
-        st.update(crown_stats_ndvi(px32, py32, ndvi32, ndvi_transform))
+        st = dict(s_h(px32, py32, height32, height_transform))
+        st.update(s_n(px32, py32, ndvi32, ndvi_transform))
     heights, mean_ndvi, var_ndvi = st["max_h"], st["ndvi_mean"], st["ndvi_var"]
     debug.update(stats=st, centroid=cent, combined=bool(t_eq and b_eq))
     pre = []
@@ -622,7 +732,7 @@ def post_process(rings, conf, ndvi32, ndvi_transform, ndvi_bounds, height32, hei
             continue
         pre.append(k)
     b32 = np.array([bounds[i] for i in F], dtype=np.float32)
-    ratio, is_c, num_c = containment(b32, cfg["containment_threshold"])
+    ratio, is_c, num_c = (containment_chunked if large else containment)(b32, cfg["containment_threshold"])
     debug.update(pre=list(pre), is_contained=is_c, num_contained=num_c)
     contained_idx = [k for k in range(len(F)) if is_c[k]]
     selected = []

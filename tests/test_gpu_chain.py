@@ -1,6 +1,7 @@
-"""The sync-free chain (capacity buffers, device-side counts: pipeline.ChainRunner) must return
-exactly what the exact-size composition returns -- same crowns, same order, same bits -- and must
-fall back to it when a capacity is too small."""
+"""The sync-free chain (td_chain_*: capacity workspace, device-side counts, CUDA-graph replay, fused
+simplify; driven by pipeline.ChainRunner) must return exactly what the exact-size composition of the
+separate kernels returns -- same crowns, same order, same bits -- and must fall back to it when a
+capacity is too small."""
 import numpy as np
 import pytest
 import torch
@@ -33,22 +34,41 @@ def _same(a, b):
         np.testing.assert_array_equal(x, y, err_msg=f)
 
 
+@pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("ndsm_px", [0.2, 1.0])
-def test_dyn_chain_equals_exact_chain(dev, ndsm_px):
+def test_dyn_chain_equals_exact_chain(dev, ndsm_px, graph):
     sc, det, tile_tf, tile_boxes, rasters, p = _setup(dev, 11, ndsm_px=ndsm_px)
     table = pipeline.predict_stage(**det, tile_tf=tile_tf, tile_boxes=tile_boxes, p=p)
-    ref = pipeline.postprocess_stage(table, rasters(), p)
-    run = pipeline.ChainRunner(p)
+    ref = pipeline.postprocess_stage(table, rasters(), p, keep_debug=True)
+    run = pipeline.ChainRunner(p, use_graph=graph)
     n0, f0 = run.collect(run.submit(det, tile_tf, tile_boxes, rasters))       # exact path, learns capacities
     assert n0 == len(table)
     _same(f0, ref)
-    tickets = [run.submit(det, tile_tf, tile_boxes, rasters) for _ in range(3)]   # enqueued back to back
-    assert all(t[0] == "dyn" for t in tickets)
-    for t in tickets:
-        n, f = run.collect(t)
-        assert n == len(table) and len(f) == len(ref) and len(f) > 50
-        _same(f, ref)
+    r = rasters()                                                             # same raster buffers -> same graph
+    for rep in range(2):
+        tickets = [run.submit(det, tile_tf, tile_boxes, lambda: r) for _ in range(3)]   # enqueued back to back
+        assert all(t[0] == "dyn" for t in tickets)
+        for t in tickets:
+            n, f = run.collect(t)
+            assert n == len(table) and len(f) == len(ref) and len(f) > 50
+            _same(f, ref)
+            tab = run.table(run.last_counters, t[3])                          # the stitched table of that image
+            np.testing.assert_array_equal(tab.verts.cpu().numpy(), table.verts.cpu().numpy())
+            np.testing.assert_array_equal(tab.ring_off.cpu().numpy(), table.ring_off.cpu().numpy())
+            np.testing.assert_array_equal(tab.conf.cpu().numpy(), table.conf.cpu().numpy())
     assert run.fallbacks == 0
+
+
+def test_dyn_chain_too_many_in_flight(dev):
+    _, det, tile_tf, tile_boxes, rasters, p = _setup(dev, 12, size_px=1000)
+    run = pipeline.ChainRunner(p, n_slots=2)
+    run.collect(run.submit(det, tile_tf, tile_boxes, rasters))
+    t = [run.submit(det, tile_tf, tile_boxes, rasters) for _ in range(2)]
+    with pytest.raises(ops._lib.TreedetError):
+        run.submit(det, tile_tf, tile_boxes, rasters)
+    for x in t:
+        run.collect(x)
+    run.collect(run.submit(det, tile_tf, tile_boxes, rasters))
 
 
 def test_dyn_chain_other_image_same_capacities(dev):
@@ -64,22 +84,42 @@ def test_dyn_chain_other_image_same_capacities(dev):
     _same(f, ref)
 
 
-@pytest.mark.parametrize("small", ["words", "px", "ptslots", "rings", "verts", "nbr"])
+@pytest.mark.parametrize("small", ["inst", "words", "px", "ptslots", "rings", "verts", "nbr", "contours"])
 def test_capacity_overflow_falls_back(dev, small):
     sc, det, tile_tf, tile_boxes, rasters, p = _setup(dev, 31, size_px=1000)
     table = pipeline.predict_stage(**det, tile_tf=tile_tf, tile_boxes=tile_boxes, p=p)
     ref = pipeline.postprocess_stage(table, rasters(), p)
     run = pipeline.ChainRunner(p)
     run.collect(run.submit(det, tile_tf, tile_boxes, rasters))
-    run.caps[small] = 3                                                   # too small on purpose
+    if small == "nbr":                                                    # too small on purpose
+        run.nbr_per_crown = 1
+    elif small == "contours":
+        run.slot_contours = 0
+    else:
+        run.caps[small] = 3
+    run.chain = None
+    if small == "contours":
+        with pytest.raises(ops._lib.TreedetError):
+            run.submit(det, tile_tf, tile_boxes, rasters)                 # a zero capacity is refused outright
+        return
     t = run.submit(det, tile_tf, tile_boxes, rasters)
+    if small == "inst":                                                   # more instances than the workspace holds
+        assert t[0] == "done"
+        n, f = run.collect(t)
+        assert n == len(table)
+        _same(f, ref)
+        return
     assert t[0] == "dyn"
     n, f = run.collect(t)
     assert run.fallbacks == 1 and n == len(table)
     _same(f, ref)
-    n, f = run.collect(run.submit(det, tile_tf, tile_boxes, rasters))          # capacities were re-learnt
-    assert run.fallbacks == 1
-    _same(f, ref)
+    for _ in range(4):        # capacities were re-learnt (the neighbour slots double per fallback: 1 -> 2 -> 4 -> 8)
+        before = run.fallbacks
+        n, f = run.collect(run.submit(det, tile_tf, tile_boxes, rasters))
+        _same(f, ref)
+        if run.fallbacks == before:
+            break
+    assert run.fallbacks == before and (small == "nbr" or run.fallbacks == 1)
 
 
 def test_bookkeeping_ops(dev):

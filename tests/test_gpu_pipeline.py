@@ -137,6 +137,38 @@ def test_postprocess_stage_matches_reference_golden(dev, name):
     np.testing.assert_array_equal(f.verts.cpu().numpy(), g["out_verts"])
 
 
+@pytest.mark.parametrize("name", ["combined", "split"])
+def test_postprocess_stage_matches_reference_on_threshold_grid(dev, name):
+    """nested crowns (num_contained up to 7), empty statistics sets (-1) and 9 rows of the reference's
+    hyper-parameter grid (supplementary/postprocessing_hyperparams.py:6-11), against the outputs of the
+    reference's own process_features / process_containment_features (tests/golden/make_golden_grid.py)"""
+    from tests.test_oracle_golden import grid_cfg
+    g = np.load(os.path.join(G, f"grid_{name}.npz"))
+    table = pipeline.CrownTable(torch.from_numpy(g["rings_verts"]).to(dev), torch.from_numpy(g["rings_off"]).to(dev),
+                                torch.from_numpy(g["conf"]).to(dev))
+    rasters = {"ndvi": torch.from_numpy(g["ndvi"]).to(dev), "ndvi_transform": tuple(g["ndvi_transform"]),
+               "ndvi_bounds": geo.BoundingBox(*g["ndvi_bounds"]), "height": torch.from_numpy(g["height"]).to(dev),
+               "height_transform": tuple(g["height_transform"]), "height_bounds": geo.BoundingBox(*g["height_bounds"]),
+               "pixel_x": float(g["pixel"][0]), "pixel_y": float(g["pixel"][1])}
+    for k, combo in enumerate(g["combos"]):
+        p = pipeline.PipelineParams.from_config(grid_cfg(combo))
+        f = pipeline.postprocess_stage(table, rasters, p, keep_debug=True)
+        ex = f.extras
+        assert ex["combined"] == (name == "combined")
+        np.testing.assert_array_equal(ex["pid_after_nms"].cpu().numpy(), g[f"c{k}_ids_after_nms"])
+        np.testing.assert_array_equal(ex["num_contained"].cpu().numpy(), g[f"c{k}_p8_num_contained"])
+        np.testing.assert_array_equal(ex["is_contained"].cpu().numpy().astype(bool), g[f"c{k}_p8_is_contained"])
+        np.testing.assert_array_equal(ex["containment_ratio"].cpu().numpy(), g[f"c{k}_p8_ratio"])
+        np.testing.assert_array_equal(f.poly_id.cpu().numpy(), g[f"c{k}_out_poly_id"])
+        np.testing.assert_array_equal(f.area.cpu().numpy(), g[f"c{k}_out_area"])
+        np.testing.assert_array_equal(f.tree_height.cpu().numpy(), g[f"c{k}_out_height"])
+        np.testing.assert_array_equal(f.centroid.cpu().numpy().astype(np.float64), g[f"c{k}_out_centroid"])
+        np.testing.assert_array_equal(f.is_contained.cpu().numpy().astype(bool), g[f"c{k}_out_is_contained"])
+        np.testing.assert_array_equal(f.num_contained.cpu().numpy(), g[f"c{k}_out_num_contained"])
+        np.testing.assert_array_equal(f.ring_off.cpu().numpy(), g[f"c{k}_out_off"])
+        np.testing.assert_array_equal(f.verts.cpu().numpy(), g[f"c{k}_out_verts"])
+
+
 def test_nms_golden(dev):
     g = np.load(os.path.join(G, "nms.npz"))
     for case in "abc":

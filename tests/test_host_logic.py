@@ -139,14 +139,14 @@ def test_geotiff_round_trip_with_geo_tags(tmp_path):
 
 
 def test_chain_runner_capacity_planning():
-    """capacities grow, never shrink, and the NMS neighbour capacity follows the ring capacity"""
+    """capacities grow, never shrink; a grown capacity drops the chain object so that it is rebuilt"""
     run = pipeline.ChainRunner(pipeline.PipelineParams())
-    run._learn({"words": 1000, "px": 50000, "ptslots": 9000, "contours": 40, "points": 700, "rings": 35, "verts": 600})
+    run._learn({"inst": 900, "words": 1000, "px": 50000, "ptslots": 9000, "rings": 35, "verts": 600})
     first = dict(run.caps)
-    assert first["words"] == int(1000 * 1.25) + 1024 and first["nbr"] == 8 * first["rings"]
+    assert first["words"] == int(1000 * 1.25) + 1024 and first["inst"] == int(900 * 1.25) + 1024
+    run.chain = "sentinel"
     run._learn({"words": 10, "px": 10, "ptslots": 10, "rings": 3, "verts": 5})
-    assert run.caps == first
-    run.nbr_per_crown = 16
+    assert run.caps == first and run.chain == "sentinel"
     run._learn({"words": 5000, "px": 10, "ptslots": 10, "rings": 300, "verts": 5})
     assert run.caps["words"] == int(5000 * 1.25) + 1024 and run.caps["px"] == first["px"]
-    assert run.caps["nbr"] == 16 * run.caps["rings"] and run.caps["contours"] == first["contours"]
+    assert run.caps["rings"] == int(300 * 1.25) + 1024 and run.chain is None

@@ -88,3 +88,41 @@ def test_config1_port_matches_reference():
     np.testing.assert_array_equal(np.array([f["Area"] for f in out]), g["out_area"])
     np.testing.assert_array_equal(np.array([f["TreeHeight"] for f in out], dtype=np.float32), g["out_height"])
     np.testing.assert_array_equal(np.array([p for f in out for p in f["coords"]]).reshape(-1, 2), g["out_verts"])
+
+
+GRID_KEYS = ("confidence_threshold", "containment_threshold", "iou_threshold", "ndvi_mean_threshold", "ndvi_var_threshold",
+             "use_overlap")
+
+
+def grid_cfg(combo):
+    cfg = dict(CFG)
+    cfg.update({k: (bool(v) if k == "use_overlap" else float(v)) for k, v in zip(GRID_KEYS, combo)})
+    return cfg
+
+
+@pytest.mark.parametrize("name", ["combined", "split"])
+def test_post_process_port_matches_reference_on_threshold_grid(name):
+    """nested crowns (num_contained up to 7), empty statistics sets (-1), 9 rows of the reference's
+    hyper-parameter grid (supplementary/postprocessing_hyperparams.py:6-11): tests/golden/make_golden_grid.py"""
+    g = np.load(os.path.join(G, f"grid_{name}.npz"))
+    rings = rings_of(g["rings_verts"], g["rings_off"])
+    seen_nc, seen_empty = set(), 0
+    for k, combo in enumerate(g["combos"]):
+        cfg = grid_cfg(combo)
+        out, dbg = port.post_process(rings, g["conf"].tolist(), g["ndvi"], tuple(g["ndvi_transform"]),
+                                     tuple(g["ndvi_bounds"]), g["height"], tuple(g["height_transform"]),
+                                     tuple(g["height_bounds"]), float(g["pixel"][0]), float(g["pixel"][1]), cfg)
+        assert dbg["combined"] == (name == "combined")
+        np.testing.assert_array_equal(np.array(dbg["ids_after_nms"]), g[f"c{k}_ids_after_nms"])
+        np.testing.assert_array_equal(np.asarray(dbg["num_contained"]), g[f"c{k}_p8_num_contained"])
+        np.testing.assert_array_equal(np.asarray(dbg["is_contained"]).astype(bool), g[f"c{k}_p8_is_contained"])
+        np.testing.assert_array_equal(np.array([int(f["poly_id"]) for f in out]), g[f"c{k}_out_poly_id"])
+        np.testing.assert_array_equal(np.array([f["Area"] for f in out]), g[f"c{k}_out_area"])
+        np.testing.assert_array_equal(np.array([f["TreeHeight"] for f in out], dtype=np.float32), g[f"c{k}_out_height"])
+        np.testing.assert_array_equal(np.array([f["Centroid"] for f in out]).reshape(-1, 2), g[f"c{k}_out_centroid"])
+        np.testing.assert_array_equal(np.array([f["is_contained"] for f in out]), g[f"c{k}_out_is_contained"])
+        np.testing.assert_array_equal(np.array([f["num_contained"] for f in out]), g[f"c{k}_out_num_contained"])
+        np.testing.assert_array_equal(np.array([p for f in out for p in f["coords"]]).reshape(-1, 2), g[f"c{k}_out_verts"])
+        seen_nc |= set(int(v) for v in g[f"c{k}_p8_num_contained"])
+        seen_empty += int((g[f"c{k}_out_height"] == -1).sum())
+    assert {0, 1, 2, 3, 4, 5} <= seen_nc and seen_empty > 0

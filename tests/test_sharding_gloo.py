@@ -43,7 +43,14 @@ def _worker(rank, world, port, out):
 
 def test_halo_rows_matches_reference_strip_height():
     # (50 + 2*20) * 3 = 270 px strip, half from each image
-    assert sharding.halo_rows(50, 20, 3) == 135
+    assert sharding.halo_rows(50, 20, 3) == 135 and sharding.strip_height(50, 20, 3) == 270
+    # odd strip (45 + 2*20) * 3 = 255: crop_image starts at mh // 2 - sh // 2, i.e. 127 rows above the seam
+    # and 128 below it -- the extra row comes from the lower neighbour (what merging.py cuts on one GPU)
+    assert sharding.strip_height(45, 20, 3) == 255 and sharding.halo_rows(45, 20, 3) == 128
+    H = 400
+    mh, sh = 2 * H, 255
+    top = max(mh // 2 - sh // 2, 0)
+    assert (H - top, top + sh - H) == (sh // 2, sharding.halo_rows(45, 20, 3))
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -44,9 +44,38 @@ struct ContourCounts {
   int n_ring_verts;   // their points + the closing point where first != last (:238-239)
 };
 
+// How the three bit planes are accessed: through generic pointers (anywhere), or -- when the caller
+// KNOWS they sit in shared memory -- with explicit shared-space instructions (a generic access costs a
+// trip through the L1TEX pipe even when it lands in shared memory; the walk is a chain of dependent
+// plane reads, so that latency is its critical path).
+struct GenericMem {
+  TD_HD static uint32_t ld(const uint32_t* p) { return *p; }
+  TD_HD static void st(uint32_t* p, uint32_t v) { *p = v; }
+};
+#if defined(__CUDACC__)
+struct SharedMem {
+  __device__ static uint32_t ld(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+  }
+  __device__ static void st(uint32_t* p, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  }
+};
+#endif
+
+TD_HD inline int highest_bit(uint32_t v) {   // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)v);
+#else
+  return 31 - __builtin_clz(v);
+#endif
+}
+
 // LabelT: unsigned short in general; unsigned char when the window has < 255 borders (known
 // from the count pass), which halves the shared-memory footprint of the emit pass.
-template <typename LabelT>
+template <typename LabelT, typename Mem = GenericMem>
 struct RasterT {
   const uint32_t* fg;
   uint32_t* visited;
@@ -56,21 +85,22 @@ struct RasterT {
 
   TD_HD bool is_fg(int x, int y) const {
     if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) return false;
-    return (fg[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+    return (Mem::ld(fg + (size_t)y * wpr + (x >> 5)) >> (x & 31)) & 1u;
   }
   TD_HD uint32_t word(const uint32_t* plane, int y, int wi) const {
     if (wi < 0 || wi >= wpr) return 0u;
-    return plane[(size_t)y * wpr + wi];
+    return Mem::ld(plane + (size_t)y * wpr + wi);
   }
   TD_HD void mark(int x, int y, bool right_flag, int lab) {
     const size_t wi = (size_t)y * wpr + (x >> 5);
     const uint32_t bit = 1u << (x & 31);
+    const uint32_t v = Mem::ld(visited + wi);
     if (right_flag) {
-      right[wi] |= bit;
-      visited[wi] |= bit;
+      Mem::st(right + wi, Mem::ld(right + wi) | bit);
+      Mem::st(visited + wi, v | bit);
       if (label) label[(size_t)y * w + x] = (LabelT)lab;
-    } else if (!(visited[wi] & bit)) {
-      visited[wi] |= bit;
+    } else if (!(v & bit)) {
+      Mem::st(visited + wi, v | bit);
       if (label) label[(size_t)y * w + x] = (LabelT)lab;
     }
   }
@@ -82,11 +112,7 @@ struct RasterT {
     const int b = (x - 1) & 31;
     if (b < 31) m &= (2u << b) - 1u;
     while (true) {
-      if (m) {
-        int hb = 31;
-        while (!((m >> hb) & 1u)) --hb;
-        return (int)label[(size_t)y * w + (wi * 32 + hb)];
-      }
+      if (m) return (int)label[(size_t)y * w + (wi * 32 + highest_bit(m))];
       if (--wi < 0) return -1;
       m = word(visited, y, wi);
     }

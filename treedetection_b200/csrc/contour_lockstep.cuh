@@ -18,10 +18,11 @@
 namespace td {
 
 enum LaneMode { kScan = 0, kFollow = 1, kDone = 2 };
+constexpr int kScanRows = 4;
 
-template <typename LabelT>
+template <typename LabelT, typename Mem = GenericMem>
 struct LaneState {
-  RasterT<LabelT> R;
+  RasterT<LabelT, Mem> R;
   ContourOut* out;      // null: count only
   ContourCounts cc;
   int mode;
@@ -44,27 +45,27 @@ TD_HD inline int ffs32(uint32_t v) {   // index of the lowest set bit, v != 0
 }
 
 // bits (x-1, x, x+1) of row y as a 3-bit value, zero outside the window
-template <typename LabelT>
-TD_HD inline uint32_t row3(const RasterT<LabelT>& R, int x, int y) {
+template <typename LabelT, typename Mem>
+TD_HD inline uint32_t row3(const RasterT<LabelT, Mem>& R, int x, int y) {
   if ((unsigned)y >= (unsigned)R.h) return 0u;
   const int wi = x >> 5, b = x & 31;
   const uint32_t* row = R.fg + (size_t)y * R.wpr;
-  const uint32_t lo = row[wi];
-  if (b == 0) return (wi > 0 ? (row[wi - 1] >> 31) : 0u) | ((lo & 3u) << 1);
-  if (b == 31) return ((lo >> 30) & 3u) | ((wi + 1 < R.wpr ? (row[wi + 1] & 1u) : 0u) << 2);
+  const uint32_t lo = Mem::ld(row + wi);
+  if (b == 0) return (wi > 0 ? (Mem::ld(row + wi - 1) >> 31) : 0u) | ((lo & 3u) << 1);
+  if (b == 31) return ((lo >> 30) & 3u) | ((wi + 1 < R.wpr ? (Mem::ld(row + wi + 1) & 1u) : 0u) << 2);
   return (lo >> (b - 1)) & 7u;
 }
 
 // 8-neighbour foreground mask of (x, y), bit k = direction k (E, NE, N, NW, W, SW, S, SE)
-template <typename LabelT>
-TD_HD inline uint32_t neighbours(const RasterT<LabelT>& R, int x, int y) {
+template <typename LabelT, typename Mem>
+TD_HD inline uint32_t neighbours(const RasterT<LabelT, Mem>& R, int x, int y) {
   const uint32_t t = row3(R, x, y - 1), m = row3(R, x, y), b = row3(R, x, y + 1);
   return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
          ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
 }
 
-template <typename LabelT>
-TD_HD inline void lane_emit(LaneState<LabelT>& S, int x, int y) {
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_emit(LaneState<LabelT, Mem>& S, int x, int y) {
   if (S.out && S.cc.n_points + S.npts < S.out->cap_points) {
     short* p = S.out->pts + 2 * ((size_t)S.cc.n_points + S.npts);
     p[0] = (short)x;
@@ -76,8 +77,8 @@ TD_HD inline void lane_emit(LaneState<LabelT>& S, int x, int y) {
   ++S.npts;
 }
 
-template <typename LabelT>
-TD_HD inline void lane_finish_border(LaneState<LabelT>& S) {
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_finish_border(LaneState<LabelT, Mem>& S) {
   const int idx = S.cc.n_contours;
   if (S.out && idx < S.out->cap_contours) {
     S.out->parent[idx] = S.parent;
@@ -96,8 +97,8 @@ TD_HD inline void lane_finish_border(LaneState<LabelT>& S) {
   S.mode = kScan;
 }
 
-template <typename LabelT>
-TD_HD inline void lane_init(LaneState<LabelT>& S, ContourOut* out) {
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_init(LaneState<LabelT, Mem>& S, ContourOut* out) {
   S.out = out;
   S.cc.n_contours = S.cc.n_points = S.cc.n_rings = S.cc.n_ring_verts = 0;
   S.y = 0; S.wi = 0; S.min_o = 0; S.min_h = 0;
@@ -108,9 +109,9 @@ TD_HD inline void lane_init(LaneState<LabelT>& S, ContourOut* out) {
 }
 
 // one micro-step of one lane
-template <typename LabelT>
-TD_HD inline void lane_step(LaneState<LabelT>& S) {
-  RasterT<LabelT>& R = S.R;
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_step(LaneState<LabelT, Mem>& S) {
+  RasterT<LabelT, Mem>& R = S.R;
   if (S.mode == kFollow) {
     // ---- one step along the border ------------------------------------------------------------
     const int s_end = S.s;
@@ -137,7 +138,9 @@ TD_HD inline void lane_step(LaneState<LabelT>& S) {
     return;
   }
   if (S.mode != kScan) return;
-  // ---- advance the raster scan to the next border start ----------------------------------------
+  // ---- advance the raster scan to the next border start (up to kScanRows rows per micro-step: rows
+  // without a start are the common case and cost one word test each) ---------------------------------
+  for (int scanned = 0; scanned < kScanRows; ++scanned) {
   const int y = S.y;
   for (; S.wi < R.wpr; ++S.wi) {
     const int wi = S.wi;
@@ -172,14 +175,12 @@ TD_HD inline void lane_step(LaneState<LabelT>& S) {
     // first neighbour clockwise from west (outer) / east (hole)
     const int s_end = hole ? 0 : 4;
     const uint32_t m = neighbours(R, x, y);
-    int s = s_end;
-    bool found = false;
-    for (int j = 0; j < 8 && !found; ++j) {
-      s = (s - 1) & 7;
-      found = (m >> s) & 1u;
-      if (s == s_end) break;
-    }
-    if (!found || s == s_end) {   // isolated pixel
+    // directions s_end - 1, s_end - 2, ... s_end - 7: bit t of the rotated mask is direction s_end + t,
+    // so the first hit clockwise is the HIGHEST set bit among t = 7 .. 1
+    const uint32_t rot = ((m | (m << 8)) >> s_end) & 0xfeu;
+    const bool found = rot != 0u;
+    const int s = found ? ((s_end + highest_bit(rot)) & 7) : s_end;
+    if (!found) {   // isolated pixel (the start pixel's own s_end neighbour is background by construction)
       R.mark(x, y, true, S.cc.n_contours);
       lane_emit(S, x, y);
       lane_finish_border(S);
@@ -194,7 +195,8 @@ TD_HD inline void lane_step(LaneState<LabelT>& S) {
   }
   // row exhausted
   S.wi = 0; S.min_o = 0; S.min_h = 0;
-  if (++S.y >= R.h) S.mode = kDone;
+  if (++S.y >= R.h) { S.mode = kDone; return; }
+  }
 }
 
 }  // namespace td

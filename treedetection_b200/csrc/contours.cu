@@ -26,19 +26,20 @@ constexpr int kSmemPerWarpDefault = 32 * 1024;   // bit planes of the 32 windows
 // the launch are resident at once (one wave): the budget shrinks from 32 KB as far as needed for
 // ceil(warps / SMs) CTAs to fit the 227 KB of an SM, but not below 16 KB (windows that do not fit
 // use the global scratch planes, which costs more than a second wave).
-int smem_per_warp(int n_inst) {
+int smem_per_warp(int n_inst, int lanes = 32) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("TREEDET_TRACE_SMEM");
     forced = e && atoi(e) > 0 ? atoi(e) : 0;
   }
   if (forced) return forced;
-  const int warps = td_div_up(n_inst, 32);
+  const int warps = td_div_up(n_inst, lanes);
   const int per_sm = td_div_up(warps, td_num_sms());
-  int v = kSmemPerWarpDefault;
+  const int full = kSmemPerWarpDefault * lanes / 32, least = 16 * 1024 * lanes / 32;
+  int v = full;
   if (per_sm > 0) {
     const int fit = ((227 * 1024) / per_sm - 1024) & ~1023;      // 1 KB per CTA is reserved by the system
-    if (fit < v) v = fit < 16 * 1024 ? kSmemPerWarpDefault : fit;
+    if (fit < v) v = fit < least ? full : fit;
   }
   return v;
 }
@@ -49,8 +50,8 @@ int smem_per_warp(int n_inst) {
 // two scratch planes) are packed into the warp's shared memory by a warp prefix sum over the
 // windows' sizes; windows that do not fit (rare, large boxes) use the global scratch planes.
 // Labels (needed only for the parent lookup at a border start) stay in global memory.
-template <typename LabelT>
-__device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_t* __restrict__ bits,
+template <typename LabelT, typename Mem>
+__device__ bool stage_windows(td::RasterT<LabelT, Mem>& R, bool active, const uint32_t* __restrict__ bits,
                               const int* __restrict__ win, const long long* __restrict__ word_off, int i,
                               uint32_t* __restrict__ planes, long long total_words, unsigned char* smem,
                               int smem_bytes) {
@@ -96,6 +97,7 @@ __device__ void stage_windows(td::RasterT<LabelT>& R, bool active, const uint32_
     R.right = planes + total_words + woff;
   }
   R.label = nullptr;
+  return in_smem || nwords == 0;
 }
 
 __global__ void __launch_bounds__(32)
@@ -254,12 +256,14 @@ struct WalkArgs {
   int smem_bytes;
 };
 
-__global__ void __launch_bounds__(32) trace_walk_kernel(WalkArgs A) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  const bool active = i < A.n;
-  td::LaneState<unsigned short> S;
-  stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem, A.smem_bytes);
+// kLanes instances per warp (the other lanes idle): the walk is a chain of dependent shared-memory
+// reads, so what hides its latency is the number of resident WARPS, and an image only has n / 32 of them
+// with full warps (7 per SM at 34 k instances); 16 instances per warp double that at the price of idle
+// issue slots nobody was using.  When all windows of the warp were staged into shared memory (nearly
+// always) the planes are accessed with shared-space instructions (td::SharedMem).
+template <typename Mem>
+__device__ __forceinline__ void walk_lanes(td::LaneState<unsigned short, Mem>& S, const WalkArgs& A, int i,
+                                           bool active) {
   const size_t c0 = (size_t)(active ? i : 0) * A.cap_contours;
   td::ContourOut out;
   out.parent = A.ct_parent + c0;
@@ -282,6 +286,24 @@ __global__ void __launch_bounds__(32) trace_walk_kernel(WalkArgs A) {
   A.counts[4 * i + 3] = over ? 0 : S.cc.n_ring_verts;
   A.sizes_kn[i] = over ? 0 : S.cc.n_rings;
   A.sizes_kn[(size_t)A.n + i] = over ? 0 : S.cc.n_ring_verts;
+}
+
+template <int kLanes>
+__global__ void __launch_bounds__(32) trace_walk_kernel(WalkArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x;
+  const int i = blockIdx.x * kLanes + lane;
+  const bool active = lane < kLanes && i < A.n;
+  td::LaneState<unsigned short, td::SharedMem> S;
+  const bool ok = stage_windows(S.R, active, A.bits, A.win, A.word_off, i, A.planes, A.total_words, smem, A.smem_bytes);
+  if (__all_sync(0xffffffffu, ok)) {
+    walk_lanes(S, A, i, active);
+  } else {      // some window did not fit the warp's shared memory: generic accesses for this warp
+    td::LaneState<unsigned short, td::GenericMem> G;
+    G.R.fg = S.R.fg; G.R.visited = S.R.visited; G.R.right = S.R.right; G.R.label = nullptr;
+    G.R.w = S.R.w; G.R.h = S.R.h; G.R.wpr = S.R.wpr;
+    walk_lanes(G, A, i, active);
+  }
 }
 
 // slot form of trace_rings_kernel: one warp per instance
@@ -401,8 +423,13 @@ extern "C" int td_trace_walk(const uint32_t* bits, const int* win, const long lo
   A.labels = labels; A.px_off = px_off; A.pts_off = pts_off; A.cap_contours = cap_contours;
   A.ct_parent = ct_int6; A.ct_npts = ct_int6 + nc; A.ct_ptoff = ct_int6 + 2 * nc; A.ct_scratch = ct_int6 + 3 * nc;
   A.ct_hole = ct_hole; A.pts = pts; A.counts = counts; A.sizes_kn = sizes_kn; A.flag = flag;
-  A.smem_bytes = smem_per_warp(n_inst);
-  trace_walk_kernel<<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
+  static int lanes = 0;
+  if (lanes == 0) { const char* e = getenv("TREEDET_TRACE_LANES"); lanes = e && atoi(e) > 0 ? atoi(e) : 16; }
+  const int L = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
+  A.smem_bytes = smem_per_warp(n_inst, L);
+  if (L == 32) trace_walk_kernel<32><<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
+  else if (L == 16) trace_walk_kernel<16><<<td_div_up(n_inst, 16), 32, A.smem_bytes, st>>>(A);
+  else trace_walk_kernel<8><<<td_div_up(n_inst, 8), 32, A.smem_bytes, st>>>(A);
   TD_CHECK_LAUNCH("td_trace_walk");
   return TD_OK;
 }

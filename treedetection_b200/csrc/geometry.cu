@@ -13,6 +13,7 @@
 // kernel (td_take_rings) gathers the surviving vertices once the caller has scanned the counts.
 #include <cstdlib>
 
+#include "chain_internal.cuh"
 #include "common.cuh"
 #include "simplify_core.cuh"
 
@@ -123,7 +124,7 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
 __global__ void take_rings_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
                                   const long long* __restrict__ sel, int n_out, const int* __restrict__ scratch,
                                   const long long* __restrict__ dst_off, double* __restrict__ out_verts,
-                                  const long long* __restrict__ n_dev) {
+                                  const long long* __restrict__ n_dev, int round3) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n_out || (n_dev && q >= *n_dev)) return;
@@ -134,8 +135,13 @@ __global__ void take_rings_kernel(const double* __restrict__ verts, const long l
   const int* sc = scratch ? scratch + 5 * v0 : nullptr;
   for (int k = lane; k < cnt; k += 32) {
     const long long s = v0 + (sc ? sc[k] : k);
-    out_verts[2 * (o + k)] = verts[2 * s];
-    out_verts[2 * (o + k) + 1] = verts[2 * s + 1];
+    double x = verts[2 * s], y = verts[2 * s + 1];
+    if (round3) {   // round_coordinates (utilities.py:146-161): round(v * 1000) / 1000, half to even
+      x = __ddiv_rn(rint(__dmul_rn(x, 1000.0)), 1000.0);
+      y = __ddiv_rn(rint(__dmul_rn(y, 1000.0)), 1000.0);
+    }
+    out_verts[2 * (o + k)] = x;
+    out_verts[2 * (o + k) + 1] = y;
   }
 }
 
@@ -164,14 +170,20 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
 // out ring q = ring sel[q] of the input; dst_off (n_out + 1) = offsets of the output rings
 // (lengths = kept counts when `scratch` holds the index lists of td_simplify_rings, else
 // the source ring lengths).
-extern "C" int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
-                             const int* scratch, const long long* dst_off, double* out_verts,
-                             const long long* n_dev, void* stream) {
+int td_take_rings_ex(const double* verts, const long long* ring_off, const long long* sel, int n_out,
+                     const int* scratch, const long long* dst_off, double* out_verts, const long long* n_dev,
+                     int round3, cudaStream_t st) {
   TD_ARG(n_out >= 0);
   if (n_out == 0) return TD_OK;
   TD_ARG(verts && ring_off && sel && dst_off && out_verts);
-  take_rings_kernel<<<td_div_up((long long)n_out * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      verts, ring_off, sel, n_out, scratch, dst_off, out_verts, n_dev);
+  take_rings_kernel<<<td_div_up((long long)n_out * 32, 256), 256, 0, st>>>(verts, ring_off, sel, n_out, scratch,
+                                                                           dst_off, out_verts, n_dev, round3);
   TD_CHECK_LAUNCH("td_take_rings");
   return TD_OK;
+}
+
+extern "C" int td_take_rings(const double* verts, const long long* ring_off, const long long* sel, int n_out,
+                             const int* scratch, const long long* dst_off, double* out_verts,
+                             const long long* n_dev, void* stream) {
+  return td_take_rings_ex(verts, ring_off, sel, n_out, scratch, dst_off, out_verts, n_dev, 0, (cudaStream_t)stream);
 }

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "chain_internal.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -511,12 +512,12 @@ extern "C" int td_bbox_nms_ordered_dyn(const double* bounds, const double* conf,
   return nms_impl(bounds, conf, area, n, n_dev, iou_threshold, area_threshold, nbr_cap, flag, removed, stream);
 }
 
-extern "C" int td_containment(const float* bounds32, int n, double threshold, float* ratio_max,
-                              unsigned char* is_contained, int* num_contained, const long long* n_dev, void* stream) {
+// bounds64 (N,4) f64 (cast to float32 here, as cp.array(..., dtype=float32) does) or bounds32 (N,4) f32
+int td_containment_ex(const double* bounds64, const float* bounds32, int n, double threshold, float* ratio_max,
+                      unsigned char* is_contained, int* num_contained, const long long* n_dev, cudaStream_t st) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
-  TD_ARG(bounds32 && ratio_max && is_contained && num_contained);
-  cudaStream_t st = (cudaStream_t)stream;
+  TD_ARG((bounds32 || bounds64) && ratio_max && is_contained && num_contained);
   td_ensure_pool();
   Scratch sc(st);
   float4* box32 = (float4*)sc.get(sizeof(float4) * n);
@@ -524,7 +525,8 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   if (!box32 || !gp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
   const int blocks = td_div_up(n, 256);
   grid_init_kernel<<<1, 1, 0, st>>>(gp);
-  box32_from_f32_kernel<<<blocks, 256, 0, st>>>(bounds32, n, box32, gp, n_dev);
+  if (bounds64) prep_boxes_kernel<<<blocks, 256, 0, st>>>(bounds64, n, box32, gp, n_dev);
+  else box32_from_f32_kernel<<<blocks, 256, 0, st>>>(bounds32, n, box32, gp, n_dev);
   TD_CHECK_LAUNCH("containment prep");
   PairGrid g;
   g.box32 = box32; g.gp = gp; g.n = n; g.n_dev = n_dev;
@@ -539,4 +541,13 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   containment_kernel<<<blocks, 256, 0, st>>>(g, thr, ratio_max, is_contained, num_contained);
   TD_CHECK_LAUNCH("containment");
   return TD_OK;
+}
+
+extern "C" int td_containment(const float* bounds32, int n, double threshold, float* ratio_max,
+                              unsigned char* is_contained, int* num_contained, const long long* n_dev, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(bounds32);
+  return td_containment_ex(nullptr, bounds32, n, threshold, ratio_max, is_contained, num_contained, n_dev,
+                           (cudaStream_t)stream);
 }

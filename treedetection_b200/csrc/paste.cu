@@ -17,6 +17,7 @@
 //     w   = u - floor(u);  e = 1 - w      (x axis; n, s on the y axis)
 //     out = fma(se, n*w, fma(sw, n*e, fma(ne, s*w, nw * (s*e))))   zero padded
 //     bit = out >= threshold
+#include "chain_internal.cuh"
 #include "common.cuh"
 
 namespace {
@@ -31,9 +32,15 @@ constexpr int kPasteThreads = 128;  // 4 warps per instance
 __global__ void paste_plan_kernel(const float* __restrict__ boxes_net, const int* __restrict__ inst_tile,
                                   const int* __restrict__ tile_dims, int n, float* __restrict__ boxes_px,
                                   int* __restrict__ win, long long* __restrict__ nwords,
-                                  long long* __restrict__ npx) {
+                                  long long* __restrict__ npx, const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (n_dev && i >= *n_dev) {   // capacity tail (n is then the capacity): an empty window, nothing read
+    win[4 * i + 0] = 0; win[4 * i + 1] = 0; win[4 * i + 2] = 0; win[4 * i + 3] = 0;
+    nwords[i] = 0;
+    if (npx) { npx[i] = 0; npx[(size_t)n + i] = 0; }
+    return;
+  }
   const int t = inst_tile[i];
   const int out_h = tile_dims[4 * t + 0], out_w = tile_dims[4 * t + 1];
   const int net_h = tile_dims[4 * t + 2], net_w = tile_dims[4 * t + 3];
@@ -205,16 +212,23 @@ __global__ void paste_values_kernel(const float* __restrict__ boxes_px, const in
 
 }  // namespace
 
-extern "C" int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst,
-                             int n_tiles, float* boxes_px, int* win, long long* nwords, long long* npx,
-                             void* stream) {
+int td_paste_plan_ex(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst, int n_tiles,
+                     float* boxes_px, int* win, long long* nwords, long long* npx, const long long* n_dev,
+                     cudaStream_t st) {
   TD_ARG(n_inst >= 0 && n_tiles >= 0);
   if (n_inst == 0) return TD_OK;
   TD_ARG(boxes_net && inst_tile && tile_dims && boxes_px && win && nwords);
-  paste_plan_kernel<<<td_div_up(n_inst, 256), 256, 0, (cudaStream_t)stream>>>(boxes_net, inst_tile, tile_dims, n_inst,
-                                                                              boxes_px, win, nwords, npx);
+  paste_plan_kernel<<<td_div_up(n_inst, 256), 256, 0, st>>>(boxes_net, inst_tile, tile_dims, n_inst, boxes_px, win,
+                                                            nwords, npx, n_dev);
   TD_CHECK_LAUNCH("td_paste_plan");
   return TD_OK;
+}
+
+extern "C" int td_paste_plan(const float* boxes_net, const int* inst_tile, const int* tile_dims, int n_inst,
+                             int n_tiles, float* boxes_px, int* win, long long* nwords, long long* npx,
+                             void* stream) {
+  return td_paste_plan_ex(boxes_net, inst_tile, tile_dims, n_inst, n_tiles, boxes_px, win, nwords, npx, nullptr,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int td_paste_threshold_pack(const float* boxes_px, const int* win, const long long* word_off,

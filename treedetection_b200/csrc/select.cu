@@ -13,25 +13,22 @@
 // fallback compares against 0.
 #include <cub/device/device_scan.cuh>
 
+#include "chain_internal.cuh"
 #include "common.cuh"
 
 namespace {
 
-struct SelectParams {
-  int use_overlap;
-  int is_seam_image;         // rows / cols match a merged strip: no overlap-band discard
-  double left, bottom, right, top;                          // raster bounds (ndvi_bounds)
-  double band_left, band_right, band_top, band_bottom;      // overlap-band borders
-  float height_threshold, ndvi_mean_threshold, ndvi_var_threshold;
-};
+typedef TdSelectParams SelectParams;
 
 __global__ void preselect_kernel(const double* __restrict__ bounds, const float* __restrict__ max_h,
                                  const float* __restrict__ ndvi_stats, int n, SelectParams P,
+                                 const SelectParams* __restrict__ P_dev,
                                  int* __restrict__ pre, int* __restrict__ first_contained,
                                  const unsigned char* __restrict__ is_contained,
                                  const long long* __restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (P_dev) P = *P_dev;     // per-image parameters of the chain (device memory)
   if (n_dev && i >= *n_dev) { pre[i] = 0; return; }   // capacity tail: keeps the rank scan exact
   bool keep = true;
   const double bx0 = bounds[4 * i], by0 = bounds[4 * i + 1], bx1 = bounds[4 * i + 2], by1 = bounds[4 * i + 3];
@@ -110,25 +107,17 @@ __global__ void round_coords_kernel(const double* __restrict__ in, long long n, 
 
 }  // namespace
 
-// params: 14 doubles = [use_overlap, is_seam_image, left, bottom, right, top, band_left,
-//   band_right, band_top, band_bottom, height_threshold, ndvi_mean_threshold,
-//   ndvi_var_threshold, reserved] (host pointer)
 // out_idx[i]: index of the crown emitted at position i of the pre-selected walk, or -1.
-extern "C" int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats,
-                                const double* area, const int* num_contained, const unsigned char* is_contained,
-                                int n, const double* params, int* pre, int* out_idx, const long long* n_dev,
-                                void* stream) {
+// p_host / p_dev: the parameters by value, or (chain) in device memory.
+int td_select_crowns_ex(const double* bounds, const float* max_h, const float* ndvi_stats, const double* area,
+                        const int* num_contained, const unsigned char* is_contained, int n,
+                        const TdSelectParams* p_host, const TdSelectParams* p_dev, int* pre, int* out_idx,
+                        const long long* n_dev, cudaStream_t st) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
-  TD_ARG(bounds && max_h && ndvi_stats && area && num_contained && is_contained && params && pre && out_idx);
-  cudaStream_t st = (cudaStream_t)stream;
-  SelectParams P;
-  P.use_overlap = params[0] != 0.0; P.is_seam_image = params[1] != 0.0;
-  P.left = params[2]; P.bottom = params[3]; P.right = params[4]; P.top = params[5];
-  P.band_left = params[6]; P.band_right = params[7]; P.band_top = params[8]; P.band_bottom = params[9];
-  // python scalars compared with float32 array elements: the comparison is in float32
-  P.height_threshold = (float)params[10]; P.ndvi_mean_threshold = (float)params[11];
-  P.ndvi_var_threshold = (float)params[12];
+  TD_ARG(bounds && max_h && ndvi_stats && area && num_contained && is_contained && (p_host || p_dev) && pre && out_idx);
+  SelectParams P = {};
+  if (p_host) P = *p_host;
   td_ensure_pool();
   int* first = nullptr;
   int* rank = nullptr;
@@ -138,7 +127,7 @@ extern "C" int td_select_crowns(const double* bounds, const float* max_h, const 
   TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
   TD_CUDA(cudaMemsetAsync(first, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: larger than any index
   const int blocks = td_div_up(n, 256);
-  preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, pre, first, is_contained, n_dev);
+  preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, p_dev, pre, first, is_contained, n_dev);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pre, rank, n, st);
   TD_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pre, rank, n, st);
@@ -149,6 +138,27 @@ extern "C" int td_select_crowns(const double* bounds, const float* max_h, const 
   cudaFreeAsync(first, st);
   if (e != cudaSuccess) { td_set_error("td_select_crowns: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
+}
+
+// params: 14 doubles = [use_overlap, is_seam_image, left, bottom, right, top, band_left,
+//   band_right, band_top, band_bottom, height_threshold, ndvi_mean_threshold,
+//   ndvi_var_threshold, reserved] (host pointer)
+extern "C" int td_select_crowns(const double* bounds, const float* max_h, const float* ndvi_stats,
+                                const double* area, const int* num_contained, const unsigned char* is_contained,
+                                int n, const double* params, int* pre, int* out_idx, const long long* n_dev,
+                                void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(params);
+  SelectParams P;
+  P.use_overlap = params[0] != 0.0; P.is_seam_image = params[1] != 0.0;
+  P.left = params[2]; P.bottom = params[3]; P.right = params[4]; P.top = params[5];
+  P.band_left = params[6]; P.band_right = params[7]; P.band_top = params[8]; P.band_bottom = params[9];
+  // python scalars compared with float32 array elements: the comparison is in float32
+  P.height_threshold = (float)params[10]; P.ndvi_mean_threshold = (float)params[11];
+  P.ndvi_var_threshold = (float)params[12];
+  return td_select_crowns_ex(bounds, max_h, ndvi_stats, area, num_contained, is_contained, n, &P, nullptr, pre, out_idx,
+                             n_dev, (cudaStream_t)stream);
 }
 
 // flags (n) u8 = conf >= conf_thr && area_min <= area <= area_max; poly_id (n) i64 = number of crowns

@@ -249,19 +249,21 @@ struct WarpCoop {
 //   scratch layout: res[n] | flat[n] | stack[3n]   (flat[k] = end index + 1 when result
 //   segment k is a flattened section, i.e. a member of the output segment index, else 0)
 //   alive: n bits in (n + 31) / 32 words (input segment k = pts[k], pts[k+1] still indexed)
-template <typename Coop>
-TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, uint32_t* alive, const Coop& co) {
+//   IdxT: int in general; unsigned char when n <= 254 (every stored value is an index <= n), which
+//   lets a ring's whole scratch live in 5 * n BYTES of shared memory
+template <typename Coop, typename IdxT>
+TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, uint32_t* alive, const Coop& co) {
   if (n <= 0) return 0;
-  int* res = scratch;
-  int* flat = scratch + n;
-  int* stack = scratch + 2 * n;
+  IdxT* res = scratch;
+  IdxT* flat = scratch + n;
+  IdxT* stack = scratch + 2 * n;
   const int nseg = n - 1;
   const int lane = co.lane(), nl = co.size();
   for (int k = lane; k < (n + 31) / 32; k += nl) alive[k] = 0xffffffffu;
   co.sync();
   int m = 0;        // number of result segments; res[k] and the next start (or flat end) are its ends
   int sp = 0;
-  stack[0] = 0; stack[1] = n - 1; stack[2] = 0;
+  stack[0] = 0; stack[1] = (IdxT)(n - 1); stack[2] = 0;
   sp = 1;
   const int min_size = 4;
   while (sp > 0) {
@@ -269,7 +271,7 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
     const int i = stack[3 * sp], j = stack[3 * sp + 1];
     const int depth = stack[3 * sp + 2] + 1;
     if (i + 1 == j) {
-      res[m] = i; flat[m] = 0; ++m;
+      res[m] = (IdxT)i; flat[m] = 0; ++m;
       continue;
     }
     bool valid = true;
@@ -324,14 +326,14 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, int* scratch, u
         alive[w] &= ~mask;
       }
       co.sync();
-      res[m] = i; flat[m] = j + 1; ++m;
+      res[m] = (IdxT)i; flat[m] = (IdxT)(j + 1); ++m;
       continue;
     }
     // right section is processed second
-    stack[3 * sp] = far; stack[3 * sp + 1] = j; stack[3 * sp + 2] = depth; ++sp;
-    stack[3 * sp] = i; stack[3 * sp + 1] = far; stack[3 * sp + 2] = depth; ++sp;
+    stack[3 * sp] = (IdxT)far; stack[3 * sp + 1] = (IdxT)j; stack[3 * sp + 2] = (IdxT)depth; ++sp;
+    stack[3 * sp] = (IdxT)i; stack[3 * sp + 1] = (IdxT)far; stack[3 * sp + 2] = (IdxT)depth; ++sp;
   }
-  res[m] = n - 1;
+  res[m] = (IdxT)(n - 1);
   return m + 1;
 }
 

@@ -20,13 +20,12 @@
 // NDVI min / max / mean / population variance; empty set -> -1.
 // mean / var are accumulated in float64 and rounded once (the reference sums in
 // float32; agreement is to ~1e-7, the contract is 1e-5 absolute).
+#include "chain_internal.cuh"
 #include "common.cuh"
 
 namespace {
 
-struct Affine6 {
-  double a, b, c, d, e, f;
-};
+typedef TdAffine6 Affine6;
 
 enum StatsMode { kCombined = 0, kHeightOnly = 1, kNdviOnly = 2 };
 
@@ -53,17 +52,21 @@ TD_D bool better_min(float v, long long k, float bv, long long bk) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
+crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
+                   const long long* __restrict__ ring_idx, int n,
                    const float* __restrict__ ndvi, const float* __restrict__ height, int rows, int cols, Affine6 T,
+                   const Affine6* __restrict__ T_dev,
                    float* __restrict__ max_h, float* __restrict__ hxy, float* __restrict__ ndvi_stats,
                    const long long* __restrict__ n_dev) {
   const int lane = threadIdx.x & 31;
   const int crown = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (crown >= n || (n_dev && crown >= *n_dev)) return;
   const unsigned full = 0xffffffffu;
+  if (T_dev) T = *T_dev;     // per-image transform of the chain (device memory)
 
   // ---- circle from the float32 vertices ------------------------------------
-  const long long v0 = ring_off[crown], v1 = ring_off[crown + 1];
+  const long long ring = ring_idx ? ring_idx[crown] : crown;
+  const long long v0 = ring_off[ring], v1 = ring_off[ring + 1];
   float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
   for (long long k = v0 + lane; k < v1; k += 32) {
     const float x = __double2float_rn(verts[2 * k]), y = __double2float_rn(verts[2 * k + 1]);
@@ -223,22 +226,28 @@ __device__ float np_pairwise_sum(const RowGetter& a, int lo, int n) {
   return __fadd_rn(np_pairwise_sum(a, lo, n2), np_pairwise_sum(a, lo + n2, n - n2));
 }
 
-__global__ void max_ring_len_kernel(const long long* __restrict__ ring_off, int n, int* __restrict__ vmax,
-                                    const long long* __restrict__ n_dev) {
+__global__ void max_ring_len_kernel(const long long* __restrict__ ring_off, const long long* __restrict__ ring_idx,
+                                    int n, int* __restrict__ vmax, const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int len = (i < n && !(n_dev && i >= *n_dev)) ? (int)(ring_off[i + 1] - ring_off[i]) : 0;
+  int len = 0;
+  if (i < n && !(n_dev && i >= *n_dev)) {
+    const long long r = ring_idx ? ring_idx[i] : i;
+    len = (int)(ring_off[r + 1] - ring_off[r]);
+  }
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
   if ((threadIdx.x & 31) == 0) atomicMax(vmax, len);
 }
 
-__global__ void centroid_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n,
+__global__ void centroid_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
+                                const long long* __restrict__ ring_idx, int n,
                                 const int* __restrict__ vmax, float* __restrict__ centroid,
                                 const long long* __restrict__ n_dev) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || (n_dev && i >= *n_dev)) return;
   const int V = *vmax;
   RowGetter g;
-  g.verts = verts; g.v0 = ring_off[i]; g.len = (int)(ring_off[i + 1] - ring_off[i]);
+  const long long ring = ring_idx ? ring_idx[i] : i;
+  g.verts = verts; g.v0 = ring_off[ring]; g.len = (int)(ring_off[ring + 1] - ring_off[ring]);
   long long cntx = 0, cnty = 0;
   for (int k = 0; k < g.len; ++k) {
     if (!isnan(__double2float_rn(verts[2 * (g.v0 + k)]))) ++cntx;
@@ -255,50 +264,68 @@ __global__ void centroid_kernel(const double* __restrict__ verts, const long lon
 
 }  // namespace
 
-extern "C" int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi,
-                              const float* height, int rows, int cols, const double* transform6, int mode,
-                              float* max_h, float* hxy, float* ndvi_stats, const long long* n_dev, void* stream) {
+int td_crown_stats_ex(const double* verts, const long long* ring_off, const long long* ring_idx, int n,
+                      const float* ndvi, const float* height, int rows, int cols, const TdAffine6* tf_host,
+                      const TdAffine6* tf_dev, int mode, float* max_h, float* hxy, float* ndvi_stats,
+                      const long long* n_dev, cudaStream_t st) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
-  TD_ARG(verts && ring_off && transform6 && rows > 0 && cols > 0);
+  TD_ARG(verts && ring_off && (tf_host || tf_dev) && rows > 0 && cols > 0);
   TD_ARG(mode >= 0 && mode <= 2);
   if (mode != kNdviOnly) TD_ARG(height && max_h && hxy);
   if (mode != kHeightOnly) TD_ARG(ndvi && ndvi_stats);
-  Affine6 T{transform6[0], transform6[1], transform6[2], transform6[3], transform6[4], transform6[5]};
-  cudaStream_t st = (cudaStream_t)stream;
+  Affine6 T = tf_host ? *tf_host : Affine6{1, 0, 0, 0, 1, 0};
   const int threads = 256;                       // 8 crowns per CTA
   const int blocks = td_div_up((long long)n * 32, threads);
   switch (mode) {
     case kCombined:
-      crown_stats_kernel<kCombined><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
-                                                                 hxy, ndvi_stats, n_dev);
+      crown_stats_kernel<kCombined><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows, cols,
+                                                                 T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
       break;
     case kHeightOnly:
-      crown_stats_kernel<kHeightOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T,
-                                                                   max_h, hxy, ndvi_stats, n_dev);
+      crown_stats_kernel<kHeightOnly><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows,
+                                                                   cols, T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
       break;
     default:
-      crown_stats_kernel<kNdviOnly><<<blocks, threads, 0, st>>>(verts, ring_off, n, ndvi, height, rows, cols, T, max_h,
-                                                                 hxy, ndvi_stats, n_dev);
+      crown_stats_kernel<kNdviOnly><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows, cols,
+                                                                 T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
   }
   TD_CHECK_LAUNCH("td_crown_stats");
   return TD_OK;
 }
 
-extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid,
-                            const long long* n_dev, void* stream) {
+extern "C" int td_crown_stats(const double* verts, const long long* ring_off, int n, const float* ndvi,
+                              const float* height, int rows, int cols, const double* transform6, int mode,
+                              float* max_h, float* hxy, float* ndvi_stats, const long long* n_dev, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(transform6);
+  const Affine6 T{transform6[0], transform6[1], transform6[2], transform6[3], transform6[4], transform6[5]};
+  return td_crown_stats_ex(verts, ring_off, nullptr, n, ndvi, height, rows, cols, &T, nullptr, mode, max_h, hxy,
+                           ndvi_stats, n_dev, (cudaStream_t)stream);
+}
+
+// vmax_scratch: one int of device scratch (null: taken from the stream-ordered pool)
+int td_centroids_ex(const double* verts, const long long* ring_off, const long long* ring_idx, int n, float* centroid,
+                    int* vmax_scratch, const long long* n_dev, cudaStream_t st) {
   TD_ARG(n >= 0);
   if (n == 0) return TD_OK;
   TD_ARG(verts && ring_off && centroid);
-  cudaStream_t st = (cudaStream_t)stream;
-  td_ensure_pool();
-  int* vmax = nullptr;
-  TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
+  int* vmax = vmax_scratch;
+  if (!vmax) {
+    td_ensure_pool();
+    TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
+  }
   TD_CUDA(cudaMemsetAsync(vmax, 0, sizeof(int), st));
-  max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, n, vmax, n_dev);
-  centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, n, vmax, centroid, n_dev);
+  max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, ring_idx, n, vmax, n_dev);
+  centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, ring_idx, n, vmax, centroid, n_dev);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(vmax, st);
+  if (!vmax_scratch) cudaFreeAsync(vmax, st);
   if (e != cudaSuccess) { td_set_error("td_centroids: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
+}
+
+extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid,
+                            const long long* n_dev, void* stream) {
+  return td_centroids_ex(verts, ring_off, nullptr, n, centroid, nullptr, n_dev, (cudaStream_t)stream);
 }

@@ -13,6 +13,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include "chain_internal.cuh"
 #include "common.cuh"
 
 namespace {
@@ -57,7 +58,10 @@ __global__ void clamp_offsets_kernel(const long long* __restrict__ sizes, long l
 struct FlagLive {
   const unsigned char* flags;
   const long long* n_dev;
-  __host__ __device__ bool operator()(int i) const { return (n_dev == nullptr || i < *n_dev) && flags[i] != 0; }
+  int want;    // 1: flags[i] != 0 selects, 0: flags[i] == 0 selects
+  __host__ __device__ bool operator()(int i) const {
+    return (n_dev == nullptr || i < *n_dev) && ((flags[i] != 0) == (want != 0));
+  }
 };
 struct NonNegLive {
   const int* values;
@@ -178,17 +182,21 @@ extern "C" int td_scan_clamp(const long long* sizes, int k, int n, const long lo
 
 // sel[0..count) = ascending indices i < n (and < *n_dev when given) with flags[i] != 0; sel[count..n) = 0;
 // *count stays on the device.
-extern "C" int td_compact_flags(const unsigned char* flags, int n, const long long* n_dev, long long* sel,
-                                long long* count, void* stream) {
+int td_compact_flags_ex(const unsigned char* flags, int want, int n, const long long* n_dev, long long* sel,
+                        long long* count, cudaStream_t st) {
   TD_ARG(n >= 0 && count);
-  cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) { TD_CUDA(cudaMemsetAsync(count, 0, sizeof(long long), st)); return TD_OK; }
   TD_ARG(flags && sel);
   td_ensure_pool();
   cub::CountingInputIterator<int> iota(0);
-  cub::TransformInputIterator<bool, FlagLive, cub::CountingInputIterator<int>> fl(iota, FlagLive{flags, n_dev});
+  cub::TransformInputIterator<bool, FlagLive, cub::CountingInputIterator<int>> fl(iota, FlagLive{flags, n_dev, want});
   cub::CountingInputIterator<long long> ids(0);
   return select_flagged(ids, fl, sel, count, n, st);
+}
+
+extern "C" int td_compact_flags(const unsigned char* flags, int n, const long long* n_dev, long long* sel,
+                                long long* count, void* stream) {
+  return td_compact_flags_ex(flags, 1, n, n_dev, sel, count, (cudaStream_t)stream);
 }
 
 // out[0..count) = the non-negative values[i] (i < n, i < *n_dev) in order; out[count..n) = 0

@@ -205,19 +205,26 @@ def trace_rings_slots(bits, win, word_off, px_off, slot_off, inst_tile, tile_tf,
 # ----------------------------------------------------------------------------
 # P5  NDVI + decimation
 # ----------------------------------------------------------------------------
-def ndvi_decimate(rgbi, out_h, out_w):
-    """rgbi (bands>=4, H, W) uint8 -> NDVI (out_h, out_w) float32."""
+def ndvi_decimate(rgbi, out_h, out_w, out=None):
+    """rgbi (bands>=4, H, W) uint8 -> NDVI (out_h, out_w) float32 (into ``out`` when given: a buffer kept
+    across images keeps the pointers -- and with them the captured graphs of the chain -- stable)."""
     _chk(rgbi, torch.uint8, "rgbi")
     b, h, w = rgbi.shape
-    out = torch.empty((out_h, out_w), dtype=torch.float32, device=rgbi.device)
+    if out is None:
+        out = torch.empty((out_h, out_w), dtype=torch.float32, device=rgbi.device)
+    elif out.shape != (out_h, out_w) or out.dtype != torch.float32:
+        raise _lib.TreedetError("ndvi_decimate: output buffer of the wrong shape / dtype")
     _lib.call("td_ndvi_decimate", _ptr(rgbi), b, h, w, out_h, out_w, _ptr(out), _stream())
     return out
 
 
-def decimate_f32(band, out_h, out_w):
+def decimate_f32(band, out_h, out_w, out=None):
     _chk(band, torch.float32, "band")
     h, w = band.shape
-    out = torch.empty((out_h, out_w), dtype=torch.float32, device=band.device)
+    if out is None:
+        out = torch.empty((out_h, out_w), dtype=torch.float32, device=band.device)
+    elif out.shape != (out_h, out_w) or out.dtype != torch.float32:
+        raise _lib.TreedetError("decimate_f32: output buffer of the wrong shape / dtype")
     _lib.call("td_decimate_f32", _ptr(band), h, w, out_h, out_w, _ptr(out), _stream())
     return out
 
@@ -535,3 +542,94 @@ def forest_predicates(a_verts, a_off, f_verts, f_off, f_bounds=None, a_filter=No
     if na and int(torch.maximum(inter.max(), within.max()).item()) > 1:
         raise _lib.TreedetError("td_forest_predicates: forest outline too dense for the kernel's per-query limits")
     return inter, within
+
+
+# ----------------------------------------------------------------------------
+# The whole chain of one image (td_chain_*): P2-P4 and P6-P9 as CUDA-graph replays
+# ----------------------------------------------------------------------------
+class Chain:
+    """One ``td_chain`` object: a device workspace sized by capacities plus the captured graphs.
+    ``params``: pipeline.PipelineParams; ``caps``: [instances, words, label pixels, point slots, rings,
+    vertices, NMS neighbour slots per crown, contour rows per instance]."""
+
+    _OUT = (("counters", torch.int64, 16, 1), ("tverts", torch.float64, "V", 2), ("toff", torch.int64, "R1", 1),
+            ("tconf", torch.float64, "R", 1), ("verts", torch.float64, "V", 2), ("ring_off", torch.int64, "R1", 1),
+            ("poly_id", torch.int64, "R", 1), ("conf", torch.float64, "R", 1), ("area", torch.float64, "R", 1),
+            ("tree_height", torch.float32, "R", 1), ("centroid", torch.float32, "R", 2),
+            ("is_contained", torch.uint8, "R", 1), ("num_contained", torch.int32, "R", 1),
+            ("hxy", torch.float32, "R", 2), ("ndvi_stats", torch.float32, "R", 4))
+
+    def __init__(self, params, caps, n_slots, device):
+        import ctypes as C
+        self.caps = [int(c) for c in caps]
+        self.n_slots = int(n_slots)
+        self.device = torch.device(device)
+        caps_h = (C.c_longlong * 8)(*self.caps)
+        nbytes = _lib.lib().td_chain_workspace_bytes(caps_h, self.n_slots)
+        if nbytes < 0:
+            raise _lib.TreedetError(f"td_chain_workspace_bytes: bad capacities {self.caps}")
+        self.workspace = torch.empty((int(nbytes) + 256,), dtype=torch.uint8, device=self.device)
+        base = self.workspace.data_ptr()
+        self._pad = (-base) % 256
+        cfg = (C.c_double * 16)(float(params.mask_threshold), float(params.simplify_tolerance), 2.0,
+                                float(params.confidence_threshold), float(params.area_threshold), 1000.0,
+                                float(params.iou_threshold), float(params.area_threshold),
+                                float(params.containment_threshold), *([0.0] * 7))
+        self._h = C.c_void_p()
+        _lib.call("td_chain_create", cfg, caps_h, self.n_slots, base + self._pad, int(nbytes), C.byref(self._h))
+        self._views = []
+        dims = {"R": self.caps[4], "R1": self.caps[4] + 1, "V": self.caps[5]}
+        for s in range(self.n_slots):
+            offs = (C.c_longlong * 16)()
+            _lib.call("td_chain_layout", self._h, s, offs)
+            v = {}
+            for k, (name, dt, rows, cols) in enumerate(self._OUT):
+                r = rows if isinstance(rows, int) else dims[rows]
+                nb = r * cols * torch.empty((), dtype=dt).element_size()
+                o = self._pad + int(offs[k])
+                t = self.workspace[o:o + nb].view(dt)
+                v[name] = t.view(r, cols) if cols > 1 else t
+            self._views.append(v)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                _lib.lib().td_chain_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def predict(self, slot, det, tile_tf, tile_boxes, use_graph=True):
+        n = det["boxes_net"].shape[0]
+        _chk(det["boxes_net"], torch.float32, "boxes_net"); _chk(det["scores"], torch.float32, "scores")
+        _chk(det["probs"], torch.float32, "probs"); _chk(det["inst_tile"], torch.int32, "inst_tile")
+        _chk(det["tile_dims"], torch.int32, "tile_dims"); _chk(tile_tf, torch.float64, "tile_tf")
+        _chk(tile_boxes, torch.float64, "tile_boxes")
+        dummy = self.workspace      # n == 0: the pointers are never dereferenced but must not be null
+        ptr = (lambda t: _ptr(t)) if n else (lambda t: _ptr(t) if t.numel() else dummy.data_ptr())
+        _lib.call("td_chain_predict", self._h, int(slot), ptr(det["boxes_net"]), ptr(det["scores"]), ptr(det["probs"]),
+                  ptr(det["inst_tile"]), int(n), _ptr(det["tile_dims"]), _ptr(tile_tf), _ptr(tile_boxes),
+                  int(det["tile_dims"].shape[0]), 1 if use_graph else 0, _stream())
+
+    def post(self, slot, ndvi, ndvi_tf, height, height_tf, combined, select_params, use_graph=True):
+        import ctypes as C
+        _chk(ndvi, torch.float32, "ndvi"); _chk(height, torch.float32, "height")
+        ntf = (C.c_double * 6)(*[float(v) for v in list(ndvi_tf)[:6]])
+        htf = (C.c_double * 6)(*[float(v) for v in list(height_tf)[:6]])
+        sp = (C.c_double * 14)(*([float(v) for v in select_params] + [0.0] * (14 - len(select_params))))
+        _lib.call("td_chain_post", self._h, int(slot), _ptr(ndvi), int(ndvi.shape[0]), int(ndvi.shape[1]), ntf,
+                  _ptr(height), int(height.shape[0]), int(height.shape[1]), htf, 1 if combined else 0, sp,
+                  1 if use_graph else 0, _stream())
+
+    def counters(self, slot):
+        return self._views[slot]["counters"]
+
+    def table(self, slot):
+        v = self._views[slot]
+        return v["tverts"], v["toff"], v["tconf"]
+
+    def features(self, slot):
+        from .pipeline import Features
+        v = self._views[slot]
+        return Features(v["verts"], v["ring_off"], v["poly_id"], v["conf"], v["area"], v["tree_height"], v["centroid"],
+                        v["is_contained"], v["num_contained"], {"hxy": v["hxy"], "ndvi_stats": v["ndvi_stats"]})

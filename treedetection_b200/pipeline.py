@@ -15,6 +15,7 @@ back.  PyTorch is used for device memory, prefix sums and boolean compaction.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -127,17 +128,26 @@ def _stitch(rings, scores, inst_tile, tile_boxes, p: PipelineParams):
     return CrownTable(verts, ring_off, conf)
 
 
-def raster_stage(rgbi, rgbi_transform, ndsm, ndsm_transform, p: PipelineParams):
+def raster_stage(rgbi, rgbi_transform, ndsm, ndsm_transform, p: PipelineParams, buffers: dict = None):
     """P5: decimated reads + NDVI (postprocessing.py:780-800).  rgbi (4,H,W) u8,
-    ndsm (h,w) f32 on the device; transforms are 6-tuples."""
+    ndsm (h,w) f32 on the device; transforms are 6-tuples.  ``buffers``: optional dict that keeps the
+    output rasters ("ndvi", "height") across images of the same shape."""
     _, H, W = rgbi.shape
     oh, ow = int(H * p.ndvi_scaling_factor), int(W * p.ndvi_scaling_factor)
-    ndvi = ops.ndvi_decimate(rgbi, oh, ow)
+
+    def buf(name, shape):
+        if buffers is None:
+            return None
+        b = buffers.get(name)
+        if b is None or tuple(b.shape) != shape or b.device != rgbi.device:
+            b = buffers[name] = torch.empty(shape, dtype=torch.float32, device=rgbi.device)
+        return b
+    ndvi = ops.ndvi_decimate(rgbi, oh, ow, out=buf("ndvi", (oh, ow)))
     ndvi_tf = geo.compose(rgbi_transform, geo.scale(W / ow, H / oh))
     ndvi_bounds = geo.raster_bounds(rgbi_transform, W, H)
     h, w = ndsm.shape
     hh, hw = int(h * p.height_scaling_factor), int(w * p.height_scaling_factor)
-    height = ops.decimate_f32(ndsm, hh, hw) if (hh, hw) != (h, w) else ndsm
+    height = ops.decimate_f32(ndsm, hh, hw, out=buf("height", (hh, hw))) if (hh, hw) != (h, w) else ndsm
     height_tf = geo.compose(ndsm_transform, geo.scale(w / hw, h / hh))
     height_bounds = geo.raster_bounds(ndsm_transform, w, h)
     return {"ndvi": ndvi, "ndvi_transform": ndvi_tf, "ndvi_bounds": ndvi_bounds,
@@ -229,153 +239,72 @@ def postprocess_stage(table: CrownTable, rasters: dict, p: PipelineParams, keep_
 
 
 # ======================================================================================
-# Sync-free form of the two stages.
+# Sync-free form of the two stages: td_chain_* (csrc/chain.cu).
 #
 # The exact-size functions above read a size back from the device before every allocation
-# (about ten host synchronisations per image).  The functions below allocate by CAPACITY
-# (remembered from earlier images with the same tiling, see ChainRunner), keep every live
-# count on the device (``n_dev`` arguments of the C-ABI) and record them in one small
-# counter tensor, so an image is enqueued without waiting for the GPU; the counters are
-# read once, when the results are consumed.  Results are bit-identical to the exact-size
-# path; an overflow of any capacity raises bit 0 / 1 of the flag and the image is redone
-# with exact sizes.
+# (about ten host synchronisations per image).  ChainRunner drives the C-ABI chain instead:
+# every variable-length buffer lives BY CAPACITY (remembered from earlier images with the
+# same tiling) in one device workspace, live counts stay on the device in a 16-slot counter
+# block, and the static launch sequence of P2-P4 / P6-P9 is a CUDA graph replayed with one
+# launch each -- the host neither waits for the GPU nor sits between two kernels.  The
+# counters are read once, when the results are consumed.  Results are bit-identical to the
+# exact-size path; an overflow of any capacity raises a bit of the flag counter and the
+# image is redone with exact sizes.
 # ======================================================================================
 CTR_FLAG, CTR_WORDS, CTR_PX, CTR_SLOTS, CTR_CONT, CTR_PTS, CTR_RINGS, CTR_VERTS = 0, 1, 2, 3, 4, 5, 6, 7
 CTR_NTABLE, CTR_VTABLE, CTR_N1, CTR_N2, CTR_NFINAL, CTR_VFINAL, CTR_SIZE = 8, 9, 10, 11, 12, 13, 16
-# the border walk of the capacity form: one pass into per-instance slots (default) or count + emit
-TRACE_TWO_PASS = bool(__import__("os").environ.get("TREEDET_TRACE_TWO_PASS"))
-
-
-@dataclass
-class DynTable:
-    """Capacity-sized CrownTable: rows / vertices past the live counts are undefined."""
-    verts: torch.Tensor      # (cap_v, 2) f64
-    ring_off: torch.Tensor   # (cap_r + 1,) i64
-    conf: torch.Tensor       # (cap_r,) f64
-    n_dev: torch.Tensor      # (1,) i64 live ring count (a view into the counter tensor)
-
-
-def new_counters(device):
-    return torch.zeros((CTR_SIZE,), dtype=torch.int64, device=device)
-
-
-def predict_stage_dyn(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams,
-                      caps: dict, ctr: torch.Tensor, mark=None, two_pass=False) -> DynTable:
-    """P2 + P3 + P4 without host synchronisation (see the section comment).  ``mark("p3")`` is called
-    once the border walk is enqueued (schedulers use it to start work that should not share the SMs
-    with the shared-memory hungry walk)."""
-    flag = ctr[CTR_FLAG:CTR_FLAG + 1]
-    sizes1 = torch.empty((3, boxes_net.shape[0]), dtype=torch.int64, device=boxes_net.device)
-    boxes_px, win, _ = ops.paste_plan(boxes_net, inst_tile, tile_dims, sizes=sizes1)
-    offs1, _ = ops.scan_clamp(sizes1, [caps["words"], caps["px"], caps["ptslots"]], flag, win_zero=win,
-                              totals=ctr[CTR_WORDS:CTR_SLOTS + 1])
-    word_off, px_off, slot_off = offs1[0], offs1[1], offs1[2]
-    bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, int(caps["words"]))
-    if TRACE_TWO_PASS or two_pass:
-        rings = ops.trace_rings_dyn(bits, win, word_off, px_off, inst_tile, tile_tf, caps, flag,
-                                    ctr[CTR_CONT:CTR_VERTS + 1])
-    else:      # one border walk into per-instance slots
-        rings = ops.trace_rings_slots(bits, win, word_off, px_off, slot_off, inst_tile, tile_tf, caps, flag,
-                                      ctr[CTR_RINGS:CTR_VERTS + 1])
-    if mark is not None:
-        mark("p3")
-    n_rings = ctr[CTR_RINGS:CTR_RINGS + 1]
-    cap_r = int(caps["rings"])
-    ring_inst = rings.ring_inst[:cap_r].long()
-    ring_tile = inst_tile[ring_inst].contiguous()
-    ring_off = rings.ring_off[:cap_r + 1]
-    simp = ops.simplify_rings(rings.verts, ring_off, p.simplify_tolerance, tile_boxes, ring_tile, want_bounds=False,
-                              n_dev=n_rings)
-    n_table = ctr[CTR_NTABLE:CTR_NTABLE + 1]
-    sel, _ = ops.compact_flags(simp["keep"], n_dev=n_rings, count=n_table)
-    verts, dst_off = ops.take_rings_dyn(rings.verts, ring_off, sel, n_table, int(caps["verts"]), simp["scratch"],
-                                        simp["count"])
-    ctr[CTR_VTABLE:CTR_VTABLE + 1] = dst_off.gather(0, n_table)
-    conf = scores[ring_inst[sel]].to(torch.float64)
-    return DynTable(verts, dst_off, conf, n_table)
-
-
-def postprocess_stage_dyn(table: DynTable, rasters: dict, p: PipelineParams, caps: dict, ctr: torch.Tensor):
-    """P9 head, P6, P7, P8, P9 without host synchronisation.  Returns a capacity-sized Features whose
-    live sizes are ctr[CTR_NFINAL] rings / ctr[CTR_VFINAL] vertices."""
-    dev = table.verts.device
-    cap = table.conf.shape[0]
-    cap_v = table.verts.shape[0]
-    flag = ctr[CTR_FLAG:CTR_FLAG + 1]
-    n0 = table.n_dev
-    s2 = ops.simplify_rings(table.verts, table.ring_off, 2.0, want_bounds=True, want_area=True, bounds_of_input=True,
-                            n_dev=n0)
-    area_all = s2["area"]
-    flags1, pid_all = ops.select_head(table.conf, area_all, p.confidence_threshold, p.area_threshold, 1000.0, n_dev=n0)
-    n1 = ctr[CTR_N1:CTR_N1 + 1]
-    sel1, _ = ops.compact_flags(flags1, count=n1)
-    verts1, off1 = ops.take_rings_dyn(table.verts, table.ring_off, sel1, n1, cap_v)
-    conf1, area1, pid1, b1 = ops.gather_rows([table.conf, area_all, pid_all, s2["bounds"]], sel1, n1)
-    removed = ops.bbox_nms_ordered_dyn(b1, conf1, area1, n1, p.iou_threshold, p.area_threshold,
-                                       int(caps["nbr"]), flag)
-    n2 = ctr[CTR_N2:CTR_N2 + 1]
-    sel2, _ = ops.compact_flags(removed == 0, n_dev=n1, count=n2)
-    verts2, off2 = ops.take_rings_dyn(verts1, off1, sel2, n2, cap_v)
-    conf2, area2, pid2, b2 = ops.gather_rows([conf1, area1, pid1, b1], sel2, n2)
-    cent = ops.centroids(verts2, off2, n_dev=n2)
-    for key in ("height_ready", "ndvi_ready"):       # rasters produced / copied on another stream
-        if rasters.get(key) is not None:
-            torch.cuda.current_stream().wait_event(rasters[key])
-    combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
-        _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
-    if combined:
-        st = ops.crown_stats(verts2, off2, rasters["ndvi"], rasters["height"], rasters["ndvi_transform"],
-                             ops.STATS_COMBINED, n_dev=n2)
-        max_h, nst = st["max_h"], st["ndvi"]
-    else:
-        sh = ops.crown_stats(verts2, off2, None, rasters["height"], rasters["height_transform"], ops.STATS_HEIGHT_ONLY,
-                             n_dev=n2)
-        sn = ops.crown_stats(verts2, off2, rasters["ndvi"], None, rasters["ndvi_transform"], ops.STATS_NDVI_ONLY,
-                             n_dev=n2)
-        max_h, nst = sh["max_h"], sn["ndvi"]
-    ratio, isc, num = ops.containment(b2.to(torch.float32).contiguous(), p.containment_threshold, n_dev=n2)
-    sp = select_params(p, tuple(rasters["ndvi"].shape), rasters["ndvi_bounds"], rasters["pixel_x"], rasters["pixel_y"])
-    pre, out_idx = ops.select_crowns(b2, max_h, nst, area2, num, isc, sp, n_dev=n2)
-    nf = ctr[CTR_NFINAL:CTR_NFINAL + 1]
-    final, _ = ops.compact_nonneg(out_idx, n_dev=n2, count=nf)
-    vf, of = ops.take_rings_dyn(verts2, off2, final, nf, cap_v)
-    ctr[CTR_VFINAL:CTR_VFINAL + 1] = of.gather(0, nf)
-    vf = ops.round_coords(vf)
-    pidf, conff, areaf, hf, centf, iscf, numf = ops.gather_rows([pid2, conf2, area2, max_h, cent, isc, num], final, nf)
-    return Features(vf, of, pidf, conff, areaf, hf, centf, iscf, numf, {})
 
 
 def trim_features(f: Features, n: int, v: int) -> Features:
     """Views of a capacity-sized Features cut to the live sizes (read from the counters)."""
     return Features(f.verts[:v], f.ring_off[:n + 1], f.poly_id[:n], f.conf[:n], f.area[:n], f.tree_height[:n],
-                    f.centroid[:n], f.is_contained[:n], f.num_contained[:n], f.extras)
+                    f.centroid[:n], f.is_contained[:n], f.num_contained[:n],
+                    {k: t[:n] for k, t in f.extras.items()})
 
 
 class ChainRunner:
     """P2-P9 for a stream of images with the same tiling.  The first image (and any image whose
     sizes outgrow the remembered capacities) runs through the exact-size path; the others are
-    enqueued without synchronisation.  ``submit`` returns a ticket, ``collect`` turns it into
-    (n_candidates, Features) -- the only point where the host waits for the GPU."""
+    enqueued through ``td_chain_predict`` / ``td_chain_post`` without synchronisation.  ``submit``
+    returns a ticket, ``collect`` turns it into (n_candidates, Features) -- the only point where the
+    host waits for the GPU.  The Features of a ticket are views into the chain's workspace: they
+    stay valid until ``n_slots`` further images have been submitted."""
 
     GROW = 1.25
 
-    def __init__(self, params: PipelineParams):
+    def __init__(self, params: PipelineParams, n_slots: int = 4, use_graph: bool = True):
         self.p = params
         self.caps = None
         self.nbr_per_crown = 8
+        self.slot_contours = ops.TRACE_SLOT_CONTOURS
         self.fallbacks = 0
-        self.two_pass = TRACE_TWO_PASS     # border walk: one pass into slots, or count + emit
-        self._pinned = []          # recycled pinned read-back buffers (allocating one costs ~0.1 ms)
+        self.n_slots = n_slots
+        self.use_graph = use_graph and not os.environ.get("TREEDET_NO_GRAPH")
+        self.chain = None
+        self._seq = 0
+        self._busy = [None] * n_slots   # ticket id occupying each slot
+        self._pinned = []               # recycled pinned read-back buffers (allocating one costs ~0.1 ms)
 
     def _learn(self, sizes: dict):
         def cap(v):
             return int(v * self.GROW) + 1024
         new = {k: cap(v) for k, v in sizes.items()}
         if self.caps is None:
+            grown = True
             self.caps = new
         else:
+            grown = any(new[k] > self.caps.get(k, 0) for k in new)
             self.caps.update({k: max(self.caps.get(k, 0), new[k]) for k in new})
-        self.caps["nbr"] = self.nbr_per_crown * self.caps["rings"]
+        if grown and self.chain is not None:
+            self.chain = None           # rebuilt (with the larger workspace) by the next submit
+
+    def _chain(self, device):
+        if self.chain is None:
+            c = self.caps
+            self.chain = ops.Chain(self.p, [c["inst"], c["words"], c["px"], c["ptslots"], c["rings"], c["verts"],
+                                            self.nbr_per_crown, self.slot_contours], self.n_slots, device)
+            self._busy = [None] * self.n_slots
+        return self.chain
 
     def _exact(self, det, tile_tf, tile_boxes, rasters_fn):
         """Exact-size path; also measures the sizes the capacities are learnt from."""
@@ -388,8 +317,7 @@ class ChainRunner:
                                                   torch.where(w64 * h64 > 0, 4 * (w64 + h64) + 64, 0).sum()]).tolist()]
         bits = ops.paste_threshold_pack(boxes_px, win, word_off, det["probs"], p.mask_threshold, total_words)
         rings = ops.trace_rings(bits, win, word_off, det["inst_tile"], tile_tf, total_words)
-        sizes = {"words": total_words, "px": px, "ptslots": slots, "contours": rings.n_contours,
-                 "points": rings.n_points,
+        sizes = {"inst": int(det["boxes_net"].shape[0]), "words": total_words, "px": px, "ptslots": slots,
                  "rings": len(rings), "verts": int(rings.verts.shape[0])}
         self._learn(sizes)
         table = _stitch(rings, det["scores"], det["inst_tile"], tile_boxes, p)
@@ -401,46 +329,73 @@ class ChainRunner:
         rasters_fn(): the P5 rasters dict (called after P2-P4 are enqueued);
         mark(name): optional callback at the stage boundaries ("p4", "p5", "p9"), e.g. to record events."""
         mark = mark or (lambda name: None)
-        if self.caps is None:
+        n_inst = int(det["boxes_net"].shape[0])
+        if self.caps is None or n_inst > self.caps["inst"]:
             out = ("done",) + self._exact(det, tile_tf, tile_boxes, rasters_fn)
             for name in ("p3", "p4", "p5", "p9"):
                 mark(name)
             return out
         dev = det["boxes_net"].device
-        ctr = new_counters(dev)
-        table = predict_stage_dyn(det["boxes_net"], det["scores"], det["probs"], det["inst_tile"], det["tile_dims"],
-                                  tile_tf, tile_boxes, self.p, self.caps, ctr, mark=mark, two_pass=self.two_pass)
+        chain = self._chain(dev)
+        slot = self._seq % self.n_slots
+        if self._busy[slot] is not None:
+            raise _lib_error(f"ChainRunner: more than {self.n_slots} images in flight (collect the oldest ticket first)")
+        self._seq += 1
+        chain.predict(slot, det, tile_tf, tile_boxes, self.use_graph)
+        mark("p3")
         mark("p4")
         rasters = rasters_fn()
         mark("p5")
-        feats = postprocess_stage_dyn(table, rasters, self.p, self.caps, ctr)
+        for key in ("height_ready", "ndvi_ready"):       # rasters produced / copied on another stream
+            if rasters.get(key) is not None:
+                torch.cuda.current_stream().wait_event(rasters[key])
+        combined = geo.almost_equals(rasters["height_transform"], rasters["ndvi_transform"]) and \
+            _similar_bounds(rasters["height_bounds"], rasters["ndvi_bounds"])
+        sp = select_params(self.p, tuple(rasters["ndvi"].shape), rasters["ndvi_bounds"], rasters["pixel_x"],
+                           rasters["pixel_y"])
+        chain.post(slot, rasters["ndvi"], rasters["ndvi_transform"], rasters["height"], rasters["height_transform"],
+                   combined, sp, self.use_graph)
         mark("p9")
         host = self._pinned.pop() if self._pinned else torch.empty((CTR_SIZE,), dtype=torch.int64).pin_memory()
-        host.copy_(ctr, non_blocking=True)
+        host.copy_(chain.counters(slot), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return ("dyn", ev, host, feats, (det, tile_tf, tile_boxes, rasters_fn))
+        ticket = ("dyn", ev, host, slot, chain, (det, tile_tf, tile_boxes, rasters_fn))
+        self._busy[slot] = id(ticket)
+        return ticket
 
     def collect(self, ticket):
         if ticket[0] == "done":
             return ticket[1], ticket[2]
-        _, ev, host, feats, again = ticket
+        _, ev, host, slot, chain, again = ticket
         ev.synchronize()
         c = host.tolist()
         self._pinned.append(host)
+        if chain is self.chain and self._busy[slot] == id(ticket):
+            self._busy[slot] = None
         if c[CTR_FLAG] != 0:
             # some capacity was too small: redo this image with exact sizes (which also re-learns them)
             self.fallbacks += 1
             if c[CTR_FLAG] & 2:
                 self.nbr_per_crown *= 2
-            if c[CTR_FLAG] & 4:
-                # an instance outgrew its slot of the single-pass walk (ragged mask: many borders or a
-                # long outline); the same image would do so again, so this runner walks twice from now on
-                self.two_pass = True
+                self.chain = None
+            if c[CTR_FLAG] & 4 and self.slot_contours < 256:
+                # an instance outgrew its contour slot of the single-pass walk (ragged mask: many borders)
+                self.slot_contours *= 2
+                self.chain = None
             return self._exact(*again)
-        learnt = {"words": c[CTR_WORDS], "px": c[CTR_PX], "ptslots": c[CTR_SLOTS], "rings": c[CTR_RINGS],
-                  "verts": c[CTR_VERTS]}
-        if self.two_pass:
-            learnt.update(contours=c[CTR_CONT], points=c[CTR_PTS])
-        self._learn(learnt)
-        return c[CTR_NTABLE], trim_features(feats, c[CTR_NFINAL], c[CTR_VFINAL])
+        self._learn({"words": c[CTR_WORDS], "px": c[CTR_PX], "ptslots": c[CTR_SLOTS], "rings": c[CTR_RINGS],
+                     "verts": c[CTR_VERTS]})
+        self.last_counters = c
+        return c[CTR_NTABLE], trim_features(chain.features(slot), c[CTR_NFINAL], c[CTR_VFINAL])
+
+    def table(self, ticket_counters, slot):
+        """The stitched crown table (``geojson_predictions/<image>.gpkg``) of a collected dyn ticket."""
+        c = ticket_counters
+        verts, ring_off, conf = self.chain.table(slot)
+        return CrownTable(verts[:c[CTR_VTABLE]], ring_off[:c[CTR_NTABLE] + 1], conf[:c[CTR_NTABLE]])
+
+
+def _lib_error(msg):
+    from . import _lib
+    return _lib.TreedetError(msg)

@@ -25,7 +25,8 @@ from .tiling import resize_shortest_edge
 
 
 class FixturePredictor:
-    def __init__(self, model_path, exclude_vars=None):
+    def __init__(self, model_path, exclude_vars=None, allow_missing=False):
+        self.allow_missing = allow_missing
         if not os.path.isdir(model_path):
             raise FileNotFoundError(
                 f"{model_path}: the Mask R-CNN forward pass is outside this build; point the model key of config.yml "
@@ -42,12 +43,24 @@ class FixturePredictor:
             nh, nw = resize_shortest_edge(h, w)
             tile_dims[t] = (h, w, nh, nw)
         if not os.path.exists(path):
-            z = np.zeros
-            return Detections(z((0, 4), np.float32), z(0, np.float32), z((0, 28, 28), np.float32), z(0, np.int32),
-                              tile_dims, tile_ids, tiles)
+            if self.allow_missing:      # explicit opt-in: "no fixture" means "no detections"
+                z = np.zeros
+                return Detections(z((0, 4), np.float32), z(0, np.float32), z((0, 28, 28), np.float32), z(0, np.int32),
+                                  tile_dims, tile_ids, tiles)
+            # a mis-staged fixture directory must not produce silently empty crown layers that a resumed
+            # run then skips as "already predicted": predict_on_model logs the error and does not mark the file
+            raise FileNotFoundError(f"no ROI-head fixture for image {image_stem!r}: {path}")
         with np.load(path, allow_pickle=False) as f:
             fx_ids = [str(s) for s in f["tile_ids"]]
             boxes, scores, probs, inst_tile = f["boxes_net"], f["scores"], f["probs"], f["inst_tile"]
+        n = len(scores)
+        if boxes.shape != (n, 4) or probs.shape != (n, 28, 28) or inst_tile.shape != (n,):
+            raise ValueError(f"{path}: boxes_net {boxes.shape}, scores {scores.shape}, probs {probs.shape}, inst_tile "
+                             f"{inst_tile.shape} do not describe the same instances")
+        if n and (int(inst_tile.min()) < 0 or int(inst_tile.max()) >= len(fx_ids)):
+            raise ValueError(f"{path}: inst_tile outside [0, {len(fx_ids)})")
+        if n and np.any(np.diff(inst_tile.astype(np.int64)) < 0):
+            raise ValueError(f"{path}: instances are not in tile-major order")
         if fx_ids != tile_ids:   # fixtures were dumped with another tiling: remap by tile id
             pos = {tid: t for t, tid in enumerate(tile_ids)}
             remap = np.array([pos.get(tid, -1) for tid in fx_ids], dtype=np.int64)

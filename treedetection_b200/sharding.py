@@ -14,11 +14,17 @@ import torch
 import torch.distributed as dist
 
 
+def strip_height(tile_height, buffer, overlapping_tiles_height):
+    """Height of a down-seam strip in PIXELS (merging.py:98-100)."""
+    return int((tile_height + 2 * buffer) * overlapping_tiles_height)
+
+
 def halo_rows(tile_height, buffer, overlapping_tiles_height):
-    """Half of the down-seam strip height in pixels: the strip is
-    ``(tile_height + 2 * buffer) * overlapping_tiles_height`` PIXELS high (merging.py:98-100),
-    centred on the seam."""
-    return int((tile_height + 2 * buffer) * overlapping_tiles_height) // 2
+    """Rows of the LOWER neighbour inside the down-seam strip.  crop_image (helpers.py:1053-1085) cuts
+    ``sh`` rows starting at ``mh // 2 - sh // 2`` of the two-image mosaic, i.e. ``sh // 2`` rows above the
+    seam and ``sh - sh // 2`` below it: for an odd strip height the extra row comes from the lower image."""
+    sh = strip_height(tile_height, buffer, overlapping_tiles_height)
+    return sh - sh // 2
 
 
 def exchange_down_halos(tops, rank, world, group=None):
@@ -38,11 +44,17 @@ def exchange_down_halos(tops, rank, world, group=None):
     return recv
 
 
-def assemble_down_strip(own, halo):
+def assemble_down_strip(own, halo, sh=None):
     """own (bands, H, W) device raster of this rank, halo (bands, rows, W) = top rows of the
-    lower neighbour.  Returns the (bands, 2 * rows, W) seam strip: the centre crop of the
-    two-image mosaic, gathered without building the mosaic."""
+    lower neighbour, ``sh`` = strip height (default 2 * rows).  Returns the (bands, sh, W) seam strip:
+    ``sh // 2`` bottom rows of ``own`` followed by ``sh - sh // 2`` rows of the halo -- the same rows
+    merging.py's centre crop of the two-image mosaic selects, gathered without building the mosaic."""
     from . import ops
     rows = halo.shape[1]
-    bottom = own[:, own.shape[1] - rows:, :].contiguous()
-    return ops.seam_crop(bottom, halo, 1, own.shape[2], 2 * rows)
+    sh = 2 * rows if sh is None else int(sh)
+    up = sh // 2
+    if sh - up != rows:
+        raise ValueError(f"assemble_down_strip: a strip of {sh} rows needs {sh - up} halo rows, got {rows}")
+    bottom = own[:, own.shape[1] - up:, :].contiguous()
+    # mosaic of (up rows, rows rows): its centre crop of height sh starts at (up + rows) // 2 - sh // 2 = 0
+    return ops.seam_crop(bottom, halo, 1, own.shape[2], sh)
