@@ -77,3 +77,34 @@ def test_lzw_decoder_errors_and_kwkwk():
     bad = bytes([0xFF, 0xFF, 0xFF, 0xFF])
     assert lib.td_tiff_lzw_decode(bad, len(bad), dst, 16) < 0             # code beyond the table
     assert b"corrupt" in lib.td_last_error()
+
+
+@pytest.mark.parametrize("compression,tile", [(None, None), ("tiff_adobe_deflate", None), ("tiff_adobe_deflate", 128),
+                                              ("tiff_lzw", None)])
+def test_windowed_read_decodes_only_what_it_needs(tmp_path, compression, tile):
+    """rasterio's windowed reads (prediction.py:164, postprocessing.py:781-800): any window of a strip / tile
+    file equals the slice of the full read; the destination may be a caller buffer (a pinned staging area)."""
+    arr = _cases()["rgba"]
+    path = str(tmp_path / "w.tif")
+    if compression is None:
+        geotiff.write(path, arr, (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0), epsg=25832)
+    else:
+        try:
+            _save(path, arr, compression, None, tile)
+        except Exception as e:
+            pytest.skip(f"PIL cannot write {compression}/{tile}: {e}")
+    full, info = geotiff.read(path)
+    np.testing.assert_array_equal(full, arr)
+    rng = np.random.default_rng(1)
+    for _ in range(12):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        c0, r0 = int(rng.integers(0, 517 - w + 1)), int(rng.integers(0, 300 - h + 1))
+        dst = np.full((4, h, w), 77, np.uint8)
+        got, winfo = geotiff.read(path, window=(c0, r0, w, h), out=dst)
+        assert got is dst
+        np.testing.assert_array_equal(got, arr[:, r0:r0 + h, c0:c0 + w])
+        assert (winfo.width, winfo.height) == (w, h)
+    with pytest.raises(ValueError):
+        geotiff.read(path, window=(500, 0, 100, 10))
+    with pytest.raises(ValueError):
+        geotiff.read(path, out=np.zeros((4, 10, 10), np.uint8))

@@ -181,3 +181,30 @@ def test_full_size_chain_dyn_equals_exact_and_invariants(dev, big):
     assert np.array_equal(v, np.round(v, 3))                                              # round_coordinates
     b = geo.raster_bounds(big.transform, 10000, 10000)
     assert v[:, 0].min() >= b.left + 1 and v[:, 0].max() <= b.right - 1                    # border rule (use_overlap)
+
+
+@pytest.mark.parametrize("variant,ndsm_px", [("split", 0.2), ("combined", 1.0)])
+def test_full_size_config2_equals_oracle_golden(dev, big, variant, ndsm_px):
+    """The bench workload itself (10 000 x 10 000 px, 34 374 instances): stitched table and final crown layer of
+    the CUDA path -- exact-size kernels AND the CUDA-graph chain -- against the golden the CPU oracle produced for
+    the same scene (tests/golden/make_golden_config2.py), for both nDSM resolutions of BASELINE config 2."""
+    from treedetection_b200 import golden_check
+    assert golden_check.golden_matches_workload(10000, 1234, 2500)
+    p = pipeline.PipelineParams()
+    tables = api.TileTables(big.tiles, dev, p.shift)
+    det = _det(big, dev)
+    rgbi = torch.from_numpy(big.rgbi).to(dev)
+    if ndsm_px == 0.2:
+        ndsm_np, ndsm_tf = big.ndsm, big.ndsm_transform
+    else:
+        ndsm_np = synth.make_ndsm(big.field, 1.0, 1234)
+        ndsm_tf = synth.image_transform(big.field.left, big.field.bottom + big.field.height_m, 1.0)
+    ndsm = torch.from_numpy(ndsm_np).to(dev)
+    rasters = lambda: pipeline.raster_stage(rgbi, big.transform, ndsm, ndsm_tf, p)
+    table = pipeline.predict_stage(**det, tile_tf=tables.tile_tf, tile_boxes=tables.tile_boxes, p=p)
+    golden_check.check_table(table.verts.cpu().numpy(), table.ring_off.cpu().numpy(), table.conf.cpu().numpy())
+    run = pipeline.ChainRunner(p)
+    for which in ("exact", "graph", "graph replay"):
+        n, f = run.collect(run.submit(det, tables.tile_tf, tables.tile_boxes, rasters))
+        golden_check.check_layer(api.features_to_host(f), variant, n_candidates=n)
+    assert run.fallbacks == 0

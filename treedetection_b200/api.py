@@ -100,8 +100,19 @@ def _copy_stream(device):
     return _copy_streams[key]
 
 
+def table_to_host(t: pipeline.CrownTable):
+    """the stitched crown table (geojson_predictions/<image>.gpkg) in host memory"""
+    out = {}
+    for name, x in (("table_verts", t.verts), ("table_ring_off", t.ring_off), ("table_conf", t.conf)):
+        h = _pinned_like(name, x)
+        h.copy_(x, non_blocking=True)
+        out[name] = h
+    torch.cuda.current_stream().synchronize()
+    return {k: v.numpy().copy() for k, v in out.items()}
+
+
 def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: TileTables = None, p1_out=None,
-              with_p1=True, runner: pipeline.ChainRunner = None):
+              with_p1=True, runner: pipeline.ChainRunner = None, want_table=False):
     """Host buffers in, final crowns (host numpy) out.  ``p1_out``: optional reusable
     device buffer for the normalised tiles (they feed the predictor, not this path).
     ``runner``: a :class:`pipeline.ChainRunner` kept across images of the same tiling -- P2-P9 are
@@ -155,7 +166,10 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
         n_cand = len(table)
     else:
         n_cand, feats = runner.collect(runner.submit(det, tables.tile_tf, tables.tile_boxes, rasters_fn))
+        table = runner.last_table
     host = features_to_host(feats)
+    if want_table:
+        host.update(table_to_host(table))
     host["n_candidates"] = n_cand
     if with_p1:
         main.wait_stream(_p1_stream(device))

@@ -28,6 +28,37 @@ void td_ensure_pool() {
   done[dev] = true;
 }
 
+static thread_local TdArena* g_arena = nullptr;
+
+void td_set_arena(TdArena* arena) {
+  g_arena = arena;
+  if (arena) arena->off = 0;
+}
+
+void td_arena_rewind() {
+  if (g_arena) g_arena->off = 0;
+}
+
+cudaError_t td_tmp_alloc(void** p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) bytes = 1;
+  if (g_arena) {
+    const size_t o = (g_arena->off + 255) & ~(size_t)255;
+    if (o + bytes <= g_arena->bytes) {
+      *p = g_arena->base + o;
+      g_arena->off = o + bytes;
+      return cudaSuccess;
+    }
+  }
+  td_ensure_pool();
+  return cudaMallocAsync(p, bytes, st);
+}
+
+void td_tmp_free(void* p, cudaStream_t st) {
+  if (!p) return;
+  if (g_arena && (char*)p >= g_arena->base && (char*)p < g_arena->base + g_arena->bytes) return;
+  cudaFreeAsync(p, st);
+}
+
 extern "C" int td_version() { return 100; }  // 0.1.0
 
 extern "C" const char* td_last_error() { return g_err; }

@@ -122,6 +122,8 @@ struct Chain {
   float* cent; float* max_h; float* hxy; float* nst;
   float* ratio; unsigned char* isc; int* num; int* pre; int* out_idx; long long* fin; long long* idxf;
   int* vmax;
+  char* arena_mem;               // scratch arena of the composed calls
+  TdArena arena;
   TdImageParams* d_params;       // one per slot
   TdImageParams* h_params;       // pinned ring
   unsigned long long seq;
@@ -142,6 +144,13 @@ struct Bump {
     return o;
   }
 };
+
+// scratch of the largest composed call (the NMS: float4 boxes, half conf / area, offsets, best / state, sort
+// keys and values in double buffers, neighbour slots) plus CUB's temporary storage, with head room
+size_t arena_size(const long long* cap) {
+  const size_t R = (size_t)cap[kCapRings], Ni = (size_t)cap[kCapInst];
+  return (size_t)(96 + 4 * cap[kCapNbrPer]) * R + 64 * Ni + (8u << 20);
+}
 
 // lays the workspace out; with c == nullptr only the size is computed
 size_t layout(Chain* c, const long long* cap, int n_slots) {
@@ -173,6 +182,9 @@ size_t layout(Chain* c, const long long* cap, int n_slots) {
   TAKE(ratio, float, R); TAKE(isc, unsigned char, R); TAKE(num, int, R); TAKE(pre, int, R); TAKE(out_idx, int, R);
   TAKE(fin, long long, R); TAKE(idxf, long long, R);
   TAKE(vmax, int, 4);
+  const size_t arena_bytes = arena_size(cap);
+  TAKE(arena_mem, char, arena_bytes);
+  if (c) c->arena = TdArena{c->arena_mem, arena_bytes, 0};
   TAKE(d_params, TdImageParams, kMaxSlots);
 #undef TAKE
   for (int s = 0; s < n_slots; ++s) {
@@ -223,9 +235,11 @@ __global__ void pick_total_kernel(const long long* __restrict__ off, const long 
   *out = off[live];
 }
 
-#define RC(call)                  \
-  do {                            \
-    const int rc__ = (call);      \
+// every composed call starts at the beginning of the scratch arena (see TdArena in common.cuh)
+#define RC(call)                    \
+  do {                              \
+    td_arena_rewind();              \
+    const int rc__ = (call);        \
     if (rc__ != TD_OK) return rc__; \
   } while (0)
 
@@ -338,6 +352,11 @@ int enqueue_post(Chain* c, int s, const PostIn& in, cudaStream_t st) {
   TD_CHECK_LAUNCH("pick_total");
   return TD_OK;
 }
+
+struct ArenaScope {
+  explicit ArenaScope(TdArena* a) { td_set_arena(a); }
+  ~ArenaScope() { td_set_arena(nullptr); }
+};
 
 bool same_predict(const PredictIn& a, const PredictIn& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
 bool same_post(const PostIn& a, const PostIn& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
@@ -466,6 +485,7 @@ extern "C" int td_chain_predict(void* chain, int slot, const float* boxes_net, c
   hp->n_inst = n_inst;
   TD_CUDA(cudaMemcpyAsync(&c->d_params[slot].n_inst, &hp->n_inst, sizeof(long long), cudaMemcpyHostToDevice, st));
   PredictIn in = {boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, n_tiles};
+  ArenaScope scope(&c->arena);
   if (!use_graph) return enqueue_predict(c, slot, in, n_inst > 0 ? n_inst : 1, st);
   const int n_cap = (int)c->cap[kCapInst];
   return run_graph(c, 0, slot, &in, nullptr, st, [&](cudaStream_t cs) { return enqueue_predict(c, slot, in, n_cap, cs); });
@@ -495,6 +515,7 @@ extern "C" int td_chain_post(void* chain, int slot, const float* ndvi, int nrows
   TD_CUDA(cudaMemcpyAsync((char*)&c->d_params[slot] + o, (const char*)hp + o, sizeof(TdImageParams) - o,
                           cudaMemcpyHostToDevice, st));
   PostIn in = {ndvi, nrows, ncols, height, hrows, hcols, combined != 0};
+  ArenaScope scope(&c->arena);
   if (!use_graph) return enqueue_post(c, slot, in, st);
   return run_graph(c, 1, slot, nullptr, &in, st, [&](cudaStream_t cs) { return enqueue_post(c, slot, in, cs); });
 }

@@ -28,6 +28,22 @@
 void td_set_error(const char* fmt, ...);
 void td_ensure_pool();   // keeps the stream-ordered scratch pool cached across synchronisations
 
+// Temporary device scratch of one entry point.  By default it comes from the stream-ordered pool
+// (cudaMallocAsync / cudaFreeAsync).  td_chain_* installs an ARENA for the calling thread instead: a region of
+// its workspace that every composed call bumps through from the start (the calls are ordered on one
+// stream, so a region is dead by the time the next call's kernels run).  That keeps memory-allocation
+// nodes out of the captured CUDA graphs -- a graph that owns allocations re-maps them on launch, which
+// showed up as multi-millisecond stalls in front of its first memset node.
+struct TdArena {
+  char* base;
+  size_t bytes;
+  size_t off;
+};
+void td_set_arena(TdArena* arena);            // nullptr: back to the stream-ordered pool
+void td_arena_rewind();                       // the next td_tmp_alloc starts at the arena's beginning again
+cudaError_t td_tmp_alloc(void** p, size_t bytes, cudaStream_t st);
+void td_tmp_free(void* p, cudaStream_t st);
+
 #define TD_CHECK_LAUNCH(name)                                                        \
   do {                                                                               \
     cudaError_t e__ = cudaGetLastError();                                            \

@@ -424,7 +424,7 @@ extern "C" int td_trace_walk(const uint32_t* bits, const int* win, const long lo
   A.ct_parent = ct_int6; A.ct_npts = ct_int6 + nc; A.ct_ptoff = ct_int6 + 2 * nc; A.ct_scratch = ct_int6 + 3 * nc;
   A.ct_hole = ct_hole; A.pts = pts; A.counts = counts; A.sizes_kn = sizes_kn; A.flag = flag;
   static int lanes = 0;
-  if (lanes == 0) { const char* e = getenv("TREEDET_TRACE_LANES"); lanes = e && atoi(e) > 0 ? atoi(e) : 16; }
+  if (lanes == 0) { const char* e = getenv("TREEDET_TRACE_LANES"); lanes = e && atoi(e) > 0 ? atoi(e) : 8; }
   const int L = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
   A.smem_bytes = smem_per_warp(n_inst, L);
   if (L == 32) trace_walk_kernel<32><<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);

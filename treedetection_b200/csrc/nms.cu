@@ -380,12 +380,12 @@ struct Scratch {
   explicit Scratch(cudaStream_t st) : s(st) {}
   void* get(size_t bytes) {
     void* p = nullptr;
-    if (cudaMallocAsync(&p, bytes ? bytes : 1, s) != cudaSuccess) return nullptr;
+    if (td_tmp_alloc(&p, bytes, s) != cudaSuccess) return nullptr;
     ptrs[n++] = p;
     return p;
   }
   ~Scratch() {
-    for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], s);
+    for (int i = 0; i < n; ++i) td_tmp_free(ptrs[i], s);
   }
 };
 
@@ -396,13 +396,13 @@ int build_grid(Scratch& sc, float4* box32, GridParams* gp, int n, KeyT** keys_ou
   auto* keys_b = (KeyT*)sc.get(sizeof(KeyT) * n);
   int* idx_a = (int*)sc.get(sizeof(int) * n);
   int* idx_b = (int*)sc.get(sizeof(int) * n);
-  if (!keys_a || !keys_b || !idx_a || !idx_b) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+  if (!keys_a || !keys_b || !idx_a || !idx_b) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
   cell_keys_kernel<<<td_div_up(n, 256), 256, 0, st>>>(box32, n, gp, keys_a, idx_a, n_dev);
   TD_CHECK_LAUNCH("cell_keys");
   size_t tmp_bytes = 0;
   TD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 32, st));
   void* tmp = sc.get(tmp_bytes);
-  if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+  if (!tmp) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
   TD_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 32, st));
   *keys_out = keys_b;
   *idx_out = idx_b;
@@ -431,7 +431,7 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
   int* state = (int*)sc.get(sizeof(int) * n);
   int* pending = (int*)sc.get(sizeof(int) * 2);
   if (!box32 || !gp || !c16 || !a16 || !off || !deg || !best || !state || !pending) {
-    td_set_error("cudaMallocAsync failed");
+    td_set_error("scratch allocation failed");
     return TD_ERR_CUDA;
   }
   const int blocks = td_div_up(n, 256);
@@ -456,7 +456,7 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
     // capacity form: fixed slots per crown, one pass (deg doubles as the end-offset array)
     const int slots = (int)(nbr_cap / n > 0 ? nbr_cap / n : 1);
     nbr = (int*)sc.get(sizeof(int) * (size_t)n * slots);
-    if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    if (!nbr) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
     nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, slots, deg, flag);
     TD_CHECK_LAUNCH("nms fill (slots)");
     end_c = deg;
@@ -468,14 +468,14 @@ static int nms_impl(const double* bounds, const double* conf, const double* area
     size_t tmp_bytes = 0;
     TD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, off, n + 1, st));
     void* tmp = sc.get(tmp_bytes);
-    if (!tmp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    if (!tmp) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
     TD_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, off, n + 1, st));
     // the neighbour count is data dependent: one 8-byte read back sizes the CSR array
     long long total = 0;
     TD_CUDA(cudaMemcpyAsync(&total, off + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
     nbr = (int*)sc.get(sizeof(int) * (size_t)(total > 0 ? total : 1));
-    if (!nbr) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+    if (!nbr) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
     nms_adjacency_kernel<true><<<blocks, 256, 0, st>>>(g, c16, a16, iou_thr, area_thr, off, nbr, best, 0, nullptr, nullptr);
     TD_CHECK_LAUNCH("nms fill");
   }
@@ -522,7 +522,7 @@ int td_containment_ex(const double* bounds64, const float* bounds32, int n, doub
   Scratch sc(st);
   float4* box32 = (float4*)sc.get(sizeof(float4) * n);
   GridParams* gp = (GridParams*)sc.get(sizeof(GridParams));
-  if (!box32 || !gp) { td_set_error("cudaMallocAsync failed"); return TD_ERR_CUDA; }
+  if (!box32 || !gp) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
   const int blocks = td_div_up(n, 256);
   grid_init_kernel<<<1, 1, 0, st>>>(gp);
   if (bounds64) prep_boxes_kernel<<<blocks, 256, 0, st>>>(bounds64, n, box32, gp, n_dev);

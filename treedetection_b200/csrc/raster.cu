@@ -412,83 +412,7 @@ tile_resize_u8_up_kernel(const unsigned char* __restrict__ image, long long imag
   up_phase2(T, s_tmp, s_ytab, max_rows, ox0, oy0, warp, x4, out);
 }
 
-// ---- TMA variant of the fast path -----------------------------------------------------------
-// Phase 0 of the kernel above costs ~1/3 of its instructions (address arithmetic, two loads
-// and a funnel shift per staged word).  Here one elected thread issues three
-// cp.async.bulk.tensor.3d loads (one per band: box = box_w bytes x max_rows rows x 1 band of the
-// (W, H, bands) uint8 tensor, zero fill outside the raster) that land directly in shared
-// memory, completion is signalled on an mbarrier, and the other threads fetch their filter taps
-// meanwhile.  Needs W % 16 == 0 (global strides of a tensor map are multiples of 16 bytes).
 TD_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(kThreads)
-tile_resize_u8_up_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TileDesc* __restrict__ tiles,
-                             const int2* __restrict__ blk, const int* __restrict__ tab_min,
-                             const int* __restrict__ tab_cnt, const int* __restrict__ tab_k, float* __restrict__ out,
-                             int max_rows, int box_w, int region) {
-  extern __shared__ __align__(128) unsigned char smem_tma[];
-  unsigned char* s_src = smem_tma;                               // [3][region]  (region = box_w * max_rows, 128-aligned)
-  unsigned char* s_tmp = smem_tma + (size_t)3 * region;          // [3][max_rows][kBX]
-  int4* s_ytab = reinterpret_cast<int4*>(s_tmp + (size_t)3 * max_rows * kBX + kBX);   // [kBY]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_ytab + kBY);
-  const int2 me = blk[blockIdx.x];
-  const TileDesc T = tiles[me.x];
-  const int ox0 = (me.y & 0xffff) * kBX, oy0 = (me.y >> 16) * kBY;
-  const int oy_last = min(oy0 + kBY, T.nh) - 1;
-  const int row_lo = tab_min[T.ytab + oy0];
-  const int nrows = tab_min[T.ytab + oy_last] + tab_cnt[T.ytab + oy_last] - row_lo;
-  const int col_lo = tab_min[T.xtab + ox0];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- phase 0: three TMA box loads ------------------------------------------------------------
-  // the innermost start coordinate of a tiled TMA load must be 16-byte aligned (an unaligned
-  // start faults with "illegal instruction"): load from the aligned column below the window
-  // and let phase 1 add the remainder
-  const int x_box = (T.c_off + col_lo) & ~15;
-  const int x_shift = (T.c_off + col_lo) - x_box;
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"((uint32_t)(3 * box_w * max_rows))
-                 : "memory");
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      // output channel c reads band 2 - c (BGR order)
-      asm volatile(
-          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-          ::"r"(smem_u32(s_src + (size_t)c * region)), "l"(&tmap), "r"(x_box), "r"(T.r_off + row_lo),
-          "r"(2 - c), "r"(smem_u32(bar))
-          : "memory");
-    }
-  }
-  // overlapped with the copies: y taps of the CTA's rows and this thread's x taps
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + kBY) {
-    const int y = threadIdx.x - 32;
-    const int oy = min(oy0 + y, T.nh - 1);
-    const int* k = tab_k + (size_t)(T.ytab + oy) * kMaxK;
-    s_ytab[y] = make_int4(tab_min[T.ytab + oy] - row_lo, k[0], k[1], 0);
-  }
-  const int x4 = 4 * lane;
-  const XTaps taps = load_xtaps(T, tab_min, tab_k, ox0 + x4, col_lo, x_shift);
-  {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-          : "=r"(done)
-          : "r"(smem_u32(bar)), "r"(0u)
-          : "memory");
-    }
-  }
-  // ---- phase 1 + 2 ------------------------------------------------------------------------------
-  up_phase1(s_src, region, box_w, s_tmp, max_rows, taps, nrows, warp, x4);
-  __syncthreads();
-  if (ox0 + x4 >= T.nw) return;
-  up_phase2(T, s_tmp, s_ytab, max_rows, ox0, oy0, warp, x4, out);
-}
 
 // ---- warp-autonomous variant of the fast path ("v6") -------------------------------------------
 // The CTA kernels above spend more than half of their issue slots outside the arithmetic: the
@@ -960,13 +884,12 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
     bool launched = false;
     if (P->max_cnt <= 2 && P->max_k <= 3 && (W % 16) == 0 && ((size_t)H * W) % 16 == 0 &&
         ((uintptr_t)image & 15) == 0 && max_rows <= 256 && !getenv("TREEDET_NO_TMA")) {
-      // TMA-staged fast path
+      // TMA-staged fast path (warp-autonomous strips); anything else takes the CTA kernels below
       const int box_w = (P->max_cols + 2 + 15 + 15) & ~15;   // + up to 15 bytes of start alignment
-      const int region = (box_w * max_rows + 127) & ~127;
       CUtensorMap tmap;
       // v6 (warp-autonomous strips): staged row pitch 96 bytes (every 450 -> 800 tile) or 160 (any up-scaling)
       const int box_v6 = box_w <= 96 ? 96 : 160;
-      if (box_w <= 160 && !getenv("TREEDET_P1_CTA") && make_image_tensor_map(&tmap, image, bands, H, W, box_v6, kChunk, 3)) {
+      if (box_w <= 160 && make_image_tensor_map(&tmap, image, bands, H, W, box_v6, kChunk, 3)) {
         const size_t smem_need = (size_t)kWarpsV6 * (2 * 3 * kChunk * box_v6 + 16 + sizeof(float) * kBX);
         // Residency: 4 CTAs (16 warps) per SM already saturate HBM (2.11 ms alone against 2.14 with 6), and
         // what they leave free -- a third of the registers, ~40 KB of shared memory -- lets the latency-
@@ -997,13 +920,6 @@ extern "C" int td_tile_cut_normalize(const void* plan, const void* image, int ba
           if (fork && pass == 1) TD_CUDA(cudaEventRecord(P->ev_join, P->side));
         }
         if (fork) TD_CUDA(cudaStreamWaitEvent(st, P->ev_join, 0));
-        launched = true;
-      } else if (box_w <= 256 && make_image_tensor_map(&tmap, image, bands, H, W, box_w, max_rows, 1)) {
-        const size_t smem_tma = (size_t)3 * region + (size_t)3 * max_rows * kBX + kBX + sizeof(int4) * kBY + 16;
-        auto kern = tile_resize_u8_up_tma_kernel;
-        if (smem_tma > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
-        kern<<<grid, kThreads, smem_tma, st>>>(tmap, P->d_td, P->d_blk, P->d_min, P->d_cnt, P->d_k, out, max_rows, box_w,
-                                               region);
         launched = true;
       }
     }

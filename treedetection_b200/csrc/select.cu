@@ -123,19 +123,19 @@ int td_select_crowns_ex(const double* bounds, const float* max_h, const float* n
   int* rank = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
-  TD_CUDA(cudaMallocAsync((void**)&first, sizeof(int), st));
-  TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
+  TD_CUDA(td_tmp_alloc((void**)&first, sizeof(int), st));
+  TD_CUDA(td_tmp_alloc((void**)&rank, sizeof(int) * n, st));
   TD_CUDA(cudaMemsetAsync(first, 0x7f, sizeof(int), st));   // 0x7f7f7f7f: larger than any index
   const int blocks = td_div_up(n, 256);
   preselect_kernel<<<blocks, 256, 0, st>>>(bounds, max_h, ndvi_stats, n, P, p_dev, pre, first, is_contained, n_dev);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pre, rank, n, st);
-  TD_CUDA(cudaMallocAsync(&tmp, tmp_bytes, st));
+  TD_CUDA(td_tmp_alloc(&tmp, tmp_bytes, st));
   cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pre, rank, n, st);
   decide_kernel<<<blocks, 256, 0, st>>>(pre, rank, num_contained, ndvi_stats, area, first, n, out_idx, n_dev);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(tmp, st);
-  cudaFreeAsync(rank, st);
-  cudaFreeAsync(first, st);
+  td_tmp_free(tmp, st);
+  td_tmp_free(rank, st);
+  td_tmp_free(first, st);
   if (e != cudaSuccess) { td_set_error("td_select_crowns: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
@@ -175,20 +175,20 @@ extern "C" int td_select_head(const double* conf, const double* area, int n, con
   int* rank = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;
-  TD_CUDA(cudaMallocAsync((void**)&ok, sizeof(int) * n, st));
-  TD_CUDA(cudaMallocAsync((void**)&rank, sizeof(int) * n, st));
+  TD_CUDA(td_tmp_alloc((void**)&ok, sizeof(int) * n, st));
+  TD_CUDA(td_tmp_alloc((void**)&rank, sizeof(int) * n, st));
   const int blocks = td_div_up(n, 256);
   head_flags_kernel<<<blocks, 256, 0, st>>>(conf, area, n, n_dev, conf_thr, area_min, area_max, ok, flags);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ok, rank, n, st);
-  cudaError_t e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st);
+  cudaError_t e = td_tmp_alloc(&tmp, tmp_bytes ? tmp_bytes : 1, st);
   if (e == cudaSuccess) {
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ok, rank, n, st);
     widen_kernel<<<blocks, 256, 0, st>>>(rank, n, poly_id);
     e = cudaGetLastError();
-    cudaFreeAsync(tmp, st);
+    td_tmp_free(tmp, st);
   }
-  cudaFreeAsync(rank, st);
-  cudaFreeAsync(ok, st);
+  td_tmp_free(rank, st);
+  td_tmp_free(ok, st);
   if (e != cudaSuccess) { td_set_error("td_select_head: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }

@@ -314,13 +314,13 @@ int td_centroids_ex(const double* verts, const long long* ring_off, const long l
   int* vmax = vmax_scratch;
   if (!vmax) {
     td_ensure_pool();
-    TD_CUDA(cudaMallocAsync((void**)&vmax, sizeof(int), st));
+    TD_CUDA(td_tmp_alloc((void**)&vmax, sizeof(int), st));
   }
   TD_CUDA(cudaMemsetAsync(vmax, 0, sizeof(int), st));
   max_ring_len_kernel<<<td_div_up(n, 256), 256, 0, st>>>(ring_off, ring_idx, n, vmax, n_dev);
   centroid_kernel<<<td_div_up(n, 128), 128, 0, st>>>(verts, ring_off, ring_idx, n, vmax, centroid, n_dev);
   cudaError_t e = cudaGetLastError();
-  if (!vmax_scratch) cudaFreeAsync(vmax, st);
+  if (!vmax_scratch) td_tmp_free(vmax, st);
   if (e != cudaSuccess) { td_set_error("td_centroids: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }

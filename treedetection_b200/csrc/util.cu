@@ -130,13 +130,13 @@ int select_flagged(InIt in, FlagIt flags, long long* out, long long* count, int 
   size_t bytes = 0;
   TD_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, in, flags, out, count, n, st));
   void* tmp = nullptr;
-  TD_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, st));
+  TD_CUDA(td_tmp_alloc(&tmp, bytes ? bytes : 1, st));
   cudaError_t e = cub::DeviceSelect::Flagged(tmp, bytes, in, flags, out, count, n, st);
   if (e == cudaSuccess) {
     fill_tail_kernel<<<td_div_up(n, 256), 256, 0, st>>>(out, n, count);
     e = cudaGetLastError();
   }
-  cudaFreeAsync(tmp, st);
+  td_tmp_free(tmp, st);
   if (e != cudaSuccess) { td_set_error("compaction: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
@@ -162,8 +162,8 @@ extern "C" int td_scan_clamp(const long long* sizes, int k, int n, const long lo
   TD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, sizes, offs, n, st));
   void* tmp = nullptr;
   int* i0 = nullptr;
-  TD_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, st));
-  TD_CUDA(cudaMallocAsync((void**)&i0, sizeof(int), st));
+  TD_CUDA(td_tmp_alloc(&tmp, bytes ? bytes : 1, st));
+  TD_CUDA(td_tmp_alloc((void**)&i0, sizeof(int), st));
   cudaError_t e = cudaMemsetAsync(i0, 0x7f, sizeof(int), st);   // 0x7f7f7f7f: larger than any index
   for (int r = 0; r < k && e == cudaSuccess; ++r)
     e = cub::DeviceScan::ExclusiveSum(tmp, bytes, sizes + (size_t)r * n, offs + (size_t)r * (n + 1), n, st);
@@ -174,8 +174,8 @@ extern "C" int td_scan_clamp(const long long* sizes, int k, int n, const long lo
     clamp_offsets_kernel<<<td_div_up(n + 1, 256), 256, 0, st>>>(sizes, offs, k, n, i0, totals, flag, win_zero);
     e = cudaGetLastError();
   }
-  cudaFreeAsync(i0, st);
-  cudaFreeAsync(tmp, st);
+  td_tmp_free(i0, st);
+  td_tmp_free(tmp, st);
   if (e != cudaSuccess) { td_set_error("td_scan_clamp: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
@@ -240,9 +240,9 @@ extern "C" int td_ring_offsets(const long long* ring_off, const int* count, cons
   size_t bytes = 0;
   TD_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, lens, dst_off + 1, n, st));
   void* tmp = nullptr;
-  TD_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, st));
+  TD_CUDA(td_tmp_alloc(&tmp, bytes ? bytes : 1, st));
   cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, bytes, lens, dst_off + 1, n, st);
-  cudaFreeAsync(tmp, st);
+  td_tmp_free(tmp, st);
   if (e != cudaSuccess) { td_set_error("td_ring_offsets: %s", cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }

@@ -8,7 +8,13 @@ error behaviour as ``TreeDetection/detection.py``:
     cleanup_files(config)                      detection.py:375-399
 
 Between the artefacts the work is done by the device pipeline (``pipeline.py`` over the
-C-ABI kernels): one read of each raster, one pass on the GPU, one write of each vector file.
+C-ABI kernels).  Called stage by stage (as the reference's API allows) every stage reads its
+inputs from the previous stage's artefacts.  ``process_files`` runs the stages inside a
+:class:`_Session`: while ``predict_tiles`` has an image's rasters and crown table on the device
+it also runs that image's post-processing (``api.run_image`` / ``pipeline.ChainRunner``: one read
+of each raster into pinned memory, one CUDA-graph pass, the next image's rasters decoded meanwhile)
+and writes BOTH artefacts; ``postprocess_files`` then finds its outputs in place and only does its
+bookkeeping.  The files on disk are the same either way (tests/test_gpu_api.py).
 The Mask R-CNN forward is replaced by the predictor plug (``predictor.py``)."""
 from __future__ import annotations
 
@@ -30,6 +36,35 @@ from .merging import merge_and_crop_images
 from .predictor import FixturePredictor
 
 
+class _Session:
+    """Device-side state shared by the stages of ONE ``process_files`` call (the fast path)."""
+
+    def __init__(self):
+        self.processed = {}        # stitched .gpkg path -> processed_*.gpkg written while predicting
+        self.runners = {}          # tiling key -> pipeline.ChainRunner (capacities + CUDA graphs per tiling)
+        self.tables = {}           # tiling key -> (api.TileTables, reusable P1 output buffer)
+        self.pinned = {}           # (name, shape, dtype, parity) -> pinned staging tensor
+        self.loader = None         # background decoder of the NEXT image's rasters
+        self.stage_s = {}          # wall seconds per stage (read by bench.py's e2e_files)
+        self.images = 0
+        self.fallback_images = 0   # images that went through the stage-by-stage path
+
+    def pinned_array(self, name, shape, dtype, parity):
+        key = (name, tuple(shape), np.dtype(dtype).str, parity)
+        t = self.pinned.get(key)
+        if t is None:
+            tdt = {"|u1": torch.uint8, "<f4": torch.float32, "<u2": torch.int16, "<i2": torch.int16}[np.dtype(dtype).str]
+            t = torch.empty(tuple(shape), dtype=tdt).pin_memory()
+            self.pinned[key] = t
+        return t
+
+    def close(self):
+        if self.loader is not None:
+            self.loader.shutdown(wait=True)
+            self.loader = None
+        self.runners.clear(); self.tables.clear(); self.pinned.clear()
+
+
 def _device(config):
     dev = config.get("device", "0")
     if dev == "cpu" or not torch.cuda.is_available():
@@ -41,7 +76,7 @@ def _device(config):
 # tiling (P0b)
 # --------------------------------------------------------------------------------------
 def tile_data(file_list, out_dir, buffer=30, tile_width=200, tile_height=200, parallel=False, max_workers=4,
-              forest_shapefile=None, logger=None):
+              forest_shapefile=None, logger=None, device=None):
     """preprocessing.py:125-224: one ``<stem>.json`` per image + ``recovery.yaml``."""
     os.makedirs(out_dir, exist_ok=True)
     recovery_file = os.path.join(out_dir, "recovery.yaml")
@@ -64,7 +99,7 @@ def tile_data(file_list, out_dir, buffer=30, tile_width=200, tile_height=200, pa
     forest = None
     if forest_shapefile:
         from .fusion import ForestIndex
-        forest = ForestIndex.from_file(forest_shapefile, logger=logger)
+        forest = ForestIndex.from_file(forest_shapefile, device=device, logger=logger)
     total = len(todo)
     for i, data_path in enumerate(todo):
         try:
@@ -130,9 +165,13 @@ def preprocess_files(config):
         if match:
             height_data_identifiers["".join(match.groups())] = f
 
+    # every kernel of libtreedet runs on the CURRENT device's stream and scratch pool: make the configured
+    # device current for the duration of the call (config["device"] may name any GPU of the box)
+    dev = _device(config)
     if config["use_overlap"]:
         logger.info("Using overlapping tiles for processing, do merging right now ...")
-        merge_and_crop_images(config, images_paths, height_paths, _device(config))
+        with torch.cuda.device(dev):
+            merge_and_crop_images(config, images_paths, height_paths, dev)
 
     for identifier, image_path in image_identifiers.items():
         if identifier not in height_data_identifiers:
@@ -144,9 +183,10 @@ def preprocess_files(config):
             f"already been processed.")
 
     logger.info(f"Found {len(images_paths)} images for processing. Starting tiling...")
-    tile_data(images_paths, config["tiles_path"], config["buffer"], config["tile_width"], config["tile_height"],
-              parallel=config["parallel"], max_workers=config["num_workers"], logger=config["logger"],
-              forest_shapefile=config.get("forrest_outline", None))
+    with torch.cuda.device(dev):
+        tile_data(images_paths, config["tiles_path"], config["buffer"], config["tile_width"], config["tile_height"],
+                  parallel=config["parallel"], max_workers=config["num_workers"], logger=config["logger"],
+                  forest_shapefile=config.get("forrest_outline", None), device=dev)
     return images_paths
 
 
@@ -176,6 +216,11 @@ def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10,
                      stitched_path=None):
     """detection.py:62-132 + helpers.process_and_stitch_predictions (helpers.py:556-600) in one
     device pass per image: raw ROI-head outputs -> ``<stitched_path>/<stem>.gpkg``."""
+    with torch.cuda.device(_device(config)):
+        return _predict_on_model(config, model_path, tiles_path, output_path, batch_size, exclude_vars, stitched_path)
+
+
+def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, exclude_vars, stitched_path):
     logger = config.get("logger", None)
     for path, name in [(model_path, "Model file"), (tiles_path, "Tiles directory")]:
         if not os.path.exists(path):
@@ -223,14 +268,17 @@ def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10,
             tile_json = os.path.join(tiles_path, stem + ".json")
             with open(tile_json) as f:
                 tiles = json.load(f)
-            img, info = geotiff.read(fp)
-            det = predictor.raw_outputs(stem, tiles)
             tables = api.TileTables(tiles, dev, params.shift)
-            d_img = torch.from_numpy(img.view(np.int16) if img.dtype == np.uint16 else img).to(dev)
-            # P1: normalised tiles for the predictor (a live model adapter consumes them on the device)
             if getattr(predictor, "wants_tiles", False):
+                # P1: normalised tiles for a live model adapter, consumed on the device
+                img, info = geotiff.read(fp)
+                d_img = torch.from_numpy(img.view(np.int16) if img.dtype == np.uint16 else img).to(dev)
                 tiles_dev, tiles_off, flags = tables.plan(d_img).run(d_img)
                 det = predictor.forward(stem, tiles, tiles_dev, tiles_off, flags)
+                del d_img, img
+            else:       # fixtures replay: the raster itself is not needed here, only its CRS
+                info = geotiff.read_info(fp)
+                det = predictor.raw_outputs(stem, tiles)
             t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             boxes, scores, probs, inst_tile, tile_dims = (t(det.boxes_net), t(det.scores), t(det.probs),
                                                           t(det.inst_tile), t(det.tile_dims))
@@ -280,8 +328,9 @@ def predict_tiles(config):
                          batch_size=config["batch_size"], exclude_vars=["only_urban"], stitched_path=forrest_fold)
         t2 = time.time()
         logger.info("Predictions have been processed and stitched. Begin fusing the predictions.")
-        fuse_predictions(urban_fold, forrest_fold, config["forrest_outline"], os.path.join(out, "geojson_predictions"),
-                         logger=logger)
+        with torch.cuda.device(_device(config)):
+            fuse_predictions(urban_fold, forrest_fold, config["forrest_outline"], os.path.join(out, "geojson_predictions"),
+                             logger=logger, device=_device(config))
         t3 = time.time()
         logger.info("Fusion based on forest outline has been completed.")
         logger.debug(f"predict + stitch for urban took {t1 - t0} seconds")
@@ -328,9 +377,36 @@ def _find_matching_file(base_name, geojson_pattern, search_pattern, directory, i
     return None
 
 
+def _match_rasters(base_name, patterns, height_directory, image_directory, height_index=None, image_index=None):
+    """the nDSM / RGBI rasters of a crown layer (postprocessing.py:1030-1049): plain images by the configured
+    regexes, seam strips by the merged ones"""
+    image_pattern, height_pattern, image_merged_pattern, height_merged_pattern = patterns
+    hpath = _find_matching_file(base_name, image_pattern, height_pattern, height_directory, height_index)
+    ipath = _find_matching_file(base_name, image_pattern, image_pattern, image_directory, image_index)
+    if hpath is None or ipath is None:
+        hpath = _find_matching_file(base_name, image_merged_pattern, height_merged_pattern, height_directory)
+        ipath = _find_matching_file(base_name, image_merged_pattern, image_merged_pattern, image_directory)
+    return hpath, ipath
+
+
 _RECOVERY_KEYS = ("confidence_threshold", "containment_threshold", "height_threshold", "ndvi_mean_threshold",
                   "ndvi_var_threshold", "iou_threshold", "area_threshold", "ndvi_scaling_factor",
                   "height_scaling_factor", "use_overlap")
+
+
+def _write_processed(h, processed_file_path, epsg, logger=None):
+    """``processed_<image>.gpkg`` (schema postprocessing.py:904-919) from the host crown layer"""
+    columns = {
+        "Confidence_score": h["conf"], "poly_id": [str(int(v)) for v in h["poly_id"]], "Area": h["area"],
+        "TreeHeight": h["tree_height"],
+        "Centroid": [json.dumps({"x": float(c[0]), "y": float(c[1])}) for c in h["centroid"]],
+        "Diameter": [2 * (float(a) / np.pi) ** 0.5 for a in h["area"]],
+        "is_contained": [str(bool(v)) for v in h["is_contained"]], "num_contained": h["num_contained"],
+    }
+    layer = Path(processed_file_path).stem
+    gpkg.write_layer(processed_file_path, layer, h["verts"], h["ring_off"], columns, gpkg.PROCESSED_SCHEMA, epsg=epsg)
+    if logger:
+        logger.debug(f" File {os.path.basename(processed_file_path)}, # crowns {len(h['poly_id'])} ")
 
 
 def process_single_file(file_path, processed_file_path, height_data_path, rgbi_data_path, config, dev):
@@ -353,18 +429,7 @@ def process_single_file(file_path, processed_file_path, height_data_path, rgbi_d
                                         hinfo.transform, params)
         feats = pipeline.postprocess_stage(table, rasters, params)
         h = api.features_to_host(feats)
-        n = len(h["poly_id"])
-        columns = {
-            "Confidence_score": h["conf"], "poly_id": [str(int(v)) for v in h["poly_id"]], "Area": h["area"],
-            "TreeHeight": h["tree_height"],
-            "Centroid": [json.dumps({"x": float(c[0]), "y": float(c[1])}) for c in h["centroid"]],
-            "Diameter": [2 * (float(a) / np.pi) ** 0.5 for a in h["area"]],
-            "is_contained": [str(bool(v)) for v in h["is_contained"]], "num_contained": h["num_contained"],
-        }
-        layer = Path(processed_file_path).stem
-        gpkg.write_layer(processed_file_path, layer, h["verts"], h["ring_off"], columns, gpkg.PROCESSED_SCHEMA,
-                         epsg=epsg or rinfo.epsg or 4326)
-        logger.debug(f" File {os.path.basename(processed_file_path)}, # crowns {n} ")
+        _write_processed(h, processed_file_path, epsg or rinfo.epsg or 4326, logger)
         return file_path
     except Exception as e:
         print(f"Error postprocessing file {file_path}: {e}")
@@ -374,6 +439,11 @@ def process_single_file(file_path, processed_file_path, height_data_path, rgbi_d
 def process_files_in_directory(directory, height_directory, image_directory, config, parallel=True,
                                filename_pattern=None):
     """postprocessing.py:945-1076 (files are independent; one device pass each)."""
+    with torch.cuda.device(_device(config)):
+        return _process_files_in_directory(directory, height_directory, image_directory, config, filename_pattern)
+
+
+def _process_files_in_directory(directory, height_directory, image_directory, config, filename_pattern):
     logger = config["logger"]
     dev = _device(config)
     rec_file = os.path.join(directory, "recovery.yaml")
@@ -395,14 +465,18 @@ def process_files_in_directory(directory, height_directory, image_directory, con
     height_merged_pattern = re.compile(config["height_data_merged_regex"])
     image_index = _build_file_index(image_directory, image_pattern)
     height_index = _build_file_index(height_directory, height_pattern)
+    session = config.get("_session")
     for filename in files:
         file_path = os.path.join(directory, filename)
         base_name = os.path.splitext(os.path.basename(filename))[0]
-        hpath = _find_matching_file(base_name, image_pattern, height_pattern, height_directory, height_index)
-        ipath = _find_matching_file(base_name, image_pattern, image_pattern, image_directory, image_index)
-        if hpath is None or ipath is None:
-            hpath = _find_matching_file(base_name, image_merged_pattern, height_merged_pattern, height_directory)
-            ipath = _find_matching_file(base_name, image_merged_pattern, image_merged_pattern, image_directory)
+        done = session.processed.get(file_path) if session is not None else None
+        if done and os.path.exists(done):        # post-processed while its rasters were on the device (fast path)
+            logger.info(f"Processing file {file_path}: already post-processed in the prediction pass.")
+            processed_files.add(file_path)
+            continue
+        hpath, ipath = _match_rasters(base_name, (image_pattern, height_pattern, image_merged_pattern,
+                                                  height_merged_pattern), height_directory, image_directory,
+                                      height_index, image_index)
         if hpath and ipath:
             res = process_single_file(file_path, os.path.join(directory, f"processed_{filename}"), hpath, ipath, config,
                                       dev)
@@ -447,14 +521,29 @@ def process_files(config):
     logger = config["logger"]
     config_obj = Config()
     config_obj._load_into_config(config)
-    t0 = time.time()
-    preprocess_files(config)
-    t1 = time.time()
-    predict_tiles(config)
-    t2 = time.time()
-    postprocess_files(config)
-    t3 = time.time()
-    cleanup_files(config)
+    # the stages share device state for the duration of this call (see _Session); a two-model run needs the
+    # fusion between prediction and post-processing and takes the stage-by-stage path
+    session = config.get("_session")
+    own_session = session is None and not config.get("no_session", False)
+    if own_session:
+        session = config["_session"] = _Session()
+    try:
+        t0 = time.time()
+        preprocess_files(config)
+        t1 = time.time()
+        predict_tiles(config)
+        t2 = time.time()
+        postprocess_files(config)
+        t3 = time.time()
+        cleanup_files(config)
+        if session is not None:
+            session.stage_s.update(preprocess=t1 - t0, predict=t2 - t1, postprocess=t3 - t2, cleanup=time.time() - t3)
+            config["_last_session_stats"] = {"stage_s": dict(session.stage_s), "images": session.images,
+                                             "fallback_images": session.fallback_images}
+    finally:
+        if own_session:
+            session.close()
+            config.pop("_session", None)
     logger.debug(f"preprocess step took {t1 - t0} seconds. ")
     logger.debug(f"predict step took {t2 - t1} seconds. ")
     logger.debug(f"postprocess step took {t3 - t2} seconds. ")

@@ -110,19 +110,37 @@ def _lzw(raw: bytes, cap: int) -> bytes:
 
 
 def read_info(path) -> GeoInfo:
+    import mmap
     with open(path, "rb") as f:
-        head = f.read(8)
-        bo = "<" if head[:2] == b"II" else ">"
-        if struct.unpack(bo + "H", head[2:4])[0] != 42:
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)   # only the pages of the header / IFD are touched
+    try:
+        bo = "<" if buf[:2] == b"II" else ">"
+        if struct.unpack(bo + "H", buf[2:4])[0] != 42:
             raise ValueError("not a classic TIFF")
-        buf = head + f.read()          # IFD may be anywhere; files on this path are modest
-    return _info_from_tags(_read_ifd(buf, bo))
+        return _info_from_tags(_read_ifd(buf, bo))
+    finally:
+        buf.close()
 
 
-def read(path, window=None):
-    """Returns (array (bands, H, W), GeoInfo).  window = (col_off, row_off, w, h)."""
+def read(path, window=None, out=None):
+    """Returns (array (bands, h, w), GeoInfo).  window = (col_off, row_off, w, h): only the strips / tiles
+    that intersect it are decoded (rasterio's windowed read, prediction.py:164, postprocessing.py:781-800).
+    ``out``: optional destination of shape (bands, h, w) and the raster's dtype -- e.g. the NumPy view of a
+    PINNED torch tensor, so that the pixels go from the page cache to the buffer the H2D copy reads with a
+    single copy.  The file is memory mapped; uncompressed data is never staged anywhere else."""
+    import mmap
     with open(path, "rb") as f:
-        buf = f.read()
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    try:
+        return _read_mapped(buf, window, out)
+    finally:
+        try:
+            buf.close()
+        except BufferError:      # a zero-copy view is still alive (never the case for the returned array)
+            pass
+
+
+def _read_mapped(buf, window, out):
     bo = "<" if buf[:2] == b"II" else ">"
     if struct.unpack(bo + "H", buf[2:4])[0] != 42:
         raise ValueError("not a classic TIFF")
@@ -137,13 +155,33 @@ def read(path, window=None):
     planar = int(t.get(284, (1,))[0])
     W, H, C = info.width, info.height, info.count
     dt = info.dtype.newbyteorder(bo)
-    out = np.empty((C, H, W), dtype=info.dtype)
+    if window is None:
+        c0, r0, w, h = 0, 0, W, H
+    else:
+        c0, r0, w, h = (int(v) for v in window)
+        if c0 < 0 or r0 < 0 or w <= 0 or h <= 0 or c0 + w > W or r0 + h > H:
+            raise ValueError(f"window {window} outside the {W}x{H} raster")
+    if out is None:
+        out = np.empty((C, h, w), dtype=info.dtype)
+    elif tuple(out.shape) != (C, h, w) or out.dtype != info.dtype:
+        raise ValueError(f"out has shape {out.shape} / {out.dtype}, the read needs {(C, h, w)} / {info.dtype}")
     spp = 1 if planar == 2 else C              # samples per pixel inside one chunk
-    if 322 in t:
+    tiled = 322 in t
+    if tiled:
         chunk_rows, chunk_cols = int(t[323][0]), int(t[322][0])
+        all_offs, all_cnts = t[324], t[325]
     else:
         chunk_rows, chunk_cols = int(t.get(278, (H,))[0]), W
+        all_offs, all_cnts = t[273], t[279]
+    chunk_rows = min(chunk_rows, H) if not tiled else chunk_rows
     chunk_bytes = chunk_rows * chunk_cols * spp * info.dtype.itemsize
+    nx = (W + chunk_cols - 1) // chunk_cols
+    ny = (H + chunk_rows - 1) // chunk_rows
+    per_plane = nx * ny
+    # chunks that intersect the window
+    js = range(r0 // chunk_rows, (r0 + h - 1) // chunk_rows + 1)
+    is_ = range(c0 // chunk_cols, (c0 + w - 1) // chunk_cols + 1)
+    need = [(p, j, i) for p in range(C if planar == 2 else 1) for j in js for i in is_]
 
     def unpredict(raw, rows):
         """undo the TIFF predictor of one decoded chunk (rows x chunk_cols x spp samples)"""
@@ -159,59 +197,45 @@ def read(path, window=None):
         b = b.reshape(rows, 4, n)[:, ::-1, :] if bo == "<" else b.reshape(rows, 4, n)
         return np.ascontiguousarray(b.transpose(0, 2, 1)).tobytes()
 
-    def decode(k):
-        off, cnt = all_offs[k], all_cnts[k]
-        raw = buf[off:off + cnt]
-        if comp == 5:
-            raw = _lzw(raw, chunk_bytes)
-        elif comp != 1:
-            raw = zlib.decompress(raw)
-        return raw
+    def rows_of(j):
+        return chunk_rows if tiled else min(chunk_rows, H - j * chunk_rows)
 
-    all_offs, all_cnts = (t[324], t[325]) if 322 in t else (t[273], t[279])
-    if comp != 1 and len(all_offs) > 4:      # zlib and the LZW decoder release the GIL
+    def decode(pji):
+        p, j, i = pji
+        k = p * per_plane + j * nx + i
+        off, cnt = all_offs[k], all_cnts[k]
+        if comp == 1:
+            # zero-copy view of the mapped file: the only copy is the one into `out`
+            return np.frombuffer(buf, dtype=dt, count=rows_of(j) * chunk_cols * spp, offset=off)
+        raw = buf[off:off + cnt]
+        raw = _lzw(raw, chunk_bytes) if comp == 5 else zlib.decompress(raw)
+        return np.frombuffer(unpredict(raw, rows_of(j)), dtype=dt)
+
+    if comp != 1 and len(need) > 4:      # zlib and the LZW decoder release the GIL
         from concurrent.futures import ThreadPoolExecutor
         import os
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-            decoded = list(ex.map(decode, range(len(all_offs))))
+            decoded = list(ex.map(decode, need))
     else:
-        decoded = [decode(k) for k in range(len(all_offs))]
-
-    def chunk(k, rows):
-        return unpredict(decoded[k], rows)
-
-    if 322 in t:   # tiles
-        tw, th = int(t[322][0]), int(t[323][0])
-        offs, cnts = t[324], t[325]
-        tx, ty = (W + tw - 1) // tw, (H + th - 1) // th
-        per_plane = tx * ty
-        for p in range(C if planar == 2 else 1):
-            for j in range(ty):
-                for i in range(tx):
-                    k = p * per_plane + j * tx + i
-                    a = np.frombuffer(chunk(k, th), dtype=dt)
-                    hh, ww = min(th, H - j * th), min(tw, W - i * tw)
-                    if planar == 2:
-                        out[p, j * th:j * th + hh, i * tw:i * tw + ww] = a.reshape(th, tw)[:hh, :ww]
-                    else:
-                        out[:, j * th:j * th + hh, i * tw:i * tw + ww] = a.reshape(th, tw, C)[:hh, :ww].transpose(2, 0, 1)
-    else:
-        rps = int(t.get(278, (H,))[0])
-        offs, cnts = t[273], t[279]
-        ns = (H + rps - 1) // rps
-        for p in range(C if planar == 2 else 1):
-            for s_ in range(ns):
-                k = p * ns + s_
-                r0 = s_ * rps
-                hh = min(rps, H - r0)
-                a = np.frombuffer(chunk(k, hh), dtype=dt)
-                if planar == 2:
-                    out[p, r0:r0 + hh] = a[:hh * W].reshape(hh, W)
-                else:
-                    out[:, r0:r0 + hh] = a[:hh * W * C].reshape(hh, W, C).transpose(2, 0, 1)
+        decoded = None
+    for n_, (p, j, i) in enumerate(need):
+        a = decoded[n_] if decoded is not None else decode((p, j, i))
+        rr = rows_of(j)
+        y0, x0 = j * chunk_rows, i * chunk_cols
+        # intersection of the chunk with the window, in chunk and in output coordinates
+        ya, yb = max(y0, r0), min(y0 + min(rr, H - y0), r0 + h)
+        xa, xb = max(x0, c0), min(x0 + min(chunk_cols, W - x0), c0 + w)
+        if ya >= yb or xa >= xb:
+            continue
+        if planar == 2:
+            out[p, ya - r0:yb - r0, xa - c0:xb - c0] = a[:rr * chunk_cols].reshape(rr, chunk_cols)[ya - y0:yb - y0,
+                                                                                                  xa - x0:xb - x0]
+        else:
+            out[:, ya - r0:yb - r0, xa - c0:xb - c0] = \
+                a[:rr * chunk_cols * C].reshape(rr, chunk_cols, C)[ya - y0:yb - y0, xa - x0:xb - x0].transpose(2, 0, 1)
+        del a
+    decoded = None
     if window is not None:
-        c0, r0, w, h = window
-        out = np.ascontiguousarray(out[:, r0:r0 + h, c0:c0 + w])
         a, b, c, d, e, f = info.transform
         info = GeoInfo(w, h, C, info.dtype, (a, b, a * c0 + b * r0 + c, d, e, d * c0 + e * r0 + f), info.epsg, info.nodata)
     return out, info

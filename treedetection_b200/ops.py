@@ -509,14 +509,17 @@ def tile_cut_normalize(image, tile_win, tile_net, out=None):
     return TilePlan(tile_win, tile_net, elem, h, w).run(image, out)
 
 
-def seam_crop(a, b, axis, strip_w, strip_h):
+def seam_crop(a, b, axis, strip_w, strip_h, out=None):
     """a, b: (bands,H,W) device rasters of the same dtype; axis 0 = b is the right
-    neighbour, 1 = b is the lower neighbour.  Returns (bands, strip_h, strip_w)."""
+    neighbour, 1 = b is the lower neighbour.  Returns (bands, strip_h, strip_w) (``out`` when given)."""
     if a.dtype != b.dtype:
         raise _lib.TreedetError("seam_crop: dtype mismatch")
     bands, ha, wa = a.shape
     _, hb, wb = b.shape
-    out = torch.empty((bands, strip_h, strip_w), dtype=a.dtype, device=a.device)
+    if out is None:
+        out = torch.empty((bands, strip_h, strip_w), dtype=a.dtype, device=a.device)
+    elif tuple(out.shape) != (bands, strip_h, strip_w) or out.dtype != a.dtype:
+        raise _lib.TreedetError("seam_crop: output buffer of the wrong shape / dtype")
     _lib.call("td_seam_crop", _ptr(a), _ptr(b), a.element_size(), bands, ha, wa, hb, wb, axis, strip_w, strip_h,
               _ptr(out), _stream())
     return out

@@ -283,6 +283,8 @@ class ChainRunner:
         self.chain = None
         self._seq = 0
         self._busy = [None] * n_slots   # ticket id occupying each slot
+        self.last_table = None          # stitched table (CrownTable) of the image collected last
+        self.last_counters = None
         self._pinned = []               # recycled pinned read-back buffers (allocating one costs ~0.1 ms)
 
     def _learn(self, sizes: dict):
@@ -322,6 +324,7 @@ class ChainRunner:
         self._learn(sizes)
         table = _stitch(rings, det["scores"], det["inst_tile"], tile_boxes, p)
         feats = postprocess_stage(table, rasters_fn(), p)
+        self.last_table = table
         return len(table), feats
 
     def submit(self, det: dict, tile_tf, tile_boxes, rasters_fn, mark=None):
@@ -387,6 +390,8 @@ class ChainRunner:
         self._learn({"words": c[CTR_WORDS], "px": c[CTR_PX], "ptslots": c[CTR_SLOTS], "rings": c[CTR_RINGS],
                      "verts": c[CTR_VERTS]})
         self.last_counters = c
+        tv, to, tc = chain.table(slot)
+        self.last_table = CrownTable(tv[:c[CTR_VTABLE]], to[:c[CTR_NTABLE] + 1], tc[:c[CTR_NTABLE]])
         return c[CTR_NTABLE], trim_features(chain.features(slot), c[CTR_NFINAL], c[CTR_VFINAL])
 
     def table(self, ticket_counters, slot):

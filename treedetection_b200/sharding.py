@@ -27,15 +27,20 @@ def halo_rows(tile_height, buffer, overlapping_tiles_height):
     return sh - sh // 2
 
 
-def exchange_down_halos(tops, rank, world, group=None):
+def exchange_down_halos(tops, rank, world, group=None, recv=None):
     """``tops``: list of contiguous tensors holding the TOP halo rows of this rank's rasters.
     Sends them to rank - 1 and returns the list received from rank + 1 (``None`` on the last
-    rank).  One batched isend/irecv per call; tensors keep their device."""
+    rank).  One batched isend/irecv per call; tensors keep their device.  ``recv``: optional
+    pre-allocated receive buffers (same shapes as ``tops``), re-used across steps."""
     if world == 1:
         return None
-    ops_, recv = [], None
+    ops_ = []
     if rank + 1 < world:
-        recv = [torch.empty_like(t) for t in tops]
+        if recv is None:
+            recv = [torch.empty_like(t) for t in tops]
+    else:
+        recv = None
+    if rank + 1 < world:
         ops_ += [dist.P2POp(dist.irecv, t, rank + 1, group) for t in recv]
     if rank > 0:
         ops_ += [dist.P2POp(dist.isend, t, rank - 1, group) for t in tops]
@@ -44,7 +49,7 @@ def exchange_down_halos(tops, rank, world, group=None):
     return recv
 
 
-def assemble_down_strip(own, halo, sh=None):
+def assemble_down_strip(own, halo, sh=None, out=None):
     """own (bands, H, W) device raster of this rank, halo (bands, rows, W) = top rows of the
     lower neighbour, ``sh`` = strip height (default 2 * rows).  Returns the (bands, sh, W) seam strip:
     ``sh // 2`` bottom rows of ``own`` followed by ``sh - sh // 2`` rows of the halo -- the same rows
@@ -57,4 +62,4 @@ def assemble_down_strip(own, halo, sh=None):
         raise ValueError(f"assemble_down_strip: a strip of {sh} rows needs {sh - up} halo rows, got {rows}")
     bottom = own[:, own.shape[1] - up:, :].contiguous()
     # mosaic of (up rows, rows rows): its centre crop of height sh starts at (up + rows) // 2 - sh // 2 = 0
-    return ops.seam_crop(bottom, halo, 1, own.shape[2], sh)
+    return ops.seam_crop(bottom, halo, 1, own.shape[2], sh, out=out)
