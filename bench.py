@@ -45,9 +45,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
-    ap.add_argument("--p1-after-walk", action="store_true",
-                    help="start P1 only when the border walk of the image is done (they compete for shared memory)")
-    ap.add_argument("--strip-last", action="store_true", help="N > 1: enqueue the seam strip after the image's chain")
+    ap.add_argument("--no-files", action="store_true", help="skip e2e_files (process_files on GeoTIFFs on tmpfs)")
+    ap.add_argument("--files-images", type=int, default=3, help="images of the workload in e2e_files")
+    ap.add_argument("--join-steps", action="store_true",
+                    help="join all streams after every image (default: the streams run free between the two ends of "
+                         "the timed region; images are independent)")
     ap.add_argument("--no-alone", action="store_true",
                     help="do not time the roofline kernel alone after the timed region (profiling runs: keeps the "
                          "launch list to whole steps); the roofline entry then uses the in-step time")
@@ -188,6 +190,79 @@ def run_reference(a):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# e2e_files: the reference-facing API on GeoTIFFs (process_files), per-stage wall clock
+# --------------------------------------------------------------------------------------
+def e2e_files(sc, n_images, label):
+    """``process_files(config)`` -- the call a user of the reference makes -- over ``n_images`` GeoTIFF pairs on
+    tmpfs: RGBI + nDSM rasters written uncompressed, ROI-head fixtures staged as the "model", config.yml as in
+    example/config.yml.  The images are copies of the scene at origins 10 km apart (no neighbours, so no
+    seam strips; use_overlap stays on).  Returns km^2/s over the whole call and the per-stage seconds."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import yaml
+
+    from treedetection_b200 import detection, geotiff, predictor, synth, tiling
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = tempfile.mkdtemp(prefix="treedet_e2e_", dir=base)
+    try:
+        img_dir, h_dir, model = (os.path.join(root, d) for d in ("rgb", "ndsm", "model"))
+        for d in (img_dir, h_dir, model):
+            os.makedirs(d)
+        H, W = sc.rgbi.shape[1:]
+        h, w = sc.ndsm.shape
+        px, npx = sc.px, abs(sc.ndsm_transform[0])
+        t_w0 = time.perf_counter()
+        for k in range(n_images):
+            stem = f"FDOP20_{k:06d}_rgbi"
+            left = synth.ORIGIN_X + 10000.0 * k
+            top = synth.ORIGIN_Y + H * px
+            tf = synth.image_transform(left, top, px)
+            geotiff.write(os.path.join(img_dir, stem + ".tif"), sc.rgbi, tf, epsg=synth.EPSG)
+            geotiff.write(os.path.join(h_dir, f"nDSM_{k:06d}_1km.tif"), sc.ndsm, synth.image_transform(left, top, npx),
+                          epsg=synth.EPSG, nodata=-3.4028234663852886e38)
+            tiles = tiling.tile_grid(stem, tf, W, H, synth.EPSG, 50, 50, 20)
+            d = sc.det
+            predictor.dump_fixtures(model, stem, synth.Detections(d.boxes_net, d.scores, d.probs, d.inst_tile, d.tile_dims,
+                                                                   list(tiles.keys()), tiles))
+        write_s = time.perf_counter() - t_w0
+        cfg = {
+            "image_directory": img_dir, "height_data_path": h_dir, "image_regex": "FDOP20_(\\d+)_rgbi\\.tif",
+            "height_data_regex": "nDSM_(\\d+)_1km\\.tif", "combined_model": model,
+            "output_directory": os.path.join(root, "output"), "tiles_path": os.path.join(root, "tiles"),
+            "use_overlap": True, "merged_path": "merged", "tile_width": 50, "tile_height": 50, "buffer": 20,
+            "ndvi_scaling_factor": 0.2, "height_scaling_factor": 1.0, "keep_intermediate": False, "device": "0",
+            "image_merged_regex": "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_rgbi\\.tif",
+            "height_data_merged_regex": "nDSM_(\\d+)(\\d+)_1km\\.tif",
+        }
+        path = os.path.join(root, "config.yml")
+        with open(path, "w") as f:
+            yaml.safe_dump(cfg, f)
+        config, _ = detection.get_config(path)
+        config["logger"].setLevel("ERROR")
+        t0 = time.perf_counter()
+        detection.process_files(config)
+        wall = time.perf_counter() - t0
+        stats = config.get("_last_session_stats", {})
+        outs = [f for f in os.listdir(config["output_directory"]) if f.endswith(".gpkg")]
+        from treedetection_b200 import gpkg
+        n_crowns = [len(gpkg.read_layer(os.path.join(config["output_directory"], f))[1]) - 1 for f in sorted(outs)]
+        area = n_images * H * W * px * px / 1e6
+        return {"workload": label, "images": n_images, "value": area / wall, "unit": UNIT, "wall_s": wall,
+                "stage_s": {k: round(v, 3) for k, v in stats.get("stage_s", {}).items()},
+                "fast_path_images": stats.get("images"), "fallback_images": stats.get("fallback_images"),
+                "crowns_per_image": n_crowns,
+                "input_bytes": int(n_images * (sc.rgbi.nbytes + sc.ndsm.nbytes)),
+                "note": f"GeoTIFFs uncompressed on {'tmpfs (/dev/shm)' if base else 'the default temp dir'} (written in "
+                        f"{write_s:.1f} s, not timed); timed: get tiles -> read + decode rasters and fixtures -> H2D -> P1 "
+                        f"+ P2-P9 -> D2H -> stitched, processed and final .gpkg written; the first image of a tiling "
+                        f"learns the capacities (exact-size path), the others replay the CUDA graphs"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -354,7 +429,7 @@ def run_b200(a):
     p5_bufs = [{}, {}, {}]     # NDVI output rasters, rotated (two steps are in flight at most)
     p5_seq = [0]
 
-    def chain(e, on_p3=None):
+    def chain(e):
         """P2-P9 of the resident image on the current stream; e[2..5] bracket the stages"""
         e[2].record()
         if a.exact:
@@ -370,10 +445,7 @@ def run_b200(a):
         marks = {"p4": e[3], "p5": e[4], "p9": e[5]}
 
         def mark(name):
-            if name == "p3":
-                if on_p3 is not None:
-                    on_p3()
-            else:
+            if name in marks:
                 marks[name].record()
         pre = pre_rasters.pop() if pre_rasters else None
         return runner.submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
@@ -381,15 +453,31 @@ def run_b200(a):
                              (lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)),
                              mark=mark)
 
+    side_streams = (p1_stream, chain_stream, strip_stream, p5_stream)
+    p5_guard = [None] * len(p5_bufs)           # chain event after which a P5 output buffer may be overwritten
+    per_step = 2 if (world > 1 and rank + 1 < world) else 1
+    in_flight_steps = 2
+
+    def region_begin():
+        main = torch.cuda.current_stream()
+        for st in side_streams:
+            st.wait_stream(main)
+
+    def region_end():
+        main = torch.cuda.current_stream()
+        for st in side_streams:
+            main.wait_stream(st)
+
     def step_resident():
-        # results of the image enqueued one step ago (the only host wait; the GPU is already busy with
-        # nothing pending only at the very first step)
-        while len(pending) > 1:
+        """One image per GPU (plus, N > 1, the seam strip below it).  The four streams run FREE between the two
+        ends of a timed region: images are independent, so P1 of the next image may start while the chain of
+        this one finishes -- there is no join per step (``--join-steps`` restores one).  The host stays at most
+        ``in_flight_steps`` images ahead: it collects the counters of the image enqueued that long ago."""
+        while len(pending) > (in_flight_steps - 1) * per_step:
             r, t = pending.pop(0)
             n_c, f = r.collect(t)
             if r is runner:
                 results.append((n_c, len(f)))
-        main = torch.cuda.current_stream()
         e = [ev() for _ in range(6)]
         ts = None
         if a.serial:
@@ -400,44 +488,38 @@ def run_b200(a):
             if world > 1:
                 ts = step_strip()
         else:
-            for st in (p1_stream, chain_stream, strip_stream):
-                st.wait_stream(main)
-            def launch_p1(after=None):
-                with torch.cuda.stream(p1_stream):
-                    if after is not None:
-                        p1_stream.wait_event(after)
-                    e[0].record()
-                    tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
-                    e[1].record()
-            p1_late = a.p1_after_walk and not a.exact
-            if not p1_late:
-                launch_p1()
+            if a.join_steps:
+                region_begin()
+            with torch.cuda.stream(p1_stream):
+                e[0].record()
+                tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+                e[1].record()
             if not a.exact:
                 # P5 (issue bound, needed only by the statistics) on its own stream, next to P2-P4
-                p5_stream.wait_stream(main)
                 with torch.cuda.stream(p5_stream):
+                    p5_seq[0] += 1
+                    b = p5_seq[0] % len(p5_bufs)
+                    if p5_guard[b] is not None:
+                        p5_stream.wait_event(p5_guard[b])        # the chain that read this buffer is done
                     q0, q1 = ev(), ev()
                     q0.record()
-                    p5_seq[0] += 1
                     r = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p,
-                                              buffers=p5_bufs[p5_seq[0] % len(p5_bufs)])
+                                              buffers=p5_bufs[b])
                     q1.record()
                     p5_ev.append((q0, q1))
                     r["ndvi_ready"] = p5_stream.record_event()
+                    r["_buf"] = b
                 pre_rasters.append(r)
-            # the strip's ~130 small dependent launches go in first: they run under P1 while the host is
-            # still enqueuing, instead of queueing behind the image's big kernels
-            if world > 1 and not a.strip_last:
+            # the strip's small dependent launches go in first: they run under P1 while the host is still enqueuing
+            if world > 1:
                 with torch.cuda.stream(strip_stream):
                     ts = step_strip()
             with torch.cuda.stream(chain_stream):
-                # --p1-after-walk: P1 starts when the border walk (which wants the SM's shared memory) is done
-                t = chain(e, on_p3=(lambda: launch_p1(chain_stream.record_event())) if p1_late else None)
-            if world > 1 and a.strip_last:
-                with torch.cuda.stream(strip_stream):
-                    ts = step_strip()
-            for st in (p1_stream, chain_stream, strip_stream, p5_stream):
-                main.wait_stream(st)
+                t = chain(e)
+                if not a.exact:
+                    p5_guard[p5_seq[0] % len(p5_bufs)] = chain_stream.record_event()
+            if a.join_steps:
+                region_end()
         p1_ev.append((e[0], e[1]))
         stage_ev.append(e)
         if t is not None:
@@ -460,13 +542,17 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, free_running=False):
         barrier()
         s, e = ev(), ev()
         s.record()
+        if free_running:
+            region_begin()
         out = None
         for _ in range(steps):
             out = fn()
+        if free_running:
+            region_end()
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -476,8 +562,10 @@ def run_b200(a):
             ms = float(t.item())
         return ms, out
 
+    region_begin()
     for _ in range(a.warmup):
         step_resident()
+    region_end()
     drain()
     p1_ev.clear()
     stage_ev.clear()
@@ -486,7 +574,7 @@ def run_b200(a):
     if rank == 0 and not a.no_clocks:
         sampler.start()
     l0 = _lib.launch_count
-    ms, _ = timed(step_resident, a.steps)
+    ms, _ = timed(step_resident, a.steps, free_running=not a.serial)
     drain()
     launches = _lib.launch_count - l0
     assert len(results) == a.steps and len(set(results)) == 1, "steps disagree on the crown counts"
@@ -527,9 +615,10 @@ def run_b200(a):
     # end to end through the host-buffer API
     e2e_runner = pipeline.ChainRunner(p)
     def step_e2e():
+        ts = step_strip() if world > 1 else None     # enqueued first: runs under the image's H2D copies
         out, _ = api.run_image(host, p, dev, tables, p1_out, runner=None if a.exact else e2e_runner)
-        if world > 1:
-            step_strip()
+        if ts is not None:
+            strip_runner.collect(ts)
         return out
     for _ in range(max(1, min(a.warmup, 2))):
         step_e2e()
@@ -571,6 +660,17 @@ def run_b200(a):
                             f"overlap equivalent), P6 ordered bbox NMS + P8 containment, "
                             f"{int(rem.sum().item())} suppressed"}
 
+    files = None
+    if rank == 0 and world == 1 and not a.no_files:
+        torch.cuda.synchronize()
+        del d, p1_out                   # e2e_files brings its own device buffers
+        torch.cuda.empty_cache()
+        files = [e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px))]
+        try:      # BASELINE config 1: the reference's example tile (bundled nDSM 1000^2 @ 1 m + synthetic RGBI 5000^2)
+            files.append(e2e_files(synth.config1_scene(), 2, "BASELINE config 1: example/config.yml on the bundled nDSM tile "
+                                                       "324125317 (1 m) + synthetic 5000x5000 px RGBI"))
+        except Exception as e:          # the fixture of the bundled tile is test data; never fail the bench on it
+            files.append({"workload": "BASELINE config 1", "error": str(e)})
     if rank == 0:
         peaks = {}
         try:
@@ -608,6 +708,9 @@ def run_b200(a):
                        "chain": chain_mode,
                        "streams": ("one stream, stages back to back" if a.serial else
                                    "P1 and P5 on their own streams concurrent with the P2-P4 / P6-P9 chain (high-priority stream); "
+                                   + ("all streams joined after every image; " if a.join_steps else
+                                      "streams run free between the two ends of the timed region (images are independent; the "
+                                      "host stays <= 2 images ahead); ") +
                                    "stage_ms are per-stream CUDA-event times and overlap"),
                        "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                        "cache": "inputs (rasters 0.8 GB, P1 output 12 GB) exceed the 126 MB L2; no flush needed",
@@ -636,6 +739,7 @@ def run_b200(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d_bytes(), "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,
+            "e2e_files": files,
             "parity": parity or "not checked (no golden for this workload size)",
             "clocks": clocks,
             "crowns_merged": merged,

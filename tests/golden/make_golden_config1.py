@@ -26,12 +26,7 @@ SEED = 31
 
 def config1_scene():
     """RGBI 5000^2 @0.2 m + detections over the bundled tile's extent (top-left 412000, 5318000)."""
-    ndsm = np.load(os.path.join(OUT, "ndsm_324125317.npz"))["ndsm"]
-    left, top = 412000.0, 5318000.0
-    sc = synth.make_scene(seed=SEED, size_px=5000, px=0.2, ndsm_px=1.0, density_per_km2=2500.0,
-                          stem="324125317", left=left, bottom=top - 1000.0)
-    sc.ndsm = ndsm
-    return sc
+    return synth.config1_scene(os.path.join(OUT, "ndsm_324125317.npz"), SEED)
 
 
 def main():

@@ -127,3 +127,53 @@ def test_config_errors(tmp_path):
     p.write_text(yaml.safe_dump({"image_directory": str(tmp_path / "missing"), "height_data_path": str(tmp_path)}))
     with pytest.raises(AssertionError):
         detection.get_config(str(p))
+
+
+class _FieldPredictor:
+    """predictor plug that synthesises the ROI-head outputs of any tiling from one tree field"""
+
+    def __init__(self, field):
+        self.field = field
+
+    def raw_outputs(self, stem, tiles):
+        return synth.make_detections(self.field, tiles, PX, seed=5)
+
+
+def test_process_files_fast_path_writes_the_same_files(tmp_path):
+    """``process_files`` (one session: every image decoded once into pinned memory, P1 + the CUDA-graph chain
+    while the next image is decoded, both artefacts written from the device results) against the same stages
+    called one by one (each stage re-reads the previous stage's artefacts): identical layers on disk."""
+    layers = {}
+    for mode in ("session", "staged"):
+        root = tmp_path / mode
+        root.mkdir()
+        cfg_path, field, _ = _project(root)
+        config, _ = detection.get_config(cfg_path)
+        config["predictor"] = _FieldPredictor(field)
+        if mode == "session":
+            detection.process_files(config)
+            stats = config["_last_session_stats"]
+            assert stats["images"] == 3 and stats["fallback_images"] == 0, stats
+            assert set(stats["stage_s"]) >= {"preprocess", "predict", "postprocess", "decode", "device", "write"}
+        else:
+            detection.preprocess_files(config)
+            detection.predict_tiles(config)
+            detection.postprocess_files(config)
+        out = config["output_directory"]
+        got = {}
+        for sub in ("geojson_predictions", "."):
+            d = os.path.join(out, sub)
+            for name in sorted(os.listdir(d)):
+                if name.endswith(".gpkg"):
+                    got[os.path.join(sub, name)] = gpkg.read_layer(os.path.join(d, name))
+        layers[mode] = got
+    a, b = layers["session"], layers["staged"]
+    assert sorted(a) == sorted(b) and len(a) == 9          # 3 x (stitched, processed, final)
+    for name in a:
+        (va, oa, ca, ea), (vb, ob, cb, eb) = a[name], b[name]
+        np.testing.assert_array_equal(va, vb, err_msg=name)
+        np.testing.assert_array_equal(oa, ob, err_msg=name)
+        assert list(ca) == list(cb) and ea == eb, name
+        for col in ca:
+            assert list(ca[col]) == list(cb[col]), (name, col)
+    assert any(len(a[n][1]) - 1 > 10 for n in a if n.startswith("./"))

@@ -56,6 +56,17 @@ class TileTables:
         self.p1_floats = int((3 * self.net[:, 0].long() * self.net[:, 1].long()).sum())
         self._plans = {}
 
+    def retarget(self, tiles: dict, device, shift=1):
+        """Another image with the SAME tile grid (windows, network sizes): only the georeferenced tables -- the
+        tile transforms and the stitch filter boxes -- are refreshed, in place, so that device pointers (and the
+        CUDA graphs keyed on them) and the P1 plans stay valid."""
+        win = torch.tensor([m["window"] for m in tiles.values()], dtype=torch.int32).reshape(-1, 4)
+        if win.shape != self.win.shape or not torch.equal(win, self.win):
+            raise _lib.TreedetError("retarget: the image has another tile grid")
+        tile_tf, boxes_int = pipeline.tile_tables(tiles, device)
+        self.tile_tf.copy_(tile_tf)
+        self.tile_boxes.copy_(pipeline.filter_boxes(boxes_int, shift, device))
+
     def plan(self, image):
         """P1 plan (device tile tables) for rasters shaped like ``image``; built once."""
         key = (image.element_size(), image.shape[1], image.shape[2])

@@ -212,6 +212,110 @@ def _write_tile_predictions(pred_subdir, tifpath, tiles, rings, inst_tile, score
             f.write(json.dumps(ev))
 
 
+class _FastPath:
+    """One image of ``process_files`` end to end while its data is on the device: rasters decoded ONCE into pinned
+    memory (the next image's in a background thread meanwhile), ``api.run_image`` (P1 + the CUDA-graph chain
+    P2-P9, H2D copies overlapped with the stages), then both artefacts -- ``geojson_predictions/<stem>.gpkg`` and
+    ``processed_<stem>.gpkg`` -- are written.  Returns False for anything it does not cover (no matching nDSM,
+    16-bit imagery, a predictor that consumes the tiles): the caller then takes the stage-by-stage path."""
+
+    def __init__(self, config, session, dev, params, predictor, stitched_path, output_path, logger):
+        from concurrent.futures import ThreadPoolExecutor
+        self.config, self.s, self.dev, self.p = config, session, dev, params
+        self.predictor, self.stitched_path, self.output_path, self.logger = predictor, stitched_path, output_path, logger
+        if session.loader is None:
+            session.loader = ThreadPoolExecutor(max_workers=1)
+        self.pending = {}          # image path -> Future of _load
+        self.parity = 0
+        image_pattern = re.compile(config.get("image_regex") or "(\\d+)\\.tif")
+        height_pattern = re.compile(config.get("height_data_regex") or "(\\d+)\\.tif")
+        self.patterns = (image_pattern, height_pattern, re.compile(config["image_merged_regex"]),
+                         re.compile(config["height_data_merged_regex"]))
+        self.height_index = _build_file_index(config["height_data_path"], height_pattern)
+        self.image_index = _build_file_index(config["image_directory"], image_pattern)
+
+    def _load(self, fp, tiles_path, parity):
+        """decode one image's rasters into pinned staging buffers (runs on the loader thread)"""
+        t0 = time.time()
+        stem = Path(fp).stem
+        with open(os.path.join(tiles_path, stem + ".json")) as f:
+            tiles = json.load(f)
+        hpath, ipath = _match_rasters(stem, self.patterns, self.config["height_data_path"],
+                                      self.config["image_directory"], self.height_index, self.image_index)
+        if hpath is None or ipath is None:
+            return None
+        rinfo, hinfo = geotiff.read_info(fp), geotiff.read_info(hpath)
+        if rinfo.dtype != np.uint8 or rinfo.count < 4 or hinfo.dtype != np.float32:
+            return None
+        rgbi = self.s.pinned_array("rgbi", (rinfo.count, rinfo.height, rinfo.width), np.uint8, parity)
+        geotiff.read(fp, out=rgbi.numpy())
+        ndsm = self.s.pinned_array("ndsm", (hinfo.count, hinfo.height, hinfo.width), np.float32, parity)
+        geotiff.read(hpath, out=ndsm.numpy())
+        return {"tiles": tiles, "rgbi": rgbi, "rinfo": rinfo, "ndsm": ndsm[0], "hinfo": hinfo,
+                "decode_s": time.time() - t0}
+
+    def prefetch(self, fp, tiles_path):
+        if fp is not None and fp not in self.pending:
+            self.pending[fp] = self.s.loader.submit(self._load, fp, tiles_path, self.parity)
+            self.parity ^= 1
+
+    def run(self, fp, tiles_path, next_fp):
+        self.prefetch(fp, tiles_path)
+        data = self.pending.pop(fp).result()
+        self.prefetch(next_fp, tiles_path)               # decoded while this image is on the GPU
+        if data is None or getattr(self.predictor, "wants_tiles", False):
+            return False
+        stem = Path(fp).stem
+        tiles, rinfo, hinfo = data["tiles"], data["rinfo"], data["hinfo"]
+        det = self.predictor.raw_outputs(stem, tiles)
+        # images of one shape share a tile grid: tables, the P1 output buffer, capacities and graphs are re-used
+        key = (rinfo.height, rinfo.width, len(tiles), hinfo.height, hinfo.width)
+        if key in self.s.tables:
+            try:
+                self.s.tables[key][0].retarget(tiles, self.dev, self.p.shift)   # same grid, this image's georeference
+            except ops._lib.TreedetError:
+                del self.s.tables[key]
+        if key not in self.s.tables:
+            tables = api.TileTables(tiles, self.dev, self.p.shift)
+            self.s.tables[key] = (tables, torch.empty((tables.p1_floats,), dtype=torch.float32, device=self.dev))
+            self.s.runners[key] = pipeline.ChainRunner(self.p)
+        tables, p1_out = self.s.tables[key]
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        img = api.HostImage(data["rgbi"], rinfo.transform, data["ndsm"], hinfo.transform, tiles, pin(det.boxes_net),
+                            pin(det.scores), pin(det.probs), pin(det.inst_tile), pin(det.tile_dims))
+        t0 = time.time()
+        host, _ = api.run_image(img, self.p, self.dev, tables, p1_out, runner=self.s.runners[key], want_table=True)
+        t1 = time.time()
+        if self.config.get("keep_intermediate", False) and len(det.scores):
+            _write_predictions_json(self.output_path, stem, fp, tiles, det, tables, self.p, self.dev)
+        epsg = rinfo.epsg or 4326
+        stitched = os.path.join(self.stitched_path, stem + ".gpkg")
+        gpkg.write_layer(stitched, stem, host["table_verts"], host["table_ring_off"],
+                         {"Confidence_score": host["table_conf"]}, gpkg.STITCHED_SCHEMA, epsg=epsg)
+        processed = os.path.join(self.stitched_path, f"processed_{stem}.gpkg")
+        self.logger.info(f"Processing file {stitched} with {len(host['table_conf'])} features.")
+        _write_processed(host, processed, epsg, self.logger)
+        self.s.processed[stitched] = processed
+        self.s.images += 1
+        st = self.s.stage_s
+        st["decode"] = st.get("decode", 0.0) + data["decode_s"]
+        st["device"] = st.get("device", 0.0) + (t1 - t0)
+        st["write"] = st.get("write", 0.0) + (time.time() - t1)
+        return True
+
+
+def _write_predictions_json(output_path, stem, fp, tiles, det, tables, params, dev):
+    """the per-tile ``Prediction_*.json`` wire format (prediction.py:253-263), kept intermediates only"""
+    t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else a
+    boxes, probs, inst_tile, tile_dims = t(det.boxes_net), t(det.probs), t(det.inst_tile), t(det.tile_dims)
+    bpx, win, nwords = ops.paste_plan(boxes, inst_tile, tile_dims)
+    woff = ops.exclusive_offsets(nwords)
+    bits = ops.paste_threshold_pack(bpx, win, woff, probs, params.mask_threshold)
+    rings = ops.trace_rings(bits, win, woff, inst_tile, tables.tile_tf)
+    _write_tile_predictions(os.path.join(output_path, stem), fp, tiles, rings, host(det.inst_tile), host(det.scores))
+
+
 def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10, exclude_vars=None,
                      stitched_path=None):
     """detection.py:62-132 + helpers.process_and_stitch_predictions (helpers.py:556-600) in one
@@ -259,12 +363,26 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
 
     total = len(images_paths)
     done = []
+    session = config.get("_session")
+    # the fast path (see _Session) applies to a single-model run whose crown layers go straight to
+    # post-processing; with two models the fusion sits between the stages
+    fast = session is not None and exclude_vars is None and \
+        os.path.abspath(stitched_path) == os.path.abspath(os.path.join(config["output_directory"], "geojson_predictions"))
+    if fast:
+        fast_ctx = _FastPath(config, session, dev, params, predictor, stitched_path, output_path, logger)
+        fast_ctx.prefetch(images_paths[0], tiles_path)
     for i, fp in enumerate(images_paths):
         cur, prev = int(100 * (i + 1) / total), int(100 * i / total)
         if logger and ((cur // 5) != (prev // 5) or cur == 100 or i == 0):
             logger.info(f"Predicting file {i + 1}/{total} ({cur}%)")
         try:
             stem = Path(fp).stem
+            if fast:
+                nxt = images_paths[i + 1] if i + 1 < total else None
+                if fast_ctx.run(fp, tiles_path, nxt):
+                    done.append(fp)
+                    continue
+                session.fallback_images += 1
             tile_json = os.path.join(tiles_path, stem + ".json")
             with open(tile_json) as f:
                 tiles = json.load(f)
@@ -284,12 +402,7 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
                                                           t(det.inst_tile), t(det.tile_dims))
             host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else a
             if config.get("keep_intermediate", False) and len(det.scores):
-                bpx, win, nwords = ops.paste_plan(boxes, inst_tile, tile_dims)
-                woff = ops.exclusive_offsets(nwords)
-                bits = ops.paste_threshold_pack(bpx, win, woff, probs, params.mask_threshold)
-                rings = ops.trace_rings(bits, win, woff, inst_tile, tables.tile_tf)
-                _write_tile_predictions(os.path.join(output_path, stem), fp, tiles, rings, host(det.inst_tile),
-                                        host(det.scores))
+                _write_predictions_json(output_path, stem, fp, tiles, det, tables, params, dev)
             table = pipeline.predict_stage(boxes, scores, probs, inst_tile, tile_dims, tables.tile_tf,
                                            tables.tile_boxes, params)
             gpkg.write_layer(os.path.join(stitched_path, stem + ".gpkg"), stem, table.verts.cpu().numpy(),

@@ -223,3 +223,20 @@ def make_scene(seed=1234, size_px=10000, px=0.2, ndsm_px=1.0, density_per_km2=25
     rgbi = make_rgbi(field, px, seed) if with_rasters else None
     ndsm = make_ndsm(field, ndsm_px, seed) if with_rasters else None
     return Scene(stem, tf, px, rgbi, ndsm, image_transform(left, top, ndsm_px), field, tiles, det)
+
+
+def config1_scene(ndsm_npz=None, seed=31):
+    """BASELINE config 1: the reference's example tile.  The bundled ``data/nDSM/324125317.tif`` (1000 x 1000
+    float32, 1 m, top-left 412000 / 5318000; a lossless copy of its pixels is committed as
+    tests/golden/ndsm_324125317.npz) plus a SYNTHETIC 5000 x 5000 RGBI companion at 0.2 m (the bundled RGB is
+    absent from the reference: .MISSING_LARGE_BLOBS) and ROI-head outputs replayed from seeded fixtures."""
+    import os
+    if ndsm_npz is None:
+        ndsm_npz = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                "ndsm_324125317.npz")
+    ndsm = np.load(ndsm_npz)["ndsm"]
+    left, top = 412000.0, 5318000.0
+    sc = make_scene(seed=seed, size_px=5000, px=0.2, ndsm_px=1.0, density_per_km2=2500.0, stem="324125317", left=left,
+                    bottom=top - 1000.0)
+    sc.ndsm = ndsm
+    return sc
