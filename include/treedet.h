@@ -200,15 +200,21 @@ int td_select_head(const double* conf, const double* area, int n, const long lon
 /* ---- P10: forest-outline predicates (two-model fusion, tile flags) -----------------------------
  * Replaces the GEOS predicates of fuse_predictions (TreeDetection/helpers.py:795-811) and of
  * tile_single_file (TreeDetection/preprocessing.py:67-96).  a_*: query rings (crowns or tile
- * boxes); f_*: forest polygons, one closed ring each (no holes); f_bounds (n_f,4) f64;
- * a_filter (n_a,4) f64 or null: pick candidate polygons by strict bbox overlap with this box
- * (the un-buffered tile box) instead of the ring's own bounds.
+ * boxes); f_verts / f_off: forest RINGS; f_poly_off (n_poly + 1) i64 groups them into polygons
+ * (first ring = shell, the others = holes; null: every ring is a polygon without holes);
+ * f_bounds (n_poly,4) f64 = bounds of each polygon's shell; a_filter (n_a,4) f64 or null: pick
+ * candidate polygons by strict bbox overlap with this box (the un-buffered tile box) instead of the
+ * ring's own bounds.
  * out_intersects / out_within (n_a) u8: 1 = ring intersects / lies within the union of the
- * forest polygons, 0 = not, 2 = capacity exceeded (> 128 overlapping polygons or > 62
- * crossings on one edge).                                                                  */
+ * forest polygons, 0 = not; out_within 2 = more than 62 crossings on one edge of the query.  */
 int td_forest_predicates(const double* a_verts, const long long* a_off, int n_a, const double* f_verts,
-                         const long long* f_off, const double* f_bounds, int n_f, const double* a_filter,
-                         unsigned char* out_intersects, unsigned char* out_within, void* stream);
+                         const long long* f_off, const long long* f_poly_off, const double* f_bounds, int n_poly,
+                         const double* a_filter, unsigned char* out_intersects, unsigned char* out_within,
+                         void* stream);
+
+/*   out (n) u8 = ring r is a valid polygon shell (simple closed ring): the `is_valid` test that selects the
+ *   geometries fuse_predictions repairs with buffer(0) / make_valid (TreeDetection/helpers.py:816-821)   */
+int td_ring_is_simple(const double* verts, const long long* ring_off, int n_rings, unsigned char* out, void* stream);
 
 /* ---- Device-side bookkeeping of the sync-free chain ----------------------------------------------
  * The reference sizes every intermediate through the host (len(), .get(), Python lists, e.g.

@@ -901,24 +901,68 @@ def _split_params(a0, a1, q1, q2):
             ((q2[0] - a0[0]) * dx + (q2[1] - a0[1]) * dy) / len2]
 
 
+def _as_polygon(F):
+    """a forest polygon is a list of rings [shell, hole, ...]; a bare ring is a polygon without holes"""
+    if len(F) and isinstance(F[0][0], (int, float, np.floating, np.integer)):
+        return [F]
+    return F
+
+
+def locate_in_polygon(p, poly):
+    """1 interior, 0 boundary (shell or hole), -1 exterior (outside the shell or strictly inside a hole)."""
+    s = locate_in_ring(p, poly[0])
+    if s <= 0:
+        return s
+    for h in poly[1:]:
+        k = locate_in_ring(p, h)
+        if k == 1:
+            return -1
+        if k == 0:
+            return 0
+    return 1
+
+
+def ring_intersects_polygon(A, poly):
+    """GEOS ``intersects`` of the areal ring A with a polygon with holes (closed sets, touching counts)."""
+    for R in poly:
+        for i in range(len(A) - 1):
+            for j in range(len(R) - 1):
+                if segments_touch(A[i], A[i + 1], R[j], R[j + 1]):
+                    return True
+    if len(A) and locate_in_polygon(A[0], poly) >= 0:
+        return True
+    if len(poly[0]) and locate_in_ring(poly[0][0], A) >= 0:
+        return True
+    return False
+
+
 def ring_within_union(A, forest):
+    """GEOS ``within`` against the union of the forest polygons without building the union: every piece of A's
+    boundary (edges split at their crossings with shells and holes) has its midpoint in some closed polygon,
+    and no hole has a vertex strictly inside A."""
+    forest = [_as_polygon(F) for F in forest]
     if len(A) < 2 or not forest:
         return False
     for i in range(len(A) - 1):
         a0, a1 = A[i], A[i + 1]
         ts = [0.0, 1.0]
-        for F in forest:
-            for j in range(len(F) - 1):
-                for t in _split_params(a0, a1, F[j], F[j + 1]):
-                    if 0.0 < t < 1.0:
-                        ts.append(t)
+        for P in forest:
+            for R in P:
+                for j in range(len(R) - 1):
+                    for t in _split_params(a0, a1, R[j], R[j + 1]):
+                        if 0.0 < t < 1.0:
+                            ts.append(t)
         ts.sort()
         for k in range(len(ts) - 1):
             if not ts[k + 1] > ts[k]:
                 continue
             tm = (ts[k] + ts[k + 1]) / 2.0
             m = (a0[0] + (a1[0] - a0[0]) * tm, a0[1] + (a1[1] - a0[1]) * tm)
-            if not any(locate_in_ring(m, F) >= 0 for F in forest):
+            if not any(locate_in_polygon(m, P) >= 0 for P in forest):
+                return False
+    for P in forest:
+        for h in P[1:]:
+            if any(locate_in_ring(v, A) == 1 for v in h[:-1]):
                 return False
     return True
 
@@ -929,14 +973,15 @@ def _bounds(ring):
 
 
 def forest_predicates(rings, forest):
-    """(intersects, within) of every ring against the union of the forest rings; forest
-    polygons are pre-filtered by bounding-box overlap exactly as the kernel does."""
-    fb = [_bounds(F) for F in forest]
+    """(intersects, within) of every ring against the union of the forest polygons (rings or [shell, holes...]
+    lists); polygons are pre-filtered by bounding-box overlap of their shells exactly as the kernel does."""
+    forest = [_as_polygon(F) for F in forest]
+    fb = [_bounds(P[0]) for P in forest]
     inter, within = [], []
     for A in rings:
         ab = _bounds(A)
-        cand = [F for F, b in zip(forest, fb) if not (ab[0] > b[2] or ab[2] < b[0] or ab[1] > b[3] or ab[3] < b[1])]
-        hit = any(ring_intersects_ring(A, F) for F in cand)
+        cand = [P for P, b in zip(forest, fb) if not (ab[0] > b[2] or ab[2] < b[0] or ab[1] > b[3] or ab[3] < b[1])]
+        hit = any(ring_intersects_polygon(A, P) for P in cand)
         inter.append(hit)
         within.append(bool(hit and ring_within_union(A, cand)))
     return np.array(inter), np.array(within)
@@ -946,15 +991,17 @@ def tile_flags(tile_bounds, buffered_box_ring, forest):
     """preprocessing.py:67-96 for one tile: (only_forest, only_urban).  ``tile_bounds`` =
     un-buffered tile box (bbox prefilter, strict inequalities), ``buffered_box_ring`` = the
     buffered tile box as a ring (the geometry tests)."""
+    forest = [_as_polygon(F) for F in forest]
     minx, miny, maxx, maxy = tile_bounds
-    cand = [F for F in forest
-            if (_bounds(F)[2] > minx and _bounds(F)[0] < maxx and _bounds(F)[3] > miny and _bounds(F)[1] < maxy)]
+    cand = [P for P in forest
+            if (_bounds(P[0])[2] > minx and _bounds(P[0])[0] < maxx and _bounds(P[0])[3] > miny and
+                _bounds(P[0])[1] < maxy)]
     if not cand:
         return False, True
-    hit = [F for F in cand if ring_intersects_ring(buffered_box_ring, F)]
+    hit = [P for P in cand if ring_intersects_polygon(buffered_box_ring, P)]
     if not hit:
         return False, True
-    return bool(ring_within_union(buffered_box_ring, hit)), False
+    return bool(ring_within_union(buffered_box_ring, cand)), False
 
 
 def fuse(urban, forest_crowns, forest):

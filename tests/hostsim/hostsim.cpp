@@ -175,20 +175,24 @@ int hs_interior_intersection(const double* p) {
 #endif
 
 #ifdef HS_HAVE_FOREST
-// query rings vs forest rings (ragged, closed); all candidates = every forest ring whose
-// bounding box overlaps (as the kernel does).  out: intersects / within per query ring.
+// query rings vs forest polygons (rings grouped by poly_off: first ring = shell, others = holes; poly_off may be
+// null: every ring is a polygon); candidates = every polygon whose shell bounds overlap, as the kernel does.
 void hs_forest_predicates(const double* a_xy, const long long* a_off, int n_a, const double* f_xy,
-                          const long long* f_off, int n_f, unsigned char* inter, unsigned char* within) {
+                          const long long* f_off, const long long* poly_off, int n_poly, unsigned char* inter,
+                          unsigned char* within) {
   const td::P2* AV = reinterpret_cast<const td::P2*>(a_xy);
-  const td::P2* FV = reinterpret_cast<const td::P2*>(f_xy);
-  std::vector<td::Box2> fb(n_f);
-  for (int k = 0; k < n_f; ++k) {
+  td::ForestSet S;
+  S.fverts = reinterpret_cast<const td::P2*>(f_xy); S.foff = f_off; S.poly_off = poly_off;
+  std::vector<double> fb(4 * (size_t)n_poly);
+  for (int k = 0; k < n_poly; ++k) {
     td::Box2 b = {1e300, 1e300, -1e300, -1e300};
-    for (long long v = f_off[k]; v < f_off[k + 1]; ++v) {
-      b.minx = std::fmin(b.minx, FV[v].x); b.maxx = std::fmax(b.maxx, FV[v].x);
-      b.miny = std::fmin(b.miny, FV[v].y); b.maxy = std::fmax(b.maxy, FV[v].y);
+    const long long r = S.ring0(k);
+    for (int v = 0; v < S.ring_len(r); ++v) {
+      const td::P2 q = S.ring(r)[v];
+      b.minx = std::fmin(b.minx, q.x); b.maxx = std::fmax(b.maxx, q.x);
+      b.miny = std::fmin(b.miny, q.y); b.maxy = std::fmax(b.maxy, q.y);
     }
-    fb[k] = b;
+    fb[4 * k] = b.minx; fb[4 * k + 1] = b.miny; fb[4 * k + 2] = b.maxx; fb[4 * k + 3] = b.maxy;
   }
   for (int r = 0; r < n_a; ++r) {
     const td::P2* A = AV + a_off[r];
@@ -198,14 +202,12 @@ void hs_forest_predicates(const double* a_xy, const long long* a_off, int n_a, c
       ab.minx = std::fmin(ab.minx, A[k].x); ab.maxx = std::fmax(ab.maxx, A[k].x);
       ab.miny = std::fmin(ab.miny, A[k].y); ab.maxy = std::fmax(ab.maxy, A[k].y);
     }
-    std::vector<int> cand;
-    for (int k = 0; k < n_f; ++k)
-      if (td::boxes_overlap(ab, fb[k])) cand.push_back(k);
+    td::CandSet C;
+    C.list = nullptr; C.n = 0; C.bounds = fb.data(); C.q = ab; C.n_poly = n_poly; C.strict = false;
     bool hit = false;
-    for (size_t c = 0; c < cand.size() && !hit; ++c)
-      hit = td::ring_intersects_ring(A, na, FV + f_off[cand[c]], (int)(f_off[cand[c] + 1] - f_off[cand[c]]));
+    for (int c = C.first(); c >= 0 && !hit; c = C.next(c)) hit = td::ring_intersects_polygon(A, na, S, C.poly(c));
     inter[r] = hit ? 1 : 0;
-    within[r] = (hit ? (unsigned char)td::ring_within_union(A, na, FV, f_off, cand.data(), (int)cand.size()) : 0);
+    within[r] = hit ? (unsigned char)td::ring_within_union(A, na, S, C) : 0;
   }
 }
 #endif

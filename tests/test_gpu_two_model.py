@@ -1,0 +1,212 @@
+"""BASELINE config 3 through the reference's API on the B200: two models + a forest outline with holes
+(ESRI shapefile) -> tile flags (preprocess_files), per-model exclusion and stitching (predict_tiles: two
+predict_on_model passes, fuse_predictions), post-processing -- every artefact against the oracle composition
+of the same steps (preprocessing.py:67-96, prediction.py:79-93, helpers.py:703-834, postprocessing.py)."""
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import port
+from treedetection_b200 import detection, fusion, geo, geotiff, gpkg, ops, predictor, synth
+
+pytestmark = pytest.mark.gpu
+PX = 0.2
+
+
+def write_shapefile(path, polygons):
+    """minimal .shp (type 5): one record per polygon, shell clockwise, holes counter-clockwise"""
+    def area2(r):
+        r = np.asarray(r)
+        return float(np.sum(r[:-1, 0] * r[1:, 1] - r[1:, 0] * r[:-1, 1]))
+    recs = []
+    for k, poly in enumerate(polygons):
+        rings = []
+        for j, r in enumerate(poly):
+            r = np.asarray(r, dtype=np.float64)
+            cw = area2(r) < 0
+            if (j == 0) != cw:
+                r = r[::-1]
+            rings.append(r)
+        pts = np.concatenate(rings)
+        parts = np.cumsum([0] + [len(r) for r in rings[:-1]])
+        body = struct.pack("<i4d2i", 5, pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max(), len(rings), len(pts))
+        body += struct.pack("<" + "i" * len(rings), *[int(p) for p in parts]) + pts.astype("<f8").tobytes()
+        recs.append(struct.pack(">ii", k + 1, len(body) // 2) + body)
+    data = b"".join(recs)
+    head = struct.pack(">i5ii", 9994, 0, 0, 0, 0, 0, (100 + len(data)) // 2) + struct.pack("<ii", 1000, 5) + b"\x00" * 64
+    with open(path, "wb") as f:
+        f.write(head + data)
+
+
+def rect(x0, y0, x1, y1):
+    return [(x1, y0), (x1, y1), (x0, y1), (x0, y0), (x1, y0)]
+
+
+def convex(rng, cx, cy, r, k):
+    ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+    pts = [(float(cx + r * np.cos(a)), float(cy + r * np.sin(a))) for a in ang]
+    return pts + [pts[0]]
+
+
+def test_shapefile_reader_keeps_holes(tmp_path, dev):
+    polys = [[rect(0.0, 0.0, 100.0, 100.0), rect(40.0, 40.0, 60.0, 60.0), rect(10.0, 10.0, 20.0, 20.0)],
+             [rect(200.0, 0.0, 260.0, 60.0)]]
+    write_shapefile(str(tmp_path / "f.shp"), polys)
+    got = fusion.read_shapefile_polygons(str(tmp_path / "f.shp"))
+    assert [len(p) for p in got] == [3, 1]
+    crowns = [rect(45.0, 45.0, 55.0, 55.0), rect(30.0, 30.0, 70.0, 70.0), rect(60.0, 45.0, 70.0, 55.0),
+              rect(12.0, 12.0, 18.0, 18.0), rect(210.0, 10.0, 220.0, 20.0)]
+    idx = fusion.ForestIndex.from_file(str(tmp_path / "f.shp"), dev)
+    off = np.zeros(len(crowns) + 1, dtype=np.int64); off[1:] = np.cumsum([len(c) for c in crowns])
+    xy = np.array([p for c in crowns for p in c], dtype=np.float64)
+    gi, gw = idx.predicates(torch.from_numpy(xy).to(dev), torch.from_numpy(off).to(dev))
+    wi, ww = port.forest_predicates(crowns, [[[tuple(q) for q in r] for r in p] for p in got])
+    np.testing.assert_array_equal(gi.cpu().numpy().astype(bool), wi)
+    np.testing.assert_array_equal(gw.cpu().numpy().astype(bool), ww)
+    assert wi.tolist() == [False, True, True, False, True] and ww.tolist() == [False, False, True, False, True]
+
+
+class _FieldPredictor:
+    """ROI-head outputs of any tiling from one tree field; drops the tiles a model must skip (prediction.py:79-93)"""
+
+    def __init__(self, field, seed, exclude_vars=None):
+        self.field, self.seed, self.exclude_vars = field, seed, exclude_vars or []
+
+    def raw_outputs(self, stem, tiles):
+        det = synth.make_detections(self.field, tiles, PX, seed=self.seed)
+        return _exclude(det, tiles, self.exclude_vars)
+
+
+def _exclude(det, tiles, exclude_vars):
+    if not exclude_vars:
+        return det
+    ids = list(tiles.keys())
+    skip = np.array([any(bool(tiles[t].get(v, False)) for v in exclude_vars) for t in ids])
+    keep = ~skip[det.inst_tile]
+    return synth.Detections(det.boxes_net[keep], det.scores[keep], det.probs[keep], det.inst_tile[keep], det.tile_dims,
+                            det.tile_ids, det.tiles)
+
+
+def test_two_model_run_matches_oracle(tmp_path, dev, monkeypatch):
+    rng = np.random.default_rng(17)
+    left, bottom, size_m = synth.ORIGIN_X, synth.ORIGIN_Y, 300.0
+    field = synth.tree_field(91, size_m, size_m, 6000.0, left, bottom)
+    n = int(size_m / PX)
+    rgbi, ndsm = synth.make_rgbi(field, PX, 91), synth.make_ndsm(field, 1.0, 91)
+    top = bottom + size_m
+    img_dir, h_dir = tmp_path / "rgb", tmp_path / "ndsm"
+    img_dir.mkdir(); h_dir.mkdir()
+    stem = "FDOP20_000007_rgbi"
+    geotiff.write(str(img_dir / f"{stem}.tif"), rgbi, (PX, 0.0, left, 0.0, -PX, top), epsg=25832)
+    geotiff.write(str(h_dir / "nDSM_000007_1km.tif"), ndsm, (1.0, 0.0, left, 0.0, -1.0, top), epsg=25832)
+    # forest outline: a large block with two holes (one clearing swallows whole tiles), a convex patch, a strip
+    forest = [[rect(left - 10, bottom - 10, left + 170, bottom + 310), rect(left + 20, bottom + 30, left + 150, bottom + 160),
+               convex(rng, left + 90, bottom + 230, 18, 9)],
+              [convex(rng, left + 240, bottom + 80, 45, 11)],
+              [rect(left + 200, bottom + 200, left + 320, bottom + 240)]]
+    write_shapefile(str(tmp_path / "forest.shp"), forest)
+    for d in ("urban_model", "forest_model"):
+        (tmp_path / d).mkdir()
+    cfg = {
+        "image_directory": str(img_dir), "height_data_path": str(h_dir), "image_regex": "FDOP20_(\\d+)_rgbi\\.tif",
+        "height_data_regex": "nDSM_(\\d+)_1km\\.tif", "urban_model": str(tmp_path / "urban_model"),
+        "forrest_model": str(tmp_path / "forest_model"), "forrest_outline": str(tmp_path / "forest.shp"),
+        "output_directory": str(tmp_path / "output"), "tiles_path": str(tmp_path / "tiles"), "use_overlap": True,
+        "merged_path": "merged", "tile_width": 50, "tile_height": 50, "buffer": 20, "ndvi_scaling_factor": 0.2,
+        "height_scaling_factor": 1.0, "keep_intermediate": True, "device": "0",
+        "image_merged_regex": "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_rgbi\\.tif",
+        "height_data_merged_regex": "nDSM_(\\d+)(\\d+)_1km\\.tif",
+    }
+    path = tmp_path / "config.yml"
+    path.write_text(yaml.safe_dump(cfg))
+    config, _ = detection.get_config(str(path))
+    # ---- preprocess: tile flags against the oracle ----
+    detection.preprocess_files(config)
+    tiles = json.load(open(os.path.join(config["tiles_path"], stem + ".json")))
+    opolys = [[[tuple(q) for q in r] for r in p] for p in fusion.read_shapefile_polygons(str(tmp_path / "forest.shp"))]
+    n_f = n_u = 0
+    for tid, m in tiles.items():
+        parts = [int(p) for p in tid.split("_")[-5:]]
+        b = m["bounds"]
+        want = port.tile_flags((float(parts[0]), float(parts[1]), float(parts[0] + 50), float(parts[1] + 50)),
+                               rect(b[0], b[1], b[2], b[3]), opolys)
+        assert (m["only_forest"], m["only_urban"]) == want, tid
+        n_f += m["only_forest"]; n_u += m["only_urban"]
+    assert n_f > 0 and n_u > 0 and n_f + n_u < len(tiles)          # forest-only, urban-only (the clearing) and mixed tiles
+    # ---- predict: the two models are two predictor plugs fed from the same field with different seeds ----
+    plugs = {config["urban_model"]: _FieldPredictor(field, 5, ["only_forest"]),
+             config["forrest_model"]: _FieldPredictor(field, 6, ["only_urban"])}
+    real = detection._predict_on_model
+
+    def with_plug(config_, model_path, *a, **k):
+        config_["predictor"] = plugs[model_path]
+        try:
+            return real(config_, model_path, *a, **k)
+        finally:
+            config_.pop("predictor", None)
+    monkeypatch.setattr(detection, "_predict_on_model", with_plug)
+    detection.predict_tiles(config)
+    out = config["output_directory"]
+    want_rings = {}
+    for name, seed, excl in (("urban", 5, ["only_forest"]), ("forrest", 6, ["only_urban"])):
+        det = _exclude(synth.make_detections(field, tiles, PX, seed=seed), tiles, excl)
+        rings, conf = port.predict_stage(det, tiles)
+        v, o, cols, _ = gpkg.read_layer(os.path.join(out, f"{name}_geojson", stem + ".gpkg"))
+        assert len(o) - 1 == len(rings) > 50
+        np.testing.assert_array_equal(v, np.array([q for r in rings for q in r]).reshape(-1, 2))
+        np.testing.assert_array_equal(np.array(cols["Confidence_score"]), np.array(conf))
+        want_rings[name] = (rings, conf)
+    (ur, uc), (fr, fc) = want_rings["urban"], want_rings["forrest"]
+    keep_f, keep_u = port.fuse(ur, fr, opolys)
+    fused = [fr[i] for i in keep_f] + [ur[i] for i in keep_u]
+    fconf = [fc[i] for i in keep_f] + [uc[i] for i in keep_u]
+    v, o, cols, _ = gpkg.read_layer(os.path.join(out, "geojson_predictions", stem + ".gpkg"))
+    assert len(o) - 1 == len(fused) and 0 < len(keep_f) < len(fr) and 0 < len(keep_u) < len(ur)
+    np.testing.assert_array_equal(v, np.array([q for r in fused for q in r]).reshape(-1, 2))
+    np.testing.assert_array_equal(np.array(cols["Confidence_score"]), np.array(fconf))
+    # the reference hands only INVALID geometries to buffer(0) / make_valid (helpers.py:816-821): none here, so
+    # the fused layer's vertices are those of the inputs
+    assert all(fusion.ring_is_simple(r) for r in fused)
+    # ---- post-processing of the fused layer ----
+    detection.postprocess_files(config)
+    H, W = rgbi.shape[1:]
+    oh, ow = int(H * 0.2), int(W * 0.2)
+    dec = np.stack([port.decimate_bilinear(rgbi[b], oh, ow) for b in (0, 0, 0, 3)])
+    ndvi = port.ndvi_from_rgbi(dec).astype(np.float32)
+    tf = (PX, 0.0, left, 0.0, -PX, top)
+    htf = (1.0, 0.0, left, 0.0, -1.0, top)
+    want, _ = port.post_process(fused, fconf, ndvi, geo.compose(tf, geo.scale(W / ow, H / oh)),
+                                tuple(geo.raster_bounds(tf, W, H)), ndsm, htf,
+                                tuple(geo.raster_bounds(htf, ndsm.shape[1], ndsm.shape[0])), PX, PX, config)
+    v, o, cols, _ = gpkg.read_layer(os.path.join(out, stem + ".gpkg"))
+    assert cols["poly_id"] == [w["poly_id"] for w in want] and len(want) > 30
+    np.testing.assert_array_equal(np.array(cols["Area"]), np.array([w["Area"] for w in want]))
+    np.testing.assert_array_equal(np.array(cols["TreeHeight"], dtype=np.float32),
+                                  np.array([w["TreeHeight"] for w in want], dtype=np.float32))
+    np.testing.assert_array_equal(v, np.array([q for w in want for q in w["coords"]]).reshape(-1, 2))
+
+
+def test_ring_is_simple(dev):
+    sq = [(0.0, 0.0), (2.0, 0.0), (2.0, 2.0), (0.0, 2.0), (0.0, 0.0)]
+    bow = [(0.0, 0.0), (2.0, 2.0), (2.0, 0.0), (0.0, 2.0), (0.0, 0.0)]                       # self-crossing
+    pinch = [(0.0, 0.0), (1.0, 1.0), (2.0, 0.0), (2.0, 2.0), (1.0, 1.0), (0.0, 2.0), (0.0, 0.0)]  # touches itself
+    spike = [(0.0, 0.0), (2.0, 0.0), (1.0, 0.0), (1.0, 2.0), (0.0, 0.0)]                     # folds back
+    assert fusion.ring_is_simple(sq) and not fusion.ring_is_simple(bow)
+    assert not fusion.ring_is_simple(pinch) and not fusion.ring_is_simple(spike)
+    rng = np.random.default_rng(4)
+    rings = [sq, bow, pinch, spike]
+    for _ in range(300):                      # random star polygons: many cross themselves
+        k = int(rng.integers(4, 14))
+        pts = [(float(x), float(y)) for x, y in rng.integers(0, 9, (k, 2))]
+        rings.append(pts + [pts[0]])
+    off = np.zeros(len(rings) + 1, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in rings])
+    xy = np.array([p for r in rings for p in r], dtype=np.float64)
+    got = ops.rings_are_simple(torch.from_numpy(xy).to(dev), torch.from_numpy(off).to(dev)).cpu().numpy().astype(bool)
+    want = np.array([fusion.ring_is_simple(r) for r in rings])
+    np.testing.assert_array_equal(got, want)
+    assert want.any() and (~want).any()

@@ -15,12 +15,22 @@ def ragged(rings):
     return np.ascontiguousarray(xy), off
 
 
+def flatten(forest):
+    """forest polygons (bare rings or [shell, hole, ...]) -> (rings, poly_off)"""
+    polys = [port._as_polygon(F) for F in forest]
+    rings = [r for p in polys for r in p]
+    poly_off = np.zeros(len(polys) + 1, dtype=np.int64)
+    poly_off[1:] = np.cumsum([len(p) for p in polys])
+    return rings, poly_off
+
+
 def ours(rings, forest):
     lib = hostsim.load()
-    a, ao = ragged(rings); f, fo = ragged(forest)
+    frings, poly_off = flatten(forest)
+    a, ao = ragged(rings); f, fo = ragged(frings)
     inter = np.zeros(len(rings), dtype=np.uint8); within = np.zeros(len(rings), dtype=np.uint8)
     vp = lambda x: x.ctypes.data_as(C.c_void_p)
-    lib.hs_forest_predicates(vp(a), vp(ao), len(rings), vp(f), vp(fo), len(forest), vp(inter), vp(within))
+    lib.hs_forest_predicates(vp(a), vp(ao), len(rings), vp(f), vp(fo), vp(poly_off), len(forest), vp(inter), vp(within))
     return inter.astype(bool), within.astype(bool)
 
 
@@ -72,3 +82,43 @@ def test_touching_and_shared_edges():
     gi, gw = ours(crowns, forest)
     np.testing.assert_array_equal(gi, wi)
     np.testing.assert_array_equal(gw, ww)
+
+
+def test_polygons_with_holes():
+    """holes of the outline (helpers.py:802-807 tests against unary_union, which keeps them): a crown inside a
+    hole does not intersect the forest, a crown around a hole is not within it, a crown on the rim is both"""
+    shell, hole = rect(0.0, 0.0, 100.0, 100.0), rect(40.0, 40.0, 60.0, 60.0)
+    forest = [[shell, hole], rect(200.0, 0.0, 260.0, 60.0)]
+    crowns = [rect(45.0, 45.0, 55.0, 55.0),      # strictly inside the hole: disjoint from the forest
+              rect(30.0, 30.0, 70.0, 70.0),      # swallows the hole: intersects, not within
+              rect(35.0, 45.0, 45.0, 55.0),      # straddles the hole's rim: intersects, not within
+              rect(10.0, 10.0, 30.0, 30.0),      # solid part: within
+              rect(39.0, 39.0, 61.0, 61.0),      # a little larger than the hole: intersects, not within
+              rect(60.0, 45.0, 70.0, 55.0),      # touches the hole from the solid side: within
+              rect(210.0, 10.0, 220.0, 20.0)]    # the second polygon (no holes): within
+    wi, ww = port.forest_predicates(crowns, forest)
+    assert wi.tolist() == [False, True, True, True, True, True, True]
+    assert ww.tolist() == [False, False, False, True, False, True, True]
+    gi, gw = ours(crowns, forest)
+    np.testing.assert_array_equal(gi, wi)
+    np.testing.assert_array_equal(gw, ww)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_crowns_against_forest_with_holes(seed):
+    rng = np.random.default_rng(100 + seed)
+    forest = []
+    for F in make_forest(rng, 18, 600.0):
+        xs = [p[0] for p in F]; ys = [p[1] for p in F]
+        cx, cy = (min(xs) + max(xs)) / 2, (min(ys) + max(ys)) / 2
+        r = min(max(xs) - min(xs), max(ys) - min(ys)) / 6
+        # a hole around the centre (convex shells: the centre region is inside), orientation opposite to the shell
+        forest.append([F, convex(rng, cx, cy, r, 7)[::-1]] if rng.uniform() < 0.7 else F)
+    crowns = [convex(rng, 412000 + rng.uniform(-20, 620), 5318000 + rng.uniform(-20, 620), rng.uniform(1.5, 12), 9)
+              for _ in range(500)]
+    wi, ww = port.forest_predicates(crowns, forest)
+    gi, gw = ours(crowns, forest)
+    np.testing.assert_array_equal(gi, wi)
+    np.testing.assert_array_equal(gw, ww)
+    plain_i, plain_w = port.forest_predicates(crowns, [port._as_polygon(F)[0] for F in forest])
+    assert (plain_w & ~ww).any()        # the holes matter (test_polygons_with_holes covers `intersects`)

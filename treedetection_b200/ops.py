@@ -528,23 +528,37 @@ def seam_crop(a, b, axis, strip_w, strip_h, out=None):
 # ----------------------------------------------------------------------------
 # P10  forest-outline predicates
 # ----------------------------------------------------------------------------
-def forest_predicates(a_verts, a_off, f_verts, f_off, f_bounds=None, a_filter=None):
-    """Query rings (crowns / tile boxes) against the union of the forest polygons.
-    Returns (intersects u8 (Na,), within u8 (Na,)); raises when the kernel's capacity
-    limits were exceeded for some query."""
+def forest_predicates(a_verts, a_off, f_verts, f_off, f_bounds=None, a_filter=None, f_poly_off=None):
+    """Query rings (crowns / tile boxes) against the union of the forest polygons.  ``f_poly_off`` (n_poly + 1,)
+    i64 groups the forest rings into polygons (first ring = shell, the others = holes); without it every ring
+    is a polygon.  ``f_bounds`` (n_poly, 4): bounds of the shells.  Returns (intersects u8 (Na,), within u8
+    (Na,)); raises when an edge of a query crosses more forest edges than the kernel's split buffer holds."""
     na = a_off.shape[0] - 1
-    nf = f_off.shape[0] - 1
+    n_rings = f_off.shape[0] - 1
+    n_poly = n_rings if f_poly_off is None else f_poly_off.shape[0] - 1
     dev = a_verts.device
-    if f_bounds is None and nf > 0:
-        f_bounds = simplify_rings(f_verts, f_off, 0.0, want_bounds=True)["bounds"]
+    if f_bounds is None and n_poly > 0:
+        rb = simplify_rings(f_verts, f_off, 0.0, want_bounds=True)["bounds"]
+        f_bounds = rb if f_poly_off is None else rb[f_poly_off[:-1]].contiguous()
+    if f_poly_off is not None:
+        _chk(f_poly_off, torch.int64, "f_poly_off")
     inter = torch.zeros((na,), dtype=torch.uint8, device=dev)
     within = torch.zeros((na,), dtype=torch.uint8, device=dev)
-    _lib.call("td_forest_predicates", _ptr(a_verts), _ptr(a_off), na, _ptr(f_verts) if nf else None,
-              _ptr(f_off) if nf else None, _ptr(f_bounds) if nf else None, nf, _ptr(a_filter), _ptr(inter), _ptr(within),
-              _stream())
-    if na and int(torch.maximum(inter.max(), within.max()).item()) > 1:
-        raise _lib.TreedetError("td_forest_predicates: forest outline too dense for the kernel's per-query limits")
+    _lib.call("td_forest_predicates", _ptr(a_verts), _ptr(a_off), na, _ptr(f_verts) if n_poly else None,
+              _ptr(f_off) if n_poly else None, _ptr(f_poly_off) if (n_poly and f_poly_off is not None) else None,
+              _ptr(f_bounds) if n_poly else None, n_poly, _ptr(a_filter), _ptr(inter), _ptr(within), _stream())
+    if na and int(within.max().item()) > 1:
+        raise _lib.TreedetError("td_forest_predicates: an edge crosses more than 62 forest edges (split buffer)")
     return inter, within
+
+
+def rings_are_simple(verts, ring_off):
+    """u8 (R,): 1 where the ring is a valid polygon shell (GEOS ``is_valid`` of a single-ring polygon)."""
+    n = ring_off.shape[0] - 1
+    _chk(verts, torch.float64, "verts"); _chk(ring_off, torch.int64, "ring_off")
+    out = torch.empty((n,), dtype=torch.uint8, device=verts.device)
+    _lib.call("td_ring_is_simple", _ptr(verts), _ptr(ring_off), n, _ptr(out), _stream())
+    return out
 
 
 # ----------------------------------------------------------------------------
