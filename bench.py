@@ -236,6 +236,9 @@ def e2e_files(sc, n_images, label):
             "output_directory": os.path.join(root, "output"), "tiles_path": os.path.join(root, "tiles"),
             "use_overlap": True, "merged_path": "merged", "tile_width": 50, "tile_height": 50, "buffer": 20,
             "ndvi_scaling_factor": 0.2, "height_scaling_factor": 1.0, "keep_intermediate": False, "device": "0",
+            # example/config.yml
+            "confidence_threshold": 0.3, "containment_threshold": 0.75, "height_threshold": 3, "ndvi_mean_threshold": 0.1,
+            "ndvi_var_threshold": 0.1, "iou_threshold": 0.6, "area_threshold": 1,
             "image_merged_regex": "FDOP20_(\\d+)_(\\d+)_(\\d+)_(\\d+)_rgbi\\.tif",
             "height_data_merged_regex": "nDSM_(\\d+)(\\d+)_1km\\.tif",
         }
@@ -250,12 +253,26 @@ def e2e_files(sc, n_images, label):
         stats = config.get("_last_session_stats", {})
         outs = [f for f in os.listdir(config["output_directory"]) if f.endswith(".gpkg")]
         from treedetection_b200 import gpkg
-        n_crowns = [len(gpkg.read_layer(os.path.join(config["output_directory"], f))[1]) - 1 for f in sorted(outs)]
+        layers = [gpkg.read_layer(os.path.join(config["output_directory"], f)) for f in sorted(outs)]
+        n_crowns = [len(l[1]) - 1 for l in layers]
+        parity = None
+        from treedetection_b200 import golden_check
+        if golden_check.golden_matches_workload(W, 1234, 2500) and H == W and npx in (0.2, 1.0):
+            # the files on disk against the CPU oracle's golden of this scene (ids, areas, heights, vertices)
+            for v, o, cols, _ in layers:
+                golden_check.check_layer({"poly_id": np.array([int(x) for x in cols["poly_id"]]), "area": np.array(cols["Area"]),
+                                          "tree_height": np.array(cols["TreeHeight"], dtype=np.float32),
+                                          "centroid": np.array([[json.loads(c)["x"], json.loads(c)["y"]] for c in cols["Centroid"]],
+                                                               dtype=np.float32),
+                                          "is_contained": np.array([c == "True" for c in cols["is_contained"]]),
+                                          "num_contained": np.array(cols["num_contained"], dtype=np.int32),
+                                          "ring_off": o, "verts": v}, "split" if npx == 0.2 else "combined")
+            parity = f"all {len(layers)} output layers equal the CPU oracle's golden"
         area = n_images * H * W * px * px / 1e6
         return {"workload": label, "images": n_images, "value": area / wall, "unit": UNIT, "wall_s": wall,
                 "stage_s": {k: round(v, 3) for k, v in stats.get("stage_s", {}).items()},
                 "fast_path_images": stats.get("images"), "fallback_images": stats.get("fallback_images"),
-                "crowns_per_image": n_crowns,
+                "crowns_per_image": n_crowns, "parity": parity,
                 "input_bytes": int(n_images * (sc.rgbi.nbytes + sc.ndsm.nbytes)),
                 "note": f"GeoTIFFs uncompressed on {'tmpfs (/dev/shm)' if base else 'the default temp dir'} (written in "
                         f"{write_s:.1f} s, not timed); timed: get tiles -> read + decode rasters and fixtures -> H2D -> P1 "

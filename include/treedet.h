@@ -162,6 +162,16 @@ int td_bbox_nms_ordered_dyn(const double* bounds, const double* conf, const doub
                             const long long* n_dev, double iou_threshold, double area_threshold, long long nbr_cap,
                             long long* flag, unsigned char* removed, void* stream);
 
+/*   Opt-in mask-IoU cleaner on the packed rasters of P2 (``iou_mode: mask``): the rule of clean_crowns
+ *   (TreeDetection/helpers.py:602-701, never called by the reference) with the PIXEL IoU
+ *   popcount(a & b) / popcount(a | b) of the 1-bit crown rasters on the image's pixel grid.
+ *   win (N,4) i32 [x0,y0,w,h] in tile pixels, tile_org (T,2) i32 [col_off,row_off] of each tile window,
+ *   scores (N) f32 -> keep (N) u8, match (N) i32 (best-confidence crown with IoU > iou_thr, -1: none),
+ *   best_iou (N) f32 nullable                                                                      */
+int td_mask_iou_clean(const uint32_t* bits, const long long* word_off, const int* win, const int* tile_org,
+                      const int* inst_tile, const float* scores, int n, float iou_thr, float confidence,
+                      unsigned char* keep, int* match, float* best_iou, void* stream);
+
 /* ---- P7: per-crown raster statistics, centroids ----------------------------------------------
  * Replaces get_metadata_within_polygon (TreeDetection/postprocessing.py:221-347; mode 0),
  * get_height_within_polygon (:25-115; mode 1), get_ndvi_within_polygon (:117-219; mode 2),

@@ -564,6 +564,45 @@ def crown_stats_ndvi_windowed(px32, py32, ndvi32, transform):
 
 
 # ============================================================================
+# opt-in mask-IoU cleaner (the rule of clean_crowns, helpers.py:602-701, on pixel masks)
+# ============================================================================
+
+
+def mask_iou_clean(masks, origins, scores, iou_threshold=0.7, confidence=0.2):
+    """``clean_crowns`` (helpers.py:602-701; detectree2's, never called by the reference) restated with the
+    PIXEL IoU of boolean masks: for every crown, among the crowns whose IoU with it exceeds the threshold
+    (itself included) take the one with the highest confidence (first of equals, as ``nlargest(1, field)``);
+    the crown survives only if that one coincides with it (IoU == 1) and its confidence exceeds ``confidence``.
+    masks: list of 2-D bool arrays, origins: their (x0, y0) on the image's pixel grid.  Returns (keep, match)."""
+    n = len(masks)
+    area = [int(m.sum()) for m in masks]
+    keep = np.zeros(n, dtype=bool)
+    match = np.full(n, -1, dtype=np.int64)
+    boxes = [(int(o[0]), int(o[1]), int(o[0]) + m.shape[1], int(o[1]) + m.shape[0]) for m, o in zip(masks, origins)]
+    for i in range(n):
+        if area[i] == 0:
+            continue
+        best, best_conf, best_eq = -1, 0.0, False
+        for j in range(n):
+            x0, y0 = max(boxes[i][0], boxes[j][0]), max(boxes[i][1], boxes[j][1])
+            x1, y1 = min(boxes[i][2], boxes[j][2]), min(boxes[i][3], boxes[j][3])
+            if x0 >= x1 or y0 >= y1 or area[j] == 0:
+                continue
+            a = masks[i][y0 - boxes[i][1]:y1 - boxes[i][1], x0 - boxes[i][0]:x1 - boxes[i][0]]
+            b = masks[j][y0 - boxes[j][1]:y1 - boxes[j][1], x0 - boxes[j][0]:x1 - boxes[j][0]]
+            inter = int((a & b).sum())
+            uni = area[i] + area[j] - inter
+            if not np.float32(inter) / np.float32(uni) > np.float32(iou_threshold):
+                continue
+            cj = float(scores[j])
+            if best < 0 or cj > best_conf:
+                best, best_conf, best_eq = j, cj, inter == uni
+        match[i] = best
+        keep[i] = best >= 0 and best_eq and best_conf > float(np.float32(confidence))
+    return keep, match
+
+
+# ============================================================================
 # P8  containment   (postprocessing.py:408-476)
 # ============================================================================
 

@@ -177,3 +177,32 @@ def test_process_files_fast_path_writes_the_same_files(tmp_path):
         for col in ca:
             assert list(ca[col]) == list(cb[col]), (name, col)
     assert any(len(a[n][1]) - 1 > 10 for n in a if n.startswith("./"))
+
+
+def test_exclude_files_remove_crowns_within_the_outline(tmp_path, dev):
+    """helpers.exclude_outlines (helpers.py:33-69): crowns of the existing processed_* layers that lie within the
+    union of an exclusion outline disappear; the others (incl. those only touching it) stay, columns intact."""
+    import torch
+    from tests.test_gpu_two_model import rect, write_shapefile
+    cfg_path, field, _ = _project(tmp_path)
+    config, _ = detection.get_config(cfg_path)
+    config["predictor"] = _FieldPredictor(field)
+    detection.process_files(config)                       # keep_intermediate: the processed_* layers stay
+    pred = os.path.join(config["output_directory"], "geojson_predictions")
+    name = "processed_FDOP20_000001_rgbi.gpkg"
+    v, o, cols, _ = gpkg.read_layer(os.path.join(pred, name))
+    rings = [[(float(x), float(y)) for x, y in v[o[i]:o[i + 1]]] for i in range(len(o) - 1)]
+    left, bottom = synth.ORIGIN_X, synth.ORIGIN_Y
+    outline = [[rect(left + 30.0, bottom + 30.0, left + 120.0, bottom + 150.0), rect(left + 60.0, bottom + 60.0, left + 90.0, bottom + 100.0)]]
+    write_shapefile(str(tmp_path / "water.shp"), outline)
+    _, within = port.forest_predicates(rings, outline)
+    assert 0 < within.sum() < len(rings)
+    config["exclude_files"] = [str(tmp_path / "water.shp"), str(tmp_path / "missing.shp")]     # a missing file is logged, not raised
+    with torch.cuda.device(dev):
+        detection.exclude_outlines(config, config["logger"])
+    v2, o2, cols2, _ = gpkg.read_layer(os.path.join(pred, name))
+    keep = np.nonzero(~within)[0]
+    assert len(o2) - 1 == len(keep) and list(cols2) == list(cols)
+    np.testing.assert_array_equal(v2, np.concatenate([v[o[k]:o[k + 1]] for k in keep]))
+    assert cols2["poly_id"] == [cols["poly_id"][k] for k in keep]
+    assert cols2["TreeHeight"] == [cols["TreeHeight"][k] for k in keep]

@@ -199,3 +199,41 @@ def test_decimate_f32(dev):
     ref = port.decimate_bilinear(band, 180, 220)
     got = ops.decimate_f32(torch.from_numpy(band).to(dev), 180, 220).cpu().numpy()
     np.testing.assert_array_equal(got, ref)
+
+
+def test_mask_iou_clean_matches_restated_clean_crowns(dev):
+    """opt-in ``iou_mode: mask``: popcount IoU over the packed P2 rasters + the rule of the reference's (uncalled)
+    clean_crowns (helpers.py:602-701) against its NumPy restatement on the same masks -- instances of overlapping
+    tiles (every tree is seen by ~3 tiles), exact duplicates, empty masks"""
+    sc = synth.make_scene(seed=13, size_px=900, px=0.2, ndsm_px=1.0, density_per_km2=6000.0, with_rasters=False)
+    d = sc.det
+    # duplicate a few instances (same mask, another confidence) and blank one out
+    dup = np.array([3, 40, 41, 200])
+    boxes = np.concatenate([d.boxes_net, d.boxes_net[dup]]); probs = np.concatenate([d.probs, d.probs[dup]])
+    inst_tile = np.concatenate([d.inst_tile, d.inst_tile[dup]])
+    scores = np.concatenate([d.scores, np.array([0.99, d.scores[40], 0.31, 0.5], np.float32)])
+    order = np.argsort(inst_tile, kind="stable")          # keep the tile-major layout
+    boxes, probs, inst_tile, scores = boxes[order], probs[order], inst_tile[order], scores[order]
+    probs = probs.copy(); probs[7] = 0.0                   # an instance whose mask is empty
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    boxes_px, win, nwords = ops.paste_plan(t(boxes), t(inst_tile), t(d.tile_dims))
+    off = ops.exclusive_offsets(nwords)
+    bits = ops.paste_threshold_pack(boxes_px, win, off, t(probs))
+    tile_org = np.array([m["window"][:2] for m in sc.tiles.values()], dtype=np.int32)
+    for thr, conf in ((0.7, 0.2), (0.3, 0.45), (0.95, 0.0)):
+        keep, match, best = ops.mask_iou_clean(bits, off, win, t(tile_org), t(inst_tile), t(scores), thr, conf)
+        # restatement on the unpacked masks
+        b, o, w = bits.cpu().numpy().view(np.uint32), off.cpu().numpy(), win.cpu().numpy()
+        masks, orgs = [], []
+        for i in range(len(scores)):
+            x0, y0, ww, hh = w[i]
+            wpr = (ww + 31) // 32
+            words = b[o[i]:o[i] + wpr * hh].reshape(hh, wpr) if ww * hh else np.zeros((0, 0), np.uint32)
+            m = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(hh, -1)[:, :ww].astype(bool) \
+                if ww * hh else np.zeros((0, 0), bool)
+            masks.append(m); orgs.append((tile_org[inst_tile[i]][0] + x0, tile_org[inst_tile[i]][1] + y0))
+        wkeep, wmatch = port.mask_iou_clean(masks, orgs, scores, thr, conf)
+        np.testing.assert_array_equal(match.cpu().numpy(), wmatch)
+        np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), wkeep)
+        assert 0 < wkeep.sum() < len(wkeep)
+    assert not wkeep[7] and wmatch[7] == -1

@@ -211,3 +211,28 @@ def test_full_chain_matches_oracle(dev):
     np.testing.assert_array_equal(f.area.cpu().numpy(), np.array([o["Area"] for o in out]))
     np.testing.assert_array_equal(f.tree_height.cpu().numpy(), np.array([o["TreeHeight"] for o in out], np.float32))
     np.testing.assert_array_equal(f.verts.cpu().numpy(), np.array([q for o in out for q in o["coords"]]).reshape(-1, 2))
+
+
+def test_predict_stage_mask_iou_mode(dev):
+    """opt-in ``iou_mode: mask``: instances dropped by the mask-IoU cleaner leave no rings, the others go through
+    P3 / P4 unchanged -- equal to the oracle's predict stage on the surviving instances"""
+    sc = synth.make_scene(seed=15, size_px=1000, px=0.2, ndsm_px=1.0, density_per_km2=6000.0, with_rasters=False)
+    p = pipeline.PipelineParams(iou_mode="mask", mask_iou_threshold=0.5, confidence_threshold_stitching=0.3)
+    dd = _dev_det(sc, dev)
+    tile_org = torch.tensor([m["window"][:2] for m in sc.tiles.values()], dtype=torch.int32, device=dev)
+    table = pipeline.predict_stage(**dd, p=p, tile_org=tile_org)
+    plain = pipeline.predict_stage(**dd, p=pipeline.PipelineParams())
+    boxes_px, win, nwords = ops.paste_plan(dd["boxes_net"], dd["inst_tile"], dd["tile_dims"])
+    off = ops.exclusive_offsets(nwords)
+    bits = ops.paste_threshold_pack(boxes_px, win, off, dd["probs"])
+    keep, match, _ = ops.mask_iou_clean(bits, off, win, tile_org, dd["inst_tile"], dd["scores"], 0.5, 0.3)
+    keep, match = keep.cpu().numpy().astype(bool), match.cpu().numpy()
+    d = sc.det
+    sub = synth.Detections(d.boxes_net[keep], d.scores[match[keep]], d.probs[keep], d.inst_tile[keep], d.tile_dims,
+                           d.tile_ids, d.tiles)
+    rings_ref, conf_ref = port.predict_stage(sub, sc.tiles)
+    got = _rings_of(table.verts.cpu().numpy(), table.ring_off.cpu().numpy())
+    assert len(got) == len(rings_ref) and 50 < len(got) < len(plain)
+    for a, b in zip(got, rings_ref):
+        assert a == [tuple(q) for q in b]
+    np.testing.assert_array_equal(table.conf.cpu().numpy(), np.array(conf_ref))

@@ -65,7 +65,7 @@ def test_shapefile_reader_keeps_holes(tmp_path, dev):
     off = np.zeros(len(crowns) + 1, dtype=np.int64); off[1:] = np.cumsum([len(c) for c in crowns])
     xy = np.array([p for c in crowns for p in c], dtype=np.float64)
     gi, gw = idx.predicates(torch.from_numpy(xy).to(dev), torch.from_numpy(off).to(dev))
-    wi, ww = port.forest_predicates(crowns, [[[tuple(q) for q in r] for r in p] for p in got])
+    wi, ww = port.forest_predicates(crowns, [[[(float(q[0]), float(q[1])) for q in r] for r in p] for p in got])
     np.testing.assert_array_equal(gi.cpu().numpy().astype(bool), wi)
     np.testing.assert_array_equal(gw.cpu().numpy().astype(bool), ww)
     assert wi.tolist() == [False, True, True, False, True] and ww.tolist() == [False, False, True, False, True]
@@ -128,7 +128,8 @@ def test_two_model_run_matches_oracle(tmp_path, dev, monkeypatch):
     # ---- preprocess: tile flags against the oracle ----
     detection.preprocess_files(config)
     tiles = json.load(open(os.path.join(config["tiles_path"], stem + ".json")))
-    opolys = [[[tuple(q) for q in r] for r in p] for p in fusion.read_shapefile_polygons(str(tmp_path / "forest.shp"))]
+    opolys = [[[(float(q[0]), float(q[1])) for q in r] for r in p]
+              for p in fusion.read_shapefile_polygons(str(tmp_path / "forest.shp"))]
     n_f = n_u = 0
     for tid, m in tiles.items():
         parts = [int(p) for p in tid.split("_")[-5:]]

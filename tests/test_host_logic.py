@@ -150,3 +150,39 @@ def test_chain_runner_capacity_planning():
     run._learn({"words": 5000, "px": 10, "ptslots": 10, "rings": 300, "verts": 5})
     assert run.caps["words"] == int(5000 * 1.25) + 1024 and run.caps["px"] == first["px"]
     assert run.caps["rings"] == int(300 * 1.25) + 1024 and run.chain is None
+
+
+def test_prediction_and_stitching_ledgers_follow_the_reference(tmp_path):
+    """recoveries.py:5-144: same file formats (``files: {image: [tile ids]}``, ``completed_files``), the tile-count
+    validation incl. excluded tiles, and the model-path check"""
+    import logging
+    from treedetection_b200 import detection
+    log = logging.getLogger("ledger-test")
+    out, tiles_dir, stitched = tmp_path / "predictions", tmp_path / "tiles", tmp_path / "geojson_predictions"
+    for d in (out, tiles_dir, stitched):
+        d.mkdir()
+    tiles = {f"img1_{k}_0_50_20_25832": {"only_forest": k == 2, "only_urban": False} for k in range(4)}
+    for stem in ("img1", "img2", "img3"):
+        (tiles_dir / f"{stem}.json").write_text(json.dumps(tiles))
+        (stitched / f"{stem}.gpkg").write_bytes(b"")
+    files = [str(tmp_path / "rgb" / f"{s}.tif") for s in ("img1", "img2", "img3")]
+    rec = str(out / "prediction_recovery.yaml")
+    detection._save_prediction_ledger(rec, str(tiles_dir), "modelA", files, log)
+    detection._save_stitching_ledger(str(stitched), files[:2], log)
+    data = yaml.safe_load(open(rec))
+    assert data["model_path"] == "modelA" and data["files"][files[0]] == list(tiles)          # the reference's layout
+    assert yaml.safe_load(open(stitched / "stitching_recovery.yaml")) == {"completed_files": ["img1", "img2"]}
+    load = lambda model="modelA", excl=None: detection._load_prediction_ledger(rec, str(out), str(tiles_dir), model,
+                                                                                 str(stitched), excl, log)
+    assert load() == set(files[:2])                      # img3 is not in the stitching ledger, no tile files either
+    assert load("modelB") == set()                       # another model: no recovery
+    # per-tile prediction files present: the reference's count rule decides
+    (out / "img3").mkdir()
+    for k in range(3):
+        (out / "img3" / f"Prediction_{k}.json").write_text("[]")
+    assert files[2] not in load()                        # 3 files, 4 tiles
+    assert files[2] in load(excl=["only_forest"])        # ... but 3 tiles once the forest-only tile is excluded
+    (out / "img3" / "Prediction_3.json").write_text("[]")
+    assert files[2] in load()
+    os.remove(stitched / "img1.gpkg")
+    assert files[0] not in load()                        # the stitched layer itself is gone

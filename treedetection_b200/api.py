@@ -51,6 +51,7 @@ class TileTables:
         self.win = torch.tensor([m["window"] for m in tiles.values()], dtype=torch.int32).reshape(-1, 4)
         self.net = torch.tensor([tiling.resize_shortest_edge(int(w[3]), int(w[2])) for w in self.win.tolist()],
                                 dtype=torch.int32).reshape(-1, 2)
+        self.tile_org = self.win[:, :2].contiguous().to(device)       # (T,2) window origins (iou_mode: mask)
         self.tile_tf, boxes_int = pipeline.tile_tables(tiles, device)
         self.tile_boxes = pipeline.filter_boxes(boxes_int, shift, device)
         self.p1_floats = int((3 * self.net[:, 0].long() * self.net[:, 1].long()).sum())

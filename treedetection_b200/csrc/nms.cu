@@ -373,6 +373,124 @@ __global__ void containment_kernel(PairGrid g, float thr, float* __restrict__ ra
   num_contained[t] = num;
 }
 
+// ---- opt-in mask-IoU de-duplication over the packed crown rasters of P2 (iou_mode: mask) -----------------
+// The reference ships a polygon-IoU cleaner it never calls (clean_crowns, TreeDetection/helpers.py:602-701,
+// detectree2's): for every crown, among the crowns whose IoU with it exceeds the threshold (itself included)
+// the one with the highest confidence is taken, and the crown survives only if that one coincides with it
+// (IoU == 1).  Every crown is decided on its own -- no order dependence.  Here the IoU is the PIXEL IoU of
+// the 1-bit rasters P2 already left on the device: popcount(a & b) / popcount(a | b) on the image's pixel
+// grid (tile windows are pixel aligned, so rasters of different tiles compare exactly), candidates from the
+// same uniform grid as the bbox NMS.  One warp per instance: lanes take rows of the overlap rectangle, a
+// row's bits are fetched 32 at a time at an arbitrary bit offset (funnel shift of two words), AND + POPC,
+// warp-reduced with REDUX.
+struct MaskSet {
+  const uint32_t* bits;
+  const long long* word_off;
+  const int4* gbox;   // per instance: global x0, y0, width, height (pixels of the image)
+};
+
+// 32 bits of instance k's row `row` (window coordinates) starting at window column x (any x, zero outside)
+TD_D uint32_t mask_chunk(const MaskSet& M, int k, int row, int x) {
+  const int4 b = M.gbox[k];
+  if (row < 0 || row >= b.w || x >= b.z || x <= -32) return 0u;
+  const int wpr = (b.z + 31) >> 5;
+  const uint32_t* r = M.bits + M.word_off[k] + (size_t)row * wpr;
+  const int wi = x >> 5;               // floor division also for negative x
+  const int sh = x & 31;
+  const uint32_t lo = (wi >= 0 && wi < wpr) ? r[wi] : 0u;
+  const uint32_t hi = (wi + 1 >= 0 && wi + 1 < wpr) ? r[wi + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void mask_gbox_kernel(const int* __restrict__ win, const int* __restrict__ tile_org,
+                                 const int* __restrict__ inst_tile, int n, int4* __restrict__ gbox,
+                                 float4* __restrict__ box32, GridParams* gp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float x0 = 0, y0 = 0, w = 0, h = 0;
+  bool ok = false;
+  if (i < n) {
+    const int t = inst_tile[i];
+    const int4 b = make_int4(tile_org[2 * t] + win[4 * i], tile_org[2 * t + 1] + win[4 * i + 1], win[4 * i + 2],
+                             win[4 * i + 3]);
+    gbox[i] = b;
+    // pixel boxes as float boxes [x0, x0 + w) for the grid (exact below 2^24)
+    box32[i] = make_float4((float)b.x, (float)b.y, (float)(b.x + b.z), (float)(b.y + b.w));
+    x0 = (float)b.x; y0 = (float)b.y; w = (float)b.z; h = (float)b.w;
+    ok = b.z > 0 && b.w > 0;
+    if (!ok) box32[i] = make_float4(nanf(""), nanf(""), nanf(""), nanf(""));   // parked in the far cell
+  }
+  int ex = ok ? enc_f(x0) : 0x7fffffff, ey = ok ? enc_f(y0) : 0x7fffffff;
+  int ew = ok ? enc_f(w) : enc_f(0.f), eh = ok ? enc_f(h) : enc_f(0.f);
+  for (int o = 16; o > 0; o >>= 1) {
+    ex = min(ex, __shfl_xor_sync(0xffffffffu, ex, o));
+    ey = min(ey, __shfl_xor_sync(0xffffffffu, ey, o));
+    ew = max(ew, __shfl_xor_sync(0xffffffffu, ew, o));
+    eh = max(eh, __shfl_xor_sync(0xffffffffu, eh, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&gp->minx_enc, ex);
+    atomicMin(&gp->miny_enc, ey);
+    atomicMax(&gp->maxw_enc, ew);
+    atomicMax(&gp->maxh_enc, eh);
+  }
+}
+
+__global__ void mask_area_kernel(MaskSet M, int n, int* __restrict__ area) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int4 b = M.gbox[i];
+  const long long nw = (long long)((b.z + 31) >> 5) * b.w;
+  const uint32_t* p = M.bits + M.word_off[i];
+  int a = 0;
+  for (long long k = lane; k < nw; k += 32) a += __popc(p[k]);
+  a = __reduce_add_sync(0xffffffffu, a);
+  if (lane == 0) area[i] = a;
+}
+
+__global__ void __launch_bounds__(128)
+mask_iou_kernel(PairGrid g, MaskSet M, const int* __restrict__ area, const float* __restrict__ scores, float iou_thr,
+                float confidence, unsigned char* __restrict__ keep, int* __restrict__ match,
+                float* __restrict__ best_iou) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= g.n) return;
+  const int4 bi = M.gbox[i];
+  const int ai = area[i];
+  int best = -1, best_inter = 0, best_uni = 1;
+  float best_conf = 0.f;
+  if (bi.z > 0 && bi.w > 0 && ai > 0) {
+    for_each_candidate(g, i, [&](int j) {          // every lane walks the same candidates
+      const int4 bj = M.gbox[j];
+      const int ox0 = max(bi.x, bj.x), oy0 = max(bi.y, bj.y);
+      const int ox1 = min(bi.x + bi.z, bj.x + bj.z), oy1 = min(bi.y + bi.w, bj.y + bj.w);
+      if (ox0 >= ox1 || oy0 >= oy1 || area[j] <= 0) return;
+      int inter = 0;
+      for (int y = oy0 + lane; y < oy1; y += 32) {
+        for (int x = ox0; x < ox1; x += 32) {
+          uint32_t w = mask_chunk(M, i, y - bi.y, x - bi.x) & mask_chunk(M, j, y - bj.y, x - bj.x);
+          if (ox1 - x < 32) w &= (1u << (ox1 - x)) - 1u;
+          inter += __popc(w);
+        }
+      }
+      inter = __reduce_add_sync(0xffffffffu, inter);
+      const int uni = ai + area[j] - inter;
+      const float iou = __fdiv_rn((float)inter, (float)uni);
+      if (!(iou > iou_thr)) return;
+      const float cj = scores[j];
+      // nlargest(1, field): the highest confidence, the lowest index among equals
+      if (best < 0 || cj > best_conf || (cj == best_conf && j < best)) {
+        best = j; best_conf = cj; best_inter = inter; best_uni = uni;
+      }
+    });
+  }
+  if (lane != 0) return;
+  const bool kept = best >= 0 && best_inter == best_uni && best_conf > confidence;
+  keep[i] = kept ? 1 : 0;
+  match[i] = best;
+  if (best_iou) best_iou[i] = best >= 0 ? __fdiv_rn((float)best_inter, (float)best_uni) : 0.f;
+}
+
 struct Scratch {
   cudaStream_t s;
   void* ptrs[16];
@@ -550,4 +668,42 @@ extern "C" int td_containment(const float* bounds32, int n, double threshold, fl
   TD_ARG(bounds32);
   return td_containment_ex(nullptr, bounds32, n, threshold, ratio_max, is_contained, num_contained, n_dev,
                            (cudaStream_t)stream);
+}
+
+// Opt-in mask-IoU cleaner on the packed rasters of P2 (the rule of clean_crowns, TreeDetection/helpers.py:602-701,
+// with pixel IoU instead of polygon IoU): keep[i] = the best-confidence crown among those with IoU(i, .) >
+// iou_thr coincides with crown i (IoU == 1) and its confidence exceeds `confidence`; match[i] = that crown
+// (-1: none, e.g. an empty mask).  win (N,4) [x0,y0,w,h] in tile pixels, tile_org (T,2) [col_off,row_off] of
+// each tile window in the image, best_iou nullable.
+extern "C" int td_mask_iou_clean(const uint32_t* bits, const long long* word_off, const int* win, const int* tile_org,
+                                 const int* inst_tile, const float* scores, int n, float iou_thr, float confidence,
+                                 unsigned char* keep, int* match, float* best_iou, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(bits && word_off && win && tile_org && inst_tile && scores && keep && match);
+  cudaStream_t st = (cudaStream_t)stream;
+  td_ensure_pool();
+  Scratch sc(st);
+  int4* gbox = (int4*)sc.get(sizeof(int4) * n);
+  float4* box32 = (float4*)sc.get(sizeof(float4) * n);
+  GridParams* gp = (GridParams*)sc.get(sizeof(GridParams));
+  int* area = (int*)sc.get(sizeof(int) * n);
+  if (!gbox || !box32 || !gp || !area) { td_set_error("scratch allocation failed"); return TD_ERR_CUDA; }
+  const int blocks = td_div_up(n, 256);
+  grid_init_kernel<<<1, 1, 0, st>>>(gp);
+  mask_gbox_kernel<<<blocks, 256, 0, st>>>(win, tile_org, inst_tile, n, gbox, box32, gp);
+  MaskSet M{bits, word_off, gbox};
+  mask_area_kernel<<<td_div_up((long long)n * 32, 256), 256, 0, st>>>(M, n, area);
+  TD_CHECK_LAUNCH("mask iou prep");
+  PairGrid g;
+  g.box32 = box32; g.gp = gp; g.n = n; g.n_dev = nullptr; g.all_pairs = 0;
+  KeyT* keys = nullptr;
+  int* idx = nullptr;
+  int rc = build_grid(sc, box32, gp, n, &keys, &idx, nullptr);
+  if (rc != TD_OK) return rc;
+  g.keys = keys; g.idx = idx;
+  mask_iou_kernel<<<td_div_up((long long)n * 32, 128), 128, 0, st>>>(g, M, area, scores, iou_thr, confidence, keep, match,
+                                                                   best_iou);
+  TD_CHECK_LAUNCH("td_mask_iou_clean");
+  return TD_OK;
 }

@@ -316,6 +316,100 @@ def _write_predictions_json(output_path, stem, fp, tiles, det, tables, params, d
     _write_tile_predictions(os.path.join(output_path, stem), fp, tiles, rings, host(det.inst_tile), host(det.scores))
 
 
+def _load_prediction_ledger(rec_file, output_path, tiles_path, model_path, stitched_path, exclude, logger):
+    """recoveries.load_prediction_recovery_data (recoveries.py:5-73), same file format
+    ``{model_path, files: {image path: [tile ids]}}``.  An image counts as predicted when the ledger was written
+    for the same model, its tiles JSON still exists and -- the reference's rule -- the number of per-tile
+    ``Prediction_*.json`` files equals the number of (non-excluded) tiles; this build writes those files only
+    with ``keep_intermediate``, so without them the stitched layer and the stitching ledger
+    (recoveries.py:111-144, ``stitching_recovery.yaml``) are the evidence."""
+    processed = set()
+    if not os.path.exists(rec_file):
+        return processed
+    try:
+        rec = yaml.safe_load(open(rec_file)) or {}
+    except Exception as e:
+        if logger:
+            logger.warning(f"Could not load prediction recovery file: {e}")
+        return processed
+    if rec.get("model_path") != model_path:
+        if logger:
+            logger.warning("Model path does not match the one stored in the recovery file. Skipping recovery.")
+        return processed
+    stitched = _load_stitching_ledger(stitched_path, logger)
+    files = rec.get("files")
+    if files is None:                         # ledger of an older build: a flat list
+        files = {f: None for f in rec.get("processed_files", [])}
+    for file_path, keys in files.items():
+        stem = Path(file_path).stem
+        json_path = os.path.join(tiles_path, stem + ".json")
+        if not os.path.exists(json_path):
+            if logger:
+                logger.debug(f"Missing JSON metadata for {file_path}. Skipping.")
+            continue
+        folder = os.path.join(output_path, stem)
+        if os.path.isdir(folder) and keys is not None:
+            n_files = len(os.listdir(folder))
+            ok = n_files == len(keys)
+            if not ok:
+                with open(json_path) as jf:
+                    tiles = json.load(jf)
+                valid = [k for k, v in tiles.items() if not any(v.get(flag, False) for flag in (exclude or []))]
+                ok = n_files == len(valid)
+            if not ok:
+                if logger:
+                    logger.debug(f"Mismatch between output folder and JSON (after excludes) for {file_path}.")
+                continue
+        elif stem not in stitched:
+            continue
+        if os.path.exists(os.path.join(stitched_path, stem + ".gpkg")):
+            processed.add(file_path)
+    if processed and logger:
+        logger.info(f"Skipped {len(processed)} files that were already processed.")
+    return processed
+
+
+def _save_prediction_ledger(rec_file, tiles_path, model_path, files, logger):
+    """recoveries.save_prediction_recovery_data (recoveries.py:75-108)"""
+    try:
+        data = {"model_path": model_path, "files": {}}
+        for file_path in files:
+            json_path = os.path.join(tiles_path, Path(file_path).stem + ".json")
+            if os.path.exists(json_path):
+                with open(json_path) as jf:
+                    data["files"][file_path] = list(json.load(jf).keys())
+        with open(rec_file, "w") as f:
+            yaml.safe_dump(data, f, sort_keys=False)
+    except Exception as e:
+        if logger:
+            logger.warning(f"Failed to save prediction recovery file: {e}")
+
+
+def _load_stitching_ledger(stitched_path, logger=None):
+    """recoveries.load_stitching_recovery (recoveries.py:111-127): base names of the stitched layers"""
+    rec_file = os.path.join(stitched_path, "stitching_recovery.yaml")
+    done = set()
+    if os.path.exists(rec_file):
+        try:
+            rec = yaml.safe_load(open(rec_file)) or {}
+            done = {os.path.splitext(os.path.basename(p))[0] for p in rec.get("completed_files", [])}
+        except Exception as e:
+            if logger:
+                logger.warning(f"Failed to load stitching recovery: {e}")
+    return done
+
+
+def _save_stitching_ledger(stitched_path, files, logger=None):
+    """recoveries.save_stitching_recovery (recoveries.py:129-144)"""
+    try:
+        done = _load_stitching_ledger(stitched_path) | {Path(f).stem for f in files}
+        with open(os.path.join(stitched_path, "stitching_recovery.yaml"), "w") as f:
+            yaml.safe_dump({"completed_files": sorted(done)}, f, sort_keys=False)
+    except Exception as e:
+        if logger:
+            logger.warning(f"Failed to save stitching recovery: {e}")
+
+
 def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10, exclude_vars=None,
                      stitched_path=None):
     """detection.py:62-132 + helpers.process_and_stitch_predictions (helpers.py:556-600) in one
@@ -347,15 +441,8 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
         return
 
     rec_file = os.path.join(output_path, "prediction_recovery.yaml")
-    processed = set()
-    if os.path.exists(rec_file):
-        try:
-            rec = yaml.safe_load(open(rec_file)) or {}
-            if rec.get("model_path") == model_path:
-                processed = {f for f in rec.get("processed_files", [])
-                             if os.path.exists(os.path.join(stitched_path, Path(f).stem + ".gpkg"))}
-        except Exception:
-            processed = set()
+    processed = _load_prediction_ledger(rec_file, output_path, tiles_path, model_path, stitched_path, exclude_vars,
+                                        logger)
     images_paths = [f for f in images_paths if f not in processed]
     if not images_paths:
         logger.info("All files have already been predicted. Exiting Prediction.")
@@ -412,12 +499,8 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
         except Exception as e:   # per-file failures are logged and skipped (detection.py:117-120)
             logger.error(f"Error processing {fp}: {e}")
     logger.info(f"Completed prediction for {len(images_paths)} images.")
-    try:
-        with open(rec_file, "w") as f:
-            yaml.safe_dump({"model_path": model_path, "tiles_path": tiles_path,
-                            "processed_files": sorted(processed | set(done))}, f, sort_keys=False)
-    except Exception as e:
-        logger.warning(f"Failed to save recovery file: {e}")
+    _save_prediction_ledger(rec_file, tiles_path, model_path, sorted(processed | set(done)), logger)
+    _save_stitching_ledger(stitched_path, sorted(processed | set(done)), logger)
 
 
 def predict_tiles(config):
@@ -604,16 +687,55 @@ def _process_files_in_directory(directory, height_directory, image_directory, co
         logger.warning(f"Failed to save recovery file: {e}")
 
 
+def exclude_outlines(config, logger=None):
+    """helpers.py:33-69: every crown of the already existing ``processed_*`` layers that lies WITHIN the union of
+    an exclusion outline (water, buildings) is removed and the layer is rewritten.  The reference clips the
+    outline to the layer's bounds before the test (no effect on the predicate) and calls it before the
+    post-processing of the current run; the ``within`` test runs on the device (td_forest_predicates)."""
+    from .fusion import ForestIndex
+    pred_dir = os.path.join(config["output_directory"], "geojson_predictions")
+    for outline in config.get("exclude_files", []) or []:
+        try:
+            index = ForestIndex.from_file(outline, _device(config), logger)
+        except Exception as e:
+            msg = f"Failed to read exclude file '{outline}': {e}"
+            logger.error(msg) if logger else print(msg)
+            continue
+        if not os.path.isdir(pred_dir):
+            continue
+        for file in sorted(os.listdir(pred_dir)):
+            if not (file.endswith(".geojson") or file.endswith(".gpkg")) or not file.startswith("processed_"):
+                continue
+            file_path = os.path.join(pred_dir, file)
+            try:
+                verts, off, cols, epsg = gpkg.read_layer(file_path)
+                if len(off) <= 1:
+                    continue
+                _, within = index.predicates(torch.from_numpy(np.ascontiguousarray(verts)).to(index.device),
+                                             torch.from_numpy(off).to(index.device))
+                keep = np.nonzero(within.cpu().numpy() == 0)[0]
+                lens = np.diff(off)[keep]
+                new_off = np.zeros(len(keep) + 1, dtype=np.int64)
+                new_off[1:] = np.cumsum(lens)
+                new_verts = np.concatenate([verts[off[k]:off[k + 1]] for k in keep]) if len(keep) else np.zeros((0, 2))
+                new_cols = {k: [v[i] for i in keep] for k, v in cols.items()}
+                schema = {k: gpkg.PROCESSED_SCHEMA.get(k, "str") for k in cols}
+                gpkg.write_layer(file_path, Path(file_path).stem, new_verts, new_off, new_cols, schema, epsg=epsg or 4326)
+            except Exception as e:
+                msg = f"Error processing file '{file_path}': {e}."
+                logger.error(msg) if logger else print(msg)
+
+
 def postprocess_files(config):
     config_obj = Config()
     config_obj._load_into_config(config)
     logger = config["logger"]
     logger.info("Postprocessing the predictions.")
     filename_pattern = (config.get("image_regex", "(\\d+)\\.tif"), config.get("height_data_regex", "(\\d+)\\.tif"))
+    logger.info("Excluding Outlines.")
     if config.get("exclude_files"):
-        # helpers.exclude_outlines (helpers.py:33-69) only touches already existing processed_* files and is
-        # off in every benchmark configuration: not part of this build
-        logger.warning("exclude_files is not supported by treedetection_b200; ignoring.")
+        with torch.cuda.device(_device(config)):
+            exclude_outlines(config, logger)
     pred_dir = os.path.join(config["output_directory"], "geojson_predictions")
     process_files_in_directory(pred_dir, config["height_data_path"], config["image_directory"], config,
                                parallel=config["parallel"], filename_pattern=filename_pattern)

@@ -253,6 +253,22 @@ def bbox_nms_ordered_dyn(bounds, conf, area, n_dev, iou_threshold, area_threshol
     return removed
 
 
+def mask_iou_clean(bits, word_off, win, tile_org, inst_tile, scores, iou_threshold=0.7, confidence=0.2):
+    """Opt-in ``iou_mode: mask``: the rule of the reference's (uncalled) clean_crowns on the packed crown
+    rasters of P2 with pixel IoU.  tile_org (T,2) i32 = [col_off, row_off] of every tile window.
+    Returns (keep u8 (N,), match i32 (N,), best_iou f32 (N,))."""
+    n = win.shape[0]
+    dev = win.device
+    _chk(win, torch.int32, "win"); _chk(tile_org, torch.int32, "tile_org"); _chk(inst_tile, torch.int32, "inst_tile")
+    _chk(scores, torch.float32, "scores"); _chk(word_off, torch.int64, "word_off")
+    keep = torch.empty((n,), dtype=torch.uint8, device=dev)
+    match = torch.empty((n,), dtype=torch.int32, device=dev)
+    best = torch.empty((n,), dtype=torch.float32, device=dev)
+    _lib.call("td_mask_iou_clean", _ptr(bits), _ptr(word_off), _ptr(win), _ptr(tile_org), _ptr(inst_tile), _ptr(scores),
+              n, float(iou_threshold), float(confidence), _ptr(keep), _ptr(match), _ptr(best), _stream())
+    return keep, match, best
+
+
 # ----------------------------------------------------------------------------
 # device-side bookkeeping (counts stay on the device)
 # ----------------------------------------------------------------------------

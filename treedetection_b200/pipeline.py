@@ -45,6 +45,12 @@ class PipelineParams:
     simplify_tolerance: float = 0.2
     shift: int = 1                       # detection.py:240
     mask_threshold: float = 0.5          # detectron2 ROI_HEADS mask threshold
+    # opt-in (not in the reference's schema): "mask" runs the rule of the reference's uncalled clean_crowns
+    # (helpers.py:602-701) with pixel IoU on the packed P2 rasters before the contours are traced; its
+    # thresholds are clean_crowns' defaults / the config key the reference reserves for it
+    iou_mode: str = "bbox"
+    mask_iou_threshold: float = 0.7
+    confidence_threshold_stitching: float = 0.3
 
     @classmethod
     def from_config(cls, config: dict):
@@ -101,12 +107,23 @@ def filter_boxes(boxes_int, shift, device):
     return torch.tensor(rows, dtype=torch.float64, device=device).reshape(-1, 4)
 
 
-def predict_stage(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams):
-    """P2 + P3 + P4.  All arguments are device tensors (see :mod:`synth` for layouts)."""
+def predict_stage(boxes_net, scores, probs, inst_tile, tile_dims, tile_tf, tile_boxes, p: PipelineParams,
+                  tile_org=None):
+    """P2 + P3 + P4.  All arguments are device tensors (see :mod:`synth` for layouts).  ``tile_org`` (T,2) i32
+    [col_off, row_off] of the tile windows is needed by ``iou_mode: mask`` only."""
     boxes_px, win, nwords = ops.paste_plan(boxes_net, inst_tile, tile_dims)
     word_off = ops.exclusive_offsets(nwords)
     total_words = int(word_off[-1].item())
     bits = ops.paste_threshold_pack(boxes_px, win, word_off, probs, p.mask_threshold, total_words)
+    if p.iou_mode == "mask":
+        if tile_org is None:
+            raise ValueError("iou_mode 'mask' needs the tile window origins (tile_org)")
+        keep, match, _ = ops.mask_iou_clean(bits, word_off, win, tile_org, inst_tile, scores, p.mask_iou_threshold,
+                                            p.confidence_threshold_stitching)
+        # a dropped instance gets an empty window (no contours); a kept one takes the confidence of its match
+        # (itself, or an exact duplicate with a higher confidence: clean_crowns appends the MATCH)
+        win = torch.where(keep.bool()[:, None], win, torch.zeros_like(win)).contiguous()
+        scores = scores[match.clamp(min=0).long()].contiguous()
     rings = ops.trace_rings(bits, win, word_off, inst_tile, tile_tf, total_words)
     return _stitch(rings, scores, inst_tile, tile_boxes, p)
 
@@ -333,6 +350,9 @@ class ChainRunner:
         mark(name): optional callback at the stage boundaries ("p4", "p5", "p9"), e.g. to record events."""
         mark = mark or (lambda name: None)
         n_inst = int(det["boxes_net"].shape[0])
+        if self.p.iou_mode != "bbox":
+            raise _lib_error("ChainRunner covers the reference's path (iou_mode 'bbox'); the opt-in mask mode runs "
+                             "through pipeline.predict_stage")
         if self.caps is None or n_inst > self.caps["inst"]:
             out = ("done",) + self._exact(det, tile_tf, tile_boxes, rasters_fn)
             for name in ("p3", "p4", "p5", "p9"):
