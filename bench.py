@@ -45,6 +45,13 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     ap.add_argument("--no-merged", action="store_true", help="skip the secondary crowns-merged/s measurement")
+    ap.add_argument("--images-per-rank", type=int, default=1,
+                    help="images per GPU and step (replicas of the rank's image with their right-seam strips between "
+                         "them and, N > 1, one down-seam strip each towards the next rank); 8 at --gpus 8 is the full "
+                         "BASELINE config 5 (64 images, 56 right + 56 down strips)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE.json config: 2 = single model 10k x 10k (the headline), 3 = two models + forest outline "
+                         "on a 20k x 20k mosaic (one extra line, 1 GPU)")
     ap.add_argument("--no-files", action="store_true", help="skip e2e_files (process_files on GeoTIFFs on tmpfs)")
     ap.add_argument("--files-images", type=int, default=3, help="images of the workload in e2e_files")
     ap.add_argument("--join-steps", action="store_true",
@@ -395,10 +402,56 @@ def run_b200(a):
                         ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")},
             }
 
+    # ---- more than one image per rank: the right-seam strip between horizontally adjacent images (same rank) ----
+    M = max(1, a.images_per_rank)
+    rstrip = None
+    if M > 1:
+        from treedetection_b200 import tiling
+        assert a.ndsm_px == 0.2, "--images-per-rank > 1 needs the 0.2 m nDSM (strips are 270 PIXELS wide in both rasters)"
+        px = 0.2
+        sw = int((p.tile_width + 2 * p.buffer) * p.overlapping_tiles_width)           # 270 px (merging.py:60-62)
+        own = sc.field
+        right = synth.TreeField(own.x + own.width_m, own.y, own.r, own.h, own.score, own.ecc, own.left + own.width_m,
+                                own.bottom, own.width_m, own.height_m)                # the replica to the right
+        both = synth.TreeField(*[np.concatenate([getattr(own, k), getattr(right, k)]) for k in
+                                 ("x", "y", "r", "h", "score", "ecc")], own.left, own.bottom, 2 * own.width_m, own.height_m)
+        r_left = own.left + own.width_m - (sw // 2) * px
+        r_tf = synth.image_transform(r_left, own.bottom + own.height_m, px)
+        r_tiles = tiling.tile_grid(f"FDOP20_rseam{rank}_rgbi", r_tf, sw, a.size, synth.EPSG, p.tile_width, p.tile_height,
+                                   p.buffer)
+        r_det = synth.make_detections(both, r_tiles, px, 4321 + rank)
+        r_tables = api.TileTables(r_tiles, dev, p.shift)
+        rstrip = {"tf": r_tf, "tables": r_tables, "sw": sw,
+                  "p1": torch.empty((r_tables.p1_floats,), dtype=torch.float32, device=dev),
+                  "rgbi": torch.empty((d["rgbi"].shape[0], a.size, sw), dtype=d["rgbi"].dtype, device=dev),
+                  "ndsm": torch.empty((1, a.size, sw), dtype=d["ndsm"].dtype, device=dev), "p5": {},
+                  "det": {k: torch.from_numpy(getattr(r_det, k)).to(dev) for k in
+                          ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}}
+
     det_keys = ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")
     runner = pipeline.ChainRunner(p)           # P2-P9 without host synchronisation (capacity buffers)
     strip_runner = pipeline.ChainRunner(p)
-    pending = []                               # tickets of enqueued images, collected one step later
+    rstrip_runner = pipeline.ChainRunner(p)
+    pending = []                               # tickets of enqueued images / strips, oldest first
+    MAX_IN_FLIGHT = 3                          # per runner (a ChainRunner has 4 output slots)
+
+    def make_room(r):
+        """collect the oldest tickets until runner ``r`` has fewer than MAX_IN_FLIGHT images in flight"""
+        while sum(1 for q, _ in pending if q is r) >= MAX_IN_FLIGHT:
+            q, t = pending.pop(0)
+            n_c, f = q.collect(t)
+            if q is runner:
+                results.append((n_c, len(f)))
+
+    def step_rstrip():
+        """the right-seam strip between this image and its right neighbour (a replica held by the same rank)"""
+        ops.seam_crop(d["rgbi"], d["rgbi"], 0, rstrip["sw"], a.size, out=rstrip["rgbi"])
+        ops.seam_crop(d["ndsm"][None], d["ndsm"][None], 0, rstrip["sw"], a.size, out=rstrip["ndsm"])
+        rstrip["tables"].plan(rstrip["rgbi"]).run(rstrip["rgbi"], rstrip["p1"])
+        sd = rstrip["det"]
+        return rstrip_runner.submit({k: sd[k] for k in det_keys}, rstrip["tables"].tile_tf, rstrip["tables"].tile_boxes,
+                                    lambda: pipeline.raster_stage(rstrip["rgbi"], rstrip["tf"], rstrip["ndsm"][0],
+                                                                  rstrip["tf"], p, buffers=rstrip["p5"]))
 
     # halo receive buffers, strip rasters and P5 outputs are allocated once: nothing is allocated inside a step,
     # and the strip's chain replays the same CUDA graphs every step (their keys are the buffer addresses)
@@ -472,8 +525,6 @@ def run_b200(a):
 
     side_streams = (p1_stream, chain_stream, strip_stream, p5_stream)
     p5_guard = [None] * len(p5_bufs)           # chain event after which a P5 output buffer may be overwritten
-    per_step = 2 if (world > 1 and rank + 1 < world) else 1
-    in_flight_steps = 2
 
     def region_begin():
         main = torch.cuda.current_stream()
@@ -486,63 +537,68 @@ def run_b200(a):
             main.wait_stream(st)
 
     def step_resident():
-        """One image per GPU (plus, N > 1, the seam strip below it).  The four streams run FREE between the two
-        ends of a timed region: images are independent, so P1 of the next image may start while the chain of
-        this one finishes -- there is no join per step (``--join-steps`` restores one).  The host stays at most
-        ``in_flight_steps`` images ahead: it collects the counters of the image enqueued that long ago."""
-        while len(pending) > (in_flight_steps - 1) * per_step:
-            r, t = pending.pop(0)
-            n_c, f = r.collect(t)
-            if r is runner:
-                results.append((n_c, len(f)))
-        e = [ev() for _ in range(6)]
-        ts = None
-        if a.serial:
-            e[0].record()
-            tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
-            e[1].record()
-            t = chain(e)
-            if world > 1:
-                ts = step_strip()
-        else:
-            if a.join_steps:
-                region_begin()
-            with torch.cuda.stream(p1_stream):
+        """One step = M images per GPU (default 1), the right-seam strips between them and, N > 1, the down-seam
+        strip below each of them.  The streams run FREE between the two ends of a timed region: images are
+        independent, so P1 of the next image may start while the chain of this one finishes -- there is no join
+        per image (``--join-steps`` restores one).  The host collects the counters of the oldest image whenever a
+        runner has three images in flight."""
+        for m in range(M):
+            e = [ev() for _ in range(6)]
+            t = ts = tr = None
+            make_room(runner)
+            if a.serial:
                 e[0].record()
                 tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
                 e[1].record()
-            if not a.exact:
-                # P5 (issue bound, needed only by the statistics) on its own stream, next to P2-P4
-                with torch.cuda.stream(p5_stream):
-                    p5_seq[0] += 1
-                    b = p5_seq[0] % len(p5_bufs)
-                    if p5_guard[b] is not None:
-                        p5_stream.wait_event(p5_guard[b])        # the chain that read this buffer is done
-                    q0, q1 = ev(), ev()
-                    q0.record()
-                    r = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p,
-                                              buffers=p5_bufs[b])
-                    q1.record()
-                    p5_ev.append((q0, q1))
-                    r["ndvi_ready"] = p5_stream.record_event()
-                    r["_buf"] = b
-                pre_rasters.append(r)
-            # the strip's small dependent launches go in first: they run under P1 while the host is still enqueuing
-            if world > 1:
-                with torch.cuda.stream(strip_stream):
-                    ts = step_strip()
-            with torch.cuda.stream(chain_stream):
                 t = chain(e)
+                if world > 1:
+                    make_room(strip_runner)
+                    ts = step_strip()
+                if rstrip is not None and m + 1 < M:
+                    make_room(rstrip_runner)
+                    tr = step_rstrip()
+            else:
+                if a.join_steps:
+                    region_begin()
+                with torch.cuda.stream(p1_stream):
+                    e[0].record()
+                    tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+                    e[1].record()
                 if not a.exact:
-                    p5_guard[p5_seq[0] % len(p5_bufs)] = chain_stream.record_event()
-            if a.join_steps:
-                region_end()
-        p1_ev.append((e[0], e[1]))
-        stage_ev.append(e)
-        if t is not None:
-            pending.append((runner, t))
-        if ts is not None:
-            pending.append((strip_runner, ts))
+                    # P5 (issue bound, needed only by the statistics) on its own stream, next to P2-P4
+                    with torch.cuda.stream(p5_stream):
+                        p5_seq[0] += 1
+                        b = p5_seq[0] % len(p5_bufs)
+                        if p5_guard[b] is not None:
+                            p5_stream.wait_event(p5_guard[b])        # the chain that read this buffer is done
+                        q0, q1 = ev(), ev()
+                        q0.record()
+                        r = pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p,
+                                                  buffers=p5_bufs[b])
+                        q1.record()
+                        p5_ev.append((q0, q1))
+                        r["ndvi_ready"] = p5_stream.record_event()
+                    pre_rasters.append(r)
+                # the strips' small dependent launches go in first: they run under P1 while the host is still enqueuing
+                if world > 1:
+                    make_room(strip_runner)
+                    with torch.cuda.stream(strip_stream):
+                        ts = step_strip()
+                if rstrip is not None and m + 1 < M:
+                    make_room(rstrip_runner)
+                    with torch.cuda.stream(strip_stream):
+                        tr = step_rstrip()
+                with torch.cuda.stream(chain_stream):
+                    t = chain(e)
+                    if not a.exact:
+                        p5_guard[p5_seq[0] % len(p5_bufs)] = chain_stream.record_event()
+                if a.join_steps:
+                    region_end()
+            p1_ev.append((e[0], e[1]))
+            stage_ev.append(e)
+            for q, tk in ((runner, t), (strip_runner, ts), (rstrip_runner, tr)):
+                if tk is not None:
+                    pending.append((q, tk))
 
     last_feats = []
 
@@ -594,7 +650,7 @@ def run_b200(a):
     ms, _ = timed(step_resident, a.steps, free_running=not a.serial)
     drain()
     launches = _lib.launch_count - l0
-    assert len(results) == a.steps and len(set(results)) == 1, "steps disagree on the crown counts"
+    assert len(results) == a.steps * M and len(set(results)) == 1, "steps disagree on the crown counts"
     n_cand, n_final = results[-1]
     # parity of THIS run's crowns: the last step's final layer against the golden the CPU oracle produced for the same
     # scene (tests/golden/config2.npz; rank 0's image is the golden's scene); outside the timed region
@@ -627,7 +683,7 @@ def run_b200(a):
     if p5_ev:      # P5 ran on its own stream
         stage_ms[names[2]] = statistics.mean(x.elapsed_time(y) for x, y in p5_ev[-a.steps:])
     area = sc.area_km2
-    value = world * area * a.steps / (ms / 1e3)
+    value = world * M * area * a.steps / (ms / 1e3)
 
     # end to end through the host-buffer API
     e2e_runner = pipeline.ChainRunner(p)
@@ -721,7 +777,11 @@ def run_b200(a):
             "config": {"workload": workload_string(a.size, a.ndsm_px),
                        "counts": f"{n_tiles} tiles, {n_inst} ROI-head instances -> {n_cand} candidate crowns -> "
                                  f"{n_final} crowns per image",
-                       "area_km2_per_gpu": area, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
+                       "area_km2_per_gpu": area * M, "images_per_gpu_per_step": M,
+                       "strips_per_step": {"right_seam": world * (M - 1) if rstrip is not None else 0,
+                                           "down_seam": (world - 1) * M,
+                                           "note": "seam strips re-process imagery the images already cover: their area is "
+                                                   "NOT counted in value"}, "stages": "P1+P2+P3+P4+P5+P6+P7+P8+P9",
                        "chain": chain_mode,
                        "streams": ("one stream, stages back to back" if a.serial else
                                    "P1 and P5 on their own streams concurrent with the P2-P4 / P6-P9 chain (high-priority stream); "
@@ -783,10 +843,114 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------
+# BASELINE config 3: two models + forest outline on a 20 000 x 20 000 px mosaic (1 GPU)
+# --------------------------------------------------------------------------------------
+def run_config3(a):
+    """P1 once, P2-P4 for the urban and the forest model (each skipping the tiles the outline assigns to the other,
+    prediction.py:79-93), P10 fusion against the forest outline (helpers.py:795-811), P5, P6-P9 on the fused layer.
+    Exact-size composition (the two tables meet in the fusion, which the single-model CUDA-graph chain does not
+    cover).  Parity of this path: tests/test_gpu_two_model.py (small scene, against the oracle)."""
+    import numpy as np
+    import torch
+
+    from treedetection_b200 import api, fusion, pipeline, synth, tiling
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    size = a.size if a.size != 10000 else 20000
+    p = pipeline.PipelineParams()
+    t0 = time.perf_counter()
+    field = synth.tree_field(1234, size * 0.2, size * 0.2, 2500.0)
+    rgbi, ndsm = synth.make_rgbi(field, 0.2, 1234), synth.make_ndsm(field, a.ndsm_px, 1234)
+    top = synth.ORIGIN_Y + size * 0.2
+    tf, ntf = synth.image_transform(synth.ORIGIN_X, top, 0.2), synth.image_transform(synth.ORIGIN_X, top, a.ndsm_px)
+    # forest outline: ~40 % cover, random convex patches and rectangles, a third of them with a clearing (hole)
+    rng = np.random.default_rng(3)
+    ext = size * 0.2
+    polys, cover = [], 0.0
+    while cover < 0.4 * ext * ext:
+        cx, cy = synth.ORIGIN_X + rng.uniform(0, ext), synth.ORIGIN_Y + rng.uniform(0, ext)
+        r = rng.uniform(0.04, 0.12) * ext
+        if rng.uniform() < 0.4:
+            w, h = rng.uniform(0.8, 2.0, 2) * r
+            ring = np.array([(cx + w, cy - h), (cx + w, cy + h), (cx - w, cy + h), (cx - w, cy - h), (cx + w, cy - h)])
+            cover += 4 * w * h
+        else:
+            ang = np.sort(rng.uniform(0, 2 * np.pi, int(rng.integers(6, 14))))
+            ring = np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], 1)
+            ring = np.concatenate([ring, ring[:1]])
+            cover += 2.6 * r * r
+        poly = [ring]
+        if rng.uniform() < 0.33:
+            ha = np.sort(rng.uniform(0, 2 * np.pi, 8))[::-1]
+            hole = np.stack([cx + 0.3 * r * np.cos(ha), cy + 0.3 * r * np.sin(ha)], 1)
+            poly.append(np.concatenate([hole, hole[:1]]))
+        polys.append(poly)
+    forest = fusion.ForestIndex(polys, dev)
+    tiles = tiling.tile_grid("FDOP20_000000_rgbi", tf, size, size, synth.EPSG, p.tile_width, p.tile_height, p.buffer, forest)
+    flags = np.array([[m["only_forest"], m["only_urban"]] for m in tiles.values()])
+    dets = {}
+    for name, seed, skip_col in (("urban", 5, 0), ("forest", 6, 1)):
+        d = synth.make_detections(field, tiles, 0.2, seed)
+        keep = ~flags[d.inst_tile, skip_col]
+        dets[name] = {k: torch.from_numpy(np.ascontiguousarray(getattr(d, k)[keep] if k != "tile_dims" else d.tile_dims)).to(dev)
+                      for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
+    tables = api.TileTables(tiles, dev, p.shift)
+    d_rgbi, d_ndsm = torch.from_numpy(rgbi).to(dev), torch.from_numpy(ndsm).to(dev)
+    p1_out = torch.empty((tables.p1_floats,), dtype=torch.float32, device=dev)
+    setup_s = time.perf_counter() - t0
+    p1_stream = torch.cuda.Stream(device=dev)
+    counts = {}
+
+    def step():
+        main = torch.cuda.current_stream()
+        p1_stream.wait_stream(main)
+        with torch.cuda.stream(p1_stream):
+            tables.plan(d_rgbi).run(d_rgbi, p1_out)
+        tabs = {n: pipeline.predict_stage(**dets[n], tile_tf=tables.tile_tf, tile_boxes=tables.tile_boxes, p=p)
+                for n in ("urban", "forest")}
+        u, f = tabs["urban"], tabs["forest"]
+        verts, off, conf = fusion.fuse_tables((u.verts, u.ring_off, u.conf), (f.verts, f.ring_off, f.conf), forest)
+        rasters = pipeline.raster_stage(d_rgbi, tf, d_ndsm, ntf, p)
+        feats = pipeline.postprocess_stage(pipeline.CrownTable(verts, off, conf), rasters, p)
+        main.wait_stream(p1_stream)
+        counts.update(urban=len(u), forest=len(f), fused=int(off.shape[0] - 1), crowns=len(feats))
+        return feats
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    s, e = ev(), ev()
+    steps = max(3, min(a.steps, 10))
+    s.record()
+    for _ in range(steps):
+        feats = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    area = (size * 0.2 / 1000.0) ** 2
+    v = feats.verts.cpu().numpy()
+    assert len(feats) > 1000 and np.array_equal(v, np.round(v, 3))
+    print(json.dumps({
+        "metric": METRIC, "value": area / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f32 rasters, f32/f16 NMS, f64 geometry", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 3: two-model run with a forest outline on a synthetic {size}x{size} px mosaic "
+                               f"({len(tiles)} tiles, {int(flags[:, 0].sum())} forest-only / {int(flags[:, 1].sum())} urban-only; "
+                               f"{len(polys)} outline polygons, {sum(len(q) - 1 for q in polys)} holes)",
+                   "counts": counts, "instances": {k: int(v_["scores"].numel()) for k, v_ in dets.items()},
+                   "chain": "exact-size composition: P1 || 2 x (P2-P4) -> P10 fusion -> P5 -> P6-P9",
+                   "setup_s": round(setup_s, 1)},
+        "gpu_launches": None, "e2e": None}))
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == 3:
+        run_config3(a)
     else:
         run_b200(a)
 

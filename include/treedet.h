@@ -183,6 +183,12 @@ int td_crown_stats(const double* verts, const long long* ring_off, int n, const 
                    float* ndvi_stats, const long long* n_dev, void* stream);
 int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid, const long long* n_dev,
                  void* stream);
+/*   optional nDSM summary (north_star "min / max / mean / percentile"; the reference keeps the maximum only,
+ *   postprocessing.py:25-115): over the pixel set of get_height_within_polygon, out (N,4) f32 = [min, mean,
+ *   percentile q (0..100, numpy's "linear" rule, exact order statistics), pixel count]; empty set -> -1   */
+int td_crown_height_summary(const double* verts, const long long* ring_off, int n, const float* height, int rows,
+                            int cols, const double* transform6, double q, float* out, const long long* n_dev,
+                            void* stream);
 
 /* ---- P8: bbox containment ---------------------------------------------------------------------
  * Replaces process_containment_features (TreeDetection/postprocessing.py:408-476).

@@ -486,6 +486,26 @@ def crown_stats_ndvi(px32, py32, ndvi32, transform):
     return res
 
 
+def crown_height_summary(px32, py32, height32, transform, q=95.0):
+    """Optional nDSM summary per crown (north_star "min / max / mean / percentile"; the reference keeps the maximum
+    only): over the pixel set of ``get_height_within_polygon`` (postprocessing.py:25-115: float64 pixel
+    coordinates, full radius) -> (N,4) float32 [min, mean, numpy "linear" percentile q, pixel count]; -1 for an
+    empty set.  Mean and percentile are evaluated in float64 on the float32 values."""
+    h, w = height32.shape
+    xs, ys = pixel_coords(transform, h, w, np.float64)
+    xs = xs.ravel(); ys = ys.ravel(); hv = height32.ravel()
+    out = np.zeros((px32.shape[0], 4), dtype=np.float32)
+    for i in range(px32.shape[0]):
+        cx, cy, r = crown_circle(px32[i], py32[i])
+        sel = hv[(xs - cx) ** 2 + (ys - cy) ** 2 <= r ** 2]
+        if sel.size == 0:
+            out[i] = (-1, -1, -1, 0)
+            continue
+        s64 = sel.astype(np.float64)
+        out[i] = (sel.min(), s64.mean(), np.percentile(s64, q), sel.size)
+    return out
+
+
 # ---- windowed forms (test infrastructure for FULL-SIZE scenes) ---------------------------------
 # The three functions above follow the reference literally: every crown is tested against EVERY raster
 # pixel (O(N * P): 10^4 crowns x 10^8 pixels at BASELINE config 2).  The forms below evaluate the same

@@ -237,3 +237,32 @@ def test_mask_iou_clean_matches_restated_clean_crowns(dev):
         np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), wkeep)
         assert 0 < wkeep.sum() < len(wkeep)
     assert not wkeep[7] and wmatch[7] == -1
+
+
+@pytest.mark.parametrize("q", [50.0, 95.0, 0.0, 100.0, 33.3])
+def test_crown_height_summary_matches_numpy(dev, q):
+    """optional nDSM min / mean / percentile per crown (radix select + numpy's linear interpolation) against NumPy
+    on the pixel set of get_height_within_polygon; crowns outside the raster (-1), ties and NaN pixels included"""
+    rng = np.random.default_rng(int(q))
+    left, bottom, size_m, px = synth.ORIGIN_X + 100.0, synth.ORIGIN_Y + 50.0, 80.0, 0.5
+    n_px = int(size_m / px)
+    tf = synth.image_transform(left, bottom + size_m, px)
+    height = np.round(rng.uniform(0, 30, (n_px, n_px)), 1).astype(np.float32)      # rounded: many equal values
+    height[20:24, 30:40] = np.nan
+    rings = []
+    for _ in range(120):
+        cx, cy = left + rng.uniform(-10, size_m + 10), bottom + rng.uniform(-10, size_m + 10)
+        r = rng.uniform(0.3, 9.0)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 12))
+        ring = [(float(cx + r * np.cos(a)), float(cy + r * np.sin(a))) for a in ang]
+        rings.append(ring + [ring[0]])
+    px32, py32 = port.pad_polygons(rings)
+    want = port.crown_height_summary(px32, py32, height, tf, q)
+    off = np.zeros(len(rings) + 1, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in rings])
+    verts = torch.from_numpy(np.array([p for r in rings for p in r], dtype=np.float64)).to(dev)
+    got = ops.crown_height_summary(verts, torch.from_numpy(off).to(dev), torch.from_numpy(height).to(dev), tf, q).cpu().numpy()
+    np.testing.assert_array_equal(got[:, 3], want[:, 3])                 # the pixel sets
+    np.testing.assert_array_equal(got[:, 0], want[:, 0])                 # min (NaN where the set holds a NaN)
+    np.testing.assert_array_equal(got[:, 2], want[:, 2])                 # percentile: exact order statistics
+    np.testing.assert_allclose(got[:, 1], want[:, 1], atol=ATOL, rtol=0, equal_nan=True)
+    assert (want[:, 3] == 0).any() and np.isnan(want[:, 0]).any() and (want[:, 3] > 50).any()

@@ -186,6 +186,154 @@ crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict
   }
 }
 
+// ---- optional nDSM summary per crown: min / mean / percentile (north_star; the reference computes the maximum
+// only, postprocessing.py:25-115) -------------------------------------------------------------------------------
+// Pixel set = that of get_height_within_polygon (float64 pixel coordinates, full radius).  The percentile is
+// numpy's default ("linear"): exact order statistics by a warp-wide radix select on the order-preserving
+// integer image of the float32 values (4 passes of 8 bits, 256-bin histograms in shared memory), then
+// numpy's _lerp in float64.  out (N,4) f32 = [min, mean, percentile, number of pixels]; empty set -> -1 (count 0),
+// a NaN in the set -> NaN (as numpy).
+TD_D unsigned f32_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+TD_D float key_f32(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void __launch_bounds__(128)
+crown_height_summary_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
+                            const long long* __restrict__ ring_idx, int n, const float* __restrict__ height, int rows,
+                            int cols, Affine6 T, double q01, float* __restrict__ out,
+                            const long long* __restrict__ n_dev) {
+  __shared__ int s_hist[4][256];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int crown = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (crown >= n || (n_dev && crown >= *n_dev)) return;
+  int* hist = s_hist[wib];
+  const long long ring = ring_idx ? ring_idx[crown] : crown;
+  const long long v0 = ring_off[ring], v1 = ring_off[ring + 1];
+  float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+  for (long long k = v0 + lane; k < v1; k += 32) {
+    const float x = __double2float_rn(verts[2 * k]), y = __double2float_rn(verts[2 * k + 1]);
+    if (isnan(x) || isnan(y)) continue;
+    mnx = fminf(mnx, x); mxx = fmaxf(mxx, x);
+    mny = fminf(mny, y); mxy = fmaxf(mxy, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(full, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(full, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(full, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(full, mxy, o));
+  }
+  const float cx = __fdiv_rn(__fadd_rn(mnx, mxx), 2.f), cy = __fdiv_rn(__fadd_rn(mny, mxy), 2.f);
+  float r = -INFINITY;
+  for (long long k = v0 + lane; k < v1; k += 32) {
+    const float x = __double2float_rn(verts[2 * k]), y = __double2float_rn(verts[2 * k + 1]);
+    if (isnan(x) || isnan(y)) continue;
+    const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy);
+    r = fmaxf(r, __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+  }
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(full, r, o));
+  const double r2 = (double)__fmul_rn(r, r);
+  int c_lo = 0, c_hi = cols - 1, r_lo = 0, r_hi = rows - 1;
+  if (T.b == 0.0 && T.d == 0.0 && T.a != 0.0 && T.e != 0.0 && isfinite(r) && isfinite(cx) && isfinite(cy)) {
+    const double mag = fmax(fmax(fabs((double)cx), fabs((double)cy)), 1.0);
+    const double m = (double)r * 1e-3 + mag * 4.8e-7 + 1e-6;
+    const double xa = ((double)cx - (double)r - m - T.c) / T.a, xb = ((double)cx + (double)r + m - T.c) / T.a;
+    const double ya = ((double)cy - (double)r - m - T.f) / T.e, yb = ((double)cy + (double)r + m - T.f) / T.e;
+    c_lo = (int)fmax(floor(fmin(xa, xb)) - 1.0, 0.0); c_hi = (int)fmin(ceil(fmax(xa, xb)) + 1.0, (double)(cols - 1));
+    r_lo = (int)fmax(floor(fmin(ya, yb)) - 1.0, 0.0); r_hi = (int)fmin(ceil(fmax(ya, yb)) + 1.0, (double)(rows - 1));
+  }
+  // visits every pixel of the set: f(value)
+  auto for_each_pixel = [&](auto f) {
+    if (isnan(r)) return;
+    for (int rr = r_lo; rr <= r_hi; ++rr) {
+      const double brr = T.b * (double)rr, err = T.e * (double)rr;
+      for (int cc = c_lo + lane; cc <= c_hi; cc += 32) {
+        const double dx = (T.a * (double)cc + brr + T.c) - (double)cx, dy = (T.d * (double)cc + err + T.f) - (double)cy;
+        if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= r2) f(height[(long long)rr * cols + cc]);
+      }
+    }
+  };
+  // pass 1: count, sum, min, NaN
+  long long cnt = 0;
+  double sum = 0.0;
+  float vmin = INFINITY;
+  int has_nan = 0;
+  for_each_pixel([&](float v) {
+    ++cnt; sum += (double)v;
+    if (isnan(v)) has_nan = 1; else vmin = fminf(vmin, v);
+  });
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(full, cnt, o);
+    sum += __shfl_xor_sync(full, sum, o);
+    vmin = fminf(vmin, __shfl_xor_sync(full, vmin, o));
+    has_nan |= __shfl_xor_sync(full, has_nan, o);
+  }
+  float* o4 = out + 4 * (size_t)crown;
+  if (cnt == 0) { if (lane == 0) { o4[0] = o4[1] = o4[2] = -1.f; o4[3] = 0.f; } return; }
+  if (has_nan) { if (lane == 0) { o4[0] = o4[1] = o4[2] = nanf(""); o4[3] = (float)cnt; } return; }
+  // numpy "linear": virtual index (n - 1) * q, neighbours k and k + 1, weight gamma
+  const double virt = (double)(cnt - 1) * q01;
+  const long long k = (long long)floor(virt);
+  const double gamma = virt - (double)k;
+  // radix select of the k-th smallest key
+  unsigned prefix = 0u, pmask = 0u;
+  long long rank = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int b = lane; b < 256; b += 32) hist[b] = 0;
+    __syncwarp();
+    for_each_pixel([&](float v) {
+      const unsigned key = f32_key(v);
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    });
+    __syncwarp();
+    // bin holding the element of rank `rank`: lane l owns bins 8l .. 8l+7
+    int mine = 0;
+    for (int b = 0; b < 8; ++b) mine += hist[8 * lane + b];
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - mine;
+    const bool here = rank >= excl && rank < incl;
+    int bin = -1;
+    long long new_rank = 0;
+    if (here) {
+      long long acc = excl;
+      for (int b = 0; b < 8; ++b) {
+        const int h = hist[8 * lane + b];
+        if (rank < acc + h) { bin = 8 * lane + b; new_rank = rank - acc; break; }
+        acc += h;
+      }
+    }
+    const unsigned owner = __ballot_sync(full, here);
+    const int src = __ffs(owner) - 1;
+    bin = __shfl_sync(full, bin, src);
+    new_rank = __shfl_sync(full, new_rank, src);
+    prefix |= (unsigned)bin << shift;
+    pmask |= 255u << shift;
+    rank = new_rank;
+    __syncwarp();
+  }
+  const float vk = key_f32(prefix);
+  // the next order statistic: vk again when it is repeated beyond rank k, else the smallest larger value
+  long long le = 0;
+  float vnext = INFINITY;
+  for_each_pixel([&](float v) {
+    if (v <= vk) ++le; else vnext = fminf(vnext, v);
+  });
+  for (int o = 16; o > 0; o >>= 1) {
+    le += __shfl_xor_sync(full, le, o);
+    vnext = fminf(vnext, __shfl_xor_sync(full, vnext, o));
+  }
+  if (lane != 0) return;
+  const double a = (double)vk, b = (k + 1 < cnt) ? (double)(le > k + 1 ? vk : vnext) : (double)vk;
+  const double diff = b - a;
+  double res = a + diff * gamma;                     // numpy _lerp
+  if (gamma >= 0.5) res = b - diff * (1.0 - gamma);
+  o4[0] = vmin; o4[1] = (float)(sum / (double)cnt); o4[2] = (float)res; o4[3] = (float)cnt;
+}
+
 // ---- centroids: np.nanmean over the NaN-padded (N, V) float32 arrays ---------
 // numpy reduces every row with its pairwise summation over the PADDED length V
 // (NaN -> 0), so the blocking depends on V = the longest ring of the batch.
@@ -328,4 +476,19 @@ int td_centroids_ex(const double* verts, const long long* ring_off, const long l
 extern "C" int td_centroids(const double* verts, const long long* ring_off, int n, float* centroid,
                             const long long* n_dev, void* stream) {
   return td_centroids_ex(verts, ring_off, nullptr, n, centroid, nullptr, n_dev, (cudaStream_t)stream);
+}
+
+// Optional nDSM summary per crown over the pixel set of get_height_within_polygon (postprocessing.py:25-115):
+// out (N,4) f32 = [min, mean, percentile `q` (0..100, numpy "linear"), number of pixels]; -1 when the set is empty.
+extern "C" int td_crown_height_summary(const double* verts, const long long* ring_off, int n, const float* height,
+                                       int rows, int cols, const double* transform6, double q, float* out,
+                                       const long long* n_dev, void* stream) {
+  TD_ARG(n >= 0);
+  if (n == 0) return TD_OK;
+  TD_ARG(verts && ring_off && height && transform6 && out && rows > 0 && cols > 0 && q >= 0.0 && q <= 100.0);
+  const Affine6 T{transform6[0], transform6[1], transform6[2], transform6[3], transform6[4], transform6[5]};
+  crown_height_summary_kernel<<<td_div_up((long long)n * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      verts, ring_off, nullptr, n, height, rows, cols, T, q / 100.0, out, n_dev);
+  TD_CHECK_LAUNCH("td_crown_height_summary");
+  return TD_OK;
 }

@@ -10,9 +10,10 @@ building the union.  Forest polygons keep their interior rings (holes).  The ref
 INVALID geometries only (``geom.buffer(0) if not geom.is_valid else geom``, helpers.py:743-750 for
 the outline, :816-821 for the fused crowns): valid geometries pass through untouched, so vertex
 order and count of the fused layer are those of the inputs.  GEOS itself is absent here and its
-repair is not reproduced: invalid rings (self-touching / self-crossing) are COUNTED on the host
-(``ring_is_simple``) and reported with a warning instead (none occur in the synthetic configurations:
-tests/test_gpu_forest.py).
+repair is not reproduced: invalid rings (a mask outline with a one-pixel spur or a diagonal pinch touches
+itself) are COUNTED on the device (``td_ring_is_simple``) and reported with a warning; they are written
+unchanged (about 2 % of the crowns of the synthetic two-model scene, tests/test_gpu_two_model.py).  The
+single-model path of the reference never repairs geometries.
 """
 from __future__ import annotations
 

@@ -353,6 +353,18 @@ def crown_stats(verts, ring_off, ndvi, height, transform6, mode=STATS_COMBINED, 
     return {"max_h": max_h, "hxy": hxy, "ndvi": stats}
 
 
+def crown_height_summary(verts, ring_off, height, transform6, q=95.0, n_dev=None):
+    """Optional nDSM summary per crown (the reference computes the maximum only): (N,4) f32 = [min, mean,
+    percentile q (numpy "linear"), pixel count] over the pixel set of get_height_within_polygon."""
+    n = ring_off.shape[0] - 1
+    _chk(verts, torch.float64, "verts"); _chk(ring_off, torch.int64, "ring_off"); _chk(height, torch.float32, "height")
+    out = torch.empty((n, 4), dtype=torch.float32, device=verts.device)
+    tf = torch.tensor(list(transform6)[:6], dtype=torch.float64)
+    _lib.call("td_crown_height_summary", _ptr(verts), _ptr(ring_off), n, _ptr(height), height.shape[0], height.shape[1],
+              tf.data_ptr(), float(q), _ptr(out), _ptr(n_dev), _stream())
+    return out
+
+
 def centroids(verts, ring_off, n_dev=None):
     n = ring_off.shape[0] - 1
     out = torch.empty((n, 2), dtype=torch.float32, device=verts.device)
