@@ -658,6 +658,35 @@ def run_b200(a):
     if rank == 0 and last_feats and golden_check.golden_matches_workload(a.size, 1234, 2500) and a.ndsm_px in (0.2, 1.0):
         parity = golden_check.check_layer(api.features_to_host(last_feats[-1]), "split" if a.ndsm_px == 0.2 else "combined",
                                           n_candidates=n_cand)
+    # ---- the other nDSM resolution of BASELINE config 2 (1 m: the reference's COMBINED statistics path,
+    # get_metadata_within_polygon), same image, a short run of its own ----
+    combined = None
+    if rank == 0 and world == 1 and a.ndsm_px == 0.2 and not a.no_merged and not a.serial and not a.exact:
+        ndsm1 = torch.from_numpy(synth.make_ndsm(sc.field, 1.0, 1234)).to(dev)
+        tf1 = synth.image_transform(sc.field.left, sc.field.bottom + sc.field.height_m, 1.0)
+        run1, bufs1, ticks = pipeline.ChainRunner(p), {}, []
+
+        def step1():
+            with torch.cuda.stream(p1_stream):
+                tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
+            with torch.cuda.stream(chain_stream):
+                while len(ticks) >= 2:
+                    run1.collect(ticks.pop(0))
+                ticks.append(run1.submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
+                                         lambda: pipeline.raster_stage(d["rgbi"], host.transform, ndsm1, tf1, p, buffers=bufs1)))
+        region_begin()
+        for _ in range(3):
+            step1()
+        region_end()
+        ms1, _ = timed(step1, max(5, a.steps // 2), free_running=True)
+        f1 = None
+        while ticks:
+            n1c, f1 = run1.collect(ticks.pop(0))
+        par1 = golden_check.check_layer(api.features_to_host(f1), "combined", n_candidates=n1c) \
+            if golden_check.golden_matches_workload(a.size, 1234, 2500) else None
+        combined = {"workload": workload_string(a.size, 1.0), "value": sc.area_km2 * max(5, a.steps // 2) / (ms1 / 1e3),
+                    "unit": UNIT, "ms_per_step": ms1 / max(5, a.steps // 2), "crowns": len(f1), "parity": par1}
+        del ndsm1
     p1_ms_in_step = statistics.mean(x.elapsed_time(y) for x, y in p1_ev)
     # the roofline kernel timed alone (CUDA events on its stream, after the timed region): inside the
     # step it shares the GPU with the P2-P9 chain, which says nothing about the kernel itself
@@ -817,6 +846,7 @@ def run_b200(a):
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches,
             "e2e_files": files,
+            "combined_path": combined,
             "parity": parity or "not checked (no golden for this workload size)",
             "clocks": clocks,
             "crowns_merged": merged,

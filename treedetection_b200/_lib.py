@@ -85,9 +85,9 @@ SIGNATURES = {
 OWN_KERNELS = {
     "td_paste_plan": 1, "td_paste_threshold_pack": 1, "td_paste_values": 1, "td_trace_count": 1, "td_trace_emit": 2, "td_trace_walk": 1, "td_trace_rings": 1,
     "td_simplify_rings": 1, "td_take_rings": 1, "td_ndvi_decimate": 1, "td_decimate_f32": 1,
-    "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 2, "td_compact_flags": 1, "td_compact_nonneg": 1,
-    "td_ring_tail": 1, "td_ring_offsets": 0, "td_gather_rows": 1, "td_containment": 4, "td_mask_iou_clean": 5, "td_crown_stats": 1, "td_centroids": 2, "td_crown_height_summary": 1, "td_select_crowns": 2,
-    "td_round_coords": 1, "td_select_head": 2, "td_chain_predict": 13, "td_chain_post": 28, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1, "td_ring_is_simple": 1,
+    "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 1, "td_compact_flags": 1, "td_compact_nonneg": 1,
+    "td_ring_tail": 1, "td_ring_offsets": 1, "td_gather_rows": 1, "td_containment": 4, "td_mask_iou_clean": 5, "td_crown_stats": 1, "td_centroids": 2, "td_crown_height_summary": 1, "td_select_crowns": 2,
+    "td_round_coords": 1, "td_select_head": 1, "td_chain_predict": 14, "td_chain_post": 28, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1, "td_ring_is_simple": 1,
 }
 launch_count = 0
 

@@ -108,42 +108,40 @@ TD_HD inline void lane_init(LaneState<LabelT, Mem>& S, ContourOut* out) {
   S.first_x = S.first_y = S.last_x = S.last_y = 0;
 }
 
-// one micro-step of one lane
+// one step along the current border (mode kFollow)
 template <typename LabelT, typename Mem>
-TD_HD inline void lane_step(LaneState<LabelT, Mem>& S) {
+TD_HD inline void lane_follow_step(LaneState<LabelT, Mem>& S) {
   RasterT<LabelT, Mem>& R = S.R;
-  if (S.mode == kFollow) {
-    // ---- one step along the border ------------------------------------------------------------
-    const int s_end = S.s;
-    const uint32_t m = neighbours(R, S.x3, S.y3);
-    // first foreground neighbour counter-clockwise after s_end: directions s_end+1 .. s_end+8
-    const uint32_t rot = ((m | (m << 8)) >> (s_end + 1)) & 0xffu;
-    const int k = s_end + 1 + ffs32(rot | 0x100u);     // rot != 0: we arrived from a neighbour
-    const int s = k & 7;
-    const int x4 = S.x3 + dir_dx(s), y4 = S.y3 + dir_dy(s);
-    R.mark(S.x3, S.y3, (unsigned)(s - 1) < (unsigned)s_end, S.cc.n_contours);
-    if (s != S.prev_s) {
-      lane_emit(S, S.px, S.py);
-      S.prev_s = s;
-    }
-    S.px += dir_dx(s);
-    S.py += dir_dy(s);
-    if (x4 == S.x0 && y4 == S.y0 && S.x3 == S.x1 && S.y3 == S.y1) {
-      lane_finish_border(S);
-      return;
-    }
-    S.x3 = x4;
-    S.y3 = y4;
-    S.s = (s + 4) & 7;
+  const int s_end = S.s;
+  const uint32_t m = neighbours(R, S.x3, S.y3);
+  // first foreground neighbour counter-clockwise after s_end: directions s_end+1 .. s_end+8
+  const uint32_t rot = ((m | (m << 8)) >> (s_end + 1)) & 0xffu;
+  const int k = s_end + 1 + ffs32(rot | 0x100u);     // rot != 0: we arrived from a neighbour
+  const int s = k & 7;
+  const int x4 = S.x3 + dir_dx(s), y4 = S.y3 + dir_dy(s);
+  R.mark(S.x3, S.y3, (unsigned)(s - 1) < (unsigned)s_end, S.cc.n_contours);
+  if (s != S.prev_s) {
+    lane_emit(S, S.px, S.py);
+    S.prev_s = s;
+  }
+  S.px += dir_dx(s);
+  S.py += dir_dy(s);
+  if (x4 == S.x0 && y4 == S.y0 && S.x3 == S.x1 && S.y3 == S.y1) {
+    lane_finish_border(S);
     return;
   }
-  if (S.mode != kScan) return;
-  // ---- advance the raster scan to the next border start (up to kScanRows rows per micro-step: rows
-  // without a start are the common case and cost one word test each) ---------------------------------
-  for (int scanned = 0; scanned < kScanRows; ++scanned) {
-  const int y = S.y;
-  for (; S.wi < R.wpr; ++S.wi) {
-    const int wi = S.wi;
+  S.x3 = x4;
+  S.y3 = y4;
+  S.s = (s + 4) & 7;
+}
+
+// Scans row y from word wi0 on for the next border start: an unvisited pixel after a 0 (outer border, allowed
+// at x >= min_o) or a pixel without the "right" flag before a 0 (hole border, x >= min_h).  Returns true with
+// the start's column, kind and word.  Reads the planes only: any lane may scan any lane's window.
+template <typename LabelT, typename Mem>
+TD_HD inline bool lane_scan_row(const RasterT<LabelT, Mem>& R, int y, int wi0, int min_o, int min_h, int& x_out,
+                                int& hole_out, int& wi_out) {
+  for (int wi = wi0; wi < R.wpr; ++wi) {
     const uint32_t F = R.word(R.fg, y, wi);
     if (!F) continue;
     const uint32_t Fl = R.word(R.fg, y, wi - 1), Fr = R.word(R.fg, y, wi + 1);
@@ -153,49 +151,73 @@ TD_HD inline void lane_step(LaneState<LabelT, Mem>& S) {
     uint32_t O = F & ~V & ~prevfg;   // unvisited pixel after a 0
     uint32_t H = F & ~N & ~nextfg;   // pixel without the right flag before a 0
     const int base = wi * 32;
-    if (S.min_o > base) O &= (S.min_o - base >= 32) ? 0u : ~((1u << (S.min_o - base)) - 1u);
-    if (S.min_h > base) H &= (S.min_h - base >= 32) ? 0u : ~((1u << (S.min_h - base)) - 1u);
+    if (min_o > base) O &= (min_o - base >= 32) ? 0u : ~((1u << (min_o - base)) - 1u);
+    if (min_h > base) H &= (min_h - base >= 32) ? 0u : ~((1u << (min_h - base)) - 1u);
     if (!(O | H)) continue;
     const int a = O ? ffs32(O) : 64, b = H ? ffs32(H) : 64;
     const bool hole = !(a <= b);
-    const int x = base + (hole ? b : a);
-    if (S.cc.n_contours >= 65534) { S.cc.n_contours = -1; S.mode = kDone; return; }
-    // parent from the label of the last visited pixel on this row (see contour_core.cuh)
-    int parent = -1;
-    if (S.out) {
-      const int ln = R.lnbd(hole ? x + 1 : x, y);
-      if (ln >= 0 && ln < S.out->cap_contours) {
-        parent = ln;
-        if ((S.out->is_hole[ln] != 0) == hole) parent = S.out->parent[ln];
-      }
-    }
-    S.parent = parent;
-    S.hole = hole ? 1 : 0;
-    S.x0 = x; S.y0 = y; S.npts = 0;
-    // first neighbour clockwise from west (outer) / east (hole)
-    const int s_end = hole ? 0 : 4;
-    const uint32_t m = neighbours(R, x, y);
-    // directions s_end - 1, s_end - 2, ... s_end - 7: bit t of the rotated mask is direction s_end + t,
-    // so the first hit clockwise is the HIGHEST set bit among t = 7 .. 1
-    const uint32_t rot = ((m | (m << 8)) >> s_end) & 0xfeu;
-    const bool found = rot != 0u;
-    const int s = found ? ((s_end + highest_bit(rot)) & 7) : s_end;
-    if (!found) {   // isolated pixel (the start pixel's own s_end neighbour is background by construction)
-      R.mark(x, y, true, S.cc.n_contours);
-      lane_emit(S, x, y);
-      lane_finish_border(S);
-      return;                     // stay on this word: more starts may follow
-    }
-    S.x1 = x + dir_dx(s); S.y1 = y + dir_dy(s);
-    S.x3 = x; S.y3 = y;
-    S.s = s; S.prev_s = s ^ 4;
-    S.px = x; S.py = y;
-    S.mode = kFollow;
-    return;
+    x_out = base + (hole ? b : a);
+    hole_out = hole ? 1 : 0;
+    wi_out = wi;
+    return true;
   }
-  // row exhausted
-  S.wi = 0; S.min_o = 0; S.min_h = 0;
-  if (++S.y >= R.h) { S.mode = kDone; return; }
+  return false;
+}
+
+// starts the border found at (x, y): parent from the label plane, first neighbour, isolated pixels
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_begin_border(LaneState<LabelT, Mem>& S, int x, int y, bool hole) {
+  RasterT<LabelT, Mem>& R = S.R;
+  if (S.cc.n_contours >= 65534) { S.cc.n_contours = -1; S.mode = kDone; return; }
+  // parent from the label of the last visited pixel on this row (see contour_core.cuh)
+  int parent = -1;
+  if (S.out) {
+    const int ln = R.lnbd(hole ? x + 1 : x, y);
+    if (ln >= 0 && ln < S.out->cap_contours) {
+      parent = ln;
+      if ((S.out->is_hole[ln] != 0) == hole) parent = S.out->parent[ln];
+    }
+  }
+  S.parent = parent;
+  S.hole = hole ? 1 : 0;
+  S.x0 = x; S.y0 = y; S.npts = 0;
+  // first neighbour clockwise from west (outer) / east (hole)
+  const int s_end = hole ? 0 : 4;
+  const uint32_t m = neighbours(R, x, y);
+  // directions s_end - 1, s_end - 2, ... s_end - 7: bit t of the rotated mask is direction s_end + t,
+  // so the first hit clockwise is the HIGHEST set bit among t = 7 .. 1
+  const uint32_t rot = ((m | (m << 8)) >> s_end) & 0xfeu;
+  const bool found = rot != 0u;
+  const int s = found ? ((s_end + highest_bit(rot)) & 7) : s_end;
+  if (!found) {   // isolated pixel (the start pixel's own s_end neighbour is background by construction)
+    R.mark(x, y, true, S.cc.n_contours);
+    lane_emit(S, x, y);
+    lane_finish_border(S);
+    return;                     // the scan stays on this word: more starts may follow
+  }
+  S.x1 = x + dir_dx(s); S.y1 = y + dir_dy(s);
+  S.x3 = x; S.y3 = y;
+  S.s = s; S.prev_s = s ^ 4;
+  S.px = x; S.py = y;
+  S.mode = kFollow;
+}
+
+// one micro-step of one lane: a step along the border, or the raster scan advanced to the next border start
+// (up to kScanRows rows per micro-step: rows without a start are the common case)
+template <typename LabelT, typename Mem>
+TD_HD inline void lane_step(LaneState<LabelT, Mem>& S) {
+  if (S.mode == kFollow) { lane_follow_step(S); return; }
+  if (S.mode != kScan) return;
+  for (int scanned = 0; scanned < kScanRows; ++scanned) {
+    int x = 0, hole = 0, wi = 0;
+    if (lane_scan_row(S.R, S.y, S.wi, S.min_o, S.min_h, x, hole, wi)) {
+      S.wi = wi;
+      lane_begin_border(S, x, S.y, hole != 0);
+      return;
+    }
+    // row exhausted
+    S.wi = 0; S.min_o = 0; S.min_h = 0;
+    if (++S.y >= S.R.h) { S.mode = kDone; return; }
   }
 }
 

@@ -276,7 +276,51 @@ __device__ __forceinline__ void walk_lanes(td::LaneState<unsigned short, Mem>& S
   out.cap_points = active ? (int)(A.pts_off[i + 1] - p0) : 0;
   if (active) S.R.label = A.labels + A.px_off[i];
   td::lane_init(S, &out);
-  while (__any_sync(0xffffffffu, S.mode != td::kDone)) td::lane_step(S);
+  // Lock-step walk with a COOPERATIVE raster scan.  A lane that looks for its next border start would, on its
+  // own, test one row per micro-step while the lanes that follow a border wait for it (a third of the kernel's
+  // instructions ran with one live lane that way).  Instead the whole warp scans for it: lane k tests row
+  // y + k of that lane's window (the planes of all windows of the warp are in its shared memory), a ballot
+  // picks the first row with a start.  Then every lane that follows a border takes one step.
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned need = __ballot_sync(full, S.mode == td::kScan);
+    if (!need && !__any_sync(full, S.mode == td::kFollow)) break;
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      td::RasterT<unsigned short, Mem> R;
+      R.fg = reinterpret_cast<const uint32_t*>(__shfl_sync(full, (unsigned long long)S.R.fg, src));
+      R.visited = reinterpret_cast<uint32_t*>(__shfl_sync(full, (unsigned long long)S.R.visited, src));
+      R.right = reinterpret_cast<uint32_t*>(__shfl_sync(full, (unsigned long long)S.R.right, src));
+      R.label = nullptr;
+      R.w = __shfl_sync(full, S.R.w, src); R.h = __shfl_sync(full, S.R.h, src); R.wpr = __shfl_sync(full, S.R.wpr, src);
+      const int y0 = __shfl_sync(full, S.y, src), wi0 = __shfl_sync(full, S.wi, src);
+      const int mo = __shfl_sync(full, S.min_o, src), mh = __shfl_sync(full, S.min_h, src);
+      int row = -1, fx = 0, fhole = 0, fwi = 0;
+      for (int base = y0; base < R.h && row < 0; base += 32) {
+        const int yy = base + lane;
+        int x = 0, hole = 0, wi = 0;
+        bool f = false;
+        if (yy < R.h) f = td::lane_scan_row(R, yy, yy == y0 ? wi0 : 0, yy == y0 ? mo : 0, yy == y0 ? mh : 0, x, hole, wi);
+        const unsigned hit = __ballot_sync(full, f);
+        if (hit) {
+          const int l = __ffs(hit) - 1;
+          row = base + l;
+          fx = __shfl_sync(full, x, l); fhole = __shfl_sync(full, hole, l); fwi = __shfl_sync(full, wi, l);
+        }
+      }
+      if (lane == src) {
+        if (row < 0) { S.y = S.R.h; S.mode = td::kDone; }
+        else {
+          if (row != S.y) { S.min_o = 0; S.min_h = 0; }     // a fresh row
+          S.y = row; S.wi = fwi;
+          td::lane_begin_border(S, fx, row, fhole != 0);
+        }
+      }
+    }
+    if (S.mode == td::kFollow) td::lane_follow_step(S);
+  }
   if (!active) return;
   const bool over = S.cc.n_contours < 0 || S.cc.n_contours > out.cap_contours || S.cc.n_points > out.cap_points;
   if (over) atomicOr((unsigned long long*)A.flag, 4ull);

@@ -24,7 +24,8 @@ constexpr int kSmemInts = 5 * kSmemRing + kSmemRing / 32 + 4;   // per warp: res
 
 // one warp per ring: the stack machine runs redundantly on all lanes, the farthest-point
 // and intersection scans are strided over the lanes (td::WarpCoop)
-__global__ void __launch_bounds__(128)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(64, kMinBlocks)
 simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
                 int* __restrict__ scratch, uint32_t* __restrict__ alive, const double* __restrict__ boxes,
                 const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
@@ -160,9 +161,20 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
   TD_ARG((boxes == nullptr) == (ring_box == nullptr));
   static int bs = 0;
   if (bs == 0) { const char* e = getenv("TREEDET_SIMPLIFY_BLOCK"); bs = e && atoi(e) > 0 ? atoi(e) : 64; }
-  simplify_kernel<<<td_div_up((long long)n_rings * 32, bs), bs, sizeof(int) * (bs / 32) * kSmemInts, (cudaStream_t)stream>>>(
-      verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box, out_count, out_bounds, out_area, out_keep,
-      bounds_of_input, n_dev);
+  // residency: 10 (96 registers), 12 (80, default: ~2 % faster in the chain) or 16 (64, spills: slower) CTAs of 2 warps per SM
+  static int mb = 0;
+  if (mb == 0) { const char* e = getenv("TREEDET_SIMPLIFY_MINBLOCKS"); mb = e && atoi(e) > 0 ? atoi(e) : 12; }
+  if (bs > 64) bs = 64;
+  const dim3 grid(td_div_up((long long)n_rings * 32, bs));
+  const size_t smem = sizeof(int) * (bs / 32) * kSmemInts;
+  cudaStream_t st = (cudaStream_t)stream;
+#define TD_SIMPLIFY_LAUNCH(MB)                                                                                          \
+  simplify_kernel<MB><<<grid, bs, smem, st>>>(verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box,   \
+                                              out_count, out_bounds, out_area, out_keep, bounds_of_input, n_dev)
+  if (mb >= 16) TD_SIMPLIFY_LAUNCH(16);
+  else if (mb >= 12) TD_SIMPLIFY_LAUNCH(12);
+  else TD_SIMPLIFY_LAUNCH(10);
+#undef TD_SIMPLIFY_LAUNCH
   TD_CHECK_LAUNCH("td_simplify_rings");
   return TD_OK;
 }

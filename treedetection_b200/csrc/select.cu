@@ -94,6 +94,44 @@ __global__ void head_flags_kernel(const double* __restrict__ conf, const double*
   flags[i] = (ok && area[i] >= area_min && area[i] <= area_max) ? 1 : 0;
 }
 
+// single-block form of the head (flags + rank scan + poly_id) for small tables (<= 8192 rows): one launch
+__global__ void __launch_bounds__(1024)
+select_head_block_kernel(const double* __restrict__ conf, const double* __restrict__ area, int n,
+                         const long long* __restrict__ n_dev, double conf_thr, double area_min, double area_max,
+                         unsigned char* __restrict__ flags, long long* __restrict__ poly_id) {
+  __shared__ long long s_warp[32];
+  const int live = n_dev ? (int)min((long long)n, *n_dev) : n;
+  const int chunk = (n + 1023) / 1024;
+  const int lo = min((int)threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+  long long mine = 0;
+  for (int i = lo; i < hi; ++i) mine += (i < live && conf[i] >= conf_thr) ? 1 : 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const long long w = s_warp[lane];
+    long long wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;
+  }
+  __syncthreads();
+  long long run = s_warp[warp] + incl - mine;
+  for (int i = lo; i < hi; ++i) {
+    const bool ok = i < live && conf[i] >= conf_thr;
+    poly_id[i] = run;
+    flags[i] = (ok && area[i] >= area_min && area[i] <= area_max) ? 1 : 0;
+    run += ok ? 1 : 0;
+  }
+}
+
 __global__ void widen_kernel(const int* __restrict__ in, int n, long long* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
@@ -170,6 +208,11 @@ extern "C" int td_select_head(const double* conf, const double* area, int n, con
   if (n == 0) return TD_OK;
   TD_ARG(conf && area && flags && poly_id);
   cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 8192) {
+    select_head_block_kernel<<<1, 1024, 0, st>>>(conf, area, n, n_dev, conf_thr, area_min, area_max, flags, poly_id);
+    TD_CHECK_LAUNCH("td_select_head");
+    return TD_OK;
+  }
   td_ensure_pool();
   int* ok = nullptr;
   int* rank = nullptr;
