@@ -208,3 +208,27 @@ def test_full_size_config2_equals_oracle_golden(dev, big, variant, ndsm_px):
         n, f = run.collect(run.submit(det, tables.tile_tf, tables.tile_boxes, rasters))
         golden_check.check_layer(api.features_to_host(f), variant, n_candidates=n)
     assert run.fallbacks == 0
+
+
+def test_config4_dense_merge_at_bench_scale(dev):
+    """the ``crowns_merged`` workload of bench.py (dense-forest stress, ~2,000 crowns per 50 m tile) at 200 000 crowns
+    against the oracle's sparse NMS (itself equal to the reference-pinned dense form up to 8 000, above) and the
+    chunked containment"""
+    rng = np.random.default_rng(4)
+    n = 200_000
+    cx, cy = 412000 + rng.uniform(0, 500.0, n), 5318000 + rng.uniform(0, 500.0, n)
+    rx = rng.uniform(0.5, 2.0, n); ry = rx * rng.uniform(0.8, 1.25, n)
+    bounds = np.stack([cx - rx, cy - ry, cx + rx, cy + ry], 1)
+    conf = np.round(rng.uniform(0.3, 1.0, n), 3)
+    area = np.pi * rx * ry
+    removed = ops.bbox_nms_ordered(torch.from_numpy(bounds).to(dev), torch.from_numpy(conf).to(dev),
+                                   torch.from_numpy(area).to(dev), 0.6, 1.0).cpu().numpy().astype(bool)
+    ref = port.nms_bbox_sparse(bounds, conf, area, 0.6, 1.0)
+    assert ref.sum() > 5000
+    np.testing.assert_array_equal(removed, ref)
+    sub = bounds[:40_000].astype(np.float32)
+    ratio, isc, num = ops.containment(torch.from_numpy(sub).to(dev), 0.75)
+    r_ref, isc_ref, num_ref = port.containment_chunked(sub, 0.75, chunk=256)
+    np.testing.assert_array_equal(isc.cpu().numpy().astype(bool), isc_ref)
+    np.testing.assert_array_equal(num.cpu().numpy(), num_ref)
+    np.testing.assert_array_equal(ratio.cpu().numpy(), r_ref)

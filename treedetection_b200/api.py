@@ -103,6 +103,21 @@ def features_to_host(f: pipeline.Features):
 
 
 _copy_streams = {}
+_staging = {}
+
+
+def _device_buffer(device, name, like: torch.Tensor):
+    """A persistent device buffer for the host tensor ``like`` (capacity grows by 1.25x; the view handed out has
+    ``like``'s shape).  Keeping the inputs of successive images at the same addresses is what lets td_chain_*
+    replay the CUDA graphs it captured for the previous image instead of capturing new ones."""
+    key = (torch.device(device).index, name, like.dtype, tuple(like.shape[1:]))
+    buf = _staging.get(key)
+    rows = like.shape[0] if like.dim() else 1
+    if buf is None or buf.shape[0] < rows:
+        cap = max(int(rows * 1.25), 1)
+        buf = torch.empty((cap,) + tuple(like.shape[1:]), dtype=like.dtype, device=device)
+        _staging[key] = buf
+    return buf[:rows]
 
 
 def _copy_stream(device):
@@ -141,16 +156,23 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     main = torch.cuda.current_stream(device)
     cs = _copy_stream(device)
     cs.wait_stream(main)
+    persistent = runner is not None         # images of one runner share a tiling: stage them at fixed addresses
+    def h2d(name, t):
+        if not persistent:
+            return t.to(device, non_blocking=True)
+        dst = _device_buffer(device, name, t)
+        dst.copy_(t, non_blocking=True)
+        return dst
     with torch.cuda.stream(cs):
-        det = {k: getattr(img, k).to(device, non_blocking=True) for k in
-               ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
+        det = {k: h2d(k, getattr(img, k)) for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
         ev_det = cs.record_event()
-        rgbi = img.rgbi.to(device, non_blocking=True)
+        rgbi = h2d("rgbi", img.rgbi)
         ev_rgbi = cs.record_event()
-        ndsm = img.ndsm.to(device, non_blocking=True)
+        ndsm = h2d("ndsm", img.ndsm)
         ev_ndsm = cs.record_event()
-    for t in (*det.values(), rgbi, ndsm):
-        t.record_stream(main)
+    if not persistent:
+        for t in (*det.values(), rgbi, ndsm):
+            t.record_stream(main)
     main.wait_event(ev_det)
     tiles_out = None
 
@@ -167,7 +189,8 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
         decimated = (int(h * params.height_scaling_factor), int(w * params.height_scaling_factor)) != (h, w)
         if decimated:
             main.wait_event(ev_ndsm)
-        r = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params)
+        r = pipeline.raster_stage(rgbi, img.transform, ndsm, img.ndsm_transform, params,
+                                  buffers=_raster_buffers(device) if persistent else None)
         r["height_ready"] = None if decimated else ev_ndsm
         return r
 
@@ -189,6 +212,11 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
 
 
 _p1_streams = {}
+_p5_buffers = {}
+
+
+def _raster_buffers(device):
+    return _p5_buffers.setdefault(torch.device(device).index, {})
 
 
 def _p1_stream(device):

@@ -237,6 +237,7 @@ class _FastPath:
     def _load(self, fp, tiles_path, parity):
         """decode one image's rasters into pinned staging buffers (runs on the loader thread)"""
         t0 = time.time()
+        torch.cuda.set_device(self.dev)              # the pinned staging buffers belong to this device's context
         stem = Path(fp).stem
         with open(os.path.join(tiles_path, stem + ".json")) as f:
             tiles = json.load(f)

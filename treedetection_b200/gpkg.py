@@ -102,14 +102,38 @@ def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=
         cur.execute("INSERT INTO gpkg_geometry_columns VALUES (?,?,?,?,?,?)", (layer, "geom", "POLYGON", epsg, 0, 0))
         names = list(schema.keys())
         conv = {"float": float, "int": int, "str": str}
-        data = []
-        for i in range(n):
-            ring = verts[ring_off[i]:ring_off[i + 1]]
-            rec = [_gpb_polygon(ring, epsg)]
-            for k in names:
-                v = columns[k][i]
-                rec.append(None if v is None else conv[schema[k]](v))
-            data.append(rec)
+        # geometry blobs: header | envelope | WKB polygon header | coordinates, cut from ONE byte string of all
+        # coordinates and vectorised envelopes (a layer has tens of thousands of crowns)
+        coords = np.ascontiguousarray(verts, dtype="<f8").tobytes()
+        lens = np.diff(ring_off)
+        blobs = []
+        if n:
+            safe = np.minimum(ring_off[:-1], max(len(verts) - 1, 0))
+            if len(verts):
+                env = np.stack([np.minimum.reduceat(verts[:, 0], safe), np.maximum.reduceat(verts[:, 0], safe),
+                                np.minimum.reduceat(verts[:, 1], safe), np.maximum.reduceat(verts[:, 1], safe)], 1)
+            else:
+                env = np.zeros((n, 4))
+            env_b = np.ascontiguousarray(env, dtype="<f8").tobytes()
+            head = b"GP\x00" + bytes([0x03]) + struct.pack("<i", epsg)
+            empty = _gpb_polygon(np.zeros((0, 2)), epsg)
+            wkb_head = {}
+            for i in range(n):
+                k = int(lens[i])
+                if k == 0:
+                    blobs.append(empty)
+                    continue
+                wh = wkb_head.get(k)
+                if wh is None:
+                    wh = wkb_head[k] = struct.pack("<BIII", 1, 3, 1, k)
+                o = int(ring_off[i])
+                blobs.append(b"".join((head, env_b[32 * i:32 * i + 32], wh, coords[16 * o:16 * (o + k)])))
+        cols = []
+        for k in names:
+            c, f = columns[k], conv[schema[k]]
+            c = c.tolist() if isinstance(c, np.ndarray) else list(c)
+            cols.append([None if v is None else f(v) for v in c])
+        data = list(zip(blobs, *cols)) if names else [(b,) for b in blobs]
         ph = ",".join("?" * (1 + len(names)))
         colnames = ", ".join(["geom"] + [f'"{k}"' for k in names])
         cur.executemany(f'INSERT INTO "{layer}" ({colnames}) VALUES ({ph})', data)
