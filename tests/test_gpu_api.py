@@ -206,3 +206,29 @@ def test_exclude_files_remove_crowns_within_the_outline(tmp_path, dev):
     np.testing.assert_array_equal(v2, np.concatenate([v[o[k]:o[k + 1]] for k in keep]))
     assert cols2["poly_id"] == [cols["poly_id"][k] for k in keep]
     assert cols2["TreeHeight"] == [cols["TreeHeight"][k] for k in keep]
+
+
+def test_non_zero_device_index(tmp_path):
+    """``device: "1"`` in config.yml: every entry point makes that GPU current, so tensors, streams and the library's
+    scratch all live there.  Needs two GPUs; the layers must equal those of a run on device 0."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    layers = {}
+    for dev_index in ("0", "1"):
+        root = tmp_path / f"dev{dev_index}"
+        root.mkdir()
+        cfg_path, field, _ = _project(root)
+        config, _ = detection.get_config(cfg_path)
+        config["device"] = dev_index
+        config["predictor"] = _FieldPredictor(field)
+        detection.process_files(config)
+        out = config["output_directory"]
+        layers[dev_index] = {n: gpkg.read_layer(os.path.join(out, n)) for n in sorted(os.listdir(out)) if n.endswith(".gpkg")}
+    assert torch.cuda.current_device() == 0                  # the guard restores the caller's device
+    a, b = layers["0"], layers["1"]
+    assert sorted(a) == sorted(b) and len(a) == 3
+    for name in a:
+        np.testing.assert_array_equal(a[name][0], b[name][0], err_msg=name)
+        np.testing.assert_array_equal(a[name][1], b[name][1], err_msg=name)
+        assert a[name][2] == b[name][2], name

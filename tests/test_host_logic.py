@@ -186,3 +186,31 @@ def test_prediction_and_stitching_ledgers_follow_the_reference(tmp_path):
     assert files[2] in load()
     os.remove(stitched / "img1.gpkg")
     assert files[0] not in load()                        # the stitched layer itself is gone
+
+
+def test_fixture_predictor_fails_loudly(tmp_path):
+    """a missing fixture must not turn into a silently empty crown layer (and a ledger entry that makes resumed runs
+    skip the image); malformed fixtures are refused before anything reaches the device"""
+    from treedetection_b200 import predictor
+    tf = synth.image_transform(412000.0, 5318100.0, 0.2)
+    tiles = tiling.tile_grid("img", tf, 500, 500, 25832, 50, 50, 20)
+    model = tmp_path / "model"
+    model.mkdir()
+    fp = predictor.FixturePredictor(str(model))
+    with pytest.raises(FileNotFoundError):
+        fp.raw_outputs("img", tiles)
+    det = predictor.FixturePredictor(str(model), allow_missing=True).raw_outputs("img", tiles)       # explicit opt-in
+    assert len(det.scores) == 0 and det.tile_dims.shape == (len(tiles), 4)
+    n, ids = 5, np.array(list(tiles))
+    good = dict(boxes_net=np.zeros((n, 4), np.float32), scores=np.full(n, 0.5, np.float32),
+                probs=np.zeros((n, 28, 28), np.float32), inst_tile=np.array([0, 0, 1, 2, 2], np.int32), tile_ids=ids)
+    np.savez(model / "img.npz", **good)
+    assert len(fp.raw_outputs("img", tiles).scores) == n
+    for bad in (dict(inst_tile=np.array([0, 0, 1, 2, len(ids)], np.int32)),       # tile index out of range
+                dict(inst_tile=np.array([0, 0, -1, 2, 2], np.int32)),
+                dict(inst_tile=np.array([0, 2, 1, 2, 2], np.int32)),              # not tile-major
+                dict(scores=np.zeros(n - 1, np.float32)),                        # lengths disagree
+                dict(probs=np.zeros((n, 14, 14), np.float32))):
+        np.savez(model / "img.npz", **{**good, **bad})
+        with pytest.raises(ValueError):
+            fp.raw_outputs("img", tiles)
