@@ -53,7 +53,14 @@ def parse():
                     help="BASELINE.json config: 2 = single model 10k x 10k (the headline), 3 = two models + forest outline "
                          "on a 20k x 20k mosaic (one extra line, 1 GPU)")
     ap.add_argument("--no-files", action="store_true", help="skip e2e_files (process_files on GeoTIFFs on tmpfs)")
-    ap.add_argument("--files-images", type=int, default=3, help="images of the workload in e2e_files")
+    ap.add_argument("--files-only", action="store_true", help="diagnostic: run e2e_files alone and print its entry")
+    ap.add_argument("--files-images", type=int, default=6, help="images of the workload in e2e_files")
+    ap.add_argument("--chains", type=int, default=2,
+                    help="independent chain contexts (workspace + stream + graphs each) that consecutive images "
+                         "alternate between: the P2-P9 chain of an image is a latency-bound sequence of dependent "
+                         "launches, two images' chains side by side fill the gaps of each other")
+    ap.add_argument("--p1-priority", type=int, default=0, help="stream priority of P1 (0 or -1)")
+    ap.add_argument("--chain-priority", type=int, default=-1, help="stream priority of the chain contexts (0 or -1)")
     ap.add_argument("--join-steps", action="store_true",
                     help="join all streams after every image (default: the streams run free between the two ends of "
                          "the timed region; images are independent)")
@@ -279,14 +286,27 @@ def e2e_files(sc, n_images, label):
             parity = (f"the output layer of image 0 equals the CPU oracle's golden (ids, areas, heights, centroids, "
                       f"containment columns, vertices); the {len(layers) - 1} shifted copies have the same crown count")
         area = n_images * H * W * px * px / 1e6
+        tl = stats.get("timeline", [])
+        steady = None
+        if len(tl) >= 3:
+            # images after the first (which allocates the staging buffers, builds the tile tables and learns the
+            # capacities through the exact-size path): what a long file list converges to
+            # (the second image's decode hides behind the first image's cold start: counted from the second on)
+            k0 = 1 if len(tl) >= 4 else 0
+            per_image = (tl[-1]["t_out"] - tl[k0]["t_out"]) / (len(tl) - 1 - k0)
+            steady = {"s_per_image": round(per_image, 4), "value": (area / n_images) / per_image, "unit": UNIT,
+                      "first_image_s": round(tl[0]["t_out"] - stats.get("t0", tl[0]["t_in"]), 3),
+                      "per_image_s": {k: round(statistics.mean(t[k] for t in tl[k0 + 1:]), 4)
+                                      for k in ("wait_decode_s", "decode_s", "fixtures_s", "tables_s", "device_s")}}
         return {"workload": label, "images": n_images, "value": area / wall, "unit": UNIT, "wall_s": wall,
+                "steady_state": steady,
                 "stage_s": {k: round(v, 3) for k, v in stats.get("stage_s", {}).items()},
                 "fast_path_images": stats.get("images"), "fallback_images": stats.get("fallback_images"),
                 "crowns_per_image": n_crowns, "parity": parity,
                 "input_bytes": int(n_images * (sc.rgbi.nbytes + sc.ndsm.nbytes)),
                 "note": f"GeoTIFFs uncompressed on {'tmpfs (/dev/shm)' if base else 'the default temp dir'} (written in "
                         f"{write_s:.1f} s, not timed); timed: get tiles -> read + decode rasters and fixtures -> H2D -> P1 "
-                        f"+ P2-P9 -> D2H -> stitched, processed and final .gpkg written; the first image of a tiling "
+                        f"+ P2-P9 -> D2H -> stitched, processed and final .gpkg written (decoder thread | device | writer thread); the first image of a tiling "
                         f"learns the capacities (exact-size path), the others replay the CUDA graphs"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
@@ -368,6 +388,9 @@ def run_b200(a):
     # row-sharded mosaic: rank r owns the image of row r (its own seed / georeference)
     sc = synth.make_scene(seed=1234 + rank, size_px=a.size, px=0.2, ndsm_px=a.ndsm_px, density_per_km2=2500.0,
                           bottom=synth.ORIGIN_Y - rank * a.size * 0.2, stem=f"FDOP20_{rank:06d}_rgbi")
+    if a.files_only:
+        print(json.dumps(e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px))))
+        return
     host = api.HostImage.from_scene(sc)
     tables = api.TileTables(sc.tiles, dev, p.shift)
     p1_out = torch.empty((tables.p1_floats,), dtype=torch.float32, device=dev)
@@ -432,7 +455,10 @@ def run_b200(a):
                           ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}}
 
     det_keys = ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")
-    runner = pipeline.ChainRunner(p)           # P2-P9 without host synchronisation (capacity buffers)
+    # P2-P9 without host synchronisation (capacity workspace); consecutive images alternate between the contexts
+    runners = [pipeline.ChainRunner(p) for _ in range(max(1, a.chains))]
+    runner = runners[0]
+    img_seq = [0]
     strip_runner = pipeline.ChainRunner(p)
     rstrip_runner = pipeline.ChainRunner(p)
     pending = []                               # tickets of enqueued images / strips, oldest first
@@ -443,7 +469,7 @@ def run_b200(a):
         while sum(1 for q, _ in pending if q is r) >= MAX_IN_FLIGHT:
             q, t = pending.pop(0)
             n_c, f = q.collect(t)
-            if q is runner:
+            if q in runners:
                 results.append((n_c, len(f)))
 
     def step_rstrip():
@@ -493,13 +519,16 @@ def run_b200(a):
 
     # P1 (HBM bound, feeds the predictor) and the P2-P9 chain (latency bound, consumes the
     # predictor's outputs) are independent: P1 rides its own stream, the chain a high-priority one
-    p1_stream = torch.cuda.Stream(device=dev)
-    chain_stream = torch.cuda.Stream(device=dev, priority=-1)
+    p1_stream = torch.cuda.Stream(device=dev, priority=a.p1_priority)
+    chain_streams = [torch.cuda.Stream(device=dev, priority=a.chain_priority) for _ in runners]
+    chain_stream = chain_streams[0]
     strip_stream = torch.cuda.Stream(device=dev, priority=-1)   # N > 1: the seam strip, next to the image
     p5_stream = torch.cuda.Stream(device=dev)
     pre_rasters = []
     p5_ev = []
-    p5_bufs = [{}, {}, {}]     # NDVI output rasters, rotated (two steps are in flight at most)
+    # NDVI / height output rasters, rotated with the (chain context, output slot) an image lands in, so that every
+    # context replays ONE graph per slot (a graph's key includes the raster addresses)
+    p5_bufs = [{} for _ in range(4 * len(runners))]
     p5_seq = [0]
 
     def chain(e):
@@ -521,12 +550,12 @@ def run_b200(a):
             if name in marks:
                 marks[name].record()
         pre = pre_rasters.pop() if pre_rasters else None
-        return runner.submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
+        return runners[img_seq[0] % len(runners)].submit({k: d[k] for k in det_keys}, tables.tile_tf, tables.tile_boxes,
                              (lambda: pre) if pre is not None else
                              (lambda: pipeline.raster_stage(d["rgbi"], host.transform, d["ndsm"], host.ndsm_transform, p)),
                              mark=mark)
 
-    side_streams = (p1_stream, chain_stream, strip_stream, p5_stream)
+    side_streams = (p1_stream, *chain_streams, strip_stream, p5_stream)
     p5_guard = [None] * len(p5_bufs)           # chain event after which a P5 output buffer may be overwritten
 
     def region_begin():
@@ -548,7 +577,9 @@ def run_b200(a):
         for m in range(M):
             e = [ev() for _ in range(6)]
             t = ts = tr = None
-            make_room(runner)
+            img_seq[0] += 1
+            cur, cur_stream = runners[img_seq[0] % len(runners)], chain_streams[img_seq[0] % len(runners)]
+            make_room(cur)
             if a.serial:
                 e[0].record()
                 tables.plan(d["rgbi"]).run(d["rgbi"], p1_out)
@@ -591,15 +622,15 @@ def run_b200(a):
                     make_room(rstrip_runner)
                     with torch.cuda.stream(strip_stream):
                         tr = step_rstrip()
-                with torch.cuda.stream(chain_stream):
+                with torch.cuda.stream(cur_stream):
                     t = chain(e)
                     if not a.exact:
-                        p5_guard[p5_seq[0] % len(p5_bufs)] = chain_stream.record_event()
+                        p5_guard[p5_seq[0] % len(p5_bufs)] = cur_stream.record_event()
                 if a.join_steps:
                     region_end()
             p1_ev.append((e[0], e[1]))
             stage_ev.append(e)
-            for q, tk in ((runner, t), (strip_runner, ts), (rstrip_runner, tr)):
+            for q, tk in ((cur, t), (strip_runner, ts), (rstrip_runner, tr)):
                 if tk is not None:
                     pending.append((q, tk))
 
@@ -609,7 +640,7 @@ def run_b200(a):
         while pending:
             r, t = pending.pop(0)
             n_c, f = r.collect(t)
-            if r is runner:
+            if r in runners:
                 results.append((n_c, len(f)))
                 last_feats[:] = [f]
 
@@ -638,8 +669,11 @@ def run_b200(a):
             ms = float(t.item())
         return ms, out
 
+    # setup, untimed: every chain context learns its capacities from one exact-size image and captures the two
+    # graphs of each of its 4 output slots; then the W warm-up steps
+    priming = 0 if a.exact else -(-5 * len(runners) // M)
     region_begin()
-    for _ in range(a.warmup):
+    for _ in range(priming + a.warmup):
         step_resident()
     region_end()
     drain()
@@ -709,7 +743,9 @@ def run_b200(a):
     pairs = [(0, 1), (2, 3), (3, 4), (4, 5)]
     chain_mode = "exact sizes (host sync before every allocation)" if a.exact else \
         f"td_chain (capacity workspace, device-side counts, {'CUDA-graph replay' if runner.use_graph else 'direct launches'}; " \
-        f"exact-size fallbacks incl. warm-up: image {runner.fallbacks}, seam strip {strip_runner.fallbacks})"
+        f"{len(runners)} chain contexts that consecutive images alternate between; exact-size fallbacks incl. warm-up: " \
+        f"image {sum(r.fallbacks for r in runners)}, seam strip {strip_runner.fallbacks}; {priming} untimed priming steps " \
+        f"(capacity learning + graph capture) before the warm-up)"
     stage_ms = {n: statistics.mean(e[i].elapsed_time(e[j]) for e in stage_ev) for (i, j), n in zip(pairs, names)}
     p1_ms_in_step = stage_ms[names[0]]
     if p5_ev:      # P5 ran on its own stream
@@ -830,7 +866,7 @@ def run_b200(a):
                                    "P1 and P5 on their own streams concurrent with the P2-P4 / P6-P9 chain (high-priority stream); "
                                    + ("all streams joined after every image; " if a.join_steps else
                                       "streams run free between the two ends of the timed region (images are independent; the "
-                                      "host stays <= 2 images ahead); ") +
+                                      "host stays <= 3 images ahead per chain context); ") +
                                    "stage_ms are per-stream CUDA-event times and overlap"),
                        "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
                        "cache": "inputs (rasters 0.8 GB, P1 output 12 GB) exceed the 126 MB L2; no flush needed",

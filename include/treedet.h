@@ -313,6 +313,19 @@ int td_seam_crop(const void* a, const void* b, int elem_size, int bands, int ha,
  * section 13); returns the bytes written to dst (<= cap) or a negative TD_ERR_* code.            */
 long long td_tiff_lzw_decode(const unsigned char* src, long long n_src, unsigned char* dst, long long cap);
 
+/* ---- N2: GeoPackage feature writer (HOST function, host pointers) ----------------------------------
+ * Replaces the row loop of GeoDataFrame.to_file(driver="GPKG") behind the stitched layer
+ * (TreeDetection/helpers.py:592-599) and the processed layer (postprocessing.py:903-936): appends n_rings
+ * polygon features (GeoPackageBinary: header, envelope, WKB polygon with one ring) to table `layer` of an
+ * existing GeoPackage inside one transaction.
+ *   verts (V,2) f64, ring_off (n_rings + 1) i64;
+ *   col_types[c]: 0 = float64 array (NaN -> NULL), 1 = int64 array, 2 = text (col_data[c] = UTF-8 bytes,
+ *   col_text_off[c] = n_rings + 1 byte offsets).  SQLite is loaded with dlopen("libsqlite3.so.0"):
+ *   TD_ERR_UNSUPPORTED when it is not there.                                                          */
+int td_gpkg_append(const char* path, const char* layer, int epsg, const double* verts, const long long* ring_off,
+                   long long n_rings, int n_cols, const char* const* col_names, const int* col_types,
+                   const void* const* col_data, const long long* const* col_text_off);
+
 #ifdef __cplusplus
 }
 #endif

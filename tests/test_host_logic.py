@@ -118,6 +118,44 @@ def test_gpkg_round_trip(tmp_path):
     np.testing.assert_array_equal(np.asarray(c2["Confidence_score"], dtype=np.float64), cols["Confidence_score"])
 
 
+def test_gpkg_native_writer_writes_the_same_rows(tmp_path):
+    """td_gpkg_append (csrc/gpkgio.cu) against the Python row loop: every column of every row of the processed
+    schema, an empty ring, a NaN (NULL) and non-ASCII text"""
+    import sqlite3
+    rng = np.random.default_rng(3)
+    n = 500
+    lens = rng.integers(4, 40, n)
+    lens[7] = 0
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    verts = 412000 + rng.uniform(0, 1000, (int(off[-1]), 2))
+    conf = rng.random(n)
+    conf[3] = np.nan
+    cols = {"Confidence_score": conf, "poly_id": [str(i) for i in range(n)], "Area": rng.random(n),
+            "TreeHeight": rng.random(n).astype(np.float32), "Centroid": [f'{{"x": {i}.5, "y": "\u00e4"}}' for i in range(n)],
+            "Diameter": [float(i) for i in range(n)], "is_contained": [str(bool(i & 1)) for i in range(n)],
+            "num_contained": rng.integers(0, 9, n).astype(np.int32)}
+    a, b = str(tmp_path / "a.gpkg"), str(tmp_path / "b.gpkg")
+    gpkg.write_layer(a, "x", verts, off, cols, gpkg.PROCESSED_SCHEMA, epsg=25832, native=True)
+    gpkg.write_layer(b, "x", verts, off, cols, gpkg.PROCESSED_SCHEMA, epsg=25832, native=False)
+
+    def rows(p):
+        con = sqlite3.connect(p)
+        try:
+            return (con.execute('SELECT * FROM "x" ORDER BY fid').fetchall(),
+                    con.execute("SELECT table_name, min_x, min_y, max_x, max_y, srs_id FROM gpkg_contents").fetchall(),
+                    con.execute("SELECT * FROM gpkg_geometry_columns").fetchall())
+        finally:
+            con.close()
+    ra, rb = rows(a), rows(b)
+    assert len(ra[0]) == n and ra == rb
+    assert ra[0][3][2] is None            # NaN -> NULL on both routes
+    v2, o2, c2 = gpkg.read_layer(a)[:3]
+    np.testing.assert_array_equal(v2, verts)
+    np.testing.assert_array_equal(o2, off)
+    assert c2["Centroid"] == cols["Centroid"]
+
+
 def test_geotiff_round_trip_with_geo_tags(tmp_path):
     rng = np.random.default_rng(1)
     arr = rng.integers(0, 255, (4, 37, 53), dtype=np.uint8)

@@ -76,6 +76,8 @@ SIGNATURES = {
     "td_chain_post": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p]),
     # N1 (host function)
     "td_tiff_lzw_decode": (_ll, [_p, _ll, _p, _ll]),
+    # N2 (host function)
+    "td_gpkg_append": (_i, [C.c_char_p, C.c_char_p, _i, _p, _p, _ll, _i, _p, _p, _p, _p]),
     # P0a
     "td_seam_crop": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
@@ -142,3 +144,15 @@ def call(name: str, *args):
     fn = getattr(lib(), name)
     check(fn(*args), name)
     launch_count += OWN_KERNELS.get(name, 0)
+
+
+_cuda_ok = None
+
+
+def cuda_available():
+    """``torch.cuda.is_available()`` asked once per process (every call costs a driver round trip of ~20 ms)"""
+    global _cuda_ok
+    if _cuda_ok is None:
+        import torch
+        _cuda_ok = bool(torch.cuda.is_available())
+    return _cuda_ok

@@ -34,7 +34,7 @@ class HostImage:
     def from_scene(cls, sc, pin=True):
         def t(a):
             x = torch.from_numpy(np.ascontiguousarray(a))
-            return x.pin_memory() if pin and torch.cuda.is_available() else x
+            return x.pin_memory() if pin and _lib.cuda_available() else x
         d = sc.det
         return cls(t(sc.rgbi), sc.transform, t(sc.ndsm), sc.ndsm_transform, sc.tiles, t(d.boxes_net), t(d.scores),
                    t(d.probs), t(d.inst_tile), t(d.tile_dims))
@@ -85,7 +85,7 @@ def _pinned_like(name, t):
     memory costs more than the copy it serves)."""
     buf = _pinned.get(name)
     if buf is None or buf.dtype != t.dtype or buf.numel() < t.numel():
-        buf = torch.empty((max(int(t.numel() * 1.25), 1024),), dtype=t.dtype).pin_memory()
+        buf = torch.empty((max(int(t.numel() * 1.25), 1024),), dtype=t.dtype, pin_memory=True)
         _pinned[name] = buf
     return buf[:t.numel()].view(t.shape)
 
@@ -150,7 +150,7 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     (ROI-head outputs, RGBI, nDSM) and the compute streams wait on one event per group: P2-P4
     overlap the RGBI copy, P1 (own stream), P5 and the statistics-free part of P6-P9 overlap the
     nDSM copy; only the per-crown statistics wait for the nDSM."""
-    if not torch.cuda.is_available():
+    if not _lib.cuda_available():
         raise _lib.TreedetError("run_image needs a CUDA device (there is no CPU fallback)")
     tables = tables or TileTables(img.tiles, device, params.shift)
     main = torch.cuda.current_stream(device)

@@ -91,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(log)
     link_digest = _digest(objs)
     if rebuilt or force or not os.path.exists(LIB) or not os.path.exists(stamp) or open(stamp).read() != link_digest:
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

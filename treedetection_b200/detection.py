@@ -36,6 +36,17 @@ from .merging import merge_and_crop_images
 from .predictor import FixturePredictor
 
 
+def _yaml_dump(data, f):
+    """``yaml.safe_dump`` through libyaml when PyYAML was built with it (same bytes, ~7x faster: a prediction ledger
+    lists every tile id of every image)"""
+    dumper = getattr(yaml, "CSafeDumper", yaml.SafeDumper)
+    yaml.dump(data, f, Dumper=dumper, sort_keys=False)
+
+
+def _yaml_load(f):
+    return yaml.load(f, Loader=getattr(yaml, "CSafeLoader", yaml.SafeLoader))
+
+
 class _Session:
     """Device-side state shared by the stages of ONE ``process_files`` call (the fast path)."""
 
@@ -44,7 +55,9 @@ class _Session:
         self.runners = {}          # tiling key -> pipeline.ChainRunner (capacities + CUDA graphs per tiling)
         self.tables = {}           # tiling key -> (api.TileTables, reusable P1 output buffer)
         self.pinned = {}           # (name, shape, dtype, parity) -> pinned staging tensor
-        self.loader = None         # background decoder of the NEXT image's rasters
+        self.loader = None         # background decoder of the NEXT image's rasters and fixtures
+        self.writer = None         # background writer of the PREVIOUS image's crown layers
+        self.timeline = []         # per image: seconds waited for the decoder, on the device, ... (bench.py e2e_files)
         self.stage_s = {}          # wall seconds per stage (read by bench.py's e2e_files)
         self.images = 0
         self.fallback_images = 0   # images that went through the stage-by-stage path
@@ -54,20 +67,43 @@ class _Session:
         t = self.pinned.get(key)
         if t is None:
             tdt = {"|u1": torch.uint8, "<f4": torch.float32, "<u2": torch.int16, "<i2": torch.int16}[np.dtype(dtype).str]
-            t = torch.empty(tuple(shape), dtype=tdt).pin_memory()
+            t = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
             self.pinned[key] = t
         return t
 
+    def pinned_copy(self, name, array, parity):
+        """``array`` (host numpy) copied into a pinned staging buffer that grows by capacity"""
+        a = np.ascontiguousarray(array)
+        key = ("fx", name, a.dtype.str, parity)
+        t = self.pinned.get(key)
+        if t is None or t.numel() < a.size:
+            tdt = {"<f4": torch.float32, "<i4": torch.int32}[a.dtype.str]
+            t = torch.empty((max(int(a.size * 1.25), 16),), dtype=tdt, pin_memory=True)
+            self.pinned[key] = t
+        v = t[:a.size].view(a.shape)
+        if a.nbytes >= (32 << 20):
+            # NumPy's copy loop releases the GIL: a few threads move the mask probabilities (~100 MB per image)
+            from concurrent.futures import ThreadPoolExecutor
+            src, dst = a.reshape(-1), v.numpy().reshape(-1)
+            cuts = np.linspace(0, a.size, 5).astype(np.int64)
+            with ThreadPoolExecutor(max_workers=4) as ex:
+                list(ex.map(lambda k: np.copyto(dst[cuts[k]:cuts[k + 1]], src[cuts[k]:cuts[k + 1]]), range(4)))
+        elif a.size:
+            np.copyto(v.numpy(), a)
+        return v
+
     def close(self):
-        if self.loader is not None:
-            self.loader.shutdown(wait=True)
-            self.loader = None
+        for name in ("loader", "writer"):
+            pool = getattr(self, name)
+            if pool is not None:
+                pool.shutdown(wait=True)
+                setattr(self, name, None)
         self.runners.clear(); self.tables.clear(); self.pinned.clear()
 
 
 def _device(config):
     dev = config.get("device", "0")
-    if dev == "cpu" or not torch.cuda.is_available():
+    if dev == "cpu" or not ops._lib.cuda_available():
         raise RuntimeError("treedetection_b200 needs a CUDA device: there is no CPU implementation of this path")
     return torch.device("cuda", int(dev))
 
@@ -213,11 +249,14 @@ def _write_tile_predictions(pred_subdir, tifpath, tiles, rings, inst_tile, score
 
 
 class _FastPath:
-    """One image of ``process_files`` end to end while its data is on the device: rasters decoded ONCE into pinned
-    memory (the next image's in a background thread meanwhile), ``api.run_image`` (P1 + the CUDA-graph chain
-    P2-P9, H2D copies overlapped with the stages), then both artefacts -- ``geojson_predictions/<stem>.gpkg`` and
-    ``processed_<stem>.gpkg`` -- are written.  Returns False for anything it does not cover (no matching nDSM,
-    16-bit imagery, a predictor that consumes the tiles): the caller then takes the stage-by-stage path."""
+    """One image of ``process_files`` end to end while its data is on the device, as a three-stage pipeline over the
+    images: a LOADER thread decodes the next image's rasters and ROI-head fixtures into pinned staging buffers, the
+    calling thread runs ``api.run_image`` (P1 + the CUDA-graph chain P2-P9, H2D copies overlapped with the stages),
+    and a WRITER thread writes both artefacts of the previous image -- ``geojson_predictions/<stem>.gpkg`` and
+    ``processed_<stem>.gpkg``.  ``run`` returns False for anything it does not cover (no matching nDSM, 16-bit
+    imagery, a predictor that consumes the tiles): the caller then takes the stage-by-stage path."""
+
+    MAX_PENDING_WRITES = 3     # images whose layers may be queued for the writer threads
 
     def __init__(self, config, session, dev, params, predictor, stitched_path, output_path, logger):
         from concurrent.futures import ThreadPoolExecutor
@@ -225,7 +264,11 @@ class _FastPath:
         self.predictor, self.stitched_path, self.output_path, self.logger = predictor, stitched_path, output_path, logger
         if session.loader is None:
             session.loader = ThreadPoolExecutor(max_workers=1)
+        if session.writer is None:
+            session.writer = ThreadPoolExecutor(max_workers=2)    # the two layers of an image are independent files
         self.pending = {}          # image path -> Future of _load
+        self.writes = []           # (image path, Future of _write), oldest first
+        self.failed = set()        # images whose layers could not be written
         self.parity = 0
         image_pattern = re.compile(config.get("image_regex") or "(\\d+)\\.tif")
         height_pattern = re.compile(config.get("height_data_regex") or "(\\d+)\\.tif")
@@ -235,7 +278,7 @@ class _FastPath:
         self.image_index = _build_file_index(config["image_directory"], image_pattern)
 
     def _load(self, fp, tiles_path, parity):
-        """decode one image's rasters into pinned staging buffers (runs on the loader thread)"""
+        """decode one image's rasters and fixtures into pinned staging buffers (runs on the loader thread)"""
         t0 = time.time()
         torch.cuda.set_device(self.dev)              # the pinned staging buffers belong to this device's context
         stem = Path(fp).stem
@@ -252,23 +295,65 @@ class _FastPath:
         geotiff.read(fp, out=rgbi.numpy())
         ndsm = self.s.pinned_array("ndsm", (hinfo.count, hinfo.height, hinfo.width), np.float32, parity)
         geotiff.read(hpath, out=ndsm.numpy())
-        return {"tiles": tiles, "rgbi": rgbi, "rinfo": rinfo, "ndsm": ndsm[0], "hinfo": hinfo,
-                "decode_s": time.time() - t0}
+        t1 = time.time()
+        det = None
+        if not getattr(self.predictor, "wants_tiles", False):
+            raw = self.predictor.raw_outputs(stem, tiles)
+            det = {k: self.s.pinned_copy(k, getattr(raw, k), parity)
+                   for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
+        return {"tiles": tiles, "rgbi": rgbi, "rinfo": rinfo, "ndsm": ndsm[0], "hinfo": hinfo, "det": det,
+                "decode_s": t1 - t0, "fixtures_s": time.time() - t1}
 
     def prefetch(self, fp, tiles_path):
         if fp is not None and fp not in self.pending:
             self.pending[fp] = self.s.loader.submit(self._load, fp, tiles_path, self.parity)
             self.parity ^= 1
 
+    def _write_stitched(self, stem, host, epsg):
+        """``geojson_predictions/<stem>.gpkg`` (runs on a writer thread)"""
+        t0 = time.time()
+        stitched = os.path.join(self.stitched_path, stem + ".gpkg")
+        gpkg.write_layer(stitched, stem, host["table_verts"], host["table_ring_off"],
+                         {"Confidence_score": host["table_conf"]}, gpkg.STITCHED_SCHEMA, epsg=epsg)
+        return time.time() - t0
+
+    def _write_final(self, stem, host, epsg):
+        """``processed_<stem>.gpkg`` (runs on a writer thread)"""
+        t0 = time.time()
+        stitched = os.path.join(self.stitched_path, stem + ".gpkg")
+        processed = os.path.join(self.stitched_path, f"processed_{stem}.gpkg")
+        self.logger.info(f"Processing file {stitched} with {len(host['table_conf'])} features.")
+        _write_processed(host, processed, epsg, self.logger)
+        self.s.processed[stitched] = processed
+        return time.time() - t0
+
+    def _reap(self, keep):
+        """wait for the oldest images' writes until at most ``keep`` images are pending; a failed write un-marks its
+        image"""
+        while len(self.writes) > keep:
+            fp, futs = self.writes.pop(0)
+            for fut in futs:
+                try:
+                    self.s.stage_s["write"] = self.s.stage_s.get("write", 0.0) + fut.result()
+                except Exception as e:
+                    self.logger.error(f"Error writing the crown layers of {fp}: {e}")
+                    self.failed.add(fp)
+
+    def finish(self):
+        """all layers on disk; returns the images whose layers could not be written"""
+        self._reap(0)
+        return self.failed
+
     def run(self, fp, tiles_path, next_fp):
+        t_in = time.time()
         self.prefetch(fp, tiles_path)
         data = self.pending.pop(fp).result()
-        self.prefetch(next_fp, tiles_path)               # decoded while this image is on the GPU
-        if data is None or getattr(self.predictor, "wants_tiles", False):
+        t_got = time.time()
+        if data is None or data["det"] is None:
+            self.prefetch(next_fp, tiles_path)
             return False
         stem = Path(fp).stem
-        tiles, rinfo, hinfo = data["tiles"], data["rinfo"], data["hinfo"]
-        det = self.predictor.raw_outputs(stem, tiles)
+        tiles, rinfo, hinfo, det = data["tiles"], data["rinfo"], data["hinfo"], data["det"]
         # images of one shape share a tile grid: tables, the P1 output buffer, capacities and graphs are re-used
         key = (rinfo.height, rinfo.width, len(tiles), hinfo.height, hinfo.width)
         if key in self.s.tables:
@@ -281,28 +366,37 @@ class _FastPath:
             self.s.tables[key] = (tables, torch.empty((tables.p1_floats,), dtype=torch.float32, device=self.dev))
             self.s.runners[key] = pipeline.ChainRunner(self.p)
         tables, p1_out = self.s.tables[key]
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a))
-        img = api.HostImage(data["rgbi"], rinfo.transform, data["ndsm"], hinfo.transform, tiles, pin(det.boxes_net),
-                            pin(det.scores), pin(det.probs), pin(det.inst_tile), pin(det.tile_dims))
+        img = api.HostImage(data["rgbi"], rinfo.transform, data["ndsm"], hinfo.transform, tiles, det["boxes_net"],
+                            det["scores"], det["probs"], det["inst_tile"], det["tile_dims"])
         t0 = time.time()
+        # the staging buffers of the OTHER parity are free (their image is through run_image): decode the next image
+        # into them while this one is on the GPU
+        self.prefetch(next_fp, tiles_path)
         host, _ = api.run_image(img, self.p, self.dev, tables, p1_out, runner=self.s.runners[key], want_table=True)
         t1 = time.time()
-        if self.config.get("keep_intermediate", False) and len(det.scores):
-            _write_predictions_json(self.output_path, stem, fp, tiles, det, tables, self.p, self.dev)
+        if self.config.get("keep_intermediate", False) and int(det["scores"].numel()):
+            raw = synth_detections(det, tiles)
+            _write_predictions_json(self.output_path, stem, fp, tiles, raw, tables, self.p, self.dev)
+        self._reap(self.MAX_PENDING_WRITES - 1)
         epsg = rinfo.epsg or 4326
-        stitched = os.path.join(self.stitched_path, stem + ".gpkg")
-        gpkg.write_layer(stitched, stem, host["table_verts"], host["table_ring_off"],
-                         {"Confidence_score": host["table_conf"]}, gpkg.STITCHED_SCHEMA, epsg=epsg)
-        processed = os.path.join(self.stitched_path, f"processed_{stem}.gpkg")
-        self.logger.info(f"Processing file {stitched} with {len(host['table_conf'])} features.")
-        _write_processed(host, processed, epsg, self.logger)
-        self.s.processed[stitched] = processed
+        self.writes.append((fp, [self.s.writer.submit(self._write_stitched, stem, host, epsg),
+                                 self.s.writer.submit(self._write_final, stem, host, epsg)]))
         self.s.images += 1
         st = self.s.stage_s
-        st["decode"] = st.get("decode", 0.0) + data["decode_s"]
-        st["device"] = st.get("device", 0.0) + (t1 - t0)
-        st["write"] = st.get("write", 0.0) + (time.time() - t1)
+        for name, v in (("wait_decode", t_got - t_in), ("decode", data["decode_s"]), ("fixtures", data["fixtures_s"]),
+                        ("tables", t0 - t_got), ("device", t1 - t0)):
+            st[name] = st.get(name, 0.0) + v
+        self.s.timeline.append({"image": stem, "t_in": t_in, "wait_decode_s": t_got - t_in, "decode_s": data["decode_s"],
+                                "fixtures_s": data["fixtures_s"], "tables_s": t0 - t_got, "device_s": t1 - t0,
+                                "t_out": time.time()})
         return True
+
+
+def synth_detections(det, tiles):
+    """Detections (host arrays) from the pinned fixture tensors of the fast path"""
+    from .synth import Detections
+    return Detections(det["boxes_net"].numpy(), det["scores"].numpy(), det["probs"].numpy(), det["inst_tile"].numpy(),
+                      det["tile_dims"].numpy(), list(tiles.keys()), tiles)
 
 
 def _write_predictions_json(output_path, stem, fp, tiles, det, tables, params, dev):
@@ -328,7 +422,7 @@ def _load_prediction_ledger(rec_file, output_path, tiles_path, model_path, stitc
     if not os.path.exists(rec_file):
         return processed
     try:
-        rec = yaml.safe_load(open(rec_file)) or {}
+        rec = _yaml_load(open(rec_file)) or {}
     except Exception as e:
         if logger:
             logger.warning(f"Could not load prediction recovery file: {e}")
@@ -380,7 +474,7 @@ def _save_prediction_ledger(rec_file, tiles_path, model_path, files, logger):
                 with open(json_path) as jf:
                     data["files"][file_path] = list(json.load(jf).keys())
         with open(rec_file, "w") as f:
-            yaml.safe_dump(data, f, sort_keys=False)
+            _yaml_dump(data, f)
     except Exception as e:
         if logger:
             logger.warning(f"Failed to save prediction recovery file: {e}")
@@ -392,7 +486,7 @@ def _load_stitching_ledger(stitched_path, logger=None):
     done = set()
     if os.path.exists(rec_file):
         try:
-            rec = yaml.safe_load(open(rec_file)) or {}
+            rec = _yaml_load(open(rec_file)) or {}
             done = {os.path.splitext(os.path.basename(p))[0] for p in rec.get("completed_files", [])}
         except Exception as e:
             if logger:
@@ -405,7 +499,7 @@ def _save_stitching_ledger(stitched_path, files, logger=None):
     try:
         done = _load_stitching_ledger(stitched_path) | {Path(f).stem for f in files}
         with open(os.path.join(stitched_path, "stitching_recovery.yaml"), "w") as f:
-            yaml.safe_dump({"completed_files": sorted(done)}, f, sort_keys=False)
+            _yaml_dump({"completed_files": sorted(done)}, f)
     except Exception as e:
         if logger:
             logger.warning(f"Failed to save stitching recovery: {e}")
@@ -499,6 +593,9 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
             done.append(fp)
         except Exception as e:   # per-file failures are logged and skipped (detection.py:117-120)
             logger.error(f"Error processing {fp}: {e}")
+    if fast:
+        failed = fast_ctx.finish()
+        done = [f for f in done if f not in failed]
     logger.info(f"Completed prediction for {len(images_paths)} images.")
     _save_prediction_ledger(rec_file, tiles_path, model_path, sorted(processed | set(done)), logger)
     _save_stitching_ledger(stitched_path, sorted(processed | set(done)), logger)
@@ -648,7 +745,7 @@ def _process_files_in_directory(directory, height_directory, image_directory, co
     processed_files = set()
     if os.path.exists(rec_file):
         try:
-            rec = yaml.safe_load(open(rec_file)) or {}
+            rec = _yaml_load(open(rec_file)) or {}
             if rec.get("params") == params_now:
                 processed_files = set(rec.get("processed_files", []))
         except Exception:
@@ -775,7 +872,8 @@ def process_files(config):
         if session is not None:
             session.stage_s.update(preprocess=t1 - t0, predict=t2 - t1, postprocess=t3 - t2, cleanup=time.time() - t3)
             config["_last_session_stats"] = {"stage_s": dict(session.stage_s), "images": session.images,
-                                             "fallback_images": session.fallback_images}
+                                             "fallback_images": session.fallback_images,
+                                             "timeline": list(session.timeline), "t0": t0}
     finally:
         if own_session:
             session.close()

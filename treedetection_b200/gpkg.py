@@ -60,9 +60,64 @@ def _parse_gpb(blob: bytes) -> np.ndarray:
     return np.array(pts[:, :2], dtype=np.float64)
 
 
-def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=25832):
+def _append_native(path, layer, epsg, verts, ring_off, names, schema, columns):
+    """The feature rows through ``td_gpkg_append`` (csrc/gpkgio.cu; the GIL is released for the whole call).
+    Returns False when the library or a column cannot take that route (the Python loop then writes the rows)."""
+    import ctypes as C
+    try:
+        from . import _lib
+        fn = _lib.lib().td_gpkg_append
+    except Exception:
+        return False
+    n = len(ring_off) - 1
+    keep, types, data, offs = [], [], [], []
+    for k in names:
+        c = columns[k]
+        kind = schema[k]
+        if kind == "float":
+            if not isinstance(c, np.ndarray) and any(v is None for v in c):
+                c = [np.nan if v is None else v for v in c]
+            a = np.ascontiguousarray(c, dtype=np.float64)
+            o = None
+        elif kind == "int":
+            if not isinstance(c, np.ndarray) and any(v is None for v in c):
+                return False
+            a = np.ascontiguousarray(c, dtype=np.int64)
+            o = None
+        else:
+            if any(v is None for v in c):
+                return False
+            enc = [str(v).encode("utf-8") for v in c]
+            a = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+            o = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([len(e) for e in enc], out=o[1:])
+        if o is None and a.shape != (n,):
+            return False
+        keep.append((a, o))
+        types.append({"float": 0, "int": 1, "str": 2}[kind])
+        data.append(a.ctypes.data)
+        offs.append(o.ctypes.data if o is not None else None)
+    m = len(names)
+    c_names = (C.c_char_p * max(m, 1))(*[k.encode("utf-8") for k in names])
+    c_types = (C.c_int * max(m, 1))(*types)
+    c_data = (C.c_void_p * max(m, 1))(*data)
+    c_offs = (C.c_void_p * max(m, 1))(*offs)
+    v = np.ascontiguousarray(verts, dtype=np.float64)
+    ro = np.ascontiguousarray(ring_off, dtype=np.int64)
+    rc = fn(os.fsencode(path), layer.encode("utf-8"), int(epsg), v.ctypes.data if v.size else None, ro.ctypes.data, n, m,
+            C.cast(c_names, C.c_void_p), C.cast(c_types, C.c_void_p), C.cast(c_data, C.c_void_p),
+            C.cast(c_offs, C.c_void_p))
+    if rc != 0:
+        msg = _lib.lib().td_last_error()
+        raise RuntimeError(f"td_gpkg_append failed with code {rc}: {msg.decode() if msg else ''}")
+    return True
+
+
+def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=25832, native=None):
     """verts (V,2) f64 + ring_off (R+1): one Polygon per ring.  columns: name -> sequence of
-    R values; schema: name -> 'float' | 'int' | 'str' (fiona's names), in column order."""
+    R values; schema: name -> 'float' | 'int' | 'str' (fiona's names), in column order.
+    ``native``: None = the feature rows go through ``td_gpkg_append`` when the library is there (same bytes in
+    the table), False = the Python loop, True = the native writer or an error."""
     verts = np.asarray(verts, dtype=np.float64).reshape(-1, 2)
     ring_off = np.asarray(ring_off, dtype=np.int64)
     n = len(ring_off) - 1
@@ -91,9 +146,9 @@ def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=
         cols_sql = ", ".join(f'"{k}" {_SQL_TYPES[v]}' for k, v in schema.items())
         cur.execute(f'CREATE TABLE "{layer}" (fid INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, geom POLYGON'
                     + (", " + cols_sql if cols_sql else "") + ")")
+        xs, ys = (np.ascontiguousarray(verts[:, 0]), np.ascontiguousarray(verts[:, 1]))   # unit-stride reductions
         if len(verts):
-            mn, mx = verts.min(axis=0), verts.max(axis=0)
-            ext = (float(mn[0]), float(mn[1]), float(mx[0]), float(mx[1]))
+            ext = (float(xs.min()), float(ys.min()), float(xs.max()), float(ys.max()))
         else:
             ext = (None, None, None, None)
         now = datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%S.000Z")
@@ -101,6 +156,16 @@ def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=
                     (layer, "features", layer, "", now, *ext, epsg))
         cur.execute("INSERT INTO gpkg_geometry_columns VALUES (?,?,?,?,?,?)", (layer, "geom", "POLYGON", epsg, 0, 0))
         names = list(schema.keys())
+        if native is not False and n and _append_native is not None:
+            con.commit()
+            con.close()
+            con = None
+            if _append_native(path, layer, epsg, verts, ring_off, names, schema, columns):
+                return
+            if native is True:
+                raise RuntimeError("gpkg.write_layer: the native feature writer (td_gpkg_append) is not available")
+            con = sqlite3.connect(path)
+            cur = con.cursor()
         conv = {"float": float, "int": int, "str": str}
         # geometry blobs: header | envelope | WKB polygon header | coordinates, cut from ONE byte string of all
         # coordinates and vectorised envelopes (a layer has tens of thousands of crowns)
@@ -110,8 +175,8 @@ def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=
         if n:
             safe = np.minimum(ring_off[:-1], max(len(verts) - 1, 0))
             if len(verts):
-                env = np.stack([np.minimum.reduceat(verts[:, 0], safe), np.maximum.reduceat(verts[:, 0], safe),
-                                np.minimum.reduceat(verts[:, 1], safe), np.maximum.reduceat(verts[:, 1], safe)], 1)
+                env = np.stack([np.minimum.reduceat(xs, safe), np.maximum.reduceat(xs, safe),
+                                np.minimum.reduceat(ys, safe), np.maximum.reduceat(ys, safe)], 1)
             else:
                 env = np.zeros((n, 4))
             env_b = np.ascontiguousarray(env, dtype="<f8").tobytes()
@@ -139,7 +204,8 @@ def write_layer(path, layer, verts, ring_off, columns: dict, schema: dict, epsg=
         cur.executemany(f'INSERT INTO "{layer}" ({colnames}) VALUES ({ph})', data)
         con.commit()
     finally:
-        con.close()
+        if con is not None:
+            con.close()
 
 
 def read_layer(path, layer=None):

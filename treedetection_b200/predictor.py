@@ -24,6 +24,50 @@ from .synth import Detections
 from .tiling import resize_shortest_edge
 
 
+def _load_npz(path):
+    """Arrays of an ``.npz`` as a dict.  Members that are STORED (``np.savez``, what ``dump_fixtures`` writes) become
+    zero-copy views of the memory-mapped file -- ``np.load`` would read every member through zipfile (one extra copy
+    plus a CRC-32 pass, ~0.1 s for the 100 MB of mask probabilities of one image); deflated members fall back to it."""
+    import mmap
+    import zipfile
+    out = {}
+    with open(path, "rb") as f:
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    with zipfile.ZipFile(path) as z:
+        infos = z.infolist()
+    slow = []
+    for zi in infos:
+        name = zi.filename[:-4] if zi.filename.endswith(".npy") else zi.filename
+        if zi.compress_type != 0:
+            slow.append(name)
+            continue
+        h = zi.header_offset
+        if buf[h:h + 4] != b"PK\x03\x04":
+            slow.append(name)
+            continue
+        n_name, n_extra = int.from_bytes(buf[h + 26:h + 28], "little"), int.from_bytes(buf[h + 28:h + 30], "little")
+        start = h + 30 + n_name + n_extra
+        import io
+        head = io.BytesIO(buf[start:start + 4096])
+        try:
+            version = np.lib.format.read_magic(head)
+            shape, fortran, dtype = (np.lib.format.read_array_header_1_0(head) if version == (1, 0)
+                                     else np.lib.format.read_array_header_2_0(head))
+        except Exception:
+            slow.append(name)
+            continue
+        if fortran or dtype.hasobject:
+            slow.append(name)
+            continue
+        count = int(np.prod(shape)) if len(shape) else 1
+        out[name] = np.frombuffer(buf, dtype=dtype, count=count, offset=start + head.tell()).reshape(shape)
+    if slow:
+        with np.load(path, allow_pickle=False) as f:
+            for name in slow:
+                out[name] = f[name]
+    return out
+
+
 class FixturePredictor:
     def __init__(self, model_path, exclude_vars=None, allow_missing=False):
         self.allow_missing = allow_missing
@@ -50,9 +94,9 @@ class FixturePredictor:
             # a mis-staged fixture directory must not produce silently empty crown layers that a resumed
             # run then skips as "already predicted": predict_on_model logs the error and does not mark the file
             raise FileNotFoundError(f"no ROI-head fixture for image {image_stem!r}: {path}")
-        with np.load(path, allow_pickle=False) as f:
-            fx_ids = [str(s) for s in f["tile_ids"]]
-            boxes, scores, probs, inst_tile = f["boxes_net"], f["scores"], f["probs"], f["inst_tile"]
+        f = _load_npz(path)
+        fx_ids = [str(s) for s in f["tile_ids"]]
+        boxes, scores, probs, inst_tile = f["boxes_net"], f["scores"], f["probs"], f["inst_tile"]
         n = len(scores)
         if boxes.shape != (n, 4) or probs.shape != (n, 28, 28) or inst_tile.shape != (n,):
             raise ValueError(f"{path}: boxes_net {boxes.shape}, scores {scores.shape}, probs {probs.shape}, inst_tile "
