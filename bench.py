@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-files", action="store_true", help="skip e2e_files (process_files on GeoTIFFs on tmpfs)")
     ap.add_argument("--files-only", action="store_true", help="diagnostic: run e2e_files alone and print its entry")
     ap.add_argument("--files-images", type=int, default=6, help="images of the workload in e2e_files")
-    ap.add_argument("--chains", type=int, default=2,
+    ap.add_argument("--chains", type=int, default=1,
                     help="independent chain contexts (workspace + stream + graphs each) that consecutive images "
                          "alternate between: the P2-P9 chain of an image is a latency-bound sequence of dependent "
                          "launches, two images' chains side by side fill the gaps of each other")

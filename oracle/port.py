@@ -8,8 +8,9 @@ algorithm is restated and the function says "parity unpinned".
 Pinned here against the reference's own code through ``oracle.refshim``:
 ``nms_bbox``, ``crown_stats_combined``, ``crown_stats_height``,
 ``crown_stats_ndvi``, ``containment``, ``ndvi_from_rgbi``, ``centroids``,
-``process_features`` / ``process_geojson`` (tests/test_oracle_vs_reference.py,
-tests/golden/*.npz).
+``process_features`` / ``process_geojson`` (tests/test_oracle_golden.py against
+tests/golden/*.npz, which tests/golden/make_golden*.py produced by running the
+reference's functions).
 """
 from __future__ import annotations
 

@@ -13,7 +13,7 @@ import json, sys
 for l in open(sys.argv[2]):
     if l.startswith("{"):
         d = json.loads(l)
-        print(sys.argv[1], "=>", round(d["value"], 1), round(d["ms_per_step"], 3), (d.get("parity") or "")[:12],
+        print(sys.argv[1], "=>", round(d["value"], 1), round(d["ms_per_step"], 3), (d.get("parity") or "NO PARITY")[:12],
               "p1_alone", round(d["roofline"].get("ms_per_launch", 0), 3) if "roofline" in d else None,
               {k[:5]: v for k, v in d["config"]["stage_ms"].items()})
 PY
