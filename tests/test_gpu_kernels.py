@@ -181,8 +181,11 @@ def test_centroids_bit_exact(dev):
     np.testing.assert_array_equal(got, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("shape,factor", [((1000, 1000), 0.2), ((730, 1210), 0.2), ((500, 640), 0.5), ((300, 300), 1.0)])
+@pytest.mark.parametrize("shape,factor", [((1000, 1000), 0.2), ((730, 1210), 0.2), ((500, 640), 0.5), ((300, 300), 1.0),
+                                          ((611, 977), 1 / 3), ((700, 910), 1 / 7), ((1500, 1100), 0.1),
+                                          ((333, 20), 0.25)])
 def test_ndvi_decimate(dev, shape, factor):
+    """decimation factors 2:1 ... 10:1, ragged sizes, a raster narrower than one CTA tile"""
     rng = np.random.default_rng(shape[0])
     rgbi = rng.integers(0, 256, size=(4,) + shape, dtype=np.uint8)
     oh, ow = int(shape[0] * factor), int(shape[1] * factor)
@@ -199,6 +202,23 @@ def test_decimate_f32(dev):
     ref = port.decimate_bilinear(band, 180, 220)
     got = ops.decimate_f32(torch.from_numpy(band).to(dev), 180, 220).cpu().numpy()
     np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("out_hw", [(180, 220), (300, 367), (129, 157)])
+def test_decimate_f32_with_nodata_and_nan(dev, out_hw):
+    """nDSM rasters carry nodata (-3.4e38) and may carry NaN / Inf: they spread exactly as far as the oracle's tap
+    loop spreads them (a weight-0 tap at the edge of the support included)"""
+    rng = np.random.default_rng(5)
+    band = rng.uniform(0, 40, (900, 1100)).astype(np.float32)
+    band[rng.integers(0, 900, 300), rng.integers(0, 1100, 300)] = np.nan
+    band[rng.integers(0, 900, 100), rng.integers(0, 1100, 100)] = np.inf
+    band[rng.integers(0, 900, 300), rng.integers(0, 1100, 300)] = np.float32(-3.4028234663852886e38)
+    band[:, -1] = np.nan           # the last column: the padded taps of the last output must stay inside the row
+    with np.errstate(invalid="ignore", over="ignore"):
+        ref = port.decimate_bilinear(band, *out_hw)
+    got = ops.decimate_f32(torch.from_numpy(band).to(dev), *out_hw).cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
 
 
 def test_mask_iou_clean_matches_restated_clean_crowns(dev):

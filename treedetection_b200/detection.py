@@ -401,7 +401,7 @@ def synth_detections(det, tiles):
 
 def _write_predictions_json(output_path, stem, fp, tiles, det, tables, params, dev):
     """the per-tile ``Prediction_*.json`` wire format (prediction.py:253-263), kept intermediates only"""
-    t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.require(a, requirements=["C", "W"])).to(dev)
     host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else a
     boxes, probs, inst_tile, tile_dims = t(det.boxes_net), t(det.probs), t(det.inst_tile), t(det.tile_dims)
     bpx, win, nwords = ops.paste_plan(boxes, inst_tile, tile_dims)
@@ -579,7 +579,7 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
             else:       # fixtures replay: the raster itself is not needed here, only its CRS
                 info = geotiff.read_info(fp)
                 det = predictor.raw_outputs(stem, tiles)
-            t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            t = lambda a: a.to(dev) if torch.is_tensor(a) else torch.from_numpy(np.require(a, requirements=["C", "W"])).to(dev)
             boxes, scores, probs, inst_tile, tile_dims = (t(det.boxes_net), t(det.scores), t(det.probs),
                                                           t(det.inst_tile), t(det.tile_dims))
             host = lambda a: a.cpu().numpy() if torch.is_tensor(a) else a
