@@ -209,7 +209,7 @@ def run_reference(a):
 # --------------------------------------------------------------------------------------
 # e2e_files: the reference-facing API on GeoTIFFs (process_files), per-stage wall clock
 # --------------------------------------------------------------------------------------
-def e2e_files(sc, n_images, label):
+def e2e_files(sc, n_images, label, compression=None):
     """``process_files(config)`` -- the call a user of the reference makes -- over ``n_images`` GeoTIFF pairs on
     tmpfs: RGBI + nDSM rasters written uncompressed, ROI-head fixtures staged as the "model", config.yml as in
     example/config.yml.  The images are copies of the scene at origins 10 km apart (no neighbours, so no
@@ -236,14 +236,16 @@ def e2e_files(sc, n_images, label):
             left = synth.ORIGIN_X + 10000.0 * k
             top = synth.ORIGIN_Y + H * px
             tf = synth.image_transform(left, top, px)
-            geotiff.write(os.path.join(img_dir, stem + ".tif"), sc.rgbi, tf, epsg=synth.EPSG)
+            geotiff.write(os.path.join(img_dir, stem + ".tif"), sc.rgbi, tf, epsg=synth.EPSG, compression=compression,
+                          predictor=2 if compression else 1)
             geotiff.write(os.path.join(h_dir, f"nDSM_{k:06d}_1km.tif"), sc.ndsm, synth.image_transform(left, top, npx),
-                          epsg=synth.EPSG, nodata=-3.4028234663852886e38)
+                          epsg=synth.EPSG, nodata=-3.4028234663852886e38, compression=compression)
             tiles = tiling.tile_grid(stem, tf, W, H, synth.EPSG, 50, 50, 20)
             d = sc.det
             predictor.dump_fixtures(model, stem, synth.Detections(d.boxes_net, d.scores, d.probs, d.inst_tile, d.tile_dims,
                                                                    list(tiles.keys()), tiles))
         write_s = time.perf_counter() - t_w0
+        file_bytes = sum(os.path.getsize(os.path.join(d, f)) for d in (img_dir, h_dir) for f in os.listdir(d))
         cfg = {
             "image_directory": img_dir, "height_data_path": h_dir, "image_regex": "FDOP20_(\\d+)_rgbi\\.tif",
             "height_data_regex": "nDSM_(\\d+)_1km\\.tif", "combined_model": model,
@@ -303,8 +305,9 @@ def e2e_files(sc, n_images, label):
                 "stage_s": {k: round(v, 3) for k, v in stats.get("stage_s", {}).items()},
                 "fast_path_images": stats.get("images"), "fallback_images": stats.get("fallback_images"),
                 "crowns_per_image": n_crowns, "parity": parity,
-                "input_bytes": int(n_images * (sc.rgbi.nbytes + sc.ndsm.nbytes)),
-                "note": f"GeoTIFFs uncompressed on {'tmpfs (/dev/shm)' if base else 'the default temp dir'} (written in "
+                "input_bytes": int(n_images * (sc.rgbi.nbytes + sc.ndsm.nbytes)), "file_bytes": int(file_bytes),
+                "device_decoded_rasters": stats.get("device_decoded_rasters"),
+                "note": f"GeoTIFFs {'LZW-compressed (predictor 2 imagery; strips decoded on the GPU, one warp each)' if compression else 'uncompressed'} on {'tmpfs (/dev/shm)' if base else 'the default temp dir'} (written in "
                         f"{write_s:.1f} s, not timed); timed: get tiles -> read + decode rasters and fixtures -> H2D -> P1 "
                         f"+ P2-P9 -> D2H -> stitched, processed and final .gpkg written (decoder thread | device | writer thread); the first image of a tiling "
                         f"learns the capacities (exact-size path), the others replay the CUDA graphs"}
@@ -390,6 +393,8 @@ def run_b200(a):
                           bottom=synth.ORIGIN_Y - rank * a.size * 0.2, stem=f"FDOP20_{rank:06d}_rgbi")
     if a.files_only:
         print(json.dumps(e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px))))
+        print(json.dumps(e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px) + ", LZW-compressed GeoTIFFs",
+                                   compression="lzw")))
         return
     host = api.HostImage.from_scene(sc)
     tables = api.TileTables(sc.tiles, dev, p.shift)
@@ -817,7 +822,9 @@ def run_b200(a):
         torch.cuda.synchronize()
         del d, p1_out                   # e2e_files brings its own device buffers
         torch.cuda.empty_cache()
-        files = [e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px))]
+        files = [e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px)),
+                 e2e_files(sc, a.files_images, workload_string(a.size, a.ndsm_px) + ", LZW-compressed GeoTIFFs",
+                           compression="lzw")]
         try:      # BASELINE config 1: the reference's example tile (bundled nDSM 1000^2 @ 1 m + synthetic RGBI 5000^2)
             files.append(e2e_files(synth.config1_scene(), 2, "BASELINE config 1: example/config.yml on the bundled nDSM tile "
                                                        "324125317 (1 m) + synthetic 5000x5000 px RGBI"))

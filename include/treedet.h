@@ -313,6 +313,30 @@ int td_seam_crop(const void* a, const void* b, int elem_size, int bands, int ha,
  * section 13); returns the bytes written to dst (<= cap) or a negative TD_ERR_* code.            */
 long long td_tiff_lzw_decode(const unsigned char* src, long long n_src, unsigned char* dst, long long cap);
 
+/* The encoder of the same format (HOST function): ClearCode, MSB-first codes with early change, ClearCode when
+ * the table is full, EOI -- what libtiff writes.  Returns the bytes written (cap >= n_src * 3 / 2 + 16 suffices) or
+ * a negative TD_ERR_* code.  Used by this package's GeoTIFF writer (the reference writes its merged seam strips
+ * through rasterio: TreeDetection/merging.py:100-107).                                                       */
+long long td_tiff_lzw_encode(const unsigned char* src, long long n_src, unsigned char* dst, long long cap);
+
+/* The same decoder on the DEVICE, for all strips / tiles of a raster at once (device pointers): chunk k is the
+ * LZW stream src[src_pos[k] : src_pos[k] + src_len[k]] -- src is typically the whole file, copied to the device
+ * still compressed -- and is decoded to dst + k * dst_stride (dst_len[k] expected bytes, dst_stride <= 1 MiB; a
+ * shorter stream is zero filled).  out_len (n_chunks, nullable) receives the decoded byte counts; *status (one
+ * int) becomes a TD_ERR_* code if any stream is corrupt or overflows its chunk.  One warp per stream.       */
+int td_tiff_lzw_decode_batch(const unsigned char* src, const long long* src_pos, const int* src_len, int n_chunks,
+                             unsigned char* dst, long long dst_stride, const int* dst_len, int* out_len, int* status,
+                             void* stream);
+
+/* Decoded chunks -> the planar (bands, height, width) raster the path consumes: undoes TIFF predictor 2
+ * (horizontal differencing, 8-bit samples) and de-interleaves chunky pixels.  Replaces what GDAL does behind
+ * rasterio's read() after the codec (TreeDetection/prediction.py:61, postprocessing.py:781-800).
+ *   decoded: chunk k at decoded + k * stride, in TIFF order (planar == 2: plane-major);
+ *   sample_size 1 (predictor 1 or 2) or 4 (predictor 1); planar = TIFF PlanarConfiguration (1 chunky, 2 planar). */
+int td_tiff_place_chunks(const unsigned char* decoded, long long stride, int n_chunks, void* out, int bands, int height,
+                         int width, int sample_size, int planar, int chunk_rows, int chunk_cols, int predictor,
+                         void* stream);
+
 /* ---- N2: GeoPackage feature writer (HOST function, host pointers) ----------------------------------
  * Replaces the row loop of GeoDataFrame.to_file(driver="GPKG") behind the stitched layer
  * (TreeDetection/helpers.py:592-599) and the processed layer (postprocessing.py:903-936): appends n_rings

@@ -108,3 +108,55 @@ def test_windowed_read_decodes_only_what_it_needs(tmp_path, compression, tile):
         geotiff.read(path, window=(500, 0, 100, 10))
     with pytest.raises(ValueError):
         geotiff.read(path, out=np.zeros((4, 10, 10), np.uint8))
+
+
+@pytest.mark.parametrize("name,predictor", [("band", 1), ("band", 2), ("f32", 1), ("noise", 1), ("runs", 2), ("few", 1)])
+def test_lzw_writer_is_read_by_libtiff(tmp_path, name, predictor):
+    """td_tiff_lzw_encode (geotiff.write(compression="lzw")) pinned against libtiff: PIL decodes the file to the same
+    pixels -- smooth data, noise (codes of every width), long runs (KwKwK), a 4-symbol alphabet on long strips (the
+    table fills up and is reset many times) -- and so does this package's own reader"""
+    rng = np.random.default_rng(4)
+    smooth = (np.add.outer(np.arange(300), np.arange(517)) % 251).astype(np.uint8)
+    runs = np.zeros((200, 2048), np.uint8)
+    runs[50:120, 300:1500] = 200
+    arr = {"band": smooth, "f32": _cases()["f32"], "noise": _cases()["noise"], "runs": runs,
+           "few": rng.integers(0, 4, (300, 9000)).astype(np.uint8)}[name]
+    path = str(tmp_path / "w.tif")
+    geotiff.write(path, arr, (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0), epsg=25832, compression="lzw",
+                  predictor=predictor)
+    with Image.open(path) as im:
+        np.testing.assert_array_equal(np.array(im), arr)
+    got, info = geotiff.read(path)
+    np.testing.assert_array_equal(got[0], arr)
+    assert info.epsg == 25832 and info.transform == (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0)
+
+
+def test_lzw_writer_planar_bands_round_trip(tmp_path):
+    arr = _cases()["rgba"]
+    path = str(tmp_path / "w.tif")
+    for predictor in (1, 2):
+        geotiff.write(path, arr, (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0), epsg=25832, compression="lzw",
+                      predictor=predictor)
+        got, _ = geotiff.read(path)
+        np.testing.assert_array_equal(got, arr)
+        win, _ = geotiff.read(path, window=(100, 50, 200, 120))
+        np.testing.assert_array_equal(win, arr[:, 50:170, 100:300])
+    with pytest.raises(ValueError):
+        geotiff.write(path, _cases()["f32"], (1, 0, 0, 0, -1, 0), compression="lzw", predictor=2)
+
+
+def test_lzw_encoder_decoder_agree_at_every_stream_length():
+    """The decoder adds a table entry (and may widen the codes, or expect a ClearCode) after the LAST data code as
+    well, so the encoder must account for it before EOI (libtiff's LZWPostEncode): streams whose final code lands
+    exactly on a width boundary (254, 510, 1022, 2046 codes) or on a full table (3836 codes)"""
+    lib = _lib.lib()
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 256, 5000, dtype=np.uint8).tobytes()      # ~one code per byte
+    lengths = list(range(1, 40)) + list(range(240, 270)) + list(range(500, 520)) + list(range(1015, 1030)) + \
+        list(range(2040, 2052)) + list(range(3825, 3850)) + [4999]
+    for n in lengths:
+        raw = noise[:n]
+        enc = geotiff._lzw_encode(raw)
+        dst = C.create_string_buffer(n + 8)
+        got = lib.td_tiff_lzw_decode(enc, len(enc), dst, n + 8)
+        assert got == n and dst.raw[:n] == raw, n

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 PX = 0.2
 
 
-def _project(tmp_path):
+def _project(tmp_path, compression=None):
     left, bottom = synth.ORIGIN_X, synth.ORIGIN_Y
     field = synth.tree_field(77, 400.0, 200.0, 5000.0, left, bottom)
     rgbi = synth.make_rgbi(field, PX, 77)            # (4, 1000, 2000)
@@ -27,9 +27,10 @@ def _project(tmp_path):
     for k, name in enumerate(("000001", "000002")):
         x0 = left + 200.0 * k
         geotiff.write(str(img_dir / f"FDOP20_{name}_rgbi.tif"), rgbi[:, :, 1000 * k:1000 * (k + 1)],
-                      (PX, 0.0, x0, 0.0, -PX, top), epsg=25832)
+                      (PX, 0.0, x0, 0.0, -PX, top), epsg=25832, compression=compression,
+                      predictor=2 if compression else 1)
         geotiff.write(str(h_dir / f"nDSM_{name}_1km.tif"), ndsm[:, 200 * k:200 * (k + 1)],
-                      (1.0, 0.0, x0, 0.0, -1.0, top), epsg=25832, nodata=-3.4028234663852886e38)
+                      (1.0, 0.0, x0, 0.0, -1.0, top), epsg=25832, nodata=-3.4028234663852886e38, compression=compression)
     model = tmp_path / "model_fixtures"
     model.mkdir()
     cfg = {
@@ -177,6 +178,34 @@ def test_process_files_fast_path_writes_the_same_files(tmp_path):
         for col in ca:
             assert list(ca[col]) == list(cb[col]), (name, col)
     assert any(len(a[n][1]) - 1 > 10 for n in a if n.startswith("./"))
+
+
+def test_process_files_decodes_lzw_rasters_on_the_device(tmp_path):
+    """LZW-compressed inputs (predictor 2 imagery, float32 nDSM): the session decodes them on the GPU
+    (geotiff.read_device: compressed bytes over PCIe, one warp per strip) and writes the same layers as for the
+    uncompressed files; ``host_decode: true`` keeps the host reader."""
+    layers, stats = {}, {}
+    for mode, compression, host_decode in (("plain", None, False), ("lzw", "lzw", False), ("lzw_host", "lzw", True)):
+        root = tmp_path / mode
+        root.mkdir()
+        cfg_path, field, _ = _project(root, compression)
+        config, _ = detection.get_config(cfg_path)
+        config["predictor"] = _FieldPredictor(field)
+        config["host_decode"] = host_decode
+        detection.process_files(config)
+        stats[mode] = config["_last_session_stats"]
+        out = config["output_directory"]
+        layers[mode] = {n: gpkg.read_layer(os.path.join(out, n)) for n in sorted(os.listdir(out)) if n.endswith(".gpkg")}
+    assert stats["plain"]["device_decoded_rasters"] == 0 and stats["lzw_host"]["device_decoded_rasters"] == 0
+    # the two images' rasters (the merged seam strip is written uncompressed by the merge step)
+    assert stats["lzw"]["device_decoded_rasters"] == 4 and stats["lzw"]["fallback_images"] == 0, stats["lzw"]
+    for mode in ("lzw", "lzw_host"):
+        assert sorted(layers[mode]) == sorted(layers["plain"]) and len(layers[mode]) == 3
+        for name, (v, o, c, e) in layers["plain"].items():
+            v2, o2, c2, e2 = layers[mode][name]
+            np.testing.assert_array_equal(v2, v, err_msg=name)
+            np.testing.assert_array_equal(o2, o, err_msg=name)
+            assert c2 == c and e2 == e, name
 
 
 def test_exclude_files_remove_crowns_within_the_outline(tmp_path, dev):

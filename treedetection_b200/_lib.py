@@ -76,6 +76,9 @@ SIGNATURES = {
     "td_chain_post": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _p]),
     # N1 (host function)
     "td_tiff_lzw_decode": (_ll, [_p, _ll, _p, _ll]),
+    "td_tiff_lzw_encode": (_ll, [_p, _ll, _p, _ll]),
+    "td_tiff_lzw_decode_batch": (_i, [_p, _p, _p, _i, _p, _ll, _p, _p, _p, _p]),
+    "td_tiff_place_chunks": (_i, [_p, _ll, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     # N2 (host function)
     "td_gpkg_append": (_i, [C.c_char_p, C.c_char_p, _i, _p, _p, _ll, _i, _p, _p, _p, _p]),
     # P0a
@@ -90,6 +93,8 @@ OWN_KERNELS = {
     "td_bbox_nms_ordered": 7, "td_bbox_nms_ordered_dyn": 7, "td_scan_clamp": 1, "td_compact_flags": 1, "td_compact_nonneg": 1,
     "td_ring_tail": 1, "td_ring_offsets": 1, "td_gather_rows": 1, "td_containment": 4, "td_mask_iou_clean": 5, "td_crown_stats": 1, "td_centroids": 2, "td_crown_height_summary": 1, "td_select_crowns": 2,
     "td_round_coords": 1, "td_select_head": 1, "td_chain_predict": 14, "td_chain_post": 28, "td_tile_cut_normalize": 1, "td_seam_crop": 1, "td_tile_plan_create": 0, "td_forest_predicates": 1, "td_ring_is_simple": 1,
+    "td_tiff_lzw_encode": (_ll, [_p, _ll, _p, _ll]),
+    "td_tiff_lzw_decode_batch": 1, "td_tiff_place_chunks": 1,
 }
 launch_count = 0
 

@@ -18,7 +18,9 @@ from . import _lib, ops, pipeline, tiling
 
 @dataclass
 class HostImage:
-    """Everything the path consumes for one image, in host memory."""
+    """Everything the path consumes for one image, in host memory.  ``rgbi`` / ``ndsm`` may also be DEVICE tensors
+    (a raster decoded on the GPU, geotiff.read_device): ``ready[name]`` is then the CUDA event after which the
+    tensor is complete."""
     rgbi: torch.Tensor            # (4, H, W) uint8  (pinned for async copies)
     transform: tuple
     ndsm: torch.Tensor            # (h, w) float32
@@ -29,6 +31,7 @@ class HostImage:
     probs: torch.Tensor           # (N, 28, 28) f32
     inst_tile: torch.Tensor       # (N,) i32
     tile_dims: torch.Tensor       # (T, 4) i32
+    ready: dict = None            # name -> torch.cuda.Event for rasters that are already on the device
 
     @classmethod
     def from_scene(cls, sc, pin=True):
@@ -41,7 +44,8 @@ class HostImage:
 
     def h2d_bytes(self):
         return sum(x.numel() * x.element_size() for x in
-                   (self.rgbi, self.ndsm, self.boxes_net, self.scores, self.probs, self.inst_tile, self.tile_dims))
+                   (self.rgbi, self.ndsm, self.boxes_net, self.scores, self.probs, self.inst_tile, self.tile_dims)
+                   if not x.is_cuda)
 
 
 class TileTables:
@@ -158,6 +162,11 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     cs.wait_stream(main)
     persistent = runner is not None         # images of one runner share a tiling: stage them at fixed addresses
     def h2d(name, t):
+        if t.is_cuda:                       # decoded on the device already
+            ev = (img.ready or {}).get(name)
+            if ev is not None:
+                cs.wait_event(ev)
+            return t
         if not persistent:
             return t.to(device, non_blocking=True)
         dst = _device_buffer(device, name, t)

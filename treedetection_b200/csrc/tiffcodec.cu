@@ -72,3 +72,277 @@ extern "C" long long td_tiff_lzw_decode(const unsigned char* src, long long n_sr
   }
   return out;
 }
+
+// The encoder of the same format (TIFF 6.0 section 13 as libtiff writes it: ClearCode first, MSB-first codes,
+// "early change", ClearCode again when the table is full, EOI last), so that this package can WRITE the
+// compressed rasters its readers are measured on.  Returns the bytes written or a negative TD_ERR_* code;
+// cap >= n_src * 3 / 2 + 16 always suffices.
+extern "C" long long td_tiff_lzw_encode(const unsigned char* src, long long n_src, unsigned char* dst, long long cap) {
+  if (!src || !dst || n_src < 0 || cap < 0) { td_set_error("td_tiff_lzw_encode: bad argument"); return TD_ERR_ARG; }
+  constexpr int kHash = 1 << 14;                       // open addressing, <= 3837 live entries
+  static thread_local int32_t hkey[kHash];
+  static thread_local uint16_t hval[kHash];
+  uint64_t acc = 0;
+  int nacc = 0;
+  long long out = 0;
+  int width = 9, next = 258;
+  bool overflow = false;
+  auto put = [&](int code) {
+    acc = (acc << width) | (uint64_t)code;
+    nacc += width;
+    while (nacc >= 8) {
+      if (out < cap) dst[out] = (unsigned char)(acc >> (nacc - 8)); else overflow = true;
+      ++out;
+      nacc -= 8;
+    }
+  };
+  auto reset = [&] { for (int i = 0; i < kHash; ++i) hkey[i] = -1; width = 9; next = 258; };
+  reset();
+  put(256);
+  if (n_src > 0) {
+    int omega = src[0];
+    for (long long i = 1; i < n_src; ++i) {
+      const int k = src[i];
+      const int32_t key = (omega << 8) | k;
+      uint32_t h = ((uint32_t)key * 2654435761u) >> 18;
+      bool found = false;
+      while (hkey[h] >= 0) {
+        if (hkey[h] == key) { found = true; break; }
+        h = (h + 1) & (kHash - 1);
+      }
+      if (found) { omega = hval[h]; continue; }
+      put(omega);
+      hkey[h] = key;
+      hval[h] = (uint16_t)next;
+      ++next;
+      if (next == 4094) { put(256); reset(); }        // table full (libtiff: CODE_MAX - 1)
+      else if (next > (1 << width) - 1) ++width;
+      omega = k;
+    }
+    put(omega);
+    // the decoder adds an entry after this code too (and may widen): keep in step before EOI (libtiff LZWPostEncode)
+    ++next;
+    if (next == 4094) { put(256); reset(); }
+    else if (next > (1 << width) - 1) ++width;
+  }
+  put(257);
+  if (nacc > 0) {
+    if (out < cap) dst[out] = (unsigned char)(acc << (8 - nacc)); else overflow = true;
+    ++out;
+  }
+  if (overflow) { td_set_error("td_tiff_lzw_encode: output buffer too small"); return TD_ERR_OVERFLOW; }
+  return out;
+}
+
+// ---- device side: every strip / tile of a raster decoded at once --------------------------------------------
+// A raster of 10 000 x 10 000 px has thousands of independent LZW streams.  One warp decodes one stream.  The
+// classic decoder walks a prefix chain per code (a pointer chase per output byte); here a table entry is
+// {position, length} of an EARLIER OCCURRENCE of its string in the decoded output -- entry `next` is the previous
+// string plus the first byte of the current one, and those bytes are contiguous in the output -- so emitting a code
+// is a short lane-parallel copy inside the output, and adding an entry is one shared-memory store.  The bit reader
+// keeps 64 bits in registers and loads the following 32 one refill ahead.  Same stream rules as the host decoder
+// above (MSB-first codes, 9..12 bits, early change, ClearCode 256, EOI 257, a stream may end without EOI).
+namespace {
+
+constexpr int kLzwPosBits = 20;                     // chunks of up to 1 MiB decoded bytes
+constexpr int kLzwMaxChunk = 1 << kLzwPosBits;
+
+struct LzwBatch {
+  const unsigned char* src;     // the file (or any buffer holding the compressed chunks), device memory
+  const long long* src_pos;     // (n) first byte of chunk k in src
+  const int* src_len;           // (n) compressed bytes of chunk k
+  int n;
+  unsigned char* dst;           // chunk k is decoded to dst + k * dst_stride
+  long long dst_stride;
+  const int* dst_len;           // (n) expected decoded bytes of chunk k (<= dst_stride, <= 1 MiB)
+  int* out_len;                 // (n) nullable: decoded bytes
+  int* status;                  // one int, set to a TD_ERR_* code by the first failing chunk
+};
+
+TD_D uint32_t lzw_load_be32(const unsigned char* s, long long ip, long long n) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) w = (w << 8) | (ip + b < n ? (uint32_t)__ldg(s + ip + b) : 0u);
+  return w;
+}
+
+__global__ void __launch_bounds__(32) lzw_decode_kernel(LzwBatch a) {
+  __shared__ uint32_t tab[4096];                    // length << 20 | position, codes >= 258
+  const int lane = threadIdx.x;
+  const int c = blockIdx.x;
+  if (c >= a.n) return;
+  const unsigned char* s = a.src + a.src_pos[c];
+  const long long n_src = a.src_len[c];
+  unsigned char* d = a.dst + (long long)c * a.dst_stride;
+  const int cap = a.dst_len[c];
+  const long long total_bits = 8 * n_src;
+  long long used = 0;
+  uint64_t buf = 0;
+  int nb = 0;
+  long long ip = 0;
+  uint32_t ahead = lzw_load_be32(s, 0, n_src);
+  ip = 4;
+  int width = 9, next = 258;
+  int ppos = -1, plen = 0;      // previous string in the output (ppos < 0: first code after a clear)
+  int cur = 0, err = 0;
+  for (;;) {
+    if (nb <= 32) {
+      buf |= (uint64_t)ahead << (32 - nb);
+      nb += 32;
+      ahead = lzw_load_be32(s, ip, n_src);
+      ip += 4;
+    }
+    if (used + width > total_bits) break;           // stream ended without EOI
+    const int code = (int)(buf >> (64 - width));
+    buf <<= width;
+    nb -= width;
+    used += width;
+    if (code == 257) break;
+    if (code == 256) { width = 9; next = 258; ppos = -1; continue; }
+    int slen;
+    if (ppos < 0) {
+      if (code >= 256) { err = TD_ERR_ARG; break; }
+      if (cur + 1 > cap) { err = TD_ERR_OVERFLOW; break; }
+      if (lane == 0) d[cur] = (unsigned char)code;
+      slen = 1;
+    } else {
+      if (code < 256) {
+        if (cur + 1 > cap) { err = TD_ERR_OVERFLOW; break; }
+        if (lane == 0) d[cur] = (unsigned char)code;
+        slen = 1;
+      } else if (code < next) {
+        const uint32_t e = tab[code];
+        const int spos = (int)(e & (kLzwMaxChunk - 1));
+        slen = (int)(e >> kLzwPosBits);
+        if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
+        for (int k = lane; k < slen; k += 32) d[cur + k] = d[spos + k];
+      } else if (code == next) {                    // KwKwK: string(prev) + first(prev)
+        slen = plen + 1;
+        if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
+        for (int k = lane; k < slen; k += 32) d[cur + k] = d[ppos + (k < plen ? k : 0)];
+      } else {
+        err = TD_ERR_ARG;
+        break;
+      }
+      if (next < 4096) {
+        // string(prev) + first byte of this string = the plen + 1 output bytes starting at ppos
+        if (lane == 0) tab[next] = ((uint32_t)(plen + 1) << kLzwPosBits) | (uint32_t)ppos;
+        ++next;
+        if (next >= (1 << width) - 1 && width < 12) ++width;
+      }
+    }
+    ppos = cur;
+    plen = slen;
+    cur += slen;
+    __syncwarp();                                   // the bytes and the entry are visible to the next copy
+  }
+  __syncwarp();
+  for (int k = cur + lane; k < cap; k += 32) d[k] = 0;   // a short stream leaves zeros (deterministic)
+  if (lane == 0) {
+    if (a.out_len) a.out_len[c] = cur;
+    if (err) atomicCAS(a.status, 0, err);
+  }
+}
+
+struct PlaceArgs {
+  const unsigned char* dec;     // decoded chunks, chunk k at dec + k * stride
+  long long stride;
+  unsigned char* out;           // (C, H, W) planar raster of `ssize`-byte samples
+  int C, H, W, ssize;
+  int planar;                   // TIFF PlanarConfiguration: 1 = chunky (samples interleaved), 2 = one plane per chunk
+  int chunk_rows, chunk_cols, nx, ny;
+  int predictor;                // 1 none, 2 horizontal differencing (8-bit samples)
+};
+
+// one warp per chunk row: undo the predictor (a per-channel running sum along the row, modulo 256) and scatter
+// the samples into the planar raster
+__global__ void __launch_bounds__(128) place_chunks_kernel(PlaceArgs a, int n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x;
+  if (k >= n_chunks) return;
+  const int per_plane = a.nx * a.ny;
+  const int plane = a.planar == 2 ? k / per_plane : 0;
+  const int rem = a.planar == 2 ? k % per_plane : k;
+  const int j = rem / a.nx, i = rem % a.nx;
+  const int spp = a.planar == 2 ? 1 : a.C;
+  const int y0 = j * a.chunk_rows, x0 = i * a.chunk_cols;
+  const int ncols = min(a.chunk_cols, a.W - x0);
+  const size_t plane_px = (size_t)a.H * a.W;
+  for (int r = blockIdx.y * 4 + (threadIdx.x >> 5); r < a.chunk_rows; r += gridDim.y * 4) {
+    const int y = y0 + r;
+    if (y >= a.H) break;
+    const unsigned char* row = a.dec + (size_t)k * a.stride + (size_t)r * a.chunk_cols * spp * a.ssize;
+    if (a.ssize == 4) {        // 32-bit samples, no predictor
+      const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row);
+      uint32_t* out4 = reinterpret_cast<uint32_t*>(a.out);
+      for (int t = lane; t < ncols * spp; t += 32) {
+        const int x = t / spp, ch = t - x * spp;
+        out4[(size_t)(plane + ch) * plane_px + (size_t)y * a.W + x0 + x] = row4[t];
+      }
+      continue;
+    }
+    if (a.predictor != 2) {
+      for (int t = lane; t < ncols * spp; t += 32) {
+        const int x = t / spp, ch = t - x * spp;
+        a.out[(size_t)(plane + ch) * plane_px + (size_t)y * a.W + x0 + x] = row[t];
+      }
+      continue;
+    }
+    // predictor 2: lane l owns columns [l * seg, (l + 1) * seg)
+    const int seg = (ncols + 31) / 32;
+    const int xa = min(lane * seg, ncols), xb = min(xa + seg, ncols);
+    uint32_t sum[4] = {0, 0, 0, 0};
+    for (int x = xa; x < xb; ++x)
+      for (int ch = 0; ch < spp; ++ch) sum[ch] += row[(size_t)x * spp + ch];
+    uint32_t off[4];
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v = sum[ch];
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      off[ch] = v - sum[ch];                        // exclusive
+    }
+    for (int x = xa; x < xb; ++x)
+      for (int ch = 0; ch < spp; ++ch) {
+        off[ch] += row[(size_t)x * spp + ch];
+        a.out[(size_t)(plane + ch) * plane_px + (size_t)y * a.W + x0 + x] = (unsigned char)off[ch];
+      }
+  }
+}
+
+}  // namespace
+
+extern "C" int td_tiff_lzw_decode_batch(const unsigned char* src, const long long* src_pos, const int* src_len,
+                                        int n_chunks, unsigned char* dst, long long dst_stride, const int* dst_len,
+                                        int* out_len, int* status, void* stream) {
+  TD_ARG(n_chunks >= 0);
+  if (n_chunks == 0) return TD_OK;
+  TD_ARG(src && src_pos && src_len && dst && dst_len && status && dst_stride > 0 && dst_stride <= kLzwMaxChunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  LzwBatch a{src, src_pos, src_len, n_chunks, dst, dst_stride, dst_len, out_len, status};
+  lzw_decode_kernel<<<n_chunks, 32, 0, st>>>(a);
+  TD_CHECK_LAUNCH("td_tiff_lzw_decode_batch");
+  return TD_OK;
+}
+
+extern "C" int td_tiff_place_chunks(const unsigned char* decoded, long long stride, int n_chunks, void* out, int bands,
+                                    int height, int width, int sample_size, int planar, int chunk_rows, int chunk_cols,
+                                    int predictor, void* stream) {
+  TD_ARG(n_chunks >= 0);
+  if (n_chunks == 0) return TD_OK;
+  TD_ARG(decoded && out && bands > 0 && height > 0 && width > 0 && chunk_rows > 0 && chunk_cols > 0 && stride > 0);
+  TD_ARG(sample_size == 1 || sample_size == 4);
+  TD_ARG(planar == 1 || planar == 2);
+  TD_ARG(predictor == 1 || (predictor == 2 && sample_size == 1));
+  TD_ARG(planar == 2 || bands <= 4);
+  const int nx = td_div_up(width, chunk_cols), ny = td_div_up(height, chunk_rows);
+  TD_ARG(n_chunks == nx * ny * (planar == 2 ? bands : 1));
+  PlaceArgs a{decoded, stride, (unsigned char*)out, bands, height, width, sample_size, planar, chunk_rows, chunk_cols,
+              nx, ny, predictor};
+  const int gy = chunk_rows >= 64 ? 8 : (chunk_rows >= 8 ? 2 : 1);
+  place_chunks_kernel<<<dim3(n_chunks, gy), 128, 0, (cudaStream_t)stream>>>(a, n_chunks);
+  TD_CHECK_LAUNCH("td_tiff_place_chunks");
+  return TD_OK;
+}

@@ -57,10 +57,12 @@ class _Session:
         self.pinned = {}           # (name, shape, dtype, parity) -> pinned staging tensor
         self.loader = None         # background decoder of the NEXT image's rasters and fixtures
         self.writer = None         # background writer of the PREVIOUS image's crown layers
+        self._loader_stream = None # CUDA stream of the decoder thread (device-side raster decode)
         self.timeline = []         # per image: seconds waited for the decoder, on the device, ... (bench.py e2e_files)
         self.stage_s = {}          # wall seconds per stage (read by bench.py's e2e_files)
         self.images = 0
         self.fallback_images = 0   # images that went through the stage-by-stage path
+        self.device_decoded = 0    # rasters decoded on the GPU (LZW strips / tiles, geotiff.read_device)
 
     def pinned_array(self, name, shape, dtype, parity):
         key = (name, tuple(shape), np.dtype(dtype).str, parity)
@@ -70,6 +72,21 @@ class _Session:
             t = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
             self.pinned[key] = t
         return t
+
+    def device_array(self, name, shape, dtype, parity, device):
+        """persistent device buffer of a raster decoded on the GPU (two parities: decode k + 1 while k runs)"""
+        key = ("dev", name, tuple(shape), np.dtype(dtype).str, parity)
+        t = self.pinned.get(key)
+        if t is None:
+            tdt = {"|u1": torch.uint8, "<f4": torch.float32}[np.dtype(dtype).str]
+            t = torch.empty(tuple(shape), dtype=tdt, device=device)
+            self.pinned[key] = t
+        return t
+
+    def loader_stream(self, device):
+        if self._loader_stream is None:
+            self._loader_stream = torch.cuda.Stream(device=device)
+        return self._loader_stream
 
     def pinned_copy(self, name, array, parity):
         """``array`` (host numpy) copied into a pinned staging buffer that grows by capacity"""
@@ -291,10 +308,9 @@ class _FastPath:
         rinfo, hinfo = geotiff.read_info(fp), geotiff.read_info(hpath)
         if rinfo.dtype != np.uint8 or rinfo.count < 4 or hinfo.dtype != np.float32:
             return None
-        rgbi = self.s.pinned_array("rgbi", (rinfo.count, rinfo.height, rinfo.width), np.uint8, parity)
-        geotiff.read(fp, out=rgbi.numpy())
-        ndsm = self.s.pinned_array("ndsm", (hinfo.count, hinfo.height, hinfo.width), np.float32, parity)
-        geotiff.read(hpath, out=ndsm.numpy())
+        ready, status = {}, []
+        rgbi = self._read_raster(fp, "rgbi", rinfo, np.uint8, parity, ready, status)
+        ndsm = self._read_raster(hpath, "ndsm", hinfo, np.float32, parity, ready, status)
         t1 = time.time()
         det = None
         if not getattr(self.predictor, "wants_tiles", False):
@@ -302,7 +318,28 @@ class _FastPath:
             det = {k: self.s.pinned_copy(k, getattr(raw, k), parity)
                    for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
         return {"tiles": tiles, "rgbi": rgbi, "rinfo": rinfo, "ndsm": ndsm[0], "hinfo": hinfo, "det": det,
-                "decode_s": t1 - t0, "fixtures_s": time.time() - t1}
+                "ready": ready, "status": status, "decode_s": t1 - t0, "fixtures_s": time.time() - t1}
+
+    def _read_raster(self, path, name, info, dtype, parity, ready, status):
+        """One raster into the staging buffers of ``parity``: LZW-compressed files are decoded ON THE DEVICE
+        (geotiff.read_device: the compressed bytes cross PCIe, one warp per strip / tile), everything else goes
+        through the host reader into pinned memory."""
+        shape = (info.count, info.height, info.width)
+        if not self.config.get("host_decode", False) and geotiff.device_decodable(path):
+            out = self.s.device_array(name, shape, dtype, parity, self.dev)
+            stream = self.s.loader_stream(self.dev)
+            with torch.cuda.stream(stream):
+                # staging buffers per (parity, raster): the copies of one raster are still in flight while the
+                # next one is read
+                res = geotiff.read_device(path, self.dev, out=out, slot=2 * parity + (name != "rgbi"))
+                if res is not None:
+                    self.s.device_decoded += 1
+                    ready[name] = stream.record_event()
+                    status.append((path, res[2]))
+                    return out
+        host = self.s.pinned_array(name, shape, dtype, parity)
+        geotiff.read(path, out=host.numpy())
+        return host
 
     def prefetch(self, fp, tiles_path):
         if fp is not None and fp not in self.pending:
@@ -367,12 +404,15 @@ class _FastPath:
             self.s.runners[key] = pipeline.ChainRunner(self.p)
         tables, p1_out = self.s.tables[key]
         img = api.HostImage(data["rgbi"], rinfo.transform, data["ndsm"], hinfo.transform, tiles, det["boxes_net"],
-                            det["scores"], det["probs"], det["inst_tile"], det["tile_dims"])
+                            det["scores"], det["probs"], det["inst_tile"], det["tile_dims"], ready=data["ready"])
         t0 = time.time()
         # the staging buffers of the OTHER parity are free (their image is through run_image): decode the next image
         # into them while this one is on the GPU
         self.prefetch(next_fp, tiles_path)
         host, _ = api.run_image(img, self.p, self.dev, tables, p1_out, runner=self.s.runners[key], want_table=True)
+        for path, st in data["status"]:          # run_image has synchronised: the decoder's verdict is in
+            if int(st.item()) != 0:
+                raise ValueError(f"{path}: corrupt LZW stream (device decoder status {int(st.item())})")
         t1 = time.time()
         if self.config.get("keep_intermediate", False) and int(det["scores"].numel()):
             raw = synth_detections(det, tiles)
@@ -873,6 +913,7 @@ def process_files(config):
             session.stage_s.update(preprocess=t1 - t0, predict=t2 - t1, postprocess=t3 - t2, cleanup=time.time() - t3)
             config["_last_session_stats"] = {"stage_s": dict(session.stage_s), "images": session.images,
                                              "fallback_images": session.fallback_images,
+                                             "device_decoded_rasters": session.device_decoded,
                                              "timeline": list(session.timeline), "t0": t0}
     finally:
         if own_session:

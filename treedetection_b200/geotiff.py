@@ -141,6 +141,146 @@ def read(path, window=None, out=None):
                 pass
 
 
+_DEVICE_LZW_MAX_CHUNK = 1 << 20     # td_tiff_lzw_decode_batch: decoded bytes per strip / tile
+
+
+def device_decodable(path):
+    """True when :func:`read_device` can decode the raster on the GPU: LZW strips / tiles of at most 1 MiB,
+    8-bit samples (predictor 1 or 2, up to 4 interleaved bands or any number of planes) or 32-bit samples
+    (predictor 1)."""
+    import mmap
+    with open(path, "rb") as f:
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    try:
+        return _device_plan(buf) is not None
+    except Exception:
+        return False
+    finally:
+        buf.close()
+
+
+def _device_plan(buf):
+    bo = "<" if buf[:2] == b"II" else ">"
+    if struct.unpack(bo + "H", buf[2:4])[0] != 42:
+        return None
+    t = _read_ifd(buf, bo)
+    info = _info_from_tags(t)
+    comp, pred, planar = int(t.get(259, (1,))[0]), int(t.get(317, (1,))[0]), int(t.get(284, (1,))[0])
+    size = info.dtype.itemsize
+    if comp != 5 or size not in (1, 4) or pred not in (1, 2) or (pred == 2 and size != 1) or (size == 4 and bo != "<"):
+        return None
+    W, H, C = info.width, info.height, info.count
+    if planar != 2 and C > 4:
+        return None
+    spp = 1 if planar == 2 else C
+    tiled = 322 in t
+    if tiled:
+        chunk_rows, chunk_cols = int(t[323][0]), int(t[322][0])
+        offs, cnts = t[324], t[325]
+    else:
+        chunk_rows, chunk_cols = min(int(t.get(278, (H,))[0]), H), W
+        offs, cnts = t[273], t[279]
+    chunk_bytes = chunk_rows * chunk_cols * spp * size
+    if chunk_bytes > _DEVICE_LZW_MAX_CHUNK:
+        return None
+    nx, ny = (W + chunk_cols - 1) // chunk_cols, (H + chunk_rows - 1) // chunk_rows
+    n = nx * ny * (C if planar == 2 else 1)
+    if len(offs) != n or len(cnts) != n:
+        return None
+    rows = np.full(ny, chunk_rows, dtype=np.int64)
+    if not tiled:
+        rows[-1] = H - (ny - 1) * chunk_rows
+    dst_len = np.tile(np.repeat(rows * chunk_cols * spp * size, nx), C if planar == 2 else 1).astype(np.int32)
+    return {"info": info, "pred": pred, "planar": planar, "chunk_rows": chunk_rows, "chunk_cols": chunk_cols,
+            "chunk_bytes": chunk_bytes, "n": n, "src_pos": np.asarray(offs, dtype=np.int64),
+            "src_len": np.asarray(cnts, dtype=np.int32), "dst_len": dst_len}
+
+
+_dev_scratch = {}
+
+
+def _scratch(device, name, nbytes, pinned=False):
+    """byte buffers re-used across images (pinned host staging of the compressed file, device copies, decoded chunks)"""
+    import torch
+    key = (str(device), name, pinned)
+    t = _dev_scratch.get(key)
+    if t is None or t.numel() < nbytes:
+        cap = int(nbytes * 1.25) + 4096
+        t = torch.empty((cap,), dtype=torch.uint8, pin_memory=True) if pinned else \
+            torch.empty((cap,), dtype=torch.uint8, device=device)
+        _dev_scratch[key] = t
+    return t
+
+
+def read_device(path, device, out=None, slot=0):
+    """The raster decoded ON THE DEVICE: the file travels over PCIe still LZW-compressed, every strip / tile is one
+    warp of ``td_tiff_lzw_decode_batch``, ``td_tiff_place_chunks`` undoes the predictor and writes the planar
+    (bands, H, W) tensor.  Returns (tensor, GeoInfo, status), or None when the file needs the host reader (see
+    :func:`device_decodable`).  Work is enqueued on the current stream; ``out``: optional destination tensor;
+    ``slot``: which set of staging buffers to use -- the call returns while the copies out of the pinned staging
+    buffer are still in flight, so a caller that reads several rasters back to back gives each its own slot (and
+    synchronises before it re-uses one).  The third return value is a one-element int32 device tensor: non-zero
+    once the stream has run means a corrupt or oversized LZW stream (TD_ERR_*)."""
+    import torch
+
+    from . import _lib
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        import mmap
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            plan = _device_plan(buf)
+        finally:
+            buf.close()
+        if plan is None:
+            return None
+        # the compressed file -> pinned staging (parallel pread) -> device
+        host = _scratch(device, f"file{slot}", size, pinned=True)
+        mv = memoryview(host.numpy())[:size]
+        step = 8 << 20
+
+        def fill(lo):
+            done = lo
+            hi = min(lo + step, size)
+            while done < hi:
+                got = os.preadv(f.fileno(), [mv[done:hi]], done)
+                if got <= 0:
+                    raise ValueError("short read")
+                done += got
+        if size > step:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=8) as ex:
+                list(ex.map(fill, range(0, size, step)))
+        else:
+            fill(0)
+    info = plan["info"]
+    n = plan["n"]
+    dev_file = _scratch(device, f"file{slot}", size)
+    dev_file[:size].copy_(host[:size], non_blocking=True)
+    meta = torch.from_numpy(np.concatenate([plan["src_pos"].view(np.int32), plan["src_len"], plan["dst_len"]]))
+    meta_pin = _scratch(device, f"meta{slot}", meta.numel() * 4, pinned=True)[:meta.numel() * 4].view(torch.int32)
+    meta_pin.copy_(meta)
+    meta_dev = _scratch(device, f"meta{slot}", meta.numel() * 4 + 64)
+    meta_dev = meta_dev[:meta.numel() * 4].view(torch.int32)
+    meta_dev.copy_(meta_pin, non_blocking=True)
+    src_pos = meta_dev[:2 * n].view(torch.int64)
+    src_len, dst_len = meta_dev[2 * n:3 * n], meta_dev[3 * n:4 * n]
+    stride = plan["chunk_bytes"]
+    decoded = _scratch(device, "decoded", n * stride)
+    status = _scratch(device, f"status{slot}", 64)[:4].view(torch.int32)
+    tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.float32): torch.float32}[info.dtype]
+    if out is None:
+        out = torch.empty((info.count, info.height, info.width), dtype=tdt, device=device)
+    elif tuple(out.shape) != (info.count, info.height, info.width) or out.dtype != tdt or not out.is_cuda:
+        raise ValueError("read_device: out does not match the raster")
+    st = torch.cuda.current_stream(device).cuda_stream
+    _lib.call("td_tiff_lzw_decode_batch", dev_file.data_ptr(), src_pos.data_ptr(), src_len.data_ptr(), n,
+              decoded.data_ptr(), stride, dst_len.data_ptr(), None, status.data_ptr(), st)
+    _lib.call("td_tiff_place_chunks", decoded.data_ptr(), stride, n, out.data_ptr(), info.count, info.height, info.width,
+              info.dtype.itemsize, plan["planar"], plan["chunk_rows"], plan["chunk_cols"], plan["pred"], st)
+    return out, info, status
+
+
 def _read_mapped(buf, window, out, fd=None):
     bo = "<" if buf[:2] == b"II" else ">"
     if struct.unpack(bo + "H", buf[2:4])[0] != 42:
@@ -262,9 +402,22 @@ def _read_mapped(buf, window, out, fd=None):
     return out, info
 
 
-def write(path, array, transform, epsg=None, nodata=None):
-    """Uncompressed, little-endian, planar (band-sequential) strips -- one strip per band row
-    block, so that a device tensor's (bands, H, W) layout is written without a transpose."""
+def _lzw_encode(raw: bytes) -> bytes:
+    import ctypes as C
+    from . import _lib
+    cap = len(raw) * 3 // 2 + 16
+    dst = C.create_string_buffer(cap)
+    n = _lib.lib().td_tiff_lzw_encode(raw, len(raw), dst, cap)
+    if n < 0:
+        _lib.check(int(n), "td_tiff_lzw_encode")
+    return dst.raw[:n]
+
+
+def write(path, array, transform, epsg=None, nodata=None, compression=None, predictor=1):
+    """Little-endian, planar (band-sequential) strips -- one strip per band row block, so that a device tensor's
+    (bands, H, W) layout is written without a transpose.  ``compression``: None (strips of 4 MiB) or ``"lzw"``
+    (td_tiff_lzw_encode on a thread pool, strips of at most 128 KiB so that a raster has thousands of independent
+    streams; ``predictor`` 2 = horizontal differencing, 8-bit samples only)."""
     arr = np.ascontiguousarray(array)
     if arr.ndim == 2:
         arr = arr[None]
@@ -272,7 +425,12 @@ def write(path, array, transform, epsg=None, nodata=None):
     dt = arr.dtype
     fmt = {"u": 1, "i": 2, "f": 3}[dt.kind]
     bits = dt.itemsize * 8
-    rps = max(1, min(H, (1 << 22) // max(1, W * dt.itemsize)))
+    if compression not in (None, "lzw"):
+        raise ValueError(f"unsupported compression {compression!r}")
+    if predictor not in (1, 2) or (predictor == 2 and (compression is None or dt.itemsize != 1)):
+        raise ValueError("predictor 2 needs LZW compression and 8-bit samples")
+    strip_target = (1 << 22) if compression is None else (1 << 17)
+    rps = max(1, min(H, strip_target // max(1, W * dt.itemsize)))
     ns = (H + rps - 1) // rps
     a, b, c, d, e, f = transform
     entries = []
@@ -288,8 +446,10 @@ def write(path, array, transform, epsg=None, nodata=None):
             raw = struct.pack("<" + fmtc * cnt, *values)
         entries.append((tag, typ, cnt, raw))
 
-    add(256, 4, [W]); add(257, 4, [H]); add(258, 3, [bits] * C); add(259, 3, [1])
+    add(256, 4, [W]); add(257, 4, [H]); add(258, 3, [bits] * C); add(259, 3, [1 if compression is None else 5])
     add(262, 3, [1]); add(277, 3, [C]); add(278, 4, [rps]); add(284, 3, [2]); add(339, 3, [fmt] * C)
+    if predictor != 1:
+        add(317, 3, [predictor])
     if C > 1:
         add(338, 3, [0] * (C - 1))
     add(33550, 12, [abs(a), abs(e), 0.0])
@@ -299,6 +459,20 @@ def write(path, array, transform, epsg=None, nodata=None):
     if nodata is not None:
         add(42113, 2, repr(float(nodata)))
     strip_bytes = [min(rps, H - s * rps) * W * dt.itemsize for s in range(ns)] * C
+    strips = None
+    if compression == "lzw":
+        le = arr.astype(dt.newbyteorder("<"), copy=False)
+
+        def pack(k):
+            p, s_ = divmod(k, ns)
+            block = le[p, s_ * rps:min((s_ + 1) * rps, H)]
+            if predictor == 2:
+                block = np.diff(block, axis=1, prepend=np.zeros((block.shape[0], 1), dtype=block.dtype))
+            return _lzw_encode(np.ascontiguousarray(block).tobytes())
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            strips = list(ex.map(pack, range(ns * C)))
+        strip_bytes = [len(b) for b in strips]
     add(273, 4, [0] * (ns * C)); add(279, 4, strip_bytes)
     entries.sort(key=lambda x: x[0])
     ifd_off = 8
@@ -334,4 +508,8 @@ def write(path, array, transform, epsg=None, nodata=None):
         fh.write(struct.pack("<I", 0))
         fh.write(bytes(blob))
         fh.write(b"\x00" * (data_off - extra_off - len(blob)))
-        fh.write(arr.astype(dt.newbyteorder("<"), copy=False).tobytes())
+        if strips is None:
+            fh.write(arr.astype(dt.newbyteorder("<"), copy=False).tobytes())
+        else:
+            for b in strips:
+                fh.write(b)
