@@ -91,3 +91,30 @@ def test_corrupt_stream_sets_the_status(tmp_path, dev):
     got, _, status = geotiff.read_device(path, dev)
     torch.cuda.synchronize()
     assert int(status.item()) != 0
+
+
+def test_plain_reader_streams_uncompressed_strips_to_the_device(tmp_path, dev):
+    """geotiff.read_device_plain: file -> two-slot pinned ring -> device tensor, pieces smaller than a band (several
+    pieces per run, runs across bands), float32 and uint8; other layouts are declined"""
+    cases = _cases()
+    tf = (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0)
+    for name, piece in (("rgba", 100_000), ("rgba", 32 << 20), ("f32", 70_001), ("band", 4096)):
+        arr = cases[name]
+        path = str(tmp_path / f"{name}.tif")
+        geotiff.write(path, arr, tf, epsg=25832)
+        ref, rinfo = geotiff.read(path)
+        got, info = geotiff.read_device_plain(path, dev, piece=piece)
+        torch.cuda.synchronize()
+        assert info == rinfo
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+        out = torch.zeros(ref.shape, dtype=got.dtype, device=dev)
+        assert geotiff.read_device_plain(path, dev, out=out, slot=1, piece=piece)[0] is out
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    lzw = str(tmp_path / "lzw.tif")
+    geotiff.write(lzw, cases["rgba"], tf, epsg=25832, compression="lzw")
+    chunky = str(tmp_path / "chunky.tif")
+    Image.fromarray(np.ascontiguousarray(cases["rgba"].transpose(1, 2, 0))).save(chunky, format="TIFF")
+    assert geotiff.read_device_plain(lzw, dev) is None and geotiff.read_device_plain(chunky, dev) is None
+    assert geotiff.read_device_plain(lzw, dev, probe=True) is None
+    assert geotiff.read_device_plain(str(tmp_path / "rgba.tif"), dev, probe=True) is True

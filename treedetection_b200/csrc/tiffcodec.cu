@@ -159,77 +159,85 @@ struct LzwBatch {
   int* status;                  // one int, set to a TD_ERR_* code by the first failing chunk
 };
 
-TD_D uint32_t lzw_load_be32(const unsigned char* s, long long ip, long long n) {
-  uint32_t w = 0;
-#pragma unroll
-  for (int b = 0; b < 4; ++b) w = (w << 8) | (ip + b < n ? (uint32_t)__ldg(s + ip + b) : 0u);
-  return w;
-}
+// The per-code work is one serial dependency chain per warp (a few resident warps per scheduler), so its length in
+// INSTRUCTIONS is what bounds the decoder: 32-bit state, the compressed bytes staged through a 256-byte window in
+// shared memory (one coalesced load per ~200 codes, big-endian words), a code = one funnel shift of two window
+// words.
+constexpr int kLzwWin = 64;     // window words
 
 __global__ void __launch_bounds__(32) lzw_decode_kernel(LzwBatch a) {
   __shared__ uint32_t tab[4096];                    // length << 20 | position, codes >= 258
+  __shared__ uint32_t win[kLzwWin + 1];
   const int lane = threadIdx.x;
   const int c = blockIdx.x;
   if (c >= a.n) return;
   const unsigned char* s = a.src + a.src_pos[c];
-  const long long n_src = a.src_len[c];
+  const int n_src = a.src_len[c];
   unsigned char* d = a.dst + (long long)c * a.dst_stride;
   const int cap = a.dst_len[c];
-  const long long total_bits = 8 * n_src;
-  long long used = 0;
-  uint64_t buf = 0;
-  int nb = 0;
-  long long ip = 0;
-  uint32_t ahead = lzw_load_be32(s, 0, n_src);
-  ip = 4;
+  const int total_bits = 8 * n_src;                 // chunks are < 2^28 bytes
+  // window: words [wbase, wbase + kLzwWin) of the stream, byte-swapped; word kLzwWin is a copy of the first word of
+  // the next window so that a code may straddle the end
+  const int mis = (int)((uintptr_t)s & 3);          // the stream starts `mis` bytes into an aligned word
+  const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s - mis);
+  const int n_words = (mis + n_src + 3) >> 2;
+  int wbase = 0;
+  auto fill = [&](int base) {
+    for (int k = lane; k <= kLzwWin; k += 32) {
+      const int wi = base + k;
+      win[k] = wi < n_words ? __byte_perm(__ldg(s4 + wi), 0, 0x0123) : 0u;
+    }
+    __syncwarp();
+  };
+  fill(0);
+  int bitpos = 8 * mis;                             // in bits from s4
+  const int end_bits = bitpos + total_bits;
   int width = 9, next = 258;
   int ppos = -1, plen = 0;      // previous string in the output (ppos < 0: first code after a clear)
   int cur = 0, err = 0;
   for (;;) {
-    if (nb <= 32) {
-      buf |= (uint64_t)ahead << (32 - nb);
-      nb += 32;
-      ahead = lzw_load_be32(s, ip, n_src);
-      ip += 4;
+    int wi = (bitpos >> 5) - wbase;
+    if (wi >= kLzwWin) {
+      __syncwarp();
+      wbase += kLzwWin;
+      fill(wbase);
+      wi -= kLzwWin;
     }
-    if (used + width > total_bits) break;           // stream ended without EOI
-    const int code = (int)(buf >> (64 - width));
-    buf <<= width;
-    nb -= width;
-    used += width;
-    if (code == 257) break;
-    if (code == 256) { width = 9; next = 258; ppos = -1; continue; }
-    int slen;
-    if (ppos < 0) {
-      if (code >= 256) { err = TD_ERR_ARG; break; }
-      if (cur + 1 > cap) { err = TD_ERR_OVERFLOW; break; }
+    if (bitpos + width > end_bits) break;           // stream ended without EOI
+    const uint32_t hi = win[wi], lo = win[wi + 1];
+    const int code = (int)(__funnelshift_l(lo, hi, bitpos & 31) >> (32 - width));
+    bitpos += width;
+    int slen = 1;
+    if (code < 256) {                               // literal (the common case on imagery)
+      if (cur >= cap) { err = TD_ERR_OVERFLOW; break; }
       if (lane == 0) d[cur] = (unsigned char)code;
-      slen = 1;
+    } else if (code == 257) {
+      break;
+    } else if (code == 256) {
+      width = 9; next = 258; ppos = -1;
+      continue;
+    } else if (ppos < 0) {
+      err = TD_ERR_ARG;                             // a table code right after ClearCode
+      break;
+    } else if (code < next) {
+      const uint32_t e = tab[code];
+      const int spos = (int)(e & (kLzwMaxChunk - 1));
+      slen = (int)(e >> kLzwPosBits);
+      if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
+      for (int k = lane; k < slen; k += 32) d[cur + k] = d[spos + k];
+    } else if (code == next) {                      // KwKwK: string(prev) + first(prev)
+      slen = plen + 1;
+      if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
+      for (int k = lane; k < slen; k += 32) d[cur + k] = d[ppos + (k < plen ? k : 0)];
     } else {
-      if (code < 256) {
-        if (cur + 1 > cap) { err = TD_ERR_OVERFLOW; break; }
-        if (lane == 0) d[cur] = (unsigned char)code;
-        slen = 1;
-      } else if (code < next) {
-        const uint32_t e = tab[code];
-        const int spos = (int)(e & (kLzwMaxChunk - 1));
-        slen = (int)(e >> kLzwPosBits);
-        if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
-        for (int k = lane; k < slen; k += 32) d[cur + k] = d[spos + k];
-      } else if (code == next) {                    // KwKwK: string(prev) + first(prev)
-        slen = plen + 1;
-        if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
-        for (int k = lane; k < slen; k += 32) d[cur + k] = d[ppos + (k < plen ? k : 0)];
-      } else {
-        err = TD_ERR_ARG;
-        break;
-      }
-      if (next < 4096) {
-        // string(prev) + first byte of this string = the plen + 1 output bytes starting at ppos
-        if (lane == 0) tab[next] = ((uint32_t)(plen + 1) << kLzwPosBits) | (uint32_t)ppos;
-        ++next;
-        if (next >= (1 << width) - 1 && width < 12) ++width;
-      }
+      err = TD_ERR_ARG;
+      break;
+    }
+    if (ppos >= 0 && next < 4096) {
+      // string(prev) + first byte of this string = the plen + 1 output bytes starting at ppos
+      if (lane == 0) tab[next] = ((uint32_t)(plen + 1) << kLzwPosBits) | (uint32_t)ppos;
+      ++next;
+      if (next >= (1 << width) - 1 && width < 12) ++width;
     }
     ppos = cur;
     plen = slen;

@@ -337,6 +337,17 @@ class _FastPath:
                     ready[name] = stream.record_event()
                     status.append((path, res[2]))
                     return out
+        if self.config.get("streaming_read", False) and geotiff.read_device_plain(path, self.dev, probe=True):
+            # opt-in (config key streaming_read): uncompressed planar strips through a small pinned ring instead of
+            # a raster-sized pinned staging buffer -- 0.2 s less for the first image (no 1.8 GB to pin), 20 % more
+            # per image afterwards (measured, e2e_files)
+            out = self.s.device_array(name, shape, dtype, parity, self.dev)
+            stream = self.s.loader_stream(self.dev)
+            with torch.cuda.stream(stream):
+                res = geotiff.read_device_plain(path, self.dev, out=out, slot=2 * parity + (name != "rgbi"))
+                if res is not None:
+                    ready[name] = stream.record_event()
+                    return out
         host = self.s.pinned_array(name, shape, dtype, parity)
         geotiff.read(path, out=host.numpy())
         return host

@@ -224,6 +224,8 @@ def read_device(path, device, out=None, slot=0):
     import torch
 
     from . import _lib
+    import time
+    t_begin = time.perf_counter()
     size = os.path.getsize(path)
     with open(path, "rb") as f:
         import mmap
@@ -253,6 +255,7 @@ def read_device(path, device, out=None, slot=0):
                 list(ex.map(fill, range(0, size, step)))
         else:
             fill(0)
+    t_read = time.perf_counter()
     info = plan["info"]
     n = plan["n"]
     dev_file = _scratch(device, f"file{slot}", size)
@@ -278,7 +281,112 @@ def read_device(path, device, out=None, slot=0):
               decoded.data_ptr(), stride, dst_len.data_ptr(), None, status.data_ptr(), st)
     _lib.call("td_tiff_place_chunks", decoded.data_ptr(), stride, n, out.data_ptr(), info.count, info.height, info.width,
               info.dtype.itemsize, plan["planar"], plan["chunk_rows"], plan["chunk_cols"], plan["pred"], st)
+    if os.environ.get("TREEDET_TRACE_TIFF"):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        t_sync = time.perf_counter()
+        ev[0].record()
+        _lib.call("td_tiff_lzw_decode_batch", dev_file.data_ptr(), src_pos.data_ptr(), src_len.data_ptr(), n,
+                  decoded.data_ptr(), stride, dst_len.data_ptr(), None, status.data_ptr(), st)
+        ev[1].record()
+        torch.cuda.synchronize()
+        print(f"read_device {os.path.basename(path)}: file -> pinned {t_read - t_begin:.3f} s, enqueue + H2D + kernels "
+              f"{t_sync - t_read:.3f} s, decode kernel alone {ev[0].elapsed_time(ev[1]):.1f} ms, {n} chunks")
     return out, info, status
+
+
+_io_pool = None
+
+
+def _pool():
+    global _io_pool
+    if _io_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _io_pool = ThreadPoolExecutor(max_workers=8)
+    return _io_pool
+
+
+def _pread_into(fd, mv, file_off):
+    done = 0
+    while done < len(mv):
+        got = os.preadv(fd, [mv[done:]], file_off + done)
+        if got <= 0:
+            raise ValueError("truncated TIFF")
+        done += got
+
+
+def read_device_plain(path, device, out=None, slot=0, piece=32 << 20, probe=False):
+    """An UNCOMPRESSED planar (or single-band) strip raster straight to the device: the file is read in pieces of
+    32 MiB into a two-slot pinned ring (8 threads of ``pread``) and every piece is copied to its place in the
+    (bands, H, W) device tensor while the next one is read -- no raster-sized pinned staging buffer (pinning 1 GB
+    costs ~0.5 s), and the H2D copies hide behind the reads.  Returns (tensor, GeoInfo) or None when the layout
+    needs the host reader (compression, chunky pixels, tiles, a predictor, big-endian samples).  ``probe``: only
+    answer whether the layout qualifies (True / None)."""
+    import mmap
+
+    import torch
+    with open(path, "rb") as f:
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            bo = "<" if buf[:2] == b"II" else ">"
+            if struct.unpack(bo + "H", buf[2:4])[0] != 42:
+                return None
+            t = _read_ifd(buf, bo)
+            info = _info_from_tags(t)
+        finally:
+            buf.close()
+        comp, pred, planar = int(t.get(259, (1,))[0]), int(t.get(317, (1,))[0]), int(t.get(284, (1,))[0])
+        W, H, C = info.width, info.height, info.count
+        tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.float32): torch.float32}.get(info.dtype)
+        if comp != 1 or pred != 1 or 322 in t or (planar != 2 and C > 1) or tdt is None or \
+                (bo != "<" and info.dtype.itemsize > 1):
+            return None
+        rps = min(int(t.get(278, (H,))[0]), H)
+        ns = (H + rps - 1) // rps
+        offs, cnts = t[273], t[279]
+        if len(offs) != ns * C:
+            return None
+        row_bytes = W * info.dtype.itemsize
+        # runs of strips that are consecutive in the file AND in the destination
+        runs = []          # [file offset, bytes, destination byte offset]
+        for k in range(ns * C):
+            p, s_ = divmod(k, ns)
+            nbytes = min(rps, H - s_ * rps) * row_bytes
+            if cnts[k] < nbytes:
+                return None
+            dst = (p * H + s_ * rps) * row_bytes
+            if runs and runs[-1][0] + runs[-1][1] == offs[k] and runs[-1][2] + runs[-1][1] == dst:
+                runs[-1][1] += nbytes
+            else:
+                runs.append([offs[k], nbytes, dst])
+        if probe:
+            return True
+        if out is None:
+            out = torch.empty((C, H, W), dtype=tdt, device=device)
+        elif tuple(out.shape) != (C, H, W) or out.dtype != tdt or not out.is_cuda or not out.is_contiguous():
+            raise ValueError("read_device_plain: out does not match the raster")
+        flat = out.view(-1).view(torch.uint8)
+        ring = _scratch(device, f"ring{slot}", 2 * piece, pinned=True)
+        ring_np = memoryview(ring.numpy())
+        events = [None, None]
+        pool, k = _pool(), 0
+        for file_off, nbytes, dst in runs:
+            for lo in range(0, nbytes, piece):
+                n = min(piece, nbytes - lo)
+                half = k & 1
+                if events[half] is not None:
+                    events[half].synchronize()           # the copy out of this half of the ring is done
+                base = half * piece
+                step = max(1 << 20, -(-n // 8))
+                list(pool.map(lambda a: _pread_into(f.fileno(), ring_np[base + a:base + min(a + step, n)],
+                                                    file_off + lo + a), range(0, n, step)))
+                flat[dst + lo:dst + lo + n].copy_(ring[base:base + n], non_blocking=True)
+                events[half] = torch.cuda.current_stream(device).record_event()
+                k += 1
+        for ev in events:                                # the ring may be re-used by the next call
+            if ev is not None:
+                ev.synchronize()
+    return out, info
 
 
 def _read_mapped(buf, window, out, fd=None):
