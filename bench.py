@@ -298,6 +298,8 @@ def e2e_files(sc, n_images, label, compression=None):
             per_image = (tl[-1]["t_out"] - tl[k0]["t_out"]) / (len(tl) - 1 - k0)
             steady = {"s_per_image": round(per_image, 4), "value": (area / n_images) / per_image, "unit": UNIT,
                       "first_image_s": round(tl[0]["t_out"] - stats.get("t0", tl[0]["t_in"]), 3),
+                      "first_image_breakdown_s": {k: round(tl[0][k], 3) for k in
+                                                  ("wait_decode_s", "decode_s", "fixtures_s", "tables_s", "device_s")},
                       "per_image_s": {k: round(statistics.mean(t[k] for t in tl[k0 + 1:]), 4)
                                       for k in ("wait_decode_s", "decode_s", "fixtures_s", "tables_s", "device_s")}}
         return {"workload": label, "images": n_images, "value": area / wall, "unit": UNIT, "wall_s": wall,

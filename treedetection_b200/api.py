@@ -74,7 +74,10 @@ class TileTables:
 
     def plan(self, image):
         """P1 plan (device tile tables) for rasters shaped like ``image``; built once."""
-        key = (image.element_size(), image.shape[1], image.shape[2])
+        return self.plan_for(image.element_size(), image.shape[1], image.shape[2])
+
+    def plan_for(self, elem_size, height, width):
+        key = (int(elem_size), int(height), int(width))
         if key not in self._plans:
             self._plans[key] = ops.TilePlan(self.win, self.net, *key)
         return self._plans[key]
@@ -143,7 +146,7 @@ def table_to_host(t: pipeline.CrownTable):
 
 
 def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: TileTables = None, p1_out=None,
-              with_p1=True, runner: pipeline.ChainRunner = None, want_table=False):
+              with_p1=True, runner: pipeline.ChainRunner = None, want_table=False, on_h2d=None):
     """Host buffers in, final crowns (host numpy) out.  ``p1_out``: optional reusable
     device buffer for the normalised tiles (they feed the predictor, not this path).
     ``runner``: a :class:`pipeline.ChainRunner` kept across images of the same tiling -- P2-P9 are
@@ -153,7 +156,8 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
     The three host->device transfers ride a copy stream in the order the stages need them
     (ROI-head outputs, RGBI, nDSM) and the compute streams wait on one event per group: P2-P4
     overlap the RGBI copy, P1 (own stream), P5 and the statistics-free part of P6-P9 overlap the
-    nDSM copy; only the per-crown statistics wait for the nDSM."""
+    nDSM copy; only the per-crown statistics wait for the nDSM.  ``on_h2d(event)``: called once the copies are
+    enqueued, with the event after which the host buffers of ``img`` may be overwritten."""
     if not _lib.cuda_available():
         raise _lib.TreedetError("run_image needs a CUDA device (there is no CPU fallback)")
     tables = tables or TileTables(img.tiles, device, params.shift)
@@ -179,6 +183,8 @@ def run_image(img: HostImage, params: pipeline.PipelineParams, device, tables: T
         ev_rgbi = cs.record_event()
         ndsm = h2d("ndsm", img.ndsm)
         ev_ndsm = cs.record_event()
+    if on_h2d is not None:       # every copy out of the caller's host buffers is enqueued: they are free after ev_ndsm
+        on_h2d(ev_ndsm)
     if not persistent:
         for t in (*det.values(), rgbi, ndsm):
             t.record_stream(main)

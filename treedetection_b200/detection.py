@@ -275,7 +275,7 @@ class _FastPath:
 
     MAX_PENDING_WRITES = 3     # images whose layers may be queued for the writer threads
 
-    def __init__(self, config, session, dev, params, predictor, stitched_path, output_path, logger):
+    def __init__(self, config, session, dev, params, predictor, stitched_path, output_path, logger, n_images=1):
         from concurrent.futures import ThreadPoolExecutor
         self.config, self.s, self.dev, self.p = config, session, dev, params
         self.predictor, self.stitched_path, self.output_path, self.logger = predictor, stitched_path, output_path, logger
@@ -287,6 +287,15 @@ class _FastPath:
         self.writes = []           # (image path, Future of _write), oldest first
         self.failed = set()        # images whose layers could not be written
         self.parity = 0
+        # ONE set of pinned host staging buffers (pinning memory costs ~0.5 s / GB and stalls other CUDA calls while
+        # it happens): the decoder thread may overwrite them as soon as the previous image's host->device copies
+        # are done -- run_image reports that through `on_h2d` a few milliseconds after it starts
+        # A long file list amortises a second set (the decoder then never waits for the copies: ~12 ms per image).
+        import threading
+        self.two_sets = n_images >= 32
+        self.h2d_gate = threading.Event()
+        self.h2d_gate.set()
+        self.h2d_event = None
         image_pattern = re.compile(config.get("image_regex") or "(\\d+)\\.tif")
         height_pattern = re.compile(config.get("height_data_regex") or "(\\d+)\\.tif")
         self.patterns = (image_pattern, height_pattern, re.compile(config["image_merged_regex"]),
@@ -308,6 +317,10 @@ class _FastPath:
         rinfo, hinfo = geotiff.read_info(fp), geotiff.read_info(hpath)
         if rinfo.dtype != np.uint8 or rinfo.count < 4 or hinfo.dtype != np.float32:
             return None
+        if not self.two_sets:                         # the previous image's copies out of the staging buffers
+            self.h2d_gate.wait()
+            if self.h2d_event is not None:
+                self.h2d_event.synchronize()
         ready, status = {}, []
         rgbi = self._read_raster(fp, "rgbi", rinfo, np.uint8, parity, ready, status)
         ndsm = self._read_raster(hpath, "ndsm", hinfo, np.float32, parity, ready, status)
@@ -315,7 +328,7 @@ class _FastPath:
         det = None
         if not getattr(self.predictor, "wants_tiles", False):
             raw = self.predictor.raw_outputs(stem, tiles)
-            det = {k: self.s.pinned_copy(k, getattr(raw, k), parity)
+            det = {k: self.s.pinned_copy(k, getattr(raw, k), parity if self.two_sets else 0)
                    for k in ("boxes_net", "scores", "probs", "inst_tile", "tile_dims")}
         return {"tiles": tiles, "rgbi": rgbi, "rinfo": rinfo, "ndsm": ndsm[0], "hinfo": hinfo, "det": det,
                 "ready": ready, "status": status, "decode_s": t1 - t0, "fixtures_s": time.time() - t1}
@@ -348,9 +361,32 @@ class _FastPath:
                 if res is not None:
                     ready[name] = stream.record_event()
                     return out
-        host = self.s.pinned_array(name, shape, dtype, parity)
+        host = self.s.pinned_array(name, shape, dtype, parity if self.two_sets else 0)
         geotiff.read(path, out=host.numpy())
         return host
+
+    def warm(self, fp, tiles_path):
+        """Cold-start work that needs only the headers of the first image -- tile tables, the P1 plan and its
+        output buffer -- done on the calling thread while the decoder thread reads that image's pixels.  Purely an
+        optimisation: any failure is left to ``run``."""
+        try:
+            stem = Path(fp).stem
+            with open(os.path.join(tiles_path, stem + ".json")) as f:
+                tiles = json.load(f)
+            hpath, ipath = _match_rasters(stem, self.patterns, self.config["height_data_path"],
+                                          self.config["image_directory"], self.height_index, self.image_index)
+            if hpath is None or ipath is None:
+                return
+            rinfo, hinfo = geotiff.read_info(fp), geotiff.read_info(hpath)
+            key = (rinfo.height, rinfo.width, len(tiles), hinfo.height, hinfo.width)
+            if key not in self.s.tables:
+                tables = api.TileTables(tiles, self.dev, self.p.shift)
+                self.s.tables[key] = (tables, torch.empty((tables.p1_floats,), dtype=torch.float32, device=self.dev))
+                self.s.runners[key] = pipeline.ChainRunner(self.p)
+                if rinfo.dtype == np.uint8:
+                    tables.plan_for(1, rinfo.height, rinfo.width)
+        except Exception:
+            pass
 
     def prefetch(self, fp, tiles_path):
         if fp is not None and fp not in self.pending:
@@ -417,10 +453,19 @@ class _FastPath:
         img = api.HostImage(data["rgbi"], rinfo.transform, data["ndsm"], hinfo.transform, tiles, det["boxes_net"],
                             det["scores"], det["probs"], det["inst_tile"], det["tile_dims"], ready=data["ready"])
         t0 = time.time()
-        # the staging buffers of the OTHER parity are free (their image is through run_image): decode the next image
-        # into them while this one is on the GPU
+        # the decoder thread starts on the next image now and reads its pixels as soon as this image's host->device
+        # copies are through (rasters decoded on the device alternate between two device buffers instead)
+        self.h2d_gate.clear()
+
+        def copies_enqueued(ev):
+            self.h2d_event = ev
+            self.h2d_gate.set()
         self.prefetch(next_fp, tiles_path)
-        host, _ = api.run_image(img, self.p, self.dev, tables, p1_out, runner=self.s.runners[key], want_table=True)
+        try:
+            host, _ = api.run_image(img, self.p, self.dev, tables, p1_out, runner=self.s.runners[key], want_table=True,
+                                    on_h2d=copies_enqueued)
+        finally:
+            self.h2d_gate.set()
         for path, st in data["status"]:          # run_image has synchronised: the decoder's verdict is in
             if int(st.item()) != 0:
                 raise ValueError(f"{path}: corrupt LZW stream (device decoder status {int(st.item())})")
@@ -602,8 +647,10 @@ def _predict_on_model(config, model_path, tiles_path, output_path, batch_size, e
     fast = session is not None and exclude_vars is None and \
         os.path.abspath(stitched_path) == os.path.abspath(os.path.join(config["output_directory"], "geojson_predictions"))
     if fast:
-        fast_ctx = _FastPath(config, session, dev, params, predictor, stitched_path, output_path, logger)
+        fast_ctx = _FastPath(config, session, dev, params, predictor, stitched_path, output_path, logger,
+                             n_images=total)
         fast_ctx.prefetch(images_paths[0], tiles_path)
+        fast_ctx.warm(images_paths[0], tiles_path)
     for i, fp in enumerate(images_paths):
         cur, prev = int(100 * (i + 1) / total), int(100 * i / total)
         if logger and ((cur // 5) != (prev // 5) or cur == 100 or i == 0):

@@ -217,9 +217,9 @@ def read_device(path, device, out=None, slot=0):
     warp of ``td_tiff_lzw_decode_batch``, ``td_tiff_place_chunks`` undoes the predictor and writes the planar
     (bands, H, W) tensor.  Returns (tensor, GeoInfo, status), or None when the file needs the host reader (see
     :func:`device_decodable`).  Work is enqueued on the current stream; ``out``: optional destination tensor;
-    ``slot``: which set of staging buffers to use -- the call returns while the copies out of the pinned staging
-    buffer are still in flight, so a caller that reads several rasters back to back gives each its own slot (and
-    synchronises before it re-uses one).  The third return value is a one-element int32 device tensor: non-zero
+    the call returns once the compressed bytes have left the (single, re-used) pinned staging buffer -- the decode
+    itself is still running; ``slot`` (0..7) selects the status word, so that several reads may be in flight.  The
+    third return value is a one-element int32 device tensor: non-zero
     once the stream has run means a corrupt or oversized LZW stream (TD_ERR_*)."""
     import torch
 
@@ -237,7 +237,7 @@ def read_device(path, device, out=None, slot=0):
         if plan is None:
             return None
         # the compressed file -> pinned staging (parallel pread) -> device
-        host = _scratch(device, f"file{slot}", size, pinned=True)
+        host = _scratch(device, "file", size, pinned=True)
         mv = memoryview(host.numpy())[:size]
         step = 8 << 20
 
@@ -258,14 +258,27 @@ def read_device(path, device, out=None, slot=0):
     t_read = time.perf_counter()
     info = plan["info"]
     n = plan["n"]
-    dev_file = _scratch(device, f"file{slot}", size)
-    dev_file[:size].copy_(host[:size], non_blocking=True)
+    # the compressed bytes travel on a copy stream of their own, into one of two device buffers, so that the copy of
+    # this raster overlaps the decode kernels of the previous one (same compute stream) instead of queueing behind them
+    state = _dev_scratch.setdefault((str(device), "lzw_state"), {"copy": torch.cuda.Stream(device=device), "k": 0,
+                                                                  "done": [None, None]})
+    half = state["k"] & 1
+    state["k"] += 1
+    cur = torch.cuda.current_stream(device)
     meta = torch.from_numpy(np.concatenate([plan["src_pos"].view(np.int32), plan["src_len"], plan["dst_len"]]))
-    meta_pin = _scratch(device, f"meta{slot}", meta.numel() * 4, pinned=True)[:meta.numel() * 4].view(torch.int32)
+    meta_pin = _scratch(device, "meta", meta.numel() * 4, pinned=True)[:meta.numel() * 4].view(torch.int32)
     meta_pin.copy_(meta)
-    meta_dev = _scratch(device, f"meta{slot}", meta.numel() * 4 + 64)
-    meta_dev = meta_dev[:meta.numel() * 4].view(torch.int32)
-    meta_dev.copy_(meta_pin, non_blocking=True)
+    with torch.cuda.stream(state["copy"]):
+        dev_file = _scratch(device, f"file{half}", size)
+        meta_dev = _scratch(device, f"meta{half}", meta.numel() * 4 + 64)[:meta.numel() * 4].view(torch.int32)
+        if state["done"][half] is not None:
+            state["copy"].wait_event(state["done"][half])      # the decode that read this half last
+        dev_file[:size].copy_(host[:size], non_blocking=True)
+        meta_dev.copy_(meta_pin, non_blocking=True)
+        copied = state["copy"].record_event()
+    cur.wait_event(copied)
+    dev_file.record_stream(cur)
+    meta_dev.record_stream(cur)
     src_pos = meta_dev[:2 * n].view(torch.int64)
     src_len, dst_len = meta_dev[2 * n:3 * n], meta_dev[3 * n:4 * n]
     stride = plan["chunk_bytes"]
@@ -276,11 +289,13 @@ def read_device(path, device, out=None, slot=0):
         out = torch.empty((info.count, info.height, info.width), dtype=tdt, device=device)
     elif tuple(out.shape) != (info.count, info.height, info.width) or out.dtype != tdt or not out.is_cuda:
         raise ValueError("read_device: out does not match the raster")
-    st = torch.cuda.current_stream(device).cuda_stream
+    st = cur.cuda_stream
     _lib.call("td_tiff_lzw_decode_batch", dev_file.data_ptr(), src_pos.data_ptr(), src_len.data_ptr(), n,
               decoded.data_ptr(), stride, dst_len.data_ptr(), None, status.data_ptr(), st)
     _lib.call("td_tiff_place_chunks", decoded.data_ptr(), stride, n, out.data_ptr(), info.count, info.height, info.width,
               info.dtype.itemsize, plan["planar"], plan["chunk_rows"], plan["chunk_cols"], plan["pred"], st)
+    state["done"][half] = cur.record_event()
+    copied.synchronize()        # the pinned staging (one set, re-used by the next call) has been read
     if os.environ.get("TREEDET_TRACE_TIFF"):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         torch.cuda.synchronize()
