@@ -853,7 +853,10 @@ def run_b200(a):
         path_bytes = {
             "P1": p1_bytes,
             "P2-P4": n_inst * (3136 + 20 + 320) + n_inst * (320 + 512) + n_cand * 1024,
-            "P5": 2 * hh * ww + 4 * int(host.ndsm.numel()) + 4 * ndvi_px,
+            # bands 0 and 3 in, NDVI out; the nDSM is read by P5 only when it is decimated (height_scaling_factor != 1:
+            # otherwise the statistics of P7 read it per crown window, counted under P6-P9)
+            "P5": 2 * hh * ww + 4 * ndvi_px + (4 * int(host.ndsm.numel()) * (1 + p.height_scaling_factor ** 2)
+                                                 if p.height_scaling_factor != 1.0 else 0),
             "P6-P9": 37 * n_cand + n_final * ((10752 if a.ndsm_px == 0.2 else 717) + 205),
         }
         path_total = sum(path_bytes.values())
