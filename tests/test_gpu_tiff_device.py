@@ -1,5 +1,5 @@
 """N1 on the device: td_tiff_lzw_decode_batch + td_tiff_place_chunks (the file crosses PCIe still compressed, one
-warp per strip / tile) against the host reader -- itself pinned to PIL / libtiff in tests/test_geotiff_codec.py --
+warp per strip / tile, 32 codes per step) against the host reader -- itself pinned to PIL / libtiff in tests/test_geotiff_codec.py --
 on files written by libtiff: strips and tiles, chunky RGBA and single bands, predictor 1 / 2, float32, noise (codes
 of every width, table resets), long runs (KwKwK strings, long copies)."""
 import numpy as np
@@ -31,14 +31,22 @@ def _cases():
     runs = np.zeros((500, 2048), np.uint8)
     runs[100:300, 300:1500] = 200                      # long constant runs: KwKwK codes, strings of hundreds of bytes
     f32 = (np.sin(np.arange(700)[:, None] / 17.0) * 20 + rng.normal(0, 0.1, (700, 1017))).astype(np.float32)
+    alt = np.zeros((300, 3000), np.uint8)
+    alt[:, ::2] = 9                                    # period-2 pattern: every code names the entry made just before
+    ramp = (np.arange(300 * 3000) % 7).astype(np.uint8).reshape(300, 3000)
     return {"rgba": rgba, "band": smooth, "runs": runs, "f32": f32,
-            "noise": rng.integers(0, 256, (300, 4000)).astype(np.uint8)}
+            "noise": rng.integers(0, 256, (300, 4000)).astype(np.uint8),
+            "few": rng.integers(0, 4, (300, 9000)).astype(np.uint8),      # table fills up and is reset many times
+            "const": np.full((400, 2500), 123, np.uint8),                 # one long KwKwK chain
+            "alt": alt, "ramp": ramp}
 
 
 @pytest.mark.parametrize("name,predictor,tile", [("rgba", None, None), ("rgba", 2, None), ("band", None, None),
                                                  ("band", 2, None), ("runs", None, None), ("runs", 2, None),
                                                  ("noise", None, None), ("f32", None, None), ("rgba", None, 128),
-                                                 ("rgba", 2, 256), ("band", 2, 128)])
+                                                 ("rgba", 2, 256), ("band", 2, 128), ("few", None, None),
+                                                 ("few", 2, None), ("const", None, None), ("const", 2, None),
+                                                 ("alt", None, None), ("alt", 2, 128), ("ramp", None, None)])
 def test_device_reader_matches_host_reader(tmp_path, dev, name, predictor, tile):
     arr = _cases()[name]
     path = str(tmp_path / "x.tif")

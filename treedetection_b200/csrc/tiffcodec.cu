@@ -159,15 +159,25 @@ struct LzwBatch {
   int* status;                  // one int, set to a TD_ERR_* code by the first failing chunk
 };
 
-// The per-code work is one serial dependency chain per warp (a few resident warps per scheduler), so its length in
-// INSTRUCTIONS is what bounds the decoder: 32-bit state, the compressed bytes staged through a 256-byte window in
-// shared memory (one coalesced load per ~200 codes, big-endian words), a code = one funnel shift of two window
-// words.
+// Decoding one code at a time is one serial dependency chain per warp (~70 instructions per code were measured).
+// But between two ClearCodes the WIDTH of every code is a function of its index alone (the table grows by exactly
+// one entry per code), so the bit position of the k-th code is known in closed form: the 32 lanes extract 32
+// consecutive codes at once.  What remains sequential is tiny: string lengths (a code may name an entry created by
+// an earlier code of the same batch: length = that code's predecessor + 1, resolved in rounds over lower lanes), an
+// exclusive scan for the output positions, and the copies -- lane-parallel for the usual short strings, all lanes
+// together for long ones, in dependency rounds when the source bytes belong to the same batch.
 constexpr int kLzwWin = 64;     // window words
+constexpr int kLzwLong = 24;    // strings longer than this are copied by the whole warp
+
+TD_D int lzw_bits_before(int k) {        // bits of the first k codes after a ClearCode
+  return 9 * k + max(k - 254, 0) + max(k - 766, 0) + max(k - 1790, 0);
+}
+TD_D int lzw_width(int k) { return 9 + (k >= 254) + (k >= 766) + (k >= 1790); }
 
 __global__ void __launch_bounds__(32) lzw_decode_kernel(LzwBatch a) {
   __shared__ uint32_t tab[4096];                    // length << 20 | position, codes >= 258
   __shared__ uint32_t win[kLzwWin + 1];
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x;
   const int c = blockIdx.x;
   if (c >= a.n) return;
@@ -175,14 +185,13 @@ __global__ void __launch_bounds__(32) lzw_decode_kernel(LzwBatch a) {
   const int n_src = a.src_len[c];
   unsigned char* d = a.dst + (long long)c * a.dst_stride;
   const int cap = a.dst_len[c];
-  const int total_bits = 8 * n_src;                 // chunks are < 2^28 bytes
-  // window: words [wbase, wbase + kLzwWin) of the stream, byte-swapped; word kLzwWin is a copy of the first word of
-  // the next window so that a code may straddle the end
   const int mis = (int)((uintptr_t)s & 3);          // the stream starts `mis` bytes into an aligned word
   const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s - mis);
   const int n_words = (mis + n_src + 3) >> 2;
+  const int end_bits = 8 * (mis + n_src);
   int wbase = 0;
-  auto fill = [&](int base) {
+  auto fill = [&](int base) {                       // words [base, base + kLzwWin] of the stream, big endian
+    __syncwarp();
     for (int k = lane; k <= kLzwWin; k += 32) {
       const int wi = base + k;
       win[k] = wi < n_words ? __byte_perm(__ldg(s4 + wi), 0, 0x0123) : 0u;
@@ -190,62 +199,133 @@ __global__ void __launch_bounds__(32) lzw_decode_kernel(LzwBatch a) {
     __syncwarp();
   };
   fill(0);
-  int bitpos = 8 * mis;                             // in bits from s4
-  const int end_bits = bitpos + total_bits;
-  int width = 9, next = 258;
-  int ppos = -1, plen = 0;      // previous string in the output (ppos < 0: first code after a clear)
+  int base_bit = 8 * mis;       // bit position of code 0 of the current run (a run = the codes between two clears)
+  int k = 0;                    // codes of the run consumed so far
+  int ppos = -1, plen = 0;      // string of the last consumed code (ppos < 0: none yet in this run)
   int cur = 0, err = 0;
-  for (;;) {
-    int wi = (bitpos >> 5) - wbase;
-    if (wi >= kLzwWin) {
+  bool done = false;
+  while (!done) {
+    // ---- 32 codes ---------------------------------------------------------------------------------------------
+    const int idx = k + lane;
+    const int bit = base_bit + lzw_bits_before(idx);
+    const int width = lzw_width(idx);
+    const int first_word = (base_bit + lzw_bits_before(k)) >> 5;
+    if (first_word + 14 - wbase > kLzwWin) { wbase = first_word; fill(wbase); }
+    const bool inside = bit + width <= end_bits;
+    int code = 257;
+    if (inside) {
+      const int wi = (bit >> 5) - wbase;
+      code = (int)(__funnelshift_l(win[wi + 1], win[wi], bit & 31) >> (32 - width));
+    }
+    const unsigned stops = __ballot_sync(full, code == 256 || code == 257);
+    const int nvalid = stops ? __ffs(stops) - 1 : 32;
+    const bool live = lane < nvalid;
+    // ---- lengths and sources -----------------------------------------------------------------------------------
+    // an entry e >= 258 was created by the code of index e - 257 of this run
+    int len = 0, spos = -1, dep = -1;          // dep: lane of this batch whose string (+ next first byte) is the source
+    bool known = true;
+    if (live) {
+      if (code < 256) {
+        len = 1;
+      } else {
+        const int creator = code - 257;        // >= 1
+        if (creator < k) {
+          const uint32_t e = tab[code];
+          spos = (int)(e & (kLzwMaxChunk - 1));
+          len = (int)(e >> kLzwPosBits);
+        } else if (creator <= idx && creator - 1 <= 3838 && (idx > 0)) {
+          dep = creator - k - 1;               // -1: the last string of the previous batch
+          known = false;
+        } else {
+          err = TD_ERR_ARG;                    // a code beyond the table
+        }
+      }
+      if (idx == 0 && code >= 256) err = TD_ERR_ARG;     // a table code right after ClearCode
+    }
+    if (__any_sync(full, err != 0)) { err = TD_ERR_ARG; break; }
+    // rounds: a lane learns its length once its source lane knows its own; `round` = copy order
+    int round = 0;
+    for (int r = 1; __any_sync(full, !known); ++r) {
+      const int src = dep < 0 ? 0 : dep;
+      const int l_src = __shfl_sync(full, len, src);
+      const bool k_src = __shfl_sync(full, (int)known, src) != 0;
+      // the entry's string also takes the first byte of lane dep + 1 (for dep + 1 == lane: its own first byte)
+      const int nxt = min(dep + 1, 31);
+      const bool k_nxt = __shfl_sync(full, (int)known, nxt) != 0;
+      if (!known) {
+        if (dep < 0) {
+          if (dep + 1 == lane || k_nxt) { len = plen + 1; known = true; round = r; }
+        } else if (k_src && (dep + 1 == lane || k_nxt)) {
+          len = l_src + 1; known = true; round = r;
+        }
+      }
+      if (r > 40) { err = TD_ERR_ARG; break; }
+    }
+    if (err) break;
+    // ---- positions ---------------------------------------------------------------------------------------------
+    int incl = len;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int pos = cur + incl - len;
+    const int total = __shfl_sync(full, incl, 31);
+    if (cur + total > cap) { err = TD_ERR_OVERFLOW; break; }
+    const int pos_prev = __shfl_up_sync(full, pos, 1);
+    const int len_prev = __shfl_up_sync(full, len, 1);
+    const int p_pos = lane == 0 ? ppos : pos_prev, p_len = lane == 0 ? plen : len_prev;
+    const int pos_dep = __shfl_sync(full, pos, max(dep, 0));
+    if (live && code >= 258 && spos < 0) spos = dep >= 0 ? pos_dep : ppos;
+    // ---- table: the code of index idx >= 1 creates entry 257 + idx = previous string + this string's first byte -----
+    if (live && idx >= 1 && 257 + idx < 4096) tab[257 + idx] = ((uint32_t)(p_len + 1) << kLzwPosBits) | (uint32_t)p_pos;
+    // ---- copies ------------------------------------------------------------------------------------------------
+    const int max_round = __reduce_max_sync(full, live ? round : 0);
+    for (int r = 0; r <= max_round; ++r) {
+      const bool mine = live && round == r;
+      if (mine && len <= kLzwLong) {
+        if (code < 256) {
+          d[pos] = (unsigned char)code;
+        } else {
+          for (int t = 0; t < len; ++t) d[pos + t] = d[spos + t];     // forward: KwKwK re-reads its own first byte
+        }
+      }
+      unsigned longs = __ballot_sync(full, mine && len > kLzwLong);
       __syncwarp();
-      wbase += kLzwWin;
-      fill(wbase);
-      wi -= kLzwWin;
+      while (longs) {
+        const int l = __ffs(longs) - 1;
+        longs &= longs - 1;
+        const int lp = __shfl_sync(full, pos, l), ls = __shfl_sync(full, spos, l), ll = __shfl_sync(full, len, l);
+        // source [ls, ls + ll) ends at or before lp + 1: only the KwKwK last byte overlaps the destination
+        const int body = (ls + ll > lp) ? ll - 1 : ll;
+        for (int t = lane; t < body; t += 32) d[lp + t] = d[ls + t];
+        __syncwarp();
+        if (body < ll && lane == 0) d[lp + body] = d[ls + body];
+        __syncwarp();
+      }
     }
-    if (bitpos + width > end_bits) break;           // stream ended without EOI
-    const uint32_t hi = win[wi], lo = win[wi + 1];
-    const int code = (int)(__funnelshift_l(lo, hi, bitpos & 31) >> (32 - width));
-    bitpos += width;
-    int slen = 1;
-    if (code < 256) {                               // literal (the common case on imagery)
-      if (cur >= cap) { err = TD_ERR_OVERFLOW; break; }
-      if (lane == 0) d[cur] = (unsigned char)code;
-    } else if (code == 257) {
-      break;
-    } else if (code == 256) {
-      width = 9; next = 258; ppos = -1;
-      continue;
-    } else if (ppos < 0) {
-      err = TD_ERR_ARG;                             // a table code right after ClearCode
-      break;
-    } else if (code < next) {
-      const uint32_t e = tab[code];
-      const int spos = (int)(e & (kLzwMaxChunk - 1));
-      slen = (int)(e >> kLzwPosBits);
-      if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
-      for (int k = lane; k < slen; k += 32) d[cur + k] = d[spos + k];
-    } else if (code == next) {                      // KwKwK: string(prev) + first(prev)
-      slen = plen + 1;
-      if (cur + slen > cap) { err = TD_ERR_OVERFLOW; break; }
-      for (int k = lane; k < slen; k += 32) d[cur + k] = d[ppos + (k < plen ? k : 0)];
-    } else {
-      err = TD_ERR_ARG;
-      break;
+    __syncwarp();
+    // ---- next batch ----------------------------------------------------------------------------------------------
+    if (nvalid > 0) {
+      ppos = __shfl_sync(full, pos, nvalid - 1);
+      plen = __shfl_sync(full, len, nvalid - 1);
     }
-    if (ppos >= 0 && next < 4096) {
-      // string(prev) + first byte of this string = the plen + 1 output bytes starting at ppos
-      if (lane == 0) tab[next] = ((uint32_t)(plen + 1) << kLzwPosBits) | (uint32_t)ppos;
-      ++next;
-      if (next >= (1 << width) - 1 && width < 12) ++width;
+    cur += total;
+    k += nvalid;
+    if (nvalid < 32) {
+      const int stop_code = __shfl_sync(full, code, nvalid);
+      const bool stop_inside = __shfl_sync(full, (int)inside, nvalid) != 0;
+      if (stop_code == 256 && stop_inside) {         // ClearCode: a new run starts behind it
+        base_bit = __shfl_sync(full, bit + width, nvalid);
+        k = 0;
+        ppos = -1;
+        plen = 0;
+      } else {
+        done = true;                                  // EOI, or the stream ended without one
+      }
     }
-    ppos = cur;
-    plen = slen;
-    cur += slen;
-    __syncwarp();                                   // the bytes and the entry are visible to the next copy
   }
   __syncwarp();
-  for (int k = cur + lane; k < cap; k += 32) d[k] = 0;   // a short stream leaves zeros (deterministic)
+  for (int t = cur + lane; t < cap; t += 32) d[t] = 0;   // a short stream leaves zeros (deterministic)
   if (lane == 0) {
     if (a.out_len) a.out_len[c] = cur;
     if (err) atomicCAS(a.status, 0, err);
