@@ -169,18 +169,35 @@ paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ wi
   const int wpr = (ww + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* out = bits + word_off[i];
-  const int ntask = wpr * wh;
-  for (int t = warp; t < ntask; t += kPasteThreads / 32) {
-    const int y = t / wpr, wi = t - y * wpr;
+  // a warp owns a 32-column word column and walks down its rows: the column tap of a lane is loaded once, the
+  // row tap is one broadcast load per row, the four table addresses are two row bases plus two column indices
+  for (int wi = warp; wi < wpr; wi += kPasteThreads / 32) {
     const int x = wi * 32 + lane;
-    bool on = false;
-    if (x < ww) {
-      const Tap tx = x < kTapCap ? unpack_tap(s_tx[x]) : make_tap(wx0 + x, bx0, bx1);
+    const bool live = x < ww;
+    Tap tx{0, 0, 0.f, 0.f};
+    if (live) tx = x < kTapCap ? unpack_tap(s_tx[x]) : make_tap(wx0 + x, bx0, bx1);
+    const float* col0 = &tab[0][0] + tx.i0;
+    const float* col1 = &tab[0][0] + tx.i1;
+    for (int y = 0; y < wh; ++y) {
       const Tap ty = y < kTapCap ? unpack_tap(s_ty[y]) : make_tap(wy0 + y, by0, by1);
-      on = sample(tab, tx, ty) >= thr;
+      const int r0 = ty.i0 * kPad, r1 = ty.i1 * kPad;
+      bool on = false;
+      if (live) {
+        // sample(): the same products and fused adds in the same order
+        const float nw = col0[r0], ne = col1[r0], sw = col0[r1], se = col1[r1];
+        const float cnw = __fmul_rn(ty.w0, tx.w0);
+        const float cne = __fmul_rn(ty.w0, tx.w1);
+        const float csw = __fmul_rn(ty.w1, tx.w0);
+        const float cse = __fmul_rn(ty.w1, tx.w1);
+        float acc = __fmul_rn(nw, cnw);
+        acc = __fmaf_rn(ne, cne, acc);
+        acc = __fmaf_rn(sw, csw, acc);
+        acc = __fmaf_rn(se, cse, acc);
+        on = acc >= thr;
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) out[y * wpr + wi] = word;
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) out[t] = word;
   }
 }
 
