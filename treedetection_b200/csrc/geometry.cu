@@ -22,6 +22,49 @@ namespace {
 constexpr int kSmemRing = 128;                              // vertices of a ring whose scratch fits shared memory
 constexpr int kSmemInts = 5 * kSmemRing + kSmemRing / 32 + 4;   // per warp: res | flat | stack | alive bits
 
+// Warp-wide min / max of doubles through the integer reductions (REDUX): a double's bits, with the sign
+// bit flipped for positive values and all bits flipped for negative ones, order like unsigned integers.
+// Two 32-bit reductions per value instead of a five-step shuffle butterfly of 64-bit fmin / fmax.
+__device__ __forceinline__ unsigned long long ordered_key(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_key(unsigned long long k) {
+  return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull)));
+}
+__device__ __forceinline__ double warp_max(double d) {
+  const unsigned long long k = ordered_key(d);
+  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(k >> 32));
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0u);
+  return from_ordered_key(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ double warp_min(double d) {
+  const unsigned long long k = ordered_key(d);
+  const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32));
+  const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0xffffffffu);
+  return from_ordered_key(((unsigned long long)hi << 32) | lo);
+}
+
+// bounds of pts[idx[k]] (idx == nullptr: pts[k]), k < cnt, on every lane (coordinates are never NaN)
+__device__ __forceinline__ void warp_bounds(const td::P2* __restrict__ pts, const int* idx, int cnt, int lane,
+                                            double& minx, double& miny, double& maxx, double& maxy) {
+  minx = INFINITY; miny = INFINITY; maxx = -INFINITY; maxy = -INFINITY;
+#pragma unroll 1
+  for (int k = lane; k < cnt; k += 32) {
+    const td::P2 p = pts[idx ? idx[k] : k];
+    minx = p.x < minx ? p.x : minx; maxx = p.x > maxx ? p.x : maxx;
+    miny = p.y < miny ? p.y : miny; maxy = p.y > maxy ? p.y : maxy;
+  }
+  minx = warp_min(minx); maxx = warp_max(maxx);
+  miny = warp_min(miny); maxy = warp_max(maxy);
+}
+
+// rings of more than kSmemRing vertices (a handful per image): scratch in global memory.  Out of line, so
+// that the kernel's hot path holds ONE copy of the simplifier (the instruction cache was its top stall).
+__device__ __noinline__ int simplify_ring_global(const td::P2* pts, int len, double tol, int* sc, uint32_t* al) {
+  return td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+}
+
 // one warp per ring: the stack machine runs redundantly on all lanes, the farthest-point
 // and intersection scans are strided over the lanes (td::WarpCoop)
 template <int kMinBlocks>
@@ -42,19 +85,7 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   uint32_t* al = alive + (v0 >> 5) + r;
   // bounds of the input ring (needed for the pre-filter below and for bounds_of_input)
   double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-  if (boxes || bounds_of_input) {
-    for (int k = lane; k < len; k += 32) {
-      const td::P2 p = pts[k];
-      minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
-      miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
-      maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-      miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
-      maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
-    }
-  }
+  if (boxes || bounds_of_input) warp_bounds(pts, nullptr, len, lane, minx, miny, maxx, maxy);
   // Pre-filter of the tile box test: every vertex the simplifier drops lies within `tol` of the chord
   // that replaces it, and a chord point outside the (convex) box means a kept end point outside it.
   // So a ring that sticks out of the box by more than tol cannot be `within` it after simplification
@@ -79,29 +110,21 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
     if (len <= kSmemRing) {
       m = td::simplify_ring(pts, len, tol, my, reinterpret_cast<uint32_t*>(my + 5 * kSmemRing), td::WarpCoop());
       __syncwarp();
+#pragma unroll 1
       for (int k = lane; k < m; k += 32) sc[k] = my[k];
+      if (!bounds_of_input) warp_bounds(pts, my, m, lane, minx, miny, maxx, maxy);   // kept vertices
     } else {
-      m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+      m = simplify_ring_global(pts, len, tol, sc, al);
+      __syncwarp();
+      if (!bounds_of_input) warp_bounds(pts, sc, m, lane, minx, miny, maxx, maxy);
     }
   } else {  // helpers.py:463: simplification is skipped for a non-positive tolerance
+#pragma unroll 1
     for (int k = lane; k < len; k += 32) sc[k] = k;
     m = len;
+    if (!bounds_of_input) warp_bounds(pts, nullptr, m, lane, minx, miny, maxx, maxy);
   }
   __syncwarp();
-  if (!bounds_of_input) {
-    minx = INFINITY; miny = INFINITY; maxx = -INFINITY; maxy = -INFINITY;
-    for (int k = lane; k < m; k += 32) {
-      const td::P2 p = pts[sc[k]];
-      minx = fmin(minx, p.x); maxx = fmax(maxx, p.x);
-      miny = fmin(miny, p.y); maxy = fmax(maxy, p.y);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      minx = fmin(minx, __shfl_xor_sync(0xffffffffu, minx, o));
-      maxx = fmax(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
-      miny = fmin(miny, __shfl_xor_sync(0xffffffffu, miny, o));
-      maxy = fmax(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
-    }
-  }
   if (lane != 0) return;
   out_count[r] = m;
   if (out_bounds) {

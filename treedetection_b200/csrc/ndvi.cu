@@ -127,6 +127,86 @@ decimate_kernel(const T* __restrict__ src0, const T* __restrict__ src1, int in_h
   }
 }
 
+// The uint8 / NDVI case of decimate_kernel for <= KT taps per output column (scale <= ~5.5), which is what
+// P5 runs on every image (bands 0 and 3 at full resolution -> NDVI at ndvi_scaling_factor).  Same
+// arithmetic in the same order; what changes is the instruction count per tap (the generic kernel is
+// issue bound at ~9 instructions per tap and band):
+//   * a thread keeps the KT weights of its output column in registers and the tap loop is unrolled
+//     (taps past the column's count carry weight 0: acc + x * 0 = acc exactly for the uint8 samples);
+//   * 16 output rows per CTA instead of 8: the horizontal pass of the vertical halo rows (2 x scale rows
+//     per tile) is redone by every tile, 6 % of the rows instead of 25 % at scale 5;
+//   * the epilogue's two divisions by 255 come from a 256-entry table built by the CTA (same quotients).
+constexpr int kFastTileH = 16;
+template <int KT>
+__global__ void __launch_bounds__(kTileW* kFastTileH)
+decimate_ndvi_fast_kernel(const unsigned char* __restrict__ src0, const unsigned char* __restrict__ src1, int in_h,
+                          int in_w, int out_h, int out_w, AxisTable ax, AxisTable ay, float* __restrict__ out,
+                          int max_src_rows) {
+  extern __shared__ float sh[];  // [2][max_src_rows][kTileW]
+  __shared__ double s_unit[256];
+  const int tx = threadIdx.x % kTileW, ty = threadIdx.x / kTileW;
+  if (threadIdx.x < 256) s_unit[threadIdx.x] = (double)(float)threadIdx.x / 255.0;
+  const int ox0 = blockIdx.x * kTileW, oy0 = blockIdx.y * kFastTileH;
+  const int oy_last = min(oy0 + kFastTileH, out_h) - 1;
+  const int row_lo = ay.start[oy0];
+  const int nrows = ay.start[oy_last] + ay.count[oy_last] - row_lo;
+  const int ox = ox0 + tx;
+  // every lane may read KT bytes from its first tap: true unless the tile touches the right edge
+  const int ox_last = min(ox0 + kTileW, out_w) - 1;
+  const bool wide = ax.start[ox_last] + KT <= in_w;
+  if (ox < out_w) {
+    const int xs = ax.start[ox], xn = ax.count[ox];
+    const float* wx = ax.w + (size_t)ox * ax.ktaps;
+    if (wide) {
+      float w[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) w[k] = k < xn ? wx[k < ax.ktaps ? k : 0] : 0.f;
+#pragma unroll 1
+      for (int r = ty; r < nrows; r += kFastTileH) {
+        const unsigned char* p0 = src0 + (size_t)(row_lo + r) * in_w + xs;
+        const unsigned char* p1 = src1 + (size_t)(row_lo + r) * in_w + xs;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          acc0 = __fadd_rn(acc0, __fmul_rn((float)p0[k], w[k]));
+          acc1 = __fadd_rn(acc1, __fmul_rn((float)p1[k], w[k]));
+        }
+        sh[(size_t)r * kTileW + tx] = acc0;
+        sh[(size_t)(max_src_rows + r) * kTileW + tx] = acc1;
+      }
+    } else {
+      for (int r = ty; r < nrows; r += kFastTileH) {
+        const size_t base = (size_t)(row_lo + r) * in_w + xs;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int k = 0; k < xn; ++k) {
+          const float wk = wx[k];
+          acc0 = __fadd_rn(acc0, __fmul_rn((float)src0[base + k], wk));
+          acc1 = __fadd_rn(acc1, __fmul_rn((float)src1[base + k], wk));
+        }
+        sh[(size_t)r * kTileW + tx] = acc0;
+        sh[(size_t)(max_src_rows + r) * kTileW + tx] = acc1;
+      }
+    }
+  }
+  __syncthreads();
+  const int oy = oy0 + ty;
+  if (ox >= out_w || oy >= out_h) return;
+  const int ys = ay.start[oy] - row_lo, yn = ay.count[oy];
+  const float* wy = ay.w + (size_t)oy * ay.ktaps;
+  const float* c0 = sh + (size_t)ys * kTileW + tx;
+  const float* c1 = c0 + (size_t)max_src_rows * kTileW;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int k = 0; k < yn; ++k) {
+    const float wk = wy[k];
+    acc0 = __fadd_rn(acc0, __fmul_rn(c0[k * kTileW], wk));
+    acc1 = __fadd_rn(acc1, __fmul_rn(c1[k * kTileW], wk));
+  }
+  // uint8 band: round half up, clamp (the value is an integer in 0..255); then the NDVI of the two bands
+  const double red = s_unit[(int)fminf(fmaxf(floorf(__fadd_rn(acc0, 0.5f)), 0.f), 255.f)];
+  const double nir = s_unit[(int)fminf(fmaxf(floorf(__fadd_rn(acc1, 0.5f)), 0.f), 255.f)];
+  out[(size_t)oy * out_w + ox] = (float)((nir - red) / (nir + red + 1e-10));
+}
+
 // no decimation (scale factor 1): straight NDVI of the full-resolution bands
 __global__ void ndvi_full_kernel(const unsigned char* __restrict__ red, const unsigned char* __restrict__ nir,
                                  long long n, float* __restrict__ out) {
@@ -172,6 +252,8 @@ int get_axis(int in_size, int out_size, int group, DevAxis& d) {
   build_axis(in_size, out_size, s, c, w, d.ktaps);
   d.max_rows = 0;
   d.max_count = 0;
+  for (int i = 0; i < out_size; ++i)
+    if (c[i] > d.max_count) d.max_count = c[i];
   for (int i = 0; i < out_size; i += group) {
     const int last = (i + group < out_size ? i + group : out_size) - 1;
     const int span = s[last] + c[last] - s[i];
@@ -197,6 +279,25 @@ int run_decimate(const T* s0, const T* s1, int in_h, int in_w, int out_h, int ou
   if (dx.ktaps > kMaxTaps || dy.ktaps > kMaxTaps) {
     td_set_error("decimation factor too large for the fused kernel (taps %d x %d)", dx.ktaps, dy.ktaps);
     return TD_ERR_UNSUPPORTED;
+  }
+  if constexpr (EPI == 1) {
+    constexpr int KT = 12;
+    static int generic = -1;
+    if (generic < 0) { const char* e = getenv("TREEDET_DECIMATE_GENERIC"); generic = e && atoi(e) > 0 ? 1 : 0; }
+    DevAxis dyf;
+    if (!generic && dx.max_count <= KT && get_axis(in_h, out_h, kFastTileH, dyf) == TD_OK) {
+      const size_t smem_f = sizeof(float) * 2 * (size_t)dyf.max_rows * kTileW;
+      if (smem_f <= 160 * 1024) {
+        auto kf = decimate_ndvi_fast_kernel<KT>;
+        if (smem_f > 40 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+        AxisTable fx{dx.start, dx.count, dx.w, dx.ktaps}, fy{dyf.start, dyf.count, dyf.w, dyf.ktaps};
+        dim3 gridf(td_div_up(out_w, kTileW), td_div_up(out_h, kFastTileH));
+        kf<<<gridf, kTileW * kFastTileH, smem_f, st>>>((const unsigned char*)s0, (const unsigned char*)s1, in_h, in_w,
+                                                        out_h, out_w, fx, fy, out, dyf.max_rows);
+        TD_CHECK_LAUNCH("decimate");
+        return TD_OK;
+      }
+    }
   }
   constexpr int NB = EPI == 1 ? 2 : 1;
   const size_t smem = sizeof(float) * NB * (size_t)dy.max_rows * kTileW;

@@ -148,6 +148,31 @@ TD_HD inline bool interior_intersection(const P2& p1, const P2& p2, const P2& q1
   return true;  // proper crossing
 }
 
+// The simplifier's guard calls the predicate for a handful of segments per ring only (those whose
+// envelope meets the chord's): out of line on the device, so that the guard's hot loop is the
+// envelope test and nothing else (the inlined predicate carried four orientation bodies per call site).
+#if defined(__CUDACC__)
+__noinline__
+#endif
+TD_HD inline bool interior_intersection_cold(double p1x, double p1y, double p2x, double p2y, double q1x, double q1y,
+                                             double q2x, double q2y) {
+  return interior_intersection(P2{p1x, p1y}, P2{p2x, p2y}, P2{q1x, q1y}, P2{q2x, q2y});
+}
+
+// env_overlap(p1, p2, A, B) with the chord's envelope computed once: min(p1, p2) > max  <=>  both are,
+// so eight comparisons decide it (same booleans as the fmin / fmax form for non-NaN input)
+struct ChordEnv {
+  double minx, maxx, miny, maxy;
+};
+TD_HD inline ChordEnv chord_envelope(const P2& A, const P2& B) {
+  return ChordEnv{fmin(A.x, B.x), fmax(A.x, B.x), fmin(A.y, B.y), fmax(A.y, B.y)};
+}
+TD_HD inline bool env_overlap(const ChordEnv& c, const P2& p1, const P2& p2) {
+  const bool x_lo = (p1.x <= c.maxx) | (p2.x <= c.maxx), x_hi = (p1.x >= c.minx) | (p2.x >= c.minx);
+  const bool y_lo = (p1.y <= c.maxy) | (p2.y <= c.maxy), y_hi = (p1.y >= c.miny) | (p2.y >= c.miny);
+  return x_lo & x_hi & y_lo & y_hi;
+}
+
 TD_HD inline double point_segment_distance(const P2& p, const P2& A, const P2& B) {
   if (A.x == B.x && A.y == B.y) {
     const double dx = p.x - A.x, dy = p.y - A.y;
@@ -190,12 +215,23 @@ TD_HD inline double point_segment_distance(const P2& p, const SegPrep& g) {
     const double dx = p.x - g.A.x, dy = p.y - g.A.y;
     return sqrt(dx * dx + dy * dy);
   }
-  const double r = ((p.x - g.A.x) * g.ux + (p.y - g.A.y) * g.uy) / g.len2;
-  if (r <= 0.0) {
+  // r = dot / len2 is only ever compared with 0 and 1:
+  //   r <= 0  <=>  dot <= 0    (unless the quotient of a tiny positive dot underflows -> divide)
+  //   r >= 1  <=>  dot >= len2 (a quotient of two doubles that is below 1 is at most 1 - 2^-53, which is
+  //                             representable, so it never rounds up to 1)
+  // so the scan of a section pays one division per point, not two.
+  const double dot = (p.x - g.A.x) * g.ux + (p.y - g.A.y) * g.uy;
+  bool before = dot <= 0.0, after = dot >= g.len2;
+  if (!(g.len2 < 1e300) || (dot > 0.0 && dot < 1e-280)) {
+    const double r = dot / g.len2;
+    before = r <= 0.0;
+    after = r >= 1.0;
+  }
+  if (before) {
     const double dx = p.x - g.A.x, dy = p.y - g.A.y;
     return sqrt(dx * dx + dy * dy);
   }
-  if (r >= 1.0) {
+  if (after) {
     const double dx = p.x - g.B.x, dy = p.y - g.B.y;
     return sqrt(dx * dx + dy * dy);
   }
@@ -246,22 +282,34 @@ struct WarpCoop {
 // ---- TopologyPreservingSimplifier on one closed ring ---------------------------
 // pts[0..n) with pts[0] == pts[n-1].  scratch: 5 * n ints.  Writes the indices of the
 // kept vertices (including the closing one) to res[0..m) and returns m.
-//   scratch layout: res[n] | flat[n] | stack[3n]   (flat[k] = end index + 1 when result
-//   segment k is a flattened section, i.e. a member of the output segment index, else 0)
+//   scratch layout: res[n] | cend[n] | stack[3n]   (cend[k] = end vertex + 1 of the flattened section
+//   that starts in vertex k, i.e. of a member of the output segment index, else 0)
 //   alive: n bits in (n + 31) / 32 words (input segment k = pts[k], pts[k+1] still indexed)
-//   IdxT: int in general; unsigned char when n <= 254 (every stored value is an index <= n), which
-//   lets a ring's whole scratch live in 5 * n BYTES of shared memory
+//   IdxT: int in general; unsigned char when n <= 254 (every stored value is an index <= n)
+//
+// The guard ("the chord of a flattened section must not meet any other segment in an interior point")
+// consults GEOS's two segment sets -- output chords, live input segments -- in ONE sweep over the start
+// vertices: vertex k starts either a live input segment (k, k+1) or, when a section starting there was
+// flattened, the chord (k, cend[k] - 1); flattening a section clears the live bits of its segments, so the
+// two never coexist.  The sets are the same as in the two-loop form, and the answer is an OR over them.
 template <typename Coop, typename IdxT>
 TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, uint32_t* alive, const Coop& co) {
   if (n <= 0) return 0;
   IdxT* res = scratch;
-  IdxT* flat = scratch + n;
+  IdxT* cend = scratch + n;
   IdxT* stack = scratch + 2 * n;
   const int nseg = n - 1;
   const int lane = co.lane(), nl = co.size();
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
   for (int k = lane; k < (n + 31) / 32; k += nl) alive[k] = 0xffffffffu;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = lane; k < n; k += nl) cend[k] = 0;
   co.sync();
-  int m = 0;        // number of result segments; res[k] and the next start (or flat end) are its ends
+  int m = 0;        // number of result segments so far (res[k] = start vertex of result segment k)
   int sp = 0;
   stack[0] = 0; stack[1] = (IdxT)(n - 1); stack[2] = 0;
   sp = 1;
@@ -271,7 +319,7 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, 
     const int i = stack[3 * sp], j = stack[3 * sp + 1];
     const int depth = stack[3 * sp + 2] + 1;
     if (i + 1 == j) {
-      res[m] = (IdxT)i; flat[m] = 0; ++m;
+      res[m] = (IdxT)i; ++m;
       continue;
     }
     bool valid = true;
@@ -289,33 +337,31 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, 
     co.argmax_first(maxd, far);
     if (maxd > tol) valid = false;
     if (valid) {
-      // The segments next to the section share an end point with its chord (A or B).  Two segments
-      // that share an end point and are not collinear meet in that point only, which is interior to
-      // neither: interior_intersection is false (its "touching" branch picks the shared point).
-      // One exact orientation decides that; only collinear neighbours take the full predicate.
-      auto touches_only = [&](const P2& other) {
-        return orientation(A.x, A.y, B.x, B.y, other.x, other.y) != 0;
-      };
+      const ChordEnv env = chord_envelope(A, B);
       bool bad = false;
-      for (int k = lane; k < m; k += nl) {
-        if (!flat[k] || bad) continue;
-        const int u = res[k], v = flat[k] - 1;
-        if (v == i && touches_only(pts[u])) continue;          // output segment ending in A
-        bad = interior_intersection(pts[u], pts[v], A, B);
-      }
-      bad = co.any(bad);
-      if (!bad) {
-        for (int k = lane; k < nseg; k += nl) {
-          if (bad) break;
-          if (!((alive[k >> 5] >> (k & 31)) & 1u)) continue;
-          if (k >= i && k < j) continue;
-          if (k == j && touches_only(pts[k + 1])) continue;    // input segment starting in B
-          if (k + 1 == i && touches_only(pts[k])) continue;    // input segment ending in A
-          bad = interior_intersection(pts[k], pts[k + 1], A, B);
+      for (int k = lane; k < nseg; k += nl) {
+        const bool live = (alive[k >> 5] >> (k & 31)) & 1u;
+        int v = k + 1;
+        if (live) {
+          if (k >= i && k < j) continue;       // the section's own segments
+        } else {
+          v = (int)cend[k] - 1;
+          if (v < 0) continue;                 // vertex inside a flattened section
         }
-        bad = co.any(bad);
+        const P2 p = pts[k], q = pts[v];
+        // A segment next to the section shares an end point with its chord (A or B).  Two segments that
+        // share an end point and are not collinear meet in that point only, which is interior to
+        // neither: interior_intersection is false (its "touching" branch picks the shared point).
+        // One exact orientation decides that; only collinear neighbours take the full predicate.
+        const bool ends_in_a = v == i;                 // input segment or output chord ending in A
+        const bool starts_in_b = live && k == j;       // input segment starting in B
+        if (ends_in_a || starts_in_b) {
+          const P2 o = ends_in_a ? p : q;
+          if (orientation(A.x, A.y, B.x, B.y, o.x, o.y) != 0) continue;
+        }
+        if (env_overlap(env, p, q) && interior_intersection_cold(p.x, p.y, q.x, q.y, A.x, A.y, B.x, B.y)) bad = true;
       }
-      if (bad) valid = false;
+      if (co.any(bad)) valid = false;
     }
     if (valid) {
       // clear bits [i, j): whole words strided over the lanes (identical result for 1 lane)
@@ -326,7 +372,7 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, 
         alive[w] &= ~mask;
       }
       co.sync();
-      res[m] = (IdxT)i; flat[m] = (IdxT)(j + 1); ++m;
+      res[m] = (IdxT)i; cend[i] = (IdxT)(j + 1); ++m;
       continue;
     }
     // right section is processed second
