@@ -165,12 +165,30 @@ struct ChordEnv {
   double minx, maxx, miny, maxy;
 };
 TD_HD inline ChordEnv chord_envelope(const P2& A, const P2& B) {
-  return ChordEnv{fmin(A.x, B.x), fmax(A.x, B.x), fmin(A.y, B.y), fmax(A.y, B.y)};
+  // one comparison per axis (coordinates are never NaN; a tie selects equal values either way)
+  const bool xl = A.x < B.x, yl = A.y < B.y;
+  return ChordEnv{xl ? A.x : B.x, xl ? B.x : A.x, yl ? A.y : B.y, yl ? B.y : A.y};
 }
 TD_HD inline bool env_overlap(const ChordEnv& c, const P2& p1, const P2& p2) {
+#if defined(__CUDA_ARCH__)
+  // spelled out as eight predicate-chained comparisons: the compiler otherwise folds each pair back into
+  // a NaN-aware 64-bit min / max (five times the instructions)
+  int r;
+  asm("{\n\t.reg .pred a, b, c, d;\n\t"
+      "setp.le.f64 a, %1, %6;\n\tsetp.le.or.f64 a, %3, %6, a;\n\t"
+      "setp.ge.f64 b, %1, %5;\n\tsetp.ge.or.f64 b, %3, %5, b;\n\t"
+      "setp.le.f64 c, %2, %8;\n\tsetp.le.or.f64 c, %4, %8, c;\n\t"
+      "setp.ge.f64 d, %2, %7;\n\tsetp.ge.or.f64 d, %4, %7, d;\n\t"
+      "and.pred a, a, b;\n\tand.pred c, c, d;\n\tand.pred a, a, c;\n\t"
+      "selp.s32 %0, 1, 0, a;\n\t}"
+      : "=r"(r)
+      : "d"(p1.x), "d"(p1.y), "d"(p2.x), "d"(p2.y), "d"(c.minx), "d"(c.maxx), "d"(c.miny), "d"(c.maxy));
+  return r != 0;
+#else
   const bool x_lo = (p1.x <= c.maxx) | (p2.x <= c.maxx), x_hi = (p1.x >= c.minx) | (p2.x >= c.minx);
   const bool y_lo = (p1.y <= c.maxy) | (p2.y <= c.maxy), y_hi = (p1.y >= c.miny) | (p2.y >= c.miny);
   return x_lo & x_hi & y_lo & y_hi;
+#endif
 }
 
 TD_HD inline double point_segment_distance(const P2& p, const P2& A, const P2& B) {
@@ -211,10 +229,6 @@ TD_HD inline SegPrep prepare_segment(const P2& A, const P2& B) {
   return s;
 }
 TD_HD inline double point_segment_distance(const P2& p, const SegPrep& g) {
-  if (g.degenerate) {
-    const double dx = p.x - g.A.x, dy = p.y - g.A.y;
-    return sqrt(dx * dx + dy * dy);
-  }
   // r = dot / len2 is only ever compared with 0 and 1:
   //   r <= 0  <=>  dot <= 0    (unless the quotient of a tiny positive dot underflows -> divide)
   //   r >= 1  <=>  dot >= len2 (a quotient of two doubles that is below 1 is at most 1 - 2^-53, which is
@@ -227,12 +241,10 @@ TD_HD inline double point_segment_distance(const P2& p, const SegPrep& g) {
     before = r <= 0.0;
     after = r >= 1.0;
   }
-  if (before) {
-    const double dx = p.x - g.A.x, dy = p.y - g.A.y;
-    return sqrt(dx * dx + dy * dy);
-  }
-  if (after) {
-    const double dx = p.x - g.B.x, dy = p.y - g.B.y;
+  if (g.degenerate) { before = true; after = false; }
+  if (before || after) {   // distance to an end point (one square-root site for the three cases)
+    const P2 e = before ? g.A : g.B;
+    const double dx = p.x - e.x, dy = p.y - e.y;
     return sqrt(dx * dx + dy * dy);
   }
   const double s = ((g.A.y - p.y) * g.ux - (g.A.x - p.x) * g.uy) / g.len2;

@@ -119,6 +119,32 @@ crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict
   if (ww > 0 && wh > 0 && !isnan(r)) {
     // rows outer, lanes over the columns of a row (no per-pixel division); the arithmetic of the
     // pixel coordinates is the reference's, with the row terms hoisted (same operations, same rounding)
+    if (MODE == kHeightOnly) {
+      // Four rows per step: the four raster loads of a lane are issued together, before the distance
+      // arithmetic (one dependent load per row left every warp waiting on DRAM for most of its life).
+      // The loads are unconditional -- the window lies inside the raster -- and the arg-max carries its
+      // flat index, so neither the extra reads nor the order of evaluation change the result.
+      for (int rb = r_lo; rb <= r_hi; rb += 4) {
+        for (int cc = c_lo + lane; cc <= c_hi; cc += 32) {
+          float v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            v[q] = rb + q <= r_hi ? __ldg(height + ((long long)(rb + q) * cols + cc)) : 0.f;
+          const double ax = T.a * (double)cc, dxc = T.d * (double)cc;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int rr = rb + q;
+            if (rr > r_hi) break;
+            const double xd = ax + T.b * (double)rr + T.c;
+            const double yd = dxc + T.e * (double)rr + T.f;
+            const double dx = xd - (double)cx, dy = yd - (double)cy;
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            const long long flat = (long long)rr * cols + cc;
+            if (d2 <= (double)r2_h && better_max(v[q], flat, bh, bhk)) { bh = v[q]; bhk = flat; }
+          }
+        }
+      }
+    } else
     for (int rr = r_lo; rr <= r_hi; ++rr) {
       const double brr = T.b * (double)rr, err = T.e * (double)rr;
       const long long row_flat = (long long)rr * cols;
