@@ -20,7 +20,8 @@
 namespace {
 
 constexpr int kSmemRing = 128;                              // vertices of a ring whose scratch fits shared memory
-constexpr int kSmemInts = 5 * kSmemRing + kSmemRing / 32 + 4;   // per warp: res | flat | stack | alive bits
+constexpr int kSmemInts = 5 * kSmemRing + kSmemRing / 32 + 4;   // per warp: res | cend | stack | alive bits
+constexpr int kSmemWarpBytes = 16 * kSmemRing + 4 * kSmemInts;   // the ring's vertices in front of them
 
 // Warp-wide min / max of doubles through the integer reductions (REDUX): a double's bits, with the sign
 // bit flipped for positive values and all bits flipped for negative ones, order like unsigned integers.
@@ -59,14 +60,36 @@ __device__ __forceinline__ void warp_bounds(const td::P2* __restrict__ pts, cons
   miny = warp_min(miny); maxy = warp_max(maxy);
 }
 
-// rings of more than kSmemRing vertices (a handful per image): scratch in global memory.  Out of line, so
-// that the kernel's hot path holds ONE copy of the simplifier (the instruction cache was its top stall).
-__device__ __noinline__ int simplify_ring_global(const td::P2* pts, int len, double tol, int* sc, uint32_t* al) {
-  return td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+// Cold path, out of line (so that the kernel's hot path holds ONE copy of the simplifier -- the instruction
+// cache was its top stall): rings of more than kSmemRing vertices (a handful per image) with their scratch in
+// global memory, and the non-positive tolerance of helpers.py:463 (no simplification).  Returns the kept
+// count; bounds of the kept vertices and the area on request.
+struct ColdOut {
+  double minx, miny, maxx, maxy, area;
+};
+__device__ __noinline__ int cold_ring(const td::P2* pts, int len, double tol, int* sc, uint32_t* al, int lane,
+                                      bool want_bounds, bool want_area, ColdOut* o) {
+  int m;
+  if (tol > 0.0 && len > 0) {
+    m = td::simplify_ring(pts, len, tol, sc, al, td::WarpCoop());
+  } else {
+#pragma unroll 1
+    for (int k = lane; k < len; k += 32) sc[k] = k;
+    m = len;
+  }
+  __syncwarp();
+  if (want_bounds) warp_bounds(pts, sc, m, lane, o->minx, o->miny, o->maxx, o->maxy);
+  if (want_area) o->area = fabs(td::ring_signed_area(m, [&](int k) { return pts[sc[k]]; }));
+  return m;
 }
 
 // one warp per ring: the stack machine runs redundantly on all lanes, the farthest-point
-// and intersection scans are strided over the lanes (td::WarpCoop)
+// and intersection scans are strided over the lanes (td::WarpCoop).  Rings of up to kSmemRing vertices
+// (nearly all) are staged in shared memory together with the simplifier's scratch (result list, chord
+// ends, stack, live-segment bits): the stack machine touches them at every node, and in global memory
+// each access is a 64-bit address computation plus an L1 / L2 round trip that gets long when a
+// bandwidth-bound kernel runs next to this one.  The kept-vertex list is copied out at the end for
+// td_take_rings.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(64, kMinBlocks)
 simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off, int n, double tol,
@@ -74,6 +97,7 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
                 const int* __restrict__ ring_box, int* __restrict__ out_count, double* __restrict__ out_bounds,
                 double* __restrict__ out_area, unsigned char* __restrict__ out_keep, int bounds_of_input,
                 const long long* __restrict__ n_dev) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n || (n_dev && r >= *n_dev)) return;
@@ -81,11 +105,29 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
   const int len = (int)(ring_off[r + 1] - v0);
   const td::P2* pts = reinterpret_cast<const td::P2*>(verts) + v0;
   int* sc = scratch + 5 * v0;
-  // alive words: ring r owns (len + 31) / 32 words starting at v0 / 32 + r  (disjoint)
-  uint32_t* al = alive + (v0 >> 5) + r;
-  // bounds of the input ring (needed for the pre-filter below and for bounds_of_input)
+  unsigned char* wbase = s_raw + (threadIdx.x >> 5) * kSmemWarpBytes;
+  td::P2* spts = reinterpret_cast<td::P2*>(wbase);
+  int* my = reinterpret_cast<int*>(wbase + sizeof(td::P2) * kSmemRing);
+  const bool hot = len <= kSmemRing && len > 0 && tol > 0.0;
+  // bounds of the input ring (needed for the pre-filter below and for bounds_of_input); the hot path
+  // stages the ring in the same sweep
   double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
-  if (boxes || bounds_of_input) warp_bounds(pts, nullptr, len, lane, minx, miny, maxx, maxy);
+  if (hot) {
+#pragma unroll 1
+    for (int k = lane; k < len; k += 32) {
+      const td::P2 p = pts[k];
+      spts[k] = p;
+      minx = p.x < minx ? p.x : minx; maxx = p.x > maxx ? p.x : maxx;
+      miny = p.y < miny ? p.y : miny; maxy = p.y > maxy ? p.y : maxy;
+    }
+    if (boxes || bounds_of_input) {
+      minx = warp_min(minx); maxx = warp_max(maxx);
+      miny = warp_min(miny); maxy = warp_max(maxy);
+    }
+    __syncwarp();
+  } else if (boxes || bounds_of_input) {
+    warp_bounds(pts, nullptr, len, lane, minx, miny, maxx, maxy);
+  }
   // Pre-filter of the tile box test: every vertex the simplifier drops lies within `tol` of the chord
   // that replaces it, and a chord point outside the (convex) box means a kept end point outside it.
   // So a ring that sticks out of the box by more than tol cannot be `within` it after simplification
@@ -99,40 +141,29 @@ simplify_kernel(const double* __restrict__ verts, const long long* __restrict__ 
     }
   }
   int m;
-  if (tol > 0.0 && len > 0) {
-    // The stack machine pushes and pops its scratch (result list, flags, stack, live-segment bits)
-    // at every node; in global memory each pop is an L2 round trip (stores do not allocate in L1),
-    // and those round trips get long when a bandwidth-bound kernel runs next to this one.  Rings of
-    // up to kSmemRing vertices (nearly all) keep the scratch in shared memory; the kept-vertex list
-    // is copied out at the end for td_take_rings.
-    extern __shared__ int s_work[];
-    int* my = s_work + (threadIdx.x >> 5) * kSmemInts;
-    if (len <= kSmemRing) {
-      m = td::simplify_ring(pts, len, tol, my, reinterpret_cast<uint32_t*>(my + 5 * kSmemRing), td::WarpCoop());
-      __syncwarp();
+  double area = 0.0;
+  if (hot) {
+    m = td::simplify_ring(spts, len, tol, my, reinterpret_cast<uint32_t*>(my + 5 * kSmemRing), td::WarpCoop());
+    __syncwarp();
 #pragma unroll 1
-      for (int k = lane; k < m; k += 32) sc[k] = my[k];
-      if (!bounds_of_input) warp_bounds(pts, my, m, lane, minx, miny, maxx, maxy);   // kept vertices
-    } else {
-      m = simplify_ring_global(pts, len, tol, sc, al);
-      __syncwarp();
-      if (!bounds_of_input) warp_bounds(pts, sc, m, lane, minx, miny, maxx, maxy);
-    }
-  } else {  // helpers.py:463: simplification is skipped for a non-positive tolerance
-#pragma unroll 1
-    for (int k = lane; k < len; k += 32) sc[k] = k;
-    m = len;
-    if (!bounds_of_input) warp_bounds(pts, nullptr, m, lane, minx, miny, maxx, maxy);
+    for (int k = lane; k < m; k += 32) sc[k] = my[k];
+    if (!bounds_of_input) warp_bounds(spts, my, m, lane, minx, miny, maxx, maxy);   // kept vertices
+    // the shoelace sum is order dependent: one lane, in ring order
+    if (out_area && lane == 0) area = fabs(td::ring_signed_area(m, [&](int k) { return spts[my[k]]; }));
+  } else {
+    // alive words: ring r owns (len + 31) / 32 words starting at v0 / 32 + r  (disjoint)
+    ColdOut o;
+    m = cold_ring(pts, len, tol, sc, alive + (v0 >> 5) + r, lane, !bounds_of_input, out_area != nullptr && lane == 0, &o);
+    if (!bounds_of_input) { minx = o.minx; miny = o.miny; maxx = o.maxx; maxy = o.maxy; }
+    area = o.area;
   }
-  __syncwarp();
   if (lane != 0) return;
   out_count[r] = m;
   if (out_bounds) {
     out_bounds[4 * r + 0] = minx; out_bounds[4 * r + 1] = miny;
     out_bounds[4 * r + 2] = maxx; out_bounds[4 * r + 3] = maxy;
   }
-  // the shoelace sum is order dependent: one lane, in ring order
-  if (out_area) out_area[r] = fabs(td::ring_signed_area(m, [&](int k) { return pts[sc[k]]; }));
+  if (out_area) out_area[r] = area;
   if (out_keep) {
     bool keep = true;
     if (boxes) {
@@ -189,7 +220,7 @@ extern "C" int td_simplify_rings(const double* verts, const long long* ring_off,
   if (mb == 0) { const char* e = getenv("TREEDET_SIMPLIFY_MINBLOCKS"); mb = e && atoi(e) > 0 ? atoi(e) : 12; }
   if (bs > 64) bs = 64;
   const dim3 grid(td_div_up((long long)n_rings * 32, bs));
-  const size_t smem = sizeof(int) * (bs / 32) * kSmemInts;
+  const size_t smem = (size_t)(bs / 32) * kSmemWarpBytes;
   cudaStream_t st = (cudaStream_t)stream;
 #define TD_SIMPLIFY_LAUNCH(MB)                                                                                          \
   simplify_kernel<MB><<<grid, bs, smem, st>>>(verts, ring_off, n_rings, tolerance, scratch, alive, boxes, ring_box,   \

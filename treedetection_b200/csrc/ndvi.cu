@@ -17,6 +17,7 @@
 // stored as float32 -- the reference's float64 array is only ever consumed through
 // cp.array(ndvi_data, dtype=float32) (postprocessing.py:543); the float32 value is
 // identical for all 65 536 uint8 input pairs (tests/test_oracle_vs_reference.py).
+#include <cstdint>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -161,18 +162,29 @@ decimate_ndvi_fast_kernel(const unsigned char* __restrict__ src0, const unsigned
       float w[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) w[k] = k < xn ? wx[k < ax.ktaps ? k : 0] : 0.f;
+      // The KT bytes of a row are fetched as the four aligned 32-bit words that hold them (a byte load per
+      // tap made the kernel load-issue bound) and shifted into place: words that hold at least one byte of
+      // the row lie inside the raster's allocation.
+      static_assert(KT == 12, "three realigned words");
 #pragma unroll 1
       for (int r = ty; r < nrows; r += kFastTileH) {
-        const unsigned char* p0 = src0 + (size_t)(row_lo + r) * in_w + xs;
-        const unsigned char* p1 = src1 + (size_t)(row_lo + r) * in_w + xs;
-        float acc0 = 0.f, acc1 = 0.f;
+        const size_t o = (size_t)(row_lo + r) * in_w + xs;
+        float acc[2];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          acc0 = __fadd_rn(acc0, __fmul_rn((float)p0[k], w[k]));
-          acc1 = __fadd_rn(acc1, __fmul_rn((float)p1[k], w[k]));
+        for (int b = 0; b < 2; ++b) {
+          const unsigned char* p = (b == 0 ? src0 : src1) + o;
+          const unsigned sh8 = ((unsigned)(uintptr_t)p & 3u) * 8u;
+          const unsigned* q = reinterpret_cast<const unsigned*>((uintptr_t)p & ~(uintptr_t)3);
+          const unsigned q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+          const unsigned u[3] = {__funnelshift_r(q0, q1, sh8), __funnelshift_r(q1, q2, sh8),
+                                 __funnelshift_r(q2, q3, sh8)};
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < KT; ++k) a = __fadd_rn(a, __fmul_rn((float)((u[k >> 2] >> (8 * (k & 3))) & 0xffu), w[k]));
+          acc[b] = a;
         }
-        sh[(size_t)r * kTileW + tx] = acc0;
-        sh[(size_t)(max_src_rows + r) * kTileW + tx] = acc1;
+        sh[(size_t)r * kTileW + tx] = acc[0];
+        sh[(size_t)(max_src_rows + r) * kTileW + tx] = acc[1];
       }
     } else {
       for (int r = ty; r < nrows; r += kFastTileH) {
