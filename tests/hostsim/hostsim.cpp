@@ -165,6 +165,9 @@ int hs_simplify_ring(const double* xy, int n, double tol, int* keep_idx, double*
 int hs_orientation(double ax, double ay, double bx, double by, double cx, double cy) {
   return td::orientation(ax, ay, bx, by, cx, cy);
 }
+int hs_orientation_nonzero(double ax, double ay, double bx, double by, double cx, double cy) {
+  return td::orientation_nonzero(ax, ay, bx, by, cx, cy) ? 1 : 0;
+}
 int hs_orientation_exact(double ax, double ay, double bx, double by, double cx, double cy) {
   return td::orientation_exact(ax, ay, bx, by, cx, cy);
 }

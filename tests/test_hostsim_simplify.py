@@ -15,6 +15,7 @@ def _lib():
     lib = hostsim.load()
     lib.hs_orientation.argtypes = [C.c_double] * 6
     lib.hs_orientation_exact.argtypes = [C.c_double] * 6
+    lib.hs_orientation_nonzero.argtypes = [C.c_double] * 6
     lib.hs_simplify_ring.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     return lib
 
@@ -47,6 +48,7 @@ def test_orientation_exact_on_near_degenerate_inputs():
         want = (d > 0) - (d < 0)
         assert lib.hs_orientation(ax, ay, bx, by, cx, cy) == want
         assert lib.hs_orientation_exact(ax, ay, bx, by, cx, cy) == want
+        assert lib.hs_orientation_nonzero(ax, ay, bx, by, cx, cy) == (want != 0)   # the guard's neighbour test
         assert geom.orientation(ax, ay, bx, by, cx, cy) == want
         n_fallback += 1
     assert n_fallback
@@ -166,3 +168,35 @@ def test_tile_box_prefilter_is_conservative(tol):
                 n_pre += pre_reject
                 n_rings += 1
     assert n_pre > 50 and n_rings - n_pre > 50
+
+
+def test_orientation_nonzero_equals_orientation_on_grid_and_random_points():
+    """the branch-free neighbour test of the simplifier's guard: same answer as orientation() != 0 on exactly
+    collinear grid points (axis-parallel, diagonal), zero products, mixed signs and random triples"""
+    lib = _lib()
+    rng = np.random.default_rng(5)
+    pts = []
+    for _ in range(3000):
+        ox, oy = 412000.0 + float(rng.integers(0, 5000)) * 0.2, 5318000.0 - float(rng.integers(0, 5000)) * 0.2
+        a = (ox, oy)
+        kind = int(rng.integers(0, 5))
+        if kind == 0:      # horizontal / vertical run (one product exactly zero)
+            b, c = (ox + 0.2 * float(rng.integers(1, 9)), oy), (ox - 0.2 * float(rng.integers(0, 9)), oy)
+        elif kind == 1:
+            b, c = (ox, oy + 0.2 * float(rng.integers(1, 9))), (ox, oy - 0.2 * float(rng.integers(0, 9)))
+        elif kind == 2:    # diagonal on the pixel grid: collinear up to the rounding of the coordinates
+            k, m = float(rng.integers(1, 9)), float(rng.integers(-9, 9))
+            b, c = (ox + 0.2 * k, oy + 0.2 * k), (ox + 0.2 * m, oy + 0.2 * m)
+        elif kind == 3:    # c == a or c == b
+            b = (ox + float(rng.uniform(-3, 3)), oy + float(rng.uniform(-3, 3)))
+            c = a if rng.uniform() < 0.5 else b
+        else:
+            b = (ox + float(rng.uniform(-3, 3)), oy + float(rng.uniform(-3, 3)))
+            c = (ox + float(rng.uniform(-3, 3)), oy + float(rng.uniform(-3, 3)))
+        pts.append((a, b, c))
+    n_zero = 0
+    for a, b, c in pts:
+        want = lib.hs_orientation(a[0], a[1], b[0], b[1], c[0], c[1])
+        assert lib.hs_orientation_nonzero(a[0], a[1], b[0], b[1], c[0], c[1]) == (want != 0)
+        n_zero += want == 0
+    assert n_zero > 300

@@ -89,6 +89,19 @@ TD_HD inline int orientation(double ax, double ay, double bx, double by, double 
   return orientation_exact(ax, ay, bx, by, cx, cy);
 }
 
+// orientation(...) != 0 without the sign cases.  With detsum = |detleft| + |detright| the filter of
+// orientation() reads |det| >= 3.33e-16 * detsum in every branch: where the two products differ in sign (or
+// one is zero) det = +-detsum exactly, so the test holds whenever orientation() returns sign(det) unfiltered,
+// and where they agree in sign it is orientation()'s own error bound.
+TD_HD inline bool orientation_nonzero(double ax, double ay, double bx, double by, double cx, double cy) {
+  const double detleft = (ax - cx) * (by - cy);
+  const double detright = (ay - cy) * (bx - cx);
+  const double det = detleft - detright;
+  const double detsum = fabs(detleft) + fabs(detright);
+  if (fabs(det) >= 3.3306690738754716e-16 * detsum) return det != 0.0;
+  return orientation_exact(ax, ay, bx, by, cx, cy) != 0;
+}
+
 // ---- robust segment intersection: "is there an interior intersection" --------
 TD_HD inline bool env_has_pt(const P2& p1, const P2& p2, const P2& q) {
   return q.x >= fmin(p1.x, p2.x) && q.x <= fmax(p1.x, p2.x) && q.y >= fmin(p1.y, p2.y) && q.y <= fmax(p1.y, p2.y);
@@ -369,7 +382,7 @@ TD_HD inline int simplify_ring(const P2* pts, int n, double tol, IdxT* scratch, 
         const bool starts_in_b = live && k == j;       // input segment starting in B
         if (ends_in_a || starts_in_b) {
           const P2 o = ends_in_a ? p : q;
-          if (orientation(A.x, A.y, B.x, B.y, o.x, o.y) != 0) continue;
+          if (orientation_nonzero(A.x, A.y, B.x, B.y, o.x, o.y)) continue;
         }
         if (env_overlap(env, p, q) && interior_intersection_cold(p.x, p.y, q.x, q.y, A.x, A.y, B.x, B.y)) bad = true;
       }

@@ -20,6 +20,8 @@
 // NDVI min / max / mean / population variance; empty set -> -1.
 // mean / var are accumulated in float64 and rounded once (the reference sums in
 // float32; agreement is to ~1e-7, the contract is 1e-5 absolute).
+#include <cstdlib>
+
 #include "chain_internal.cuh"
 #include "common.cuh"
 
@@ -50,7 +52,7 @@ TD_D bool better_min(float v, long long k, float bv, long long bk) {
   return v < bv || (v == bv && k < bk);
 }
 
-template <int MODE>
+template <int MODE, int kRows = 4>
 __global__ void __launch_bounds__(256)
 crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict__ ring_off,
                    const long long* __restrict__ ring_idx, int n,
@@ -120,19 +122,19 @@ crown_stats_kernel(const double* __restrict__ verts, const long long* __restrict
     // rows outer, lanes over the columns of a row (no per-pixel division); the arithmetic of the
     // pixel coordinates is the reference's, with the row terms hoisted (same operations, same rounding)
     if (MODE == kHeightOnly) {
-      // Four rows per step: the four raster loads of a lane are issued together, before the distance
+      // kRows (four) rows per step: the four raster loads of a lane are issued together, before the distance
       // arithmetic (one dependent load per row left every warp waiting on DRAM for most of its life).
       // The loads are unconditional -- the window lies inside the raster -- and the arg-max carries its
       // flat index, so neither the extra reads nor the order of evaluation change the result.
-      for (int rb = r_lo; rb <= r_hi; rb += 4) {
+      for (int rb = r_lo; rb <= r_hi; rb += kRows) {
         for (int cc = c_lo + lane; cc <= c_hi; cc += 32) {
-          float v[4];
+          float v[kRows];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < kRows; ++q)
             v[q] = rb + q <= r_hi ? __ldg(height + ((long long)(rb + q) * cols + cc)) : 0.f;
           const double ax = T.a * (double)cc, dxc = T.d * (double)cc;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < kRows; ++q) {
             const int rr = rb + q;
             if (rr > r_hi) break;
             const double xd = ax + T.b * (double)rr + T.c;
@@ -456,10 +458,17 @@ int td_crown_stats_ex(const double* verts, const long long* ring_off, const long
       crown_stats_kernel<kCombined><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows, cols,
                                                                  T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
       break;
-    case kHeightOnly:
-      crown_stats_kernel<kHeightOnly><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows,
-                                                                   cols, T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
+    case kHeightOnly: {
+      static int rows_per_step = 0;    // raster rows in flight per lane (TREEDET_STATS_ROWS: 4 or 8)
+      if (rows_per_step == 0) { const char* e = getenv("TREEDET_STATS_ROWS"); rows_per_step = e && atoi(e) >= 8 ? 8 : 4; }
+      if (rows_per_step == 8)
+        crown_stats_kernel<kHeightOnly, 8><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows,
+                                                                        cols, T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
+      else
+        crown_stats_kernel<kHeightOnly, 4><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows,
+                                                                        cols, T, tf_dev, max_h, hxy, ndvi_stats, n_dev);
       break;
+    }
     default:
       crown_stats_kernel<kNdviOnly><<<blocks, threads, 0, st>>>(verts, ring_off, ring_idx, n, ndvi, height, rows, cols,
                                                                  T, tf_dev, max_h, hxy, ndvi_stats, n_dev);

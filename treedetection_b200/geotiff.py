@@ -317,8 +317,16 @@ def _pool():
     global _io_pool
     if _io_pool is None:
         from concurrent.futures import ThreadPoolExecutor
-        _io_pool = ThreadPoolExecutor(max_workers=8)
+        _io_pool = ThreadPoolExecutor(max_workers=_io_threads())
     return _io_pool
+
+
+def _io_threads():
+    """Threads that copy file pages into the staging buffers (``TREEDET_IO_THREADS``, default 8)."""
+    try:
+        return max(1, int(os.environ.get("TREEDET_IO_THREADS", "8")))
+    except ValueError:
+        return 8
 
 
 def _pread_into(fd, mv, file_off):
@@ -392,7 +400,7 @@ def read_device_plain(path, device, out=None, slot=0, piece=32 << 20, probe=Fals
                 if events[half] is not None:
                     events[half].synchronize()           # the copy out of this half of the ring is done
                 base = half * piece
-                step = max(1 << 20, -(-n // 8))
+                step = max(1 << 20, -(-n // _io_threads()))
                 list(pool.map(lambda a: _pread_into(f.fileno(), ring_np[base + a:base + min(a + step, n)],
                                                     file_off + lo + a), range(0, n, step)))
                 flat[dst + lo:dst + lo + n].copy_(ring[base:base + n], non_blocking=True)
