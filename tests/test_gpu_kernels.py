@@ -196,6 +196,22 @@ def test_ndvi_decimate(dev, shape, factor):
     np.testing.assert_array_equal(got, ref)
 
 
+def test_ndvi_decimate_unaligned_view(dev):
+    """the fast kernel fetches aligned words around each run of taps: a raster that starts at an odd byte offset
+    inside its allocation (a band slice of a larger tensor, odd band size) must give the same NDVI"""
+    rng = np.random.default_rng(77)
+    big = rng.integers(0, 256, size=(6, 335, 501), dtype=np.uint8)
+    rgbi = big[1:5]
+    oh, ow = 67, 100
+    red = port.decimate_bilinear(rgbi[0], oh, ow); nir = port.decimate_bilinear(rgbi[3], oh, ow)
+    dec = np.stack([red, rgbi[1][:oh, :ow], rgbi[2][:oh, :ow], nir])
+    ref = port.ndvi_from_rgbi(dec).astype(np.float32)
+    d = torch.from_numpy(big).to(dev)[1:5]
+    assert d.data_ptr() % 4 != 0 and d.is_contiguous()
+    got = ops.ndvi_decimate(d, oh, ow).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+
+
 def test_decimate_f32(dev):
     rng = np.random.default_rng(2)
     band = rng.uniform(0, 40, (900, 1100)).astype(np.float32)

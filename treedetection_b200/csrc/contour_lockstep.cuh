@@ -8,7 +8,7 @@
 // One call performs one bounded micro-step: either "advance the raster scan to the next border
 // start (and begin that border)" or "one step along the current border".  The step along a
 // border is branch-light: the 8 neighbours are gathered into a bit mask from three 3-bit row
-// reads and the next direction is a find-first-set on the rotated mask.  contour_core.cuh keeps
+// reads (one funnel shift per row) and the next direction is a find-first-set on the rotated mask.  contour_core.cuh keeps
 // the straightforward sequential form; both are checked against cv2 (tests/test_hostsim_contours.py).
 //
 // Plain C++ (tests/hostsim runs it with a single lane).
@@ -44,24 +44,47 @@ TD_HD inline int ffs32(uint32_t v) {   // index of the lowest set bit, v != 0
 #endif
 }
 
-// bits (x-1, x, x+1) of row y as a 3-bit value, zero outside the window
-template <typename LabelT, typename Mem>
-TD_HD inline uint32_t row3(const RasterT<LabelT, Mem>& R, int x, int y) {
-  if ((unsigned)y >= (unsigned)R.h) return 0u;
-  const int wi = x >> 5, b = x & 31;
-  const uint32_t* row = R.fg + (size_t)y * R.wpr;
-  const uint32_t lo = Mem::ld(row + wi);
-  if (b == 0) return (wi > 0 ? (Mem::ld(row + wi - 1) >> 31) : 0u) | ((lo & 3u) << 1);
-  if (b == 31) return ((lo >> 30) & 3u) | ((wi + 1 < R.wpr ? (Mem::ld(row + wi + 1) & 1u) : 0u) << 2);
-  return (lo >> (b - 1)) & 7u;
+// low 32 bits of the 64-bit value (hi : lo) shifted right by s (0 <= s < 32): one funnel shift on the device
+TD_HD inline uint32_t shr64(uint32_t lo, uint32_t hi, int s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31));
+#endif
 }
 
-// 8-neighbour foreground mask of (x, y), bit k = direction k (E, NE, N, NW, W, SW, S, SE)
+// 8-neighbour foreground mask of (x, y), bit k = direction k (E, NE, N, NW, W, SW, S, SE).
+// The step along a border calls this once per pixel, so it is written without a per-row case analysis:
+// word index, bit position and the "neighbour word needed" predicates are computed once, each of
+// the three rows is one load (plus one predicated load when x sits on a word boundary) and the three bits
+// come out of a 64-bit window (previous word's top bit : this word : next word's low bit) with a funnel
+// shift.  A word that is not loaded only feeds bits the shift does not select.
 template <typename LabelT, typename Mem>
 TD_HD inline uint32_t neighbours(const RasterT<LabelT, Mem>& R, int x, int y) {
-  const uint32_t t = row3(R, x, y - 1), m = row3(R, x, y), b = row3(R, x, y + 1);
+  const int wi = x >> 5, b = x & 31;
+  const bool need_l = b == 0 && wi > 0, need_r = b == 31 && wi + 1 < R.wpr;
+  const uint32_t* mid = R.fg + ((size_t)y * R.wpr + wi);
+  uint32_t r[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int d = 0; d < 3; ++d) {
+    const int yy = y + d - 1;
+    uint32_t v = 0u;
+    if ((unsigned)yy < (unsigned)R.h) {
+      const uint32_t* p = mid + (d - 1) * R.wpr;
+      const uint32_t lo = Mem::ld(p);
+      const uint32_t pl = need_l ? Mem::ld(p - 1) : 0u;
+      const uint32_t pr = need_r ? Mem::ld(p + 1) : 0u;
+      const uint32_t w_lo = (lo << 1) | (pl >> 31);            // bit k = pixel 32 * wi + k - 1
+      const uint32_t w_hi = (lo >> 31) | ((pr & 1u) << 1);
+      v = shr64(w_lo, w_hi, b) & 7u;                           // pixels x - 1, x, x + 1
+    }
+    r[d] = v;
+  }
+  const uint32_t t = r[0], m = r[1], bt = r[2];
   return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) |
-         ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
+         ((bt & 1u) << 5) | (((bt >> 1) & 1u) << 6) | (((bt >> 2) & 1u) << 7);
 }
 
 template <typename LabelT, typename Mem>
