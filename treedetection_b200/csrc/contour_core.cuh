@@ -95,11 +95,10 @@ struct RasterT {
     const size_t wi = (size_t)y * wpr + (x >> 5);
     const uint32_t bit = 1u << (x & 31);
     const uint32_t v = Mem::ld(visited + wi);
-    if (right_flag) {
-      Mem::st(right + wi, Mem::ld(right + wi) | bit);
-      Mem::st(visited + wi, v | bit);
-      if (label) label[(size_t)y * w + x] = (LabelT)lab;
-    } else if (!(v & bit)) {
+    // a pixel left through its right side always takes the border's label, any other pixel only on its first
+    // visit (one store site for both cases: lanes of a warp that differ in right_flag do not serialise)
+    if (right_flag) Mem::st(right + wi, Mem::ld(right + wi) | bit);
+    if (right_flag || !(v & bit)) {
       Mem::st(visited + wi, v | bit);
       if (label) label[(size_t)y * w + x] = (LabelT)lab;
     }

@@ -332,8 +332,8 @@ __device__ __forceinline__ void walk_lanes(td::LaneState<unsigned short, Mem>& S
   A.sizes_kn[(size_t)A.n + i] = over ? 0 : S.cc.n_ring_verts;
 }
 
-template <int kLanes>
-__global__ void __launch_bounds__(32) trace_walk_kernel(WalkArgs A) {
+template <int kLanes, int kMinBlocks = 1>
+__global__ void __launch_bounds__(32, kMinBlocks) trace_walk_kernel(WalkArgs A) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x;
   const int i = blockIdx.x * kLanes + lane;
@@ -473,7 +473,16 @@ extern "C" int td_trace_walk(const uint32_t* bits, const int* win, const long lo
   A.smem_bytes = smem_per_warp(n_inst, L);
   if (L == 32) trace_walk_kernel<32><<<td_div_up(n_inst, 32), 32, A.smem_bytes, st>>>(A);
   else if (L == 16) trace_walk_kernel<16><<<td_div_up(n_inst, 16), 32, A.smem_bytes, st>>>(A);
-  else trace_walk_kernel<8><<<td_div_up(n_inst, 8), 32, A.smem_bytes, st>>>(A);
+  else {
+    // residency of the 8-lane form: 96 registers without a bound (21 one-warp CTAs per SM), 80 at 24 CTAs (default:
+    // step 3.561 -> 3.537 ms), 72 at 28 (a few spilled words: 3.554); the walk is a chain of dependent
+    // shared-memory reads, resident warps are what hides it
+    static int mb = -1;
+    if (mb < 0) { const char* e = getenv("TREEDET_TRACE_MINBLOCKS"); mb = e ? atoi(e) : 24; }
+    if (mb >= 28) trace_walk_kernel<8, 28><<<td_div_up(n_inst, 8), 32, A.smem_bytes, st>>>(A);
+    else if (mb >= 24) trace_walk_kernel<8, 24><<<td_div_up(n_inst, 8), 32, A.smem_bytes, st>>>(A);
+    else trace_walk_kernel<8><<<td_div_up(n_inst, 8), 32, A.smem_bytes, st>>>(A);
+  }
   TD_CHECK_LAUNCH("td_trace_walk");
   return TD_OK;
 }
