@@ -136,6 +136,11 @@ struct PackedTap {
   float w1;
 };
 
+struct __align__(16) TapRec {
+  int off0, off1;   // byte offsets of the two taps (rows: i * kPad * 4, columns: i * 4)
+  float w1, w0;
+};
+
 TD_D PackedTap pack_tap(const Tap& t) { return PackedTap{t.i0 | (t.i1 << 8), t.w1}; }
 TD_D Tap unpack_tap(const PackedTap& p) {
   Tap t;
@@ -148,8 +153,13 @@ __global__ void __launch_bounds__(kPasteThreads)
 paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ win,
                   const long long* __restrict__ word_off, const float* __restrict__ probs, int n, float thr,
                   uint32_t* __restrict__ bits) {
-  __shared__ float tab[kPad][kPad];
-  __shared__ PackedTap s_tx[kTapCap], s_ty[kTapCap];
+  __shared__ __align__(16) float tab[kPad][kPad];
+  // one tap-table area, two views: byte-offset records (windows up to kTapCap x kTapCap, nearly all) or packed taps
+  __shared__ __align__(16) TapRec s_rec[2 * kTapCap];
+  TapRec* s_rx = s_rec;
+  TapRec* s_ry = s_rec + kTapCap;
+  PackedTap* s_tx = reinterpret_cast<PackedTap*>(s_rec);
+  PackedTap* s_ty = s_tx + kTapCap;
   const int i = blockIdx.x;
   if (i >= n) return;
   const int ww = win[4 * i + 2], wh = win[4 * i + 3];
@@ -163,14 +173,61 @@ paste_pack_kernel(const float* __restrict__ boxes_px, const int* __restrict__ wi
     if (r >= 1 && r <= kM && c >= 1 && c <= kM) v = probs[(size_t)i * kM * kM + (r - 1) * kM + (c - 1)];
     tab[r][c] = v;
   }
-  for (int k = threadIdx.x; k < min(ww, kTapCap); k += kPasteThreads) s_tx[k] = pack_tap(make_tap(wx0 + k, bx0, bx1));
-  for (int k = threadIdx.x; k < min(wh, kTapCap); k += kPasteThreads) s_ty[k] = pack_tap(make_tap(wy0 + k, by0, by1));
+  if (ww > kTapCap || wh > kTapCap) {
+    for (int k = threadIdx.x; k < min(ww, kTapCap); k += kPasteThreads) s_tx[k] = pack_tap(make_tap(wx0 + k, bx0, bx1));
+    for (int k = threadIdx.x; k < min(wh, kTapCap); k += kPasteThreads) s_ty[k] = pack_tap(make_tap(wy0 + k, by0, by1));
+  }
+  // the same taps as byte offsets into the table (rows: i * kPad * 4, columns: i * 4) with both weights: the
+  // inner loop below then needs one 16-byte broadcast load, four adds and four table loads per row
+  const bool fast = ww <= kTapCap && wh <= kTapCap;
+  if (fast) {
+    for (int k = threadIdx.x; k < ww; k += kPasteThreads) {
+      const Tap t = make_tap(wx0 + k, bx0, bx1);
+      s_rx[k] = TapRec{t.i0 * 4, t.i1 * 4, t.w1, t.w0};
+    }
+    for (int k = threadIdx.x; k < wh; k += kPasteThreads) {
+      const Tap t = make_tap(wy0 + k, by0, by1);
+      s_ry[k] = TapRec{t.i0 * kPad * 4, t.i1 * kPad * 4, t.w1, t.w0};
+    }
+  }
   __syncthreads();
   const int wpr = (ww + 31) >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* out = bits + word_off[i];
-  // a warp owns a 32-column word column and walks down its rows: the column tap of a lane is loaded once, the
-  // row tap is one broadcast load per row, the four table addresses are two row bases plus two column indices
+  if (fast) {
+    // a warp owns a 32-column word column and walks down its rows; lanes past the window sample table entry
+    // (0, 0) with zero weights and are masked out of the ballot.  sample(): the same products and fused adds
+    // in the same order
+    const char* tab0 = reinterpret_cast<const char*>(&tab[0][0]);
+    for (int wi = warp; wi < wpr; wi += kPasteThreads / 32) {
+      const int x = wi * 32 + lane;
+      const bool live = x < ww;
+      const TapRec cx = live ? s_rx[x] : TapRec{0, 0, 0.f, 0.f};
+      const char* col0 = tab0 + cx.off0;
+      const char* col1 = tab0 + cx.off1;
+      uint32_t* o = out + wi;
+#pragma unroll 2
+      for (int y = 0; y < wh; ++y) {
+        const TapRec ry = s_ry[y];
+        const float nw = *reinterpret_cast<const float*>(col0 + ry.off0);
+        const float ne = *reinterpret_cast<const float*>(col1 + ry.off0);
+        const float sw = *reinterpret_cast<const float*>(col0 + ry.off1);
+        const float se = *reinterpret_cast<const float*>(col1 + ry.off1);
+        const float cnw = __fmul_rn(ry.w0, cx.w0);
+        const float cne = __fmul_rn(ry.w0, cx.w1);
+        const float csw = __fmul_rn(ry.w1, cx.w0);
+        const float cse = __fmul_rn(ry.w1, cx.w1);
+        float acc = __fmul_rn(nw, cnw);
+        acc = __fmaf_rn(ne, cne, acc);
+        acc = __fmaf_rn(sw, csw, acc);
+        acc = __fmaf_rn(se, cse, acc);
+        const uint32_t word = __ballot_sync(0xffffffffu, live && acc >= thr);
+        if (lane == 0) o[(size_t)y * wpr] = word;
+      }
+    }
+    return;
+  }
+  // windows wider / higher than kTapCap (rare): packed taps for the first kTapCap columns / rows, the rest on the fly
   for (int wi = warp; wi < wpr; wi += kPasteThreads / 32) {
     const int x = wi * 32 + lane;
     const bool live = x < ww;
