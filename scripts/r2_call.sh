@@ -1,11 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/c_tests.log 2>&1; echo tests $?; tail -2 gpurun_out/c_tests.log
-timeout 200 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-merged --no-files > gpurun_out/c_bench.json 2> gpurun_out/c_bench.err; echo bench $?
+timeout 400 python bench.py > gpurun_out/v7_bench.json 2> gpurun_out/v7_bench.err; echo bench $?
 python - <<'PY'
 import json
-for l in open("gpurun_out/c_bench.json"):
+for l in open("gpurun_out/v7_bench.json"):
     if l.startswith("{"):
         d = json.loads(l)
-        print(round(d["value"], 1), round(d["ms_per_step"], 3), (d.get("parity") or "NO PARITY")[:40], d["config"].get("stage_ms"), d["e2e"]["value"])
+        print(round(d["value"], 1), round(d["ms_per_step"], 3), d["e2e"]["value"], d["combined_path"]["value"], d["path_roofline"]["frac"], (d.get("parity") or "")[:30])
 PY
