@@ -152,9 +152,10 @@ decimate_ndvi_fast_kernel(const unsigned char* __restrict__ src0, const unsigned
   const int row_lo = ay.start[oy0];
   const int nrows = ay.start[oy_last] + ay.count[oy_last] - row_lo;
   const int ox = ox0 + tx;
-  // every lane may read KT bytes from its first tap: true unless the tile touches the right edge
+  // every lane may read the four aligned words around the KT bytes from its first tap (up to KT + 4 bytes past
+  // it) without leaving its row: true unless the tile touches the right edge
   const int ox_last = min(ox0 + kTileW, out_w) - 1;
-  const bool wide = ax.start[ox_last] + KT <= in_w;
+  const bool wide = ax.start[ox_last] + KT + 4 <= in_w;
   if (ox < out_w) {
     const int xs = ax.start[ox], xn = ax.count[ox];
     const float* wx = ax.w + (size_t)ox * ax.ktaps;
@@ -163,8 +164,8 @@ decimate_ndvi_fast_kernel(const unsigned char* __restrict__ src0, const unsigned
 #pragma unroll
       for (int k = 0; k < KT; ++k) w[k] = k < xn ? wx[k < ax.ktaps ? k : 0] : 0.f;
       // The KT bytes of a row are fetched as the four aligned 32-bit words that hold them (a byte load per
-      // tap made the kernel load-issue bound) and shifted into place: words that hold at least one byte of
-      // the row lie inside the raster's allocation.
+      // tap made the kernel load-issue bound) and shifted into place; `wide` keeps all four inside the row (the
+      // first word may start up to 3 bytes before the first tap: inside the row or the previous row / band).
       static_assert(KT == 12, "three realigned words");
 #pragma unroll 1
       for (int r = ty; r < nrows; r += kFastTileH) {
