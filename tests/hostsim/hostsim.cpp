@@ -105,6 +105,20 @@ int hs_find_contours_lockstep(const uint8_t* mask, int h, int w, int* npts_out, 
   return nc;
 }
 
+// 8-neighbour masks of every pixel of a mask (contour_lockstep.cuh neighbours()): out[y * w + x], bit k = direction k
+void hs_neighbour_masks(const uint8_t* mask, int h, int w, uint8_t* out) {
+  const int wpr = (w + 31) / 32;
+  std::vector<uint32_t> fg((size_t)wpr * h, 0u);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      if (mask[(size_t)y * w + x]) fg[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+  td::Raster R;
+  R.fg = fg.data(); R.visited = nullptr; R.right = nullptr; R.label = nullptr;
+  R.w = w; R.h = h; R.wpr = wpr;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = (uint8_t)td::neighbours(R, x, y);
+}
+
 // Single-pass walk into a SLOT (contours.cu trace_walk_kernel): tables of cap_contours rows and
 // cap_points points, guarded by canaries.  Returns 0 when everything fitted, 1 when the instance
 // outgrew its slot (the counts are still complete), -1 when a canary was overwritten.

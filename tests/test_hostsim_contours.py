@@ -133,3 +133,21 @@ def test_single_pass_walk_into_slots(seed):
         rc2, counts2, _ = _walk_slot(mask, cc, cp)
         assert rc2 == 1, "overflow must be reported and no canary touched"
         np.testing.assert_array_equal(counts2, counts)
+
+
+@pytest.mark.parametrize("w", [1, 2, 31, 32, 33, 63, 64, 65, 97])
+def test_neighbour_masks_across_word_boundaries(w):
+    """neighbours() reads one word per row plus a predicated neighbour word at bit 0 / bit 31: every pixel of random
+    masks whose widths straddle the 32-bit word boundaries against a plain pixel lookup (E, NE, N, NW, W, SW, S, SE)"""
+    lib = hostsim.load()
+    rng = np.random.default_rng(w)
+    h = 9
+    mask = (rng.uniform(size=(h, w)) < 0.55).astype(np.uint8)
+    got = np.zeros((h, w), dtype=np.uint8)
+    lib.hs_neighbour_masks(mask.ctypes.data_as(C.c_void_p), h, w, got.ctypes.data_as(C.c_void_p))
+    pad = np.zeros((h + 2, w + 2), dtype=np.uint8)
+    pad[1:-1, 1:-1] = mask
+    want = np.zeros((h, w), dtype=np.uint8)
+    for k, (dx, dy) in enumerate([(1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1), (0, 1), (1, 1)]):
+        want |= (pad[1 + dy:1 + dy + h, 1 + dx:1 + dx + w] << k).astype(np.uint8)
+    np.testing.assert_array_equal(got, want)
