@@ -160,3 +160,70 @@ def test_lzw_encoder_decoder_agree_at_every_stream_length():
         dst = C.create_string_buffer(n + 8)
         got = lib.td_tiff_lzw_decode(enc, len(enc), dst, n + 8)
         assert got == n and dst.raw[:n] == raw, n
+
+
+TF = (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0)
+
+
+@pytest.mark.parametrize("mode", ["gray", "rgb", "f32"])
+def test_bigtiff_reader_matches_pil(tmp_path, mode):
+    """BigTIFF (magic 43, 64-bit offsets: what GDAL writes for rasters beyond 4 GB) written by PIL's own writer:
+    the reader returns the same pixels -- single band, chunky RGB, float32 -- whole and windowed"""
+    rng = np.random.default_rng(9)
+    arr = {"gray": rng.integers(0, 255, (211, 333), dtype=np.uint8),
+           "rgb": rng.integers(0, 255, (97, 120, 3), dtype=np.uint8),
+           "f32": rng.normal(size=(64, 75)).astype(np.float32)}[mode]
+    path = str(tmp_path / "b.tif")
+    try:
+        Image.fromarray(arr).save(path, format="TIFF", big_tiff=True)
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"PIL cannot write BigTIFF: {e}")
+    with open(path, "rb") as f:
+        if f.read(4) != b"II+\x00":
+            pytest.skip("this PIL ignores big_tiff")
+    want = arr.transpose(2, 0, 1) if arr.ndim == 3 else arr[None]
+    got, info = geotiff.read(path)
+    np.testing.assert_array_equal(got, want)
+    assert (info.width, info.height, info.count) == (want.shape[2], want.shape[1], want.shape[0])
+    assert geotiff.read_info(path).dtype == arr.dtype
+    win, _ = geotiff.read(path, window=(10, 20, 40, 30))
+    np.testing.assert_array_equal(win, want[:, 20:50, 10:50])
+
+
+@pytest.mark.parametrize("compression,predictor", [(None, 1), ("lzw", 1), ("lzw", 2)])
+def test_bigtiff_writer_is_read_by_libtiff_and_round_trips(tmp_path, compression, predictor):
+    """geotiff.write(bigtiff=True): libtiff (through PIL) decodes the single-band file to the same pixels; planar
+    multi-band rasters, the geo tags and windowed reads round-trip through this package's reader; classic and
+    BigTIFF layouts hold the same pixels; a classic file cannot be forced past 4 GB of offsets"""
+    smooth = (np.add.outer(np.arange(300), np.arange(517)) % 251).astype(np.uint8)
+    path = str(tmp_path / "w.tif")
+    geotiff.write(path, smooth, TF, epsg=25832, compression=compression, predictor=predictor, bigtiff=True)
+    with open(path, "rb") as f:
+        assert f.read(4) == b"II+\x00"
+    with Image.open(path) as im:
+        np.testing.assert_array_equal(np.array(im), smooth)
+    got, info = geotiff.read(path)
+    np.testing.assert_array_equal(got[0], smooth)
+    assert info.epsg == 25832 and info.transform == TF
+    arr = _cases()["rgba"]
+    geotiff.write(path, arr, TF, epsg=25832, nodata=0.0, compression=compression, predictor=predictor, bigtiff=True)
+    got, info = geotiff.read(path)
+    np.testing.assert_array_equal(got, arr)
+    assert info.nodata == 0.0 and info.count == arr.shape[0]
+    win, _ = geotiff.read(path, window=(100, 50, 200, 120))
+    np.testing.assert_array_equal(win, arr[:, 50:170, 100:300])
+    classic = str(tmp_path / "c.tif")
+    geotiff.write(classic, arr, TF, epsg=25832, compression=compression, predictor=predictor)       # auto: classic
+    with open(classic, "rb") as f:
+        assert f.read(4) == b"II*\x00"
+    np.testing.assert_array_equal(geotiff.read(classic)[0], arr)
+
+
+def test_not_a_tiff_is_rejected(tmp_path):
+    p = tmp_path / "x.tif"
+    p.write_bytes(b"II\x2c\x00" + b"\x00" * 32)
+    with pytest.raises(ValueError):
+        geotiff.read_info(str(p))
+    p.write_bytes(b"II+\x00\x04\x00\x00\x00" + b"\x00" * 32)       # BigTIFF magic with a wrong offset size
+    with pytest.raises(ValueError):
+        geotiff.read(str(p))

@@ -126,3 +126,27 @@ def test_plain_reader_streams_uncompressed_strips_to_the_device(tmp_path, dev):
     assert geotiff.read_device_plain(lzw, dev) is None and geotiff.read_device_plain(chunky, dev) is None
     assert geotiff.read_device_plain(lzw, dev, probe=True) is None
     assert geotiff.read_device_plain(str(tmp_path / "rgba.tif"), dev, probe=True) is True
+
+
+def test_bigtiff_on_the_device_paths(tmp_path, dev):
+    """BigTIFF files (64-bit offsets) through the device LZW decoder and the streaming reader of uncompressed strips:
+    same pixels as the host reader, which tests/test_geotiff_codec.py pins against libtiff"""
+    cases = _cases()
+    tf = (0.2, 0.0, 412000.0, 0.0, -0.2, 5318000.0)
+    for name, predictor in (("rgba", 2), ("f32", 1), ("band", 1)):
+        arr = cases[name]
+        path = str(tmp_path / f"{name}_lzw.tif")
+        geotiff.write(path, arr, tf, epsg=25832, compression="lzw", predictor=predictor, bigtiff=True)
+        ref, rinfo = geotiff.read(path)
+        np.testing.assert_array_equal(ref, arr if arr.ndim == 3 else arr[None])
+        assert geotiff.device_decodable(path)
+        got, info, status = geotiff.read_device(path, dev)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0 and info == rinfo
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+        plain = str(tmp_path / f"{name}_plain.tif")
+        geotiff.write(plain, arr, tf, epsg=25832, bigtiff=True)
+        got, info = geotiff.read_device_plain(plain, dev, piece=100_000)
+        torch.cuda.synchronize()
+        assert info == rinfo
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)

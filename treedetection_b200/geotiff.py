@@ -21,7 +21,21 @@ from dataclasses import dataclass
 import numpy as np
 
 _TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 7: ("B", 1), 8: ("h", 2),
-          9: ("i", 4), 10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 16: ("Q", 8)}
+          9: ("i", 4), 10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 16: ("Q", 8), 17: ("q", 8), 18: ("Q", 8)}
+
+
+def _tiff_kind(buf):
+    """(byte order, is BigTIFF) of a TIFF header, or None: classic TIFF (magic 42, 32-bit offsets) or BigTIFF
+    (magic 43, 64-bit offsets -- what GDAL writes for rasters beyond 4 GB, e.g. a merged county mosaic)."""
+    if len(buf) < 16 or buf[:2] not in (b"II", b"MM"):
+        return None
+    bo = "<" if buf[:2] == b"II" else ">"
+    magic = struct.unpack(bo + "H", buf[2:4])[0]
+    if magic == 42:
+        return bo, False
+    if magic == 43 and struct.unpack(bo + "HH", buf[4:8]) == (8, 0):
+        return bo, True
+    return None
 
 
 @dataclass
@@ -41,18 +55,25 @@ class GeoInfo:
 
 
 def _read_ifd(buf, bo):
-    off = struct.unpack(bo + "I", buf[4:8])[0]
-    n = struct.unpack(bo + "H", buf[off:off + 2])[0]
+    big = struct.unpack(bo + "H", buf[2:4])[0] == 43
+    if big:      # BigTIFF: 64-bit first-IFD offset, entry count, value counts and value offsets; 20-byte entries
+        off = struct.unpack(bo + "Q", buf[8:16])[0]
+        n = struct.unpack(bo + "Q", buf[off:off + 8])[0]
+        first, esize, inline, cfmt, ofmt = off + 8, 20, 8, "Q", "Q"
+    else:
+        off = struct.unpack(bo + "I", buf[4:8])[0]
+        n = struct.unpack(bo + "H", buf[off:off + 2])[0]
+        first, esize, inline, cfmt, ofmt = off + 2, 12, 4, "I", "I"
     tags = {}
     for i in range(n):
-        e = buf[off + 2 + 12 * i: off + 14 + 12 * i]
-        tag, typ, cnt = struct.unpack(bo + "HHI", e[:8])
+        e = buf[first + esize * i: first + esize * (i + 1)]
+        tag, typ, cnt = struct.unpack(bo + "HH" + cfmt, e[:esize - inline])
         fmt, size = _TYPES.get(typ, ("B", 1))
         total = size * cnt
-        if total <= 4:
-            raw = e[8:8 + total]
+        if total <= inline:
+            raw = e[esize - inline:esize - inline + total]
         else:
-            p = struct.unpack(bo + "I", e[8:12])[0]
+            p = struct.unpack(bo + ofmt, e[esize - inline:esize])[0]
             raw = buf[p:p + total]
         if typ == 2:
             val = raw.split(b"\x00")[0].decode("latin1")
@@ -115,10 +136,10 @@ def read_info(path) -> GeoInfo:
     with open(path, "rb") as f:
         buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)   # only the pages of the header / IFD are touched
     try:
-        bo = "<" if buf[:2] == b"II" else ">"
-        if struct.unpack(bo + "H", buf[2:4])[0] != 42:
-            raise ValueError("not a classic TIFF")
-        return _info_from_tags(_read_ifd(buf, bo))
+        kind = _tiff_kind(buf)
+        if kind is None:
+            raise ValueError("not a TIFF / BigTIFF file")
+        return _info_from_tags(_read_ifd(buf, kind[0]))
     finally:
         buf.close()
 
@@ -160,9 +181,10 @@ def device_decodable(path):
 
 
 def _device_plan(buf):
-    bo = "<" if buf[:2] == b"II" else ">"
-    if struct.unpack(bo + "H", buf[2:4])[0] != 42:
+    kind = _tiff_kind(buf)
+    if kind is None:
         return None
+    bo = kind[0]
     t = _read_ifd(buf, bo)
     info = _info_from_tags(t)
     comp, pred, planar = int(t.get(259, (1,))[0]), int(t.get(317, (1,))[0]), int(t.get(284, (1,))[0])
@@ -351,9 +373,10 @@ def read_device_plain(path, device, out=None, slot=0, piece=32 << 20, probe=Fals
     with open(path, "rb") as f:
         buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         try:
-            bo = "<" if buf[:2] == b"II" else ">"
-            if struct.unpack(bo + "H", buf[2:4])[0] != 42:
+            kind = _tiff_kind(buf)
+            if kind is None:
                 return None
+            bo = kind[0]
             t = _read_ifd(buf, bo)
             info = _info_from_tags(t)
         finally:
@@ -413,9 +436,10 @@ def read_device_plain(path, device, out=None, slot=0, piece=32 << 20, probe=Fals
 
 
 def _read_mapped(buf, window, out, fd=None):
-    bo = "<" if buf[:2] == b"II" else ">"
-    if struct.unpack(bo + "H", buf[2:4])[0] != 42:
-        raise ValueError("not a classic TIFF")
+    kind = _tiff_kind(buf)
+    if kind is None:
+        raise ValueError("not a TIFF / BigTIFF file")
+    bo = kind[0]
     t = _read_ifd(buf, bo)
     info = _info_from_tags(t)
     comp = int(t.get(259, (1,))[0])
@@ -544,11 +568,12 @@ def _lzw_encode(raw: bytes) -> bytes:
     return dst.raw[:n]
 
 
-def write(path, array, transform, epsg=None, nodata=None, compression=None, predictor=1):
+def write(path, array, transform, epsg=None, nodata=None, compression=None, predictor=1, bigtiff=None):
     """Little-endian, planar (band-sequential) strips -- one strip per band row block, so that a device tensor's
     (bands, H, W) layout is written without a transpose.  ``compression``: None (strips of 4 MiB) or ``"lzw"``
     (td_tiff_lzw_encode on a thread pool, strips of at most 128 KiB so that a raster has thousands of independent
-    streams; ``predictor`` 2 = horizontal differencing, 8-bit samples only)."""
+    streams; ``predictor`` 2 = horizontal differencing, 8-bit samples only).  ``bigtiff``: None = BigTIFF (64-bit
+    offsets) only when the file would pass 4 GB, True / False force the layout."""
     arr = np.ascontiguousarray(array)
     if arr.ndim == 2:
         arr = arr[None]
@@ -604,39 +629,49 @@ def write(path, array, transform, epsg=None, nodata=None, compression=None, pred
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
             strips = list(ex.map(pack, range(ns * C)))
         strip_bytes = [len(b) for b in strips]
-    add(273, 4, [0] * (ns * C)); add(279, 4, strip_bytes)
+    payload = sum(strip_bytes)
+    big = bool(bigtiff) if bigtiff is not None else payload + (1 << 20) + 16 * ns * C >= (1 << 32)
+    otyp = 16 if big else 4                    # LONG8 / LONG strip offsets and byte counts
+    add(273, otyp, [0] * (ns * C)); add(279, otyp, strip_bytes)
     entries.sort(key=lambda x: x[0])
-    ifd_off = 8
-    ifd_size = 2 + 12 * len(entries) + 4
+    # classic: 8-byte header, 2-byte entry count, 12-byte entries (4 bytes inline), 4-byte next-IFD offset;
+    # BigTIFF: 16-byte header, 8-byte count, 20-byte entries (8 bytes inline), 8-byte next-IFD offset
+    hdr, ncnt, esize, inline, ofmt = (16, 8, 20, 8, "<Q") if big else (8, 2, 12, 4, "<I")
+    ifd_off = hdr
+    ifd_size = ncnt + esize * len(entries) + inline
     extra_off = ifd_off + ifd_size
     # layout: header | IFD | out-of-line values | pixel data
     pos = extra_off
     placed = []
     for tag, typ, cnt, raw in entries:
-        if len(raw) <= 4:
-            placed.append((tag, typ, cnt, raw.ljust(4, b"\x00"), None))
+        if len(raw) <= inline:
+            placed.append((tag, typ, cnt, raw.ljust(inline, b"\x00"), None))
         else:
-            placed.append((tag, typ, cnt, struct.pack("<I", pos), raw))
+            placed.append((tag, typ, cnt, struct.pack(ofmt, pos), raw))
             pos += len(raw) + (len(raw) & 1)
     data_off = (pos + 15) & ~15
     offsets, o = [], data_off
     for sb in strip_bytes:
         offsets.append(o); o += sb
-    if o >= (1 << 32):
-        raise ValueError("raster too large for classic TIFF")
+    if o >= (1 << 32) and not big:
+        raise ValueError("raster too large for classic TIFF (bigtiff=False)")
     with open(path, "wb") as fh:
-        fh.write(b"II" + struct.pack("<HI", 42, ifd_off))
-        fh.write(struct.pack("<H", len(placed)))
+        if big:
+            fh.write(b"II" + struct.pack("<HHHQ", 43, 8, 0, ifd_off))
+            fh.write(struct.pack("<Q", len(placed)))
+        else:
+            fh.write(b"II" + struct.pack("<HI", 42, ifd_off))
+            fh.write(struct.pack("<H", len(placed)))
         blob = bytearray()
         for tag, typ, cnt, val, raw in placed:
             if tag == 273:
-                raw = struct.pack("<" + "I" * len(offsets), *offsets)
-                if len(raw) <= 4:
-                    val, raw = raw.ljust(4, b"\x00"), None
-            fh.write(struct.pack("<HHI", tag, typ, cnt) + val)
+                raw = struct.pack("<" + _TYPES[otyp][0] * len(offsets), *offsets)
+                if len(raw) <= inline:
+                    val, raw = raw.ljust(inline, b"\x00"), None
+            fh.write(struct.pack("<HHQ" if big else "<HHI", tag, typ, cnt) + val)
             if raw is not None:
                 blob += raw + (b"\x00" if len(raw) & 1 else b"")
-        fh.write(struct.pack("<I", 0))
+        fh.write(struct.pack(ofmt, 0))
         fh.write(bytes(blob))
         fh.write(b"\x00" * (data_off - extra_off - len(blob)))
         if strips is None:
