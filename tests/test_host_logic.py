@@ -252,3 +252,66 @@ def test_fixture_predictor_fails_loudly(tmp_path):
         np.savez(model / "img.npz", **{**good, **bad})
         with pytest.raises(ValueError):
             fp.raw_outputs("img", tiles)
+
+
+def test_gpkg_conforms_to_the_geopackage_core_requirements(tmp_path):
+    """No OGR / fiona exists offline to open the file, so the layer is checked against what the OGC GeoPackage
+    encoding standard (12-128r15, core + features) requires and OGR / QGIS rely on: SQLite header fields,
+    gpkg_spatial_ref_sys / gpkg_contents / gpkg_geometry_columns rows, an integer primary key, and the
+    GeoPackageBinary header + WKB of every geometry (written by both the Python and the native row writer)."""
+    import sqlite3
+    import struct
+    rng = np.random.default_rng(3)
+    rings = [np.concatenate([r, r[:1]]) for r in (412000 + rng.uniform(0, 100, (k, 2)) for k in (4, 9, 33, 5))]
+    verts = np.concatenate(rings)
+    off = np.zeros(len(rings) + 1, dtype=np.int64); off[1:] = np.cumsum([len(r) for r in rings])
+    n = len(rings)
+    cols = {"Confidence_score": rng.uniform(0, 1, n), "poly_id": [str(k) for k in range(n)], "Area": rng.uniform(1, 50, n),
+            "TreeHeight": rng.uniform(3, 30, n), "Centroid": [f"POINT ({k} {k})" for k in range(n)],
+            "Diameter": rng.uniform(1, 9, n), "is_contained": ["False"] * n, "num_contained": np.arange(n)}
+    for native in (False, True):
+        path = str(tmp_path / f"layer_{native}.gpkg")
+        gpkg.write_layer(path, "processed_x", verts, off, cols, gpkg.PROCESSED_SCHEMA, epsg=25832, native=native)
+        raw = open(path, "rb").read(100)
+        assert raw[:16] == b"SQLite format 3\x00"                               # R1
+        assert struct.unpack(">I", raw[68:72])[0] == 0x47504B47                   # R2: application_id 'GPKG'
+        assert struct.unpack(">I", raw[60:64])[0] >= 10200                        # user_version
+        con = sqlite3.connect(path)
+        try:
+            assert con.execute("PRAGMA integrity_check").fetchone()[0] == "ok"   # R6
+            assert con.execute("PRAGMA foreign_key_check").fetchall() == []      # R7
+            srs = {r[0]: r for r in con.execute("SELECT srs_id, organization, organization_coordsys_id, definition "
+                                                "FROM gpkg_spatial_ref_sys")}
+            assert {-1, 0, 4326, 25832} <= set(srs)                               # R11 + the layer's own
+            assert srs[25832][1].upper() == "EPSG" and srs[25832][2] == 25832 and "UTM zone 32N" in srs[25832][3]
+            tname, dtype, ident, minx, miny, maxx, maxy, sid = con.execute(
+                "SELECT table_name, data_type, identifier, min_x, min_y, max_x, max_y, srs_id FROM gpkg_contents").fetchone()
+            assert (tname, dtype, sid) == ("processed_x", "features", 25832)      # R13 / R18
+            assert minx <= verts[:, 0].min() and maxx >= verts[:, 0].max() and miny <= verts[:, 1].min() \
+                and maxy >= verts[:, 1].max()
+            gt, gc, gtype, gsrs, z, m = con.execute(
+                "SELECT table_name, column_name, geometry_type_name, srs_id, z, m FROM gpkg_geometry_columns").fetchone()
+            assert (gt, gtype, gsrs, z, m) == ("processed_x", "POLYGON", 25832, 0, 0)     # R22 - R28
+            info = con.execute(f"PRAGMA table_info({tname})").fetchall()
+            pk = [c for c in info if c[5] == 1]
+            assert len(pk) == 1 and pk[0][2].upper() == "INTEGER"                 # R29: integer primary key
+            names = [c[1] for c in info]
+            assert gc in names and all(k in names for k in cols)
+            blobs = [r[0] for r in con.execute(f"SELECT {gc} FROM {tname} ORDER BY {pk[0][1]}")]
+        finally:
+            con.close()
+        assert len(blobs) == n
+        for k, b in enumerate(blobs):                                              # R19: GeoPackageBinary
+            assert b[:2] == b"GP" and b[2] == 0
+            flags = b[3]
+            assert flags & 1 == 1 and (flags >> 5) & 1 == 0 and (flags >> 4) & 1 == 0      # little endian, standard, non-empty
+            assert (flags >> 1) & 7 == 1                                          # envelope: minx, maxx, miny, maxy
+            assert struct.unpack("<i", b[4:8])[0] == 25832
+            env = struct.unpack("<4d", b[8:40])
+            ring = rings[k]
+            assert env == (ring[:, 0].min(), ring[:, 0].max(), ring[:, 1].min(), ring[:, 1].max())
+            order, wtype, nrings, npts = struct.unpack("<BIII", b[40:53])
+            assert (order, wtype, nrings, npts) == (1, 3, 1, len(ring))           # WKB Polygon, one closed ring
+            xy = np.frombuffer(b, dtype="<f8", offset=53).reshape(-1, 2)
+            np.testing.assert_array_equal(xy, ring)
+            assert (xy[0] == xy[-1]).all() and len(b) == 53 + 16 * len(ring)
