@@ -261,3 +261,38 @@ def test_non_zero_device_index(tmp_path):
         np.testing.assert_array_equal(a[name][0], b[name][0], err_msg=name)
         np.testing.assert_array_equal(a[name][1], b[name][1], err_msg=name)
         assert a[name][2] == b[name][2], name
+
+
+def test_stitching_from_prediction_json_files(tmp_path):
+    """detection.process_and_stitch_predictions (helpers.py:556-600): predictions that exist as per-tile
+    ``Prediction_*.json`` files -- the reference's wire format, written here by ``keep_intermediate`` -- give the same
+    stitched layers as the device path that produced them; a second call is answered from the stitching ledger"""
+    cfg_path, field, model = _project(tmp_path)
+    config, _ = detection.get_config(cfg_path)
+    images = detection.preprocess_files(config)
+    for p in images:
+        stem = os.path.splitext(os.path.basename(p))[0]
+        tiles = json.load(open(os.path.join(config["tiles_path"], stem + ".json")))
+        predictor.dump_fixtures(str(model), stem, synth.make_detections(field, tiles, PX, seed=5))
+    detection.predict_tiles(config)
+    out = config["output_directory"]
+    again = str(tmp_path / "stitched_again")
+    got = detection.process_and_stitch_predictions(config["tiles_path"], os.path.join(out, "predictions"), again,
+                                                   shift=1, simplify_tolerance=config["simplify_tolerance"])
+    assert got == again
+    n_rows = 0
+    for p in images:
+        stem = os.path.splitext(os.path.basename(p))[0]
+        v0, o0, c0, e0 = gpkg.read_layer(os.path.join(out, "geojson_predictions", stem + ".gpkg"))
+        v1, o1, c1, e1 = gpkg.read_layer(os.path.join(again, stem + ".gpkg"))
+        assert e0 == e1 == 25832
+        np.testing.assert_array_equal(o1, o0)
+        np.testing.assert_array_equal(v1, v0)
+        np.testing.assert_array_equal(np.array(c1["Confidence_score"]), np.array(c0["Confidence_score"]))
+        n_rows += len(o1) - 1
+    assert n_rows > 50
+    ledger = yaml.safe_load(open(os.path.join(again, "stitching_recovery.yaml")))
+    assert len(ledger["completed_files"]) == len(images)
+    stamp = {f: os.path.getmtime(os.path.join(again, f)) for f in os.listdir(again) if f.endswith(".gpkg")}
+    detection.process_and_stitch_predictions(config["tiles_path"], os.path.join(out, "predictions"), again)
+    assert stamp == {f: os.path.getmtime(os.path.join(again, f)) for f in stamp}

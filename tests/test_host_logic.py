@@ -315,3 +315,43 @@ def test_gpkg_conforms_to_the_geopackage_core_requirements(tmp_path):
             xy = np.frombuffer(b, dtype="<f8", offset=53).reshape(-1, 2)
             np.testing.assert_array_equal(xy, ring)
             assert (xy[0] == xy[-1]).all() and len(b) == 53 + 16 * len(ring)
+
+
+def test_prediction_json_files_become_one_ragged_ring_set(tmp_path):
+    """detection._rings_from_prediction_files: the reference's per-tile ``Prediction_*.json`` wire format
+    (prediction.py:253-263) in tiles-JSON order; open rings are closed as shapely's Polygon() does, a tile with a
+    degenerate ring or an RLE entry is dropped as a whole (helpers.py:419-476), missing tiles are skipped"""
+    import logging
+
+    from treedetection_b200 import detection
+    tiles = {f"img_4120{k}0_5318000_50_20_25832": {"crs": 25832} for k in range(5)}
+    ids = list(tiles)
+    sq = lambda x: [[x, 0.0], [x + 1.0, 0.0], [x + 1.0, 1.0], [x, 1.0]]
+    files = {
+        ids[0]: [{"image_id": "a", "category_id": 0, "score": 0.9, "polygon_coords": [sq(0.0) + [[0.0, 0.0]]]},
+                 {"image_id": "a", "category_id": 0, "score": 0.8, "polygon_coords": [sq(5.0)]}],            # open ring
+        ids[1]: [{"image_id": "a", "category_id": 0, "score": 0.7, "polygon_coords": [[[0.0, 0.0], [1.0, 1.0]]]}],  # degenerate
+        ids[2]: [],
+        ids[3]: [{"image_id": "a", "category_id": 0, "score": 0.6, "segmentation": {"counts": "x", "size": [1, 1]}}],
+        # ids[4]: no file
+    }
+    d = tmp_path / "img"
+    d.mkdir()
+    for tid, ev in files.items():
+        (d / f"Prediction_{tid}.json").write_text(json.dumps(ev))
+    (d / f"Prediction_{ids[4]}_extra.json").write_text("[]")
+    records = []
+    logger = logging.getLogger("stitch-test")
+    logger.addHandler(type("H", (logging.Handler,), {"emit": lambda self, r: records.append(r.getMessage())})())
+    v, off, ring_tile, conf = detection._rings_from_prediction_files(str(d), tiles, logger)
+    np.testing.assert_array_equal(off, [0, 5, 10])
+    np.testing.assert_array_equal(ring_tile, [0, 0])
+    np.testing.assert_array_equal(conf, [0.9, 0.8])
+    np.testing.assert_array_equal(v[:5], np.array(sq(0.0) + [[0.0, 0.0]]))
+    np.testing.assert_array_equal(v[5:], np.array(sq(5.0) + [[5.0, 0.0]]))
+    assert v.dtype == np.float64 and ring_tile.dtype == np.int32
+    assert len(records) == 2 and ids[1] in records[0] and ids[3] in records[1]
+    v, off, ring_tile, conf = detection._rings_from_prediction_files(str(tmp_path / "nothing"), tiles)
+    assert v.shape == (0, 2) and list(off) == [0] and len(conf) == 0
+    with pytest.raises(FileNotFoundError):
+        detection.process_and_stitch_predictions(str(tmp_path / "no_tiles"), str(d), str(tmp_path / "out"))

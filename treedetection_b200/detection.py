@@ -602,6 +602,94 @@ def _save_stitching_ledger(stitched_path, files, logger=None):
             logger.warning(f"Failed to save stitching recovery: {e}")
 
 
+def _rings_from_prediction_files(pred_dir, tiles, logger=None):
+    """The ``Prediction_<tile id>.json`` files of one image (prediction.py:253-263: ``[{image_id, category_id,
+    score, polygon_coords: [ring]}]`` per tile) as one ragged ring set in the order of the tiles JSON: vertices
+    (V, 2) f64, ring offsets, the tile of every ring, its confidence.  What shapely's ``Polygon(coords)`` does to
+    a ring is reproduced: an open ring is closed; a tile with a ring of fewer than three points fails as a whole
+    (helpers.py:419-476 logs the error and drops the file)."""
+    verts, lens, ring_tile, conf = [], [], [], []
+    for t, tid in enumerate(tiles.keys()):
+        path = os.path.join(pred_dir, f"Prediction_{os.path.basename(tid)}.json")
+        if not os.path.exists(path):
+            continue
+        try:
+            with open(path) as f:
+                data = json.load(f)
+            tile_rings, tile_conf = [], []
+            for crown in data:
+                if "polygon_coords" not in crown:
+                    raise ValueError("RLE-encoded predictions (pycocotools) are not supported")
+                xy = np.asarray(crown["polygon_coords"], dtype=np.float64).reshape(-1, 2)
+                if len(xy) and (xy[0] != xy[-1]).any():
+                    xy = np.concatenate([xy, xy[:1]])
+                if len(xy) < 4:
+                    raise ValueError("A LinearRing must have at least 3 coordinate tuples")
+                tile_rings.append(xy)
+                tile_conf.append(float(crown["score"]))
+        except Exception as e:
+            if logger:
+                logger.warning(f"Error processing file {path}: {e}")
+            continue
+        verts += tile_rings
+        lens += [len(r) for r in tile_rings]
+        ring_tile += [t] * len(tile_rings)
+        conf += tile_conf
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    v = np.concatenate(verts) if verts else np.zeros((0, 2), dtype=np.float64)
+    return v, off, np.asarray(ring_tile, dtype=np.int32), np.asarray(conf, dtype=np.float64)
+
+
+def process_and_stitch_predictions(tiles_path, pred_fold, output_path, max_workers=50, shift=1, simplify_tolerance=0.2,
+                                   logger=None, device="0"):
+    """helpers.process_and_stitch_predictions (helpers.py:556-600) for predictions that already exist as
+    ``<pred_fold>/<image>/Prediction_<tile id>.json`` -- e.g. written by the reference's own detectron2 run, or by
+    this package with ``keep_intermediate``: every ring is simplified (``simplify_tolerance``, GEOS semantics) and
+    kept when it lies within its tile's box shrunk by ``shift`` (P4 on the device, ``td_simplify_rings``), the
+    survivors of an image go to ``<output_path>/<image>.gpkg`` (``Confidence_score`` + geometry).  Rows are in the
+    order of the tiles JSON (the reference concatenates in directory-listing order).  Images listed in
+    ``stitching_recovery.yaml`` are skipped and the ledger is updated, as in the reference."""
+    for pth, what in ((tiles_path, "tiles path"), (pred_fold, "prediction folder")):
+        if not os.path.isdir(pth):
+            raise FileNotFoundError(f"The {what} '{pth}' does not exist.")
+    os.makedirs(output_path, exist_ok=True)
+    done = _load_stitching_ledger(output_path, logger)
+    folders = sorted(f for f in os.listdir(tiles_path) if f.endswith(".json") and os.path.isfile(os.path.join(tiles_path, f)))
+    todo = [f for f in folders if os.path.splitext(f)[0] not in done]
+    if logger and len(todo) < len(folders):
+        logger.info(f"Skipping stiching {len(folders) - len(todo)} of {len(folders)} folders that have already been processed.")
+    dev = _device({"device": device})
+    results = []
+    with torch.cuda.device(dev):
+        for k, folder in enumerate(todo):
+            stem = os.path.splitext(folder)[0]
+            try:
+                with open(os.path.join(tiles_path, folder)) as f:
+                    tiles = json.load(f)
+                v, off, ring_tile, conf = _rings_from_prediction_files(os.path.join(pred_fold, stem), tiles, logger)
+                epsg = next(iter(tiles.values()))["crs"] if tiles else 4326
+                if len(off) > 1:
+                    _, boxes_int = pipeline.tile_tables(tiles, dev)
+                    d_v, d_off = torch.from_numpy(v).to(dev), torch.from_numpy(off).to(dev)
+                    simp = ops.simplify_rings(d_v, d_off, float(simplify_tolerance), pipeline.filter_boxes(boxes_int, shift, dev),
+                                              torch.from_numpy(ring_tile).to(dev), want_bounds=False)
+                    sel = torch.nonzero(simp["keep"]).flatten()
+                    kv, koff = ops.take_rings(d_v, d_off, sel, simp["scratch"], simp["count"])
+                    v, off, conf = kv.cpu().numpy(), koff.cpu().numpy(), conf[sel.cpu().numpy()]
+                digits = re.search(r"(\d+)$", str(epsg))
+                gpkg.write_layer(os.path.join(output_path, stem + ".gpkg"), stem, v, off, {"Confidence_score": conf},
+                                 gpkg.STITCHED_SCHEMA, epsg=int(digits.group(1)) if digits else 4326)
+                results.append(stem)
+            except Exception as e:
+                if logger:
+                    logger.error(f"Error processing folder {folder}: {e}")
+            if logger and todo and (k == 0 or (100 * (k + 1) // len(todo)) // 5 != (100 * k // len(todo)) // 5):
+                logger.info(f"Stitching file {k + 1}/{len(todo)} ({100 * (k + 1) // len(todo)}%)")
+    _save_stitching_ledger(output_path, sorted(done | set(results)), logger)
+    return output_path
+
+
 def predict_on_model(config, model_path, tiles_path, output_path, batch_size=10, exclude_vars=None,
                      stitched_path=None):
     """detection.py:62-132 + helpers.process_and_stitch_predictions (helpers.py:556-600) in one
