@@ -355,3 +355,62 @@ def test_prediction_json_files_become_one_ragged_ring_set(tmp_path):
     assert v.shape == (0, 2) and list(off) == [0] and len(conf) == 0
     with pytest.raises(FileNotFoundError):
         detection.process_and_stitch_predictions(str(tmp_path / "no_tiles"), str(d), str(tmp_path / "out"))
+
+
+def test_gpkg_reader_accepts_the_geometry_encodings_ogr_writes(tmp_path):
+    """``geojson_predictions/*.gpkg`` may come from the reference (geopandas / fiona / OGR): feature table with
+    ``fid`` + ``geom``, GeoPackageBinary blobs with any envelope type and byte order, Polygon / PolygonZ / PolygonZM,
+    polygons with holes (the exterior ring is the crown), MultiPolygon (first polygon, postprocessing.py:493-494),
+    NULL and empty geometries"""
+    import sqlite3
+    import struct
+    sq = np.array([[412000.0, 5318000.0], [412004.0, 5318000.0], [412004.0, 5318003.0], [412000.0, 5318003.0],
+                   [412000.0, 5318000.0]])
+    hole = sq[::-1] * 1.0
+    hole[:, 0] = 412001.0 + (hole[:, 0] - 412000.0) * 0.25
+    hole[:, 1] = 5318001.0 + (hole[:, 1] - 5318000.0) * 0.25
+
+    def wkb_poly(rings, bo="<", z=0):
+        code = 3 + 1000 * z
+        out = struct.pack(bo + "BII", 1 if bo == "<" else 0, code, len(rings))
+        for r in rings:
+            out += struct.pack(bo + "I", len(r))
+            for x, y in r:
+                out += struct.pack(bo + "dd" + "d" * {0: 0, 1: 1, 3: 2}[z], x, y, *([7.0] * {0: 0, 1: 1, 3: 2}[z]))
+        return out
+
+    def gpb(wkb, env=1, bo="<", srs=25832, empty=False):
+        flags = (1 if bo == "<" else 0) | (env << 1) | (0x10 if empty else 0)
+        nenv = {0: 0, 1: 4, 2: 6, 3: 6, 4: 8}[env]
+        return b"GP\x00" + bytes([flags]) + struct.pack(bo + "i", srs) + struct.pack(bo + "d" * nenv, *([0.0] * nenv)) + wkb
+
+    multi = struct.pack("<BII", 1, 6, 2) + wkb_poly([sq + 10.0]) + wkb_poly([sq + 50.0])
+    blobs = [
+        ("ogr default", gpb(wkb_poly([sq])), sq),
+        ("no envelope", gpb(wkb_poly([sq + 1.0]), env=0), sq + 1.0),
+        ("xyz envelope, PolygonZ", gpb(wkb_poly([sq + 2.0], z=1), env=2), sq + 2.0),
+        ("xyzm envelope, PolygonZM", gpb(wkb_poly([sq + 3.0], z=3), env=4), sq + 3.0),
+        ("big endian", gpb(wkb_poly([sq + 4.0], bo=">"), bo=">"), sq + 4.0),
+        ("hole", gpb(wkb_poly([sq, hole])), sq),
+        ("multipolygon", gpb(multi), sq + 10.0),
+        ("empty", gpb(struct.pack("<BII", 1, 3, 0), env=0, empty=True), np.zeros((0, 2))),
+        ("null", None, np.zeros((0, 2))),
+    ]
+    path = str(tmp_path / "ogr.gpkg")
+    gpkg.write_layer(path, "crowns", np.zeros((0, 2)), np.zeros(1, dtype=np.int64), {"Confidence_score": np.zeros(0)},
+                     gpkg.STITCHED_SCHEMA, epsg=25832, native=False)           # metadata tables of a valid file
+    con = sqlite3.connect(path)
+    con.execute('DROP TABLE "crowns"')
+    con.execute('CREATE TABLE "crowns" (fid INTEGER PRIMARY KEY AUTOINCREMENT NOT NULL, geom POLYGON, '
+                '"Confidence_score" REAL, note TEXT)')
+    con.execute("UPDATE gpkg_geometry_columns SET column_name = 'geom'")
+    for k, (name, blob, _) in enumerate(blobs):
+        con.execute('INSERT INTO "crowns" (geom, "Confidence_score", note) VALUES (?, ?, ?)', (blob, 0.1 * k, name))
+    con.commit()
+    con.close()
+    verts, off, cols, epsg = gpkg.read_layer(path)
+    assert epsg == 25832 and cols["note"] == [b[0] for b in blobs]
+    np.testing.assert_allclose(cols["Confidence_score"], [0.1 * k for k in range(len(blobs))])
+    assert len(off) == len(blobs) + 1
+    for k, (name, _, want) in enumerate(blobs):
+        np.testing.assert_array_equal(verts[off[k]:off[k + 1]], want, err_msg=name)

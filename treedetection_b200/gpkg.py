@@ -55,7 +55,7 @@ def _parse_gpb(blob: bytes) -> np.ndarray:
     if gtype % 1000 != 3 or nrings == 0:
         return np.zeros((0, 2))
     npts = struct.unpack(bo + "I", wkb[9:13])[0]
-    dims = 2 + (1 if gtype >= 1000 else 0)
+    dims = 2 + {0: 0, 1: 1, 2: 1, 3: 2}.get(gtype // 1000, 0)      # ISO WKB: +1000 Z, +2000 M, +3000 ZM
     pts = np.frombuffer(wkb, dtype=bo + "f8", count=npts * dims, offset=13).reshape(npts, dims)
     return np.array(pts[:, :2], dtype=np.float64)
 
